@@ -1,0 +1,413 @@
+// grid.cu -- uniform-grid neighbour build for sm_100a:
+//   (1) cell hash + warp-aggregated atomic count   <- ComputeCounts   (uniform_grid_sph_cs.glsl:112-125,
+//                                                                      ugrid_particles_cs.glsl:90-95)
+//   (2) single-pass decoupled-look-back scan       <- ParallelScan::Compute (ParallelScan.cpp:43-95,
+//                                                                      prefix_sum_cs.glsl:18-43)
+//   (3) insert + canonical per-cell ordering       <- InsertPoint / InsertParticle
+//                                                     (uniform_grid_sph_cs.glsl:154-165, ugrid_particles_cs.glsl:110-117)
+// The reference clears the counter twice with glCopyNamedBufferSubData and runs 2*log2(C)
+// dispatches for the scan; here one memset + three kernels (+ a tiny per-cell ordering pass that
+// makes the index list deterministic: ascending particle id inside a cell).
+#include "internal.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// (1) hash + count
+// ---------------------------------------------------------------------------------------------
+// One thread per particle.  Lanes of a warp that fall in the same cell are grouped with
+// __match_any_sync; the group leader issues ONE atomicAdd for the whole group and every lane
+// derives its arrival rank from the returned base, so the later insert needs no second atomic
+// pass (the reference runs the atomics twice: count, clear, insert).
+template <int DIM>
+__global__ void __launch_bounds__(256)
+grid_hash_count_kernel(const char* __restrict__ particles, int stride_bytes, int n, GridView g,
+                       int* __restrict__ counter, int* __restrict__ cell_of, int* __restrict__ rank)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int cell = -1;
+    if (i < n) {
+        const float4 p = __ldg(reinterpret_cast<const float4*>(particles + (size_t)i * stride_bytes));
+        if (DIM == 2) {
+            // point_in_aabb: strict on both axes (uniform_grid_sph_cs.glsl:19-23,115)
+            const bool inside = (p.x > g.min[0]) && (p.y > g.min[1]) && (p.x < g.max[0]) && (p.y < g.max[1]);
+            if (inside) {
+                int ci, cj;
+                cwa_cell2(g, p.x, p.y, ci, cj);
+                cell = ci * g.n[1] + cj;                       // Index(i,j) :149-152
+            }
+        } else {
+            int ci, cj, ck;
+            cwa_cell3(g, p.x, p.y, p.z, ci, cj, ck);
+            cell = (ci * g.n[1] + cj) * g.n[0] + ck;           // Index(i,j,k) ugrid_particles_cs.glsl:105-108 (sic)
+        }
+        cell_of[i] = cell;
+    }
+    // warp aggregation (all 32 lanes participate; lanes without a cell use key -1 and skip)
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned peers = __match_any_sync(0xffffffffu, cell);
+    const int leader = __ffs(peers) - 1;
+    const int my_rank = __popc(peers & ((1u << lane) - 1u));
+    int base = 0;
+    if (cell >= 0 && (int)lane == leader) base = atomicAdd(&counter[cell], __popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (i < n && cell >= 0) rank[i] = base + my_rank;
+}
+
+// ---------------------------------------------------------------------------------------------
+// (2) decoupled look-back exclusive scan (single pass, any n)
+// ---------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;   // 4096 ints per tile
+
+size_t scan_num_tiles(int n) { return (size_t)((n + SCAN_TILE - 1) / SCAN_TILE); }
+
+// tile_state word: [63:62] flag (0 invalid, 1 aggregate, 2 inclusive prefix) | [31:0] value
+__device__ __forceinline__ unsigned long long scan_pack(unsigned flag, int v)
+{
+    return ((unsigned long long)flag << 62) | (unsigned long long)(unsigned)v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_lookback_kernel(const int* __restrict__ in, int* __restrict__ out, int n, int write_total,
+                     int* __restrict__ ticket, volatile unsigned long long* __restrict__ tile_state)
+{
+    __shared__ int s_tile;
+    __shared__ int s_warp[SCAN_THREADS / 32];
+    __shared__ int s_prefix;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1);        // tiles are handed out in start order
+    __syncthreads();
+    const int tile = s_tile;
+    const long long base = (long long)tile * SCAN_TILE + (long long)tid * SCAN_ITEMS;
+
+    int v[SCAN_ITEMS];
+    if (base + SCAN_ITEMS <= n) {
+        const int4* p = reinterpret_cast<const int4*>(in + base);
+#pragma unroll
+        for (int q = 0; q < SCAN_ITEMS / 4; q++) {
+            int4 t = __ldg(p + q);
+            v[4 * q + 0] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < SCAN_ITEMS; q++) v[q] = (base + q < n) ? __ldg(in + base + q) : 0;
+    }
+    int tsum = 0;
+#pragma unroll
+    for (int q = 0; q < SCAN_ITEMS; q++) tsum += v[q];
+
+    // block-wide exclusive scan of the thread sums
+    int incl = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int w = (lane < SCAN_THREADS / 32) ? s_warp[lane] : 0;
+        int wi = w;
+#pragma unroll
+        for (int d = 1; d < SCAN_THREADS / 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += t;
+        }
+        if (lane < SCAN_THREADS / 32) s_warp[lane] = wi - w;          // exclusive warp offsets
+        const int aggregate = __shfl_sync(0xffffffffu, wi, SCAN_THREADS / 32 - 1);
+
+        // publish, then look back over the predecessors 32 tiles at a time
+        int exclusive = 0;
+        if (tile == 0) {
+            if (lane == 0) tile_state[0] = scan_pack(2u, aggregate);
+        } else {
+            if (lane == 0) tile_state[tile] = scan_pack(1u, aggregate);
+            int look = tile - 1;
+            while (true) {
+                const int idx = look - lane;
+                unsigned long long st = scan_pack(2u, 0);              // tiles before 0: prefix 0
+                if (idx >= 0) {
+                    do { st = tile_state[idx]; } while ((st >> 62) == 0ull);
+                }
+                const unsigned flag = (unsigned)(st >> 62);
+                const int val = (int)(unsigned)(st & 0xffffffffull);
+                const unsigned has_prefix = __ballot_sync(0xffffffffu, flag == 2u);
+                // sum the values from lane 0 up to and including the first lane holding a prefix
+                const int first = has_prefix ? (__ffs(has_prefix) - 1) : 31;
+                int contrib = (lane <= first) ? val : 0;
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+                exclusive += contrib;
+                if (has_prefix) break;
+                look -= 32;
+            }
+            if (lane == 0) tile_state[tile] = scan_pack(2u, exclusive + aggregate);
+        }
+        if (lane == 0) s_prefix = exclusive;
+    }
+    __syncthreads();
+
+    int run = s_prefix + s_warp[wid] + (incl - tsum);
+    if (base + SCAN_ITEMS <= n) {
+        int4* o = reinterpret_cast<int4*>(out + base);
+#pragma unroll
+        for (int q = 0; q < SCAN_ITEMS / 4; q++) {
+            int4 t;
+            t.x = run; run += v[4 * q + 0];
+            t.y = run; run += v[4 * q + 1];
+            t.z = run; run += v[4 * q + 2];
+            t.w = run; run += v[4 * q + 3];
+            o[q] = t;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < SCAN_ITEMS; q++) {
+            if (base + q < n) out[base + q] = run;
+            run += v[q];
+        }
+    }
+    // the thread that owns element n-1 also writes the grand total to out[n]
+    if (write_total && base <= (long long)n - 1 && (long long)n - 1 < base + SCAN_ITEMS) out[n] = run;
+}
+
+int scan_exclusive_launch(cwa_ctx* ctx, const int* in, int* out, int n, int* ticket, unsigned long long* tile_state)
+{
+    // n < 0 encodes "do not write the total at out[|n|]"
+    const int write_total = n > 0;
+    if (n < 0) n = -n;
+    const int tiles = (int)scan_num_tiles(n);
+    scan_lookback_kernel<<<tiles, SCAN_THREADS, 0, ctx->stream>>>(in, out, n, write_total, ticket, tile_state);
+    ctx->launches++;
+    CWA_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// One level of the reference's multi-dispatch Blelloch scan (prefix_sum_cs.glsl:18-43), kept so a
+// host that still drives ParallelScan::Compute level by level through ComputeShader::Dispatch gets
+// identical results.  The fused path never uses it.
+__global__ void prefix_sum_level_kernel(int* x, int n, int phase, int stride, int nthreads)
+{
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= nthreads) return;
+    const long long ka = (long long)(stride / 2 - 1) + (long long)gid * stride;
+    const long long kb = ka + stride / 2;
+    if (kb >= n) return;
+    if (phase == 0) {
+        x[kb] = x[ka] + x[kb];
+    } else {
+        if (stride == n) x[n - 1] = 0;
+        int t = x[ka];
+        x[ka] = x[kb];
+        x[kb] = t + x[kb];
+    }
+}
+
+int prefix_sum_level_launch(cwa_ctx* ctx, int* x, int n, int phase, int stride, int nthreads)
+{
+    CWA_CHECK(n >= 2 && stride >= 2 && nthreads >= 1, "prefix_sum_cs: bad uniforms n=%d stride=%d", n, stride);
+    prefix_sum_level_kernel<<<ceil_div(nthreads, 256), 256, 0, ctx->stream>>>(x, n, phase, stride, nthreads);
+    ctx->launches++;
+    CWA_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// (3) insert + canonical ordering
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+grid_insert_kernel(const int* __restrict__ cell_of, const int* __restrict__ rank, const int* __restrict__ offset,
+                   int n, int* __restrict__ index_list)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = __ldg(cell_of + i);
+    if (c < 0) return;
+    index_list[__ldg(offset + c) + __ldg(rank + i)] = i;          // mIndexList[offset+count] = gid
+}
+
+// Arrival order inside a cell depends on warp scheduling; sort each cell's short list so the index
+// list is the canonical one (ascending particle id == stable counting sort == CPU twin).
+__global__ void __launch_bounds__(256)
+grid_cell_order_kernel(const int* __restrict__ offset, int num_cells, int* __restrict__ index_list)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= num_cells) return;
+    const int b = __ldg(offset + c), e = __ldg(offset + c + 1);
+    const int m = e - b;
+    if (m < 2) return;
+    int* a = index_list + b;
+    if (m <= 16) {
+        int v[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) v[q] = (q < m) ? a[q] : 0x7fffffff;
+        // odd-even transposition network on registers (16 phases, branch-free)
+#pragma unroll
+        for (int ph = 0; ph < 16; ph++) {
+#pragma unroll
+            for (int q = (ph & 1); q + 1 < 16; q += 2) {
+                int lo = min(v[q], v[q + 1]), hi = max(v[q], v[q + 1]);
+                v[q] = lo; v[q + 1] = hi;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 16; q++) if (q < m) a[q] = v[q];
+    } else {
+        for (int x = 1; x < m; x++) {                             // insertion sort for crowded cells
+            int key = a[x], y = x - 1;
+            while (y >= 0 && a[y] > key) { a[y + 1] = a[y]; y--; }
+            a[y + 1] = key;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+int grid_build_internal(cwa_ctx* ctx, GridObj* g, const void* particles, int stride_bytes, int n)
+{
+    CWA_CHECK(n >= 0 && n <= g->max_particles, "grid build: %d particles exceed the grid's capacity %d", n, g->max_particles);
+    CWA_CHECK(stride_bytes >= 16 && stride_bytes % 16 == 0, "grid build: particle stride must be a multiple of 16 bytes");
+    g->n_built = n;
+    CWA_CUDA(cudaMemsetAsync(g->counter, 0, g->clear_bytes, ctx->stream));      // ClearCounter + scan state, one memset
+    const int C = g->view.num_cells;
+    if (n > 0) {
+        if (g->dim == 2)
+            grid_hash_count_kernel<2><<<ceil_div(n, 256), 256, 0, ctx->stream>>>((const char*)particles, stride_bytes, n, g->view, g->counter, g->cell_of, g->rank);
+        else
+            grid_hash_count_kernel<3><<<ceil_div(n, 256), 256, 0, ctx->stream>>>((const char*)particles, stride_bytes, n, g->view, g->counter, g->cell_of, g->rank);
+        ctx->launches++;
+        CWA_CUDA(cudaGetLastError());
+    }
+    CWA_TRY(scan_exclusive_launch(ctx, g->counter, g->offset, C, g->ticket, g->tile_state));
+    if (n > 0) {
+        grid_insert_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(g->cell_of, g->rank, g->offset, n, g->index_list);
+        ctx->launches++;
+        CWA_CUDA(cudaGetLastError());
+        grid_cell_order_kernel<<<ceil_div(C, 256), 256, 0, ctx->stream>>>(g->offset, C, g->index_list);
+        ctx->launches++;
+        CWA_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+extern "C" int cwa_grid_create(cwa_ctx* ctx, int dim, const float* mn, const float* mx, const int* num_cells,
+                               int max_particles, cwa_grid* out)
+{
+    CWA_CHECK(ctx && mn && mx && num_cells && out, "null argument");
+    CWA_CHECK(dim == 2 || dim == 3, "cwa_grid_create: dim must be 2 or 3");
+    CWA_CHECK(max_particles > 0, "cwa_grid_create: max_particles must be positive");
+    *out = -1;
+    GridObj g;
+    g.live = true; g.dim = dim; g.max_particles = max_particles;
+    long long C = 1;
+    for (int a = 0; a < 4; a++) { g.info.min[a] = g.info.max[a] = 0.0f; g.info.num_cells[a] = 1; g.info.cell_size[a] = 0.0f; }
+    for (int a = 0; a < dim; a++) {
+        CWA_CHECK(num_cells[a] >= 1 && mx[a] > mn[a], "cwa_grid_create: bad extent/cell count on axis %d", a);
+        g.info.min[a] = mn[a]; g.info.max[a] = mx[a]; g.info.num_cells[a] = num_cells[a];
+        // mCellSize = (mMax - mMin) / vec(mNumCells), FP32 on the host (UniformGridGpu2D.cpp:160)
+        g.info.cell_size[a] = (mx[a] - mn[a]) / (float)num_cells[a];
+    }
+    if (dim == 3) {
+        // The reference's 3-D index (i*Ny + j)*Nx + k aliases cells when Nz > Nx; refuse loudly.
+        CWA_CHECK(num_cells[2] <= num_cells[0],
+                  "cwa_grid_create: Nz (%d) > Nx (%d) aliases cells under the reference index formula (i*Ny+j)*Nx+k",
+                  num_cells[2], num_cells[0]);
+        C = (long long)num_cells[0] * num_cells[1] * num_cells[0];   // covers every index the formula can produce
+    } else {
+        C = (long long)num_cells[0] * num_cells[1];
+    }
+    CWA_CHECK(C < (1ll << 30), "cwa_grid_create: too many cells (%lld)", C);
+    for (int a = 0; a < 3; a++) {
+        g.view.min[a] = g.info.min[a]; g.view.max[a] = g.info.max[a];
+        g.view.cell[a] = (a < dim) ? g.info.cell_size[a] : 1.0f;
+        g.view.n[a] = (a < dim) ? g.info.num_cells[a] : 1;
+    }
+    g.view.dim = dim; g.view.num_cells = (int)C;
+
+    const size_t tiles = scan_num_tiles((int)C);
+    // [counter C ints (padded to 8 B)][ticket 2 ints][tile_state tiles x 8 B]
+    const size_t counter_bytes = (((size_t)C * 4 + 15) / 16) * 16;
+    g.clear_bytes = counter_bytes + 16 + tiles * 8;
+    char* blk = nullptr;
+    CWA_CUDA(cudaMalloc(&blk, g.clear_bytes));
+    g.counter = (int*)blk;
+    g.ticket = (int*)(blk + counter_bytes);
+    g.tile_state = (unsigned long long*)(blk + counter_bytes + 16);
+    CWA_CUDA(cudaMalloc(&g.offset, ((size_t)C + 1) * 4));
+    CWA_CUDA(cudaMalloc(&g.cell_of, (size_t)max_particles * 4));
+    CWA_CUDA(cudaMalloc(&g.rank, (size_t)max_particles * 4));
+    CWA_CUDA(cudaMalloc(&g.index_list, (size_t)max_particles * 4));
+    CWA_CUDA(cudaMemsetAsync(blk, 0, g.clear_bytes, ctx->stream));
+    CWA_CUDA(cudaMemsetAsync(g.offset, 0, ((size_t)C + 1) * 4, ctx->stream));
+    CWA_CUDA(cudaMemsetAsync(g.index_list, 0xff, (size_t)max_particles * 4, ctx->stream));
+    g.buf_counter = new_buffer(ctx, g.counter, (size_t)C * 4, false);
+    g.buf_offset = new_buffer(ctx, g.offset, ((size_t)C + 1) * 4, false);
+    g.buf_index = new_buffer(ctx, g.index_list, (size_t)max_particles * 4, false);
+    g.buf_cell_of = new_buffer(ctx, g.cell_of, (size_t)max_particles * 4, false);
+    ctx->grids.push_back(g);
+    *out = (int)ctx->grids.size() - 1;
+    return 0;
+}
+
+extern "C" int cwa_grid_destroy(cwa_ctx* ctx, cwa_grid h)
+{
+    GridObj* g = get_grid(ctx, h);
+    CWA_CHECK(g, "invalid grid handle %d", h);
+    CWA_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(g->counter); cudaFree(g->offset); cudaFree(g->cell_of); cudaFree(g->rank); cudaFree(g->index_list);
+    for (cwa_buf b : {g->buf_counter, g->buf_offset, g->buf_index, g->buf_cell_of})
+        if (BufferObj* o = get_buffer(ctx, b)) o->live = false;
+    g->live = false;
+    return 0;
+}
+
+extern "C" int cwa_grid_get_info(cwa_ctx* ctx, cwa_grid h, cwa_grid_info* out, int* num_cells_total)
+{
+    GridObj* g = get_grid(ctx, h);
+    CWA_CHECK(g, "invalid grid handle %d", h);
+    if (out) *out = g->info;
+    if (num_cells_total) *num_cells_total = g->view.num_cells;
+    return 0;
+}
+
+extern "C" int cwa_grid_build(cwa_ctx* ctx, cwa_grid h, cwa_buf particles, int stride_bytes, int n)
+{
+    GridObj* g = get_grid(ctx, h);
+    CWA_CHECK(g, "invalid grid handle %d", h);
+    BufferObj* p = get_buffer(ctx, particles);
+    CWA_CHECK(p, "invalid particle buffer handle %d", particles);
+    CWA_CHECK((size_t)n * stride_bytes <= p->bytes, "cwa_grid_build: %d particles of %d bytes exceed the buffer", n, stride_bytes);
+    return grid_build_internal(ctx, g, p->ptr, stride_bytes, n);
+}
+
+extern "C" int cwa_grid_read(cwa_ctx* ctx, cwa_grid h, int which, int* host, int count)
+{
+    GridObj* g = get_grid(ctx, h);
+    CWA_CHECK(g && host, "invalid grid handle %d", h);
+    const int* src = nullptr; int avail = 0;
+    switch (which) {
+    case CWA_GRID_COUNTER: src = g->counter; avail = g->view.num_cells; break;
+    case CWA_GRID_OFFSET: src = g->offset; avail = g->view.num_cells + 1; break;
+    case CWA_GRID_INDEX_LIST: src = g->index_list; avail = g->max_particles; break;
+    case CWA_GRID_CELL_OF: src = g->cell_of; avail = g->max_particles; break;
+    default: CWA_CHECK(false, "cwa_grid_read: unknown array %d", which);
+    }
+    CWA_CHECK(count >= 0 && count <= avail, "cwa_grid_read: count %d exceeds %d", count, avail);
+    CWA_CUDA(cudaMemcpyAsync(host, src, (size_t)count * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CWA_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int cwa_grid_buffer(cwa_ctx* ctx, cwa_grid h, int which, cwa_buf* out)
+{
+    GridObj* g = get_grid(ctx, h);
+    CWA_CHECK(g && out, "invalid grid handle %d", h);
+    switch (which) {
+    case CWA_GRID_COUNTER: *out = g->buf_counter; break;
+    case CWA_GRID_OFFSET: *out = g->buf_offset; break;
+    case CWA_GRID_INDEX_LIST: *out = g->buf_index; break;
+    case CWA_GRID_CELL_OF: *out = g->buf_cell_of; break;
+    default: CWA_CHECK(false, "cwa_grid_buffer: unknown array %d", which);
+    }
+    return 0;
+}

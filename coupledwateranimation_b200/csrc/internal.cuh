@@ -1,0 +1,269 @@
+// internal.cuh -- shared host/device declarations of libcwa_b200 (not part of the C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/cwa_b200.h"
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing: no exceptions cross the C ABI
+// ---------------------------------------------------------------------------------------------
+void cwa_set_error(const char* fmt, ...);
+
+#define CWA_CUDA(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            cwa_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return -2;                                                                          \
+        }                                                                                       \
+    } while (0)
+
+#define CWA_CHECK(cond, ...)                                                                    \
+    do {                                                                                        \
+        if (!(cond)) { cwa_set_error(__VA_ARGS__); return -1; }                                 \
+    } while (0)
+
+#define CWA_TRY(expr)                                                                           \
+    do { int _r = (expr); if (_r != 0) return _r; } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// device-visible parameter views
+// ---------------------------------------------------------------------------------------------
+// Pointers to the currently bound UBO-equivalents (std140 blocks of Main.cpp:184-204 + the
+// promoted shader constants).  Passed by value to the kernels, read through the constant cache.
+struct ParamPtrs {
+    const cwa_constants_uniform* constants;   // binding 1
+    const cwa_boundary_uniform*  boundary;    // binding 2
+    const cwa_wave_uniforms*     wave;        // binding 3
+    const cwa_sim_constants*     sim;         // binding 4
+};
+
+// sampler2D wave_tex (binding 0): LINEAR / CLAMP_TO_EDGE, .r channel.  data == nullptr: unbound.
+struct TexView {
+    const float* data;
+    int w, h, ch;
+};
+
+// UniformGridInfo as the kernels see it.
+struct GridView {
+    float min[3];
+    float cell[3];
+    float max[3];
+    int   n[3];          // Nx, Ny, Nz (Nz = 1 in 2-D)
+    int   dim;           // 2 or 3
+    int   num_cells;     // allocated/scanned linear cells
+    // linear index: 3-D (i*Ny + j)*Nx + k (ugrid_particles_cs.glsl:105-108), 2-D i*Ny + j
+    // (uniform_grid_sph_cs.glsl:149-152).  A "row" is the run of cells sharing everything but the
+    // fastest coordinate (k in 3-D, j in 2-D); rows are contiguous in the sorted particle order.
+};
+
+// ---------------------------------------------------------------------------------------------
+// host objects behind the handles
+// ---------------------------------------------------------------------------------------------
+struct BufferObj {
+    void*  ptr   = nullptr;
+    size_t bytes = 0;
+    bool   owned = false;
+    bool   live  = false;
+};
+
+struct GridObj {
+    bool live = false;
+    int  dim = 3;
+    cwa_grid_info info{};
+    GridView view{};
+    int  max_particles = 0;
+    int  n_built = 0;              // particle count of the last build
+    // one allocation, cleared by a single memset per build: [counter C][ticket][tile_state]
+    int* counter = nullptr;        // int[C]
+    int* ticket = nullptr;         // scan tile ticket
+    unsigned long long* tile_state = nullptr;
+    size_t clear_bytes = 0;
+    int* offset = nullptr;         // int[C+1]  (offset[C] = number of inserted particles)
+    int* cell_of = nullptr;        // int[max_particles]  (-1: not inserted)
+    int* rank = nullptr;           // int[max_particles]  arrival rank inside the cell
+    int* index_list = nullptr;     // int[max_particles]  canonical: ascending id within a cell
+    cwa_buf buf_counter = -1, buf_offset = -1, buf_index = -1, buf_cell_of = -1;
+};
+
+struct WaveObj {
+    bool live = false;
+    int  w = 64, h = 64, ch = 1, variant = CWA_WAVE_COUPLED;
+    float* image[3] = {nullptr, nullptr, nullptr};
+    cwa_buf image_buf[3] = {-1, -1, -1};
+    // StencilImage2DTripleBuffered.h:35-37 and ImageTexture::mUnit
+    int  read_index[2] = {0, 1};
+    int  write_index = 2;
+    int  unit[3] = {0, 1, 2};
+    int  tex_unit0 = -1;           // physical image bound to GL texture unit 0 (-1: unbound)
+    bool evolve = true;
+    float* simp_params = nullptr;  // device float4 (lambda, atten, beta, 0) for variant SIMP
+    // TMA descriptors (scalar fast path): per physical image, halo box and plain box
+    CUtensorMap tmap_halo[3];
+    CUtensorMap tmap_core[3];
+    bool tma_ok = false;
+};
+
+struct SphObj {
+    bool live = false;
+    cwa_buf particles = -1;
+    int  n = 0;
+    cwa_grid grid = -1;            // -1: all-pairs
+    cwa_wave wave = -1;            // sampler binding
+    int  wave_image = -1;          // physical image, -1 unbound
+    // cell-ordered snapshot (grid mode) -- see DESIGN.md "data layout"
+    float4 *posS = nullptr, *velS = nullptr, *forceS = nullptr, *miscS = nullptr;
+    float4 *packA = nullptr, *packB = nullptr;   // (pos.xyz, p) and (vel.xyz, rho)
+    bool snapshot_valid = false;
+};
+
+struct Sph2Obj {
+    bool live = false;
+    int  n = 0, variant = CWA_SPH2_WAVE, substeps = 1;
+    cwa_grid grid = -1;
+    cwa_buf buffer[2] = {-1, -1};
+    int  read_index = 0, write_index = 1;
+    float time = 0.0f, bottom = 0.3f, psi = -1.0f, view_width = 2.0f * 4.8f;
+    int  init_width = 128;
+    cwa_buf wave1d = -1;
+    int  wave1d_width = 0;
+    float4 *posS = nullptr, *velS = nullptr, *accS = nullptr;   // cell-ordered snapshot of the read buffer
+};
+
+struct ShaderObj {
+    bool live = false;
+    std::string name;
+    int kind = -1;
+    int mode = 0;
+    int object = -1;
+    int   ui[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float uf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+struct cwa_ctx {
+    int device = 0;
+    int sm_count = 148;
+    int cc_major = 0, cc_minor = 0;
+    size_t total_mem = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
+    unsigned long long launches = 0;
+    std::vector<BufferObj> buffers;
+    std::vector<GridObj>   grids;
+    std::vector<WaveObj>   waves;
+    std::vector<SphObj>    sphs;
+    std::vector<Sph2Obj>   sph2s;
+    std::vector<ShaderObj> shaders;
+    cwa_buf ssbo_binding[16];
+    cwa_buf ubo_binding[8];
+    cwa_buf default_ubo[8];
+    cwa_sph  bound_sph = -1;
+    cwa_wave bound_wave = -1;
+    // scratch for cwa_scan_exclusive
+    int* scan_ticket = nullptr;
+    unsigned long long* scan_state = nullptr;
+    size_t scan_state_tiles = 0;
+    void* encode_tiled = nullptr;  // PFN cuTensorMapEncodeTiled
+};
+
+// handle helpers (defined in api.cu)
+BufferObj* get_buffer(cwa_ctx* ctx, cwa_buf b);
+GridObj*   get_grid(cwa_ctx* ctx, cwa_grid g);
+WaveObj*   get_wave(cwa_ctx* ctx, cwa_wave w);
+SphObj*    get_sph(cwa_ctx* ctx, cwa_sph s);
+Sph2Obj*   get_sph2(cwa_ctx* ctx, cwa_sph2 s);
+int        new_buffer(cwa_ctx* ctx, void* ptr, size_t bytes, bool owned);
+ParamPtrs  current_params(cwa_ctx* ctx);
+
+// cross-module internals
+int  scan_exclusive_launch(cwa_ctx* ctx, const int* in, int* out, int n, int* ticket,
+                           unsigned long long* tile_state);          // grid.cu; out has n+1 entries
+size_t scan_num_tiles(int n);
+int  grid_build_internal(cwa_ctx* ctx, GridObj* g, const void* particles, int stride_bytes, int n);
+TexView wave_tex_view(cwa_ctx* ctx, cwa_wave w, int image);           // wave.cu
+int  wave_step_internal(cwa_ctx* ctx, WaveObj* w);
+int  wave_dispatch_mode(cwa_ctx* ctx, WaveObj* w, int mode);           // kernel for uMode on units 0/1/2, no rotation                   // one EVOLVE dispatch + PingPong
+int  sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which /*bit0 rho, bit1 force, bit2 integrate*/);
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------------
+// device helpers shared by the kernels
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// float -> cell coordinate, clamp in the float domain first (NaN -> 0).  Restates
+// ivec(floor(q)); clamp(cell, 0, n-1) of uniform_grid_sph_cs.glsl:144-145 with a defined
+// result for NaN/huge inputs.  `q` must come from a true IEEE division (__fdiv_rn).
+__device__ __forceinline__ int cwa_cell_coord(float q, int n)
+{
+    float f = floorf(q);
+    if (!(f >= 0.0f)) return 0;
+    if (f > (float)(n - 1)) return n - 1;
+    return (int)f;
+}
+
+__device__ __forceinline__ void cwa_cell3(const GridView& g, float x, float y, float z, int& i, int& j, int& k)
+{
+    i = cwa_cell_coord(__fdiv_rn(__fsub_rn(x, g.min[0]), g.cell[0]), g.n[0]);
+    j = cwa_cell_coord(__fdiv_rn(__fsub_rn(y, g.min[1]), g.cell[1]), g.n[1]);
+    k = cwa_cell_coord(__fdiv_rn(__fsub_rn(z, g.min[2]), g.cell[2]), g.n[2]);
+}
+
+__device__ __forceinline__ void cwa_cell2(const GridView& g, float x, float y, int& i, int& j)
+{
+    i = cwa_cell_coord(__fdiv_rn(__fsub_rn(x, g.min[0]), g.cell[0]), g.n[0]);
+    j = cwa_cell_coord(__fdiv_rn(__fsub_rn(y, g.min[1]), g.cell[1]), g.n[1]);
+}
+
+// canonical length (shared with the oracle): explicit fma chain, IEEE sqrt
+__device__ __forceinline__ float cwa_len2sq(float x, float y) { return __fmaf_rn(y, y, __fmul_rn(x, x)); }
+__device__ __forceinline__ float cwa_len3sq(float x, float y, float z)
+{
+    return __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
+}
+
+__device__ __forceinline__ int cwa_tex_index(float f, int n)
+{
+    if (!(f >= 0.0f)) return 0;
+    if (f > (float)(n - 1)) return n - 1;
+    return (int)f;
+}
+
+// texture(wave_tex, (s,t)).r : GL_LINEAR, GL_CLAMP_TO_EDGE, LOD 0, full FP32 weights
+__device__ __forceinline__ float cwa_tex_bilinear(const TexView& t, float s, float tt)
+{
+    if (t.data == nullptr) return 0.0f;
+    const int W = t.w, H = t.h, C = t.ch;
+    float u = __fsub_rn(__fmul_rn(s, (float)W), 0.5f);
+    float v = __fsub_rn(__fmul_rn(tt, (float)H), 0.5f);
+    float fu = floorf(u), fv = floorf(v);
+    float a = __fsub_rn(u, fu), b = __fsub_rn(v, fv);
+    int i0 = cwa_tex_index(fu, W), i1 = cwa_tex_index(fu + 1.0f, W);
+    int j0 = cwa_tex_index(fv, H), j1 = cwa_tex_index(fv + 1.0f, H);
+    float t00 = __ldg(t.data + ((size_t)j0 * W + i0) * C);
+    float t10 = __ldg(t.data + ((size_t)j0 * W + i1) * C);
+    float t01 = __ldg(t.data + ((size_t)j1 * W + i0) * C);
+    float t11 = __ldg(t.data + ((size_t)j1 * W + i1) * C);
+    float r0 = __fadd_rn(t00, __fmul_rn(a, __fsub_rn(t10, t00)));
+    float r1 = __fadd_rn(t01, __fmul_rn(a, __fsub_rn(t11, t01)));
+    return __fadd_rn(r0, __fmul_rn(b, __fsub_rn(r1, r0)));
+}
+
+__device__ __forceinline__ float cwa_smoothstep(float e0, float e1, float x)
+{
+    float t = __fdiv_rn(__fsub_rn(x, e0), __fsub_rn(e1, e0));
+    t = fminf(fmaxf(t, 0.0f), 1.0f);
+    return __fmul_rn(__fmul_rn(t, t), __fsub_rn(3.0f, __fmul_rn(2.0f, t)));
+}
+
+#endif // __CUDACC__

@@ -1,0 +1,924 @@
+// sph3.cu -- the three 3-D SPH passes of CoupledWaterAnimation for sm_100a.
+//   rho_pres_comp.glsl:49-81   -> sph3_density_*   (poly6 density, EOS pressure, wave coupling)
+//   force_comp.glsl:62-139     -> sph3_force_*     (spiky pressure, viscosity, crest rule, torque,
+//                                                   wave drag / normal force, gravity)
+//   integrate_comp.glsl:56-178 -> sph3_integrate_* (symplectic Euler, foam rule, surface clamp, box)
+//
+// Grid mode (the north-star path): particles are gathered into cell order (coalesced float4
+// reorder, (3) of the north-star list); a CTA owns P consecutive cell-ordered particles and L
+// lanes cooperate on each of them.  The neighbour rows of the CTA's cells are contiguous runs of
+// the cell-ordered arrays, so each run is staged into shared memory with ONE 1-D bulk async copy
+// (cp.async.bulk, TMA engine, completion on an mbarrier); lanes then walk their own row ranges in
+// shared memory and combine partial sums with warp shuffles.  Ranges that do not fit the staging
+// budget are read through L1 from global memory by the same loop.
+// All-pairs mode reproduces the shipped O(N^2) loops with shared-memory tiles.
+#include "internal.cuh"
+#include <math_constants.h>
+
+#define CWA_PI 3.141592741f   // rho_pres_comp.glsl:8
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s3_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void s3_mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s3_smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void s3_mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s3_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void s3_mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s3_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void s3_mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "S3_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra S3_WAIT_DONE;\n"
+        "bra S3_WAIT_LOOP;\n"
+        "S3_WAIT_DONE:\n"
+        "}\n" ::"r"(s3_smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared (bytes % 16 == 0, both addresses 16-B aligned)
+__device__ __forceinline__ void s3_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(s3_smem_u32(dst)), "l"(src), "r"(bytes), "r"(s3_smem_u32(bar)) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// constants derived from the parameter blocks
+// ---------------------------------------------------------------------------------------------
+struct Sph3Const {
+    float h, h2, accept_r2;        // accept pair  <=>  r2 <= accept_r2  <=>  sqrt_rn(r2) < h
+    float mass, rho0, visc_coeff;
+    float poly6;                   // mass*315 / (64*PI*h^9)
+    float spiky, laplacian;        // -20/(PI*h^6), +20/(PI*h^6)
+    float gas, radius, dt, gravity_y, damping, crest, foam_speed, uv_scale;
+    float wave_type;
+    float upper[3], lower[3];
+};
+
+// largest float t with sqrt_rn(t) < h: the pair test "length(delta) < h" of the shaders becomes an
+// exact compare on the squared distance (correctly rounded sqrt is monotonic).
+__device__ __forceinline__ float accept_threshold(float h)
+{
+    if (!(h > 0.0f)) return -1.0f;
+    float t = __fmul_rn(h, h);
+    for (int it = 0; it < 4 && __fsqrt_rn(t) >= h; it++) t = __uint_as_float(__float_as_uint(t) - 1u);
+    for (int it = 0; it < 4; it++) {
+        float u = __uint_as_float(__float_as_uint(t) + 1u);
+        if (__fsqrt_rn(u) < h) t = u; else break;
+    }
+    return t;
+}
+
+__device__ __forceinline__ Sph3Const load_consts(const ParamPtrs& prm)
+{
+    Sph3Const c;
+    const cwa_constants_uniform cu = *prm.constants;
+    const cwa_sim_constants sc = *prm.sim;
+    c.mass = cu.mass; c.rho0 = cu.resting_rho; c.visc_coeff = cu.visc;
+    c.h = __fmul_rn(cu.smoothing_coeff, sc.particle_radius);        // rho_pres_comp.glsl:54
+    c.h2 = __fmul_rn(c.h, c.h);
+    c.accept_r2 = accept_threshold(c.h);
+    const float h2 = c.h2, h4 = __fmul_rn(h2, h2), h8 = __fmul_rn(h4, h4);
+    const float h9 = __fmul_rn(h8, c.h), h6 = __fmul_rn(h4, h2);
+    c.poly6 = __fdiv_rn(__fmul_rn(cu.mass, 315.0f), __fmul_rn(__fmul_rn(64.0f, CWA_PI), h9));
+    c.spiky = __fdiv_rn(-20.0f, __fmul_rn(CWA_PI, h6));            // force_comp.glsl:68
+    c.laplacian = -c.spiky;                                        // :69
+    c.gas = sc.gas_const; c.radius = sc.particle_radius; c.dt = sc.dt; c.gravity_y = sc.gravity_y;
+    c.damping = sc.damping; c.crest = sc.crest_threshold; c.foam_speed = sc.foam_speed; c.uv_scale = sc.uv_scale;
+    c.wave_type = prm.wave->attributes[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) { c.upper[a] = prm.boundary->upper[a]; c.lower[a] = prm.boundary->lower[a]; }
+    return c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pair terms
+// ---------------------------------------------------------------------------------------------
+// rho_pres_comp.glsl:62-67
+__device__ __forceinline__ void pair_density(const Sph3Const& c, float px, float py, float pz, const float4 q, float& rho)
+{
+    const float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
+    const float r2 = cwa_len3sq(dx, dy, dz);
+    if (r2 <= c.accept_r2) {
+        const float d = c.h2 - r2;
+        rho = fmaf(c.poly6, d * d * d, rho);
+    }
+}
+
+// force_comp.glsl:79-87 (caller excludes j == i)
+__device__ __forceinline__ void pair_force(const Sph3Const& c, float px, float py, float pz, float prs_i,
+                                           float vx, float vy, float vz, const float4 qa, const float4 qb,
+                                           float& fpx, float& fpy, float& fpz, float& fvx, float& fvy, float& fvz)
+{
+    const float inv_r = rsqrtf(cwa_len3sq(px - qa.x, py - qa.y, pz - qa.z));
+    const float dx = px - qa.x, dy = py - qa.y, dz = pz - qa.z;
+    const float r = cwa_len3sq(dx, dy, dz) * inv_r;             // r = 0 -> NaN like normalize(0)
+    const float hr = c.h - r;
+    const float inv_rho = __frcp_rn(qb.w);
+    // pres_force -= mass*(p_i+p_j)/(2 rho_j) * spiky * (h-r)^2 * normalize(delta)
+    const float a = c.mass * (prs_i + qa.w) * (0.5f * inv_rho) * c.spiky * (hr * hr) * inv_r;
+    fpx = fmaf(-a, dx, fpx); fpy = fmaf(-a, dy, fpy); fpz = fmaf(-a, dz, fpz);
+    // visc_force += mass*(v_j - v_i)/rho_j * laplacian * (h-r)
+    const float b = c.mass * inv_rho * c.laplacian * hr;
+    fvx = fmaf(b, qb.x - vx, fvx); fvy = fmaf(b, qb.y - vy, fvy); fvz = fmaf(b, qb.z - vz, fvz);
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-particle epilogues (shared by grid and all-pairs kernels)
+// ---------------------------------------------------------------------------------------------
+// rho_pres_comp.glsl:70-80
+__device__ __forceinline__ void density_epilogue(const Sph3Const& c, const TexView& tex, float px, float pz, float rho,
+                                                 float& rho_out, float& prs_out)
+{
+    float pressure = fmaxf(c.gas * (rho - c.rho0), 0.0f);
+    const float height = cwa_tex_bilinear(tex, c.uv_scale * px, c.uv_scale * pz);
+    const float wave_force = height * rho;
+    pressure += wave_force;
+    rho += __fdiv_rn(wave_force, c.gas * c.radius);
+    rho_out = fmaxf(c.rho0, rho);
+    prs_out = pressure;
+}
+
+// force_comp.glsl:90-114.  fprev = particles[i].force as stored by the previous frame.
+__device__ __forceinline__ float4 force_epilogue(const Sph3Const& c, const TexView& tex, float px, float py, float pz,
+                                                 float vx, float vy, float vz, float rho_i, float4 fprev,
+                                                 float fpx, float fpy, float fpz, float fvx, float fvy, float fvz)
+{
+    if (py > c.crest) {                                            // :91-95
+        fprev.x = __fdiv_rn(fprev.x, 0.25f); fprev.y = __fdiv_rn(fprev.y, 0.25f);
+        fprev.z = __fdiv_rn(fprev.z, 0.25f); fprev.w = __fdiv_rn(fprev.w, 0.25f);
+        fvx *= 0.5f; fvy *= 0.5f; fvz *= 0.5f;
+    }
+    fvx *= c.visc_coeff; fvy *= c.visc_coeff; fvz *= c.visc_coeff; // :97
+    const float cu = px * c.uv_scale, cv = pz * c.uv_scale;        // :99
+    const float height = cwa_tex_bilinear(tex, cu, cv);            // :100
+    // torque = 0.25 * cross(pos, force_prev.xyz)  :103-104
+    const float tx = 0.25f * (py * fprev.z - pz * fprev.y);
+    const float ty = 0.25f * (pz * fprev.x - px * fprev.z);
+    const float tz = 0.25f * (px * fprev.y - py * fprev.x);
+    // WaveVelocity :117-128
+    const float hX = cwa_tex_bilinear(tex, cu + 0.01f, cv);
+    const float hY = cwa_tex_bilinear(tex, cu, cv + 0.01f);
+    const float wvx = __fdiv_rn(hX - height, c.dt), wvy = __fdiv_rn(hY - height, c.dt), wvz = __fdiv_rn(hX - hY, 0.01f);
+    const float dgx = -0.25f * (vx - wvx), dgy = -0.25f * (vy - wvy), dgz = -0.25f * (vz - wvz);   // :107-108
+    // WaveNormal :131-139: cross(dy,dx) = (dx.z, dy.z, -1)
+    const float nx = cwa_tex_bilinear(tex, cu + 1.0f, cv) - height;
+    const float ny = cwa_tex_bilinear(tex, cu, cv + 1.0f) - height;
+    const float wfx = -height * nx * 0.5f, wfy = -height * ny * 0.5f, wfz = -height * -1.0f * 0.5f;  // :110
+    const float gy = rho_i * c.gravity_y;                                                         // :113
+    float4 f;
+    f.x = fpx + fvx + 0.0f + tx + dgx + wfx;                       // :114
+    f.y = fpy + fvy + gy + ty + dgy + wfy;
+    f.z = fpz + fvz + 0.0f + tz + dgz + wfz;
+    f.w = fprev.w;
+    return f;
+}
+
+// integrate_comp.glsl:56-92 + CheckBoundary :135-178
+__device__ __forceinline__ void integrate_particle(const Sph3Const& c, const TexView& tex, float4& pos, float4& vel,
+                                                   float4& force, float& rho, float& prs)
+{
+    const float ax = __fdiv_rn(force.x, rho), ay = __fdiv_rn(force.y, rho), az = __fdiv_rn(force.z, rho);
+    float nvx = vel.x + c.dt * ax, nvy = vel.y + c.dt * ay, nvz = vel.z + c.dt * az;
+    float npx = pos.x + c.dt * nvx, npy = pos.y + c.dt * nvy, npz = pos.z + c.dt * nvz;
+    const float damp = 1.0f - c.damping * c.dt;
+    nvx *= damp; nvy *= damp; nvz *= damp;
+    if (__fsqrt_rn(cwa_len3sq(nvx, nvy, nvz)) > c.foam_speed) {    // :69-76
+        force.x *= 0.5f; force.y *= 0.5f; force.z *= 0.5f; force.w *= 0.5f;
+        rho *= 0.1f; prs *= 0.25f;
+        nvx *= 0.1f; nvy *= 0.1f; nvz *= 0.1f;
+    }
+    const float th = cwa_tex_bilinear(tex, npx * c.uv_scale, npz * c.uv_scale);   // :79
+    if (npy < th) npy = th - c.radius;                                            // :80-83
+    const float D = c.damping;
+    if (npx < c.lower[0]) { npx = c.lower[0]; nvx *= -D; } else if (npx > c.upper[0]) { npx = c.upper[0]; nvx *= -D; }
+    if (npy < c.lower[1]) { npy = c.lower[1]; nvy *= -D; } else if (npy > c.upper[1]) { npy = c.upper[1]; nvy *= -D; }
+    if (npz < c.lower[2]) { npz = c.lower[2]; nvz *= -D; } else if (npz > c.upper[2]) { npz = c.upper[2]; nvz *= -D; }
+    if (c.wave_type > 0.0f && c.wave_type < 1.0f) {                               // :170-177
+        if (npy > c.upper[1] + 0.1f) { npy = c.upper[1] + 0.1f; nvy *= -D; }
+    }
+    pos.x = npx; pos.y = npy; pos.z = npz;
+    vel.x = nvx; vel.y = nvy; vel.z = nvz;
+}
+
+// The integrate pass must not fuse its multiply-adds differently from the oracle where a branch
+// decision hangs on the result (foam, surface clamp, walls); the tolerance on pos/vel is 1e-4 and
+// decisions are compared on fixtures with margins, so default contraction is kept.
+
+// ---------------------------------------------------------------------------------------------
+// (3) coalesced float4 reorder into cell order
+// ---------------------------------------------------------------------------------------------
+// 4 lanes per particle: lane q moves vec4 q of the 64-B struct, so the gather reads whole 64-B
+// records and the four cell-ordered arrays are written with 128-B contiguous runs per 8 slots.
+__global__ void __launch_bounds__(256)
+sph3_reorder_kernel(const float4* __restrict__ aos, const int* __restrict__ index_list, int n,
+                    float4* __restrict__ posS, float4* __restrict__ velS, float4* __restrict__ forceS,
+                    float4* __restrict__ miscS)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = t >> 2, q = t & 3;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (s < n) {
+        const int i = __ldg(index_list + s);
+        v = __ldg(aos + (size_t)i * 4 + q);
+    }
+    // lane 3 (extras) needs pos.w and vel.w from lanes 0 and 1 of its quad
+    const unsigned lane = threadIdx.x & 31u, quad = lane & ~3u;
+    const float pw = __shfl_sync(0xffffffffu, v.w, quad + 0);
+    const float vw = __shfl_sync(0xffffffffu, v.w, quad + 1);
+    if (s >= n) return;
+    if (q == 0) posS[s] = v;
+    else if (q == 1) velS[s] = v;
+    else if (q == 2) forceS[s] = v;
+    else miscS[s] = make_float4(pw, vw, v.z, v.w);      // (pos.w, vel.w, extras.z, extras.w)
+}
+
+// ---------------------------------------------------------------------------------------------
+// grid-mode neighbour kernels
+// ---------------------------------------------------------------------------------------------
+constexpr int NB_WINDOWS = 9;
+
+struct BlockWindows {
+    int lo[NB_WINDOWS];      // first cell-ordered slot covered by the window
+    int hi[NB_WINDOWS];      // one past the last slot
+    int soff[NB_WINDOWS];    // start inside the staging buffer (slots); -1 = not staged
+};
+
+// Windows of the CTA: for row offset (di,dj) the neighbour cells of every target lie between
+// lin(first target) + off - 1 and lin(last target) + off + 1 in linear cell order.  Thread w < 9
+// fetches the bounds of window w; thread 0 then packs the windows into the staging buffer.
+__device__ __forceinline__ void window_bounds(const GridView& g, const int* __restrict__ offset, const float4 pfirst,
+                                              const float4 plast, int w, BlockWindows* bw)
+{
+    int i, j, k;
+    cwa_cell3(g, pfirst.x, pfirst.y, pfirst.z, i, j, k);
+    const int lin_f = (i * g.n[1] + j) * g.n[0] + k;
+    cwa_cell3(g, plast.x, plast.y, plast.z, i, j, k);
+    const int lin_l = (i * g.n[1] + j) * g.n[0] + k;
+    const int si = g.n[1] * g.n[0], sj = g.n[0];
+    const int off = (w / 3 - 1) * si + (w % 3 - 1) * sj;
+    int lo_lin = lin_f + off - 1, hi_lin = lin_l + off + 1;
+    lo_lin = max(lo_lin, 0); hi_lin = min(hi_lin, g.num_cells - 1);
+    int lo = 0, hi = 0;
+    if (hi_lin >= lo_lin) { lo = __ldg(offset + lo_lin); hi = __ldg(offset + hi_lin + 1); }
+    bw->lo[w] = lo; bw->hi[w] = hi;
+}
+
+__device__ __forceinline__ uint32_t window_pack(int cap_slots, bool reach_ok, BlockWindows* bw)
+{
+    int acc = 0;
+    for (int w = 0; w < NB_WINDOWS; w++) {
+        const int len = bw->hi[w] - bw->lo[w];
+        if (reach_ok && len > 0 && acc + len <= cap_slots) { bw->soff[w] = acc; acc += len; }
+        else bw->soff[w] = -1;
+    }
+    return (uint32_t)acc;
+}
+
+struct RowRange { int g0, g1, win; };
+
+template <int P, int L>
+__global__ void __launch_bounds__(P * L)
+sph3_density_grid_kernel(const float4* __restrict__ posS, const float4* __restrict__ velS,
+                         float4* __restrict__ packA, float4* __restrict__ packB, int n, GridView g,
+                         const int* __restrict__ offset, ParamPtrs prm, TexView tex, int cap_slots)
+{
+    extern __shared__ float4 stage[];
+    __shared__ BlockWindows bw;
+    __shared__ uint64_t bar;
+    const int tid = threadIdx.x;
+    const int t0 = blockIdx.x * P;
+    const int nt = min(P, n - t0);
+    const Sph3Const c = load_consts(prm);
+    const bool reach_ok = (c.h <= g.cell[0]) && (c.h <= g.cell[1]) && (c.h <= g.cell[2]);
+
+    if (tid < NB_WINDOWS) window_bounds(g, offset, __ldg(posS + t0), __ldg(posS + t0 + nt - 1), tid, &bw);
+    if (tid == 0) s3_mbar_init(&bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t slots = window_pack(cap_slots, reach_ok, &bw);
+        if (slots > 0) {
+            s3_mbar_expect_tx(&bar, slots * 16u);
+            for (int w = 0; w < NB_WINDOWS; w++)
+                if (bw.soff[w] >= 0) s3_bulk_g2s(stage + bw.soff[w], posS + bw.lo[w], (uint32_t)(bw.hi[w] - bw.lo[w]) * 16u, &bar);
+        } else {
+            s3_mbar_arrive(&bar);
+        }
+    }
+    __syncthreads();                                   // windows + barrier init visible
+
+    const int slot = t0 + tid / L, sub = tid % L;
+    const bool active = (tid / L) < nt;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    int i0 = 0, i1 = -1, j0 = 0, j1 = -1, k0 = 0, k1 = 0, ci = 0, cj = 0;
+    if (active) {
+        p = __ldg(posS + slot);
+        int ck;
+        cwa_cell3(g, p.x, p.y, p.z, ci, cj, ck);
+        cwa_cell3(g, p.x - c.h, p.y - c.h, p.z - c.h, i0, j0, k0);     // cells overlapped by pos +- h
+        cwa_cell3(g, p.x + c.h, p.y + c.h, p.z + c.h, i1, j1, k1);
+    }
+    s3_mbar_wait(&bar, 0);
+
+    float rho = 0.0f;
+    const int nj = j1 - j0 + 1;
+    const int nr = (i1 - i0 + 1) * nj;
+    for (int r = sub; r < nr; r += L) {
+        const int i = i0 + r / nj, j = j0 + r % nj;
+        const int base = (i * g.n[1] + j) * g.n[0];
+        const int g0 = __ldg(offset + base + k0), g1 = __ldg(offset + base + k1 + 1);
+        const int di = i - ci + 1, dj = j - cj + 1;
+        bool in_smem = false;
+        int shift = 0;
+        if ((unsigned)di < 3u && (unsigned)dj < 3u) {
+            const int w = di * 3 + dj;
+            if (bw.soff[w] >= 0 && g0 >= bw.lo[w] && g1 <= bw.hi[w]) { in_smem = true; shift = bw.soff[w] - bw.lo[w]; }
+        }
+        if (in_smem) {
+            const float4* src = stage + shift;
+            for (int q = g0; q < g1; q++) pair_density(c, p.x, p.y, p.z, src[q], rho);
+        } else {
+            for (int q = g0; q < g1; q++) pair_density(c, p.x, p.y, p.z, __ldg(posS + q), rho);
+        }
+    }
+#pragma unroll
+    for (int d = 1; d < L; d <<= 1) rho += __shfl_xor_sync(0xffffffffu, rho, d);
+    if (active && sub == 0) {
+        float rho_out, prs_out;
+        density_epilogue(c, tex, p.x, p.z, rho, rho_out, prs_out);
+        const float4 v = __ldg(velS + slot);
+        packA[slot] = make_float4(p.x, p.y, p.z, prs_out);
+        packB[slot] = make_float4(v.x, v.y, v.z, rho_out);
+    }
+}
+
+template <int P, int L>
+__global__ void __launch_bounds__(P * L)
+sph3_force_grid_kernel(const float4* __restrict__ packA, const float4* __restrict__ packB,
+                       float4* __restrict__ forceS, int n, GridView g, const int* __restrict__ offset,
+                       ParamPtrs prm, TexView tex, int cap_slots)
+{
+    extern __shared__ float4 stage[];                 // [cap_slots] A followed by [cap_slots] B
+    __shared__ BlockWindows bw;
+    __shared__ uint64_t bar;
+    const int tid = threadIdx.x;
+    const int t0 = blockIdx.x * P;
+    const int nt = min(P, n - t0);
+    const Sph3Const c = load_consts(prm);
+    const bool reach_ok = (c.h <= g.cell[0]) && (c.h <= g.cell[1]) && (c.h <= g.cell[2]);
+    float4* stageA = stage;
+    float4* stageB = stage + cap_slots;
+
+    if (tid < NB_WINDOWS) window_bounds(g, offset, __ldg(packA + t0), __ldg(packA + t0 + nt - 1), tid, &bw);
+    if (tid == 0) s3_mbar_init(&bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t slots = window_pack(cap_slots, reach_ok, &bw);
+        if (slots > 0) {
+            s3_mbar_expect_tx(&bar, slots * 32u);
+            for (int w = 0; w < NB_WINDOWS; w++)
+                if (bw.soff[w] >= 0) {
+                    const uint32_t b = (uint32_t)(bw.hi[w] - bw.lo[w]) * 16u;
+                    s3_bulk_g2s(stageA + bw.soff[w], packA + bw.lo[w], b, &bar);
+                    s3_bulk_g2s(stageB + bw.soff[w], packB + bw.lo[w], b, &bar);
+                }
+        } else {
+            s3_mbar_arrive(&bar);
+        }
+    }
+    __syncthreads();
+
+    const int slot = t0 + tid / L, sub = tid % L;
+    const bool active = (tid / L) < nt;
+    float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa;
+    int i0 = 0, i1 = -1, j0 = 0, j1 = -1, k0 = 0, k1 = 0, ci = 0, cj = 0;
+    if (active) {
+        pa = __ldg(packA + slot);
+        pb = __ldg(packB + slot);
+        int ck;
+        cwa_cell3(g, pa.x, pa.y, pa.z, ci, cj, ck);
+        cwa_cell3(g, pa.x - c.h, pa.y - c.h, pa.z - c.h, i0, j0, k0);
+        cwa_cell3(g, pa.x + c.h, pa.y + c.h, pa.z + c.h, i1, j1, k1);
+    }
+    s3_mbar_wait(&bar, 0);
+
+    float fpx = 0.f, fpy = 0.f, fpz = 0.f, fvx = 0.f, fvy = 0.f, fvz = 0.f;
+    const int nj = j1 - j0 + 1;
+    const int nr = (i1 - i0 + 1) * nj;
+    for (int r = sub; r < nr; r += L) {
+        const int i = i0 + r / nj, j = j0 + r % nj;
+        const int base = (i * g.n[1] + j) * g.n[0];
+        const int g0 = __ldg(offset + base + k0), g1 = __ldg(offset + base + k1 + 1);
+        const int di = i - ci + 1, dj = j - cj + 1;
+        bool in_smem = false;
+        int shift = 0;
+        if ((unsigned)di < 3u && (unsigned)dj < 3u) {
+            const int w = di * 3 + dj;
+            if (bw.soff[w] >= 0 && g0 >= bw.lo[w] && g1 <= bw.hi[w]) { in_smem = true; shift = bw.soff[w] - bw.lo[w]; }
+        }
+        if (in_smem) {
+            const float4* sa = stageA + shift;
+            const float4* sb = stageB + shift;
+            for (int q = g0; q < g1; q++) {
+                const float4 qa = sa[q];
+                const float r2 = cwa_len3sq(pa.x - qa.x, pa.y - qa.y, pa.z - qa.z);
+                if (r2 <= c.accept_r2 && q != slot)
+                    pair_force(c, pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, qa, sb[q], fpx, fpy, fpz, fvx, fvy, fvz);
+            }
+        } else {
+            for (int q = g0; q < g1; q++) {
+                const float4 qa = __ldg(packA + q);
+                const float r2 = cwa_len3sq(pa.x - qa.x, pa.y - qa.y, pa.z - qa.z);
+                if (r2 <= c.accept_r2 && q != slot)
+                    pair_force(c, pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, qa, __ldg(packB + q), fpx, fpy, fpz, fvx, fvy, fvz);
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 1; d < L; d <<= 1) {
+        fpx += __shfl_xor_sync(0xffffffffu, fpx, d); fpy += __shfl_xor_sync(0xffffffffu, fpy, d);
+        fpz += __shfl_xor_sync(0xffffffffu, fpz, d); fvx += __shfl_xor_sync(0xffffffffu, fvx, d);
+        fvy += __shfl_xor_sync(0xffffffffu, fvy, d); fvz += __shfl_xor_sync(0xffffffffu, fvz, d);
+    }
+    if (active && sub == 0) {
+        const float4 fprev = forceS[slot];
+        forceS[slot] = force_epilogue(c, tex, pa.x, pa.y, pa.z, pb.x, pb.y, pb.z, pb.w, fprev, fpx, fpy, fpz, fvx, fvy, fvz);
+    }
+}
+
+// integrate on the cell-ordered snapshot, results scattered back to the particle SSBO in its
+// original order (full 64-B records, 4 lanes per particle).
+__global__ void __launch_bounds__(256)
+sph3_integrate_sorted_kernel(const float4* __restrict__ packA, const float4* __restrict__ packB,
+                             const float4* __restrict__ forceS, const float4* __restrict__ miscS,
+                             const int* __restrict__ index_list, int n, float4* __restrict__ aos,
+                             ParamPtrs prm, TexView tex)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = t >> 2, q = t & 3;
+    if (s >= n) return;
+    const Sph3Const c = load_consts(prm);
+    const float4 a = __ldg(packA + s), b = __ldg(packB + s), m = __ldg(miscS + s);
+    float4 f = __ldg(forceS + s);
+    float4 pos = make_float4(a.x, a.y, a.z, m.x), vel = make_float4(b.x, b.y, b.z, m.y);
+    float rho = b.w, prs = a.w;
+    integrate_particle(c, tex, pos, vel, f, rho, prs);
+    const int i = __ldg(index_list + s);
+    float4 o;
+    if (q == 0) o = pos;
+    else if (q == 1) o = vel;
+    else if (q == 2) o = f;
+    else o = make_float4(rho, prs, m.z, m.w);
+    aos[(size_t)i * 4 + q] = o;
+}
+
+// write-back of a single pass result to the SSBO (individually dispatched passes)
+__global__ void __launch_bounds__(256)
+sph3_scatter_rho_pres_kernel(const float4* __restrict__ packA, const float4* __restrict__ packB,
+                             const int* __restrict__ index_list, int n, float4* __restrict__ aos)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int i = __ldg(index_list + s);
+    float2* e = reinterpret_cast<float2*>(aos + (size_t)i * 4 + 3);
+    *e = make_float2(__ldg(packB + s).w, __ldg(packA + s).w);      // extras[0] = rho, extras[1] = pressure
+}
+
+__global__ void __launch_bounds__(256)
+sph3_scatter_force_kernel(const float4* __restrict__ forceS, const int* __restrict__ index_list, int n,
+                          float4* __restrict__ aos)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    aos[(size_t)__ldg(index_list + s) * 4 + 2] = __ldg(forceS + s);
+}
+
+// integrate directly on the SSBO (original order); used when the pass is dispatched on its own
+__global__ void __launch_bounds__(256)
+sph3_integrate_aos_kernel(float4* __restrict__ aos, int n, ParamPtrs prm, TexView tex)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = t >> 2, q = t & 3;
+    if (i >= n) return;
+    const Sph3Const c = load_consts(prm);
+    float4 pos = aos[(size_t)i * 4 + 0], vel = aos[(size_t)i * 4 + 1], f = aos[(size_t)i * 4 + 2];
+    const float4 e = aos[(size_t)i * 4 + 3];
+    float rho = e.x, prs = e.y;
+    integrate_particle(c, tex, pos, vel, f, rho, prs);
+    __syncwarp();                                      // all four lanes of a particle have read it
+    float4 o;
+    if (q == 0) o = pos;
+    else if (q == 1) o = vel;
+    else if (q == 2) o = f;
+    else o = make_float4(rho, prs, e.z, e.w);
+    aos[(size_t)i * 4 + q] = o;
+}
+
+// ---------------------------------------------------------------------------------------------
+// all-pairs kernels (the shipped O(N^2) loops): TT targets x 4 candidate quarters per CTA
+// ---------------------------------------------------------------------------------------------
+constexpr int AP_TT = 64;        // targets per CTA
+constexpr int AP_L = 4;          // lanes per target (each scans one quarter of every tile)
+constexpr int AP_TILE = 256;     // candidates per shared-memory tile
+
+__global__ void __launch_bounds__(AP_TT * AP_L)
+sph3_density_allpairs_kernel(float4* __restrict__ aos, int n, ParamPtrs prm, TexView tex, float2* __restrict__ out_rp)
+{
+    __shared__ float4 tile[AP_TILE];
+    const int tid = threadIdx.x;
+    const int i = blockIdx.x * AP_TT + tid / AP_L, sub = tid % AP_L;
+    const Sph3Const c = load_consts(prm);
+    const bool active = i < n;
+    const float4 p = active ? aos[(size_t)i * 4] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float rho = 0.0f;
+    for (int j0 = 0; j0 < n; j0 += AP_TILE) {
+        const int j = j0 + tid;
+        tile[tid] = (j < n) ? aos[(size_t)j * 4] : make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f);
+        __syncthreads();
+#pragma unroll 8
+        for (int q = sub; q < AP_TILE; q += AP_L) pair_density(c, p.x, p.y, p.z, tile[q], rho);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int d = 1; d < AP_L; d <<= 1) rho += __shfl_xor_sync(0xffffffffu, rho, d);
+    if (active && sub == 0) {
+        float rho_out, prs_out;
+        density_epilogue(c, tex, p.x, p.z, rho, rho_out, prs_out);
+        out_rp[i] = make_float2(rho_out, prs_out);     // committed to the SSBO after the pass (no read/write race)
+    }
+}
+
+__global__ void __launch_bounds__(256)
+sph3_commit_rho_pres_kernel(const float2* __restrict__ rp, int n, float4* __restrict__ aos)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    *reinterpret_cast<float2*>(aos + (size_t)i * 4 + 3) = rp[i];
+}
+
+__global__ void __launch_bounds__(AP_TT * AP_L)
+sph3_force_allpairs_kernel(float4* __restrict__ aos, int n, ParamPtrs prm, TexView tex, float4* __restrict__ out_force)
+{
+    __shared__ float4 tileA[AP_TILE];
+    __shared__ float4 tileB[AP_TILE];
+    const int tid = threadIdx.x;
+    const int i = blockIdx.x * AP_TT + tid / AP_L, sub = tid % AP_L;
+    const Sph3Const c = load_consts(prm);
+    const bool active = i < n;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f), v = p, e = p;
+    if (active) { p = aos[(size_t)i * 4]; v = aos[(size_t)i * 4 + 1]; e = aos[(size_t)i * 4 + 3]; }
+    float fpx = 0.f, fpy = 0.f, fpz = 0.f, fvx = 0.f, fvy = 0.f, fvz = 0.f;
+    for (int j0 = 0; j0 < n; j0 += AP_TILE) {
+        const int j = j0 + tid;
+        if (j < n) {
+            const float4 qp = aos[(size_t)j * 4], qv = aos[(size_t)j * 4 + 1], qe = aos[(size_t)j * 4 + 3];
+            tileA[tid] = make_float4(qp.x, qp.y, qp.z, qe.y);
+            tileB[tid] = make_float4(qv.x, qv.y, qv.z, qe.x);
+        } else {
+            tileA[tid] = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f);
+            tileB[tid] = make_float4(0.f, 0.f, 0.f, 1.f);
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int q = sub; q < AP_TILE; q += AP_L) {
+            const float4 qa = tileA[q];
+            const float r2 = cwa_len3sq(p.x - qa.x, p.y - qa.y, p.z - qa.z);
+            if (r2 <= c.accept_r2 && (j0 + q) != i)
+                pair_force(c, p.x, p.y, p.z, e.y, v.x, v.y, v.z, qa, tileB[q], fpx, fpy, fpz, fvx, fvy, fvz);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int d = 1; d < AP_L; d <<= 1) {
+        fpx += __shfl_xor_sync(0xffffffffu, fpx, d); fpy += __shfl_xor_sync(0xffffffffu, fpy, d);
+        fpz += __shfl_xor_sync(0xffffffffu, fpz, d); fvx += __shfl_xor_sync(0xffffffffu, fvx, d);
+        fvy += __shfl_xor_sync(0xffffffffu, fvy, d); fvz += __shfl_xor_sync(0xffffffffu, fvz, d);
+    }
+    if (active && sub == 0) {
+        const float4 fprev = aos[(size_t)i * 4 + 2];
+        out_force[i] = force_epilogue(c, tex, p.x, p.y, p.z, v.x, v.y, v.z, e.x, fprev, fpx, fpy, fpz, fvx, fvy, fvz);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+sph3_commit_force_kernel(const float4* __restrict__ f, int n, float4* __restrict__ aos)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    aos[(size_t)i * 4 + 2] = f[i];
+}
+
+// neighbour counts for the "neighbour set identical" assertions
+__global__ void __launch_bounds__(256)
+sph3_neighbour_count_grid_kernel(const float4* __restrict__ posS, const int* __restrict__ index_list, int n,
+                                 GridView g, const int* __restrict__ offset, ParamPtrs prm, int* __restrict__ out)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const Sph3Const c = load_consts(prm);
+    const float4 p = __ldg(posS + s);
+    int i0, j0, k0, i1, j1, k1;
+    cwa_cell3(g, p.x - c.h, p.y - c.h, p.z - c.h, i0, j0, k0);
+    cwa_cell3(g, p.x + c.h, p.y + c.h, p.z + c.h, i1, j1, k1);
+    int cnt = 0;
+    for (int i = i0; i <= i1; i++)
+        for (int j = j0; j <= j1; j++) {
+            const int base = (i * g.n[1] + j) * g.n[0];
+            const int g0 = __ldg(offset + base + k0), g1 = __ldg(offset + base + k1 + 1);
+            for (int q = g0; q < g1; q++) {
+                const float4 o = __ldg(posS + q);
+                if (cwa_len3sq(p.x - o.x, p.y - o.y, p.z - o.z) <= c.accept_r2) cnt++;
+            }
+        }
+    out[__ldg(index_list + s)] = cnt;
+}
+
+__global__ void __launch_bounds__(256)
+sph3_neighbour_count_allpairs_kernel(const float4* __restrict__ aos, int n, ParamPtrs prm, int* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Sph3Const c = load_consts(prm);
+    const float4 p = aos[(size_t)i * 4];
+    int cnt = 0;
+    for (int j = 0; j < n; j++) {
+        const float4 o = __ldg(aos + (size_t)j * 4);
+        if (cwa_len3sq(p.x - o.x, p.y - o.y, p.z - o.z) <= c.accept_r2) cnt++;
+    }
+    out[i] = cnt;
+}
+
+// make_cube + init_particles, CoupledWaterAnimation/Main.cpp:735-776
+__global__ void __launch_bounds__(256)
+sph3_init_cube_kernel(float4* __restrict__ aos, int nx, int ny, int nz, ParamPtrs prm)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = nx * ny * nz;
+    if (t >= n) return;
+    const float spacing = __fmul_rn(__fmul_rn(prm.constants->smoothing_coeff, 0.85f), prm.sim->particle_radius);   // :739
+    const int k = t % nz, j = (t / nz) % ny, i = t / (nz * ny);       // i outer, j, k inner :743-753
+    aos[(size_t)t * 4 + 0] = make_float4(__fadd_rn(0.0f, __fmul_rn((float)i, spacing)), __fmul_rn((float)j, spacing),
+                                         __fadd_rn(0.0f, __fmul_rn((float)k, spacing)), 1.0f);
+    aos[(size_t)t * 4 + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    aos[(size_t)t * 4 + 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+    aos[(size_t)t * 4 + 3] = make_float4(prm.constants->resting_rho, 0.0f, 500.0f, 50.0f);   // :774
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+constexpr int NB_P = 128;                 // targets per CTA
+constexpr int NB_L = 4;                   // lanes per target
+constexpr int DENS_CAP = 3072;            // staged slots (16 B each)  -> 48 KB
+constexpr int FORCE_CAP = 2048;           // staged slots (32 B each)  -> 64 KB
+
+static int sph_snapshot(cwa_ctx* ctx, SphObj* s)
+{
+    GridObj* g = get_grid(ctx, s->grid);
+    BufferObj* pb = get_buffer(ctx, s->particles);
+    CWA_CHECK(g && pb, "sph: grid or particle buffer vanished");
+    CWA_TRY(grid_build_internal(ctx, g, pb->ptr, 64, s->n));
+    sph3_reorder_kernel<<<ceil_div((long long)s->n * 4, 256), 256, 0, ctx->stream>>>(
+        (const float4*)pb->ptr, g->index_list, s->n, s->posS, s->velS, s->forceS, s->miscS);
+    ctx->launches++;
+    CWA_CUDA(cudaGetLastError());
+    s->snapshot_valid = true;
+    return 0;
+}
+
+static float2* sph_scratch_rp(SphObj* s) { return reinterpret_cast<float2*>(s->packA); }
+static float4* sph_scratch_force(SphObj* s) { return s->packB; }
+
+// which: bit0 rho_pres, bit1 force, bit2 integrate.  In grid mode a full step (7) keeps every
+// intermediate in the cell-ordered snapshot and writes the SSBO once, at the end.
+int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which)
+{
+    BufferObj* pb = get_buffer(ctx, s->particles);
+    CWA_CHECK(pb, "sph: particle buffer vanished");
+    float4* aos = (float4*)pb->ptr;
+    const ParamPtrs prm = current_params(ctx);
+    const int n = s->n;
+    if (n == 0) return 0;
+
+    if (s->grid < 0) {                                             // ---- all-pairs, as shipped
+        const int blocks = ceil_div(n, AP_TT);
+        if (which & 1) {
+            sph3_density_allpairs_kernel<<<blocks, AP_TT * AP_L, 0, ctx->stream>>>(aos, n, prm, tex, sph_scratch_rp(s));
+            sph3_commit_rho_pres_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(sph_scratch_rp(s), n, aos);
+            ctx->launches += 2;
+        }
+        if (which & 2) {
+            sph3_force_allpairs_kernel<<<blocks, AP_TT * AP_L, 0, ctx->stream>>>(aos, n, prm, tex, sph_scratch_force(s));
+            sph3_commit_force_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(sph_scratch_force(s), n, aos);
+            ctx->launches += 2;
+        }
+        if (which & 4) {
+            sph3_integrate_aos_kernel<<<ceil_div((long long)n * 4, 256), 256, 0, ctx->stream>>>(aos, n, prm, tex);
+            ctx->launches++;
+        }
+        CWA_CUDA(cudaGetLastError());
+        return 0;
+    }
+
+    // ---- grid mode
+    GridObj* g = get_grid(ctx, s->grid);
+    CWA_CHECK(g && g->dim == 3, "sph: the bound grid must be a 3-D grid");
+    static bool attrs_done = false;
+    if (!attrs_done) {
+        CWA_CUDA(cudaFuncSetAttribute(sph3_density_grid_kernel<NB_P, NB_L>, cudaFuncAttributeMaxDynamicSharedMemorySize, DENS_CAP * 16));
+        CWA_CUDA(cudaFuncSetAttribute(sph3_force_grid_kernel<NB_P, NB_L>, cudaFuncAttributeMaxDynamicSharedMemorySize, FORCE_CAP * 32));
+        attrs_done = true;
+    }
+    const int blocks = ceil_div(n, NB_P);
+    const bool full = (which == 7);
+    if (which & 1) {
+        CWA_TRY(sph_snapshot(ctx, s));                             // positions changed since the last frame
+        sph3_density_grid_kernel<NB_P, NB_L><<<blocks, NB_P * NB_L, DENS_CAP * 16, ctx->stream>>>(
+            s->posS, s->velS, s->packA, s->packB, n, g->view, g->offset, prm, tex, DENS_CAP);
+        ctx->launches++;
+        if (!full) {
+            sph3_scatter_rho_pres_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(s->packA, s->packB, g->index_list, n, aos);
+            ctx->launches++;
+        }
+    }
+    if (which & 2) {
+        CWA_CHECK(s->snapshot_valid, "force pass dispatched before a density pass built the cell-ordered snapshot");
+        sph3_force_grid_kernel<NB_P, NB_L><<<blocks, NB_P * NB_L, FORCE_CAP * 32, ctx->stream>>>(
+            s->packA, s->packB, s->forceS, n, g->view, g->offset, prm, tex, FORCE_CAP);
+        ctx->launches++;
+        if (!full) {
+            sph3_scatter_force_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(s->forceS, g->index_list, n, aos);
+            ctx->launches++;
+        }
+    }
+    if (which & 4) {
+        if (full) {
+            sph3_integrate_sorted_kernel<<<ceil_div((long long)n * 4, 256), 256, 0, ctx->stream>>>(
+                s->packA, s->packB, s->forceS, s->miscS, g->index_list, n, aos, prm, tex);
+        } else {
+            sph3_integrate_aos_kernel<<<ceil_div((long long)n * 4, 256), 256, 0, ctx->stream>>>(aos, n, prm, tex);
+        }
+        ctx->launches++;
+        s->snapshot_valid = false;                                 // positions moved
+    }
+    CWA_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int cwa_sph_create(cwa_ctx* ctx, cwa_buf particles, int n, cwa_grid grid, cwa_sph* out)
+{
+    CWA_CHECK(ctx && out, "null argument");
+    *out = -1;
+    BufferObj* pb = get_buffer(ctx, particles);
+    CWA_CHECK(pb, "invalid particle buffer handle %d", particles);
+    CWA_CHECK(n >= 0 && (size_t)n * sizeof(cwa_particle) <= pb->bytes, "cwa_sph_create: buffer holds fewer than %d particles", n);
+    if (grid >= 0) {
+        GridObj* g = get_grid(ctx, grid);
+        CWA_CHECK(g && g->dim == 3, "cwa_sph_create: grid handle %d is not a 3-D grid", grid);
+        CWA_CHECK(g->max_particles >= n, "cwa_sph_create: grid capacity %d < %d particles", g->max_particles, n);
+    }
+    SphObj s;
+    s.live = true; s.particles = particles; s.n = n; s.grid = grid;
+    const size_t bytes = (size_t)(n > 0 ? n : 1) * 16;
+    CWA_CUDA(cudaMalloc(&s.packA, bytes));
+    CWA_CUDA(cudaMalloc(&s.packB, bytes));
+    if (grid >= 0) {
+        CWA_CUDA(cudaMalloc(&s.posS, bytes));
+        CWA_CUDA(cudaMalloc(&s.velS, bytes));
+        CWA_CUDA(cudaMalloc(&s.forceS, bytes));
+        CWA_CUDA(cudaMalloc(&s.miscS, bytes));
+    }
+    ctx->sphs.push_back(s);
+    *out = (int)ctx->sphs.size() - 1;
+    return 0;
+}
+
+extern "C" int cwa_sph_destroy(cwa_ctx* ctx, cwa_sph h)
+{
+    SphObj* s = get_sph(ctx, h);
+    CWA_CHECK(s, "invalid sph handle %d", h);
+    CWA_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(s->packA); cudaFree(s->packB); cudaFree(s->posS); cudaFree(s->velS); cudaFree(s->forceS); cudaFree(s->miscS);
+    s->live = false;
+    if (ctx->bound_sph == h) ctx->bound_sph = -1;
+    return 0;
+}
+
+extern "C" int cwa_sph_bind_wave(cwa_ctx* ctx, cwa_sph h, cwa_wave w, int image)
+{
+    SphObj* s = get_sph(ctx, h);
+    CWA_CHECK(s, "invalid sph handle %d", h);
+    CWA_CHECK(w == -1 || get_wave(ctx, w), "invalid wave handle %d", w);
+    CWA_CHECK(image >= -1 && image < 3, "image index %d out of range", image);
+    s->wave = w; s->wave_image = (w == -1) ? -1 : image;
+    return 0;
+}
+
+static TexView sph_current_tex(cwa_ctx* ctx, SphObj* s)
+{
+    return wave_tex_view(ctx, s->wave, s->wave_image);
+}
+
+extern "C" int cwa_sph_rho_pres(cwa_ctx* ctx, cwa_sph h)
+{
+    SphObj* s = get_sph(ctx, h);
+    CWA_CHECK(s, "invalid sph handle %d", h);
+    return sph_passes_internal(ctx, s, sph_current_tex(ctx, s), 1);
+}
+
+extern "C" int cwa_sph_force(cwa_ctx* ctx, cwa_sph h)
+{
+    SphObj* s = get_sph(ctx, h);
+    CWA_CHECK(s, "invalid sph handle %d", h);
+    return sph_passes_internal(ctx, s, sph_current_tex(ctx, s), 2);
+}
+
+extern "C" int cwa_sph_integrate(cwa_ctx* ctx, cwa_sph h)
+{
+    SphObj* s = get_sph(ctx, h);
+    CWA_CHECK(s, "invalid sph handle %d", h);
+    return sph_passes_internal(ctx, s, sph_current_tex(ctx, s), 4);
+}
+
+extern "C" int cwa_sph_step(cwa_ctx* ctx, cwa_sph h, int nsteps)
+{
+    SphObj* s = get_sph(ctx, h);
+    CWA_CHECK(s, "invalid sph handle %d", h);
+    for (int k = 0; k < nsteps; k++) CWA_TRY(sph_passes_internal(ctx, s, sph_current_tex(ctx, s), 7));
+    return 0;
+}
+
+extern "C" int cwa_sph_neighbour_count(cwa_ctx* ctx, cwa_sph h, int* host)
+{
+    SphObj* s = get_sph(ctx, h);
+    CWA_CHECK(s && host, "invalid sph handle %d", h);
+    BufferObj* pb = get_buffer(ctx, s->particles);
+    CWA_CHECK(pb, "sph: particle buffer vanished");
+    if (s->n == 0) return 0;
+    int* dout = nullptr;
+    CWA_CUDA(cudaMalloc(&dout, (size_t)s->n * 4));
+    const ParamPtrs prm = current_params(ctx);
+    if (s->grid >= 0) {
+        GridObj* g = get_grid(ctx, s->grid);
+        CWA_TRY(sph_snapshot(ctx, s));
+        sph3_neighbour_count_grid_kernel<<<ceil_div(s->n, 256), 256, 0, ctx->stream>>>(s->posS, g->index_list, s->n, g->view, g->offset, prm, dout);
+    } else {
+        sph3_neighbour_count_allpairs_kernel<<<ceil_div(s->n, 256), 256, 0, ctx->stream>>>((const float4*)pb->ptr, s->n, prm, dout);
+    }
+    ctx->launches++;
+    CWA_CUDA(cudaGetLastError());
+    CWA_CUDA(cudaMemcpyAsync(host, dout, (size_t)s->n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CWA_CUDA(cudaStreamSynchronize(ctx->stream));
+    CWA_CUDA(cudaFree(dout));
+    return 0;
+}
+
+extern "C" int cwa_sph_init_cube(cwa_ctx* ctx, cwa_sph h, int nx, int ny, int nz)
+{
+    SphObj* s = get_sph(ctx, h);
+    CWA_CHECK(s, "invalid sph handle %d", h);
+    CWA_CHECK(nx > 0 && ny > 0 && nz > 0 && (long long)nx * ny * nz == s->n, "cwa_sph_init_cube: %dx%dx%d != %d particles", nx, ny, nz, s->n);
+    BufferObj* pb = get_buffer(ctx, s->particles);
+    CWA_CHECK(pb, "sph: particle buffer vanished");
+    sph3_init_cube_kernel<<<ceil_div(s->n, 256), 256, 0, ctx->stream>>>((float4*)pb->ptr, nx, ny, nz, current_params(ctx));
+    ctx->launches++;
+    CWA_CUDA(cudaGetLastError());
+    s->snapshot_valid = false;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// coupled frame: idle() of Main.cpp:530-562 followed by the display() bind of Main.cpp:413
+// ---------------------------------------------------------------------------------------------
+extern "C" int cwa_coupled_step(cwa_ctx* ctx, cwa_sph hs, cwa_wave hw, int nframes, int coupling)
+{
+    SphObj* s = get_sph(ctx, hs);
+    WaveObj* w = get_wave(ctx, hw);
+    CWA_CHECK(s && w, "cwa_coupled_step: invalid sph (%d) or wave (%d) handle", hs, hw);
+    CWA_CHECK(coupling == CWA_COUPLING_AS_SHIPPED || coupling == CWA_COUPLING_LATEST, "unknown coupling mode %d", coupling);
+    for (int f = 0; f < nframes; f++) {
+        int image;
+        if (coupling == CWA_COUPLING_LATEST) {
+            image = -1;
+            for (int i = 0; i < 3; i++) if (w->unit[i] == 0) image = i;      // newest level = image unit 0
+        } else {
+            image = w->tex_unit0;                                            // whatever display() last bound to texture unit 0
+        }
+        s->wave = hw; s->wave_image = image;
+        CWA_TRY(sph_passes_internal(ctx, s, wave_tex_view(ctx, hw, image), 7));   // :549-557
+        if (w->evolve) CWA_TRY(wave_step_internal(ctx, w));                      // Module::sComputeAll :560
+        CWA_TRY(cwa_wave_bind_texture_unit(ctx, hw));                            // display() :413
+    }
+    return 0;
+}

@@ -1,0 +1,187 @@
+/*
+ * cwa_b200.h -- C ABI of the B200-native CoupledWaterAnimation simulation step.
+ *
+ * This is the drop-in boundary: plain C, plain pointers and sizes, no CUDA/torch types.  Each
+ * entry point names the reference interface it replaces (paths relative to the reference repo).
+ * The header-only C++ mirrors of the reference classes (Module / ComputeShader / Buffer /
+ * ImageTexture / StencilImage2DTripleBuffered / StencilBuffer / SphUgrid / UniformGridSph2D /
+ * UgridParticles3D / ParallelScan) in include/cwa/ are written on top of exactly these symbols.
+ *
+ * Conventions (mirroring the reference's GL conventions):
+ *   - every function returns 0 on success, <0 on error (text via cwa_last_error()); none throws;
+ *   - one host thread per context; calls enqueue work on the context's CUDA stream and return
+ *     without synchronising unless stated ("synchronises");
+ *   - handles are small non-negative ints, -1 is the invalid handle (the GLuint(-1) idiom);
+ *   - there is NO CPU fallback: without a CUDA device cwa_create() fails.
+ */
+#ifndef CWA_B200_H
+#define CWA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define CWA_API __declspec(dllexport)
+#else
+#define CWA_API __attribute__((visibility("default")))
+#endif
+
+typedef struct cwa_ctx cwa_ctx;
+typedef int cwa_buf;    /* Buffer                        (SphWave2D/Buffer.h:5-24)                  */
+typedef int cwa_wave;   /* StencilImage2DTripleBuffered  (StencilImage2DTripleBuffered.h:8-41)       */
+typedef int cwa_grid;   /* UniformGridSph2D / UgridParticles3D (UniformGridGpu2D.h:82-142, UniformGridParticles3D.h:50-130) */
+typedef int cwa_sph;    /* the 3 SPH compute programs + particle SSBO of Main.cpp:540-557           */
+typedef int cwa_sph2;   /* SphUgrid                      (SphWave2D/StencilBuffer.h:64-79)           */
+typedef int cwa_shader; /* ComputeShader                 (CoupledWaterAnimation/ComputeShader.h:7-39) */
+
+/* ---- structs with the reference's memory layout -------------------------------------------- */
+/* struct Particle, CoupledWaterAnimation/Main.cpp:167-173 == rho_pres_comp.glsl:14-20 (std430) */
+typedef struct { float pos[4], vel[4], force[4], extras[4]; } cwa_particle;      /* 64 B */
+/* struct Particle, SphWave2D/Main.cpp:35-40 == SphWaveKoschier2D_grid_cs.glsl:39-44 */
+typedef struct { float pos[4], vel[4], acc[4]; } cwa_particle2d;                 /* 48 B */
+/* UBO blocks, CoupledWaterAnimation/Main.cpp:184-204 (std140) */
+typedef struct { float mass, smoothing_coeff, visc, resting_rho; } cwa_constants_uniform;   /* binding 1 */
+typedef struct { float upper[4], lower[4]; } cwa_boundary_uniform;                           /* binding 2 */
+typedef struct { float attributes[4], mesh_ws_pos[4]; } cwa_wave_uniforms;                   /* binding 3 */
+/* Shader `const`s of the reference promoted to a parameter block (north-star: dt, gravity, k ...).
+ * Defaults == rho_pres_comp.glsl:5,41,43; force_comp.glsl:7,52-55; integrate_comp.glsl:8,51,69. */
+typedef struct {
+    float particle_radius, gas_const, dt, gravity_y;
+    float damping, crest_threshold, foam_speed, uv_scale;
+} cwa_sim_constants;                                                                         /* binding 4 (extension) */
+/* UniformGridInfo: 2-D SphWave2D/UniformGridGpu2D.h:89-94, 3-D UniformGrid2D/UniformGridParticles3D.h:60-67 */
+typedef struct { float min[4], max[4]; int num_cells[4]; float cell_size[4]; } cwa_grid_info;
+
+enum { CWA_TARGET_SSBO = 0, CWA_TARGET_UBO = 1 };
+enum { CWA_UBO_SCENE = 0, CWA_UBO_CONSTANTS = 1, CWA_UBO_BOUNDARY = 2, CWA_UBO_WAVE = 3, CWA_UBO_SIM = 4 };
+/* StencilImage2DTripleBuffered.h:26-29 */
+enum { CWA_MODE_INIT = 0, CWA_MODE_INIT_FROM_TEXTURE = 1, CWA_MODE_EVOLVE = 2, CWA_MODE_TEST = 10 };
+/* which wave shader the stencil object runs: wave_comp.glsl or Wave2DSimp/Wave2D_cs.glsl */
+enum { CWA_WAVE_COUPLED = 0, CWA_WAVE_SIMP = 1 };
+/* SPH<-wave sampling schedule: as shipped (stale texture-unit-0 binding) or newest */
+enum { CWA_COUPLING_AS_SHIPPED = 0, CWA_COUPLING_LATEST = 1 };
+/* neighbour search of the 3-D passes: all-pairs as shipped (rho_pres_comp.glsl:60) or uniform grid */
+enum { CWA_NEIGHBOURS_ALL_PAIRS = 0, CWA_NEIGHBOURS_GRID = 1 };
+enum { CWA_SPH2_KOSCHIER = 0, CWA_SPH2_WAVE = 1 };
+enum { CWA_GRID_COUNTER = 0, CWA_GRID_OFFSET = 1, CWA_GRID_INDEX_LIST = 2, CWA_GRID_CELL_OF = 3 };
+
+/* ---- context --------------------------------------------------------------------------------- */
+CWA_API const char* cwa_last_error(void);
+CWA_API int  cwa_version(void);
+CWA_API int  cwa_create(int device, cwa_ctx** out);                 /* replaces glfw/glew context setup, Main.cpp:990-1019 */
+CWA_API void cwa_destroy(cwa_ctx* ctx);
+CWA_API int  cwa_synchronize(cwa_ctx* ctx);                         /* glFinish */
+CWA_API void* cwa_stream(cwa_ctx* ctx);                             /* cudaStream_t the context enqueues on */
+CWA_API int  cwa_device_info(cwa_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
+/* device-side timing on the context stream (cudaEvent): used by bench.py for per-kernel roofline */
+CWA_API int  cwa_timer_begin(cwa_ctx* ctx);
+CWA_API int  cwa_timer_end(cwa_ctx* ctx, float* ms);                /* synchronises */
+/* number of kernels this library launched (graph replays count their kernel nodes) */
+CWA_API unsigned long long cwa_launch_count(cwa_ctx* ctx);
+
+/* ---- Buffer: Init / BufferSubData / BindBufferBase / DebugRead*  (SphWave2D/Buffer.cpp:5-83) -- */
+CWA_API int cwa_buffer_create(cwa_ctx* ctx, size_t bytes, const void* host_or_null, cwa_buf* out); /* glNamedBufferStorage */
+CWA_API int cwa_buffer_wrap(cwa_ctx* ctx, void* device_ptr, size_t bytes, cwa_buf* out);            /* external memory (CUDA-GL interop map, torch) */
+CWA_API int cwa_buffer_destroy(cwa_ctx* ctx, cwa_buf b);                                             /* glDeleteBuffers */
+CWA_API int cwa_buffer_sub_data(cwa_ctx* ctx, cwa_buf b, size_t off, size_t bytes, const void* host);/* glNamedBufferSubData */
+CWA_API int cwa_buffer_read(cwa_ctx* ctx, cwa_buf b, size_t off, size_t bytes, void* host);          /* glGetNamedBufferSubData; synchronises */
+CWA_API int cwa_buffer_copy(cwa_ctx* ctx, cwa_buf src, cwa_buf dst, size_t soff, size_t doff, size_t bytes); /* glCopyNamedBufferSubData */
+CWA_API int cwa_buffer_bind_base(cwa_ctx* ctx, int target, int binding, cwa_buf b);                  /* glBindBufferBase */
+CWA_API int cwa_buffer_device_ptr(cwa_ctx* ctx, cwa_buf b, void** ptr, size_t* bytes);
+/* the context's own parameter blocks (created with the reference defaults, bound at UBO 1..4) */
+CWA_API int cwa_default_ubo(cwa_ctx* ctx, int binding, cwa_buf* out);
+
+/* ---- ParallelScan::Compute (SphWave2D/ParallelScan.cpp:43-95 + prefix_sum_cs.glsl) ------------ */
+/* exclusive prefix sum of n int32 (any n >= 1; the reference asserts n is a power of two) */
+CWA_API int cwa_scan_exclusive(cwa_ctx* ctx, cwa_buf in, cwa_buf out, int n);
+
+/* ---- uniform grid: ctor / Init / CollisionQuery|BuildGrid ------------------------------------- */
+/* dim = 2: UniformGridSph2D (UniformGridGpu2D.cpp:156-265, uniform_grid_sph_cs.glsl)
+ * dim = 3: UgridParticles3D (UniformGridParticles3D.cpp:92-211, ugrid_particles_cs.glsl) */
+CWA_API int cwa_grid_create(cwa_ctx* ctx, int dim, const float* mn, const float* mx, const int* num_cells,
+                            int max_particles, cwa_grid* out);
+CWA_API int cwa_grid_destroy(cwa_ctx* ctx, cwa_grid g);
+CWA_API int cwa_grid_get_info(cwa_ctx* ctx, cwa_grid g, cwa_grid_info* out, int* num_cells_total);
+/* build over n particles whose pos vec4 sits at byte offset 0 of each `stride_bytes` record */
+CWA_API int cwa_grid_build(cwa_ctx* ctx, cwa_grid g, cwa_buf particles, int stride_bytes, int n);
+/* which = CWA_GRID_*; counts ints copied to host; synchronises (DebugReadInt) */
+CWA_API int cwa_grid_read(cwa_ctx* ctx, cwa_grid g, int which, int* host, int count);
+CWA_API int cwa_grid_buffer(cwa_ctx* ctx, cwa_grid g, int which, cwa_buf* out);   /* mGridCounter / mGridOffset / mIndexList as Buffers */
+
+/* ---- StencilImage2DTripleBuffered: Init / Reinit / ReinitFromTexture / Compute / PingPong ------ */
+CWA_API int cwa_wave_create(cwa_ctx* ctx, int w, int h, int channels /*1 scalar | 4 RGBA32F*/, int variant, cwa_wave* out); /* Init() :10-31 (runs Reinit) */
+CWA_API int cwa_wave_destroy(cwa_ctx* ctx, cwa_wave w);
+CWA_API int cwa_wave_reinit(cwa_ctx* ctx, cwa_wave w);                                   /* Reinit() :42-59 */
+CWA_API int cwa_wave_reinit_from_texture(cwa_ctx* ctx, cwa_wave w, const float* rgba, int tw, int th); /* ReinitFromTexture :61-77 */
+CWA_API int cwa_wave_compute(cwa_ctx* ctx, cwa_wave w, int nsteps);                      /* Compute() :79-95, nsteps times */
+CWA_API int cwa_wave_pingpong(cwa_ctx* ctx, cwa_wave w);                                 /* PingPong() :33-40 */
+CWA_API int cwa_wave_set_evolve(cwa_ctx* ctx, cwa_wave w, int evolve);                   /* mEvolve checkbox */
+CWA_API int cwa_wave_set_params(cwa_ctx* ctx, cwa_wave w, float lambda, float atten, float beta); /* Wave2D_cs.glsl:17-19 uniforms (variant SIMP) */
+CWA_API int cwa_wave_resize(cwa_ctx* ctx, cwa_wave w, int nw, int nh);                   /* DrawGui "Apply" :117-123 */
+/* state of the rotation, as the reference exposes it: indices (GetReadImage(i)/GetWriteImage) and units */
+CWA_API int cwa_wave_state(cwa_ctx* ctx, cwa_wave w, int read_index[2], int* write_index, int unit[3], int* tex_unit0_image);
+/* display(): wave2d.GetReadImage(0).BindTextureUnit() -- binds at that image's mUnit (Main.cpp:413, F5) */
+CWA_API int cwa_wave_bind_texture_unit(cwa_ctx* ctx, cwa_wave w);
+/* image by physical index 0..2 (ImageTexture), or by role: 0 newest, 1 previous, 2 next output */
+CWA_API int cwa_wave_read_image(cwa_ctx* ctx, cwa_wave w, int image, float* host);       /* synchronises */
+CWA_API int cwa_wave_write_image(cwa_ctx* ctx, cwa_wave w, int image, const float* host);
+CWA_API int cwa_wave_role_image(cwa_ctx* ctx, cwa_wave w, int role, int* image);
+CWA_API int cwa_wave_image_buffer(cwa_ctx* ctx, cwa_wave w, int image, cwa_buf* out);    /* GetTexture() for interop */
+CWA_API int cwa_wave_size(cwa_ctx* ctx, cwa_wave w, int* width, int* height, int* channels);
+
+/* ---- 3-D SPH passes on the particle SSBO (Main.cpp:540-557) ------------------------------------ */
+/* particles: cwa_particle[n] buffer (SSBO binding 0).  grid = -1 -> all-pairs as shipped. */
+CWA_API int cwa_sph_create(cwa_ctx* ctx, cwa_buf particles, int n, cwa_grid grid, cwa_sph* out);
+CWA_API int cwa_sph_destroy(cwa_ctx* ctx, cwa_sph s);
+/* sampler unit 0 for the SPH passes: an image of `w` (physical index) or -1 = unbound (samples 0) */
+CWA_API int cwa_sph_bind_wave(cwa_ctx* ctx, cwa_sph s, cwa_wave w, int image);
+CWA_API int cwa_sph_rho_pres(cwa_ctx* ctx, cwa_sph s);      /* compute_programs[0]: rho_pres_comp.glsl  */
+CWA_API int cwa_sph_force(cwa_ctx* ctx, cwa_sph s);         /* compute_programs[1]: force_comp.glsl     */
+CWA_API int cwa_sph_integrate(cwa_ctx* ctx, cwa_sph s);     /* compute_programs[2]: integrate_comp.glsl */
+CWA_API int cwa_sph_step(cwa_ctx* ctx, cwa_sph s, int nsteps); /* the three passes, fused schedule */
+/* per-particle neighbour counts (r < h, self included) of the current positions; synchronises */
+CWA_API int cwa_sph_neighbour_count(cwa_ctx* ctx, cwa_sph s, int* host);
+/* make_cube + init_particles (Main.cpp:735-776) generalised to nx*ny*nz; writes the bound SSBO */
+CWA_API int cwa_sph_init_cube(cwa_ctx* ctx, cwa_sph s, int nx, int ny, int nz);
+
+/* ---- per-frame entry points named by the north-star ------------------------------------------- */
+/* idle() of Main.cpp:530-562 + the display() texture bind: nframes x (rho, force, integrate, wave) */
+CWA_API int cwa_coupled_step(cwa_ctx* ctx, cwa_sph s, cwa_wave w, int nframes, int coupling);
+/* bind the objects sph_step / wave_step act on (the globals of Main.cpp:74-75) */
+CWA_API int cwa_bind_scene(cwa_ctx* ctx, cwa_sph s, cwa_wave w);
+CWA_API int sph_step(cwa_ctx* ctx, int nsteps);             /* ComputeShader::Dispatch x3 -> one call */
+CWA_API int wave_step(cwa_ctx* ctx, int nsteps);            /* StencilImage2DTripleBuffered::Compute   */
+
+/* ---- 2-D Koschier SPH on the uniform grid: SphUgrid (SphWave2D/StencilBuffer.cpp:138-179) ------ */
+CWA_API int cwa_sph2_create(cwa_ctx* ctx, int n, int variant, cwa_grid grid, cwa_sph2* out); /* Init + Reinit (MODE_INIT) */
+CWA_API int cwa_sph2_destroy(cwa_ctx* ctx, cwa_sph2 s);
+CWA_API int cwa_sph2_reinit(cwa_ctx* ctx, cwa_sph2 s);                                   /* StencilBuffer::Reinit :38-51 */
+CWA_API int cwa_sph2_set_substeps(cwa_ctx* ctx, cwa_sph2 s, int substeps);               /* SetSubsteps */
+CWA_API int cwa_sph2_set_uniforms(cwa_ctx* ctx, cwa_sph2 s, float time, float bottom, float psi /*<0: default*/, int init_width);
+CWA_API int cwa_sph2_set_view_width(cwa_ctx* ctx, cwa_sph2 s, float view_width);        /* shader const VIEW_WIDTH = 9.6 (extension: wider tanks for C2) */
+CWA_API int cwa_sph2_bind_wave1d(cwa_ctx* ctx, cwa_sph2 s, cwa_buf rgba_or_minus1, int width); /* sampler1D wave_tex, unit 0 */
+CWA_API int cwa_sph2_compute(cwa_ctx* ctx, cwa_sph2 s, int nframes);                     /* SphUgrid::Compute */
+CWA_API int cwa_sph2_read(cwa_ctx* ctx, cwa_sph2 s, cwa_particle2d* host);               /* GetReadBuffer(); synchronises */
+CWA_API int cwa_sph2_write(cwa_ctx* ctx, cwa_sph2 s, const cwa_particle2d* host);
+CWA_API int cwa_sph2_read_buffer(cwa_ctx* ctx, cwa_sph2 s, cwa_buf* out);
+
+/* ---- ComputeShader: Init / SetMode / SetGridSize / Dispatch (ComputeShader.cpp:9-56) ----------- */
+/* glsl_filename selects the CUDA kernel set that replaces that shader; unknown names fail like
+ * InitShader() returning -1.  Dispatch acts on the currently bound buffers/images like
+ * glDispatchCompute.  Supported: rho_pres_comp.glsl, force_comp.glsl, integrate_comp.glsl,
+ * wave_comp.glsl, Wave2D_cs.glsl, prefix_sum_cs.glsl. */
+CWA_API int cwa_shader_create(cwa_ctx* ctx, const char* glsl_filename, cwa_shader* out);
+CWA_API int cwa_shader_set_mode(cwa_ctx* ctx, cwa_shader s, int mode);
+CWA_API int cwa_shader_set_uniform_i(cwa_ctx* ctx, cwa_shader s, int location, int v);
+CWA_API int cwa_shader_set_uniform_f(cwa_ctx* ctx, cwa_shader s, int location, float v);
+CWA_API int cwa_shader_bind_object(cwa_ctx* ctx, cwa_shader s, int object_handle);       /* the cwa_sph / cwa_wave it drives */
+CWA_API int cwa_shader_dispatch(cwa_ctx* ctx, cwa_shader s, int gx, int gy, int gz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CWA_B200_H */
