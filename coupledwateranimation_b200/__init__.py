@@ -97,6 +97,16 @@ class Context:
     def launch_count(self) -> int:
         return int(self.lib.cwa_launch_count(self.h))
 
+    def profile_begin(self):
+        check(self.lib.cwa_profile_begin(self.h))
+
+    def profile_end(self) -> dict:
+        """{kernel name: (total ms, launches)} for every launch since profile_begin()."""
+        k = self.lib.cwa_profile_kernel_count()
+        ms = (C.c_float * k)(); cnt = (C.c_int * k)()
+        check(self.lib.cwa_profile_end(self.h, ms, cnt, k))
+        return {self.lib.cwa_profile_kernel_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(k) if cnt[i] > 0}
+
     # -- parameter blocks (UBO bindings 1..4) -----------------------------------------------------
     def default_ubo(self, binding: int) -> "Buffer":
         b = C.c_int()

@@ -54,6 +54,10 @@ SIGNATURES = {
     "cwa_timer_begin": (_I, [_P]),
     "cwa_timer_end": (_I, [_P, C.POINTER(_F)]),
     "cwa_launch_count": (C.c_ulonglong, [_P]),
+    "cwa_profile_kernel_count": (_I, []),
+    "cwa_profile_kernel_name": (C.c_char_p, [_I]),
+    "cwa_profile_begin": (_I, [_P]),
+    "cwa_profile_end": (_I, [_P, C.POINTER(_F), _IP, _I]),
     "cwa_buffer_create": (_I, [_P, _Z, _P, _IP]),
     "cwa_buffer_wrap": (_I, [_P, _P, _Z, _IP]),
     "cwa_buffer_destroy": (_I, [_P, _I]),

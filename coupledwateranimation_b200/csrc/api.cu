@@ -194,6 +194,40 @@ extern "C" int cwa_timer_end(cwa_ctx* ctx, float* ms)
 
 extern "C" unsigned long long cwa_launch_count(cwa_ctx* ctx) { return ctx ? ctx->launches : 0ull; }
 
+// per-kernel device timing (CUDA-event pairs around every launch on the context stream)
+static const char* const g_kernel_names[KID_COUNT] = {
+    "clear(memset)", "grid_hash_count", "scan_lookback", "grid_insert", "grid_cell_order", "reorder",
+    "density", "force", "integrate", "wave_evolve", "other"};
+
+extern "C" int cwa_profile_kernel_count(void) { return KID_COUNT; }
+extern "C" const char* cwa_profile_kernel_name(int id) { return (id >= 0 && id < KID_COUNT) ? g_kernel_names[id] : ""; }
+
+extern "C" int cwa_profile_begin(cwa_ctx* ctx)
+{
+    CWA_CHECK(ctx, "null context");
+    CWA_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (auto& r : ctx->prof) { ctx->ev_pool.push_back(r.a); ctx->ev_pool.push_back(r.b); }
+    ctx->prof.clear();
+    ctx->profiling = true;
+    return 0;
+}
+
+extern "C" int cwa_profile_end(cwa_ctx* ctx, float* ms, int* launches, int cap)
+{
+    CWA_CHECK(ctx && ms && launches && cap >= KID_COUNT, "cwa_profile_end: need arrays of %d entries", KID_COUNT);
+    ctx->profiling = false;
+    CWA_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < cap; i++) { ms[i] = 0.0f; launches[i] = 0; }
+    for (auto& r : ctx->prof) {
+        float t = 0.0f;
+        CWA_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+        ms[r.id] += t; launches[r.id]++;
+        ctx->ev_pool.push_back(r.a); ctx->ev_pool.push_back(r.b);
+    }
+    ctx->prof.clear();
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Buffer  (SphWave2D/Buffer.cpp:5-83)
 // ---------------------------------------------------------------------------------------------

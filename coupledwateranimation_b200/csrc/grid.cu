@@ -176,8 +176,8 @@ int scan_exclusive_launch(cwa_ctx* ctx, const int* in, int* out, int n, int* tic
     const int write_total = n > 0;
     if (n < 0) n = -n;
     const int tiles = (int)scan_num_tiles(n);
-    scan_lookback_kernel<<<tiles, SCAN_THREADS, 0, ctx->stream>>>(in, out, n, write_total, ticket, tile_state);
-    ctx->launches++;
+    { KScope k(ctx, KID_SCAN);
+      scan_lookback_kernel<<<tiles, SCAN_THREADS, 0, ctx->stream>>>(in, out, n, write_total, ticket, tile_state); }
     CWA_CUDA(cudaGetLastError());
     return 0;
 }
@@ -205,8 +205,8 @@ __global__ void prefix_sum_level_kernel(int* x, int n, int phase, int stride, in
 int prefix_sum_level_launch(cwa_ctx* ctx, int* x, int n, int phase, int stride, int nthreads)
 {
     CWA_CHECK(n >= 2 && stride >= 2 && nthreads >= 1, "prefix_sum_cs: bad uniforms n=%d stride=%d", n, stride);
-    prefix_sum_level_kernel<<<ceil_div(nthreads, 256), 256, 0, ctx->stream>>>(x, n, phase, stride, nthreads);
-    ctx->launches++;
+    { KScope k(ctx, KID_OTHER);
+      prefix_sum_level_kernel<<<ceil_div(nthreads, 256), 256, 0, ctx->stream>>>(x, n, phase, stride, nthreads); }
     CWA_CUDA(cudaGetLastError());
     return 0;
 }
@@ -268,23 +268,24 @@ int grid_build_internal(cwa_ctx* ctx, GridObj* g, const void* particles, int str
     CWA_CHECK(n >= 0 && n <= g->max_particles, "grid build: %d particles exceed the grid's capacity %d", n, g->max_particles);
     CWA_CHECK(stride_bytes >= 16 && stride_bytes % 16 == 0, "grid build: particle stride must be a multiple of 16 bytes");
     g->n_built = n;
-    CWA_CUDA(cudaMemsetAsync(g->counter, 0, g->clear_bytes, ctx->stream));      // ClearCounter + scan state, one memset
+    { KScope k(ctx, KID_CLEAR);                                                // ClearCounter + scan state, one memset
+      CWA_CUDA(cudaMemsetAsync(g->counter, 0, g->clear_bytes, ctx->stream)); }
     const int C = g->view.num_cells;
     if (n > 0) {
+        KScope k(ctx, KID_HASH_COUNT);
         if (g->dim == 2)
             grid_hash_count_kernel<2><<<ceil_div(n, 256), 256, 0, ctx->stream>>>((const char*)particles, stride_bytes, n, g->view, g->counter, g->cell_of, g->rank);
         else
             grid_hash_count_kernel<3><<<ceil_div(n, 256), 256, 0, ctx->stream>>>((const char*)particles, stride_bytes, n, g->view, g->counter, g->cell_of, g->rank);
-        ctx->launches++;
         CWA_CUDA(cudaGetLastError());
     }
     CWA_TRY(scan_exclusive_launch(ctx, g->counter, g->offset, C, g->ticket, g->tile_state));
     if (n > 0) {
-        grid_insert_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(g->cell_of, g->rank, g->offset, n, g->index_list);
-        ctx->launches++;
+        { KScope k(ctx, KID_INSERT);
+          grid_insert_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(g->cell_of, g->rank, g->offset, n, g->index_list); }
         CWA_CUDA(cudaGetLastError());
-        grid_cell_order_kernel<<<ceil_div(C, 256), 256, 0, ctx->stream>>>(g->offset, C, g->index_list);
-        ctx->launches++;
+        { KScope k(ctx, KID_CELL_ORDER);
+          grid_cell_order_kernel<<<ceil_div(C, 256), 256, 0, ctx->stream>>>(g->offset, C, g->index_list); }
         CWA_CUDA(cudaGetLastError());
     }
     return 0;

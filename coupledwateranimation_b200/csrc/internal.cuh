@@ -149,7 +149,18 @@ struct ShaderObj {
     float uf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
+// kernels of the hot path, as reported by the per-kernel profile (bench.py roofline section)
+enum KernelId {
+    KID_CLEAR = 0, KID_HASH_COUNT, KID_SCAN, KID_INSERT, KID_CELL_ORDER, KID_REORDER,
+    KID_DENSITY, KID_FORCE, KID_INTEGRATE, KID_WAVE, KID_OTHER, KID_COUNT
+};
+
+struct ProfRec { int id; cudaEvent_t a, b; };
+
 struct cwa_ctx {
+    bool profiling = false;
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> ev_pool;
     int device = 0;
     int sm_count = 148;
     int cc_major = 0, cc_minor = 0;
@@ -195,6 +206,26 @@ int  wave_dispatch_mode(cwa_ctx* ctx, WaveObj* w, int mode);           // kernel
 int  sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which /*bit0 rho, bit1 force, bit2 integrate*/);
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// RAII bracket around one launch (or memset): counts it and, while a profile is being taken,
+// records a CUDA-event pair on the launching stream.
+struct KScope {
+    cwa_ctx* ctx; int slot;
+    KScope(cwa_ctx* c, int id) : ctx(c), slot(-1)
+    {
+        ctx->launches++;
+        if (!ctx->profiling) return;
+        cudaEvent_t e[2];
+        for (int k = 0; k < 2; k++) {
+            if (!ctx->ev_pool.empty()) { e[k] = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); }
+            else cudaEventCreate(&e[k]);
+        }
+        cudaEventRecord(e[0], ctx->stream);
+        slot = (int)ctx->prof.size();
+        ctx->prof.push_back(ProfRec{id, e[0], e[1]});
+    }
+    ~KScope() { if (slot >= 0) cudaEventRecord(ctx->prof[slot].b, ctx->stream); }
+};
 
 // ---------------------------------------------------------------------------------------------
 // device helpers shared by the kernels

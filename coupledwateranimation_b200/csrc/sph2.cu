@@ -304,8 +304,8 @@ extern "C" int cwa_sph2_reinit(cwa_ctx* ctx, cwa_sph2 h)
     BufferObj* wb = get_buffer(ctx, s->buffer[s->write_index]);
     CWA_CHECK(wb, "sph2: buffer vanished");
     CWA_CHECK(s->init_width > 0 && s->n / s->init_width > 0, "sph2: init lattice width %d does not fit %d particles", s->init_width, s->n);
-    sph2_init_kernel<<<ceil_div(s->n, 256), 256, 0, ctx->stream>>>((float4*)wb->ptr, s->n, sph2_params(ctx, s));   // MODE_INIT :43-48
-    ctx->launches++;
+    { KScope k(ctx, KID_OTHER);
+      sph2_init_kernel<<<ceil_div(s->n, 256), 256, 0, ctx->stream>>>((float4*)wb->ptr, s->n, sph2_params(ctx, s)); }   // MODE_INIT :43-48
     CWA_CUDA(cudaGetLastError());
     sph2_pingpong(s);                                                        // :50
     return 0;
@@ -393,18 +393,23 @@ extern "C" int cwa_sph2_compute(cwa_ctx* ctx, cwa_sph2 h, int nframes)
             const float4* rd = (const float4*)get_buffer(ctx, s->buffer[s->read_index])->ptr;
             float4* wr = (float4*)get_buffer(ctx, s->buffer[s->write_index])->ptr;
             CWA_TRY(grid_build_internal(ctx, g, rd, 48, n));                 // mGrid.CollisionQuery() :163-164
-            sph2_reorder_kernel<<<ceil_div((long long)n * 3, 256), 256, 0, ctx->stream>>>(rd, g->index_list, g->offset, g->view.num_cells, s->posS, s->velS, s->accS);
-            for (int tail = 0; tail < 2; tail++)                             // mode 1 :169-176
+            { KScope k(ctx, KID_REORDER);
+              sph2_reorder_kernel<<<ceil_div((long long)n * 3, 256), 256, 0, ctx->stream>>>(rd, g->index_list, g->offset, g->view.num_cells, s->posS, s->velS, s->accS); }
+            for (int tail = 0; tail < 2; tail++) {                           // mode 1 :169-176
+                KScope k(ctx, KID_DENSITY);
                 sph2_density_kernel<<<blocks, 128, 0, ctx->stream>>>(rd, wr, n, g->view, g->offset, g->index_list, g->cell_of, s->posS, prm, tail);
+            }
             sph2_pingpong(s);
             rd = (const float4*)get_buffer(ctx, s->buffer[s->read_index])->ptr;
             wr = (float4*)get_buffer(ctx, s->buffer[s->write_index])->ptr;
             // mode 2 reads the density output through the SAME (now stale) grid lists
-            sph2_reorder_kernel<<<ceil_div((long long)n * 3, 256), 256, 0, ctx->stream>>>(rd, g->index_list, g->offset, g->view.num_cells, s->posS, s->velS, s->accS);
-            for (int tail = 0; tail < 2; tail++)
+            { KScope k(ctx, KID_REORDER);
+              sph2_reorder_kernel<<<ceil_div((long long)n * 3, 256), 256, 0, ctx->stream>>>(rd, g->index_list, g->offset, g->view.num_cells, s->posS, s->velS, s->accS); }
+            for (int tail = 0; tail < 2; tail++) {
+                KScope k(ctx, KID_FORCE);
                 sph2_forces_kernel<<<blocks, 128, 0, ctx->stream>>>(rd, wr, n, g->view, g->offset, g->index_list, g->cell_of, s->posS, s->velS, s->accS, prm, tail);
+            }
             sph2_pingpong(s);
-            ctx->launches += 6;
         }
     }
     CWA_CUDA(cudaGetLastError());

@@ -689,9 +689,9 @@ static int sph_snapshot(cwa_ctx* ctx, SphObj* s)
     BufferObj* pb = get_buffer(ctx, s->particles);
     CWA_CHECK(g && pb, "sph: grid or particle buffer vanished");
     CWA_TRY(grid_build_internal(ctx, g, pb->ptr, 64, s->n));
-    sph3_reorder_kernel<<<ceil_div((long long)s->n * 4, 256), 256, 0, ctx->stream>>>(
-        (const float4*)pb->ptr, g->index_list, s->n, s->posS, s->velS, s->forceS, s->miscS);
-    ctx->launches++;
+    { KScope k(ctx, KID_REORDER);
+      sph3_reorder_kernel<<<ceil_div((long long)s->n * 4, 256), 256, 0, ctx->stream>>>(
+          (const float4*)pb->ptr, g->index_list, s->n, s->posS, s->velS, s->forceS, s->miscS); }
     CWA_CUDA(cudaGetLastError());
     s->snapshot_valid = true;
     return 0;
@@ -714,18 +714,20 @@ int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which)
     if (s->grid < 0) {                                             // ---- all-pairs, as shipped
         const int blocks = ceil_div(n, AP_TT);
         if (which & 1) {
-            sph3_density_allpairs_kernel<<<blocks, AP_TT * AP_L, 0, ctx->stream>>>(aos, n, prm, tex, sph_scratch_rp(s));
-            sph3_commit_rho_pres_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(sph_scratch_rp(s), n, aos);
-            ctx->launches += 2;
+            { KScope k(ctx, KID_DENSITY);
+              sph3_density_allpairs_kernel<<<blocks, AP_TT * AP_L, 0, ctx->stream>>>(aos, n, prm, tex, sph_scratch_rp(s)); }
+            { KScope k(ctx, KID_OTHER);
+              sph3_commit_rho_pres_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(sph_scratch_rp(s), n, aos); }
         }
         if (which & 2) {
-            sph3_force_allpairs_kernel<<<blocks, AP_TT * AP_L, 0, ctx->stream>>>(aos, n, prm, tex, sph_scratch_force(s));
-            sph3_commit_force_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(sph_scratch_force(s), n, aos);
-            ctx->launches += 2;
+            { KScope k(ctx, KID_FORCE);
+              sph3_force_allpairs_kernel<<<blocks, AP_TT * AP_L, 0, ctx->stream>>>(aos, n, prm, tex, sph_scratch_force(s)); }
+            { KScope k(ctx, KID_OTHER);
+              sph3_commit_force_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(sph_scratch_force(s), n, aos); }
         }
         if (which & 4) {
+            KScope k(ctx, KID_INTEGRATE);
             sph3_integrate_aos_kernel<<<ceil_div((long long)n * 4, 256), 256, 0, ctx->stream>>>(aos, n, prm, tex);
-            ctx->launches++;
         }
         CWA_CUDA(cudaGetLastError());
         return 0;
@@ -744,32 +746,32 @@ int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which)
     const bool full = (which == 7);
     if (which & 1) {
         CWA_TRY(sph_snapshot(ctx, s));                             // positions changed since the last frame
-        sph3_density_grid_kernel<NB_P, NB_L><<<blocks, NB_P * NB_L, DENS_CAP * 16, ctx->stream>>>(
-            s->posS, s->velS, s->packA, s->packB, n, g->view, g->offset, prm, tex, DENS_CAP);
-        ctx->launches++;
+        { KScope k(ctx, KID_DENSITY);
+          sph3_density_grid_kernel<NB_P, NB_L><<<blocks, NB_P * NB_L, DENS_CAP * 16, ctx->stream>>>(
+              s->posS, s->velS, s->packA, s->packB, n, g->view, g->offset, prm, tex, DENS_CAP); }
         if (!full) {
+            KScope k(ctx, KID_OTHER);
             sph3_scatter_rho_pres_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(s->packA, s->packB, g->index_list, n, aos);
-            ctx->launches++;
         }
     }
     if (which & 2) {
         CWA_CHECK(s->snapshot_valid, "force pass dispatched before a density pass built the cell-ordered snapshot");
-        sph3_force_grid_kernel<NB_P, NB_L><<<blocks, NB_P * NB_L, FORCE_CAP * 32, ctx->stream>>>(
-            s->packA, s->packB, s->forceS, n, g->view, g->offset, prm, tex, FORCE_CAP);
-        ctx->launches++;
+        { KScope k(ctx, KID_FORCE);
+          sph3_force_grid_kernel<NB_P, NB_L><<<blocks, NB_P * NB_L, FORCE_CAP * 32, ctx->stream>>>(
+              s->packA, s->packB, s->forceS, n, g->view, g->offset, prm, tex, FORCE_CAP); }
         if (!full) {
+            KScope k(ctx, KID_OTHER);
             sph3_scatter_force_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(s->forceS, g->index_list, n, aos);
-            ctx->launches++;
         }
     }
     if (which & 4) {
+        KScope k(ctx, KID_INTEGRATE);
         if (full) {
             sph3_integrate_sorted_kernel<<<ceil_div((long long)n * 4, 256), 256, 0, ctx->stream>>>(
                 s->packA, s->packB, s->forceS, s->miscS, g->index_list, n, aos, prm, tex);
         } else {
             sph3_integrate_aos_kernel<<<ceil_div((long long)n * 4, 256), 256, 0, ctx->stream>>>(aos, n, prm, tex);
         }
-        ctx->launches++;
         s->snapshot_valid = false;                                 // positions moved
     }
     CWA_CUDA(cudaGetLastError());

@@ -318,6 +318,9 @@ int wave_dispatch_mode(cwa_ctx* ctx, WaveObj* w, int mode)
     const int in0 = image_with_unit(w, 0), in1 = image_with_unit(w, 1), outi = image_with_unit(w, 2);
     const dim3 gblock(256), ggrid(ceil_div(w->w, 32), ceil_div(w->h, 8));
     const float4* attr = wave_attr_ptr(ctx, w);
+    if (mode == CWA_MODE_TEST) return 0;                           // MODE_TEST does nothing (wave_comp.glsl:71-72)
+    CWA_CHECK(mode == CWA_MODE_INIT || mode == CWA_MODE_EVOLVE, "wave dispatch: unsupported uMode %d", mode);
+    KScope kscope(ctx, mode == CWA_MODE_EVOLVE ? KID_WAVE : KID_OTHER);
     if (mode == CWA_MODE_INIT) {
         wave_init_kernel<<<ggrid, gblock, 0, ctx->stream>>>(w->image[outi], w->w, w->h, w->ch, attr, w->variant);
     } else if (mode == CWA_MODE_EVOLVE) {
@@ -337,12 +340,7 @@ int wave_dispatch_mode(cwa_ctx* ctx, WaveObj* w, int mode)
             wave_evolve_generic_kernel<<<ggrid, gblock, 0, ctx->stream>>>(w->image[in0], w->image[in1], w->image[outi],
                                                                          w->w, w->h, w->ch, attr, w->variant);
         }
-    } else if (mode == CWA_MODE_TEST) {
-        return 0;                                                  // MODE_TEST does nothing (wave_comp.glsl:71-72)
-    } else {
-        CWA_CHECK(false, "wave dispatch: unsupported uMode %d", mode);
     }
-    ctx->launches++;
     CWA_CUDA(cudaGetLastError());
     return 0;
 }
@@ -416,9 +414,9 @@ extern "C" int cwa_wave_reinit_from_texture(cwa_ctx* ctx, cwa_wave h, const floa
     CWA_CUDA(cudaMemcpyAsync(dtex, rgba, bytes, cudaMemcpyHostToDevice, ctx->stream));
     const int outi = image_with_unit(w, 2);
     const dim3 gblock(256), ggrid(ceil_div(w->w, 32), ceil_div(w->h, 8));
-    wave_init_from_texture_kernel<<<ggrid, gblock, 0, ctx->stream>>>(w->image[outi], w->w, w->h, w->ch, dtex, tw, th,
-                                                                    w->variant == CWA_WAVE_COUPLED ? 2 : 1);
-    ctx->launches++;
+    { KScope k(ctx, KID_OTHER);
+      wave_init_from_texture_kernel<<<ggrid, gblock, 0, ctx->stream>>>(w->image[outi], w->w, w->h, w->ch, dtex, tw, th,
+                                                                      w->variant == CWA_WAVE_COUPLED ? 2 : 1); }
     CWA_CUDA(cudaGetLastError());
     CWA_CUDA(cudaStreamSynchronize(ctx->stream));
     CWA_CUDA(cudaFree(dtex));

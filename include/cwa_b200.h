@@ -82,6 +82,12 @@ CWA_API int  cwa_timer_begin(cwa_ctx* ctx);
 CWA_API int  cwa_timer_end(cwa_ctx* ctx, float* ms);                /* synchronises */
 /* number of kernels this library launched (graph replays count their kernel nodes) */
 CWA_API unsigned long long cwa_launch_count(cwa_ctx* ctx);
+/* per-kernel device time: every launch between begin/end is bracketed by a CUDA-event pair on the
+ * context stream (the GpuTimer of SphWave2D/Timer.cpp:30-72, per kernel instead of per frame) */
+CWA_API int  cwa_profile_kernel_count(void);
+CWA_API const char* cwa_profile_kernel_name(int id);
+CWA_API int  cwa_profile_begin(cwa_ctx* ctx);
+CWA_API int  cwa_profile_end(cwa_ctx* ctx, float* ms, int* launches, int cap);   /* synchronises */
 
 /* ---- Buffer: Init / BufferSubData / BindBufferBase / DebugRead*  (SphWave2D/Buffer.cpp:5-83) -- */
 CWA_API int cwa_buffer_create(cwa_ctx* ctx, size_t bytes, const void* host_or_null, cwa_buf* out); /* glNamedBufferStorage */
