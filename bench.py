@@ -34,6 +34,13 @@ WAVE = 2048
 BOX_UPPER = (0.55 * S, 1.0, 0.55 * S, 500.0)       # box that contains the lattice (0.48*S would clamp 7*S columns -> coincident particles -> NaN)
 BOX_LOWER = (0.0, -0.02, 0.0, 50.0)
 GRID_MIN, GRID_MAX, GRID_N = (0.0, -0.02, 0.0), (0.55 * S, 1.0, 0.55 * S), (192, 51, 192)
+_GRID_VARIANT = os.environ.get("CWA_BENCH_GRID", "2h")        # tuning knob: cell size / extent of the uniform grid
+if _GRID_VARIANT == "h":                                      # cells of h = 0.01 (27-cell queries)
+    GRID_N = (384, 102, 384)
+elif _GRID_VARIANT == "h_tight":                              # cells of h, y extent cut to the occupied slab (outliers clamp into the top layer)
+    GRID_MAX, GRID_N = (0.55 * S, 0.18, 0.55 * S), (384, 20, 384)
+elif _GRID_VARIANT == "2h_tight":
+    GRID_MAX, GRID_N = (0.55 * S, 0.18, 0.55 * S), (192, 10, 192)
 UV_SCALE = 2.0 / S
 COUPLING = 0                                        # AS_SHIPPED (reference schedule)
 WORKLOAD = (f"C4: 3-D coupled SPH+wave, {N_PARTICLES} particles ({NX}x{NY}x{NZ} lattice), grid {GRID_N[0]}x{GRID_N[1]}x{GRID_N[2]} "
@@ -45,7 +52,7 @@ ALGO_BYTES = {
     "grid_hash_count": (24, 0, 0),     # pos 16 B read, cell id 4 B + arrival rank 4 B written
     "scan_lookback": (0, 8, 0),        # 4 B read + 4 B written per cell, single pass
     "grid_insert": (16, 0, 0),         # cell id, rank, offset read; index written
-    "grid_cell_order": (8, 4, 0),      # offsets read; index list read + written
+    "grid_cell_order": (16, 0, 0),     # cell id + offset read, arrival list read (once per entry), index written
     "reorder": (132, 0, 0),            # index 4 B + 64 B gathered + 64 B written
     "density": (64, 0, 0),             # compulsory: pos+vel 32 B read, packA/packB 32 B written (neighbour loop is FP32-bound)
     "force": (64, 0, 0),               # compulsory: packA/packB/force 48 B read, force 16 B written

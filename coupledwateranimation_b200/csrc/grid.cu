@@ -34,7 +34,9 @@ grid_hash_count_kernel(const char* __restrict__ particles, int stride_bytes, int
                 cwa_cell2(g, p.x, p.y, ci, cj);
                 cell = ci * g.n[1] + cj;                       // Index(i,j) :149-152
             }
-        } else {
+        } else if (p.x == p.x && p.y == p.y && p.z == p.z) {
+            // ivec3(floor(NaN)) is undefined in GLSL; a NaN particle can never pass a distance test
+            // again, so the canonical choice (shared with the oracle) is: not inserted.
             int ci, cj, ck;
             cwa_cell3(g, p.x, p.y, p.z, ci, cj, ck);
             cell = (ci * g.n[1] + cj) * g.n[0] + ck;           // Index(i,j,k) ugrid_particles_cs.glsl:105-108 (sic)
@@ -214,50 +216,35 @@ int prefix_sum_level_launch(cwa_ctx* ctx, int* x, int n, int phase, int stride, 
 // ---------------------------------------------------------------------------------------------
 // (3) insert + canonical ordering
 // ---------------------------------------------------------------------------------------------
+// arrival[offset + arrival rank] = gid: the reference's InsertPoint with the atomic already folded
+// into the count pass.  Order inside a cell is the (scheduling-dependent) arrival order.
 __global__ void __launch_bounds__(256)
 grid_insert_kernel(const int* __restrict__ cell_of, const int* __restrict__ rank, const int* __restrict__ offset,
-                   int n, int* __restrict__ index_list)
+                   int n, int* __restrict__ arrival)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int c = __ldg(cell_of + i);
     if (c < 0) return;
-    index_list[__ldg(offset + c) + __ldg(rank + i)] = i;          // mIndexList[offset+count] = gid
+    arrival[__ldg(offset + c) + __ldg(rank + i)] = i;             // mIndexList[offset+count] = gid
 }
 
-// Arrival order inside a cell depends on warp scheduling; sort each cell's short list so the index
-// list is the canonical one (ascending particle id == stable counting sort == CPU twin).
+// Canonical order (ascending particle id inside a cell == stable counting sort == the CPU twin,
+// SURVEY F7) by rank-by-counting: particle i lands at offset[c] + #{ids in its cell smaller than i}.
+// One thread per particle, reads only (no in-place sorting, no write hazards); the cell's arrival
+// list is a handful of consecutive ints that stay in L1 for the threads of the same cell.
 __global__ void __launch_bounds__(256)
-grid_cell_order_kernel(const int* __restrict__ offset, int num_cells, int* __restrict__ index_list)
+grid_cell_order_kernel(const int* __restrict__ cell_of, const int* __restrict__ offset, const int* __restrict__ arrival,
+                       int n, int* __restrict__ index_list)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= num_cells) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = __ldg(cell_of + i);
+    if (c < 0) return;
     const int b = __ldg(offset + c), e = __ldg(offset + c + 1);
-    const int m = e - b;
-    if (m < 2) return;
-    int* a = index_list + b;
-    if (m <= 16) {
-        int v[16];
-#pragma unroll
-        for (int q = 0; q < 16; q++) v[q] = (q < m) ? a[q] : 0x7fffffff;
-        // odd-even transposition network on registers (16 phases, branch-free)
-#pragma unroll
-        for (int ph = 0; ph < 16; ph++) {
-#pragma unroll
-            for (int q = (ph & 1); q + 1 < 16; q += 2) {
-                int lo = min(v[q], v[q + 1]), hi = max(v[q], v[q + 1]);
-                v[q] = lo; v[q + 1] = hi;
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < 16; q++) if (q < m) a[q] = v[q];
-    } else {
-        for (int x = 1; x < m; x++) {                             // insertion sort for crowded cells
-            int key = a[x], y = x - 1;
-            while (y >= 0 && a[y] > key) { a[y + 1] = a[y]; y--; }
-            a[y + 1] = key;
-        }
-    }
+    int smaller = 0;
+    for (int q = b; q < e; q++) smaller += (__ldg(arrival + q) < i) ? 1 : 0;
+    index_list[b + smaller] = i;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -282,10 +269,10 @@ int grid_build_internal(cwa_ctx* ctx, GridObj* g, const void* particles, int str
     CWA_TRY(scan_exclusive_launch(ctx, g->counter, g->offset, C, g->ticket, g->tile_state));
     if (n > 0) {
         { KScope k(ctx, KID_INSERT);
-          grid_insert_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(g->cell_of, g->rank, g->offset, n, g->index_list); }
+          grid_insert_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(g->cell_of, g->rank, g->offset, n, g->arrival); }
         CWA_CUDA(cudaGetLastError());
         { KScope k(ctx, KID_CELL_ORDER);
-          grid_cell_order_kernel<<<ceil_div(C, 256), 256, 0, ctx->stream>>>(g->offset, C, g->index_list); }
+          grid_cell_order_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(g->cell_of, g->offset, g->arrival, n, g->index_list); }
         CWA_CUDA(cudaGetLastError());
     }
     return 0;
@@ -322,6 +309,7 @@ extern "C" int cwa_grid_create(cwa_ctx* ctx, int dim, const float* mn, const flo
         g.view.min[a] = g.info.min[a]; g.view.max[a] = g.info.max[a];
         g.view.cell[a] = (a < dim) ? g.info.cell_size[a] : 1.0f;
         g.view.n[a] = (a < dim) ? g.info.num_cells[a] : 1;
+        g.view.inv_cell[a] = 1.0f / g.view.cell[a];
     }
     g.view.dim = dim; g.view.num_cells = (int)C;
 
@@ -337,6 +325,7 @@ extern "C" int cwa_grid_create(cwa_ctx* ctx, int dim, const float* mn, const flo
     CWA_CUDA(cudaMalloc(&g.offset, ((size_t)C + 1) * 4));
     CWA_CUDA(cudaMalloc(&g.cell_of, (size_t)max_particles * 4));
     CWA_CUDA(cudaMalloc(&g.rank, (size_t)max_particles * 4));
+    CWA_CUDA(cudaMalloc(&g.arrival, (size_t)max_particles * 4));
     CWA_CUDA(cudaMalloc(&g.index_list, (size_t)max_particles * 4));
     CWA_CUDA(cudaMemsetAsync(blk, 0, g.clear_bytes, ctx->stream));
     CWA_CUDA(cudaMemsetAsync(g.offset, 0, ((size_t)C + 1) * 4, ctx->stream));
@@ -355,7 +344,7 @@ extern "C" int cwa_grid_destroy(cwa_ctx* ctx, cwa_grid h)
     GridObj* g = get_grid(ctx, h);
     CWA_CHECK(g, "invalid grid handle %d", h);
     CWA_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(g->counter); cudaFree(g->offset); cudaFree(g->cell_of); cudaFree(g->rank); cudaFree(g->index_list);
+    cudaFree(g->counter); cudaFree(g->offset); cudaFree(g->cell_of); cudaFree(g->rank); cudaFree(g->arrival); cudaFree(g->index_list);
     for (cwa_buf b : {g->buf_counter, g->buf_offset, g->buf_index, g->buf_cell_of})
         if (BufferObj* o = get_buffer(ctx, b)) o->live = false;
     g->live = false;

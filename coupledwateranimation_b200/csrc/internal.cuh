@@ -58,6 +58,7 @@ struct GridView {
     float min[3];
     float cell[3];
     float max[3];
+    float inv_cell[3];   // 1/cell, only for the conservative neighbour-range estimate (never for the hash)
     int   n[3];          // Nx, Ny, Nz (Nz = 1 in 2-D)
     int   dim;           // 2 or 3
     int   num_cells;     // allocated/scanned linear cells
@@ -91,6 +92,7 @@ struct GridObj {
     int* offset = nullptr;         // int[C+1]  (offset[C] = number of inserted particles)
     int* cell_of = nullptr;        // int[max_particles]  (-1: not inserted)
     int* rank = nullptr;           // int[max_particles]  arrival rank inside the cell
+    int* arrival = nullptr;        // int[max_particles]  index list in arrival order (input of the canonical ordering)
     int* index_list = nullptr;     // int[max_particles]  canonical: ascending id within a cell
     cwa_buf buf_counter = -1, buf_offset = -1, buf_index = -1, buf_cell_of = -1;
 };
@@ -123,7 +125,11 @@ struct SphObj {
     // cell-ordered snapshot (grid mode) -- see DESIGN.md "data layout"
     float4 *posS = nullptr, *velS = nullptr, *forceS = nullptr, *miscS = nullptr;
     float4 *packA = nullptr, *packB = nullptr;   // (pos.xyz, p) and (vel.xyz, rho)
+    float4 *pairP = nullptr;                     // neighbour sums of the force pass: (pres.xyz, visc.x)
+    float2 *pairV = nullptr;                     //                                   (visc.y, visc.z)
+    void*  consts = nullptr;                     // Sph3Const prepared on the device once per dispatch
     bool snapshot_valid = false;
+    bool pair_sums_valid = false;
 };
 
 struct Sph2Obj {

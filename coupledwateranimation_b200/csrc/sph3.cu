@@ -1,19 +1,23 @@
 // sph3.cu -- the three 3-D SPH passes of CoupledWaterAnimation for sm_100a.
 //   rho_pres_comp.glsl:49-81   -> sph3_density_*   (poly6 density, EOS pressure, wave coupling)
-//   force_comp.glsl:62-139     -> sph3_force_*     (spiky pressure, viscosity, crest rule, torque,
-//                                                   wave drag / normal force, gravity)
+//   force_comp.glsl:62-139     -> sph3_force_* + force_epilogue (spiky pressure, viscosity, crest
+//                                 rule, torque, wave drag / normal force, gravity)
 //   integrate_comp.glsl:56-178 -> sph3_integrate_* (symplectic Euler, foam rule, surface clamp, box)
 //
 // Grid mode (the north-star path): particles are gathered into cell order (coalesced float4
-// reorder, (3) of the north-star list); a CTA owns P consecutive cell-ordered particles and L
-// lanes cooperate on each of them.  The neighbour rows of the CTA's cells are contiguous runs of
-// the cell-ordered arrays, so each run is staged into shared memory with ONE 1-D bulk async copy
-// (cp.async.bulk, TMA engine, completion on an mbarrier); lanes then walk their own row ranges in
-// shared memory and combine partial sums with warp shuffles.  Ranges that do not fit the staging
-// budget are read through L1 from global memory by the same loop.
+// reorder); a CTA owns P consecutive cell-ordered particles and L lanes cooperate on each of them.
+// The neighbour rows of the CTA's cells are contiguous runs of the cell-ordered arrays, so each run
+// is staged into shared memory with ONE 1-D bulk async copy (cp.async.bulk, TMA engine, completion
+// on an mbarrier).  The L lanes of a particle walk CONSECUTIVE candidates of each row (conflict-free
+// 16*L-byte shared-memory reads, equal trip counts) and combine their partial sums with warp
+// shuffles.  The force kernel first marks accepted candidates in a per-lane bit mask and then
+// evaluates only those, so the expensive pair term runs with most lanes active.  Ranges that do not
+// fit the staging budget are read through L1 from global memory by the same loops.
 // All-pairs mode reproduces the shipped O(N^2) loops with shared-memory tiles.
 #include "internal.cuh"
 #include <math_constants.h>
+#include <climits>
+#include <cstdlib>
 
 #define CWA_PI 3.141592741f   // rho_pres_comp.glsl:8
 
@@ -54,7 +58,7 @@ __device__ __forceinline__ void s3_bulk_g2s(void* dst, const void* src, uint32_t
 }
 
 // ---------------------------------------------------------------------------------------------
-// constants derived from the parameter blocks
+// constants derived from the parameter blocks (prepared on the device once per dispatch)
 // ---------------------------------------------------------------------------------------------
 struct Sph3Const {
     float h, h2, accept_r2;        // accept pair  <=>  r2 <= accept_r2  <=>  sqrt_rn(r2) < h
@@ -102,28 +106,35 @@ __device__ __forceinline__ Sph3Const load_consts(const ParamPtrs& prm)
     return c;
 }
 
+__global__ void sph3_prepare_kernel(ParamPtrs prm, Sph3Const* __restrict__ out)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) *out = load_consts(prm);
+}
+
 // ---------------------------------------------------------------------------------------------
 // pair terms
 // ---------------------------------------------------------------------------------------------
 // rho_pres_comp.glsl:62-67
-__device__ __forceinline__ void pair_density(const Sph3Const& c, float px, float py, float pz, const float4 q, float& rho)
+__device__ __forceinline__ void pair_density(float accept_r2, float h2, float poly6, float px, float py, float pz,
+                                             const float4 q, float& rho)
 {
     const float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
     const float r2 = cwa_len3sq(dx, dy, dz);
-    if (r2 <= c.accept_r2) {
-        const float d = c.h2 - r2;
-        rho = fmaf(c.poly6, d * d * d, rho);
+    if (r2 <= accept_r2) {
+        const float d = h2 - r2;
+        rho = fmaf(poly6, d * d * d, rho);
     }
 }
 
-// force_comp.glsl:79-87 (caller excludes j == i)
+// force_comp.glsl:79-87 (caller excludes j == i and rejects r >= h)
 __device__ __forceinline__ void pair_force(const Sph3Const& c, float px, float py, float pz, float prs_i,
                                            float vx, float vy, float vz, const float4 qa, const float4 qb,
                                            float& fpx, float& fpy, float& fpz, float& fvx, float& fvy, float& fvz)
 {
-    const float inv_r = rsqrtf(cwa_len3sq(px - qa.x, py - qa.y, pz - qa.z));
     const float dx = px - qa.x, dy = py - qa.y, dz = pz - qa.z;
-    const float r = cwa_len3sq(dx, dy, dz) * inv_r;             // r = 0 -> NaN like normalize(0)
+    const float r2 = cwa_len3sq(dx, dy, dz);
+    const float inv_r = rsqrtf(r2);
+    const float r = r2 * inv_r;                                  // r = 0 -> NaN like normalize(0)
     const float hr = c.h - r;
     const float inv_rho = __frcp_rn(qb.w);
     // pres_force -= mass*(p_i+p_j)/(2 rho_j) * spiky * (h-r)^2 * normalize(delta)
@@ -150,7 +161,8 @@ __device__ __forceinline__ void density_epilogue(const Sph3Const& c, const TexVi
     prs_out = pressure;
 }
 
-// force_comp.glsl:90-114.  fprev = particles[i].force as stored by the previous frame.
+// force_comp.glsl:90-114.  fprev = particles[i].force as stored by the previous frame;
+// (fp*, fv*) = the neighbour sums of :74-88.
 __device__ __forceinline__ float4 force_epilogue(const Sph3Const& c, const TexView& tex, float px, float py, float pz,
                                                  float vx, float vy, float vz, float rho_i, float4 fprev,
                                                  float fpx, float fpy, float fpz, float fvx, float fvy, float fvz)
@@ -212,22 +224,19 @@ __device__ __forceinline__ void integrate_particle(const Sph3Const& c, const Tex
     vel.x = nvx; vel.y = nvy; vel.z = nvz;
 }
 
-// The integrate pass must not fuse its multiply-adds differently from the oracle where a branch
-// decision hangs on the result (foam, surface clamp, walls); the tolerance on pos/vel is 1e-4 and
-// decisions are compared on fixtures with margins, so default contraction is kept.
-
 // ---------------------------------------------------------------------------------------------
 // (3) coalesced float4 reorder into cell order
 // ---------------------------------------------------------------------------------------------
 // 4 lanes per particle: lane q moves vec4 q of the 64-B struct, so the gather reads whole 64-B
 // records and the four cell-ordered arrays are written with 128-B contiguous runs per 8 slots.
 __global__ void __launch_bounds__(256)
-sph3_reorder_kernel(const float4* __restrict__ aos, const int* __restrict__ index_list, int n,
+sph3_reorder_kernel(const float4* __restrict__ aos, const int* __restrict__ index_list, const int* __restrict__ count,
                     float4* __restrict__ posS, float4* __restrict__ velS, float4* __restrict__ forceS,
                     float4* __restrict__ miscS)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int s = t >> 2, q = t & 3;
+    const int n = __ldg(count);                  // inserted particles (NaN positions are left out)
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (s < n) {
         const int i = __ldg(index_list + s);
@@ -286,23 +295,71 @@ __device__ __forceinline__ uint32_t window_pack(int cap_slots, bool reach_ok, Bl
     return (uint32_t)acc;
 }
 
-struct RowRange { int g0, g1, win; };
+// Conservative cell coordinate for the neighbour query: floor((x - min) * inv_cell + bias) clamped.
+// The hash itself uses the exact IEEE division (cwa_cell3); here a slightly LARGER cell range than
+// ComputeCellIndex(pos -+ h) is harmless: cells outside the exact range only hold particles farther
+// than h on that axis, which the distance test rejects, so the accepted set is unchanged.
+__device__ __forceinline__ int approx_cell(float x, float mn, float inv, float bias, int n)
+{
+    const float f = floorf(fmaf(x - mn, inv, bias));
+    return (int)fminf(fmaxf(f, 0.0f), (float)(n - 1));           // NaN -> 0
+}
+#define CWA_RANGE_EPS 1e-3f
+
+struct Query3 { int i0, i1, j0, j1, k0, k1, ci, cj; };
+
+__device__ __forceinline__ Query3 make_query(const GridView& g, float x, float y, float z, float h)
+{
+    Query3 q;
+    q.i0 = approx_cell(x - h, g.min[0], g.inv_cell[0], -CWA_RANGE_EPS, g.n[0]);
+    q.i1 = approx_cell(x + h, g.min[0], g.inv_cell[0], +CWA_RANGE_EPS, g.n[0]);
+    q.j0 = approx_cell(y - h, g.min[1], g.inv_cell[1], -CWA_RANGE_EPS, g.n[1]);
+    q.j1 = approx_cell(y + h, g.min[1], g.inv_cell[1], +CWA_RANGE_EPS, g.n[1]);
+    q.k0 = approx_cell(z - h, g.min[2], g.inv_cell[2], -CWA_RANGE_EPS, g.n[2]);
+    q.k1 = approx_cell(z + h, g.min[2], g.inv_cell[2], +CWA_RANGE_EPS, g.n[2]);
+    q.ci = approx_cell(x, g.min[0], g.inv_cell[0], 0.0f, g.n[0]);
+    q.cj = approx_cell(y, g.min[1], g.inv_cell[1], 0.0f, g.n[1]);
+    return q;
+}
+
+// staged-window lookup for the row (i,j) of a query: returns the index shift into the staging
+// buffer, or INT_MIN when the row range must be read from global memory
+__device__ __forceinline__ int row_shift(const BlockWindows& bw, const Query3& q, int i, int j, int g0, int g1)
+{
+    const int di = i - q.ci + 1, dj = j - q.cj + 1;
+    if ((unsigned)di < 3u && (unsigned)dj < 3u) {
+        const int w = di * 3 + dj;
+        if (bw.soff[w] >= 0 && g0 >= bw.lo[w] && g1 <= bw.hi[w]) return bw.soff[w] - bw.lo[w];
+    }
+    return INT_MIN;
+}
 
 template <int P, int L>
 __global__ void __launch_bounds__(P * L)
 sph3_density_grid_kernel(const float4* __restrict__ posS, const float4* __restrict__ velS,
-                         float4* __restrict__ packA, float4* __restrict__ packB, int n, GridView g,
-                         const int* __restrict__ offset, ParamPtrs prm, TexView tex, int cap_slots)
+                         float4* __restrict__ packA, float4* __restrict__ packB, int n_max, GridView g,
+                         const int* __restrict__ offset, const Sph3Const* __restrict__ cc, TexView tex, int cap_slots)
 {
     extern __shared__ float4 stage[];
     __shared__ BlockWindows bw;
     __shared__ uint64_t bar;
     const int tid = threadIdx.x;
     const int t0 = blockIdx.x * P;
+    const int n = min(n_max, __ldg(offset + g.num_cells));   // inserted particles
+    if (t0 >= n) return;
     const int nt = min(P, n - t0);
-    const Sph3Const c = load_consts(prm);
-    const bool reach_ok = (c.h <= g.cell[0]) && (c.h <= g.cell[1]) && (c.h <= g.cell[2]);
+    const float h = cc->h, accept_r2 = cc->accept_r2, h2 = cc->h2, poly6 = cc->poly6;
+    const bool reach_ok = (h <= g.cell[0]) && (h <= g.cell[1]) && (h <= g.cell[2]);
 
+    // own target first: its load overlaps the window setup below
+    const int slot = t0 + tid / L, sub = tid % L;
+    const bool active = (tid / L) < nt;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    Query3 q{0, -1, 0, -1, 0, 0, 0, 0};
+    if (active) {
+        p = __ldg(posS + slot);
+        q = make_query(g, p.x, p.y, p.z, h);
+    }
     if (tid < NB_WINDOWS) window_bounds(g, offset, __ldg(posS + t0), __ldg(posS + t0 + nt - 1), tid, &bw);
     if (tid == 0) s3_mbar_init(&bar, 1);
     __syncthreads();
@@ -316,70 +373,64 @@ sph3_density_grid_kernel(const float4* __restrict__ posS, const float4* __restri
             s3_mbar_arrive(&bar);
         }
     }
-    __syncthreads();                                   // windows + barrier init visible
-
-    const int slot = t0 + tid / L, sub = tid % L;
-    const bool active = (tid / L) < nt;
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    int i0 = 0, i1 = -1, j0 = 0, j1 = -1, k0 = 0, k1 = 0, ci = 0, cj = 0;
-    if (active) {
-        p = __ldg(posS + slot);
-        int ck;
-        cwa_cell3(g, p.x, p.y, p.z, ci, cj, ck);
-        cwa_cell3(g, p.x - c.h, p.y - c.h, p.z - c.h, i0, j0, k0);     // cells overlapped by pos +- h
-        cwa_cell3(g, p.x + c.h, p.y + c.h, p.z + c.h, i1, j1, k1);
-    }
+    __syncthreads();                                   // windows packed, barrier armed
     s3_mbar_wait(&bar, 0);
 
     float rho = 0.0f;
-    const int nj = j1 - j0 + 1;
-    const int nr = (i1 - i0 + 1) * nj;
-    for (int r = sub; r < nr; r += L) {
-        const int i = i0 + r / nj, j = j0 + r % nj;
-        const int base = (i * g.n[1] + j) * g.n[0];
-        const int g0 = __ldg(offset + base + k0), g1 = __ldg(offset + base + k1 + 1);
-        const int di = i - ci + 1, dj = j - cj + 1;
-        bool in_smem = false;
-        int shift = 0;
-        if ((unsigned)di < 3u && (unsigned)dj < 3u) {
-            const int w = di * 3 + dj;
-            if (bw.soff[w] >= 0 && g0 >= bw.lo[w] && g1 <= bw.hi[w]) { in_smem = true; shift = bw.soff[w] - bw.lo[w]; }
-        }
-        if (in_smem) {
-            const float4* src = stage + shift;
-            for (int q = g0; q < g1; q++) pair_density(c, p.x, p.y, p.z, src[q], rho);
-        } else {
-            for (int q = g0; q < g1; q++) pair_density(c, p.x, p.y, p.z, __ldg(posS + q), rho);
+    for (int i = q.i0; i <= q.i1; i++) {
+        for (int j = q.j0; j <= q.j1; j++) {
+            const int base = (i * g.n[1] + j) * g.n[0];
+            const int g0 = __ldg(offset + base + q.k0), g1 = __ldg(offset + base + q.k1 + 1);
+            const int shift = row_shift(bw, q, i, j, g0, g1);
+            if (shift != INT_MIN) {
+                const float4* src = stage + shift;
+                for (int c = g0 + sub; c < g1; c += L) pair_density(accept_r2, h2, poly6, p.x, p.y, p.z, src[c], rho);
+            } else {
+                for (int c = g0 + sub; c < g1; c += L) pair_density(accept_r2, h2, poly6, p.x, p.y, p.z, __ldg(posS + c), rho);
+            }
         }
     }
 #pragma unroll
     for (int d = 1; d < L; d <<= 1) rho += __shfl_xor_sync(0xffffffffu, rho, d);
     if (active && sub == 0) {
         float rho_out, prs_out;
-        density_epilogue(c, tex, p.x, p.z, rho, rho_out, prs_out);
+        density_epilogue(*cc, tex, p.x, p.z, rho, rho_out, prs_out);
         const float4 v = __ldg(velS + slot);
         packA[slot] = make_float4(p.x, p.y, p.z, prs_out);
         packB[slot] = make_float4(v.x, v.y, v.z, rho_out);
     }
 }
 
+// neighbour sums of force_comp.glsl:74-88 only; the per-particle terms (:90-114) are evaluated by
+// the element-wise kernels below, where every lane has work.
 template <int P, int L>
 __global__ void __launch_bounds__(P * L)
 sph3_force_grid_kernel(const float4* __restrict__ packA, const float4* __restrict__ packB,
-                       float4* __restrict__ forceS, int n, GridView g, const int* __restrict__ offset,
-                       ParamPtrs prm, TexView tex, int cap_slots)
+                       float4* __restrict__ pairP, float2* __restrict__ pairV, int n_max, GridView g,
+                       const int* __restrict__ offset, const Sph3Const* __restrict__ cc, int cap_slots)
 {
     extern __shared__ float4 stage[];                 // [cap_slots] A followed by [cap_slots] B
     __shared__ BlockWindows bw;
     __shared__ uint64_t bar;
     const int tid = threadIdx.x;
     const int t0 = blockIdx.x * P;
+    const int n = min(n_max, __ldg(offset + g.num_cells));   // inserted particles
+    if (t0 >= n) return;
     const int nt = min(P, n - t0);
-    const Sph3Const c = load_consts(prm);
+    const Sph3Const c = *cc;
     const bool reach_ok = (c.h <= g.cell[0]) && (c.h <= g.cell[1]) && (c.h <= g.cell[2]);
     float4* stageA = stage;
     float4* stageB = stage + cap_slots;
 
+    const int slot = t0 + tid / L, sub = tid % L;
+    const bool active = (tid / L) < nt;
+    float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa;
+    Query3 q{0, -1, 0, -1, 0, 0, 0, 0};
+    if (active) {
+        pa = __ldg(packA + slot);
+        pb = __ldg(packB + slot);
+        q = make_query(g, pa.x, pa.y, pa.z, c.h);
+    }
     if (tid < NB_WINDOWS) window_bounds(g, offset, __ldg(packA + t0), __ldg(packA + t0 + nt - 1), tid, &bw);
     if (tid == 0) s3_mbar_init(&bar, 1);
     __syncthreads();
@@ -398,50 +449,33 @@ sph3_force_grid_kernel(const float4* __restrict__ packA, const float4* __restric
         }
     }
     __syncthreads();
-
-    const int slot = t0 + tid / L, sub = tid % L;
-    const bool active = (tid / L) < nt;
-    float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa;
-    int i0 = 0, i1 = -1, j0 = 0, j1 = -1, k0 = 0, k1 = 0, ci = 0, cj = 0;
-    if (active) {
-        pa = __ldg(packA + slot);
-        pb = __ldg(packB + slot);
-        int ck;
-        cwa_cell3(g, pa.x, pa.y, pa.z, ci, cj, ck);
-        cwa_cell3(g, pa.x - c.h, pa.y - c.h, pa.z - c.h, i0, j0, k0);
-        cwa_cell3(g, pa.x + c.h, pa.y + c.h, pa.z + c.h, i1, j1, k1);
-    }
     s3_mbar_wait(&bar, 0);
 
     float fpx = 0.f, fpy = 0.f, fpz = 0.f, fvx = 0.f, fvy = 0.f, fvz = 0.f;
-    const int nj = j1 - j0 + 1;
-    const int nr = (i1 - i0 + 1) * nj;
-    for (int r = sub; r < nr; r += L) {
-        const int i = i0 + r / nj, j = j0 + r % nj;
-        const int base = (i * g.n[1] + j) * g.n[0];
-        const int g0 = __ldg(offset + base + k0), g1 = __ldg(offset + base + k1 + 1);
-        const int di = i - ci + 1, dj = j - cj + 1;
-        bool in_smem = false;
-        int shift = 0;
-        if ((unsigned)di < 3u && (unsigned)dj < 3u) {
-            const int w = di * 3 + dj;
-            if (bw.soff[w] >= 0 && g0 >= bw.lo[w] && g1 <= bw.hi[w]) { in_smem = true; shift = bw.soff[w] - bw.lo[w]; }
-        }
-        if (in_smem) {
-            const float4* sa = stageA + shift;
-            const float4* sb = stageB + shift;
-            for (int q = g0; q < g1; q++) {
-                const float4 qa = sa[q];
-                const float r2 = cwa_len3sq(pa.x - qa.x, pa.y - qa.y, pa.z - qa.z);
-                if (r2 <= c.accept_r2 && q != slot)
-                    pair_force(c, pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, qa, sb[q], fpx, fpy, fpz, fvx, fvy, fvz);
-            }
-        } else {
-            for (int q = g0; q < g1; q++) {
-                const float4 qa = __ldg(packA + q);
-                const float r2 = cwa_len3sq(pa.x - qa.x, pa.y - qa.y, pa.z - qa.z);
-                if (r2 <= c.accept_r2 && q != slot)
-                    pair_force(c, pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, qa, __ldg(packB + q), fpx, fpy, fpz, fvx, fvy, fvz);
+    for (int i = q.i0; i <= q.i1; i++) {
+        for (int j = q.j0; j <= q.j1; j++) {
+            const int base = (i * g.n[1] + j) * g.n[0];
+            const int g0 = __ldg(offset + base + q.k0), g1 = __ldg(offset + base + q.k1 + 1);
+            const int shift = row_shift(bw, q, i, j, g0, g1);
+            const float4* sa = (shift != INT_MIN) ? (const float4*)(stageA + shift) : packA;
+            const float4* sb = (shift != INT_MIN) ? (const float4*)(stageB + shift) : packB;
+            for (int cb = g0 + sub; cb < g1; cb += 32 * L) {
+                // phase 1: mark accepted candidates (up to 32 per lane) -- cheap, runs on every candidate
+                unsigned mask = 0u;
+                int cnd = cb;
+#pragma unroll 4
+                for (int t = 0; t < 32 && cnd < g1; t++, cnd += L) {
+                    const float4 qa = sa[cnd];
+                    const float r2 = cwa_len3sq(pa.x - qa.x, pa.y - qa.y, pa.z - qa.z);
+                    if (r2 <= c.accept_r2 && cnd != slot) mask |= (1u << t);
+                }
+                // phase 2: evaluate only the accepted ones
+                while (mask) {
+                    const int t = __ffs(mask) - 1;
+                    mask &= mask - 1u;
+                    const int cj = cb + t * L;
+                    pair_force(c, pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, sa[cj], sb[cj], fpx, fpy, fpz, fvx, fvy, fvz);
+                }
             }
         }
     }
@@ -452,77 +486,73 @@ sph3_force_grid_kernel(const float4* __restrict__ packA, const float4* __restric
         fvy += __shfl_xor_sync(0xffffffffu, fvy, d); fvz += __shfl_xor_sync(0xffffffffu, fvz, d);
     }
     if (active && sub == 0) {
-        const float4 fprev = forceS[slot];
-        forceS[slot] = force_epilogue(c, tex, pa.x, pa.y, pa.z, pb.x, pb.y, pb.z, pb.w, fprev, fpx, fpy, fpz, fvx, fvy, fvz);
+        pairP[slot] = make_float4(fpx, fpy, fpz, fvx);
+        pairV[slot] = make_float2(fvy, fvz);
     }
 }
 
-// integrate on the cell-ordered snapshot, results scattered back to the particle SSBO in its
-// original order (full 64-B records, 4 lanes per particle).
+// force epilogue + integrate on the cell-ordered snapshot; one thread per particle writes the full
+// 64-B record back to the particle SSBO in its original order.
 __global__ void __launch_bounds__(256)
-sph3_integrate_sorted_kernel(const float4* __restrict__ packA, const float4* __restrict__ packB,
-                             const float4* __restrict__ forceS, const float4* __restrict__ miscS,
-                             const int* __restrict__ index_list, int n, float4* __restrict__ aos,
-                             ParamPtrs prm, TexView tex)
+sph3_finalize_integrate_sorted_kernel(const float4* __restrict__ packA, const float4* __restrict__ packB,
+                                      const float4* __restrict__ forceS, const float4* __restrict__ miscS,
+                                      const float4* __restrict__ pairP, const float2* __restrict__ pairV,
+                                      const int* __restrict__ index_list, const int* __restrict__ count, float4* __restrict__ aos,
+                                      const Sph3Const* __restrict__ cc, TexView tex)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int s = t >> 2, q = t & 3;
-    if (s >= n) return;
-    const Sph3Const c = load_consts(prm);
-    const float4 a = __ldg(packA + s), b = __ldg(packB + s), m = __ldg(miscS + s);
-    float4 f = __ldg(forceS + s);
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= __ldg(count)) return;
+    const Sph3Const c = *cc;
+    const float4 a = __ldg(packA + s), b = __ldg(packB + s), m = __ldg(miscS + s), pp = __ldg(pairP + s);
+    const float2 pv = __ldg(pairV + s);
+    float4 f = force_epilogue(c, tex, a.x, a.y, a.z, b.x, b.y, b.z, b.w, __ldg(forceS + s), pp.x, pp.y, pp.z, pp.w, pv.x, pv.y);
     float4 pos = make_float4(a.x, a.y, a.z, m.x), vel = make_float4(b.x, b.y, b.z, m.y);
     float rho = b.w, prs = a.w;
     integrate_particle(c, tex, pos, vel, f, rho, prs);
-    const int i = __ldg(index_list + s);
-    float4 o;
-    if (q == 0) o = pos;
-    else if (q == 1) o = vel;
-    else if (q == 2) o = f;
-    else o = make_float4(rho, prs, m.z, m.w);
-    aos[(size_t)i * 4 + q] = o;
+    float4* o = aos + (size_t)__ldg(index_list + s) * 4;
+    o[0] = pos; o[1] = vel; o[2] = f; o[3] = make_float4(rho, prs, m.z, m.w);
 }
 
-// write-back of a single pass result to the SSBO (individually dispatched passes)
+// individually dispatched passes: commit one pass result to the SSBO
 __global__ void __launch_bounds__(256)
 sph3_scatter_rho_pres_kernel(const float4* __restrict__ packA, const float4* __restrict__ packB,
-                             const int* __restrict__ index_list, int n, float4* __restrict__ aos)
+                             const int* __restrict__ index_list, const int* __restrict__ count, float4* __restrict__ aos)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
+    if (s >= __ldg(count)) return;
     const int i = __ldg(index_list + s);
     float2* e = reinterpret_cast<float2*>(aos + (size_t)i * 4 + 3);
     *e = make_float2(__ldg(packB + s).w, __ldg(packA + s).w);      // extras[0] = rho, extras[1] = pressure
 }
 
 __global__ void __launch_bounds__(256)
-sph3_scatter_force_kernel(const float4* __restrict__ forceS, const int* __restrict__ index_list, int n,
-                          float4* __restrict__ aos)
+sph3_finalize_force_sorted_kernel(const float4* __restrict__ packA, const float4* __restrict__ packB,
+                                  const float4* __restrict__ forceS, const float4* __restrict__ pairP,
+                                  const float2* __restrict__ pairV, const int* __restrict__ index_list, const int* __restrict__ count,
+                                  float4* __restrict__ aos, const Sph3Const* __restrict__ cc, TexView tex)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    aos[(size_t)__ldg(index_list + s) * 4 + 2] = __ldg(forceS + s);
+    if (s >= __ldg(count)) return;
+    const Sph3Const c = *cc;
+    const float4 a = __ldg(packA + s), b = __ldg(packB + s), pp = __ldg(pairP + s);
+    const float2 pv = __ldg(pairV + s);
+    const float4 f = force_epilogue(c, tex, a.x, a.y, a.z, b.x, b.y, b.z, b.w, __ldg(forceS + s), pp.x, pp.y, pp.z, pp.w, pv.x, pv.y);
+    aos[(size_t)__ldg(index_list + s) * 4 + 2] = f;
 }
 
 // integrate directly on the SSBO (original order); used when the pass is dispatched on its own
 __global__ void __launch_bounds__(256)
-sph3_integrate_aos_kernel(float4* __restrict__ aos, int n, ParamPtrs prm, TexView tex)
+sph3_integrate_aos_kernel(float4* __restrict__ aos, int n, const Sph3Const* __restrict__ cc, TexView tex)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = t >> 2, q = t & 3;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const Sph3Const c = load_consts(prm);
-    float4 pos = aos[(size_t)i * 4 + 0], vel = aos[(size_t)i * 4 + 1], f = aos[(size_t)i * 4 + 2];
-    const float4 e = aos[(size_t)i * 4 + 3];
+    const Sph3Const c = *cc;
+    float4* o = aos + (size_t)i * 4;
+    float4 pos = o[0], vel = o[1], f = o[2];
+    const float4 e = o[3];
     float rho = e.x, prs = e.y;
     integrate_particle(c, tex, pos, vel, f, rho, prs);
-    __syncwarp();                                      // all four lanes of a particle have read it
-    float4 o;
-    if (q == 0) o = pos;
-    else if (q == 1) o = vel;
-    else if (q == 2) o = f;
-    else o = make_float4(rho, prs, e.z, e.w);
-    aos[(size_t)i * 4 + q] = o;
+    o[0] = pos; o[1] = vel; o[2] = f; o[3] = make_float4(rho, prs, e.z, e.w);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -533,12 +563,13 @@ constexpr int AP_L = 4;          // lanes per target (each scans one quarter of 
 constexpr int AP_TILE = 256;     // candidates per shared-memory tile
 
 __global__ void __launch_bounds__(AP_TT * AP_L)
-sph3_density_allpairs_kernel(float4* __restrict__ aos, int n, ParamPtrs prm, TexView tex, float2* __restrict__ out_rp)
+sph3_density_allpairs_kernel(const float4* __restrict__ aos, int n, const Sph3Const* __restrict__ cc, TexView tex,
+                             float2* __restrict__ out_rp)
 {
     __shared__ float4 tile[AP_TILE];
     const int tid = threadIdx.x;
     const int i = blockIdx.x * AP_TT + tid / AP_L, sub = tid % AP_L;
-    const Sph3Const c = load_consts(prm);
+    const float accept_r2 = cc->accept_r2, h2 = cc->h2, poly6 = cc->poly6;
     const bool active = i < n;
     const float4 p = active ? aos[(size_t)i * 4] : make_float4(0.f, 0.f, 0.f, 0.f);
     float rho = 0.0f;
@@ -547,15 +578,15 @@ sph3_density_allpairs_kernel(float4* __restrict__ aos, int n, ParamPtrs prm, Tex
         tile[tid] = (j < n) ? aos[(size_t)j * 4] : make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f);
         __syncthreads();
 #pragma unroll 8
-        for (int q = sub; q < AP_TILE; q += AP_L) pair_density(c, p.x, p.y, p.z, tile[q], rho);
+        for (int q = sub; q < AP_TILE; q += AP_L) pair_density(accept_r2, h2, poly6, p.x, p.y, p.z, tile[q], rho);
         __syncthreads();
     }
 #pragma unroll
     for (int d = 1; d < AP_L; d <<= 1) rho += __shfl_xor_sync(0xffffffffu, rho, d);
     if (active && sub == 0) {
         float rho_out, prs_out;
-        density_epilogue(c, tex, p.x, p.z, rho, rho_out, prs_out);
-        out_rp[i] = make_float2(rho_out, prs_out);     // committed to the SSBO after the pass (no read/write race)
+        density_epilogue(*cc, tex, p.x, p.z, rho, rho_out, prs_out);
+        out_rp[i] = make_float2(rho_out, prs_out);     // committed to the SSBO after the pass
     }
 }
 
@@ -568,13 +599,14 @@ sph3_commit_rho_pres_kernel(const float2* __restrict__ rp, int n, float4* __rest
 }
 
 __global__ void __launch_bounds__(AP_TT * AP_L)
-sph3_force_allpairs_kernel(float4* __restrict__ aos, int n, ParamPtrs prm, TexView tex, float4* __restrict__ out_force)
+sph3_force_allpairs_kernel(const float4* __restrict__ aos, int n, const Sph3Const* __restrict__ cc, TexView tex,
+                           float4* __restrict__ out_force)
 {
     __shared__ float4 tileA[AP_TILE];
     __shared__ float4 tileB[AP_TILE];
     const int tid = threadIdx.x;
     const int i = blockIdx.x * AP_TT + tid / AP_L, sub = tid % AP_L;
-    const Sph3Const c = load_consts(prm);
+    const Sph3Const c = *cc;
     const bool active = i < n;
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f), v = p, e = p;
     if (active) { p = aos[(size_t)i * 4]; v = aos[(size_t)i * 4 + 1]; e = aos[(size_t)i * 4 + 3]; }
@@ -590,12 +622,19 @@ sph3_force_allpairs_kernel(float4* __restrict__ aos, int n, ParamPtrs prm, TexVi
             tileB[tid] = make_float4(0.f, 0.f, 0.f, 1.f);
         }
         __syncthreads();
-#pragma unroll 4
-        for (int q = sub; q < AP_TILE; q += AP_L) {
-            const float4 qa = tileA[q];
+        // same two-phase scheme as the grid kernel: 64 candidates per lane and tile
+        unsigned long long mask = 0ull;
+#pragma unroll 8
+        for (int t = 0; t < AP_TILE / AP_L; t++) {
+            const float4 qa = tileA[sub + t * AP_L];
             const float r2 = cwa_len3sq(p.x - qa.x, p.y - qa.y, p.z - qa.z);
-            if (r2 <= c.accept_r2 && (j0 + q) != i)
-                pair_force(c, p.x, p.y, p.z, e.y, v.x, v.y, v.z, qa, tileB[q], fpx, fpy, fpz, fvx, fvy, fvz);
+            if (r2 <= c.accept_r2 && (j0 + sub + t * AP_L) != i) mask |= (1ull << t);
+        }
+        while (mask) {
+            const int t = __ffsll((long long)mask) - 1;
+            mask &= mask - 1ull;
+            const int q = sub + t * AP_L;
+            pair_force(c, p.x, p.y, p.z, e.y, v.x, v.y, v.z, tileA[q], tileB[q], fpx, fpy, fpz, fvx, fvy, fvz);
         }
         __syncthreads();
     }
@@ -621,16 +660,18 @@ sph3_commit_force_kernel(const float4* __restrict__ f, int n, float4* __restrict
 
 // neighbour counts for the "neighbour set identical" assertions
 __global__ void __launch_bounds__(256)
-sph3_neighbour_count_grid_kernel(const float4* __restrict__ posS, const int* __restrict__ index_list, int n,
-                                 GridView g, const int* __restrict__ offset, ParamPtrs prm, int* __restrict__ out)
+sph3_neighbour_count_grid_kernel(const float4* __restrict__ posS, const int* __restrict__ index_list, const int* __restrict__ count,
+                                 GridView g, const int* __restrict__ offset, const Sph3Const* __restrict__ cc,
+                                 int* __restrict__ out)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    const Sph3Const c = load_consts(prm);
+    if (s >= __ldg(count)) return;
+    const float h = cc->h, accept_r2 = cc->accept_r2;
     const float4 p = __ldg(posS + s);
+    // exact reference range (ComputeCellIndex of pos -+ h), deliberately NOT the conservative one
     int i0, j0, k0, i1, j1, k1;
-    cwa_cell3(g, p.x - c.h, p.y - c.h, p.z - c.h, i0, j0, k0);
-    cwa_cell3(g, p.x + c.h, p.y + c.h, p.z + c.h, i1, j1, k1);
+    cwa_cell3(g, p.x - h, p.y - h, p.z - h, i0, j0, k0);
+    cwa_cell3(g, p.x + h, p.y + h, p.z + h, i1, j1, k1);
     int cnt = 0;
     for (int i = i0; i <= i1; i++)
         for (int j = j0; j <= j1; j++) {
@@ -638,23 +679,24 @@ sph3_neighbour_count_grid_kernel(const float4* __restrict__ posS, const int* __r
             const int g0 = __ldg(offset + base + k0), g1 = __ldg(offset + base + k1 + 1);
             for (int q = g0; q < g1; q++) {
                 const float4 o = __ldg(posS + q);
-                if (cwa_len3sq(p.x - o.x, p.y - o.y, p.z - o.z) <= c.accept_r2) cnt++;
+                if (cwa_len3sq(p.x - o.x, p.y - o.y, p.z - o.z) <= accept_r2) cnt++;
             }
         }
     out[__ldg(index_list + s)] = cnt;
 }
 
 __global__ void __launch_bounds__(256)
-sph3_neighbour_count_allpairs_kernel(const float4* __restrict__ aos, int n, ParamPtrs prm, int* __restrict__ out)
+sph3_neighbour_count_allpairs_kernel(const float4* __restrict__ aos, int n, const Sph3Const* __restrict__ cc,
+                                     int* __restrict__ out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const Sph3Const c = load_consts(prm);
+    const float accept_r2 = cc->accept_r2;
     const float4 p = aos[(size_t)i * 4];
     int cnt = 0;
     for (int j = 0; j < n; j++) {
         const float4 o = __ldg(aos + (size_t)j * 4);
-        if (cwa_len3sq(p.x - o.x, p.y - o.y, p.z - o.z) <= c.accept_r2) cnt++;
+        if (cwa_len3sq(p.x - o.x, p.y - o.y, p.z - o.z) <= accept_r2) cnt++;
     }
     out[i] = cnt;
 }
@@ -678,10 +720,62 @@ sph3_init_cube_kernel(float4* __restrict__ aos, int nx, int ny, int nz, ParamPtr
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-constexpr int NB_P = 128;                 // targets per CTA
-constexpr int NB_L = 4;                   // lanes per target
-constexpr int DENS_CAP = 3072;            // staged slots (16 B each)  -> 48 KB
-constexpr int FORCE_CAP = 2048;           // staged slots (32 B each)  -> 64 KB
+constexpr int DENS_CAP_MAX = 3072;        // staged slots (16 B each): at most 48 KB
+constexpr int FORCE_CAP_MAX = 2048;       // staged slots (32 B each): at most 64 KB
+constexpr int DENS_CAP_DEFAULT = 2048;    // 32 KB/CTA: measured best occupancy/staging trade-off on C4 (profiles/r1_tuning.md)
+constexpr int FORCE_CAP_DEFAULT = 1536;   // 48 KB/CTA
+
+static int env_int(const char* name, int dflt, int lo, int hi)
+{
+    const char* e = getenv(name);
+    if (!e) return dflt;
+    int v = atoi(e);
+    return v < lo ? lo : (v > hi ? hi : v);
+}
+// staging budgets (slots); tuning knobs CWA_NB_CAP_D / CWA_NB_CAP_F (0 disables staging)
+static int dens_cap() { static int v = -1; if (v < 0) v = env_int("CWA_NB_CAP_D", DENS_CAP_DEFAULT, 0, DENS_CAP_MAX); return v; }
+static int force_cap() { static int v = -1; if (v < 0) v = env_int("CWA_NB_CAP_F", FORCE_CAP_DEFAULT, 0, FORCE_CAP_MAX); return v; }
+
+// (targets per CTA, lanes per target) of the neighbour kernels; CWA_NB_CONFIG selects another
+// instantiation for tuning runs (0: 128x4, 1: 128x2 (default), 2: 64x4, 3: 256x1, 4: 128x1, 5: 64x2, 6: 256x2)
+static int nb_config()
+{
+    static int cfg = -1;
+    if (cfg < 0) {
+        const char* e = getenv("CWA_NB_CONFIG");
+        cfg = e ? atoi(e) : 1;
+        if (cfg < 0 || cfg > 6) cfg = 1;
+    }
+    return cfg;
+}
+
+template <int P, int L>
+static int launch_density(cwa_ctx* ctx, SphObj* s, GridObj* g, TexView tex)
+{
+    static bool attr = false;
+    if (!attr) {
+        CWA_CUDA(cudaFuncSetAttribute(sph3_density_grid_kernel<P, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, DENS_CAP_MAX * 16));
+        attr = true;
+    }
+    KScope k(ctx, KID_DENSITY);
+    sph3_density_grid_kernel<P, L><<<ceil_div(s->n, P), P * L, dens_cap() * 16, ctx->stream>>>(
+        s->posS, s->velS, s->packA, s->packB, s->n, g->view, g->offset, (const Sph3Const*)s->consts, tex, dens_cap());
+    return 0;
+}
+
+template <int P, int L>
+static int launch_force(cwa_ctx* ctx, SphObj* s, GridObj* g)
+{
+    static bool attr = false;
+    if (!attr) {
+        CWA_CUDA(cudaFuncSetAttribute(sph3_force_grid_kernel<P, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, FORCE_CAP_MAX * 32));
+        attr = true;
+    }
+    KScope k(ctx, KID_FORCE);
+    sph3_force_grid_kernel<P, L><<<ceil_div(s->n, P), P * L, force_cap() * 32, ctx->stream>>>(
+        s->packA, s->packB, s->pairP, s->pairV, s->n, g->view, g->offset, (const Sph3Const*)s->consts, force_cap());
+    return 0;
+}
 
 static int sph_snapshot(cwa_ctx* ctx, SphObj* s)
 {
@@ -691,9 +785,17 @@ static int sph_snapshot(cwa_ctx* ctx, SphObj* s)
     CWA_TRY(grid_build_internal(ctx, g, pb->ptr, 64, s->n));
     { KScope k(ctx, KID_REORDER);
       sph3_reorder_kernel<<<ceil_div((long long)s->n * 4, 256), 256, 0, ctx->stream>>>(
-          (const float4*)pb->ptr, g->index_list, s->n, s->posS, s->velS, s->forceS, s->miscS); }
+          (const float4*)pb->ptr, g->index_list, g->offset + g->view.num_cells, s->posS, s->velS, s->forceS, s->miscS); }
     CWA_CUDA(cudaGetLastError());
     s->snapshot_valid = true;
+    s->pair_sums_valid = false;
+    return 0;
+}
+
+static int sph_prepare(cwa_ctx* ctx, SphObj* s)
+{
+    KScope k(ctx, KID_OTHER);
+    sph3_prepare_kernel<<<1, 32, 0, ctx->stream>>>(current_params(ctx), (Sph3Const*)s->consts);
     return 0;
 }
 
@@ -707,27 +809,28 @@ int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which)
     BufferObj* pb = get_buffer(ctx, s->particles);
     CWA_CHECK(pb, "sph: particle buffer vanished");
     float4* aos = (float4*)pb->ptr;
-    const ParamPtrs prm = current_params(ctx);
     const int n = s->n;
     if (n == 0) return 0;
+    CWA_TRY(sph_prepare(ctx, s));
+    const Sph3Const* cc = (const Sph3Const*)s->consts;
 
     if (s->grid < 0) {                                             // ---- all-pairs, as shipped
         const int blocks = ceil_div(n, AP_TT);
         if (which & 1) {
             { KScope k(ctx, KID_DENSITY);
-              sph3_density_allpairs_kernel<<<blocks, AP_TT * AP_L, 0, ctx->stream>>>(aos, n, prm, tex, sph_scratch_rp(s)); }
+              sph3_density_allpairs_kernel<<<blocks, AP_TT * AP_L, 0, ctx->stream>>>(aos, n, cc, tex, sph_scratch_rp(s)); }
             { KScope k(ctx, KID_OTHER);
               sph3_commit_rho_pres_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(sph_scratch_rp(s), n, aos); }
         }
         if (which & 2) {
             { KScope k(ctx, KID_FORCE);
-              sph3_force_allpairs_kernel<<<blocks, AP_TT * AP_L, 0, ctx->stream>>>(aos, n, prm, tex, sph_scratch_force(s)); }
+              sph3_force_allpairs_kernel<<<blocks, AP_TT * AP_L, 0, ctx->stream>>>(aos, n, cc, tex, sph_scratch_force(s)); }
             { KScope k(ctx, KID_OTHER);
               sph3_commit_force_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(sph_scratch_force(s), n, aos); }
         }
         if (which & 4) {
             KScope k(ctx, KID_INTEGRATE);
-            sph3_integrate_aos_kernel<<<ceil_div((long long)n * 4, 256), 256, 0, ctx->stream>>>(aos, n, prm, tex);
+            sph3_integrate_aos_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(aos, n, cc, tex);
         }
         CWA_CUDA(cudaGetLastError());
         return 0;
@@ -736,43 +839,52 @@ int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which)
     // ---- grid mode
     GridObj* g = get_grid(ctx, s->grid);
     CWA_CHECK(g && g->dim == 3, "sph: the bound grid must be a 3-D grid");
-    static bool attrs_done = false;
-    if (!attrs_done) {
-        CWA_CUDA(cudaFuncSetAttribute(sph3_density_grid_kernel<NB_P, NB_L>, cudaFuncAttributeMaxDynamicSharedMemorySize, DENS_CAP * 16));
-        CWA_CUDA(cudaFuncSetAttribute(sph3_force_grid_kernel<NB_P, NB_L>, cudaFuncAttributeMaxDynamicSharedMemorySize, FORCE_CAP * 32));
-        attrs_done = true;
-    }
-    const int blocks = ceil_div(n, NB_P);
     const bool full = (which == 7);
+    const int cfg = nb_config();
     if (which & 1) {
         CWA_TRY(sph_snapshot(ctx, s));                             // positions changed since the last frame
-        { KScope k(ctx, KID_DENSITY);
-          sph3_density_grid_kernel<NB_P, NB_L><<<blocks, NB_P * NB_L, DENS_CAP * 16, ctx->stream>>>(
-              s->posS, s->velS, s->packA, s->packB, n, g->view, g->offset, prm, tex, DENS_CAP); }
+        switch (cfg) {
+        case 1: CWA_TRY((launch_density<128, 2>(ctx, s, g, tex))); break;
+        case 2: CWA_TRY((launch_density<64, 4>(ctx, s, g, tex))); break;
+        case 3: CWA_TRY((launch_density<256, 1>(ctx, s, g, tex))); break;
+        case 4: CWA_TRY((launch_density<128, 1>(ctx, s, g, tex))); break;
+        case 5: CWA_TRY((launch_density<64, 2>(ctx, s, g, tex))); break;
+        case 6: CWA_TRY((launch_density<256, 2>(ctx, s, g, tex))); break;
+        default: CWA_TRY((launch_density<128, 4>(ctx, s, g, tex))); break;
+        }
         if (!full) {
             KScope k(ctx, KID_OTHER);
-            sph3_scatter_rho_pres_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(s->packA, s->packB, g->index_list, n, aos);
+            sph3_scatter_rho_pres_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(s->packA, s->packB, g->index_list, g->offset + g->view.num_cells, aos);
         }
     }
     if (which & 2) {
         CWA_CHECK(s->snapshot_valid, "force pass dispatched before a density pass built the cell-ordered snapshot");
-        { KScope k(ctx, KID_FORCE);
-          sph3_force_grid_kernel<NB_P, NB_L><<<blocks, NB_P * NB_L, FORCE_CAP * 32, ctx->stream>>>(
-              s->packA, s->packB, s->forceS, n, g->view, g->offset, prm, tex, FORCE_CAP); }
+        switch (cfg) {
+        case 1: CWA_TRY((launch_force<128, 2>(ctx, s, g))); break;
+        case 2: CWA_TRY((launch_force<64, 4>(ctx, s, g))); break;
+        case 3: CWA_TRY((launch_force<256, 1>(ctx, s, g))); break;
+        case 4: CWA_TRY((launch_force<128, 1>(ctx, s, g))); break;
+        case 5: CWA_TRY((launch_force<64, 2>(ctx, s, g))); break;
+        case 6: CWA_TRY((launch_force<256, 2>(ctx, s, g))); break;
+        default: CWA_TRY((launch_force<128, 4>(ctx, s, g))); break;
+        }
+        s->pair_sums_valid = true;
         if (!full) {
             KScope k(ctx, KID_OTHER);
-            sph3_scatter_force_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(s->forceS, g->index_list, n, aos);
+            sph3_finalize_force_sorted_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(
+                s->packA, s->packB, s->forceS, s->pairP, s->pairV, g->index_list, g->offset + g->view.num_cells, aos, cc, tex);
         }
     }
     if (which & 4) {
         KScope k(ctx, KID_INTEGRATE);
         if (full) {
-            sph3_integrate_sorted_kernel<<<ceil_div((long long)n * 4, 256), 256, 0, ctx->stream>>>(
-                s->packA, s->packB, s->forceS, s->miscS, g->index_list, n, aos, prm, tex);
+            sph3_finalize_integrate_sorted_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(
+                s->packA, s->packB, s->forceS, s->miscS, s->pairP, s->pairV, g->index_list, g->offset + g->view.num_cells, aos, cc, tex);
         } else {
-            sph3_integrate_aos_kernel<<<ceil_div((long long)n * 4, 256), 256, 0, ctx->stream>>>(aos, n, prm, tex);
+            sph3_integrate_aos_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(aos, n, cc, tex);
         }
         s->snapshot_valid = false;                                 // positions moved
+        s->pair_sums_valid = false;
     }
     CWA_CUDA(cudaGetLastError());
     return 0;
@@ -793,6 +905,7 @@ extern "C" int cwa_sph_create(cwa_ctx* ctx, cwa_buf particles, int n, cwa_grid g
     SphObj s;
     s.live = true; s.particles = particles; s.n = n; s.grid = grid;
     const size_t bytes = (size_t)(n > 0 ? n : 1) * 16;
+    CWA_CUDA(cudaMalloc(&s.consts, sizeof(Sph3Const)));
     CWA_CUDA(cudaMalloc(&s.packA, bytes));
     CWA_CUDA(cudaMalloc(&s.packB, bytes));
     if (grid >= 0) {
@@ -800,6 +913,8 @@ extern "C" int cwa_sph_create(cwa_ctx* ctx, cwa_buf particles, int n, cwa_grid g
         CWA_CUDA(cudaMalloc(&s.velS, bytes));
         CWA_CUDA(cudaMalloc(&s.forceS, bytes));
         CWA_CUDA(cudaMalloc(&s.miscS, bytes));
+        CWA_CUDA(cudaMalloc(&s.pairP, bytes));
+        CWA_CUDA(cudaMalloc(&s.pairV, bytes / 2));
     }
     ctx->sphs.push_back(s);
     *out = (int)ctx->sphs.size() - 1;
@@ -812,6 +927,7 @@ extern "C" int cwa_sph_destroy(cwa_ctx* ctx, cwa_sph h)
     CWA_CHECK(s, "invalid sph handle %d", h);
     CWA_CUDA(cudaStreamSynchronize(ctx->stream));
     cudaFree(s->packA); cudaFree(s->packB); cudaFree(s->posS); cudaFree(s->velS); cudaFree(s->forceS); cudaFree(s->miscS);
+    cudaFree(s->pairP); cudaFree(s->pairV); cudaFree(s->consts);
     s->live = false;
     if (ctx->bound_sph == h) ctx->bound_sph = -1;
     return 0;
@@ -870,15 +986,18 @@ extern "C" int cwa_sph_neighbour_count(cwa_ctx* ctx, cwa_sph h, int* host)
     if (s->n == 0) return 0;
     int* dout = nullptr;
     CWA_CUDA(cudaMalloc(&dout, (size_t)s->n * 4));
-    const ParamPtrs prm = current_params(ctx);
+    CWA_CUDA(cudaMemsetAsync(dout, 0, (size_t)s->n * 4, ctx->stream));   // NaN particles are in no list: 0 neighbours
+    CWA_TRY(sph_prepare(ctx, s));
+    const Sph3Const* cc = (const Sph3Const*)s->consts;
     if (s->grid >= 0) {
         GridObj* g = get_grid(ctx, s->grid);
         CWA_TRY(sph_snapshot(ctx, s));
-        sph3_neighbour_count_grid_kernel<<<ceil_div(s->n, 256), 256, 0, ctx->stream>>>(s->posS, g->index_list, s->n, g->view, g->offset, prm, dout);
+        KScope k(ctx, KID_OTHER);
+        sph3_neighbour_count_grid_kernel<<<ceil_div(s->n, 256), 256, 0, ctx->stream>>>(s->posS, g->index_list, g->offset + g->view.num_cells, g->view, g->offset, cc, dout);
     } else {
-        sph3_neighbour_count_allpairs_kernel<<<ceil_div(s->n, 256), 256, 0, ctx->stream>>>((const float4*)pb->ptr, s->n, prm, dout);
+        KScope k(ctx, KID_OTHER);
+        sph3_neighbour_count_allpairs_kernel<<<ceil_div(s->n, 256), 256, 0, ctx->stream>>>((const float4*)pb->ptr, s->n, cc, dout);
     }
-    ctx->launches++;
     CWA_CUDA(cudaGetLastError());
     CWA_CUDA(cudaMemcpyAsync(host, dout, (size_t)s->n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CWA_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -893,8 +1012,8 @@ extern "C" int cwa_sph_init_cube(cwa_ctx* ctx, cwa_sph h, int nx, int ny, int nz
     CWA_CHECK(nx > 0 && ny > 0 && nz > 0 && (long long)nx * ny * nz == s->n, "cwa_sph_init_cube: %dx%dx%d != %d particles", nx, ny, nz, s->n);
     BufferObj* pb = get_buffer(ctx, s->particles);
     CWA_CHECK(pb, "sph: particle buffer vanished");
-    sph3_init_cube_kernel<<<ceil_div(s->n, 256), 256, 0, ctx->stream>>>((float4*)pb->ptr, nx, ny, nz, current_params(ctx));
-    ctx->launches++;
+    { KScope k(ctx, KID_OTHER);
+      sph3_init_cube_kernel<<<ceil_div(s->n, 256), 256, 0, ctx->stream>>>((float4*)pb->ptr, nx, ny, nz, current_params(ctx)); }
     CWA_CUDA(cudaGetLastError());
     s->snapshot_valid = false;
     return 0;

@@ -272,11 +272,15 @@ void orc_grid2_build(const orc_grid2* g, const float* pos, int stride, int n,
 void orc_grid3_build(const orc_grid3* g, const float* pos, int stride, int n,
                      int* cell_of, int* counter, int* offset, int* index_list)
 {
+    /* Canonical choice for an undefined case: ivec3(floor(NaN)) is undefined in GLSL, so a particle
+     * whose position holds a NaN lands in an implementation-defined cell.  Such a particle can never
+     * pass a distance test again (every r is NaN), so it is simply NOT inserted (cell_of = -1). */
     const int C = grid3_num_cells(g);
     memset(counter, 0, sizeof(int) * (size_t)C);
     memset(offset, 0, sizeof(int) * (size_t)C);
     for (int i = 0; i < n; i++) {
         const float* p = pos + (size_t)i * stride;
+        if (p[0] != p[0] || p[1] != p[1] || p[2] != p[2]) { if (cell_of) cell_of[i] = -1; continue; }
         int ix = orc_grid3_cell_index(g, p[0], p[1], p[2]);
         if (cell_of) cell_of[i] = ix;
         counter[ix]++;
@@ -285,6 +289,7 @@ void orc_grid3_build(const orc_grid3* g, const float* pos, int stride, int n,
     memset(counter, 0, sizeof(int) * (size_t)C);
     for (int i = 0; i < n; i++) {
         const float* p = pos + (size_t)i * stride;
+        if (p[0] != p[0] || p[1] != p[1] || p[2] != p[2]) continue;
         int ix = orc_grid3_cell_index(g, p[0], p[1], p[2]);
         int count = counter[ix]++;
         index_list[offset[ix] + count] = i;
