@@ -245,6 +245,22 @@ class StencilImage2DTripleBuffered:
         check(ctx.lib.cwa_wave_create(ctx.h, w, h, channels, variant, C.byref(o)))   # Init() incl. Reinit()
         self.h = o.value
 
+    @classmethod
+    def create_block(cls, ctx: Context, w: int, h_global: int, row0: int, rows: int, channels=1, variant=WAVE_COUPLED):
+        """Row block [row0, row0+rows) of a field h_global rows tall (multi-GPU decomposition)."""
+        self = cls.__new__(cls)
+        self.ctx, self.w, self.height, self.ch, self.variant = ctx, w, rows, channels, variant
+        self.h_global, self.row0 = h_global, row0
+        o = C.c_int(-1)
+        check(ctx.lib.cwa_wave_create_block(ctx.h, w, h_global, row0, rows, channels, variant, C.byref(o)))
+        self.h = o.value
+        return self
+
+    def last_row_buffer(self, image: int) -> Buffer:
+        b = C.c_int()
+        check(self.ctx.lib.cwa_wave_last_row_buffer(self.ctx.h, self.h, image, C.byref(b)))
+        return Buffer(self.ctx, handle=b.value, nbytes=self.w * self.ch * 4)
+
     def _shape(self):
         return (self.height, self.w) if self.ch == 1 else (self.height, self.w, self.ch)
 

@@ -103,6 +103,10 @@ SIGNATURES = {
     "cwa_bind_scene": (_I, [_P, _I, _I]),
     "sph_step": (_I, [_P, _I]),
     "wave_step": (_I, [_P, _I]),
+    "cwa_sph_set_count": (_I, [_P, _I, _I]),
+    "cwa_particles_copy_if": (_I, [_P, _I, _I, _I, _I, _F, _F, _I, _I, _IP]),
+    "cwa_wave_create_block": (_I, [_P, _I, _I, _I, _I, _I, _I, _IP]),
+    "cwa_wave_last_row_buffer": (_I, [_P, _I, _I, _IP]),
     "cwa_sph2_create": (_I, [_P, _I, _I, _I, _IP]),
     "cwa_sph2_destroy": (_I, [_P, _I]),
     "cwa_sph2_reinit": (_I, [_P, _I]),

@@ -48,9 +48,14 @@ struct ParamPtrs {
 };
 
 // sampler2D wave_tex (binding 0): LINEAR / CLAMP_TO_EDGE, .r channel.  data == nullptr: unbound.
+// Multi-GPU: `data` may hold only the rows [row0, row0 + h) of a field that is h_global rows tall
+// (row-block decomposition); `last_row` then points at a copy of the GLOBAL last row, which
+// WaveNormal's uv + (0,1) tap clamps to from everywhere (force_comp.glsl:136).
 struct TexView {
     const float* data;
     int w, h, ch;
+    int row0, h_global;
+    const float* last_row;
 };
 
 // UniformGridInfo as the kernels see it.
@@ -109,6 +114,11 @@ struct WaveObj {
     int  tex_unit0 = -1;           // physical image bound to GL texture unit 0 (-1: unbound)
     bool evolve = true;
     float* simp_params = nullptr;  // device float4 (lambda, atten, beta, 0) for variant SIMP
+    // row-block decomposition (multi-GPU): the arrays hold global rows [row0, row0 + h) of a field
+    // that is h_global rows tall; last_row[i] = copy of the global last row of physical image i
+    int  row0 = 0, h_global = 64;
+    float* last_row[3] = {nullptr, nullptr, nullptr};
+    cwa_buf last_row_buf[3] = {-1, -1, -1};
     // TMA descriptors (scalar fast path): per physical image, halo box and plain box
     CUtensorMap tmap_halo[3];
     CUtensorMap tmap_core[3];
@@ -119,6 +129,7 @@ struct SphObj {
     bool live = false;
     cwa_buf particles = -1;
     int  n = 0;
+    int  capacity = 0;             // particles the scratch arrays were sized for (cwa_sph_set_count limit)
     cwa_grid grid = -1;            // -1: all-pairs
     cwa_wave wave = -1;            // sampler binding
     int  wave_image = -1;          // physical image, -1 unbound
@@ -276,21 +287,33 @@ __device__ __forceinline__ int cwa_tex_index(float f, int n)
     return (int)f;
 }
 
+__device__ __forceinline__ const float* cwa_tex_row(const TexView& t, int j)
+{
+    const int l = j - t.row0;
+    if ((unsigned)l < (unsigned)t.h) return t.data + (size_t)l * t.w * t.ch;
+    if (j == t.h_global - 1 && t.last_row != nullptr) return t.last_row;
+    return t.data + (size_t)(l < 0 ? 0 : t.h - 1) * t.w * t.ch;
+}
+
 // texture(wave_tex, (s,t)).r : GL_LINEAR, GL_CLAMP_TO_EDGE, LOD 0, full FP32 weights
 __device__ __forceinline__ float cwa_tex_bilinear(const TexView& t, float s, float tt)
 {
     if (t.data == nullptr) return 0.0f;
-    const int W = t.w, H = t.h, C = t.ch;
+    const int W = t.w, H = t.h_global, C = t.ch;
     float u = __fsub_rn(__fmul_rn(s, (float)W), 0.5f);
     float v = __fsub_rn(__fmul_rn(tt, (float)H), 0.5f);
     float fu = floorf(u), fv = floorf(v);
     float a = __fsub_rn(u, fu), b = __fsub_rn(v, fv);
     int i0 = cwa_tex_index(fu, W), i1 = cwa_tex_index(fu + 1.0f, W);
     int j0 = cwa_tex_index(fv, H), j1 = cwa_tex_index(fv + 1.0f, H);
-    float t00 = __ldg(t.data + ((size_t)j0 * W + i0) * C);
-    float t10 = __ldg(t.data + ((size_t)j0 * W + i1) * C);
-    float t01 = __ldg(t.data + ((size_t)j1 * W + i0) * C);
-    float t11 = __ldg(t.data + ((size_t)j1 * W + i1) * C);
+    // global row -> storage: local block, else the replicated global last row, else the nearest
+    // local row (only reachable when the caller under-sized the sampling halo)
+    const float* p0 = cwa_tex_row(t, j0);
+    const float* p1 = cwa_tex_row(t, j1);
+    float t00 = __ldg(p0 + (size_t)i0 * C);
+    float t10 = __ldg(p0 + (size_t)i1 * C);
+    float t01 = __ldg(p1 + (size_t)i0 * C);
+    float t11 = __ldg(p1 + (size_t)i1 * C);
     float r0 = __fadd_rn(t00, __fmul_rn(a, __fsub_rn(t10, t00)));
     float r1 = __fadd_rn(t01, __fmul_rn(a, __fsub_rn(t11, t01)));
     return __fadd_rn(r0, __fmul_rn(b, __fsub_rn(r1, r0)));

@@ -903,7 +903,7 @@ extern "C" int cwa_sph_create(cwa_ctx* ctx, cwa_buf particles, int n, cwa_grid g
         CWA_CHECK(g->max_particles >= n, "cwa_sph_create: grid capacity %d < %d particles", g->max_particles, n);
     }
     SphObj s;
-    s.live = true; s.particles = particles; s.n = n; s.grid = grid;
+    s.live = true; s.particles = particles; s.n = n; s.capacity = n; s.grid = grid;
     const size_t bytes = (size_t)(n > 0 ? n : 1) * 16;
     CWA_CUDA(cudaMalloc(&s.consts, sizeof(Sph3Const)));
     CWA_CUDA(cudaMalloc(&s.packA, bytes));

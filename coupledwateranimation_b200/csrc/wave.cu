@@ -188,11 +188,14 @@ wave_evolve_generic_kernel(const float* __restrict__ u0, const float* __restrict
 
 // InitWave: wave_comp.glsl:82-140 / Wave2D_cs.glsl:66-76
 __global__ void __launch_bounds__(256)
-wave_init_kernel(float* __restrict__ out, int W, int H, int ch, const float4* __restrict__ attr, int variant)
+wave_init_kernel(float* __restrict__ out, int W, int H_local, int ch, const float4* __restrict__ attr, int variant,
+                 int row0, int H)
 {
+    // (x, y) are GLOBAL image coordinates; a row block stores row y at local row y - row0
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= W || y >= H) return;
+    const int yl = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= W || yl >= H_local) return;
+    const int y = yl + row0;
     const float type = __ldg(attr).w;
     int c0x, c0y, c1x, c1y, c2x = 0, c2y = 0;
     bool third = false;
@@ -226,7 +229,7 @@ wave_init_kernel(float* __restrict__ out, int W, int H, int ch, const float4* __
     float d = fminf(dist(c0x, c0y), dist(c1x, c1y));
     if (third) d = fminf(d, dist(c2x, c2y));
     const float v = __fmul_rn(peak, cwa_smoothstep(e0, 0.0f, d));
-    float* o = out + ((size_t)y * W + x) * ch;
+    float* o = out + ((size_t)yl * W + x) * ch;
     o[0] = v;
     for (int c = 1; c < ch; c++) o[c] = 0.0f;
 }
@@ -322,7 +325,7 @@ int wave_dispatch_mode(cwa_ctx* ctx, WaveObj* w, int mode)
     CWA_CHECK(mode == CWA_MODE_INIT || mode == CWA_MODE_EVOLVE, "wave dispatch: unsupported uMode %d", mode);
     KScope kscope(ctx, mode == CWA_MODE_EVOLVE ? KID_WAVE : KID_OTHER);
     if (mode == CWA_MODE_INIT) {
-        wave_init_kernel<<<ggrid, gblock, 0, ctx->stream>>>(w->image[outi], w->w, w->h, w->ch, attr, w->variant);
+        wave_init_kernel<<<ggrid, gblock, 0, ctx->stream>>>(w->image[outi], w->w, w->h, w->ch, attr, w->variant, w->row0, w->h_global);
     } else if (mode == CWA_MODE_EVOLVE) {
         if (w->tma_ok) {
             static bool attr_set = false;
@@ -354,9 +357,12 @@ int wave_step_internal(cwa_ctx* ctx, WaveObj* w)
 
 TexView wave_tex_view(cwa_ctx* ctx, cwa_wave h, int image)
 {
-    TexView t{nullptr, 1, 1, 1};
+    TexView t{nullptr, 1, 1, 1, 0, 1, nullptr};
     WaveObj* w = get_wave(ctx, h);
-    if (w && image >= 0 && image < 3) { t.data = w->image[image]; t.w = w->w; t.h = w->h; t.ch = w->ch; }
+    if (w && image >= 0 && image < 3) {
+        t.data = w->image[image]; t.w = w->w; t.h = w->h; t.ch = w->ch;
+        t.row0 = w->row0; t.h_global = w->h_global; t.last_row = w->last_row[image];
+    }
     return t;
 }
 
@@ -369,6 +375,7 @@ extern "C" int cwa_wave_create(cwa_ctx* ctx, int width, int height, int channels
     CWA_CHECK(variant == CWA_WAVE_COUPLED || variant == CWA_WAVE_SIMP, "cwa_wave_create: unknown shader variant %d", variant);
     WaveObj w;
     w.live = true; w.w = width; w.h = height; w.ch = channels; w.variant = variant;
+    w.row0 = 0; w.h_global = height;
     const float simp[4] = {0.01f, 0.9995f, 0.001f, 1.0f};            // Wave2D_cs.glsl:17-19
     CWA_CUDA(cudaMalloc(&w.simp_params, 16));
     CWA_CUDA(cudaMemcpyAsync(w.simp_params, simp, 16, cudaMemcpyHostToDevice, ctx->stream));
@@ -388,6 +395,10 @@ extern "C" int cwa_wave_destroy(cwa_ctx* ctx, cwa_wave h)
         if (BufferObj* b = get_buffer(ctx, w->image_buf[i])) b->live = false;
     }
     cudaFree(w->simp_params);
+    for (int i = 0; i < 3; i++) {
+        if (w->last_row[i]) cudaFree(w->last_row[i]);
+        if (BufferObj* b = get_buffer(ctx, w->last_row_buf[i])) b->live = false;
+    }
     w->live = false;
     return 0;
 }
@@ -465,7 +476,8 @@ extern "C" int cwa_wave_resize(cwa_ctx* ctx, cwa_wave h, int nw, int nh)
     CWA_CHECK(nw >= 1 && nh >= 1, "cwa_wave_resize: bad size");
     CWA_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < 3; i++) { cudaFree(w->image[i]); w->image[i] = nullptr; }
-    w->w = nw; w->h = nh;
+    CWA_CHECK(w->row0 == 0 && w->h == w->h_global, "cwa_wave_resize: not supported on a row-block wave object");
+    w->w = nw; w->h = nh; w->h_global = nh;
     return wave_alloc_images(ctx, w);                                // ImageTexture::Resize: new storage, contents cleared
 }
 
@@ -540,5 +552,47 @@ extern "C" int cwa_wave_size(cwa_ctx* ctx, cwa_wave h, int* width, int* height, 
     if (width) *width = w->w;
     if (height) *height = w->h;
     if (channels) *channels = w->ch;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// row-block decomposition (multi-GPU): this rank stores global rows [row0, row0+rows)
+// of a field that is h_global rows tall (its owned block plus the sampling halos).  EVOLVE clamps
+// at the local array border; the caller overwrites the halo rows with the neighbours' owned rows
+// after every step, so only genuinely global borders keep the clamp.
+// ---------------------------------------------------------------------------------------------
+extern "C" int cwa_wave_create_block(cwa_ctx* ctx, int width, int h_global, int row0, int rows, int channels, int variant, cwa_wave* out)
+{
+    CWA_CHECK(ctx && out, "null argument");
+    *out = -1;
+    CWA_CHECK(width >= 1 && h_global >= 1 && rows >= 1 && row0 >= 0 && row0 + rows <= h_global,
+              "cwa_wave_create_block: rows [%d,%d) outside a field of %d rows", row0, row0 + rows, h_global);
+    CWA_CHECK(channels == 1 || channels == 4, "cwa_wave_create_block: channels must be 1 or 4");
+    CWA_CHECK(variant == CWA_WAVE_COUPLED || variant == CWA_WAVE_SIMP, "cwa_wave_create_block: unknown shader variant %d", variant);
+    WaveObj w;
+    w.live = true; w.w = width; w.h = rows; w.ch = channels; w.variant = variant;
+    w.row0 = row0; w.h_global = h_global;
+    const float simp[4] = {0.01f, 0.9995f, 0.001f, 1.0f};
+    CWA_CUDA(cudaMalloc(&w.simp_params, 16));
+    CWA_CUDA(cudaMemcpyAsync(w.simp_params, simp, 16, cudaMemcpyHostToDevice, ctx->stream));
+    CWA_TRY(wave_alloc_images(ctx, &w));
+    for (int i = 0; i < 3; i++) {
+        const size_t bytes = (size_t)width * channels * 4;
+        CWA_CUDA(cudaMalloc(&w.last_row[i], bytes));
+        CWA_CUDA(cudaMemsetAsync(w.last_row[i], 0, bytes, ctx->stream));
+        w.last_row_buf[i] = new_buffer(ctx, w.last_row[i], bytes, false);
+    }
+    ctx->waves.push_back(w);
+    *out = (int)ctx->waves.size() - 1;
+    return cwa_wave_reinit(ctx, *out);
+}
+
+extern "C" int cwa_wave_last_row_buffer(cwa_ctx* ctx, cwa_wave h, int image, cwa_buf* out)
+{
+    WaveObj* w = get_wave(ctx, h);
+    CWA_CHECK(w && out, "invalid wave handle %d", h);
+    CWA_CHECK(image >= 0 && image < 3, "image index %d out of range", image);
+    CWA_CHECK(w->last_row_buf[image] >= 0, "cwa_wave_last_row_buffer: not a row-block wave object");
+    *out = w->last_row_buf[image];
     return 0;
 }

@@ -162,6 +162,18 @@ CWA_API int cwa_bind_scene(cwa_ctx* ctx, cwa_sph s, cwa_wave w);
 CWA_API int sph_step(cwa_ctx* ctx, int nsteps);             /* ComputeShader::Dispatch x3 -> one call */
 CWA_API int wave_step(cwa_ctx* ctx, int nsteps);            /* StencilImage2DTripleBuffered::Compute   */
 
+/* ---- multi-GPU decomposition primitives (no reference counterpart: the reference is single-GPU) ---- */
+/* number of live particles at the front of the SSBO (owned + ghosts); <= the count given to cwa_sph_create */
+CWA_API int cwa_sph_set_count(cwa_ctx* ctx, cwa_sph s, int n);
+/* stable copy of the particles of src[0..n) whose pos[axis] satisfies the predicate into dst[dst_offset..]:
+ * kind 0: a <= x < b, 1: x < a, 2: x >= a, 3: !(x < a) && !(x >= b) (NaN stays).  *count = copied; synchronises */
+CWA_API int cwa_particles_copy_if(cwa_ctx* ctx, cwa_buf src, int n, int axis, int kind, float a, float b,
+                                  cwa_buf dst, int dst_offset, int* count);
+/* wave field stored as a row block: global rows [row0, row0+rows) of a field h_global rows tall (owned rows + halos) */
+CWA_API int cwa_wave_create_block(cwa_ctx* ctx, int w, int h_global, int row0, int rows, int channels, int variant, cwa_wave* out);
+/* replicated copy of the GLOBAL last row of physical image `image` (WaveNormal's uv+(0,1) tap clamps to it) */
+CWA_API int cwa_wave_last_row_buffer(cwa_ctx* ctx, cwa_wave w, int image, cwa_buf* out);
+
 /* ---- 2-D Koschier SPH on the uniform grid: SphUgrid (SphWave2D/StencilBuffer.cpp:138-179) ------ */
 CWA_API int cwa_sph2_create(cwa_ctx* ctx, int n, int variant, cwa_grid grid, cwa_sph2* out); /* Init + Reinit (MODE_INIT) */
 CWA_API int cwa_sph2_destroy(cwa_ctx* ctx, cwa_sph2 s);

@@ -1,0 +1,140 @@
+"""Multi-rank protocol on CPU: world_size 2 (and 3) over gloo, oracle as the compute backend.
+Checks that N ranks reproduce the 1-rank state (particles by id, wave field bit-exact) through ghost
+exchange, migration, wave halo refresh, the global-last-row broadcast and both coupling schedules."""
+import os
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+WAVE_W, WAVE_H = 32, 96
+NX, NY, NZ = 10, 5, 56
+GRID = ((0.0, -0.02, 0.0), (0.12, 0.2, 0.52), (6, 11, 26))
+FRAMES = 7
+
+
+def scene():
+    from oracle import oracle as O
+    prm = O.default_params3()
+    prm.upper[0], prm.upper[2] = 0.1, 0.5
+    prm.dt = 0.002                                    # big time step: particles really migrate across the slab faces in 7 frames
+    prm.gravity_y = -9.8
+    prm.gas_const = 20.0
+    prm.visc = 5.0
+    p = O.make_cube(NX, NY, NZ, prm)
+    rng = np.random.default_rng(99)
+    p["pos"][:, :3] += rng.uniform(-0.1, 0.1, (p.size, 3)).astype(np.float32) * np.float32(0.0085)
+    p["vel"][:, 2] = rng.uniform(-4.0, 4.0, p.size).astype(np.float32)       # strong z motion -> migration
+    p["vel"][:, 0] = rng.uniform(-0.5, 0.5, p.size).astype(np.float32)
+    p["extras"][:, 3] = np.arange(p.size, dtype=np.float32)                  # particle id rides in the unused extras.w
+    return prm, p
+
+
+def test_slab_plan_covers_rows_and_sizes_halos():
+    from coupledwateranimation_b200.distributed import SlabPlan
+    for world in (1, 2, 3, 4, 8):
+        plans = [SlabPlan.make(world, r, 8192, 8192, 2.0 / 28.0, 0.01) for r in range(world)]
+        assert plans[0].row_lo == 0 and plans[-1].row_hi == 8192
+        for a, b in zip(plans[:-1], plans[1:]):
+            assert a.row_hi == b.row_lo and abs(a.z_hi - b.z_lo) < 1e-12
+        for p in plans:
+            p.validate()
+            assert p.store_lo <= p.row_lo and p.store_hi >= p.row_hi
+            if world > 1 and p.rank < world - 1:
+                # upper halo covers ghost reach (2h) + WaveVelocity's +0.01 tap + bilinear footprint
+                assert p.halo_hi >= (2 * 0.01 * 8192 * 2.0 / 28.0) + 0.01 * 8192 + 1
+    with pytest.raises(AssertionError):
+        SlabPlan.make(64, 3, 32, 96, 2.0, 0.01).validate()     # slabs thinner than two ghost layers
+
+
+def _worker(rank, world, coupling, init_file, out_dir):
+    import torch.distributed as dist
+    from oracle_backend import OracleBackend
+    from coupledwateranimation_b200.distributed import DistributedCoupled, SlabPlan
+    if world > 1:
+        dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
+    prm, p = scene()
+    h = prm.smoothing_coeff * prm.particle_radius
+    plan = SlabPlan.make(world, rank, WAVE_W, WAVE_H, prm.uv_scale, h)
+    be = OracleBackend(plan, p.size, prm, GRID)
+    z = p["pos"][:, 2]
+    be.upload_owned(p[(z >= plan.z_lo) & (z < plan.z_hi)])
+    drv = DistributedCoupled(be, plan, dist if world > 1 else None)
+    drv.init_wave_halos()
+    n0 = be.n_owned
+    drv.step(FRAMES, coupling)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), particles=be.download_owned(), wave=be.full_wave(), n0=n0)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _run(world, coupling):
+    import torch.multiprocessing as mp
+    with tempfile.TemporaryDirectory() as d:
+        init_file = os.path.join(d, "rendezvous")
+        if world == 1:
+            _worker(0, 1, coupling, init_file, d)
+        else:
+            mp.spawn(_worker, args=(world, coupling, init_file, d), nprocs=world, join=True)
+        parts, waves, moved = [], [], 0
+        for r in range(world):
+            f = np.load(os.path.join(d, f"rank{r}.npz"))
+            parts.append(f["particles"]); waves.append(f["wave"])
+            moved += abs(int(f["n0"]) - f["particles"].size)
+        P = np.concatenate(parts)
+        order = np.argsort(P["extras"][:, 3])
+        return P[order], np.concatenate(waves), moved
+
+
+def _assert_states_match(got, ref, ok):
+    """Summation order differs between decompositions, and the fixture's large time step amplifies it; a branch
+    of integrate_comp (surface clamp y < tex_height, walls, foam) may flip for a particle that sits on the
+    threshold, so a handful of outliers (<= 0.5 %) are tolerated while everything else must agree tightly."""
+    for f, tol in (("pos", 1e-4), ("vel", 2e-3)):
+        a, b = got[f][ok, :3].astype(np.float64), ref[f][ok, :3].astype(np.float64)
+        scale = np.sqrt(np.mean(b ** 2))
+        bad = (np.abs(a - b).max(1) > tol * scale)
+        assert bad.mean() <= 0.005, (f, int(bad.sum()), np.abs(a - b).max(), scale)
+
+
+@pytest.mark.parametrize("coupling", [0, 1])
+def test_two_ranks_reproduce_one_rank(coupling):
+    ref, ref_wave, _ = _run(1, coupling)
+    got, got_wave, moved = _run(2, coupling)
+    assert got.size == ref.size == NX * NY * NZ, "particle count conserved across migration"
+    assert np.array_equal(got["extras"][:, 3], ref["extras"][:, 3]), "every id exactly once"
+    assert moved > 0, "the fixture must actually migrate particles across the slab face"
+    assert np.array_equal(got_wave.view(np.uint32), ref_wave.view(np.uint32)), "wave field bit-exact through halo refresh"
+    # the oracle backend poisons every texel outside the stored halos / last row with NaN, so an under-sized halo
+    # would show up as EXTRA NaN particles; the physics' own NaNs (coincident clamped particles) must be the same set
+    nan_ref, nan_got = np.isnan(ref["pos"]).any(1), np.isnan(got["pos"]).any(1)
+    assert np.array_equal(nan_ref, nan_got)
+    ok = ~nan_ref
+    _assert_states_match(got, ref, ok)
+
+
+def test_single_rank_driver_equals_the_oracle_coupled_driver():
+    from oracle import oracle as O
+    prm, p = scene()
+    ref, ref_wave, _ = _run(1, 0)
+    oc = O.Coupled(p.size, WAVE_W, WAVE_H, 1, prm, O.COUPLING_AS_SHIPPED, grid=GRID)
+    oc.particles[:] = p
+    oc.step(FRAMES)
+    assert np.array_equal(ref.view(np.uint8), oc.particles.view(np.uint8))
+    assert np.array_equal(ref_wave, oc.wave(0))
+    oc.close()
+
+
+def test_three_ranks_reproduce_one_rank():
+    ref, ref_wave, _ = _run(1, 1)
+    got, got_wave, _ = _run(3, 1)
+    assert got.size == ref.size and np.array_equal(got["extras"][:, 3], ref["extras"][:, 3])
+    assert np.array_equal(got_wave.view(np.uint32), ref_wave.view(np.uint32))
+    ok = ~np.isnan(ref["pos"]).any(1)
+    assert np.array_equal(~ok, np.isnan(got["pos"]).any(1))
+    _assert_states_match(got, ref, ok)
