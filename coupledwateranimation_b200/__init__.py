@@ -206,11 +206,12 @@ class Buffer:
 class UniformGrid:
     """UniformGridSph2D (dim 2) / UgridParticles3D (dim 3): ctor + Init + CollisionQuery/BuildGrid."""
 
-    def __init__(self, ctx: Context, dim: int, mn, mx, num_cells, max_particles: int):
+    def __init__(self, ctx: Context, dim: int, mn, mx, num_cells, max_particles: int, compact_index: bool = False):
         self.ctx, self.dim, self.max_particles = ctx, dim, max_particles
         g = C.c_int(-1)
         mn_a = (C.c_float * dim)(*mn); mx_a = (C.c_float * dim)(*mx); nc_a = (C.c_int * dim)(*num_cells)
-        check(ctx.lib.cwa_grid_create(ctx.h, dim, mn_a, mx_a, nc_a, max_particles, C.byref(g)))
+        # compact_index: k-stride Nz instead of the reference's Nx (CWA_GRID_COMPACT_INDEX), for slab-local grids
+        check(ctx.lib.cwa_grid_create(ctx.h, dim | (16 if compact_index else 0), mn_a, mx_a, nc_a, max_particles, C.byref(g)))
         self.h = g.value
         info, total = _capi.GridInfo(), C.c_int()
         check(ctx.lib.cwa_grid_get_info(ctx.h, self.h, C.byref(info), C.byref(total)))

@@ -39,7 +39,7 @@ grid_hash_count_kernel(const char* __restrict__ particles, int stride_bytes, int
             // again, so the canonical choice (shared with the oracle) is: not inserted.
             int ci, cj, ck;
             cwa_cell3(g, p.x, p.y, p.z, ci, cj, ck);
-            cell = (ci * g.n[1] + cj) * g.n[0] + ck;           // Index(i,j,k) ugrid_particles_cs.glsl:105-108 (sic)
+            cell = (ci * g.n[1] + cj) * g.kstride + ck;        // Index(i,j,k) ugrid_particles_cs.glsl:105-108: kstride = Nx (sic)
         }
         cell_of[i] = cell;
     }
@@ -282,9 +282,11 @@ extern "C" int cwa_grid_create(cwa_ctx* ctx, int dim, const float* mn, const flo
                                int max_particles, cwa_grid* out)
 {
     CWA_CHECK(ctx && mn && mx && num_cells && out, "null argument");
-    CWA_CHECK(dim == 2 || dim == 3, "cwa_grid_create: dim must be 2 or 3");
+    CWA_CHECK((dim & 15) == 2 || (dim & 15) == 3, "cwa_grid_create: dim must be 2 or 3");
     CWA_CHECK(max_particles > 0, "cwa_grid_create: max_particles must be positive");
     *out = -1;
+    const bool compact = (dim >= 16);            // dim | CWA_GRID_COMPACT_INDEX: k-stride Nz instead of the reference's Nx
+    dim &= 15;
     GridObj g;
     g.live = true; g.dim = dim; g.max_particles = max_particles;
     long long C = 1;
@@ -295,12 +297,18 @@ extern "C" int cwa_grid_create(cwa_ctx* ctx, int dim, const float* mn, const flo
         // mCellSize = (mMax - mMin) / vec(mNumCells), FP32 on the host (UniformGridGpu2D.cpp:160)
         g.info.cell_size[a] = (mx[a] - mn[a]) / (float)num_cells[a];
     }
+    int kstride = 1;
     if (dim == 3) {
-        // The reference's 3-D index (i*Ny + j)*Nx + k aliases cells when Nz > Nx; refuse loudly.
-        CWA_CHECK(num_cells[2] <= num_cells[0],
-                  "cwa_grid_create: Nz (%d) > Nx (%d) aliases cells under the reference index formula (i*Ny+j)*Nx+k",
-                  num_cells[2], num_cells[0]);
-        C = (long long)num_cells[0] * num_cells[1] * num_cells[0];   // covers every index the formula can produce
+        if (compact) {
+            kstride = num_cells[2];
+        } else {
+            // The reference's 3-D index (i*Ny + j)*Nx + k aliases cells when Nz > Nx; refuse loudly.
+            CWA_CHECK(num_cells[2] <= num_cells[0],
+                      "cwa_grid_create: Nz (%d) > Nx (%d) aliases cells under the reference index formula (i*Ny+j)*Nx+k",
+                      num_cells[2], num_cells[0]);
+            kstride = num_cells[0];
+        }
+        C = (long long)num_cells[0] * num_cells[1] * kstride;        // covers every index the formula can produce
     } else {
         C = (long long)num_cells[0] * num_cells[1];
     }
@@ -311,7 +319,7 @@ extern "C" int cwa_grid_create(cwa_ctx* ctx, int dim, const float* mn, const flo
         g.view.n[a] = (a < dim) ? g.info.num_cells[a] : 1;
         g.view.inv_cell[a] = 1.0f / g.view.cell[a];
     }
-    g.view.dim = dim; g.view.num_cells = (int)C;
+    g.view.dim = dim; g.view.num_cells = (int)C; g.view.kstride = kstride;
 
     const size_t tiles = scan_num_tiles((int)C);
     // [counter C ints (padded to 8 B)][ticket 2 ints][tile_state tiles x 8 B]

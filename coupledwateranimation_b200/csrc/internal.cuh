@@ -67,6 +67,7 @@ struct GridView {
     int   n[3];          // Nx, Ny, Nz (Nz = 1 in 2-D)
     int   dim;           // 2 or 3
     int   num_cells;     // allocated/scanned linear cells
+    int   kstride;       // 3-D: stride of k in the linear index -- Nx as in the reference (sic), Nz when compact
     // linear index: 3-D (i*Ny + j)*Nx + k (ugrid_particles_cs.glsl:105-108), 2-D i*Ny + j
     // (uniform_grid_sph_cs.glsl:149-152).  A "row" is the run of cells sharing everything but the
     // fastest coordinate (k in 3-D, j in 2-D); rows are contiguous in the sorted particle order.

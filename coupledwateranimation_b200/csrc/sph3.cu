@@ -272,10 +272,10 @@ __device__ __forceinline__ void window_bounds(const GridView& g, const int* __re
 {
     int i, j, k;
     cwa_cell3(g, pfirst.x, pfirst.y, pfirst.z, i, j, k);
-    const int lin_f = (i * g.n[1] + j) * g.n[0] + k;
+    const int lin_f = (i * g.n[1] + j) * g.kstride + k;
     cwa_cell3(g, plast.x, plast.y, plast.z, i, j, k);
-    const int lin_l = (i * g.n[1] + j) * g.n[0] + k;
-    const int si = g.n[1] * g.n[0], sj = g.n[0];
+    const int lin_l = (i * g.n[1] + j) * g.kstride + k;
+    const int si = g.n[1] * g.kstride, sj = g.kstride;
     const int off = (w / 3 - 1) * si + (w % 3 - 1) * sj;
     int lo_lin = lin_f + off - 1, hi_lin = lin_l + off + 1;
     lo_lin = max(lo_lin, 0); hi_lin = min(hi_lin, g.num_cells - 1);
@@ -379,7 +379,7 @@ sph3_density_grid_kernel(const float4* __restrict__ posS, const float4* __restri
     float rho = 0.0f;
     for (int i = q.i0; i <= q.i1; i++) {
         for (int j = q.j0; j <= q.j1; j++) {
-            const int base = (i * g.n[1] + j) * g.n[0];
+            const int base = (i * g.n[1] + j) * g.kstride;
             const int g0 = __ldg(offset + base + q.k0), g1 = __ldg(offset + base + q.k1 + 1);
             const int shift = row_shift(bw, q, i, j, g0, g1);
             if (shift != INT_MIN) {
@@ -454,7 +454,7 @@ sph3_force_grid_kernel(const float4* __restrict__ packA, const float4* __restric
     float fpx = 0.f, fpy = 0.f, fpz = 0.f, fvx = 0.f, fvy = 0.f, fvz = 0.f;
     for (int i = q.i0; i <= q.i1; i++) {
         for (int j = q.j0; j <= q.j1; j++) {
-            const int base = (i * g.n[1] + j) * g.n[0];
+            const int base = (i * g.n[1] + j) * g.kstride;
             const int g0 = __ldg(offset + base + q.k0), g1 = __ldg(offset + base + q.k1 + 1);
             const int shift = row_shift(bw, q, i, j, g0, g1);
             const float4* sa = (shift != INT_MIN) ? (const float4*)(stageA + shift) : packA;
@@ -675,7 +675,7 @@ sph3_neighbour_count_grid_kernel(const float4* __restrict__ posS, const int* __r
     int cnt = 0;
     for (int i = i0; i <= i1; i++)
         for (int j = j0; j <= j1; j++) {
-            const int base = (i * g.n[1] + j) * g.n[0];
+            const int base = (i * g.n[1] + j) * g.kstride;
             const int g0 = __ldg(offset + base + k0), g1 = __ldg(offset + base + k1 + 1);
             for (int q = g0; q < g1; q++) {
                 const float4 o = __ldg(posS + q);

@@ -224,7 +224,7 @@ class CudaBackend:
         self.device = torch.device("cuda", ctx.device)
         self.capacity = capacity
         self.buffer = cwa.Buffer(ctx, nbytes=capacity * PARTICLE_BYTES)
-        self.grid = cwa.UniformGrid(ctx, 3, grid_min, grid_max, grid_cells, capacity)
+        self.grid = cwa.UniformGrid(ctx, 3, grid_min, grid_max, grid_cells, capacity, compact_index=True)
         self.sph = cwa.Sph(ctx, capacity, self.grid, buffer=self.buffer)
         self.scratch = {k: cwa.Buffer(ctx, nbytes=capacity * PARTICLE_BYTES) for k in ("l", "r", "keep", "rl", "rr")}
         self.wave = cwa.StencilImage2DTripleBuffered.create_block(ctx, plan.wave_w, plan.wave_h, plan.store_lo, plan.rows_stored, wave_ch)

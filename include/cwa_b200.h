@@ -68,6 +68,9 @@ enum { CWA_COUPLING_AS_SHIPPED = 0, CWA_COUPLING_LATEST = 1 };
 enum { CWA_NEIGHBOURS_ALL_PAIRS = 0, CWA_NEIGHBOURS_GRID = 1 };
 enum { CWA_SPH2_KOSCHIER = 0, CWA_SPH2_WAVE = 1 };
 enum { CWA_GRID_COUNTER = 0, CWA_GRID_OFFSET = 1, CWA_GRID_INDEX_LIST = 2, CWA_GRID_CELL_OF = 3 };
+/* OR into `dim` of cwa_grid_create: linear index (i*Ny + j)*Nz + k instead of the reference's (i*Ny + j)*Nx + k
+ * (ugrid_particles_cs.glsl:105-108, sic).  Identical when Nx == Nz; used by slab-local grids of the multi-GPU path. */
+enum { CWA_GRID_COMPACT_INDEX = 16 };
 
 /* ---- context --------------------------------------------------------------------------------- */
 CWA_API const char* cwa_last_error(void);
