@@ -138,21 +138,36 @@ def build_scene(cwa, ctx):
     return grid, sph, wave
 
 
-def oracle_scene(O):
+def scaled_scene(world: int):
+    """The workload of `--gpus world`: C4 itself for 1 GPU, C4 grown by sqrt(world) in x and z otherwise (weak scaling)."""
+    if world <= 1:
+        return dict(nx=NX, ny=NY, nz=NZ, wave=WAVE, uv=UV_SCALE, box=BOX_UPPER[0], gmin=GRID_MIN, gmax=GRID_MAX, gn=GRID_N)
+    import math
+    f = math.sqrt(world)
+    n = int(round(64 * S * f))
+    box = 0.55 * S * f
+    return dict(nx=n, ny=NY, nz=n, wave=int(round(WAVE * f / 4)) * 4, uv=2.0 / (S * f), box=box,
+                gmin=(0.0, -0.02, 0.0), gmax=(box, 1.0, box), gn=(int(round(192 * f)), 51, int(round(192 * f))))
+
+
+def oracle_scene(O, world: int = 1):
+    sc = scaled_scene(world)
     prm = O.default_params3()
     for a in range(4):
         prm.upper[a] = BOX_UPPER[a]
         prm.lower[a] = BOX_LOWER[a]
-    prm.uv_scale = UV_SCALE
-    oc = O.Coupled(N_PARTICLES, WAVE, WAVE, 1, prm, COUPLING, grid=(GRID_MIN, GRID_MAX, GRID_N))
-    oc.particles[:] = O.make_cube(NX, NY, NZ, prm)
-    return oc
+    prm.upper[0] = prm.upper[2] = sc["box"]
+    prm.uv_scale = sc["uv"]
+    n = sc["nx"] * sc["ny"] * sc["nz"]
+    oc = O.Coupled(n, sc["wave"], sc["wave"], 1, prm, COUPLING, grid=(sc["gmin"], sc["gmax"], sc["gn"]))
+    oc.particles[:] = O.make_cube(sc["nx"], sc["ny"], sc["nz"], prm)
+    return oc, n
 
 
-def cpu_reference_run(steps: int, warmup: int):
+def cpu_reference_run(steps: int, warmup: int, world: int = 1):
     """The reference's CPU implementation of the path = the oracle (no GL stack exists)."""
     from oracle import oracle as O
-    oc = oracle_scene(O)
+    oc, n = oracle_scene(O, world)
     cores = O.lib().orc_num_threads()
     for _ in range(warmup):
         oc.step(1)
@@ -161,7 +176,7 @@ def cpu_reference_run(steps: int, warmup: int):
         oc.step(1)
     dt = time.perf_counter() - t0
     oc.close()
-    return dt, cores
+    return dt, cores, n
 
 
 def run_reference(args):
@@ -170,16 +185,18 @@ def run_reference(args):
         return
     steps, warmup = max(1, args.steps), max(0, args.warmup)
     # bounded: a full C4 frame costs a few seconds on the host cores; cap the frame count so the run ends in minutes
-    steps_run, warm_run = min(steps, 40), min(warmup, 3)
-    dt, cores = cpu_reference_run(steps_run, warm_run)
+    world = max(1, args.gpus)
+    steps_run, warm_run = min(steps, max(4, 40 // world)), min(warmup, 3)
+    dt, cores, n_ref = cpu_reference_run(steps_run, warm_run, world)
     ms = dt / steps_run * 1e3
-    value = N_PARTICLES * steps_run / dt
-    sample = f"{steps_run} full C4 frames (of --steps {steps}) after {warm_run} warm-up, OpenMP on {cores} host threads"
+    value = n_ref * steps_run / dt
+    sample = f"{steps_run} full frames of the {n_ref}-particle scene (of --steps {steps}) after {warm_run} warm-up, OpenMP on {cores} host threads"
     line = {
         "impl": "reference", "metric": "particle_updates_per_sec", "value": value, "unit": "particle-updates/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "steps_per_sec": 1e3 / ms,
-        "config": {"workload": WORKLOAD, "note": "CPU restatement of the reference GLSL (no Mesa/llvmpipe in image)"},
+        "config": {"workload": WORKLOAD if world == 1 else f"C4 scaled by sqrt({world}) in x and z: {n_ref} particles (weak-scaling workload of --gpus {world})",
+                   "note": "CPU restatement of the reference GLSL (no Mesa/llvmpipe in image)"},
         "cpu_baseline": {"value": value, "unit": "particle-updates/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -200,6 +217,7 @@ def run_native(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        return run_native_distributed(args, world, rank, local_rank, torch, dist, cwa)
 
     def barrier():
         if world > 1:
@@ -300,7 +318,7 @@ def run_native(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         n_cpu = 20
-        dt, cores = cpu_reference_run(n_cpu, 1)
+        dt, cores, _n = cpu_reference_run(n_cpu, 1)
         cpu = {"value": N_PARTICLES * n_cpu / dt, "unit": "particle-updates/s", "cores": cores, "kind": "port",
                "sample": f"{n_cpu} full C4 frames after 1 warm-up frame, CPU restatement of the reference GLSL (OpenMP, {cores} threads)"}
 
@@ -324,6 +342,151 @@ def run_native(args):
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_native_distributed(args, world, rank, local_rank, torch, dist, cwa):
+    """N > 1: weak scaling of the slab-decomposed coupled step (coupledwateranimation_b200.distributed).
+    The scene grows by sqrt(N) in x and z (lattice, box, wave grid, uv scale), so every GPU keeps about
+    one C4 worth of work: ~1 M particles and ~2048^2/N... wave rows x sqrt(N) wider."""
+    import math
+
+    from coupledwateranimation_b200.distributed import CudaBackend, DistributedCoupled, SlabPlan
+
+    K, W = max(1, args.steps), max(3, args.warmup)
+    f = math.sqrt(world)
+    s_n = S * f
+    nxg = nzg = int(round(64 * S * f))
+    wave_n = int(round(WAVE * f / 4)) * 4
+    uv = 2.0 / s_n
+    box = 0.55 * s_n
+    h = 0.01
+    plan = SlabPlan.make(world, rank, wave_n, wave_n, uv, h)
+    sp = np.float32(np.float32(2.0 * 0.85) * np.float32(0.005))
+    ks = np.arange(nzg, dtype=np.float32) * sp
+    kk = np.nonzero((ks >= plan.z_lo) & (ks < plan.z_hi))[0]
+    i, j, k = np.meshgrid(np.arange(nxg, dtype=np.float32), np.arange(NY, dtype=np.float32), kk.astype(np.float32), indexing="ij")
+    own = np.zeros(i.size, cwa.PARTICLE)
+    own["pos"][:, 0] = i.ravel() * sp; own["pos"][:, 1] = j.ravel() * sp; own["pos"][:, 2] = k.ravel() * sp; own["pos"][:, 3] = 1.0
+    own["extras"][:] = (1000.0, 0.0, 500.0, 50.0)
+    del i, j, k
+
+    ctx = cwa.Context(local_rank)
+    ctx.set_boundary(upper=(box, 1.0, box, 500.0), lower=BOX_LOWER)
+    ctx.set_sim_constants(uv_scale=uv)
+    zl = max(0.0, plan.z_lo - 0.06) if rank > 0 else 0.0
+    zh = min(box, plan.z_hi + 0.06) if rank < world - 1 else box
+    ncx = int(round(192 * f))
+    ncz = max(4, int(math.ceil((zh - zl) / (box / ncx))))
+    be = CudaBackend(cwa, ctx, plan, int(own.size * 1.25) + 100000, (0.0, -0.02, zl), (box, 1.0, zh), (ncx, 51, ncz))
+    be.upload_owned(own)
+    n_global = nxg * NY * nzg
+    drv = DistributedCoupled(be, plan, dist)
+    drv.init_wave_halos()
+
+    sampler = ClockSampler(local_rank)
+    drv.step(W, COUPLING)
+    ctx.synchronize()
+    if rank == 0:
+        sampler.start()
+    dist.barrier(); ctx.synchronize()
+    launches0 = ctx.launch_count
+    ctx.timer_begin()
+    drv.step(K, COUPLING)
+    ms_total = ctx.timer_end()
+    launches = ctx.launch_count - launches0
+    dist.barrier()
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
+    dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+    t_end = time.time() + 1.0
+    while time.time() < t_end:
+        drv.step(20, COUPLING)
+    clocks = sampler.stop() if rank == 0 else None
+
+    ctx.profile_begin()
+    drv.step(K, COUPLING)
+    prof = ctx.profile_end()
+
+    # end to end: every rank's particle slab and wave rows live in pinned HOST buffers between steps
+    import ctypes as C
+    cap = be.capacity
+    pin_p = torch.empty(cap * cwa.PARTICLE.itemsize, dtype=torch.uint8).pin_memory()
+    row_bytes = wave_n * 4
+    pin_w = [torch.empty(plan.rows_stored * wave_n, dtype=torch.float32).pin_memory() for _ in range(2)]
+    host_p = pin_p.numpy().view(cwa.PARTICLE)
+    host_w = [w_.numpy().reshape(plan.rows_stored, wave_n) for w_ in pin_w]
+    host_p[:be.n_owned] = be.download_owned()
+    host_w[0][:] = be.wave.read_role(0); host_w[1][:] = be.wave.read_role(1)
+    lib, hnd = ctx.lib, ctx.h
+    moved = [0, 0]
+
+    def e2e_step():
+        n = be.n_owned
+        cwa.check(lib.cwa_buffer_sub_data(hnd, be.buffer.h, 0, n * 64, C.c_void_p(host_p.ctypes.data)))
+        cwa.check(lib.cwa_wave_write_image(hnd, be.wave.h, be.wave.role_image(0), C.c_void_p(host_w[0].ctypes.data)))
+        cwa.check(lib.cwa_wave_write_image(hnd, be.wave.h, be.wave.role_image(1), C.c_void_p(host_w[1].ctypes.data)))
+        drv.step(1, COUPLING)
+        n2 = be.n_owned
+        cwa.check(lib.cwa_buffer_read(hnd, be.buffer.h, 0, n2 * 64, C.c_void_p(host_p.ctypes.data)))
+        host_w[0], host_w[1] = host_w[1], host_w[0]
+        cwa.check(lib.cwa_wave_read_image(hnd, be.wave.h, be.wave.role_image(0), C.c_void_p(host_w[0].ctypes.data)))
+        moved[0] += n * 64 + 2 * plan.rows_stored * row_bytes
+        moved[1] += n2 * 64 + plan.rows_stored * row_bytes
+    for _ in range(3):
+        e2e_step()
+    moved[0] = moved[1] = 0
+    dist.barrier(); ctx.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        e2e_step()
+    ctx.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s, float(moved[0]) / K, float(moved[1]) / K], dtype=torch.float64, device="cuda")
+    tm = t.clone()
+    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    e2e_s = float(tm[0].item())
+    h2d, d2h = int(t[1].item()), int(t[2].item())
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        n_local = be.n_owned + be.n_ghost
+        c_cells = be.grid.num_cells_total
+        g_local = plan.rows_stored * wave_n
+        kern = []
+        tot_ms = sum(v[0] for v in prof.values()) or 1.0
+        for name, (ms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+            pp, pc, pw = ALGO_BYTES.get(name, (0, 0, 0))
+            per_launch = pp * n_local + pc * c_cells + pw * g_local
+            avg_ms = ms / cnt
+            gbs = per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+            kern.append({"kernel": name, "launches": cnt, "avg_us": avg_ms * 1e3, "share": ms / tot_ms, "algo_bytes": per_launch,
+                         "achieved_gbs": gbs, "frac": gbs / peak})
+        dom = kern[0]
+        ms_step = ms_total / K
+        line = {
+            "metric": "particle_updates_per_sec", "value": n_global * K / (ms_total * 1e-3), "unit": "particle-updates/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "steps_per_sec": 1e3 / ms_step,
+            "config": {"workload": f"C4 scaled by sqrt({world}) in x and z: {n_global} particles ({nxg}x{NY}x{nzg} lattice), wave {wave_n}^2 scalar, "
+                                   f"coupling AS_SHIPPED, grid cells of 2h", "per_gpu_particles": n_global // world,
+                       "parallelism": f"z-slab decomposition x{world}: ghost layer 2h + migration (NCCL p2p), wave row blocks with sampling halos + last-row broadcast",
+                       "l2": "working set > 126 MB L2 per GPU: inputs larger than L2, no flush needed",
+                       "timing": "cudaEvent on each rank's context stream around K coupled frames (communication included), max over ranks"},
+            "clocks": clocks,
+            "e2e": {"value": n_global * K / e2e_s, "unit": "particle-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_s / K * 1e3},
+            "gpu_launches": int(lt.item()),
+            "roofline": {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
+                         "traffic": None, "peak_source": peak_src, "note": "rank 0's kernels; neighbour loops are FP32-pipe bound"},
+            "roofline_kernels": kern,
+            "cpu_baseline": None,
+        }
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 def main():
