@@ -105,6 +105,9 @@ SIGNATURES = {
     "wave_step": (_I, [_P, _I]),
     "cwa_sph_set_count": (_I, [_P, _I, _I]),
     "cwa_particles_copy_if": (_I, [_P, _I, _I, _I, _I, _F, _F, _I, _I, _IP]),
+    "cwa_slab_pack": (_I, [_P, _I, _I, _F, _F, _F, _I, _I, _I, _I]),
+    "cwa_slab_unpack": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _IP]),
+    "cwa_slab_compact": (_I, [_P, _I, _I, _I, _IP]),
     "cwa_wave_create_block": (_I, [_P, _I, _I, _I, _I, _I, _I, _IP]),
     "cwa_wave_last_row_buffer": (_I, [_P, _I, _I, _IP]),
     "cwa_sph2_create": (_I, [_P, _I, _I, _I, _IP]),

@@ -4,6 +4,7 @@
 // single-pass look-back scan the grid uses -> 64-byte record copy), so results do not depend on
 // scheduling and the packed send buffers are contiguous (one NCCL send per neighbour).
 #include "internal.cuh"
+#include <math_constants.h>
 
 // predicate kinds on the coordinate x = pos[axis]
 //   0: a <= x < b        (band: ghost layer of a slab face)
@@ -109,5 +110,162 @@ extern "C" int cwa_sph_set_count(cwa_ctx* ctx, cwa_sph h, int n)
     }
     s->n = n;
     s->snapshot_valid = false;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// lean per-frame exchange (one message per neighbour and frame, counts travel in the header)
+//
+// message layout (floats / ints, 64-byte records):
+//   record 0            header: int mig_count, int ghost_count, int overflow
+//   records 1 .. cap_mig            migrants  (left the sender's slab through this face)
+//   records 1+cap_mig .. +cap_ghost ghosts    (within `band` of the face, still owned by the sender)
+// A migrant is marked DEAD in the sender's SSBO (pos = NaN, pos.w = CWA_DEAD_W): the grid build
+// leaves NaN positions out, so dead slots cost nothing and no compaction pass is needed per frame.
+// ---------------------------------------------------------------------------------------------
+#define CWA_DEAD_W (-1.0f)
+
+__device__ __forceinline__ bool slot_dead(const float4 p) { return p.w == CWA_DEAD_W && !(p.x == p.x); }
+
+__device__ __forceinline__ void copy_record(float4* __restrict__ dst, const float4* __restrict__ src)
+{
+    const float4 a = src[0], b = src[1], c = src[2], d = src[3];
+    dst[0] = a; dst[1] = b; dst[2] = c; dst[3] = d;
+}
+
+__global__ void __launch_bounds__(256)
+slab_pack_kernel(float4* __restrict__ aos, int n_owned, float z_lo, float z_hi, float band, int has_left, int has_right,
+                 float4* __restrict__ msg_l, float4* __restrict__ msg_r, int cap_mig, int cap_ghost)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_owned) return;
+    const float4 p = aos[(size_t)i * 4];
+    if (slot_dead(p)) return;
+    const float z = p.z;                                   // NaN z: every test below is false -> stays
+    float4* msg = nullptr;
+    bool migrate = false;
+    if (has_left && z < z_lo + band) { msg = msg_l; migrate = z < z_lo; }
+    else if (has_right && z >= z_hi - band) { msg = msg_r; migrate = z >= z_hi; }
+    if (msg == nullptr) return;
+    int* hdr = reinterpret_cast<int*>(msg);
+    const int slot = atomicAdd(hdr + (migrate ? 0 : 1), 1);
+    const int cap = migrate ? cap_mig : cap_ghost;
+    if (slot >= cap) { atomicExch(hdr + 2, 1); return; }    // overflow: reported to the host, particle stays put
+    copy_record(msg + 4 * (size_t)(1 + (migrate ? 0 : cap_mig) + slot), aos + (size_t)i * 4);
+    if (migrate) aos[(size_t)i * 4] = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CWA_DEAD_W);
+}
+
+// append the migrants of both received messages behind the owned range, then the ghosts behind them:
+// the received ghosts AND the particles this rank itself just sent away as migrants (the new owner
+// packed its message before adopting them, so they are not in its ghost list this frame, but they
+// still sit within 2h of the face and are needed as neighbours here).
+__global__ void __launch_bounds__(256)
+slab_unpack_kernel(float4* __restrict__ aos, int n_owned, int capacity, const float4* __restrict__ rcv_l,
+                   const float4* __restrict__ rcv_r, const float4* __restrict__ snd_l, const float4* __restrict__ snd_r,
+                   int cap_mig, int cap_ghost, int* __restrict__ counts)
+{
+    const int* hl = reinterpret_cast<const int*>(rcv_l);
+    const int* hr = reinterpret_cast<const int*>(rcv_r);
+    const int ml = rcv_l ? min(hl[0], cap_mig) : 0, gl = rcv_l ? min(hl[1], cap_ghost) : 0;
+    const int mr = rcv_r ? min(hr[0], cap_mig) : 0, gr = rcv_r ? min(hr[1], cap_ghost) : 0;
+    const int sl = snd_l ? min(reinterpret_cast<const int*>(snd_l)[0], cap_mig) : 0;
+    const int sr = snd_r ? min(reinterpret_cast<const int*>(snd_r)[0], cap_mig) : 0;
+    const int total = ml + mr + gl + gr + sl + sr;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) {
+        counts[0] = n_owned + ml + mr;                                     // owned range after adoption
+        counts[1] = n_owned + total;                                       // owned + ghosts
+        counts[2] = (rcv_l ? hl[2] : 0) | (rcv_r ? hr[2] : 0) | ((n_owned + total > capacity) ? 2 : 0);
+        counts[3] = ml + mr;
+    }
+    if (t >= total || n_owned + total > capacity) return;
+    const float4* src;
+    int u = t;
+    if (u < ml) src = rcv_l + 4 * (size_t)(1 + u);
+    else if ((u -= ml) < mr) src = rcv_r + 4 * (size_t)(1 + u);
+    else if ((u -= mr) < gl) src = rcv_l + 4 * (size_t)(1 + cap_mig + u);
+    else if ((u -= gl) < gr) src = rcv_r + 4 * (size_t)(1 + cap_mig + u);
+    else if ((u -= gr) < sl) src = snd_l + 4 * (size_t)(1 + u);
+    else src = snd_r + 4 * (size_t)(1 + (u - sl));
+    copy_record(aos + 4 * (size_t)(n_owned + t), src);
+}
+
+extern "C" int cwa_slab_pack(cwa_ctx* ctx, cwa_buf particles, int n_owned, float z_lo, float z_hi, float band,
+                             cwa_buf msg_left, cwa_buf msg_right, int cap_mig, int cap_ghost)
+{
+    BufferObj* p = get_buffer(ctx, particles);
+    BufferObj* ml = get_buffer(ctx, msg_left);
+    BufferObj* mr = get_buffer(ctx, msg_right);
+    CWA_CHECK(p && n_owned >= 0 && (size_t)n_owned * 64 <= p->bytes, "cwa_slab_pack: bad particle buffer / count");
+    const size_t need = (size_t)(1 + cap_mig + cap_ghost) * 64;
+    CWA_CHECK((msg_left == -1 || (ml && ml->bytes >= need)) && (msg_right == -1 || (mr && mr->bytes >= need)),
+              "cwa_slab_pack: message buffers smaller than %zu bytes", need);
+    if (ml) CWA_CUDA(cudaMemsetAsync(ml->ptr, 0, 64, ctx->stream));
+    if (mr) CWA_CUDA(cudaMemsetAsync(mr->ptr, 0, 64, ctx->stream));
+    if (n_owned == 0 || (!ml && !mr)) return 0;
+    KScope k(ctx, KID_OTHER);
+    slab_pack_kernel<<<ceil_div(n_owned, 256), 256, 0, ctx->stream>>>((float4*)p->ptr, n_owned, z_lo, z_hi, band, ml != nullptr, mr != nullptr,
+                                                                     ml ? (float4*)ml->ptr : nullptr, mr ? (float4*)mr->ptr : nullptr, cap_mig, cap_ghost);
+    CWA_CUDA(cudaGetLastError());
+    for (auto& s : ctx->sphs) if (s.live && s.particles == particles) s.snapshot_valid = false;
+    return 0;
+}
+
+// counts_host[4] = {owned range, owned + ghosts, flags (1: a sender overflowed its message, 2: capacity exceeded), migrants adopted}
+extern "C" int cwa_slab_unpack(cwa_ctx* ctx, cwa_buf particles, int n_owned, cwa_buf rcv_left, cwa_buf rcv_right,
+                               cwa_buf sent_left, cwa_buf sent_right, int cap_mig, int cap_ghost, int* counts_host)
+{
+    BufferObj* p = get_buffer(ctx, particles);
+    BufferObj* rl = get_buffer(ctx, rcv_left);
+    BufferObj* rr = get_buffer(ctx, rcv_right);
+    BufferObj* sl = get_buffer(ctx, sent_left);
+    BufferObj* sr = get_buffer(ctx, sent_right);
+    CWA_CHECK(p && counts_host, "cwa_slab_unpack: bad particle buffer");
+    CWA_CHECK((rcv_left == -1 || rl) && (rcv_right == -1 || rr), "cwa_slab_unpack: invalid message buffer handle");
+    MultiScratch* sc = multi_scratch(ctx, 1024);
+    CWA_CHECK(sc, "cwa_slab_unpack: out of device memory");
+    const int capacity = (int)(p->bytes / 64);
+    const int max_in = 2 * (2 * cap_mig + cap_ghost);
+    { KScope k(ctx, KID_OTHER);
+      slab_unpack_kernel<<<ceil_div(max_in > 0 ? max_in : 1, 256), 256, 0, ctx->stream>>>(
+          (float4*)p->ptr, n_owned, capacity, rl ? (const float4*)rl->ptr : nullptr, rr ? (const float4*)rr->ptr : nullptr,
+          sl ? (const float4*)sl->ptr : nullptr, sr ? (const float4*)sr->ptr : nullptr, cap_mig, cap_ghost, sc->flags); }
+    CWA_CUDA(cudaGetLastError());
+    CWA_CUDA(cudaMemcpyAsync(counts_host, sc->flags, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CWA_CUDA(cudaStreamSynchronize(ctx->stream));          // the one host synchronisation of a distributed frame
+    for (auto& s : ctx->sphs) if (s.live && s.particles == particles) s.snapshot_valid = false;
+    return 0;
+}
+
+// drop dead slots from the owned range (rare: called when the buffer runs full); stable; synchronises
+__global__ void __launch_bounds__(256)
+multi_flag_live_kernel(const float4* __restrict__ aos, int n, int* __restrict__ flags)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    flags[i] = slot_dead(__ldg(aos + (size_t)i * 4)) ? 0 : 1;
+}
+
+extern "C" int cwa_slab_compact(cwa_ctx* ctx, cwa_buf particles, int n_owned, cwa_buf scratch, int* n_live)
+{
+    BufferObj* p = get_buffer(ctx, particles);
+    BufferObj* s = get_buffer(ctx, scratch);
+    CWA_CHECK(p && s && n_live && (size_t)n_owned * 64 <= p->bytes && (size_t)n_owned * 64 <= s->bytes, "cwa_slab_compact: bad buffers");
+    *n_live = 0;
+    if (n_owned == 0) return 0;
+    MultiScratch* sc = multi_scratch(ctx, n_owned);
+    CWA_CHECK(sc, "cwa_slab_compact: out of device memory");
+    CWA_CUDA(cudaMemsetAsync(sc->ticket, 0, 16 + scan_num_tiles(n_owned) * 8, ctx->stream));
+    { KScope k(ctx, KID_OTHER);
+      multi_flag_live_kernel<<<ceil_div(n_owned, 256), 256, 0, ctx->stream>>>((const float4*)p->ptr, n_owned, sc->flags); }
+    CWA_TRY(scan_exclusive_launch(ctx, sc->flags, sc->pos, n_owned, sc->ticket, sc->state));
+    { KScope k(ctx, KID_OTHER);
+      multi_scatter_kernel<<<ceil_div((long long)n_owned * 4, 256), 256, 0, ctx->stream>>>(
+          (const float4*)p->ptr, n_owned, sc->flags, sc->pos, (float4*)s->ptr, (int)(s->bytes / 64)); }
+    int total = 0;
+    CWA_CUDA(cudaMemcpyAsync(&total, sc->pos + n_owned, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CWA_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (total > 0) CWA_CUDA(cudaMemcpyAsync(p->ptr, s->ptr, (size_t)total * 64, cudaMemcpyDeviceToDevice, ctx->stream));
+    *n_live = total;
     return 0;
 }

@@ -2,17 +2,23 @@
 
 Decomposition
     particles  -- slabs in z.  Rank r owns z in [z_lo, z_hi); the slab faces are the images of its
-                  wave-row block so every particle samples rows held locally.  Each frame:
-                  (1) GHOSTS: owned particles within 2h of a face are copied to that neighbour
-                      (2h because ghost densities are recomputed locally: a ghost within h of the face
-                      needs its own neighbours, which lie within 2h);
-                  (2) the three SPH passes run on owned + ghost particles, ghost results are dropped;
-                  (3) MIGRATION: owned particles that left [z_lo, z_hi) move to the neighbour.
+                  wave-row block so every particle samples rows held locally.  At the start of every
+                  frame each rank sends ONE fixed-size message to each neighbour:
+                    * MIGRANTS: owned particles that left the slab through that face during the last
+                      integrate (they are marked dead in place -- NaN position, skipped by the grid);
+                    * GHOSTS: owned particles within 2h of the face.  2h because ghost densities are
+                      recomputed locally: a ghost within h of the face needs its own neighbours,
+                      which lie within 2h.
+                  The counts travel in the message header, so there is no size negotiation; the
+                  receiver appends migrants to its owned range and ghosts behind it, runs the three
+                  SPH passes on owned + ghosts and drops the ghost results.
     wave field -- row blocks.  Rank r stores its owned rows plus SAMPLING halos (ghost reach 2h, the
                   WaveVelocity tap uv + 0.01, one row for the bilinear footprint); after every stencil
                   step the halo rows are overwritten by the neighbours' owned rows (one contiguous
                   send per neighbour) and the global last row -- WaveNormal's uv + (0,1) tap clamps to
                   it from everywhere (force_comp.glsl:136) -- is broadcast by the last rank.
+All communication is enqueued stream-ordered behind the library's kernels (NCCL on the context's
+stream); a frame has one host synchronisation (reading the two particle counts).
 The reference is single-GPU, so the contract is "N ranks reproduce the 1-rank state".
 
 `SlabPlan` is pure host logic; `DistributedCoupled` drives a *backend* (the CUDA library, or -- in
@@ -20,6 +26,7 @@ the CPU tests only -- the oracle) and moves bytes with torch.distributed (NCCL o
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from dataclasses import dataclass
 
@@ -27,6 +34,7 @@ import numpy as np
 
 COUPLING_AS_SHIPPED, COUPLING_LATEST = 0, 1
 PARTICLE_BYTES = 64
+DEAD_W = -1.0
 
 
 @dataclass
@@ -72,6 +80,14 @@ class SlabPlan:
     def rows_stored(self) -> int:
         return self.store_hi - self.store_lo
 
+    @property
+    def has_left(self) -> bool:
+        return self.rank > 0
+
+    @property
+    def has_right(self) -> bool:
+        return self.rank < self.world - 1
+
     def validate(self):
         assert self.row_hi > self.row_lo, "more ranks than wave rows"
         if self.world > 1:
@@ -81,7 +97,7 @@ class SlabPlan:
 
 
 class DistributedCoupled:
-    """nframes x (ghost exchange, rho -> force -> integrate, wave stencil + halo refresh, display bind, migration)."""
+    """nframes x (migrant+ghost exchange, rho -> force -> integrate, wave stencil + halo refresh, display bind)."""
 
     def __init__(self, backend, plan: SlabPlan, dist=None):
         self.b = backend
@@ -89,119 +105,79 @@ class DistributedCoupled:
         self.dist = dist                       # torch.distributed module (None: single rank)
         self.world, self.rank = plan.world, plan.rank
         plan.validate()
+        self._nbr_plans = {r: SlabPlan.make(plan.world, r, plan.wave_w, plan.wave_h, plan.uv_scale, plan.h)
+                           for r in (plan.rank - 1, plan.rank + 1) if 0 <= r < plan.world}
 
-    # ---- point-to-point helpers --------------------------------------------------------------
-    def _exchange(self, send_left, send_right):
-        """Send byte tensors to rank-1 / rank+1, receive theirs.  Returns (from_left, from_right)."""
-        import torch
+    def _p2p(self, pairs):
+        """pairs: list of (send_tensor | None, recv_tensor | None, peer).  Stream-ordered on CUDA."""
         d = self.dist
-        left = self.rank - 1 if self.rank > 0 else None
-        right = self.rank + 1 if self.rank < self.world - 1 else None
-        dev = self.b.device
-        cnt_out = {n: torch.tensor([t.numel() if t is not None else 0], dtype=torch.int64, device=dev) for n, t in (("l", send_left), ("r", send_right))}
-        cnt_in = {n: torch.zeros(1, dtype=torch.int64, device=dev) for n in ("l", "r")}
         ops = []
-        if left is not None:
-            ops += [d.P2POp(d.isend, cnt_out["l"], left), d.P2POp(d.irecv, cnt_in["l"], left)]
-        if right is not None:
-            ops += [d.P2POp(d.isend, cnt_out["r"], right), d.P2POp(d.irecv, cnt_in["r"], right)]
-        for w in d.batch_isend_irecv(ops):
-            w.wait()
-        n_l, n_r = int(cnt_in["l"].item()), int(cnt_in["r"].item())
-        recv_l = self.b.recv_tensor("l", n_l) if left is not None else None
-        recv_r = self.b.recv_tensor("r", n_r) if right is not None else None
-        ops = []
-        if left is not None:
-            if send_left is not None and send_left.numel():
-                ops.append(d.P2POp(d.isend, send_left, left))
-            if n_l:
-                ops.append(d.P2POp(d.irecv, recv_l, left))
-        if right is not None:
-            if send_right is not None and send_right.numel():
-                ops.append(d.P2POp(d.isend, send_right, right))
-            if n_r:
-                ops.append(d.P2POp(d.irecv, recv_r, right))
+        for send, recv, peer in pairs:
+            if send is not None and send.numel():
+                ops.append(d.P2POp(d.isend, send, peer))
+            if recv is not None and recv.numel():
+                ops.append(d.P2POp(d.irecv, recv, peer))
         if ops:
             for w in d.batch_isend_irecv(ops):
                 w.wait()
-        self.b.comm_done()
-        return recv_l, recv_r
 
     # ---- one frame -----------------------------------------------------------------------------
-    def _ghost_exchange(self):
+    def _particle_exchange(self):
         p, b = self.plan, self.b
         if self.world == 1:
-            b.set_ghosts(None, None)
+            b.no_exchange()
             return
-        send_l = b.select(0, p.z_lo, p.z_lo + p.ghost_width, "l") if self.rank > 0 else None
-        send_r = b.select(0, p.z_hi - p.ghost_width, p.z_hi, "r") if self.rank < self.world - 1 else None
-        b.before_comm()
-        recv_l, recv_r = self._exchange(send_l, send_r)
-        b.set_ghosts(recv_l, recv_r)
-
-    def _migrate(self):
-        p, b = self.plan, self.b
-        if self.world == 1:
-            return
-        send_l = b.select(1, p.z_lo, 0.0, "l") if self.rank > 0 else None
-        send_r = b.select(2, p.z_hi, 0.0, "r") if self.rank < self.world - 1 else None
-        b.keep(p.z_lo if self.rank > 0 else -math.inf, p.z_hi if self.rank < self.world - 1 else math.inf)
-        b.before_comm()
-        recv_l, recv_r = self._exchange(send_l, send_r)
-        b.append_owned(recv_l, recv_r)
+        with b.comm_stream():
+            send_l, send_r = b.pack(p.z_lo, p.z_hi, p.ghost_width, p.has_left, p.has_right)
+            recv_l, recv_r = b.recv_buffers(p.has_left, p.has_right)
+            pairs = []
+            if p.has_left:
+                pairs.append((send_l, recv_l, self.rank - 1))
+            if p.has_right:
+                pairs.append((send_r, recv_r, self.rank + 1))
+            self._p2p(pairs)
+            b.unpack(p.has_left, p.has_right)
 
     def _wave_halo_refresh(self):
         """After a stencil step: overwrite the halo rows of the newest level and refresh the global last row."""
         p, b = self.plan, self.b
         if self.world == 1:
             return
-        d = self.dist
         img = b.newest_image()
-        b.before_comm()
-        ops = []
-        left = self.rank - 1 if self.rank > 0 else None
-        right = self.rank + 1 if self.rank < self.world - 1 else None
-        # my top owned rows fill the left neighbour's upper halo (its halo_hi rows above its row_hi == my row_lo)
-        if left is not None:
-            left_plan = SlabPlan.make(p.world, left, p.wave_w, p.wave_h, p.uv_scale, p.h)
-            n_up = left_plan.store_hi - left_plan.row_hi
-            ops.append(d.P2POp(d.isend, b.wave_rows(img, p.row_lo, n_up), left))
-            ops.append(d.P2POp(d.irecv, b.wave_rows(img, p.store_lo, p.row_lo - p.store_lo), left))
-        if right is not None:
-            right_plan = SlabPlan.make(p.world, right, p.wave_w, p.wave_h, p.uv_scale, p.h)
-            n_dn = right_plan.row_lo - right_plan.store_lo
-            ops.append(d.P2POp(d.isend, b.wave_rows(img, p.row_hi - n_dn, n_dn), right))
-            ops.append(d.P2POp(d.irecv, b.wave_rows(img, p.row_hi, p.store_hi - p.row_hi), right))
-        for w in d.batch_isend_irecv(ops):
-            w.wait()
-        last = b.last_row(img)
-        if self.rank == self.world - 1:
-            b.copy_own_last_row(img)
-        d.broadcast(last, src=self.world - 1)
-        b.comm_done()
+        with b.comm_stream():
+            pairs = []
+            if p.has_left:
+                lp = self._nbr_plans[self.rank - 1]
+                n_up = lp.store_hi - lp.row_hi           # my first owned rows are the left neighbour's upper halo
+                pairs.append((b.wave_rows(img, p.row_lo, n_up), b.wave_rows(img, p.store_lo, p.row_lo - p.store_lo), self.rank - 1))
+            if p.has_right:
+                rp = self._nbr_plans[self.rank + 1]
+                n_dn = rp.row_lo - rp.store_lo           # my last owned rows are the right neighbour's lower halo
+                pairs.append((b.wave_rows(img, p.row_hi - n_dn, n_dn), b.wave_rows(img, p.row_hi, p.store_hi - p.row_hi), self.rank + 1))
+            self._p2p(pairs)
+            if self.rank == self.world - 1:
+                b.copy_own_last_row(img)
+            self.dist.broadcast(b.last_row(img), src=self.world - 1)
 
     def step(self, nframes: int = 1, coupling: int = COUPLING_AS_SHIPPED):
         b = self.b
         for _ in range(nframes):
-            self._ghost_exchange()
+            self._particle_exchange()
             image = b.newest_image() if coupling == COUPLING_LATEST else b.tex_unit0()
             b.sph_step(image)                      # idle(): rho_pres, force, integrate  (Main.cpp:549-557)
             b.wave_step()                          # Module::sComputeAll               (Main.cpp:560)
             self._wave_halo_refresh()
             b.bind_texture_unit()                  # display(): GetReadImage(0).BindTextureUnit()  (Main.cpp:413)
-            self._migrate()
 
     def init_wave_halos(self):
-        """Init() wrote both read levels from global coordinates, so halos and last rows only need the broadcast."""
+        """Init() wrote both read levels from global coordinates, so only the last rows need the broadcast."""
         if self.world == 1:
             return
-        for img in range(3):
-            last = self.b.last_row(img)
-            if self.rank == self.world - 1:
-                self.b.copy_own_last_row(img)
-            self.b.before_comm()
-            self.dist.broadcast(last, src=self.world - 1)
-            self.b.comm_done()
+        with self.b.comm_stream():
+            for img in range(3):
+                if self.rank == self.world - 1:
+                    self.b.copy_own_last_row(img)
+                self.dist.broadcast(self.b.last_row(img), src=self.world - 1)
 
 
 # ====================================================================================================
@@ -217,26 +193,41 @@ class _DevPtr:
 class CudaBackend:
     """Owns the per-rank library objects: particle SSBO (owned + ghosts), grid, row-block wave object."""
 
-    def __init__(self, cwa, ctx, plan: SlabPlan, capacity: int, grid_min, grid_max, grid_cells, wave_ch=1):
+    def __init__(self, cwa, ctx, plan: SlabPlan, capacity: int, grid_min, grid_max, grid_cells, wave_ch=1,
+                 cap_mig: int = 16384, cap_ghost: int = 65536):
         import torch
         self.torch = torch
         self.cwa, self.ctx, self.plan = cwa, ctx, plan
         self.device = torch.device("cuda", ctx.device)
         self.capacity = capacity
+        self._views = {}
+        self.cap_mig, self.cap_ghost = cap_mig, cap_ghost
         self.buffer = cwa.Buffer(ctx, nbytes=capacity * PARTICLE_BYTES)
         self.grid = cwa.UniformGrid(ctx, 3, grid_min, grid_max, grid_cells, capacity, compact_index=True)
         self.sph = cwa.Sph(ctx, capacity, self.grid, buffer=self.buffer)
-        self.scratch = {k: cwa.Buffer(ctx, nbytes=capacity * PARTICLE_BYTES) for k in ("l", "r", "keep", "rl", "rr")}
+        msg_bytes = (1 + cap_mig + cap_ghost) * PARTICLE_BYTES
+        self.msg = {k: cwa.Buffer(ctx, nbytes=msg_bytes) for k in ("sl", "sr", "rl", "rr")}
+        self.msg_t = {k: self._tensor(v, 0, msg_bytes) for k, v in self.msg.items()}
+        self.scratch = None                       # allocated on the first compaction
         self.wave = cwa.StencilImage2DTripleBuffered.create_block(ctx, plan.wave_w, plan.wave_h, plan.store_lo, plan.rows_stored, wave_ch)
         self.wave_ch = wave_ch
-        self.n_owned = 0
+        self.n_owned = 0                          # owned RANGE (may contain dead slots)
         self.n_ghost = 0
-        self._ptr = self.buffer.device_ptr()
+        self.migrated_in = 0
+        self._stream = torch.cuda.ExternalStream(ctx.stream, device=self.device)
 
     def _tensor(self, buf, offset_bytes: int, nbytes: int):
         if nbytes == 0:
             return self.torch.empty(0, dtype=self.torch.uint8, device=self.device)
-        return self.torch.as_tensor(_DevPtr(buf.device_ptr() + offset_bytes, nbytes), device=self.device)
+        key = (buf.h, offset_bytes, nbytes)
+        t = self._views.get(key)
+        if t is None:                             # views of library-owned memory; built once, reused every frame
+            t = self._views[key] = self.torch.as_tensor(_DevPtr(buf.device_ptr() + offset_bytes, nbytes), device=self.device)
+        return t
+
+    def comm_stream(self):
+        """torch collectives issued inside are ordered behind / ahead of the library's kernels on ITS stream."""
+        return self.torch.cuda.stream(self._stream)
 
     # ---- particles ------------------------------------------------------------------------------
     def upload_owned(self, particles: np.ndarray):
@@ -246,51 +237,47 @@ class CudaBackend:
         self.n_owned, self.n_ghost = particles.size, 0
 
     def download_owned(self) -> np.ndarray:
-        return self.buffer.read(self.cwa.PARTICLE, self.n_owned)
+        p = self.buffer.read(self.cwa.PARTICLE, self.n_owned)
+        dead = (p["pos"][:, 3] == np.float32(DEAD_W)) & np.isnan(p["pos"][:, 0])
+        return p[~dead]
 
-    def select(self, kind: int, a: float, b: float, slot: str):
-        """copy_if over the OWNED particles into the send scratch `slot`; returns a byte tensor view."""
-        import ctypes as C
-        cnt = C.c_int()
-        a = max(min(a, 3.0e38), -3.0e38); b = max(min(b, 3.0e38), -3.0e38)
-        self.cwa.check(self.ctx.lib.cwa_particles_copy_if(self.ctx.h, self.buffer.h, self.n_owned, 2, kind, a, b, self.scratch[slot].h, 0, C.byref(cnt)))
-        return self._tensor(self.scratch[slot], 0, cnt.value * PARTICLE_BYTES)
-
-    def keep(self, z_lo: float, z_hi: float):
-        import ctypes as C
-        cnt = C.c_int()
-        a = max(z_lo, -3.0e38); b = min(z_hi, 3.0e38)
-        self.cwa.check(self.ctx.lib.cwa_particles_copy_if(self.ctx.h, self.buffer.h, self.n_owned, 2, 3, a, b, self.scratch["keep"].h, 0, C.byref(cnt)))
-        if cnt.value:
-            self.cwa.check(self.ctx.lib.cwa_buffer_copy(self.ctx.h, self.scratch["keep"].h, self.buffer.h, 0, 0, cnt.value * PARTICLE_BYTES))
-        self.n_owned = cnt.value
-
-    def recv_tensor(self, side: str, nbytes: int):
-        return self._tensor(self.scratch["r" + side], 0, nbytes)
-
-    def _append(self, tensors, base: int) -> int:
-        n = base
-        for side, t in (("l", tensors[0]), ("r", tensors[1])):
-            if t is not None and t.numel():
-                m = t.numel() // PARTICLE_BYTES
-                assert n + m <= self.capacity, f"rank {self.plan.rank}: particle capacity {self.capacity} exceeded"
-                self.cwa.check(self.ctx.lib.cwa_buffer_copy(self.ctx.h, self.scratch["r" + side].h, self.buffer.h, 0, n * PARTICLE_BYTES, t.numel()))
-                n += m
-        return n
-
-    def set_ghosts(self, recv_l, recv_r):
-        self.n_ghost = self._append((recv_l, recv_r), self.n_owned) - self.n_owned
-
-    def append_owned(self, recv_l, recv_r):
-        self.n_owned = self._append((recv_l, recv_r), self.n_owned)
+    def no_exchange(self):
         self.n_ghost = 0
 
-    # ---- stream ordering between the library's stream and torch's communication streams ---------
-    def before_comm(self):
-        self.ctx.synchronize()
+    def _maybe_compact(self):
+        reserve = 2 * (2 * self.cap_mig + self.cap_ghost)
+        if self.n_owned + reserve <= self.capacity:
+            return
+        import ctypes as C
+        if self.scratch is None:
+            self.scratch = self.cwa.Buffer(self.ctx, nbytes=self.capacity * PARTICLE_BYTES)
+        n = C.c_int()
+        self.cwa.check(self.ctx.lib.cwa_slab_compact(self.ctx.h, self.buffer.h, self.n_owned, self.scratch.h, C.byref(n)))
+        self.n_owned = n.value
+        assert self.n_owned + reserve <= self.capacity, f"rank {self.plan.rank}: particle capacity {self.capacity} exhausted"
 
-    def comm_done(self):
-        self.torch.cuda.synchronize(self.device)
+    def pack(self, z_lo, z_hi, band, has_left, has_right):
+        self._maybe_compact()
+        f = lambda v: max(min(v, 3.0e38), -3.0e38)
+        self.cwa.check(self.ctx.lib.cwa_slab_pack(self.ctx.h, self.buffer.h, self.n_owned, f(z_lo), f(z_hi), band,
+                                                  self.msg["sl"].h if has_left else -1, self.msg["sr"].h if has_right else -1,
+                                                  self.cap_mig, self.cap_ghost))
+        return (self.msg_t["sl"] if has_left else None, self.msg_t["sr"] if has_right else None)
+
+    def recv_buffers(self, has_left, has_right):
+        return (self.msg_t["rl"] if has_left else None, self.msg_t["rr"] if has_right else None)
+
+    def unpack(self, has_left, has_right):
+        import ctypes as C
+        counts = (C.c_int * 4)()
+        self.cwa.check(self.ctx.lib.cwa_slab_unpack(self.ctx.h, self.buffer.h, self.n_owned, self.msg["rl"].h if has_left else -1,
+                                                    self.msg["rr"].h if has_right else -1, self.msg["sl"].h if has_left else -1,
+                                                    self.msg["sr"].h if has_right else -1, self.cap_mig, self.cap_ghost, counts))
+        if counts[2]:
+            raise RuntimeError(f"rank {self.plan.rank}: exchange overflow (flags {counts[2]}): raise cap_mig/cap_ghost/capacity")
+        self.n_ghost = counts[1] - counts[0]
+        self.n_owned = counts[0]
+        self.migrated_in += counts[3]
 
     # ---- simulation -------------------------------------------------------------------------------
     def sph_step(self, image: int):

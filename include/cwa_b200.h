@@ -172,6 +172,18 @@ CWA_API int cwa_sph_set_count(cwa_ctx* ctx, cwa_sph s, int n);
  * kind 0: a <= x < b, 1: x < a, 2: x >= a, 3: !(x < a) && !(x >= b) (NaN stays).  *count = copied; synchronises */
 CWA_API int cwa_particles_copy_if(cwa_ctx* ctx, cwa_buf src, int n, int axis, int kind, float a, float b,
                                   cwa_buf dst, int dst_offset, int* count);
+/* One exchange per frame and neighbour.  Message = 64-byte records: [0] header {int migrants, int ghosts, int overflow},
+ * [1, 1+cap_mig) migrants (left the slab [z_lo, z_hi) through this face; marked dead in the SSBO: pos = NaN, pos.w = -1),
+ * [1+cap_mig, 1+cap_mig+cap_ghost) ghosts (within `band` of the face).  msg_left / msg_right = -1: no neighbour there. */
+CWA_API int cwa_slab_pack(cwa_ctx* ctx, cwa_buf particles, int n_owned, float z_lo, float z_hi, float band,
+                          cwa_buf msg_left, cwa_buf msg_right, int cap_mig, int cap_ghost);
+/* append the received migrants behind the owned range, then the ghosts: the received ones plus the migrants of this
+ * rank's own outgoing messages (sent_*; still neighbours here this frame).  counts[4] = {owned range, owned + ghosts,
+ * flags (1: a sender overflowed, 2: capacity exceeded), migrants adopted}; the one host synchronisation of a frame */
+CWA_API int cwa_slab_unpack(cwa_ctx* ctx, cwa_buf particles, int n_owned, cwa_buf rcv_left, cwa_buf rcv_right,
+                            cwa_buf sent_left, cwa_buf sent_right, int cap_mig, int cap_ghost, int* counts);
+/* squeeze dead slots out of the owned range (rare; stable; synchronises) */
+CWA_API int cwa_slab_compact(cwa_ctx* ctx, cwa_buf particles, int n_owned, cwa_buf scratch, int* n_live);
 /* wave field stored as a row block: global rows [row0, row0+rows) of a field h_global rows tall (owned rows + halos) */
 CWA_API int cwa_wave_create_block(cwa_ctx* ctx, int w, int h_global, int row0, int rows, int channels, int variant, cwa_wave* out);
 /* replicated copy of the GLOBAL last row of physical image `image` (WaveNormal's uv+(0,1) tap clamps to it) */

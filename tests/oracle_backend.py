@@ -17,7 +17,7 @@ class OracleBackend:
     def __init__(self, plan, capacity, prm, grid_def, wtype=1.0):
         self.plan, self.capacity, self.prm, self.grid_def = plan, capacity, prm, grid_def
         self.p = np.zeros(capacity, O.PARTICLE3)
-        self.scratch = {k: np.zeros(capacity, O.PARTICLE3) for k in ("l", "r", "rl", "rr")}
+        self.msgs = None
         self.n_owned = self.n_ghost = 0
         W, H = plan.wave_w, plan.wave_h
         full = O.wave_init(W, H, 1, O.WAVE_COUPLED, wtype)
@@ -38,62 +38,78 @@ class OracleBackend:
         u[self.write_index], u[self.read_index[0]] = u[self.read_index[0]], u[self.write_index]
         u[self.read_index[0]], u[self.read_index[1]] = u[self.read_index[1]], u[self.read_index[0]]
 
-    # ---- particles ------------------------------------------------------------------------------
+    # ---- particles (same message layout as cwa_slab_pack / cwa_slab_unpack) --------------------------------
+    CAP_MIG, CAP_GHOST = 256, 2048
+
+    def _msg(self):
+        return np.zeros(1 + self.CAP_MIG + self.CAP_GHOST, O.PARTICLE3)
+
     def upload_owned(self, particles):
         self.p[:particles.size] = particles
         self.n_owned, self.n_ghost = particles.size, 0
+        self.msgs = {k: self._msg() for k in ("sl", "sr", "rl", "rr")}
+
+    def _dead(self, q):
+        return (q["pos"][:, 3] == np.float32(-1.0)) & np.isnan(q["pos"][:, 0])
 
     def download_owned(self):
-        return self.p[:self.n_owned].copy()
+        q = self.p[:self.n_owned]
+        return q[~self._dead(q)].copy()
 
-    def _pred(self, kind, a, b):
-        z = self.p["pos"][:self.n_owned, 2]
-        with np.errstate(invalid="ignore"):
-            if kind == 0:
-                return (z >= a) & (z < b)
-            if kind == 1:
-                return z < a
-            if kind == 2:
-                return z >= a
-            return ~(z < a) & ~(z >= b)
-
-    def select(self, kind, a, b, slot):
-        m = self._pred(kind, np.float32(a), np.float32(b))
-        sel = self.p[:self.n_owned][m]
-        self.scratch[slot][:sel.size] = sel
-        return torch.from_numpy(self.scratch[slot][:sel.size].view(np.uint8).reshape(-1))
-
-    def keep(self, z_lo, z_hi):
-        m = self._pred(3, np.float32(max(z_lo, -3e38)), np.float32(min(z_hi, 3e38)))
-        sel = self.p[:self.n_owned][m].copy()
-        self.p[:sel.size] = sel
-        self.n_owned = sel.size
-
-    def recv_tensor(self, side, nbytes):
-        return torch.from_numpy(self.scratch["r" + side].view(np.uint8).reshape(-1)[:nbytes])
-
-    def _append(self, tensors, base):
-        n = base
-        for side, t in (("l", tensors[0]), ("r", tensors[1])):
-            if t is not None and t.numel():
-                m = t.numel() // PB
-                assert n + m <= self.capacity
-                self.p[n:n + m] = self.scratch["r" + side][:m]
-                n += m
-        return n
-
-    def set_ghosts(self, recv_l, recv_r):
-        self.n_ghost = self._append((recv_l, recv_r), self.n_owned) - self.n_owned
-
-    def append_owned(self, recv_l, recv_r):
-        self.n_owned = self._append((recv_l, recv_r), self.n_owned)
+    def no_exchange(self):
         self.n_ghost = 0
 
-    def before_comm(self):
-        pass
+    def comm_stream(self):
+        import contextlib
+        return contextlib.nullcontext()
 
-    def comm_done(self):
-        pass
+    def pack(self, z_lo, z_hi, band, has_left, has_right):
+        q = self.p[:self.n_owned]
+        live = ~self._dead(q)
+        z = q["pos"][:, 2]
+        out = []
+        with np.errstate(invalid="ignore"):
+            zl, zh, bd = np.float32(max(z_lo, -3e38)), np.float32(min(z_hi, 3e38)), np.float32(band)
+            to_l = live & (z < zl + bd) if has_left else np.zeros(q.size, bool)
+            to_r = live & ~to_l & (z >= zh - bd) if has_right else np.zeros(q.size, bool)
+            for key, sel, mig in (("sl", to_l, to_l & (z < zl)), ("sr", to_r, to_r & (z >= zh))):
+                m = self.msgs[key]
+                m[:] = 0
+                migrants, ghosts = q[mig].copy(), q[sel & ~mig].copy()
+                assert migrants.size <= self.CAP_MIG and ghosts.size <= self.CAP_GHOST
+                hdr = m[:1].view(np.int32)
+                hdr[0], hdr[1] = migrants.size, ghosts.size
+                m[1:1 + migrants.size] = migrants
+                m[1 + self.CAP_MIG:1 + self.CAP_MIG + ghosts.size] = ghosts
+                q["pos"][mig] = (np.nan, np.nan, np.nan, -1.0)
+                out.append(torch.from_numpy(m.view(np.uint8).reshape(-1)))
+        return (out[0] if has_left else None, out[1] if has_right else None)
+
+    def recv_buffers(self, has_left, has_right):
+        f = lambda k: torch.from_numpy(self.msgs[k].view(np.uint8).reshape(-1))
+        return (f("rl") if has_left else None, f("rr") if has_right else None)
+
+    def unpack(self, has_left, has_right):
+        lists = []
+        for key, has in (("rl", has_left), ("rr", has_right)):
+            if not has:
+                lists.append((np.zeros(0, O.PARTICLE3), np.zeros(0, O.PARTICLE3)))
+                continue
+            m = self.msgs[key]
+            hdr = m[:1].view(np.int32)
+            lists.append((m[1:1 + hdr[0]].copy(), m[1 + self.CAP_MIG:1 + self.CAP_MIG + hdr[1]].copy()))
+        n = self.n_owned
+        for part in (lists[0][0], lists[1][0]):
+            self.p[n:n + part.size] = part; n += part.size
+        self.n_owned = n
+        own_sent = []                                # my own outgoing migrants are still neighbours here this frame
+        for key, has in (("sl", has_left), ("sr", has_right)):
+            m = self.msgs[key]
+            own_sent.append(m[1:1 + m[:1].view(np.int32)[0]].copy() if has else np.zeros(0, O.PARTICLE3))
+        for part in (lists[0][1], lists[1][1], own_sent[0], own_sent[1]):
+            assert n + part.size <= self.capacity
+            self.p[n:n + part.size] = part; n += part.size
+        self.n_ghost = n - self.n_owned
 
     # ---- simulation -------------------------------------------------------------------------------
     def _global_texture(self, image):

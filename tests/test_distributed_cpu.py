@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 WAVE_W, WAVE_H = 32, 96
 NX, NY, NZ = 10, 5, 56
 GRID = ((0.0, -0.02, 0.0), (0.12, 0.2, 0.52), (6, 11, 26))
-FRAMES = 7
+FRAMES = int(os.environ.get("CWA_TEST_FRAMES", "7"))
 
 
 def scene():
@@ -61,7 +61,7 @@ def _worker(rank, world, coupling, init_file, out_dir):
     prm, p = scene()
     h = prm.smoothing_coeff * prm.particle_radius
     plan = SlabPlan.make(world, rank, WAVE_W, WAVE_H, prm.uv_scale, h)
-    be = OracleBackend(plan, p.size, prm, GRID)
+    be = OracleBackend(plan, p.size + 4096, prm, GRID)
     z = p["pos"][:, 2]
     be.upload_owned(p[(z >= plan.z_lo) & (z < plan.z_hi)])
     drv = DistributedCoupled(be, plan, dist if world > 1 else None)

@@ -69,7 +69,6 @@ def main():
     be.upload_owned(mine)
     drv = DistributedCoupled(be, plan, dist if world > 1 else None)
     drv.init_wave_halos()
-    n0 = be.n_owned
     drv.step(FRAMES, coupling)
     ctx.synchronize()
     owned = be.download_owned()
@@ -77,15 +76,15 @@ def main():
     wave_rows = be.wave.read_image(img)[plan.row_lo - plan.store_lo:plan.row_hi - plan.store_lo]
     gathered = [None] * world
     if world > 1:
-        dist.all_gather_object(gathered, (owned, wave_rows, n0))
+        dist.all_gather_object(gathered, (owned, wave_rows, be.migrated_in))
     else:
-        gathered = [(owned, wave_rows, n0)]
+        gathered = [(owned, wave_rows, be.migrated_in)]
     ok = True
     if rank == 0:
         P = np.concatenate([g[0] for g in gathered])
         P = P[np.argsort(P["extras"][:, 3])]
         W = np.concatenate([g[1] for g in gathered])
-        moved = sum(abs(g[2] - g[0].size) for g in gathered)
+        moved = sum(g[2] for g in gathered)
         # single-GPU reference on this rank's device
         grid = cwa.UniformGrid(ctx, 3, (0.0, -0.02, 0.0), (BOX[0], 1.0, BOX[2]), (45, 51, 85), p.size, compact_index=True)
         sph = cwa.Sph(ctx, p.size, grid, particles=p)
