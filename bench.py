@@ -377,15 +377,37 @@ def run_native_distributed(args, world, rank, local_rank, torch, dist, cwa):
     zh = min(box, plan.z_hi + 0.06) if rank < world - 1 else box
     ncx = int(round(192 * f))
     ncz = max(4, int(math.ceil((zh - zl) / (box / ncx))))
-    be = CudaBackend(cwa, ctx, plan, int(own.size * 1.25) + 100000, (0.0, -0.02, zl), (box, 1.0, zh), (ncx, 51, ncz))
+    # the shipped parameters make the over-dense sheet blast apart (|v| in the thousands within ten frames), so tens of
+    # thousands of particles cross a slab face per frame: generous fixed-size messages (8 MB per neighbour)
+    be = CudaBackend(cwa, ctx, plan, int(own.size * 1.3) + 400000, (0.0, -0.02, zl), (box, 1.0, zh), (ncx, 51, ncz),
+                     cap_mig=65536, cap_ghost=65536)
     be.upload_owned(own)
     n_global = nxg * NY * nzg
     drv = DistributedCoupled(be, plan, dist)
     drv.init_wave_halos()
 
     sampler = ClockSampler(local_rank)
+    if os.environ.get("CWA_BENCH_DEBUG"):
+        for fr in range(8):
+            drv.step(1, COUPLING)
+            q = be.download_owned()
+            zz = q["pos"][:, 2]
+            print(f"[debug rank {rank}] frame {fr + 1}: owned range {be.n_owned} live {q.size} ghosts {be.n_ghost} migrated_in {be.migrated_in} "
+                  f"z [{np.nanmin(zz):.5f}, {np.nanmax(zz):.5f}] slab [{plan.z_lo:.5f}, {plan.z_hi:.5f}] vmax {np.nanmax(np.abs(q['vel'][:, :3])):.3f} "
+                  f"nan {int(np.isnan(zz).sum())}", flush=True)
     drv.step(W, COUPLING)
     ctx.synchronize()
+    if os.environ.get("CWA_BENCH_PHASES"):
+        # diagnostic only: wall time per phase with a device synchronise after each (perturbs the overlap)
+        acc = {"exchange": 0.0, "sph": 0.0, "wave": 0.0, "halo": 0.0}
+        nfr = 30
+        for _ in range(nfr):
+            t0 = time.perf_counter(); drv._particle_exchange(); ctx.synchronize(); t1 = time.perf_counter()
+            be.sph_step(be.tex_unit0()); ctx.synchronize(); t2 = time.perf_counter()
+            be.wave_step(); ctx.synchronize(); t3 = time.perf_counter()
+            drv._wave_halo_refresh(); be.bind_texture_unit(); ctx.synchronize(); t4 = time.perf_counter()
+            acc["exchange"] += t1 - t0; acc["sph"] += t2 - t1; acc["wave"] += t3 - t2; acc["halo"] += t4 - t3
+        print(f"[phases rank {rank}] " + ", ".join(f"{k} {v / nfr * 1e6:.0f} us" for k, v in acc.items()), flush=True)
     if rank == 0:
         sampler.start()
     dist.barrier(); ctx.synchronize()
@@ -408,6 +430,11 @@ def run_native_distributed(args, world, rank, local_rank, torch, dist, cwa):
     ctx.profile_begin()
     drv.step(K, COUPLING)
     prof = ctx.profile_end()
+    if os.environ.get("CWA_BENCH_PHASES"):
+        q = be.download_owned()
+        cnt = be.grid.read(cwa.GRID_COUNTER, be.grid.num_cells_total)
+        print(f"[kernels rank {rank}] owned {q.size} ghosts {be.n_ghost} max/cell {int(cnt.max())} cells>64: {int((cnt > 64).sum())} "
+              + ", ".join(f"{k} {v[0] / v[1] * 1e3:.0f}us" for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:6]), flush=True)
 
     # end to end: every rank's particle slab and wave rows live in pinned HOST buffers between steps
     import ctypes as C
@@ -417,7 +444,7 @@ def run_native_distributed(args, world, rank, local_rank, torch, dist, cwa):
     pin_w = [torch.empty(plan.rows_stored * wave_n, dtype=torch.float32).pin_memory() for _ in range(2)]
     host_p = pin_p.numpy().view(cwa.PARTICLE)
     host_w = [w_.numpy().reshape(plan.rows_stored, wave_n) for w_ in pin_w]
-    host_p[:be.n_owned] = be.download_owned()
+    host_p[:be.n_owned] = be.buffer.read(cwa.PARTICLE, be.n_owned)       # the owned RANGE (dead slots included), as the device holds it
     host_w[0][:] = be.wave.read_role(0); host_w[1][:] = be.wave.read_role(1)
     lib, hnd = ctx.lib, ctx.h
     moved = [0, 0]

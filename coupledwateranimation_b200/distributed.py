@@ -274,7 +274,9 @@ class CudaBackend:
                                                     self.msg["rr"].h if has_right else -1, self.msg["sl"].h if has_left else -1,
                                                     self.msg["sr"].h if has_right else -1, self.cap_mig, self.cap_ghost, counts))
         if counts[2]:
-            raise RuntimeError(f"rank {self.plan.rank}: exchange overflow (flags {counts[2]}): raise cap_mig/cap_ghost/capacity")
+            hdrs = {k: self.msg[k].read(np.int32, 4).tolist() for k in ("sl", "sr", "rl", "rr")}
+            raise RuntimeError(f"rank {self.plan.rank}: exchange overflow (flags {counts[2]}, counts {list(counts)}, n_owned {self.n_owned}, "
+                               f"capacity {self.capacity}, caps {self.cap_mig}/{self.cap_ghost}, headers {hdrs}): raise cap_mig/cap_ghost/capacity")
         self.n_ghost = counts[1] - counts[0]
         self.n_owned = counts[0]
         self.migrated_in += counts[3]

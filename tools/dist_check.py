@@ -65,7 +65,8 @@ def main():
     zl = max(0.0, plan.z_lo - 0.06) if rank > 0 else 0.0
     zh = min(BOX[2], plan.z_hi + 0.06) if rank < world - 1 else BOX[2]
     ncz = max(4, int(np.ceil((zh - zl) / 0.02)))
-    be = CudaBackend(cwa, ctx, plan, int(mine.size * 1.5) + 20000, (0.0, -0.02, zl), (BOX[0], 1.0, zh), (45, 51, ncz))
+    be = CudaBackend(cwa, ctx, plan, int(mine.size * 1.5) + 40000, (0.0, -0.02, zl), (BOX[0], 1.0, zh), (45, 51, ncz),
+                     cap_mig=2048, cap_ghost=8192)
     be.upload_owned(mine)
     drv = DistributedCoupled(be, plan, dist if world > 1 else None)
     drv.init_wave_halos()
