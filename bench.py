@@ -36,9 +36,11 @@ BOX_LOWER = (0.0, -0.02, 0.0, 50.0)
 GRID_MIN, GRID_MAX, GRID_N = (0.0, -0.02, 0.0), (0.55 * S, 1.0, 0.55 * S), (192, 51, 192)
 _GRID_VARIANT = os.environ.get("CWA_BENCH_GRID", "2h")        # tuning knob: cell size / extent of the uniform grid
 if _GRID_VARIANT == "h":                                      # cells of h = 0.01 (27-cell queries)
-    GRID_N = (384, 102, 384)
+    GRID_N = (384, 101, 384)                                  # cell = 1.0026 h x 1.0099 h x 1.0026 h: every query is exactly 3 x 3 x 3 cells
 elif _GRID_VARIANT == "h_tight":                              # cells of h, y extent cut to the occupied slab (outliers clamp into the top layer)
     GRID_MAX, GRID_N = (0.55 * S, 0.18, 0.55 * S), (384, 20, 384)
+elif _GRID_VARIANT == "h_y30":                                # cells of ~h over the layer the fluid occupies; particles above clamp into the top layer (ugrid_particles_cs.glsl:98 clamps)
+    GRID_MAX, GRID_N = (0.55 * S, 0.30, 0.55 * S), (384, 31, 384)
 elif _GRID_VARIANT == "2h_tight":
     GRID_MAX, GRID_N = (0.55 * S, 0.18, 0.55 * S), (192, 10, 192)
 UV_SCALE = 2.0 / S
@@ -56,6 +58,8 @@ ALGO_BYTES = {
     "reorder": (132, 0, 0),            # index 4 B + 64 B gathered + 64 B written
     "density": (64, 0, 0),             # compulsory: pos+vel 32 B read, packA/packB 32 B written (neighbour loop is FP32-bound)
     "force": (64, 0, 0),               # compulsory: packA/packB/force 48 B read, force 16 B written
+    "density_heavy": (0, 0, 0),        # clumped targets finished one CTA each (a few thousand particles)
+    "force_heavy": (0, 0, 0),
     "integrate": (132, 0, 0),          # 64 B read + index 4 B + 64 B written (full record back to the SSBO)
     "wave_evolve": (0, 0, 12),         # u(t-1) read once, u(t-2) read, u(t) written
 }

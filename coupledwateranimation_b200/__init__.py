@@ -97,6 +97,11 @@ class Context:
     def launch_count(self) -> int:
         return int(self.lib.cwa_launch_count(self.h))
 
+    def set_tuning(self, **kv):
+        """cwa_set_tuning: nb_config / nb_cap_d / nb_cap_f / nb_cap_r (process-wide kernel-variant knobs)."""
+        for k, v in kv.items():
+            check(self.lib.cwa_set_tuning(self.h, k.encode(), int(v)))
+
     def profile_begin(self):
         check(self.lib.cwa_profile_begin(self.h))
 

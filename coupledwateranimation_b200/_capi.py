@@ -54,6 +54,7 @@ SIGNATURES = {
     "cwa_timer_begin": (_I, [_P]),
     "cwa_timer_end": (_I, [_P, C.POINTER(_F)]),
     "cwa_launch_count": (C.c_ulonglong, [_P]),
+    "cwa_set_tuning": (_I, [_P, C.c_char_p, _I]),
     "cwa_profile_kernel_count": (_I, []),
     "cwa_profile_kernel_name": (C.c_char_p, [_I]),
     "cwa_profile_begin": (_I, [_P]),

@@ -250,7 +250,7 @@ grid_cell_order_kernel(const int* __restrict__ cell_of, const int* __restrict__ 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-int grid_build_internal(cwa_ctx* ctx, GridObj* g, const void* particles, int stride_bytes, int n)
+int grid_build_internal(cwa_ctx* ctx, GridObj* g, const void* particles, int stride_bytes, int n, bool canonical_order)
 {
     CWA_CHECK(n >= 0 && n <= g->max_particles, "grid build: %d particles exceed the grid's capacity %d", n, g->max_particles);
     CWA_CHECK(stride_bytes >= 16 && stride_bytes % 16 == 0, "grid build: particle stride must be a multiple of 16 bytes");
@@ -271,8 +271,10 @@ int grid_build_internal(cwa_ctx* ctx, GridObj* g, const void* particles, int str
         { KScope k(ctx, KID_INSERT);
           grid_insert_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(g->cell_of, g->rank, g->offset, n, g->arrival); }
         CWA_CUDA(cudaGetLastError());
-        { KScope k(ctx, KID_CELL_ORDER);
-          grid_cell_order_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(g->cell_of, g->offset, g->arrival, n, g->index_list); }
+        if (canonical_order) {
+            KScope k(ctx, KID_CELL_ORDER);
+            grid_cell_order_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(g->cell_of, g->offset, g->arrival, n, g->index_list);
+        }
         CWA_CUDA(cudaGetLastError());
     }
     return 0;

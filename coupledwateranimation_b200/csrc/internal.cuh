@@ -139,6 +139,9 @@ struct SphObj {
     float4 *packA = nullptr, *packB = nullptr;   // (pos.xyz, p) and (vel.xyz, rho)
     float4 *pairP = nullptr;                     // neighbour sums of the force pass: (pres.xyz, visc.x)
     float2 *pairV = nullptr;                     //                                   (visc.y, visc.z)
+    int   *nbr_list = nullptr, *nbr_count = nullptr;   // neighbour lists of the density pass ([slot][K]) and true counts
+    bool   nbr_lists_valid = false;
+    int   *heavy_queue = nullptr, *heavy_count = nullptr;   // targets finished one warp each: [0,cap) density, [cap,2cap) force; two counters
     void*  consts = nullptr;                     // Sph3Const prepared on the device once per dispatch
     bool snapshot_valid = false;
     bool pair_sums_valid = false;
@@ -170,7 +173,7 @@ struct ShaderObj {
 // kernels of the hot path, as reported by the per-kernel profile (bench.py roofline section)
 enum KernelId {
     KID_CLEAR = 0, KID_HASH_COUNT, KID_SCAN, KID_INSERT, KID_CELL_ORDER, KID_REORDER,
-    KID_DENSITY, KID_FORCE, KID_INTEGRATE, KID_WAVE, KID_OTHER, KID_COUNT
+    KID_DENSITY, KID_FORCE, KID_INTEGRATE, KID_WAVE, KID_OTHER, KID_DENSITY_HEAVY, KID_FORCE_HEAVY, KID_COUNT
 };
 
 struct ProfRec { int id; cudaEvent_t a, b; };
@@ -217,7 +220,8 @@ ParamPtrs  current_params(cwa_ctx* ctx);
 int  scan_exclusive_launch(cwa_ctx* ctx, const int* in, int* out, int n, int* ticket,
                            unsigned long long* tile_state);          // grid.cu; out has n+1 entries
 size_t scan_num_tiles(int n);
-int  grid_build_internal(cwa_ctx* ctx, GridObj* g, const void* particles, int stride_bytes, int n);
+int  grid_build_internal(cwa_ctx* ctx, GridObj* g, const void* particles, int stride_bytes, int n, bool canonical_order = true);
+// canonical_order = false stops after the arrival-order insert: the caller's fused kernel ranks and reorders in one pass
 TexView wave_tex_view(cwa_ctx* ctx, cwa_wave w, int image);           // wave.cu
 int  wave_step_internal(cwa_ctx* ctx, WaveObj* w);
 int  wave_dispatch_mode(cwa_ctx* ctx, WaveObj* w, int mode);           // kernel for uMode on units 0/1/2, no rotation                   // one EVOLVE dispatch + PingPong
@@ -318,6 +322,39 @@ __device__ __forceinline__ float cwa_tex_bilinear(const TexView& t, float s, flo
     float r0 = __fadd_rn(t00, __fmul_rn(a, __fsub_rn(t10, t00)));
     float r1 = __fadd_rn(t01, __fmul_rn(a, __fsub_rn(t11, t01)));
     return __fadd_rn(r0, __fmul_rn(b, __fsub_rn(r1, r0)));
+}
+
+// Same sampler for a field that is entirely local, single-channel and 32-bit indexable (row0 == 0,
+// h == h_global, ch == 1, data != nullptr): identical arithmetic and clamping (NaN -> texel 0), without the
+// row-block lookups, channel stride and 64-bit index arithmetic of the general view.
+__device__ __forceinline__ float cwa_tex_bilinear_local(const TexView& t, float s, float tt)
+{
+    const float fW = (float)t.w, fH = (float)t.h;
+    const float u = __fsub_rn(__fmul_rn(s, fW), 0.5f);
+    const float v = __fsub_rn(__fmul_rn(tt, fH), 0.5f);
+    const float fu = floorf(u), fv = floorf(v);
+    const float a = __fsub_rn(u, fu), b = __fsub_rn(v, fv);
+    const float wm = fW - 1.0f, hm = fH - 1.0f;
+    const int i0 = (int)fminf(fmaxf(fu, 0.0f), wm), i1 = (int)fminf(fmaxf(fu + 1.0f, 0.0f), wm);
+    const int j0 = (int)fminf(fmaxf(fv, 0.0f), hm), j1 = (int)fminf(fmaxf(fv + 1.0f, 0.0f), hm);
+    const float* p0 = t.data + j0 * t.w;
+    const float* p1 = t.data + j1 * t.w;
+    const float t00 = __ldg(p0 + i0), t10 = __ldg(p0 + i1), t01 = __ldg(p1 + i0), t11 = __ldg(p1 + i1);
+    const float r0 = __fadd_rn(t00, __fmul_rn(a, __fsub_rn(t10, t00)));
+    const float r1 = __fadd_rn(t01, __fmul_rn(a, __fsub_rn(t11, t01)));
+    return __fadd_rn(r0, __fmul_rn(b, __fsub_rn(r1, r0)));
+}
+
+template <bool LOCAL>
+__device__ __forceinline__ float cwa_tex_sample(const TexView& t, float s, float tt)
+{
+    if (LOCAL) return cwa_tex_bilinear_local(t, s, tt);
+    return cwa_tex_bilinear(t, s, tt);
+}
+
+static inline bool tex_view_is_local(const TexView& t)
+{
+    return t.data != nullptr && t.ch == 1 && t.row0 == 0 && t.h == t.h_global && (long long)t.w * t.h < (1ll << 30);
 }
 
 __device__ __forceinline__ float cwa_smoothstep(float e0, float e1, float x)

@@ -106,9 +106,12 @@ __device__ __forceinline__ Sph3Const load_consts(const ParamPtrs& prm)
     return c;
 }
 
-__global__ void sph3_prepare_kernel(ParamPtrs prm, Sph3Const* __restrict__ out)
+__global__ void sph3_prepare_kernel(ParamPtrs prm, Sph3Const* __restrict__ out, int* __restrict__ heavy_count)
 {
-    if (threadIdx.x == 0 && blockIdx.x == 0) *out = load_consts(prm);
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        *out = load_consts(prm);
+        if (heavy_count) { heavy_count[0] = 0; heavy_count[1] = 0; }     // queues of the heavy-target kernels
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -149,11 +152,12 @@ __device__ __forceinline__ void pair_force(const Sph3Const& c, float px, float p
 // per-particle epilogues (shared by grid and all-pairs kernels)
 // ---------------------------------------------------------------------------------------------
 // rho_pres_comp.glsl:70-80
+template <bool LOCAL = false>
 __device__ __forceinline__ void density_epilogue(const Sph3Const& c, const TexView& tex, float px, float pz, float rho,
                                                  float& rho_out, float& prs_out)
 {
     float pressure = fmaxf(c.gas * (rho - c.rho0), 0.0f);
-    const float height = cwa_tex_bilinear(tex, c.uv_scale * px, c.uv_scale * pz);
+    const float height = cwa_tex_sample<LOCAL>(tex, c.uv_scale * px, c.uv_scale * pz);
     const float wave_force = height * rho;
     pressure += wave_force;
     rho += __fdiv_rn(wave_force, c.gas * c.radius);
@@ -163,30 +167,32 @@ __device__ __forceinline__ void density_epilogue(const Sph3Const& c, const TexVi
 
 // force_comp.glsl:90-114.  fprev = particles[i].force as stored by the previous frame;
 // (fp*, fv*) = the neighbour sums of :74-88.
+template <bool LOCAL = false>
 __device__ __forceinline__ float4 force_epilogue(const Sph3Const& c, const TexView& tex, float px, float py, float pz,
                                                  float vx, float vy, float vz, float rho_i, float4 fprev,
                                                  float fpx, float fpy, float fpz, float fvx, float fvy, float fvz)
 {
     if (py > c.crest) {                                            // :91-95
-        fprev.x = __fdiv_rn(fprev.x, 0.25f); fprev.y = __fdiv_rn(fprev.y, 0.25f);
-        fprev.z = __fdiv_rn(fprev.z, 0.25f); fprev.w = __fdiv_rn(fprev.w, 0.25f);
+        // x / 0.25 == x * 4 bit for bit (power-of-two scaling is exact, overflow and subnormals included)
+        fprev.x = __fmul_rn(fprev.x, 4.0f); fprev.y = __fmul_rn(fprev.y, 4.0f);
+        fprev.z = __fmul_rn(fprev.z, 4.0f); fprev.w = __fmul_rn(fprev.w, 4.0f);
         fvx *= 0.5f; fvy *= 0.5f; fvz *= 0.5f;
     }
     fvx *= c.visc_coeff; fvy *= c.visc_coeff; fvz *= c.visc_coeff; // :97
     const float cu = px * c.uv_scale, cv = pz * c.uv_scale;        // :99
-    const float height = cwa_tex_bilinear(tex, cu, cv);            // :100
+    const float height = cwa_tex_sample<LOCAL>(tex, cu, cv);            // :100
     // torque = 0.25 * cross(pos, force_prev.xyz)  :103-104
     const float tx = 0.25f * (py * fprev.z - pz * fprev.y);
     const float ty = 0.25f * (pz * fprev.x - px * fprev.z);
     const float tz = 0.25f * (px * fprev.y - py * fprev.x);
     // WaveVelocity :117-128
-    const float hX = cwa_tex_bilinear(tex, cu + 0.01f, cv);
-    const float hY = cwa_tex_bilinear(tex, cu, cv + 0.01f);
+    const float hX = cwa_tex_sample<LOCAL>(tex, cu + 0.01f, cv);
+    const float hY = cwa_tex_sample<LOCAL>(tex, cu, cv + 0.01f);
     const float wvx = __fdiv_rn(hX - height, c.dt), wvy = __fdiv_rn(hY - height, c.dt), wvz = __fdiv_rn(hX - hY, 0.01f);
     const float dgx = -0.25f * (vx - wvx), dgy = -0.25f * (vy - wvy), dgz = -0.25f * (vz - wvz);   // :107-108
     // WaveNormal :131-139: cross(dy,dx) = (dx.z, dy.z, -1)
-    const float nx = cwa_tex_bilinear(tex, cu + 1.0f, cv) - height;
-    const float ny = cwa_tex_bilinear(tex, cu, cv + 1.0f) - height;
+    const float nx = cwa_tex_sample<LOCAL>(tex, cu + 1.0f, cv) - height;
+    const float ny = cwa_tex_sample<LOCAL>(tex, cu, cv + 1.0f) - height;
     const float wfx = -height * nx * 0.5f, wfy = -height * ny * 0.5f, wfz = -height * -1.0f * 0.5f;  // :110
     const float gy = rho_i * c.gravity_y;                                                         // :113
     float4 f;
@@ -198,6 +204,7 @@ __device__ __forceinline__ float4 force_epilogue(const Sph3Const& c, const TexVi
 }
 
 // integrate_comp.glsl:56-92 + CheckBoundary :135-178
+template <bool LOCAL = false>
 __device__ __forceinline__ void integrate_particle(const Sph3Const& c, const TexView& tex, float4& pos, float4& vel,
                                                    float4& force, float& rho, float& prs)
 {
@@ -211,7 +218,7 @@ __device__ __forceinline__ void integrate_particle(const Sph3Const& c, const Tex
         rho *= 0.1f; prs *= 0.25f;
         nvx *= 0.1f; nvy *= 0.1f; nvz *= 0.1f;
     }
-    const float th = cwa_tex_bilinear(tex, npx * c.uv_scale, npz * c.uv_scale);   // :79
+    const float th = cwa_tex_sample<LOCAL>(tex, npx * c.uv_scale, npz * c.uv_scale);   // :79
     if (npy < th) npy = th - c.radius;                                            // :80-83
     const float D = c.damping;
     if (npx < c.lower[0]) { npx = c.lower[0]; nvx *= -D; } else if (npx > c.upper[0]) { npx = c.upper[0]; nvx *= -D; }
@@ -251,6 +258,32 @@ sph3_reorder_kernel(const float4* __restrict__ aos, const int* __restrict__ inde
     else if (q == 1) velS[s] = v;
     else if (q == 2) forceS[s] = v;
     else miscS[s] = make_float4(pw, vw, v.z, v.w);      // (pos.w, vel.w, extras.z, extras.w)
+}
+
+// Canonical ordering + reorder in one pass (thread per arrival slot): the particle that arrived at slot s
+// is ranked among its cell peers by counting the smaller ids (ascending id inside a cell == the CPU twin,
+// SURVEY F7), its id goes to index_list[rank slot] and its 64-B record into the cell-ordered arrays.  The
+// record loads are issued first, so they overlap the rank chain (cell id -> offsets -> arrival list).
+__global__ void __launch_bounds__(256)
+sph3_order_reorder_kernel(const float4* __restrict__ aos, const int* __restrict__ arrival, const int* __restrict__ cell_of,
+                          const int* __restrict__ offset, const int* __restrict__ count, int* __restrict__ index_list,
+                          float4* __restrict__ posS, float4* __restrict__ velS, float4* __restrict__ forceS,
+                          float4* __restrict__ miscS)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= __ldg(count)) return;                 // inserted particles (NaN positions are left out)
+    const int id = __ldg(arrival + s);
+    const float4* rec = aos + (size_t)id * 4;
+    const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2), r3 = __ldg(rec + 3);
+    const int c = __ldg(cell_of + id);
+    const int b = __ldg(offset + c), e = __ldg(offset + c + 1);
+    int smaller = 0;
+#pragma unroll 4
+    for (int q = b; q < e; q++) smaller += (__ldg(arrival + q) < id) ? 1 : 0;
+    const int t = b + smaller;
+    index_list[t] = id;
+    posS[t] = r0; velS[t] = r1; forceS[t] = r2;
+    miscS[t] = make_float4(r0.w, r1.w, r3.z, r3.w);          // (pos.w, vel.w, extras.z, extras.w)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -491,9 +524,397 @@ sph3_force_grid_kernel(const float4* __restrict__ packA, const float4* __restric
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// "rows" neighbour kernels: ONE thread per target, per-thread row table in shared memory
+// ---------------------------------------------------------------------------------------------
+// With h <= cell the query pos -+ h touches at most 3 x 3 rows (i,j) of cells, each a contiguous
+// run [offset[k0], offset[k1+1]) of the cell-ordered arrays.  Every thread loads the (up to) 18 row
+// bounds of its target up front (independent loads, their latency overlaps the window staging),
+// translates them into staging-buffer coordinates and parks them in a shared-memory table; the
+// neighbour loop is then one rolled loop over 9 table rows with a tight candidate loop inside.
+// Table entry (int2): x = first global slot, y = length | staged_begin << 16 (0xffff: row not staged,
+// read it from global memory through L1).  Targets whose query is wider than 3 x 3 rows (h > cell) or
+// that own a row of >= 65535 candidates take the generic loop at the end.
+constexpr int RT_ROWS = 9;
+constexpr int RT_UNSTAGED = 0xffff;
+constexpr int HEAVY_CANDIDATES = 160;     // a target with more candidates than this is processed by its whole warp
+
+struct RowBounds { int b[RT_ROWS], e[RT_ROWS]; int total; bool wide; };
+
+__device__ __forceinline__ RowBounds rows_load(const GridView& g, const int* __restrict__ offset, const Query3& q)
+{
+    RowBounds rb;
+    const int ni = q.i1 - q.i0 + 1, nj = q.j1 - q.j0 + 1;          // inactive thread: 0 x 0
+    rb.wide = (ni > 3) || (nj > 3);
+#pragma unroll
+    for (int r = 0; r < RT_ROWS; r++) {
+        const int a = r / 3, b = r % 3;
+        rb.b[r] = 0; rb.e[r] = 0;
+        if (!rb.wide && a < ni && b < nj) {
+            const int base = ((q.i0 + a) * g.n[1] + (q.j0 + b)) * g.kstride;
+            rb.b[r] = __ldg(offset + base + q.k0);
+            rb.e[r] = __ldg(offset + base + q.k1 + 1);
+        }
+    }
+    rb.total = 0;
+#pragma unroll
+    for (int r = 0; r < RT_ROWS; r++) {
+        if (rb.e[r] - rb.b[r] >= 0xffff) rb.wide = true;
+        rb.total += rb.e[r] - rb.b[r];
+    }
+    return rb;
+}
+
+template <int P>
+__device__ __forceinline__ void rows_store(const BlockWindows& bw, const Query3& q, const RowBounds& rb, int tid, int2* __restrict__ tab)
+{
+#pragma unroll
+    for (int r = 0; r < RT_ROWS; r++) {
+        const int a = r / 3, b = r % 3;
+        const int len = rb.wide ? 0 : (rb.e[r] - rb.b[r]);
+        int sb = RT_UNSTAGED;
+        const int di = q.i0 + a - q.ci + 1, dj = q.j0 + b - q.cj + 1;
+        if (len > 0 && (unsigned)di < 3u && (unsigned)dj < 3u) {
+            const int w = di * 3 + dj;
+            const int so = bw.soff[w], lo = bw.lo[w], hi = bw.hi[w];
+            if (so >= 0 && rb.b[r] >= lo && rb.e[r] <= hi) sb = so + (rb.b[r] - lo);
+        }
+        tab[r * P + tid] = make_int2(rb.b[r], len | (sb << 16));
+    }
+}
+
+// Density pass + neighbour lists.  While it sums the poly6 terms the kernel appends every accepted
+// candidate (self included) to a per-thread list in shared memory and finally writes the list to the
+// target's row of K entries in global memory ([slot][K], 16-byte stores): positions do not change between
+// the density and the force pass, so the force pass walks these lists instead of testing the candidates a
+// second time.
+// count[slot] is the true neighbour count; a target with more than K neighbours keeps only its count and
+// the force kernel re-scans the grid for it.
+template <int P, int K>
+__global__ void __launch_bounds__(P)
+sph3_density_rows_kernel(const float4* __restrict__ posS, const float4* __restrict__ velS,
+                         float4* __restrict__ packA, float4* __restrict__ packB,
+                         int* __restrict__ nbr_list, int* __restrict__ nbr_count,
+                         int* __restrict__ heavy_queue, int* __restrict__ heavy_count, int n_max, GridView g,
+                         const int* __restrict__ offset, const Sph3Const* __restrict__ cc, TexView tex, int cap_slots)
+{
+    extern __shared__ float4 stage[];                  // [cap_slots] positions | int2 tab[9 * P] | int list[(K + 1) * P]
+    int2* tab = reinterpret_cast<int2*>(stage + cap_slots);
+    int* list = reinterpret_cast<int*>(tab + RT_ROWS * P);
+    __shared__ BlockWindows bw;
+    __shared__ uint64_t bar;
+    const int tid = threadIdx.x;
+    const int t0 = blockIdx.x * P;
+    const int n = min(n_max, __ldg(offset + g.num_cells));   // inserted particles
+    if (t0 >= n) return;
+    const int nt = min(P, n - t0);
+    const float h = cc->h, accept_r2 = cc->accept_r2, h2 = cc->h2, poly6 = cc->poly6;
+    const bool reach_ok = (h <= g.cell[0]) && (h <= g.cell[1]) && (h <= g.cell[2]);
+
+    const int slot = t0 + tid;
+    const bool active = tid < nt;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    Query3 q{0, -1, 0, -1, 0, 0, 0, 0};
+    if (active) {
+        p = __ldg(posS + slot);
+        q = make_query(g, p.x, p.y, p.z, h);
+    }
+    const RowBounds rb = rows_load(g, offset, q);
+    if (tid < NB_WINDOWS) window_bounds(g, offset, __ldg(posS + t0), __ldg(posS + t0 + nt - 1), tid, &bw);
+    if (tid == 0) s3_mbar_init(&bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t slots = window_pack(cap_slots, reach_ok, &bw);
+        if (slots > 0) {
+            s3_mbar_expect_tx(&bar, slots * 16u);
+            for (int w = 0; w < NB_WINDOWS; w++)
+                if (bw.soff[w] >= 0) s3_bulk_g2s(stage + bw.soff[w], posS + bw.lo[w], (uint32_t)(bw.hi[w] - bw.lo[w]) * 16u, &bar);
+        } else {
+            s3_mbar_arrive(&bar);
+        }
+    }
+    __syncthreads();                                   // windows packed, barrier armed
+    rows_store<P>(bw, q, rb, tid, tab);
+    s3_mbar_wait(&bar, 0);
+
+    float rho = 0.0f;
+    int* lp = list + tid;                              // next free entry of this thread's list (stride P)
+    int* const lend = list + K * P;
+    int* const dummy = list + K * P + tid;             // sink for rejected candidates
+    // A target with a long candidate list (a clump of particles, or a query wider than 3 x 3 rows) would
+    // keep its warp busy long after every other warp is done (clumps sit next to each other in cell
+    // order, so whole CTAs are heavy): those targets are queued and finished by sph3_density_heavy_kernel,
+    // one WARP per target spread over the whole GPU; everything else runs one thread per target here.
+    const bool heavy = active && (rb.wide || rb.total > HEAVY_CANDIDATES);
+    // branch-free candidate step: the poly6 term is added with weight 0 when rejected; the list append is
+    // a select, a store and a conditional pointer bump
+    auto step = [&](const float4 qp, int j) {
+        const float r2 = cwa_len3sq(p.x - qp.x, p.y - qp.y, p.z - qp.z);
+        const bool ok = r2 <= accept_r2;
+        const float d = ok ? (h2 - r2) : 0.0f;
+        rho = fmaf(poly6, d * d * d, rho);
+        int* dst = (ok && lp < lend) ? lp : dummy;     // always store: no branch in the candidate loop
+        *dst = j;
+        lp += ok ? P : 0;                              // keeps counting past the end of the list
+    };
+    if (!heavy) {
+#pragma unroll 1
+        for (int r = 0; r < RT_ROWS; r++) {
+            const int2 e = tab[r * P + tid];
+            const int len = e.y & 0xffff, sb = (int)((unsigned)e.y >> 16);
+            if (sb != RT_UNSTAGED) {
+                const float4* src = stage + sb;
+#pragma unroll 4
+                for (int c = 0; c < len; c++) step(src[c], e.x + c);
+            } else {
+                const float4* src = posS + e.x;
+#pragma unroll 4
+                for (int c = 0; c < len; c++) step(__ldg(src + c), e.x + c);
+            }
+        }
+    }
+    if (heavy) heavy_queue[atomicAdd(heavy_count, 1)] = slot;      // finished by sph3_density_heavy_kernel, one warp per target
+    if (active && !heavy) {
+        float rho_out, prs_out;
+        density_epilogue(*cc, tex, p.x, p.z, rho, rho_out, prs_out);
+        const float4 v = __ldg(velS + slot);
+        packA[slot] = make_float4(p.x, p.y, p.z, prs_out);
+        packB[slot] = make_float4(v.x, v.y, v.z, rho_out);
+        const int cnt = (int)(lp - (list + tid)) / P;
+        nbr_count[slot] = cnt;
+        const int m = min(cnt, K);
+        int4* out = reinterpret_cast<int4*>(nbr_list + (size_t)slot * K);      // the target's own 4K-byte-aligned row of K entries
+        for (int e = 0; e < m; e += 4)
+            out[e >> 2] = make_int4(list[e * P + tid], list[(e + 1) * P + tid], list[(e + 2) * P + tid], list[(e + 3) * P + tid]);
+    }
+}
+
+// Streamlined density + neighbour-list kernel (the default): no staging, no barriers.  Candidates are read
+// through L1 (measured faster than the TMA-staged variant above once the lists are built here: the smaller
+// shared-memory footprint doubles the resident CTAs).  When every cell is at least (1 + 2.5e-3) h wide the
+// conservative query is exactly the 3 x 3 x 3 block around the target's cell, so the per-axis range
+// computations collapse to one cell coordinate per axis.
+template <int P, int K, bool LOCAL>
+__global__ void __launch_bounds__(P)
+sph3_density_list_kernel(const float4* __restrict__ posS, const float4* __restrict__ velS,
+                         float4* __restrict__ packA, float4* __restrict__ packB,
+                         int* __restrict__ nbr_list, int* __restrict__ nbr_count,
+                         int* __restrict__ heavy_queue, int* __restrict__ heavy_count, int n_max, GridView g,
+                         const int* __restrict__ offset, const Sph3Const* __restrict__ cc, TexView tex)
+{
+    extern __shared__ int2 tab[];                      // int2 tab[9 * P] | int list[(K + 1) * P]
+    int* list = reinterpret_cast<int*>(tab + RT_ROWS * P);
+    const int tid = threadIdx.x;
+    const int slot = blockIdx.x * P + tid;
+    const int n = min(n_max, __ldg(offset + g.num_cells));   // inserted particles
+    if (slot >= n) return;
+    const float h = cc->h, accept_r2 = cc->accept_r2, h2 = cc->h2, poly6 = cc->poly6;
+    const float4 p = __ldg(posS + slot);
+    Query3 q;
+    const float hm = h * (1.0f + 2.5e-3f), hx = h * 1.25f;     // shortcut only where pos -+ h spans three cells anyway
+    if (hm <= g.cell[0] && hm <= g.cell[1] && hm <= g.cell[2] && g.cell[0] <= hx && g.cell[1] <= hx && g.cell[2] <= hx) {
+        // ci -+ 1 is a superset of ComputeCellIndex(pos -+ h): |x_j - x_i| < h <= cell / (1 + 2.5e-3) keeps a
+        // neighbour inside the adjacent cell; the bias covers the rounding of this estimate against the hash
+        const int ci = approx_cell(p.x, g.min[0], g.inv_cell[0], 0.0f, g.n[0]);
+        const int cj = approx_cell(p.y, g.min[1], g.inv_cell[1], 0.0f, g.n[1]);
+        const int ck = approx_cell(p.z, g.min[2], g.inv_cell[2], 0.0f, g.n[2]);
+        q.i0 = max(ci - 1, 0); q.i1 = min(ci + 1, g.n[0] - 1);
+        q.j0 = max(cj - 1, 0); q.j1 = min(cj + 1, g.n[1] - 1);
+        q.k0 = max(ck - 1, 0); q.k1 = min(ck + 1, g.n[2] - 1);
+        q.ci = ci; q.cj = cj;
+    } else {
+        q = make_query(g, p.x, p.y, p.z, h);
+    }
+    const RowBounds rb = rows_load(g, offset, q);
+    const bool heavy = rb.wide || rb.total > HEAVY_CANDIDATES;
+    if (heavy) {                                       // finished by sph3_density_heavy_kernel, one CTA per target
+        heavy_queue[atomicAdd(heavy_count, 1)] = slot;
+        return;
+    }
+#pragma unroll
+    for (int r = 0; r < RT_ROWS; r++) tab[r * P + tid] = make_int2(rb.b[r], rb.e[r] - rb.b[r]);
+
+    float rho = 0.0f;
+    int* lp = list + tid;                              // next free entry of this thread's list (stride P)
+    int* const lcap = list + K * P + tid;              // row K: where the stores go once the list is full
+    // Four candidates per trip, the four loads issued before the first use.  Every candidate index is
+    // stored at the current end of the list and the end only advances when the candidate is accepted (a
+    // rejected index is overwritten by the next store): no branch and no select in the loop.
+    auto quad = [&](const float4* src, int j, int left, bool tail) {
+        const float4 qp[4] = {__ldg(src), __ldg(src + 1), __ldg(src + 2), __ldg(src + 3)};
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const float r2 = cwa_len3sq(p.x - qp[u].x, p.y - qp[u].y, p.z - qp[u].z);
+            const bool ok = (r2 <= accept_r2) && (!tail || u < left);
+            const float d = ok ? (h2 - r2) : 0.0f;
+            rho = fmaf(poly6, d * d * d, rho);         // weight 0 when rejected
+            *((lp < lcap) ? lp : lcap) = j + u;
+            if (ok) lp += P;                           // keeps counting past the end of the list
+        }
+    };
+#pragma unroll 1
+    for (int r = 0; r < RT_ROWS; r++) {
+        const int2 e = tab[r * P + tid];
+        const float4* src = posS + e.x;
+        int j = e.x, left = e.y;
+        for (; left >= 4; left -= 4, src += 4, j += 4) quad(src, j, 4, false);
+        // the tail reads past the end of the row (the next slots of the cell-ordered array, padded by 4)
+        if (left > 0) quad(src, j, left, true);
+    }
+    float rho_out, prs_out;
+    density_epilogue<LOCAL>(*cc, tex, p.x, p.z, rho, rho_out, prs_out);
+    const float4 v = __ldg(velS + slot);
+    packA[slot] = make_float4(p.x, p.y, p.z, prs_out);
+    packB[slot] = make_float4(v.x, v.y, v.z, rho_out);
+    const int cnt = (int)(lp - (list + tid)) / P;
+    nbr_count[slot] = cnt;
+    const int m = min(cnt, K);
+    int4* out = reinterpret_cast<int4*>(nbr_list + (size_t)slot * K);
+    for (int e = 0; e < m; e += 4)
+        out[e >> 2] = make_int4(list[e * P + tid], list[(e + 1) * P + tid], list[(e + 2) * P + tid], list[(e + 3) * P + tid]);
+}
+
+// Heavy targets of the density pass: one CTA (4 warps) per queued target.  The rows of the query are dealt
+// round-robin to the warps, lane l takes every 32nd candidate of a row, the partial sums are combined with
+// warp shuffles and then in warp order (fixed order: run-to-run deterministic); thread 0 runs the
+// per-particle epilogue.  No neighbour list is written: the count is set past K, which routes the target to
+// sph3_force_heavy_kernel in the force pass.
+template <int K>
+__global__ void __launch_bounds__(128)
+sph3_density_heavy_kernel(const float4* __restrict__ posS, const float4* __restrict__ velS,
+                          float4* __restrict__ packA, float4* __restrict__ packB, int* __restrict__ nbr_count,
+                          const int* __restrict__ heavy_queue, const int* __restrict__ heavy_count, GridView g,
+                          const int* __restrict__ offset, const Sph3Const* __restrict__ cc, TexView tex)
+{
+    __shared__ float s_part[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int total = __ldg(heavy_count);
+    const float h = cc->h, accept_r2 = cc->accept_r2, h2 = cc->h2, poly6 = cc->poly6;
+    for (int e = blockIdx.x; e < total; e += gridDim.x) {
+        const int slot = __ldg(heavy_queue + e);
+        const float4 p = __ldg(posS + slot);
+        const Query3 q = make_query(g, p.x, p.y, p.z, h);
+        const int nj = q.j1 - q.j0 + 1, nrows = (q.i1 - q.i0 + 1) * nj;
+        float part = 0.0f;
+        for (int r = warp; r < nrows; r += 4) {
+            const int base = ((q.i0 + r / nj) * g.n[1] + (q.j0 + r % nj)) * g.kstride;
+            const int g0 = __ldg(offset + base + q.k0), g1 = __ldg(offset + base + q.k1 + 1);
+#pragma unroll 4
+            for (int c = g0 + lane; c < g1; c += 32) {
+                const float4 qp = __ldg(posS + c);
+                const float r2 = cwa_len3sq(p.x - qp.x, p.y - qp.y, p.z - qp.z);
+                const float d = (r2 <= accept_r2) ? (h2 - r2) : 0.0f;
+                part = fmaf(poly6, d * d * d, part);
+            }
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+        if (lane == 0) s_part[warp] = part;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const float rho = ((s_part[0] + s_part[1]) + s_part[2]) + s_part[3];
+            float rho_out, prs_out;
+            density_epilogue(*cc, tex, p.x, p.z, rho, rho_out, prs_out);
+            const float4 v = __ldg(velS + slot);
+            packA[slot] = make_float4(p.x, p.y, p.z, prs_out);
+            packB[slot] = make_float4(v.x, v.y, v.z, rho_out);
+            nbr_count[slot] = K + 1;
+        }
+        __syncthreads();
+    }
+}
+
+// Force pass over the neighbour lists of the density pass: neighbour sums of force_comp.glsl:74-88.
+// One thread per target, no shared memory; the gathers of (pos, p) / (vel, rho) hit L1/L2 because
+// consecutive cell-ordered targets share most of their neighbours.  Targets whose list overflowed (more
+// than K neighbours) are queued for sph3_force_heavy_kernel.
+template <int K>
+__global__ void __launch_bounds__(128, 8)
+sph3_force_list_kernel(const float4* __restrict__ packA, const float4* __restrict__ packB,
+                       const int* __restrict__ nbr_list, const int* __restrict__ nbr_count,
+                       int* __restrict__ heavy_queue, int* __restrict__ heavy_count,
+                       float4* __restrict__ pairP, float2* __restrict__ pairV, int n_max, GridView g,
+                       const int* __restrict__ offset, const Sph3Const* __restrict__ cc)
+{
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = min(n_max, __ldg(offset + g.num_cells));   // inserted particles
+    if (slot >= n) return;
+    const int cnt = __ldg(nbr_count + slot);
+    if (cnt > K) { heavy_queue[atomicAdd(heavy_count, 1)] = slot; return; }
+    const Sph3Const c = *cc;
+    const float4 pa = __ldg(packA + slot), pb = __ldg(packB + slot);
+    float fpx = 0.f, fpy = 0.f, fpz = 0.f, fvx = 0.f, fvy = 0.f, fvz = 0.f;
+    const int4* lp = reinterpret_cast<const int4*>(nbr_list + (size_t)slot * K);
+    int4 jn = (cnt > 0) ? __ldg(lp) : make_int4(slot, slot, slot, slot);
+    for (int e = 0; e < cnt; e += 4) {
+        const int4 j4 = jn;
+        if (e + 4 < cnt) jn = __ldg(lp + (e >> 2) + 1);                       // next quad of indices: overlaps the gathers below
+        int j[4] = {j4.x, j4.y, j4.z, j4.w};
+        float4 qa[4], qb[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (e + u >= cnt) j[u] = slot;            // tail of the last quad: skipped like self
+#pragma unroll
+        for (int u = 0; u < 4; u++) { qa[u] = __ldg(packA + j[u]); qb[u] = __ldg(packB + j[u]); }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (j[u] != slot) pair_force(c, pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, qa[u], qb[u], fpx, fpy, fpz, fvx, fvy, fvz);
+    }
+    pairP[slot] = make_float4(fpx, fpy, fpz, fvx);
+    pairV[slot] = make_float2(fvy, fvz);
+}
+
+// Targets with more than K neighbours: one CTA (4 warps) per queued target re-scans the grid; rows are
+// dealt round-robin to the warps, every lane takes every 32nd candidate of a row, the six sums are combined
+// with warp shuffles and then in warp order.
+__global__ void __launch_bounds__(128)
+sph3_force_heavy_kernel(const float4* __restrict__ packA, const float4* __restrict__ packB,
+                        const int* __restrict__ heavy_queue, const int* __restrict__ heavy_count,
+                        float4* __restrict__ pairP, float2* __restrict__ pairV, GridView g,
+                        const int* __restrict__ offset, const Sph3Const* __restrict__ cc)
+{
+    __shared__ float s_part[4][6];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int total = __ldg(heavy_count);
+    const Sph3Const c = *cc;
+    for (int e = blockIdx.x; e < total; e += gridDim.x) {
+        const int slot = __ldg(heavy_queue + e);
+        const float4 pa = __ldg(packA + slot), pb = __ldg(packB + slot);
+        const Query3 q = make_query(g, pa.x, pa.y, pa.z, c.h);
+        const int nj = q.j1 - q.j0 + 1, nrows = (q.i1 - q.i0 + 1) * nj;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f, s5 = 0.f;
+        for (int r = warp; r < nrows; r += 4) {
+            const int base = ((q.i0 + r / nj) * g.n[1] + (q.j0 + r % nj)) * g.kstride;
+            const int g0 = __ldg(offset + base + q.k0), g1 = __ldg(offset + base + q.k1 + 1);
+#pragma unroll 2
+            for (int k = g0 + lane; k < g1; k += 32) {
+                const float4 qa = __ldg(packA + k);
+                const float r2 = cwa_len3sq(pa.x - qa.x, pa.y - qa.y, pa.z - qa.z);
+                if (r2 <= c.accept_r2 && k != slot)
+                    pair_force(c, pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, qa, __ldg(packB + k), s0, s1, s2, s3, s4, s5);
+            }
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, d); s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, d); s3 += __shfl_xor_sync(0xffffffffu, s3, d);
+            s4 += __shfl_xor_sync(0xffffffffu, s4, d); s5 += __shfl_xor_sync(0xffffffffu, s5, d);
+        }
+        if (lane == 0) { s_part[warp][0] = s0; s_part[warp][1] = s1; s_part[warp][2] = s2; s_part[warp][3] = s3; s_part[warp][4] = s4; s_part[warp][5] = s5; }
+        __syncthreads();
+        if (threadIdx.x < 6) {
+            const int t = threadIdx.x;
+            const float v = ((s_part[0][t] + s_part[1][t]) + s_part[2][t]) + s_part[3][t];
+            if (t < 4) reinterpret_cast<float*>(pairP + slot)[t] = v;
+            else reinterpret_cast<float*>(pairV + slot)[t - 4] = v;
+        }
+        __syncthreads();
+    }
+}
+
 // force epilogue + integrate on the cell-ordered snapshot; one thread per particle writes the full
 // 64-B record back to the particle SSBO in its original order.
-__global__ void __launch_bounds__(256)
+template <bool LOCAL>
+__global__ void __launch_bounds__(128, 10)          // latency-bound gathers and scatters: favour occupancy over registers
 sph3_finalize_integrate_sorted_kernel(const float4* __restrict__ packA, const float4* __restrict__ packB,
                                       const float4* __restrict__ forceS, const float4* __restrict__ miscS,
                                       const float4* __restrict__ pairP, const float2* __restrict__ pairV,
@@ -505,10 +926,10 @@ sph3_finalize_integrate_sorted_kernel(const float4* __restrict__ packA, const fl
     const Sph3Const c = *cc;
     const float4 a = __ldg(packA + s), b = __ldg(packB + s), m = __ldg(miscS + s), pp = __ldg(pairP + s);
     const float2 pv = __ldg(pairV + s);
-    float4 f = force_epilogue(c, tex, a.x, a.y, a.z, b.x, b.y, b.z, b.w, __ldg(forceS + s), pp.x, pp.y, pp.z, pp.w, pv.x, pv.y);
+    float4 f = force_epilogue<LOCAL>(c, tex, a.x, a.y, a.z, b.x, b.y, b.z, b.w, __ldg(forceS + s), pp.x, pp.y, pp.z, pp.w, pv.x, pv.y);
     float4 pos = make_float4(a.x, a.y, a.z, m.x), vel = make_float4(b.x, b.y, b.z, m.y);
     float rho = b.w, prs = a.w;
-    integrate_particle(c, tex, pos, vel, f, rho, prs);
+    integrate_particle<LOCAL>(c, tex, pos, vel, f, rho, prs);
     float4* o = aos + (size_t)__ldg(index_list + s) * 4;
     o[0] = pos; o[1] = vel; o[2] = f; o[3] = make_float4(rho, prs, m.z, m.w);
 }
@@ -732,21 +1153,38 @@ static int env_int(const char* name, int dflt, int lo, int hi)
     int v = atoi(e);
     return v < lo ? lo : (v > hi ? hi : v);
 }
-// staging budgets (slots); tuning knobs CWA_NB_CAP_D / CWA_NB_CAP_F (0 disables staging)
-static int dens_cap() { static int v = -1; if (v < 0) v = env_int("CWA_NB_CAP_D", DENS_CAP_DEFAULT, 0, DENS_CAP_MAX); return v; }
-static int force_cap() { static int v = -1; if (v < 0) v = env_int("CWA_NB_CAP_F", FORCE_CAP_DEFAULT, 0, FORCE_CAP_MAX); return v; }
 
-// (targets per CTA, lanes per target) of the neighbour kernels; CWA_NB_CONFIG selects another
-// instantiation for tuning runs (0: 128x4, 1: 128x2 (default), 2: 64x4, 3: 256x1, 4: 128x1, 5: 64x2, 6: 256x2)
-static int nb_config()
+// Tuning knobs of the neighbour kernels.  Defaults come from the environment (CWA_NB_CONFIG,
+// CWA_NB_CAP_D / _F / _R) the first time they are needed; cwa_set_tuning() overrides them at run time
+// (used by the parity tests to cover every kernel variant in one process).
+//   nb_config: (targets per CTA, lanes per target) of the "lanes" kernels -- 0: 128x4, 1: 128x2, 2: 64x4,
+//              3: 256x1, 4: 128x1, 5: 64x2, 6: 256x2 -- or the "rows" kernels (one thread per target):
+//              7: P = 128, 8: P = 64, 9: P = 256 (TMA-staged candidates + neighbour lists), 10 / 11 / 12: the same
+//              P with candidates read through L1 (no staging, no barriers)
+//   cap_d / cap_f / cap_r: staging budgets in slots (0 disables staging)
+constexpr int NB_CONFIG_DEFAULT = 1;
+constexpr int ROWS_CAP_MAX = 3072;
+constexpr int NBR_K = 32;                 // neighbour-list entries per target (self included); longer lists fall back to a grid scan
+constexpr int ROWS_CAP_DEFAULT = 1536;    // 24 KB of staged candidates per CTA
+struct NbTuning { int config = -1, cap_d = -1, cap_f = -1, cap_r = -1, fused_order = -1; };
+static NbTuning g_tune;
+static int nb_config() { if (g_tune.config < 0) g_tune.config = env_int("CWA_NB_CONFIG", NB_CONFIG_DEFAULT, 0, 12); return g_tune.config; }
+static int dens_cap() { if (g_tune.cap_d < 0) g_tune.cap_d = env_int("CWA_NB_CAP_D", DENS_CAP_DEFAULT, 0, DENS_CAP_MAX); return g_tune.cap_d; }
+static int force_cap() { if (g_tune.cap_f < 0) g_tune.cap_f = env_int("CWA_NB_CAP_F", FORCE_CAP_DEFAULT, 0, FORCE_CAP_MAX); return g_tune.cap_f; }
+static bool fused_order() { if (g_tune.fused_order < 0) g_tune.fused_order = env_int("CWA_FUSED_ORDER", 1, 0, 1); return g_tune.fused_order != 0; }
+static int rows_cap() { if (g_tune.cap_r < 0) g_tune.cap_r = env_int("CWA_NB_CAP_R", ROWS_CAP_DEFAULT, 0, ROWS_CAP_MAX); return g_tune.cap_r; }
+
+extern "C" int cwa_set_tuning(cwa_ctx* ctx, const char* key, int value)
 {
-    static int cfg = -1;
-    if (cfg < 0) {
-        const char* e = getenv("CWA_NB_CONFIG");
-        cfg = e ? atoi(e) : 1;
-        if (cfg < 0 || cfg > 6) cfg = 1;
-    }
-    return cfg;
+    CWA_CHECK(ctx && key, "null argument");
+    const std::string k(key);
+    if (k == "nb_config") { CWA_CHECK(value >= 0 && value <= 12, "nb_config %d out of range", value); g_tune.config = value; }
+    else if (k == "nb_cap_d") { CWA_CHECK(value >= 0 && value <= DENS_CAP_MAX, "nb_cap_d %d out of range", value); g_tune.cap_d = value; }
+    else if (k == "nb_cap_f") { CWA_CHECK(value >= 0 && value <= FORCE_CAP_MAX, "nb_cap_f %d out of range", value); g_tune.cap_f = value; }
+    else if (k == "nb_cap_r") { CWA_CHECK(value >= 0 && value <= ROWS_CAP_MAX, "nb_cap_r %d out of range", value); g_tune.cap_r = value; }
+    else if (k == "fused_order") { g_tune.fused_order = value ? 1 : 0; }
+    else CWA_CHECK(false, "cwa_set_tuning: unknown key '%s'", key);
+    return 0;
 }
 
 template <int P, int L>
@@ -777,25 +1215,101 @@ static int launch_force(cwa_ctx* ctx, SphObj* s, GridObj* g)
     return 0;
 }
 
+// rows variant: one thread per target (CWA_NB_CONFIG 7: P = 128, 8: P = 64, 9: P = 256)
+
+// heavy-target kernels: a fixed grid of warps walks the device-side queue (no host round trip)
+static int heavy_grid(cwa_ctx* ctx) { return ctx->sm_count * 16; }
+
+template <int P>
+static int launch_density_rows(cwa_ctx* ctx, SphObj* s, GridObj* g, TexView tex)
+{
+    static bool attr = false;
+    const int fixed = RT_ROWS * P * 8 + (NBR_K + 1) * P * 4;
+    if (!attr) {
+        CWA_CUDA(cudaFuncSetAttribute(sph3_density_rows_kernel<P, NBR_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, ROWS_CAP_MAX * 16 + fixed));
+        attr = true;
+    }
+    { KScope k(ctx, KID_DENSITY);
+      sph3_density_rows_kernel<P, NBR_K><<<ceil_div(s->n, P), P, rows_cap() * 16 + fixed, ctx->stream>>>(
+          s->posS, s->velS, s->packA, s->packB, s->nbr_list, s->nbr_count, s->heavy_queue, s->heavy_count, s->n,
+          g->view, g->offset, (const Sph3Const*)s->consts, tex, rows_cap()); }
+    { KScope k(ctx, KID_DENSITY_HEAVY);
+      sph3_density_heavy_kernel<NBR_K><<<heavy_grid(ctx), 128, 0, ctx->stream>>>(
+          s->posS, s->velS, s->packA, s->packB, s->nbr_count, s->heavy_queue, s->heavy_count,
+          g->view, g->offset, (const Sph3Const*)s->consts, tex); }
+    s->nbr_lists_valid = true;
+    return 0;
+}
+
+template <int P>
+static int launch_density_list(cwa_ctx* ctx, SphObj* s, GridObj* g, TexView tex)
+{
+    const int smem = RT_ROWS * P * 8 + (NBR_K + 1) * P * 4;
+    const Sph3Const* cc = (const Sph3Const*)s->consts;
+    static bool attr = false;
+    if (!attr) {
+        CWA_CUDA(cudaFuncSetAttribute(sph3_density_list_kernel<P, NBR_K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CWA_CUDA(cudaFuncSetAttribute(sph3_density_list_kernel<P, NBR_K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr = true;
+    }
+    { KScope k(ctx, KID_DENSITY);
+      if (tex_view_is_local(tex))
+          sph3_density_list_kernel<P, NBR_K, true><<<ceil_div(s->n, P), P, smem, ctx->stream>>>(
+              s->posS, s->velS, s->packA, s->packB, s->nbr_list, s->nbr_count, s->heavy_queue, s->heavy_count, s->n,
+              g->view, g->offset, cc, tex);
+      else
+          sph3_density_list_kernel<P, NBR_K, false><<<ceil_div(s->n, P), P, smem, ctx->stream>>>(
+              s->posS, s->velS, s->packA, s->packB, s->nbr_list, s->nbr_count, s->heavy_queue, s->heavy_count, s->n,
+              g->view, g->offset, cc, tex); }
+    { KScope k(ctx, KID_DENSITY_HEAVY);
+      sph3_density_heavy_kernel<NBR_K><<<heavy_grid(ctx), 128, 0, ctx->stream>>>(
+          s->posS, s->velS, s->packA, s->packB, s->nbr_count, s->heavy_queue, s->heavy_count,
+          g->view, g->offset, cc, tex); }
+    s->nbr_lists_valid = true;
+    return 0;
+}
+
+static int launch_force_list(cwa_ctx* ctx, SphObj* s, GridObj* g)
+{
+    int* fq = s->heavy_queue + s->capacity;              // second half: the force pass's queue
+    { KScope k(ctx, KID_FORCE);
+      sph3_force_list_kernel<NBR_K><<<ceil_div(s->n, 128), 128, 0, ctx->stream>>>(
+          s->packA, s->packB, s->nbr_list, s->nbr_count, fq, s->heavy_count + 1, s->pairP, s->pairV, s->n,
+          g->view, g->offset, (const Sph3Const*)s->consts); }
+    { KScope k(ctx, KID_FORCE_HEAVY);
+      sph3_force_heavy_kernel<<<heavy_grid(ctx), 128, 0, ctx->stream>>>(
+          s->packA, s->packB, fq, s->heavy_count + 1, s->pairP, s->pairV, g->view, g->offset, (const Sph3Const*)s->consts); }
+    return 0;
+}
+
 static int sph_snapshot(cwa_ctx* ctx, SphObj* s)
 {
     GridObj* g = get_grid(ctx, s->grid);
     BufferObj* pb = get_buffer(ctx, s->particles);
     CWA_CHECK(g && pb, "sph: grid or particle buffer vanished");
-    CWA_TRY(grid_build_internal(ctx, g, pb->ptr, 64, s->n));
-    { KScope k(ctx, KID_REORDER);
-      sph3_reorder_kernel<<<ceil_div((long long)s->n * 4, 256), 256, 0, ctx->stream>>>(
-          (const float4*)pb->ptr, g->index_list, g->offset + g->view.num_cells, s->posS, s->velS, s->forceS, s->miscS); }
+    if (fused_order()) {
+        CWA_TRY(grid_build_internal(ctx, g, pb->ptr, 64, s->n, false));
+        KScope k(ctx, KID_REORDER);
+        sph3_order_reorder_kernel<<<ceil_div(s->n, 256), 256, 0, ctx->stream>>>(
+            (const float4*)pb->ptr, g->arrival, g->cell_of, g->offset, g->offset + g->view.num_cells, g->index_list,
+            s->posS, s->velS, s->forceS, s->miscS);
+    } else {
+        CWA_TRY(grid_build_internal(ctx, g, pb->ptr, 64, s->n));
+        KScope k(ctx, KID_REORDER);
+        sph3_reorder_kernel<<<ceil_div((long long)s->n * 4, 256), 256, 0, ctx->stream>>>(
+            (const float4*)pb->ptr, g->index_list, g->offset + g->view.num_cells, s->posS, s->velS, s->forceS, s->miscS);
+    }
     CWA_CUDA(cudaGetLastError());
     s->snapshot_valid = true;
     s->pair_sums_valid = false;
+    s->nbr_lists_valid = false;
     return 0;
 }
 
 static int sph_prepare(cwa_ctx* ctx, SphObj* s)
 {
     KScope k(ctx, KID_OTHER);
-    sph3_prepare_kernel<<<1, 32, 0, ctx->stream>>>(current_params(ctx), (Sph3Const*)s->consts);
+    sph3_prepare_kernel<<<1, 32, 0, ctx->stream>>>(current_params(ctx), (Sph3Const*)s->consts, s->heavy_count);
     return 0;
 }
 
@@ -850,6 +1364,12 @@ int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which)
         case 4: CWA_TRY((launch_density<128, 1>(ctx, s, g, tex))); break;
         case 5: CWA_TRY((launch_density<64, 2>(ctx, s, g, tex))); break;
         case 6: CWA_TRY((launch_density<256, 2>(ctx, s, g, tex))); break;
+        case 10: CWA_TRY((launch_density_list<128>(ctx, s, g, tex))); break;
+        case 11: CWA_TRY((launch_density_list<64>(ctx, s, g, tex))); break;
+        case 12: CWA_TRY((launch_density_list<256>(ctx, s, g, tex))); break;
+        case 7: CWA_TRY((launch_density_rows<128>(ctx, s, g, tex))); break;
+        case 8: CWA_TRY((launch_density_rows<64>(ctx, s, g, tex))); break;
+        case 9: CWA_TRY((launch_density_rows<256>(ctx, s, g, tex))); break;
         default: CWA_TRY((launch_density<128, 4>(ctx, s, g, tex))); break;
         }
         if (!full) {
@@ -866,6 +1386,9 @@ int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which)
         case 4: CWA_TRY((launch_force<128, 1>(ctx, s, g))); break;
         case 5: CWA_TRY((launch_force<64, 2>(ctx, s, g))); break;
         case 6: CWA_TRY((launch_force<256, 2>(ctx, s, g))); break;
+        case 7: case 8: case 9: case 10: case 11: case 12:
+            CWA_CHECK(s->nbr_lists_valid, "force pass: the neighbour lists of the density pass are missing");
+            CWA_TRY(launch_force_list(ctx, s, g)); break;
         default: CWA_TRY((launch_force<128, 4>(ctx, s, g))); break;
         }
         s->pair_sums_valid = true;
@@ -878,8 +1401,12 @@ int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which)
     if (which & 4) {
         KScope k(ctx, KID_INTEGRATE);
         if (full) {
-            sph3_finalize_integrate_sorted_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(
-                s->packA, s->packB, s->forceS, s->miscS, s->pairP, s->pairV, g->index_list, g->offset + g->view.num_cells, aos, cc, tex);
+            if (tex_view_is_local(tex))
+                sph3_finalize_integrate_sorted_kernel<true><<<ceil_div(n, 128), 128, 0, ctx->stream>>>(
+                    s->packA, s->packB, s->forceS, s->miscS, s->pairP, s->pairV, g->index_list, g->offset + g->view.num_cells, aos, cc, tex);
+            else
+                sph3_finalize_integrate_sorted_kernel<false><<<ceil_div(n, 128), 128, 0, ctx->stream>>>(
+                    s->packA, s->packB, s->forceS, s->miscS, s->pairP, s->pairV, g->index_list, g->offset + g->view.num_cells, aos, cc, tex);
         } else {
             sph3_integrate_aos_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(aos, n, cc, tex);
         }
@@ -904,17 +1431,23 @@ extern "C" int cwa_sph_create(cwa_ctx* ctx, cwa_buf particles, int n, cwa_grid g
     }
     SphObj s;
     s.live = true; s.particles = particles; s.n = n; s.capacity = n; s.grid = grid;
-    const size_t bytes = (size_t)(n > 0 ? n : 1) * 16;
+    const size_t bytes = (size_t)(n > 0 ? n : 1) * 16 + 64;          // + 4 slots: the neighbour loops read up to 3 slots past a row
     CWA_CUDA(cudaMalloc(&s.consts, sizeof(Sph3Const)));
     CWA_CUDA(cudaMalloc(&s.packA, bytes));
     CWA_CUDA(cudaMalloc(&s.packB, bytes));
     if (grid >= 0) {
         CWA_CUDA(cudaMalloc(&s.posS, bytes));
+        CWA_CUDA(cudaMemsetAsync(s.posS, 0, bytes, ctx->stream));     // the 4 pad slots are read (and masked out) by the neighbour loops
         CWA_CUDA(cudaMalloc(&s.velS, bytes));
         CWA_CUDA(cudaMalloc(&s.forceS, bytes));
         CWA_CUDA(cudaMalloc(&s.miscS, bytes));
         CWA_CUDA(cudaMalloc(&s.pairP, bytes));
         CWA_CUDA(cudaMalloc(&s.pairV, bytes / 2));
+        CWA_CUDA(cudaMalloc(&s.nbr_list, (size_t)(n > 0 ? n : 1) * NBR_K * 4));
+        CWA_CUDA(cudaMalloc(&s.nbr_count, (size_t)(n > 0 ? n : 1) * 4));
+        CWA_CUDA(cudaMalloc(&s.heavy_queue, (size_t)(n > 0 ? n : 1) * 2 * 4));
+        CWA_CUDA(cudaMalloc(&s.heavy_count, 2 * 4));
+        CWA_CUDA(cudaMemsetAsync(s.heavy_count, 0, 8, ctx->stream));
     }
     ctx->sphs.push_back(s);
     *out = (int)ctx->sphs.size() - 1;
@@ -927,7 +1460,7 @@ extern "C" int cwa_sph_destroy(cwa_ctx* ctx, cwa_sph h)
     CWA_CHECK(s, "invalid sph handle %d", h);
     CWA_CUDA(cudaStreamSynchronize(ctx->stream));
     cudaFree(s->packA); cudaFree(s->packB); cudaFree(s->posS); cudaFree(s->velS); cudaFree(s->forceS); cudaFree(s->miscS);
-    cudaFree(s->pairP); cudaFree(s->pairV); cudaFree(s->consts);
+    cudaFree(s->pairP); cudaFree(s->pairV); cudaFree(s->consts); cudaFree(s->nbr_list); cudaFree(s->nbr_count); cudaFree(s->heavy_queue); cudaFree(s->heavy_count);
     s->live = false;
     if (ctx->bound_sph == h) ctx->bound_sph = -1;
     return 0;

@@ -91,6 +91,10 @@ CWA_API int  cwa_profile_kernel_count(void);
 CWA_API const char* cwa_profile_kernel_name(int id);
 CWA_API int  cwa_profile_begin(cwa_ctx* ctx);
 CWA_API int  cwa_profile_end(cwa_ctx* ctx, float* ms, int* launches, int cap);   /* synchronises */
+/* kernel-variant / staging knobs of the neighbour loops (no reference counterpart: the GLSL has one variant).
+ * keys: "nb_config" (0..6 lanes kernels, 7..9 rows + neighbour-list kernels), "nb_cap_d", "nb_cap_f", "nb_cap_r" (staged slots),
+ *       "fused_order" (1: canonical ordering fused into the reorder pass). */
+CWA_API int  cwa_set_tuning(cwa_ctx* ctx, const char* key, int value);
 
 /* ---- Buffer: Init / BufferSubData / BindBufferBase / DebugRead*  (SphWave2D/Buffer.cpp:5-83) -- */
 CWA_API int cwa_buffer_create(cwa_ctx* ctx, size_t bytes, const void* host_or_null, cwa_buf* out); /* glNamedBufferStorage */

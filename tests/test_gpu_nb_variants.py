@@ -1,0 +1,134 @@
+"""GPU parity of every neighbour-kernel variant (cwa_set_tuning: "lanes" kernels 0..6, "rows" + neighbour-list
+kernels 7..9 (staged) and 10..12 (through L1))
+on several grids -- cells of 2h, cells slightly larger than h (27-cell queries), cells of exactly h and
+cells smaller than h (generic wide query) -- with full, partial and no shared-memory staging, against the
+all-pairs oracle.  Tolerance 1e-4 relative (summation order), neighbour sets identical."""
+import numpy as np
+import pytest
+
+from test_gpu_sph3 import NX, NY, NZ, _params
+from util import assert_close, jittered_block, smooth_field
+
+pytestmark = pytest.mark.gpu
+
+GRIDS = {
+    "2h": ((0.0, -0.02, 0.0), (0.26, 0.18, 0.26), (13, 10, 13)),
+    "h+": ((0.0, -0.02, 0.0), (0.26, 0.18, 0.26), (25, 19, 25)),        # cells 0.0104 x 0.0105: 3 x 3 rows of 3 cells
+    "h": ((0.0, -0.02, 0.0), (0.26, 0.18, 0.26), (26, 20, 26)),         # cells of exactly h: conservative ranges may reach 4 cells
+    "h/1.5": ((0.0, -0.02, 0.0), (0.26, 0.18, 0.26), (39, 30, 39)),     # h > cell: generic (wide) query
+}
+
+
+@pytest.fixture()
+def tuned(ctx):
+    yield ctx
+    ctx.set_tuning(nb_config=1, nb_cap_d=2048, nb_cap_f=1536, nb_cap_r=1536)
+
+
+def _scene(cwa, ctx, oracle, grid_key, cluster=False, seed=1234):
+    prm = _params(oracle)
+    ctx.set_params_from_oracle(prm)
+    p = jittered_block(oracle, NX, NY, NZ, prm, seed=seed, vel=0.5)
+    rng = np.random.default_rng(seed + 1)
+    p["force"] = rng.uniform(-1e4, 1e4, (p.size, 4)).astype(np.float32)
+    p["pos"][::7, 1] += np.float32(0.02)
+    if cluster:
+        # 300 particles inside a ball of radius 0.004: > 24 neighbours each (list drains), one very long row
+        c = np.array([0.101, 0.021, 0.099], np.float32)
+        d = rng.normal(size=(300, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+        p["pos"][1000:1300, :3] = c + (d * rng.uniform(0.0005, 0.004, (300, 1))).astype(np.float32)
+    tex = smooth_field(64, 64, 1, amp=0.02)
+    grid = cwa.UniformGrid(ctx, 3, *GRIDS[grid_key], p.size)
+    sph = cwa.Sph(ctx, p.size, grid, particles=p)
+    wave = cwa.StencilImage2DTripleBuffered(ctx, 64, 64, 1, cwa.WAVE_COUPLED)
+    wave.write_image(0, tex)
+    sph.bind_wave(wave, 0)
+    return prm, p, tex, sph
+
+
+def _check(oracle, prm, p, tex, sph):
+    sph.rho_pres()
+    sph.force()
+    got = sph.download()
+    ref = p.copy()
+    oracle.sph3_rho_pres(ref, prm, tex)
+    oracle.sph3_force(ref, prm, tex)
+    assert_close(got["extras"][:, 0], ref["extras"][:, 0], what="rho")
+    assert_close(got["extras"][:, 1], ref["extras"][:, 1], what="pressure")
+    assert_close(got["force"][:, :3], ref["force"][:, :3], what="force.xyz")
+
+
+@pytest.mark.parametrize("grid_key", list(GRIDS))
+@pytest.mark.parametrize("cfg", [1, 4, 7, 8, 9, 10, 11, 12])
+def test_variant_matches_oracle(cwa, tuned, oracle, cfg, grid_key):
+    tuned.set_tuning(nb_config=cfg)
+    prm, p, tex, sph = _scene(cwa, tuned, oracle, grid_key)
+    got = sph.neighbour_count()
+    assert np.array_equal(got, oracle.sph3_neighbour_count(p, 0.01))
+    _check(oracle, prm, p, tex, sph)
+
+
+@pytest.mark.parametrize("cap", [0, 96, 1536])
+@pytest.mark.parametrize("grid_key", ["2h", "h+"])
+@pytest.mark.parametrize("cfg", [1, 7])
+def test_variant_with_partial_or_no_staging(cwa, tuned, oracle, cfg, grid_key, cap):
+    tuned.set_tuning(nb_config=cfg, nb_cap_d=cap, nb_cap_f=cap, nb_cap_r=cap)
+    prm, p, tex, sph = _scene(cwa, tuned, oracle, grid_key)
+    _check(oracle, prm, p, tex, sph)
+
+
+@pytest.mark.parametrize("grid_key", ["2h", "h+", "h/1.5"])
+@pytest.mark.parametrize("cfg", [1, 7, 10])
+def test_variant_dense_cluster(cwa, tuned, oracle, cfg, grid_key):
+    """A 300-particle clump: neighbour counts far above the rows kernels' neighbour-list capacity and rows that
+    overflow the staging budget (list capacity K = 32 -> the force pass re-scans the grid for those targets)."""
+    tuned.set_tuning(nb_config=cfg)
+    prm, p, tex, sph = _scene(cwa, tuned, oracle, grid_key, cluster=True)
+    nb = oracle.sph3_neighbour_count(p, 0.01)
+    assert nb.max() >= 300
+    _check(oracle, prm, p, tex, sph)
+
+
+@pytest.mark.parametrize("cfg", [7, 10])
+def test_rows_variant_full_frames_equal_lanes_variant(cwa, tuned, oracle, cfg):
+    """3 fused frames: rows kernels vs the lanes kernels (same physics, summation order differs)."""
+    tuned.set_tuning(nb_config=1)
+    prm, p, tex, sph = _scene(cwa, tuned, oracle, "h+")
+    sph.step(3)
+    a = sph.download()
+    tuned.set_tuning(nb_config=cfg)
+    sph.upload(p)
+    sph.step(3)
+    b = sph.download()
+    assert_close(b["pos"][:, :3], a["pos"][:, :3], scale=1e-3, rtol=1e-3, what="pos")
+    assert_close(b["vel"][:, :3], a["vel"][:, :3], rtol=1e-3, what="vel")
+
+
+@pytest.mark.parametrize("cluster", [False, True])
+@pytest.mark.parametrize("fused", [0, 1])
+def test_fused_order_reorder_is_canonical(cwa, tuned, oracle, fused, cluster):
+    """The SPH snapshot path may fuse the canonical per-cell ordering into the reorder pass; the index list
+    it leaves behind must be the same bit-exact list (ascending id inside a cell) as the stand-alone build."""
+    tuned.set_tuning(fused_order=fused, nb_config=10)
+    try:
+        prm, p, tex, sph = _scene(cwa, tuned, oracle, "h+", cluster=cluster)
+        p["pos"][5, 0] = np.nan                    # a NaN particle is left out of the grid
+        sph.upload(p)
+        sph.rho_pres()
+        g = oracle.grid3(*GRIDS["h+"])
+        cell_of, cnt, off, idx = oracle.grid3_build(g, p["pos"])
+        n_ins = int(cnt.sum())
+        assert n_ins == p.size - 1
+        assert np.array_equal(sph.grid.read(cwa.GRID_COUNTER, cnt.size), cnt)
+        assert np.array_equal(sph.grid.read(cwa.GRID_OFFSET, off.size), off)
+        assert np.array_equal(sph.grid.read(cwa.GRID_INDEX_LIST, n_ins), idx[:n_ins])
+        sph.force()
+        got = sph.download()
+        ref = p.copy()
+        oracle.sph3_rho_pres(ref, prm, tex, grid=(g, cnt, off, idx))
+        oracle.sph3_force(ref, prm, tex, grid=(g, cnt, off, idx))
+        ok = np.arange(p.size) != 5
+        assert_close(got["extras"][ok, 0], ref["extras"][ok, 0], what="rho")
+        assert_close(got["force"][ok, :3], ref["force"][ok, :3], what="force.xyz")
+    finally:
+        tuned.set_tuning(fused_order=1)
