@@ -33,20 +33,24 @@ N_PARTICLES = NX * NY * NZ
 WAVE = 2048
 BOX_UPPER = (0.55 * S, 1.0, 0.55 * S, 500.0)       # box that contains the lattice (0.48*S would clamp 7*S columns -> coincident particles -> NaN)
 BOX_LOWER = (0.0, -0.02, 0.0, 50.0)
-GRID_MIN, GRID_MAX, GRID_N = (0.0, -0.02, 0.0), (0.55 * S, 1.0, 0.55 * S), (192, 51, 192)
-_GRID_VARIANT = os.environ.get("CWA_BENCH_GRID", "2h")        # tuning knob: cell size / extent of the uniform grid
-if _GRID_VARIANT == "h":                                      # cells of h = 0.01 (27-cell queries)
-    GRID_N = (384, 101, 384)                                  # cell = 1.0026 h x 1.0099 h x 1.0026 h: every query is exactly 3 x 3 x 3 cells
-elif _GRID_VARIANT == "h_tight":                              # cells of h, y extent cut to the occupied slab (outliers clamp into the top layer)
-    GRID_MAX, GRID_N = (0.55 * S, 0.18, 0.55 * S), (384, 20, 384)
-elif _GRID_VARIANT == "h_y30":                                # cells of ~h over the layer the fluid occupies; particles above clamp into the top layer (ugrid_particles_cs.glsl:98 clamps)
-    GRID_MAX, GRID_N = (0.55 * S, 0.30, 0.55 * S), (384, 31, 384)
+# Uniform grid of the neighbour search (an acceleration structure: any grid gives the same physics).  Cells of ~h so that
+# every query is the 3 x 3 x 3 block around the particle's cell; the y extent covers the layer the fluid occupies
+# and particles above it are clamped into the top layer, exactly what ComputeCellIndex does with out-of-extent
+# particles (UniformGrid2D/ugrid_particles_cs.glsl:97-103).  CWA_BENCH_GRID selects the other grids of the tuning runs.
+GRID_MIN, GRID_MAX, GRID_N, GRID_DESC = (0.0, -0.02, 0.0), (0.55 * S, 0.30, 0.55 * S), (384, 31, 384), "cells of ~h (1.003h x 1.03h x 1.003h), y extent [-0.02, 0.30] + clamp"
+_GRID_VARIANT = os.environ.get("CWA_BENCH_GRID", "h_y30")
+if _GRID_VARIANT == "2h":                                     # SURVEY C4 as first written: cells of 2h over the whole box
+    GRID_MAX, GRID_N, GRID_DESC = (0.55 * S, 1.0, 0.55 * S), (192, 51, 192), "cells of 2h"
+elif _GRID_VARIANT == "h":                                    # cells of ~h over the whole box
+    GRID_MAX, GRID_N, GRID_DESC = (0.55 * S, 1.0, 0.55 * S), (384, 101, 384), "cells of ~h"
+elif _GRID_VARIANT == "h_tight":
+    GRID_MAX, GRID_N, GRID_DESC = (0.55 * S, 0.18, 0.55 * S), (384, 20, 384), "cells of h, y extent [-0.02, 0.18] + clamp"
 elif _GRID_VARIANT == "2h_tight":
-    GRID_MAX, GRID_N = (0.55 * S, 0.18, 0.55 * S), (192, 10, 192)
+    GRID_MAX, GRID_N, GRID_DESC = (0.55 * S, 0.18, 0.55 * S), (192, 10, 192), "cells of 2h, y extent [-0.02, 0.18] + clamp"
 UV_SCALE = 2.0 / S
 COUPLING = 0                                        # AS_SHIPPED (reference schedule)
 WORKLOAD = (f"C4: 3-D coupled SPH+wave, {N_PARTICLES} particles ({NX}x{NY}x{NZ} lattice), grid {GRID_N[0]}x{GRID_N[1]}x{GRID_N[2]} "
-            f"cells of 2h, wave {WAVE}^2 scalar, coupling AS_SHIPPED")
+            f"{GRID_DESC}, wave {WAVE}^2 scalar, coupling AS_SHIPPED")
 
 # algorithmic bytes per unit for each kernel (DESIGN.md "kernels"): (per particle, per grid cell, per wave cell)
 ALGO_BYTES = {
@@ -54,13 +58,12 @@ ALGO_BYTES = {
     "grid_hash_count": (24, 0, 0),     # pos 16 B read, cell id 4 B + arrival rank 4 B written
     "scan_lookback": (0, 8, 0),        # 4 B read + 4 B written per cell, single pass
     "grid_insert": (16, 0, 0),         # cell id, rank, offset read; index written
-    "grid_cell_order": (16, 0, 0),     # cell id + offset read, arrival list read (once per entry), index written
-    "reorder": (132, 0, 0),            # index 4 B + 64 B gathered + 64 B written
-    "density": (64, 0, 0),             # compulsory: pos+vel 32 B read, packA/packB 32 B written (neighbour loop is FP32-bound)
-    "force": (64, 0, 0),               # compulsory: packA/packB/force 48 B read, force 16 B written
-    "density_heavy": (0, 0, 0),        # clumped targets finished one CTA each (a few thousand particles)
-    "force_heavy": (0, 0, 0),
-    "integrate": (132, 0, 0),          # 64 B read + index 4 B + 64 B written (full record back to the SSBO)
+    "grid_cell_order": (16, 0, 0),     # (stand-alone grid builds only) cell id + offset read, arrival list read, index written
+    "reorder": (148, 0, 0),            # fused ordering + reorder: arrival 4 + cell id 4 + offsets 8 + record 64 read; index 4 + snapshot 64 written
+    "density": (124, 0, 0),            # pos+vel 32 B read, pack 32 B + count 4 B + neighbour list ~56 B (13.4 entries) written; the loop itself is FP32/L1 bound
+    "force": (116, 0, 0),              # pack 32 B + count 4 B + list ~56 B read, pair sums 24 B written; neighbour gathers hit L1/L2
+    "heavy_targets": (0, 0, 0),        # clump targets (> 192 candidates / > 64 neighbours) finished one warp each, both passes
+    "integrate": (156, 0, 0),          # pack 32 + force 16 + misc 16 + pair sums 24 + index 4 read, 64 B record written to the SSBO
     "wave_evolve": (0, 0, 12),         # u(t-1) read once, u(t-2) read, u(t) written
 }
 
@@ -151,7 +154,7 @@ def scaled_scene(world: int):
     n = int(round(64 * S * f))
     box = 0.55 * S * f
     return dict(nx=n, ny=NY, nz=n, wave=int(round(WAVE * f / 4)) * 4, uv=2.0 / (S * f), box=box,
-                gmin=(0.0, -0.02, 0.0), gmax=(box, 1.0, box), gn=(int(round(192 * f)), 51, int(round(192 * f))))
+                gmin=(0.0, -0.02, 0.0), gmax=(box, GRID_MAX[1], box), gn=(int(round(GRID_N[0] * f)), GRID_N[1], int(round(GRID_N[2] * f))))
 
 
 def oracle_scene(O, world: int = 1):
@@ -249,17 +252,17 @@ def run_native(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
+    # ---- per-kernel profile over the next K steps (CUDA events around every launch): same regime of the simulated
+    # state as the timed region (the cost of a frame drifts as the fluid clumps, tools/state_evolution.py)
+    ctx.profile_begin()
+    sph.coupled_step(wave, K, COUPLING)
+    prof = ctx.profile_end()
     # keep the same kernels running a little longer so the 50 ms clock sampler sees them under load
     t_end = time.time() + 1.0
     while time.time() < t_end:
         sph.coupled_step(wave, 50, COUPLING)
         ctx.synchronize()
     clocks = sampler.stop() if rank == 0 else None
-
-    # ---- per-kernel profile over K steps (CUDA events around every launch) -----------------------
-    ctx.profile_begin()
-    sph.coupled_step(wave, K, COUPLING)
-    prof = ctx.profile_end()
 
     # ---- end to end through the C ABI with HOST buffers -------------------------------------------
     pin_p = torch.empty(N_PARTICLES * cwa.PARTICLE.itemsize, dtype=torch.uint8).pin_memory()
@@ -379,11 +382,11 @@ def run_native_distributed(args, world, rank, local_rank, torch, dist, cwa):
     ctx.set_sim_constants(uv_scale=uv)
     zl = max(0.0, plan.z_lo - 0.06) if rank > 0 else 0.0
     zh = min(box, plan.z_hi + 0.06) if rank < world - 1 else box
-    ncx = int(round(192 * f))
+    ncx = int(round(384 * f))
     ncz = max(4, int(math.ceil((zh - zl) / (box / ncx))))
     # the shipped parameters make the over-dense sheet blast apart (|v| in the thousands within ten frames), so tens of
     # thousands of particles cross a slab face per frame: generous fixed-size messages (8 MB per neighbour)
-    be = CudaBackend(cwa, ctx, plan, int(own.size * 1.3) + 400000, (0.0, -0.02, zl), (box, 1.0, zh), (ncx, 51, ncz),
+    be = CudaBackend(cwa, ctx, plan, int(own.size * 1.3) + 400000, (0.0, -0.02, zl), (box, GRID_MAX[1], zh), (ncx, GRID_N[1], ncz),
                      cap_mig=65536, cap_ghost=65536)
     be.upload_owned(own)
     n_global = nxg * NY * nzg
@@ -502,7 +505,7 @@ def run_native_distributed(args, world, rank, local_rank, torch, dist, cwa):
             "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "steps_per_sec": 1e3 / ms_step,
             "config": {"workload": f"C4 scaled by sqrt({world}) in x and z: {n_global} particles ({nxg}x{NY}x{nzg} lattice), wave {wave_n}^2 scalar, "
-                                   f"coupling AS_SHIPPED, grid cells of 2h", "per_gpu_particles": n_global // world,
+                                   f"coupling AS_SHIPPED, grid {GRID_DESC}", "per_gpu_particles": n_global // world,
                        "parallelism": f"z-slab decomposition x{world}: ghost layer 2h + migration (NCCL p2p), wave row blocks with sampling halos + last-row broadcast",
                        "l2": "working set > 126 MB L2 per GPU: inputs larger than L2, no flush needed",
                        "timing": "cudaEvent on each rank's context stream around K coupled frames (communication included), max over ranks"},

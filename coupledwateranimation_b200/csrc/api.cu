@@ -197,7 +197,7 @@ extern "C" unsigned long long cwa_launch_count(cwa_ctx* ctx) { return ctx ? ctx-
 // per-kernel device timing (CUDA-event pairs around every launch on the context stream)
 static const char* const g_kernel_names[KID_COUNT] = {
     "clear(memset)", "grid_hash_count", "scan_lookback", "grid_insert", "grid_cell_order", "reorder",
-    "density", "force", "integrate", "wave_evolve", "other", "density_heavy", "force_heavy"};
+    "density", "force", "integrate", "wave_evolve", "other", "heavy_targets"};
 
 extern "C" int cwa_profile_kernel_count(void) { return KID_COUNT; }
 extern "C" const char* cwa_profile_kernel_name(int id) { return (id >= 0 && id < KID_COUNT) ? g_kernel_names[id] : ""; }

@@ -136,12 +136,13 @@ struct SphObj {
     int  wave_image = -1;          // physical image, -1 unbound
     // cell-ordered snapshot (grid mode) -- see DESIGN.md "data layout"
     float4 *posS = nullptr, *velS = nullptr, *forceS = nullptr, *miscS = nullptr;
-    float4 *packA = nullptr, *packB = nullptr;   // (pos.xyz, p) and (vel.xyz, rho)
+    float4 *pack = nullptr;                      // per slot two float4: (pos.xyz, p) at 2s and (vel.xyz, rho) at 2s+1 -- one 32-byte sector
+    float4 *scratch = nullptr;                   // all-pairs mode: pass results before they are committed to the SSBO
     float4 *pairP = nullptr;                     // neighbour sums of the force pass: (pres.xyz, visc.x)
     float2 *pairV = nullptr;                     //                                   (visc.y, visc.z)
     int   *nbr_list = nullptr, *nbr_count = nullptr;   // neighbour lists of the density pass ([slot][K]) and true counts
     bool   nbr_lists_valid = false;
-    int   *heavy_queue = nullptr, *heavy_count = nullptr;   // targets finished one warp each: [0,cap) density, [cap,2cap) force; two counters
+    int   *heavy_queue = nullptr, *heavy_count = nullptr;   // targets finished one warp each: [0,cap) density pass, [cap,2cap) force pass; two counters
     void*  consts = nullptr;                     // Sph3Const prepared on the device once per dispatch
     bool snapshot_valid = false;
     bool pair_sums_valid = false;
@@ -173,7 +174,7 @@ struct ShaderObj {
 // kernels of the hot path, as reported by the per-kernel profile (bench.py roofline section)
 enum KernelId {
     KID_CLEAR = 0, KID_HASH_COUNT, KID_SCAN, KID_INSERT, KID_CELL_ORDER, KID_REORDER,
-    KID_DENSITY, KID_FORCE, KID_INTEGRATE, KID_WAVE, KID_OTHER, KID_DENSITY_HEAVY, KID_FORCE_HEAVY, KID_COUNT
+    KID_DENSITY, KID_FORCE, KID_INTEGRATE, KID_WAVE, KID_OTHER, KID_HEAVY, KID_COUNT
 };
 
 struct ProfRec { int id; cudaEvent_t a, b; };
@@ -253,6 +254,25 @@ struct KScope {
 // device helpers shared by the kernels
 // ---------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+// 256-bit global accesses (sm_100: LDG.E.ENL2.256 / STG.E.ENL2.256).  The 32-byte records of the hot path --
+// the (pos, p | vel, rho) pack of a cell-ordered slot, half a particle record, a pair of candidate positions
+// -- are exactly one sector, so one request moves what two 128-bit requests moved before.
+// `p` must be 32-byte aligned.
+struct f4x2 { float4 a, b; };
+__device__ __forceinline__ f4x2 cwa_ldg256(const float4* p)
+{
+    f4x2 r;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w)
+        : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void cwa_stg256(float4* p, const float4 a, const float4 b)
+{
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+}
 
 // float -> cell coordinate, clamp in the float domain first (NaN -> 0).  Restates
 // ivec(floor(q)); clamp(cell, 0, n-1) of uniform_grid_sph_cs.glsl:144-145 with a defined

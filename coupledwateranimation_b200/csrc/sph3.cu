@@ -110,7 +110,7 @@ __global__ void sph3_prepare_kernel(ParamPtrs prm, Sph3Const* __restrict__ out, 
 {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         *out = load_consts(prm);
-        if (heavy_count) { heavy_count[0] = 0; heavy_count[1] = 0; }     // queues of the heavy-target kernels
+        if (heavy_count) { heavy_count[0] = heavy_count[1] = 0; }     // queues of the heavy kernels (density pass, force pass)
     }
 }
 
@@ -274,7 +274,8 @@ sph3_order_reorder_kernel(const float4* __restrict__ aos, const int* __restrict_
     if (s >= __ldg(count)) return;                 // inserted particles (NaN positions are left out)
     const int id = __ldg(arrival + s);
     const float4* rec = aos + (size_t)id * 4;
-    const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2), r3 = __ldg(rec + 3);
+    const f4x2 h0 = cwa_ldg256(rec), h1 = cwa_ldg256(rec + 2);   // the 64-byte record: two sectors, two requests
+    const float4 r0 = h0.a, r1 = h0.b, r2 = h1.a, r3 = h1.b;
     const int c = __ldg(cell_of + id);
     const int b = __ldg(offset + c), e = __ldg(offset + c + 1);
     int smaller = 0;
@@ -370,7 +371,7 @@ __device__ __forceinline__ int row_shift(const BlockWindows& bw, const Query3& q
 template <int P, int L>
 __global__ void __launch_bounds__(P * L)
 sph3_density_grid_kernel(const float4* __restrict__ posS, const float4* __restrict__ velS,
-                         float4* __restrict__ packA, float4* __restrict__ packB, int n_max, GridView g,
+                         float4* __restrict__ pack, int n_max, GridView g,
                          const int* __restrict__ offset, const Sph3Const* __restrict__ cc, TexView tex, int cap_slots)
 {
     extern __shared__ float4 stage[];
@@ -429,8 +430,7 @@ sph3_density_grid_kernel(const float4* __restrict__ posS, const float4* __restri
         float rho_out, prs_out;
         density_epilogue(*cc, tex, p.x, p.z, rho, rho_out, prs_out);
         const float4 v = __ldg(velS + slot);
-        packA[slot] = make_float4(p.x, p.y, p.z, prs_out);
-        packB[slot] = make_float4(v.x, v.y, v.z, rho_out);
+        cwa_stg256(pack + 2 * (size_t)slot, make_float4(p.x, p.y, p.z, prs_out), make_float4(v.x, v.y, v.z, rho_out));
     }
 }
 
@@ -438,11 +438,11 @@ sph3_density_grid_kernel(const float4* __restrict__ posS, const float4* __restri
 // the element-wise kernels below, where every lane has work.
 template <int P, int L>
 __global__ void __launch_bounds__(P * L)
-sph3_force_grid_kernel(const float4* __restrict__ packA, const float4* __restrict__ packB,
+sph3_force_grid_kernel(const float4* __restrict__ pack,
                        float4* __restrict__ pairP, float2* __restrict__ pairV, int n_max, GridView g,
                        const int* __restrict__ offset, const Sph3Const* __restrict__ cc, int cap_slots)
 {
-    extern __shared__ float4 stage[];                 // [cap_slots] A followed by [cap_slots] B
+    extern __shared__ float4 stage[];                 // [cap_slots] records of two float4: (pos, p), (vel, rho)
     __shared__ BlockWindows bw;
     __shared__ uint64_t bar;
     const int tid = threadIdx.x;
@@ -452,19 +452,17 @@ sph3_force_grid_kernel(const float4* __restrict__ packA, const float4* __restric
     const int nt = min(P, n - t0);
     const Sph3Const c = *cc;
     const bool reach_ok = (c.h <= g.cell[0]) && (c.h <= g.cell[1]) && (c.h <= g.cell[2]);
-    float4* stageA = stage;
-    float4* stageB = stage + cap_slots;
 
     const int slot = t0 + tid / L, sub = tid % L;
     const bool active = (tid / L) < nt;
     float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa;
     Query3 q{0, -1, 0, -1, 0, 0, 0, 0};
     if (active) {
-        pa = __ldg(packA + slot);
-        pb = __ldg(packB + slot);
+        pa = __ldg(pack + 2 * (size_t)slot);
+        pb = __ldg(pack + 2 * (size_t)slot + 1);
         q = make_query(g, pa.x, pa.y, pa.z, c.h);
     }
-    if (tid < NB_WINDOWS) window_bounds(g, offset, __ldg(packA + t0), __ldg(packA + t0 + nt - 1), tid, &bw);
+    if (tid < NB_WINDOWS) window_bounds(g, offset, __ldg(pack + 2 * (size_t)t0), __ldg(pack + 2 * (size_t)(t0 + nt - 1)), tid, &bw);
     if (tid == 0) s3_mbar_init(&bar, 1);
     __syncthreads();
     if (tid == 0) {
@@ -472,11 +470,8 @@ sph3_force_grid_kernel(const float4* __restrict__ packA, const float4* __restric
         if (slots > 0) {
             s3_mbar_expect_tx(&bar, slots * 32u);
             for (int w = 0; w < NB_WINDOWS; w++)
-                if (bw.soff[w] >= 0) {
-                    const uint32_t b = (uint32_t)(bw.hi[w] - bw.lo[w]) * 16u;
-                    s3_bulk_g2s(stageA + bw.soff[w], packA + bw.lo[w], b, &bar);
-                    s3_bulk_g2s(stageB + bw.soff[w], packB + bw.lo[w], b, &bar);
-                }
+                if (bw.soff[w] >= 0)
+                    s3_bulk_g2s(stage + 2 * bw.soff[w], pack + 2 * (size_t)bw.lo[w], (uint32_t)(bw.hi[w] - bw.lo[w]) * 32u, &bar);
         } else {
             s3_mbar_arrive(&bar);
         }
@@ -490,15 +485,15 @@ sph3_force_grid_kernel(const float4* __restrict__ packA, const float4* __restric
             const int base = (i * g.n[1] + j) * g.kstride;
             const int g0 = __ldg(offset + base + q.k0), g1 = __ldg(offset + base + q.k1 + 1);
             const int shift = row_shift(bw, q, i, j, g0, g1);
-            const float4* sa = (shift != INT_MIN) ? (const float4*)(stageA + shift) : packA;
-            const float4* sb = (shift != INT_MIN) ? (const float4*)(stageB + shift) : packB;
+            // records of the row: staged (shared memory) or straight from global memory, two float4 per slot
+            const float4* sa = (shift != INT_MIN) ? (const float4*)(stage + 2 * shift) : pack;
             for (int cb = g0 + sub; cb < g1; cb += 32 * L) {
                 // phase 1: mark accepted candidates (up to 32 per lane) -- cheap, runs on every candidate
                 unsigned mask = 0u;
                 int cnd = cb;
 #pragma unroll 4
                 for (int t = 0; t < 32 && cnd < g1; t++, cnd += L) {
-                    const float4 qa = sa[cnd];
+                    const float4 qa = sa[2 * cnd];
                     const float r2 = cwa_len3sq(pa.x - qa.x, pa.y - qa.y, pa.z - qa.z);
                     if (r2 <= c.accept_r2 && cnd != slot) mask |= (1u << t);
                 }
@@ -507,7 +502,7 @@ sph3_force_grid_kernel(const float4* __restrict__ packA, const float4* __restric
                     const int t = __ffs(mask) - 1;
                     mask &= mask - 1u;
                     const int cj = cb + t * L;
-                    pair_force(c, pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, sa[cj], sb[cj], fpx, fpy, fpz, fvx, fvy, fvz);
+                    pair_force(c, pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, sa[2 * cj], sa[2 * cj + 1], fpx, fpy, fpz, fvx, fvy, fvz);
                 }
             }
         }
@@ -525,27 +520,51 @@ sph3_force_grid_kernel(const float4* __restrict__ packA, const float4* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
-// "rows" neighbour kernels: ONE thread per target, per-thread row table in shared memory
+// neighbour-list kernels (the default): ONE thread per target
 // ---------------------------------------------------------------------------------------------
-// With h <= cell the query pos -+ h touches at most 3 x 3 rows (i,j) of cells, each a contiguous
-// run [offset[k0], offset[k1+1]) of the cell-ordered arrays.  Every thread loads the (up to) 18 row
-// bounds of its target up front (independent loads, their latency overlaps the window staging),
-// translates them into staging-buffer coordinates and parks them in a shared-memory table; the
-// neighbour loop is then one rolled loop over 9 table rows with a tight candidate loop inside.
-// Table entry (int2): x = first global slot, y = length | staged_begin << 16 (0xffff: row not staged,
-// read it from global memory through L1).  Targets whose query is wider than 3 x 3 rows (h > cell) or
-// that own a row of >= 65535 candidates take the generic loop at the end.
+// With h <= cell the query pos -+ h touches at most 3 x 3 rows (i,j) of cells, each a contiguous run
+// [offset[k0], offset[k1+1]) of the cell-ordered arrays.  The density pass loads the (up to) 18 row bounds
+// of its target up front (independent loads), parks them in a small shared-memory table and walks the nine
+// rows; every accepted candidate is also appended to the target's neighbour list, which the force pass
+// walks instead of testing the candidates a second time (positions do not change between the two passes).
+//
+// Work per target varies by orders of magnitude once particles clump (cells with hundreds of particles): a thread
+// left alone with such a target would outlast the rest of the kernel.  Targets with more than EXTREME_CANDIDATES
+// candidates (density pass) or more than K neighbours (force pass) are therefore pushed to a device-side queue and
+// finished by the "heavy" kernels, one WARP per target, spread over the whole GPU.
 constexpr int RT_ROWS = 9;
-constexpr int RT_UNSTAGED = 0xffff;
-constexpr int HEAVY_CANDIDATES = 160;     // a target with more candidates than this is processed by its whole warp
+constexpr int TILE_P = 128;               // targets per tile (= CTA size of the list kernels)
+constexpr int EXTREME_CANDIDATES = 192;   // a target with more candidates than this is finished by a whole warp (heavy kernels)
+constexpr int EXTREME_MARK = 1 << 30;     // neighbour count written for such a target: routes it to the heavy force kernel
 
 struct RowBounds { int b[RT_ROWS], e[RT_ROWS]; int total; bool wide; };
+
+// Conservative query of a target.  When every cell is between (1 + 2.5e-3) h and 1.25 h wide, pos -+ h always
+// spans the 3 x 3 x 3 block around the target's cell (a superset of ComputeCellIndex(pos -+ h): a neighbour is
+// closer than h <= cell / (1 + 2.5e-3) on every axis, the margin covers the rounding of this estimate against
+// the hash), so one cell coordinate per axis is enough; otherwise the per-axis ranges of make_query.
+__device__ __forceinline__ Query3 list_query(const GridView& g, float x, float y, float z, float h)
+{
+    const float hm = h * (1.0f + 2.5e-3f), hx = h * 1.25f;
+    if (hm <= g.cell[0] && hm <= g.cell[1] && hm <= g.cell[2] && g.cell[0] <= hx && g.cell[1] <= hx && g.cell[2] <= hx) {
+        Query3 q;
+        const int ci = approx_cell(x, g.min[0], g.inv_cell[0], 0.0f, g.n[0]);
+        const int cj = approx_cell(y, g.min[1], g.inv_cell[1], 0.0f, g.n[1]);
+        const int ck = approx_cell(z, g.min[2], g.inv_cell[2], 0.0f, g.n[2]);
+        q.i0 = max(ci - 1, 0); q.i1 = min(ci + 1, g.n[0] - 1);
+        q.j0 = max(cj - 1, 0); q.j1 = min(cj + 1, g.n[1] - 1);
+        q.k0 = max(ck - 1, 0); q.k1 = min(ck + 1, g.n[2] - 1);
+        q.ci = ci; q.cj = cj;
+        return q;
+    }
+    return make_query(g, x, y, z, h);
+}
 
 __device__ __forceinline__ RowBounds rows_load(const GridView& g, const int* __restrict__ offset, const Query3& q)
 {
     RowBounds rb;
-    const int ni = q.i1 - q.i0 + 1, nj = q.j1 - q.j0 + 1;          // inactive thread: 0 x 0
-    rb.wide = (ni > 3) || (nj > 3);
+    const int ni = q.i1 - q.i0 + 1, nj = q.j1 - q.j0 + 1;
+    rb.wide = (ni > 3) || (nj > 3);                    // h > cell: the generic loops handle the target
 #pragma unroll
     for (int r = 0; r < RT_ROWS; r++) {
         const int a = r / 3, b = r % 3;
@@ -558,303 +577,167 @@ __device__ __forceinline__ RowBounds rows_load(const GridView& g, const int* __r
     }
     rb.total = 0;
 #pragma unroll
-    for (int r = 0; r < RT_ROWS; r++) {
-        if (rb.e[r] - rb.b[r] >= 0xffff) rb.wide = true;
-        rb.total += rb.e[r] - rb.b[r];
-    }
+    for (int r = 0; r < RT_ROWS; r++) rb.total += rb.e[r] - rb.b[r];
     return rb;
 }
 
-template <int P>
-__device__ __forceinline__ void rows_store(const BlockWindows& bw, const Query3& q, const RowBounds& rb, int tid, int2* __restrict__ tab)
-{
-#pragma unroll
-    for (int r = 0; r < RT_ROWS; r++) {
-        const int a = r / 3, b = r % 3;
-        const int len = rb.wide ? 0 : (rb.e[r] - rb.b[r]);
-        int sb = RT_UNSTAGED;
-        const int di = q.i0 + a - q.ci + 1, dj = q.j0 + b - q.cj + 1;
-        if (len > 0 && (unsigned)di < 3u && (unsigned)dj < 3u) {
-            const int w = di * 3 + dj;
-            const int so = bw.soff[w], lo = bw.lo[w], hi = bw.hi[w];
-            if (so >= 0 && rb.b[r] >= lo && rb.e[r] <= hi) sb = so + (rb.b[r] - lo);
-        }
-        tab[r * P + tid] = make_int2(rb.b[r], len | (sb << 16));
-    }
-}
-
-// Density pass + neighbour lists.  While it sums the poly6 terms the kernel appends every accepted
-// candidate (self included) to a per-thread list in shared memory and finally writes the list to the
-// target's row of K entries in global memory ([slot][K], 16-byte stores): positions do not change between
-// the density and the force pass, so the force pass walks these lists instead of testing the candidates a
-// second time.
-// count[slot] is the true neighbour count; a target with more than K neighbours keeps only its count and
-// the force kernel re-scans the grid for it.
-template <int P, int K>
-__global__ void __launch_bounds__(P)
-sph3_density_rows_kernel(const float4* __restrict__ posS, const float4* __restrict__ velS,
-                         float4* __restrict__ packA, float4* __restrict__ packB,
+// Density pass + neighbour lists.  Candidates are read through L1 with 256-bit loads (a pair of cell-ordered
+// positions is one sector); shared memory only holds the row table, which leaves most of the SM's 228 KB to
+// the L1 cache.  An accepted candidate (self included) is appended to the target's own row of K entries in
+// global memory ([slot][K], a private 128-byte line that stays in L2 until the force pass reads it) with one
+// predicated store; count[slot] keeps counting past K, and the force pass re-scans the grid for such a target.
+template <int K, bool LOCAL>
+__global__ void __launch_bounds__(TILE_P)
+sph3_density_list_kernel(const float4* __restrict__ posS, const float4* __restrict__ velS, float4* __restrict__ pack,
                          int* __restrict__ nbr_list, int* __restrict__ nbr_count,
-                         int* __restrict__ heavy_queue, int* __restrict__ heavy_count, int n_max, GridView g,
-                         const int* __restrict__ offset, const Sph3Const* __restrict__ cc, TexView tex, int cap_slots)
+                         int* __restrict__ heavy_queue, int* __restrict__ heavy_count,
+                         int n_max, GridView g, const int* __restrict__ offset, const Sph3Const* __restrict__ cc, TexView tex)
 {
-    extern __shared__ float4 stage[];                  // [cap_slots] positions | int2 tab[9 * P] | int list[(K + 1) * P]
-    int2* tab = reinterpret_cast<int2*>(stage + cap_slots);
-    int* list = reinterpret_cast<int*>(tab + RT_ROWS * P);
-    __shared__ BlockWindows bw;
-    __shared__ uint64_t bar;
+    __shared__ int2 tab[RT_ROWS * TILE_P];             // (first slot, length) of the 3 x 3 rows of every target
     const int tid = threadIdx.x;
-    const int t0 = blockIdx.x * P;
-    const int n = min(n_max, __ldg(offset + g.num_cells));   // inserted particles
-    if (t0 >= n) return;
-    const int nt = min(P, n - t0);
-    const float h = cc->h, accept_r2 = cc->accept_r2, h2 = cc->h2, poly6 = cc->poly6;
-    const bool reach_ok = (h <= g.cell[0]) && (h <= g.cell[1]) && (h <= g.cell[2]);
-
-    const int slot = t0 + tid;
-    const bool active = tid < nt;
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    Query3 q{0, -1, 0, -1, 0, 0, 0, 0};
-    if (active) {
-        p = __ldg(posS + slot);
-        q = make_query(g, p.x, p.y, p.z, h);
-    }
-    const RowBounds rb = rows_load(g, offset, q);
-    if (tid < NB_WINDOWS) window_bounds(g, offset, __ldg(posS + t0), __ldg(posS + t0 + nt - 1), tid, &bw);
-    if (tid == 0) s3_mbar_init(&bar, 1);
-    __syncthreads();
-    if (tid == 0) {
-        const uint32_t slots = window_pack(cap_slots, reach_ok, &bw);
-        if (slots > 0) {
-            s3_mbar_expect_tx(&bar, slots * 16u);
-            for (int w = 0; w < NB_WINDOWS; w++)
-                if (bw.soff[w] >= 0) s3_bulk_g2s(stage + bw.soff[w], posS + bw.lo[w], (uint32_t)(bw.hi[w] - bw.lo[w]) * 16u, &bar);
-        } else {
-            s3_mbar_arrive(&bar);
-        }
-    }
-    __syncthreads();                                   // windows packed, barrier armed
-    rows_store<P>(bw, q, rb, tid, tab);
-    s3_mbar_wait(&bar, 0);
-
-    float rho = 0.0f;
-    int* lp = list + tid;                              // next free entry of this thread's list (stride P)
-    int* const lend = list + K * P;
-    int* const dummy = list + K * P + tid;             // sink for rejected candidates
-    // A target with a long candidate list (a clump of particles, or a query wider than 3 x 3 rows) would
-    // keep its warp busy long after every other warp is done (clumps sit next to each other in cell
-    // order, so whole CTAs are heavy): those targets are queued and finished by sph3_density_heavy_kernel,
-    // one WARP per target spread over the whole GPU; everything else runs one thread per target here.
-    const bool heavy = active && (rb.wide || rb.total > HEAVY_CANDIDATES);
-    // branch-free candidate step: the poly6 term is added with weight 0 when rejected; the list append is
-    // a select, a store and a conditional pointer bump
-    auto step = [&](const float4 qp, int j) {
-        const float r2 = cwa_len3sq(p.x - qp.x, p.y - qp.y, p.z - qp.z);
-        const bool ok = r2 <= accept_r2;
-        const float d = ok ? (h2 - r2) : 0.0f;
-        rho = fmaf(poly6, d * d * d, rho);
-        int* dst = (ok && lp < lend) ? lp : dummy;     // always store: no branch in the candidate loop
-        *dst = j;
-        lp += ok ? P : 0;                              // keeps counting past the end of the list
-    };
-    if (!heavy) {
-#pragma unroll 1
-        for (int r = 0; r < RT_ROWS; r++) {
-            const int2 e = tab[r * P + tid];
-            const int len = e.y & 0xffff, sb = (int)((unsigned)e.y >> 16);
-            if (sb != RT_UNSTAGED) {
-                const float4* src = stage + sb;
-#pragma unroll 4
-                for (int c = 0; c < len; c++) step(src[c], e.x + c);
-            } else {
-                const float4* src = posS + e.x;
-#pragma unroll 4
-                for (int c = 0; c < len; c++) step(__ldg(src + c), e.x + c);
-            }
-        }
-    }
-    if (heavy) heavy_queue[atomicAdd(heavy_count, 1)] = slot;      // finished by sph3_density_heavy_kernel, one warp per target
-    if (active && !heavy) {
-        float rho_out, prs_out;
-        density_epilogue(*cc, tex, p.x, p.z, rho, rho_out, prs_out);
-        const float4 v = __ldg(velS + slot);
-        packA[slot] = make_float4(p.x, p.y, p.z, prs_out);
-        packB[slot] = make_float4(v.x, v.y, v.z, rho_out);
-        const int cnt = (int)(lp - (list + tid)) / P;
-        nbr_count[slot] = cnt;
-        const int m = min(cnt, K);
-        int4* out = reinterpret_cast<int4*>(nbr_list + (size_t)slot * K);      // the target's own 4K-byte-aligned row of K entries
-        for (int e = 0; e < m; e += 4)
-            out[e >> 2] = make_int4(list[e * P + tid], list[(e + 1) * P + tid], list[(e + 2) * P + tid], list[(e + 3) * P + tid]);
-    }
-}
-
-// Streamlined density + neighbour-list kernel (the default): no staging, no barriers.  Candidates are read
-// through L1 (measured faster than the TMA-staged variant above once the lists are built here: the smaller
-// shared-memory footprint doubles the resident CTAs).  When every cell is at least (1 + 2.5e-3) h wide the
-// conservative query is exactly the 3 x 3 x 3 block around the target's cell, so the per-axis range
-// computations collapse to one cell coordinate per axis.
-template <int P, int K, bool LOCAL>
-__global__ void __launch_bounds__(P)
-sph3_density_list_kernel(const float4* __restrict__ posS, const float4* __restrict__ velS,
-                         float4* __restrict__ packA, float4* __restrict__ packB,
-                         int* __restrict__ nbr_list, int* __restrict__ nbr_count,
-                         int* __restrict__ heavy_queue, int* __restrict__ heavy_count, int n_max, GridView g,
-                         const int* __restrict__ offset, const Sph3Const* __restrict__ cc, TexView tex)
-{
-    extern __shared__ int2 tab[];                      // int2 tab[9 * P] | int list[(K + 1) * P]
-    int* list = reinterpret_cast<int*>(tab + RT_ROWS * P);
-    const int tid = threadIdx.x;
-    const int slot = blockIdx.x * P + tid;
+    const int slot = blockIdx.x * TILE_P + tid;
     const int n = min(n_max, __ldg(offset + g.num_cells));   // inserted particles
     if (slot >= n) return;
     const float h = cc->h, accept_r2 = cc->accept_r2, h2 = cc->h2, poly6 = cc->poly6;
     const float4 p = __ldg(posS + slot);
-    Query3 q;
-    const float hm = h * (1.0f + 2.5e-3f), hx = h * 1.25f;     // shortcut only where pos -+ h spans three cells anyway
-    if (hm <= g.cell[0] && hm <= g.cell[1] && hm <= g.cell[2] && g.cell[0] <= hx && g.cell[1] <= hx && g.cell[2] <= hx) {
-        // ci -+ 1 is a superset of ComputeCellIndex(pos -+ h): |x_j - x_i| < h <= cell / (1 + 2.5e-3) keeps a
-        // neighbour inside the adjacent cell; the bias covers the rounding of this estimate against the hash
-        const int ci = approx_cell(p.x, g.min[0], g.inv_cell[0], 0.0f, g.n[0]);
-        const int cj = approx_cell(p.y, g.min[1], g.inv_cell[1], 0.0f, g.n[1]);
-        const int ck = approx_cell(p.z, g.min[2], g.inv_cell[2], 0.0f, g.n[2]);
-        q.i0 = max(ci - 1, 0); q.i1 = min(ci + 1, g.n[0] - 1);
-        q.j0 = max(cj - 1, 0); q.j1 = min(cj + 1, g.n[1] - 1);
-        q.k0 = max(ck - 1, 0); q.k1 = min(ck + 1, g.n[2] - 1);
-        q.ci = ci; q.cj = cj;
-    } else {
-        q = make_query(g, p.x, p.y, p.z, h);
-    }
+    const Query3 q = list_query(g, p.x, p.y, p.z, h);
     const RowBounds rb = rows_load(g, offset, q);
-    const bool heavy = rb.wide || rb.total > HEAVY_CANDIDATES;
-    if (heavy) {                                       // finished by sph3_density_heavy_kernel, one CTA per target
+    if (rb.total > EXTREME_CANDIDATES) {               // a big clump: finished by sph3_density_heavy_kernel, one CTA per target
         heavy_queue[atomicAdd(heavy_count, 1)] = slot;
         return;
     }
 #pragma unroll
-    for (int r = 0; r < RT_ROWS; r++) tab[r * P + tid] = make_int2(rb.b[r], rb.e[r] - rb.b[r]);
+    for (int r = 0; r < RT_ROWS; r++) tab[r * TILE_P + tid] = make_int2(rb.b[r], rb.e[r] - rb.b[r]);
 
     float rho = 0.0f;
-    int* lp = list + tid;                              // next free entry of this thread's list (stride P)
-    int* const lcap = list + K * P + tid;              // row K: where the stores go once the list is full
-    // Four candidates per trip, the four loads issued before the first use.  Every candidate index is
-    // stored at the current end of the list and the end only advances when the candidate is accepted (a
-    // rejected index is overwritten by the next store): no branch and no select in the loop.
-    auto quad = [&](const float4* src, int j, int left, bool tail) {
-        const float4 qp[4] = {__ldg(src), __ldg(src + 1), __ldg(src + 2), __ldg(src + 3)};
+    int cnt = 0;
+    int* const gl = nbr_list + (size_t)slot * K;       // the target's own row of K entries
+    auto step = [&](const float4 qp, int j, bool valid) {
+        const float r2 = cwa_len3sq(p.x - qp.x, p.y - qp.y, p.z - qp.z);
+        const bool ok = (r2 <= accept_r2) && valid;
+        const float d = ok ? (h2 - r2) : 0.0f;
+        rho = fmaf(poly6, d * d * d, rho);             // weight 0 when rejected: no branch around the arithmetic
+        if (ok && cnt < K) gl[cnt] = j;
+        cnt += ok ? 1 : 0;
+    };
+    // Four candidates per trip.  `j` is even: the two 256-bit loads fetch the pairs (j, j+1) and (j+2, j+3),
+    // both issued before the first use.  Candidates outside [first, first + len) -- the slot before an odd row
+    // start, the slots after the row end (the cell-ordered array is padded by 4) -- are masked out.
+    auto quad = [&](int j, int first, int len, bool masked) {
+        const f4x2 lo = cwa_ldg256(posS + j), hi = cwa_ldg256(posS + j + 2);
+        const float4 qp[4] = {lo.a, lo.b, hi.a, hi.b};
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const float r2 = cwa_len3sq(p.x - qp[u].x, p.y - qp[u].y, p.z - qp[u].z);
-            const bool ok = (r2 <= accept_r2) && (!tail || u < left);
-            const float d = ok ? (h2 - r2) : 0.0f;
-            rho = fmaf(poly6, d * d * d, rho);         // weight 0 when rejected
-            *((lp < lcap) ? lp : lcap) = j + u;
-            if (ok) lp += P;                           // keeps counting past the end of the list
-        }
+        for (int u = 0; u < 4; u++) step(qp[u], j + u, !masked || (unsigned)(j + u - first) < (unsigned)len);
     };
 #pragma unroll 1
     for (int r = 0; r < RT_ROWS; r++) {
-        const int2 e = tab[r * P + tid];
-        const float4* src = posS + e.x;
-        int j = e.x, left = e.y;
-        for (; left >= 4; left -= 4, src += 4, j += 4) quad(src, j, 4, false);
-        // the tail reads past the end of the row (the next slots of the cell-ordered array, padded by 4)
-        if (left > 0) quad(src, j, left, true);
+        const int2 e = tab[r * TILE_P + tid];
+        if (e.y <= 0) continue;
+        const int end = e.x + e.y;
+        int j = e.x & ~1;
+        quad(j, e.x, e.y, true);                       // first quad: the row may start at an odd slot
+        for (j += 4; j + 4 <= end; j += 4) quad(j, e.x, e.y, false);
+        if (j < end) quad(j, e.x, e.y, true);          // last quad: reads past the end of the row
+    }
+    if (rb.wide) {                                     // h > cell: generic query, one candidate at a time
+        for (int i = q.i0; i <= q.i1; i++)
+            for (int j = q.j0; j <= q.j1; j++) {
+                const int base = (i * g.n[1] + j) * g.kstride;
+                const int g0 = __ldg(offset + base + q.k0), g1 = __ldg(offset + base + q.k1 + 1);
+                for (int c = g0; c < g1; c++) step(__ldg(posS + c), c, true);
+            }
     }
     float rho_out, prs_out;
     density_epilogue<LOCAL>(*cc, tex, p.x, p.z, rho, rho_out, prs_out);
     const float4 v = __ldg(velS + slot);
-    packA[slot] = make_float4(p.x, p.y, p.z, prs_out);
-    packB[slot] = make_float4(v.x, v.y, v.z, rho_out);
-    const int cnt = (int)(lp - (list + tid)) / P;
+    cwa_stg256(pack + 2 * (size_t)slot, make_float4(p.x, p.y, p.z, prs_out), make_float4(v.x, v.y, v.z, rho_out));
     nbr_count[slot] = cnt;
-    const int m = min(cnt, K);
-    int4* out = reinterpret_cast<int4*>(nbr_list + (size_t)slot * K);
-    for (int e = 0; e < m; e += 4)
-        out[e >> 2] = make_int4(list[e * P + tid], list[(e + 1) * P + tid], list[(e + 2) * P + tid], list[(e + 3) * P + tid]);
 }
 
-// Heavy targets of the density pass: one CTA (4 warps) per queued target.  The rows of the query are dealt
-// round-robin to the warps, lane l takes every 32nd candidate of a row, the partial sums are combined with
-// warp shuffles and then in warp order (fixed order: run-to-run deterministic); thread 0 runs the
-// per-particle epilogue.  No neighbour list is written: the count is set past K, which routes the target to
-// sph3_force_heavy_kernel in the force pass.
-template <int K>
+// Extreme targets of the density pass (a clump: hundreds to thousands of candidates; left to one thread each they
+// would outlast the rest of the kernel): one WARP per queued target, spread over the whole GPU.  Lanes 0..8 fetch the
+// bounds of the nine rows in parallel; then lane l takes every 32nd candidate of each row (coalesced 16-byte loads),
+// and the partial sums are combined with warp shuffles (fixed order: run-to-run deterministic); lane 0 runs the
+// per-particle epilogue.  No neighbour list is written: the count is EXTREME_MARK, which routes the target to
+// sph3_force_heavy_kernel.
+template <bool LOCAL>
 __global__ void __launch_bounds__(128)
-sph3_density_heavy_kernel(const float4* __restrict__ posS, const float4* __restrict__ velS,
-                          float4* __restrict__ packA, float4* __restrict__ packB, int* __restrict__ nbr_count,
-                          const int* __restrict__ heavy_queue, const int* __restrict__ heavy_count, GridView g,
-                          const int* __restrict__ offset, const Sph3Const* __restrict__ cc, TexView tex)
+sph3_density_heavy_kernel(const float4* __restrict__ posS, const float4* __restrict__ velS, float4* __restrict__ pack,
+                          int* __restrict__ nbr_count, const int* __restrict__ heavy_queue, const int* __restrict__ heavy_count,
+                          GridView g, const int* __restrict__ offset, const Sph3Const* __restrict__ cc, TexView tex)
 {
-    __shared__ float s_part[4];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int total = __ldg(heavy_count);
     const float h = cc->h, accept_r2 = cc->accept_r2, h2 = cc->h2, poly6 = cc->poly6;
-    for (int e = blockIdx.x; e < total; e += gridDim.x) {
+    for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < total; e += nwarps) {
         const int slot = __ldg(heavy_queue + e);
         const float4 p = __ldg(posS + slot);
-        const Query3 q = make_query(g, p.x, p.y, p.z, h);
+        const Query3 q = list_query(g, p.x, p.y, p.z, h);
         const int nj = q.j1 - q.j0 + 1, nrows = (q.i1 - q.i0 + 1) * nj;
         float part = 0.0f;
-        for (int r = warp; r < nrows; r += 4) {
-            const int base = ((q.i0 + r / nj) * g.n[1] + (q.j0 + r % nj)) * g.kstride;
-            const int g0 = __ldg(offset + base + q.k0), g1 = __ldg(offset + base + q.k1 + 1);
+        for (int r0 = 0; r0 < nrows; r0 += 32) {           // 32 rows per round (nine in the usual 3 x 3 x 3 query)
+            int g0 = 0, g1 = 0;
+            if (r0 + lane < nrows) {
+                const int r = r0 + lane;
+                const int base = ((q.i0 + r / nj) * g.n[1] + (q.j0 + r % nj)) * g.kstride;
+                g0 = __ldg(offset + base + q.k0); g1 = __ldg(offset + base + q.k1 + 1);
+            }
+            const int rows_here = min(32, nrows - r0);
+            for (int r = 0; r < rows_here; r++) {
+                const int b = __shfl_sync(0xffffffffu, g0, r), en = __shfl_sync(0xffffffffu, g1, r);
 #pragma unroll 4
-            for (int c = g0 + lane; c < g1; c += 32) {
-                const float4 qp = __ldg(posS + c);
-                const float r2 = cwa_len3sq(p.x - qp.x, p.y - qp.y, p.z - qp.z);
-                const float d = (r2 <= accept_r2) ? (h2 - r2) : 0.0f;
-                part = fmaf(poly6, d * d * d, part);
+                for (int c = b + lane; c < en; c += 32) {
+                    const float4 qp = __ldg(posS + c);
+                    const float r2 = cwa_len3sq(p.x - qp.x, p.y - qp.y, p.z - qp.z);
+                    const float d = (r2 <= accept_r2) ? (h2 - r2) : 0.0f;
+                    part = fmaf(poly6, d * d * d, part);
+                }
             }
         }
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
-        if (lane == 0) s_part[warp] = part;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const float rho = ((s_part[0] + s_part[1]) + s_part[2]) + s_part[3];
+        if (lane == 0) {
             float rho_out, prs_out;
-            density_epilogue(*cc, tex, p.x, p.z, rho, rho_out, prs_out);
+            density_epilogue<LOCAL>(*cc, tex, p.x, p.z, part, rho_out, prs_out);
             const float4 v = __ldg(velS + slot);
-            packA[slot] = make_float4(p.x, p.y, p.z, prs_out);
-            packB[slot] = make_float4(v.x, v.y, v.z, rho_out);
-            nbr_count[slot] = K + 1;
+            cwa_stg256(pack + 2 * (size_t)slot, make_float4(p.x, p.y, p.z, prs_out), make_float4(v.x, v.y, v.z, rho_out));
+            nbr_count[slot] = EXTREME_MARK;
         }
-        __syncthreads();
     }
 }
 
-// Force pass over the neighbour lists of the density pass: neighbour sums of force_comp.glsl:74-88.
-// One thread per target, no shared memory; the gathers of (pos, p) / (vel, rho) hit L1/L2 because
-// consecutive cell-ordered targets share most of their neighbours.  Targets whose list overflowed (more
-// than K neighbours) are queued for sph3_force_heavy_kernel.
+// Force pass over the neighbour lists of the density pass: neighbour sums of force_comp.glsl:74-88.  One thread
+// per target, no shared memory; a neighbour's (pos, p | vel, rho) record is one sector fetched with one 256-bit
+// load, and consecutive cell-ordered targets share most of their neighbours, so the gathers hit L1/L2.  A target
+// whose list overflowed (more than K neighbours) or that the density pass marked extreme is queued for the heavy kernel.
 template <int K>
-__global__ void __launch_bounds__(128, 8)
-sph3_force_list_kernel(const float4* __restrict__ packA, const float4* __restrict__ packB,
-                       const int* __restrict__ nbr_list, const int* __restrict__ nbr_count,
+__global__ void __launch_bounds__(TILE_P, 6)
+sph3_force_list_kernel(const float4* __restrict__ pack, const int* __restrict__ nbr_list, const int* __restrict__ nbr_count,
                        int* __restrict__ heavy_queue, int* __restrict__ heavy_count,
-                       float4* __restrict__ pairP, float2* __restrict__ pairV, int n_max, GridView g,
-                       const int* __restrict__ offset, const Sph3Const* __restrict__ cc)
+                       float4* __restrict__ pairP, float2* __restrict__ pairV, int n_max,
+                       GridView g, const int* __restrict__ offset, const Sph3Const* __restrict__ cc)
 {
-    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const int slot = blockIdx.x * TILE_P + threadIdx.x;
     const int n = min(n_max, __ldg(offset + g.num_cells));   // inserted particles
     if (slot >= n) return;
     const int cnt = __ldg(nbr_count + slot);
-    if (cnt > K) { heavy_queue[atomicAdd(heavy_count, 1)] = slot; return; }
+    if (cnt > K) { heavy_queue[atomicAdd(heavy_count, 1)] = slot; return; }       // list overflow / extreme target: sph3_force_heavy_kernel
     const Sph3Const c = *cc;
-    const float4 pa = __ldg(packA + slot), pb = __ldg(packB + slot);
+    const f4x2 own = cwa_ldg256(pack + 2 * (size_t)slot);
+    const float4 pa = own.a, pb = own.b;
     float fpx = 0.f, fpy = 0.f, fpz = 0.f, fvx = 0.f, fvy = 0.f, fvz = 0.f;
     const int4* lp = reinterpret_cast<const int4*>(nbr_list + (size_t)slot * K);
     int4 jn = (cnt > 0) ? __ldg(lp) : make_int4(slot, slot, slot, slot);
     for (int e = 0; e < cnt; e += 4) {
         const int4 j4 = jn;
-        if (e + 4 < cnt) jn = __ldg(lp + (e >> 2) + 1);                       // next quad of indices: overlaps the gathers below
+        if (e + 4 < cnt) jn = __ldg(lp + (e >> 2) + 1);                           // next quad of indices: overlaps the gathers below
         int j[4] = {j4.x, j4.y, j4.z, j4.w};
         float4 qa[4], qb[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) if (e + u >= cnt) j[u] = slot;            // tail of the last quad: skipped like self
+        for (int u = 0; u < 4; u++) if (e + u >= cnt) j[u] = slot;                // tail of the last quad: skipped like self
 #pragma unroll
-        for (int u = 0; u < 4; u++) { qa[u] = __ldg(packA + j[u]); qb[u] = __ldg(packB + j[u]); }
+        for (int u = 0; u < 4; u++) { const f4x2 rec = cwa_ldg256(pack + 2 * (size_t)j[u]); qa[u] = rec.a; qb[u] = rec.b; }
 #pragma unroll
         for (int u = 0; u < 4; u++)
             if (j[u] != slot) pair_force(c, pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, qa[u], qb[u], fpx, fpy, fpz, fvx, fvy, fvz);
@@ -863,34 +746,41 @@ sph3_force_list_kernel(const float4* __restrict__ packA, const float4* __restric
     pairV[slot] = make_float2(fvy, fvz);
 }
 
-// Targets with more than K neighbours: one CTA (4 warps) per queued target re-scans the grid; rows are
-// dealt round-robin to the warps, every lane takes every 32nd candidate of a row, the six sums are combined
-// with warp shuffles and then in warp order.
+// Queued targets of the force pass (list overflow, clumps): one WARP per target re-scans the grid; lanes 0..8 fetch the row bounds in
+// parallel, lane l takes every 32nd candidate of a row, the six sums are combined with warp shuffles.
 __global__ void __launch_bounds__(128)
-sph3_force_heavy_kernel(const float4* __restrict__ packA, const float4* __restrict__ packB,
-                        const int* __restrict__ heavy_queue, const int* __restrict__ heavy_count,
+sph3_force_heavy_kernel(const float4* __restrict__ pack, const int* __restrict__ heavy_queue, const int* __restrict__ heavy_count,
                         float4* __restrict__ pairP, float2* __restrict__ pairV, GridView g,
                         const int* __restrict__ offset, const Sph3Const* __restrict__ cc)
 {
-    __shared__ float s_part[4][6];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int total = __ldg(heavy_count);
     const Sph3Const c = *cc;
-    for (int e = blockIdx.x; e < total; e += gridDim.x) {
+    for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < total; e += nwarps) {
         const int slot = __ldg(heavy_queue + e);
-        const float4 pa = __ldg(packA + slot), pb = __ldg(packB + slot);
-        const Query3 q = make_query(g, pa.x, pa.y, pa.z, c.h);
+        const f4x2 own = cwa_ldg256(pack + 2 * (size_t)slot);
+        const float4 pa = own.a, pb = own.b;
+        const Query3 q = list_query(g, pa.x, pa.y, pa.z, c.h);
         const int nj = q.j1 - q.j0 + 1, nrows = (q.i1 - q.i0 + 1) * nj;
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f, s5 = 0.f;
-        for (int r = warp; r < nrows; r += 4) {
-            const int base = ((q.i0 + r / nj) * g.n[1] + (q.j0 + r % nj)) * g.kstride;
-            const int g0 = __ldg(offset + base + q.k0), g1 = __ldg(offset + base + q.k1 + 1);
+        for (int r0 = 0; r0 < nrows; r0 += 32) {
+            int g0 = 0, g1 = 0;
+            if (r0 + lane < nrows) {
+                const int r = r0 + lane;
+                const int base = ((q.i0 + r / nj) * g.n[1] + (q.j0 + r % nj)) * g.kstride;
+                g0 = __ldg(offset + base + q.k0); g1 = __ldg(offset + base + q.k1 + 1);
+            }
+            const int rows_here = min(32, nrows - r0);
+            for (int r = 0; r < rows_here; r++) {
+                const int b = __shfl_sync(0xffffffffu, g0, r), en = __shfl_sync(0xffffffffu, g1, r);
 #pragma unroll 2
-            for (int k = g0 + lane; k < g1; k += 32) {
-                const float4 qa = __ldg(packA + k);
-                const float r2 = cwa_len3sq(pa.x - qa.x, pa.y - qa.y, pa.z - qa.z);
-                if (r2 <= c.accept_r2 && k != slot)
-                    pair_force(c, pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, qa, __ldg(packB + k), s0, s1, s2, s3, s4, s5);
+                for (int k = b + lane; k < en; k += 32) {
+                    const f4x2 rec = cwa_ldg256(pack + 2 * (size_t)k);
+                    const float r2 = cwa_len3sq(pa.x - rec.a.x, pa.y - rec.a.y, pa.z - rec.a.z);
+                    if (r2 <= c.accept_r2 && k != slot)
+                        pair_force(c, pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, rec.a, rec.b, s0, s1, s2, s3, s4, s5);
+                }
             }
         }
 #pragma unroll
@@ -899,15 +789,10 @@ sph3_force_heavy_kernel(const float4* __restrict__ packA, const float4* __restri
             s2 += __shfl_xor_sync(0xffffffffu, s2, d); s3 += __shfl_xor_sync(0xffffffffu, s3, d);
             s4 += __shfl_xor_sync(0xffffffffu, s4, d); s5 += __shfl_xor_sync(0xffffffffu, s5, d);
         }
-        if (lane == 0) { s_part[warp][0] = s0; s_part[warp][1] = s1; s_part[warp][2] = s2; s_part[warp][3] = s3; s_part[warp][4] = s4; s_part[warp][5] = s5; }
-        __syncthreads();
-        if (threadIdx.x < 6) {
-            const int t = threadIdx.x;
-            const float v = ((s_part[0][t] + s_part[1][t]) + s_part[2][t]) + s_part[3][t];
-            if (t < 4) reinterpret_cast<float*>(pairP + slot)[t] = v;
-            else reinterpret_cast<float*>(pairV + slot)[t - 4] = v;
+        if (lane == 0) {
+            pairP[slot] = make_float4(s0, s1, s2, s3);
+            pairV[slot] = make_float2(s4, s5);
         }
-        __syncthreads();
     }
 }
 
@@ -915,7 +800,7 @@ sph3_force_heavy_kernel(const float4* __restrict__ packA, const float4* __restri
 // 64-B record back to the particle SSBO in its original order.
 template <bool LOCAL>
 __global__ void __launch_bounds__(128, 10)          // latency-bound gathers and scatters: favour occupancy over registers
-sph3_finalize_integrate_sorted_kernel(const float4* __restrict__ packA, const float4* __restrict__ packB,
+sph3_finalize_integrate_sorted_kernel(const float4* __restrict__ pack,
                                       const float4* __restrict__ forceS, const float4* __restrict__ miscS,
                                       const float4* __restrict__ pairP, const float2* __restrict__ pairV,
                                       const int* __restrict__ index_list, const int* __restrict__ count, float4* __restrict__ aos,
@@ -924,30 +809,32 @@ sph3_finalize_integrate_sorted_kernel(const float4* __restrict__ packA, const fl
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= __ldg(count)) return;
     const Sph3Const c = *cc;
-    const float4 a = __ldg(packA + s), b = __ldg(packB + s), m = __ldg(miscS + s), pp = __ldg(pairP + s);
+    const f4x2 ab = cwa_ldg256(pack + 2 * (size_t)s);
+    const float4 a = ab.a, b = ab.b, m = __ldg(miscS + s), pp = __ldg(pairP + s);
     const float2 pv = __ldg(pairV + s);
     float4 f = force_epilogue<LOCAL>(c, tex, a.x, a.y, a.z, b.x, b.y, b.z, b.w, __ldg(forceS + s), pp.x, pp.y, pp.z, pp.w, pv.x, pv.y);
     float4 pos = make_float4(a.x, a.y, a.z, m.x), vel = make_float4(b.x, b.y, b.z, m.y);
     float rho = b.w, prs = a.w;
     integrate_particle<LOCAL>(c, tex, pos, vel, f, rho, prs);
-    float4* o = aos + (size_t)__ldg(index_list + s) * 4;
-    o[0] = pos; o[1] = vel; o[2] = f; o[3] = make_float4(rho, prs, m.z, m.w);
+    float4* o = aos + (size_t)__ldg(index_list + s) * 4;      // 64-byte record = two 256-bit stores (two full sectors)
+    cwa_stg256(o, pos, vel);
+    cwa_stg256(o + 2, f, make_float4(rho, prs, m.z, m.w));
 }
 
 // individually dispatched passes: commit one pass result to the SSBO
 __global__ void __launch_bounds__(256)
-sph3_scatter_rho_pres_kernel(const float4* __restrict__ packA, const float4* __restrict__ packB,
+sph3_scatter_rho_pres_kernel(const float4* __restrict__ pack,
                              const int* __restrict__ index_list, const int* __restrict__ count, float4* __restrict__ aos)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= __ldg(count)) return;
     const int i = __ldg(index_list + s);
     float2* e = reinterpret_cast<float2*>(aos + (size_t)i * 4 + 3);
-    *e = make_float2(__ldg(packB + s).w, __ldg(packA + s).w);      // extras[0] = rho, extras[1] = pressure
+    *e = make_float2(__ldg(pack + 2 * (size_t)s + 1).w, __ldg(pack + 2 * (size_t)s).w);      // extras[0] = rho, extras[1] = pressure
 }
 
 __global__ void __launch_bounds__(256)
-sph3_finalize_force_sorted_kernel(const float4* __restrict__ packA, const float4* __restrict__ packB,
+sph3_finalize_force_sorted_kernel(const float4* __restrict__ pack,
                                   const float4* __restrict__ forceS, const float4* __restrict__ pairP,
                                   const float2* __restrict__ pairV, const int* __restrict__ index_list, const int* __restrict__ count,
                                   float4* __restrict__ aos, const Sph3Const* __restrict__ cc, TexView tex)
@@ -955,7 +842,8 @@ sph3_finalize_force_sorted_kernel(const float4* __restrict__ packA, const float4
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= __ldg(count)) return;
     const Sph3Const c = *cc;
-    const float4 a = __ldg(packA + s), b = __ldg(packB + s), pp = __ldg(pairP + s);
+    const f4x2 ab = cwa_ldg256(pack + 2 * (size_t)s);
+    const float4 a = ab.a, b = ab.b, pp = __ldg(pairP + s);
     const float2 pv = __ldg(pairV + s);
     const float4 f = force_epilogue(c, tex, a.x, a.y, a.z, b.x, b.y, b.z, b.w, __ldg(forceS + s), pp.x, pp.y, pp.z, pp.w, pv.x, pv.y);
     aos[(size_t)__ldg(index_list + s) * 4 + 2] = f;
@@ -1154,34 +1042,30 @@ static int env_int(const char* name, int dflt, int lo, int hi)
     return v < lo ? lo : (v > hi ? hi : v);
 }
 
-// Tuning knobs of the neighbour kernels.  Defaults come from the environment (CWA_NB_CONFIG,
-// CWA_NB_CAP_D / _F / _R) the first time they are needed; cwa_set_tuning() overrides them at run time
-// (used by the parity tests to cover every kernel variant in one process).
-//   nb_config: (targets per CTA, lanes per target) of the "lanes" kernels -- 0: 128x4, 1: 128x2, 2: 64x4,
-//              3: 256x1, 4: 128x1, 5: 64x2, 6: 256x2 -- or the "rows" kernels (one thread per target):
-//              7: P = 128, 8: P = 64, 9: P = 256 (TMA-staged candidates + neighbour lists), 10 / 11 / 12: the same
-//              P with candidates read through L1 (no staging, no barriers)
-//   cap_d / cap_f / cap_r: staging budgets in slots (0 disables staging)
-constexpr int NB_CONFIG_DEFAULT = 1;
-constexpr int ROWS_CAP_MAX = 3072;
-constexpr int NBR_K = 32;                 // neighbour-list entries per target (self included); longer lists fall back to a grid scan
-constexpr int ROWS_CAP_DEFAULT = 1536;    // 24 KB of staged candidates per CTA
-struct NbTuning { int config = -1, cap_d = -1, cap_f = -1, cap_r = -1, fused_order = -1; };
+// Tuning knobs of the neighbour kernels.  Defaults come from the environment (CWA_NB_CONFIG, CWA_NB_CAP_D / _F,
+// CWA_FUSED_ORDER) the first time they are needed; cwa_set_tuning() overrides them at run time (used by the
+// parity tests to cover every kernel variant in one process).
+//   nb_config: 7 (default) = neighbour-list kernels, one thread per target, candidates through L1;
+//              0..6 = "lanes" kernels (targets per CTA x lanes per target: 0: 128x4, 1: 128x2, 2: 64x4, 3: 256x1,
+//              4: 128x1, 5: 64x2, 6: 256x2): neighbour rows staged in shared memory by TMA bulk copies, lanes of a
+//              target combined with warp shuffles, the force pass scans the candidates again
+//   cap_d / cap_f: staging budgets of the lanes kernels in slots (0 disables staging)
+constexpr int NB_CONFIG_DEFAULT = 7;
+constexpr int NBR_K = 64;                 // neighbour-list entries per target (self included); longer lists fall back to a grid scan
+struct NbTuning { int config = -1, cap_d = -1, cap_f = -1, fused_order = -1; };
 static NbTuning g_tune;
-static int nb_config() { if (g_tune.config < 0) g_tune.config = env_int("CWA_NB_CONFIG", NB_CONFIG_DEFAULT, 0, 12); return g_tune.config; }
+static int nb_config() { if (g_tune.config < 0) g_tune.config = env_int("CWA_NB_CONFIG", NB_CONFIG_DEFAULT, 0, 7); return g_tune.config; }
 static int dens_cap() { if (g_tune.cap_d < 0) g_tune.cap_d = env_int("CWA_NB_CAP_D", DENS_CAP_DEFAULT, 0, DENS_CAP_MAX); return g_tune.cap_d; }
 static int force_cap() { if (g_tune.cap_f < 0) g_tune.cap_f = env_int("CWA_NB_CAP_F", FORCE_CAP_DEFAULT, 0, FORCE_CAP_MAX); return g_tune.cap_f; }
 static bool fused_order() { if (g_tune.fused_order < 0) g_tune.fused_order = env_int("CWA_FUSED_ORDER", 1, 0, 1); return g_tune.fused_order != 0; }
-static int rows_cap() { if (g_tune.cap_r < 0) g_tune.cap_r = env_int("CWA_NB_CAP_R", ROWS_CAP_DEFAULT, 0, ROWS_CAP_MAX); return g_tune.cap_r; }
 
 extern "C" int cwa_set_tuning(cwa_ctx* ctx, const char* key, int value)
 {
     CWA_CHECK(ctx && key, "null argument");
     const std::string k(key);
-    if (k == "nb_config") { CWA_CHECK(value >= 0 && value <= 12, "nb_config %d out of range", value); g_tune.config = value; }
+    if (k == "nb_config") { CWA_CHECK(value >= 0 && value <= 7, "nb_config %d out of range", value); g_tune.config = value; }
     else if (k == "nb_cap_d") { CWA_CHECK(value >= 0 && value <= DENS_CAP_MAX, "nb_cap_d %d out of range", value); g_tune.cap_d = value; }
     else if (k == "nb_cap_f") { CWA_CHECK(value >= 0 && value <= FORCE_CAP_MAX, "nb_cap_f %d out of range", value); g_tune.cap_f = value; }
-    else if (k == "nb_cap_r") { CWA_CHECK(value >= 0 && value <= ROWS_CAP_MAX, "nb_cap_r %d out of range", value); g_tune.cap_r = value; }
     else if (k == "fused_order") { g_tune.fused_order = value ? 1 : 0; }
     else CWA_CHECK(false, "cwa_set_tuning: unknown key '%s'", key);
     return 0;
@@ -1197,7 +1081,7 @@ static int launch_density(cwa_ctx* ctx, SphObj* s, GridObj* g, TexView tex)
     }
     KScope k(ctx, KID_DENSITY);
     sph3_density_grid_kernel<P, L><<<ceil_div(s->n, P), P * L, dens_cap() * 16, ctx->stream>>>(
-        s->posS, s->velS, s->packA, s->packB, s->n, g->view, g->offset, (const Sph3Const*)s->consts, tex, dens_cap());
+        s->posS, s->velS, s->pack, s->n, g->view, g->offset, (const Sph3Const*)s->consts, tex, dens_cap());
     return 0;
 }
 
@@ -1211,60 +1095,34 @@ static int launch_force(cwa_ctx* ctx, SphObj* s, GridObj* g)
     }
     KScope k(ctx, KID_FORCE);
     sph3_force_grid_kernel<P, L><<<ceil_div(s->n, P), P * L, force_cap() * 32, ctx->stream>>>(
-        s->packA, s->packB, s->pairP, s->pairV, s->n, g->view, g->offset, (const Sph3Const*)s->consts, force_cap());
+        s->pack, s->pairP, s->pairV, s->n, g->view, g->offset, (const Sph3Const*)s->consts, force_cap());
     return 0;
 }
 
 // rows variant: one thread per target (CWA_NB_CONFIG 7: P = 128, 8: P = 64, 9: P = 256)
 
-// heavy-target kernels: a fixed grid of warps walks the device-side queue (no host round trip)
-static int heavy_grid(cwa_ctx* ctx) { return ctx->sm_count * 16; }
+// heavy kernels: a fixed grid of warps walks the device-side queue (no host round trip)
+static int heavy_grid(cwa_ctx* ctx) { return ctx->sm_count * 16; }     // x 4 warps: every resident warp slot of the GPU
 
-template <int P>
-static int launch_density_rows(cwa_ctx* ctx, SphObj* s, GridObj* g, TexView tex)
-{
-    static bool attr = false;
-    const int fixed = RT_ROWS * P * 8 + (NBR_K + 1) * P * 4;
-    if (!attr) {
-        CWA_CUDA(cudaFuncSetAttribute(sph3_density_rows_kernel<P, NBR_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, ROWS_CAP_MAX * 16 + fixed));
-        attr = true;
-    }
-    { KScope k(ctx, KID_DENSITY);
-      sph3_density_rows_kernel<P, NBR_K><<<ceil_div(s->n, P), P, rows_cap() * 16 + fixed, ctx->stream>>>(
-          s->posS, s->velS, s->packA, s->packB, s->nbr_list, s->nbr_count, s->heavy_queue, s->heavy_count, s->n,
-          g->view, g->offset, (const Sph3Const*)s->consts, tex, rows_cap()); }
-    { KScope k(ctx, KID_DENSITY_HEAVY);
-      sph3_density_heavy_kernel<NBR_K><<<heavy_grid(ctx), 128, 0, ctx->stream>>>(
-          s->posS, s->velS, s->packA, s->packB, s->nbr_count, s->heavy_queue, s->heavy_count,
-          g->view, g->offset, (const Sph3Const*)s->consts, tex); }
-    s->nbr_lists_valid = true;
-    return 0;
-}
-
-template <int P>
 static int launch_density_list(cwa_ctx* ctx, SphObj* s, GridObj* g, TexView tex)
 {
-    const int smem = RT_ROWS * P * 8 + (NBR_K + 1) * P * 4;
     const Sph3Const* cc = (const Sph3Const*)s->consts;
-    static bool attr = false;
-    if (!attr) {
-        CWA_CUDA(cudaFuncSetAttribute(sph3_density_list_kernel<P, NBR_K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CWA_CUDA(cudaFuncSetAttribute(sph3_density_list_kernel<P, NBR_K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr = true;
-    }
+    const int ntiles = ceil_div(s->n, TILE_P);
+    const bool local = tex_view_is_local(tex);
     { KScope k(ctx, KID_DENSITY);
-      if (tex_view_is_local(tex))
-          sph3_density_list_kernel<P, NBR_K, true><<<ceil_div(s->n, P), P, smem, ctx->stream>>>(
-              s->posS, s->velS, s->packA, s->packB, s->nbr_list, s->nbr_count, s->heavy_queue, s->heavy_count, s->n,
-              g->view, g->offset, cc, tex);
+      if (local)
+          sph3_density_list_kernel<NBR_K, true><<<ntiles, TILE_P, 0, ctx->stream>>>(
+              s->posS, s->velS, s->pack, s->nbr_list, s->nbr_count, s->heavy_queue, s->heavy_count, s->n, g->view, g->offset, cc, tex);
       else
-          sph3_density_list_kernel<P, NBR_K, false><<<ceil_div(s->n, P), P, smem, ctx->stream>>>(
-              s->posS, s->velS, s->packA, s->packB, s->nbr_list, s->nbr_count, s->heavy_queue, s->heavy_count, s->n,
-              g->view, g->offset, cc, tex); }
-    { KScope k(ctx, KID_DENSITY_HEAVY);
-      sph3_density_heavy_kernel<NBR_K><<<heavy_grid(ctx), 128, 0, ctx->stream>>>(
-          s->posS, s->velS, s->packA, s->packB, s->nbr_count, s->heavy_queue, s->heavy_count,
-          g->view, g->offset, cc, tex); }
+          sph3_density_list_kernel<NBR_K, false><<<ntiles, TILE_P, 0, ctx->stream>>>(
+              s->posS, s->velS, s->pack, s->nbr_list, s->nbr_count, s->heavy_queue, s->heavy_count, s->n, g->view, g->offset, cc, tex); }
+    { KScope k(ctx, KID_HEAVY);
+      if (local)
+          sph3_density_heavy_kernel<true><<<heavy_grid(ctx), 128, 0, ctx->stream>>>(
+              s->posS, s->velS, s->pack, s->nbr_count, s->heavy_queue, s->heavy_count, g->view, g->offset, cc, tex);
+      else
+          sph3_density_heavy_kernel<false><<<heavy_grid(ctx), 128, 0, ctx->stream>>>(
+              s->posS, s->velS, s->pack, s->nbr_count, s->heavy_queue, s->heavy_count, g->view, g->offset, cc, tex); }
     s->nbr_lists_valid = true;
     return 0;
 }
@@ -1273,12 +1131,12 @@ static int launch_force_list(cwa_ctx* ctx, SphObj* s, GridObj* g)
 {
     int* fq = s->heavy_queue + s->capacity;              // second half: the force pass's queue
     { KScope k(ctx, KID_FORCE);
-      sph3_force_list_kernel<NBR_K><<<ceil_div(s->n, 128), 128, 0, ctx->stream>>>(
-          s->packA, s->packB, s->nbr_list, s->nbr_count, fq, s->heavy_count + 1, s->pairP, s->pairV, s->n,
-          g->view, g->offset, (const Sph3Const*)s->consts); }
-    { KScope k(ctx, KID_FORCE_HEAVY);
+      sph3_force_list_kernel<NBR_K><<<ceil_div(s->n, TILE_P), TILE_P, 0, ctx->stream>>>(
+          s->pack, s->nbr_list, s->nbr_count, fq, s->heavy_count + 1, s->pairP, s->pairV, s->n, g->view, g->offset,
+          (const Sph3Const*)s->consts); }
+    { KScope k(ctx, KID_HEAVY);
       sph3_force_heavy_kernel<<<heavy_grid(ctx), 128, 0, ctx->stream>>>(
-          s->packA, s->packB, fq, s->heavy_count + 1, s->pairP, s->pairV, g->view, g->offset, (const Sph3Const*)s->consts); }
+          s->pack, fq, s->heavy_count + 1, s->pairP, s->pairV, g->view, g->offset, (const Sph3Const*)s->consts); }
     return 0;
 }
 
@@ -1313,8 +1171,8 @@ static int sph_prepare(cwa_ctx* ctx, SphObj* s)
     return 0;
 }
 
-static float2* sph_scratch_rp(SphObj* s) { return reinterpret_cast<float2*>(s->packA); }
-static float4* sph_scratch_force(SphObj* s) { return s->packB; }
+static float2* sph_scratch_rp(SphObj* s) { return reinterpret_cast<float2*>(s->scratch); }
+static float4* sph_scratch_force(SphObj* s) { return s->scratch; }
 
 // which: bit0 rho_pres, bit1 force, bit2 integrate.  In grid mode a full step (7) keeps every
 // intermediate in the cell-ordered snapshot and writes the SSBO once, at the end.
@@ -1364,17 +1222,12 @@ int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which)
         case 4: CWA_TRY((launch_density<128, 1>(ctx, s, g, tex))); break;
         case 5: CWA_TRY((launch_density<64, 2>(ctx, s, g, tex))); break;
         case 6: CWA_TRY((launch_density<256, 2>(ctx, s, g, tex))); break;
-        case 10: CWA_TRY((launch_density_list<128>(ctx, s, g, tex))); break;
-        case 11: CWA_TRY((launch_density_list<64>(ctx, s, g, tex))); break;
-        case 12: CWA_TRY((launch_density_list<256>(ctx, s, g, tex))); break;
-        case 7: CWA_TRY((launch_density_rows<128>(ctx, s, g, tex))); break;
-        case 8: CWA_TRY((launch_density_rows<64>(ctx, s, g, tex))); break;
-        case 9: CWA_TRY((launch_density_rows<256>(ctx, s, g, tex))); break;
+        case 7: CWA_TRY(launch_density_list(ctx, s, g, tex)); break;
         default: CWA_TRY((launch_density<128, 4>(ctx, s, g, tex))); break;
         }
         if (!full) {
             KScope k(ctx, KID_OTHER);
-            sph3_scatter_rho_pres_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(s->packA, s->packB, g->index_list, g->offset + g->view.num_cells, aos);
+            sph3_scatter_rho_pres_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(s->pack, g->index_list, g->offset + g->view.num_cells, aos);
         }
     }
     if (which & 2) {
@@ -1386,7 +1239,7 @@ int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which)
         case 4: CWA_TRY((launch_force<128, 1>(ctx, s, g))); break;
         case 5: CWA_TRY((launch_force<64, 2>(ctx, s, g))); break;
         case 6: CWA_TRY((launch_force<256, 2>(ctx, s, g))); break;
-        case 7: case 8: case 9: case 10: case 11: case 12:
+        case 7:
             CWA_CHECK(s->nbr_lists_valid, "force pass: the neighbour lists of the density pass are missing");
             CWA_TRY(launch_force_list(ctx, s, g)); break;
         default: CWA_TRY((launch_force<128, 4>(ctx, s, g))); break;
@@ -1395,7 +1248,7 @@ int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which)
         if (!full) {
             KScope k(ctx, KID_OTHER);
             sph3_finalize_force_sorted_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(
-                s->packA, s->packB, s->forceS, s->pairP, s->pairV, g->index_list, g->offset + g->view.num_cells, aos, cc, tex);
+                s->pack, s->forceS, s->pairP, s->pairV, g->index_list, g->offset + g->view.num_cells, aos, cc, tex);
         }
     }
     if (which & 4) {
@@ -1403,10 +1256,10 @@ int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which)
         if (full) {
             if (tex_view_is_local(tex))
                 sph3_finalize_integrate_sorted_kernel<true><<<ceil_div(n, 128), 128, 0, ctx->stream>>>(
-                    s->packA, s->packB, s->forceS, s->miscS, s->pairP, s->pairV, g->index_list, g->offset + g->view.num_cells, aos, cc, tex);
+                    s->pack, s->forceS, s->miscS, s->pairP, s->pairV, g->index_list, g->offset + g->view.num_cells, aos, cc, tex);
             else
                 sph3_finalize_integrate_sorted_kernel<false><<<ceil_div(n, 128), 128, 0, ctx->stream>>>(
-                    s->packA, s->packB, s->forceS, s->miscS, s->pairP, s->pairV, g->index_list, g->offset + g->view.num_cells, aos, cc, tex);
+                    s->pack, s->forceS, s->miscS, s->pairP, s->pairV, g->index_list, g->offset + g->view.num_cells, aos, cc, tex);
         } else {
             sph3_integrate_aos_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(aos, n, cc, tex);
         }
@@ -1433,8 +1286,8 @@ extern "C" int cwa_sph_create(cwa_ctx* ctx, cwa_buf particles, int n, cwa_grid g
     s.live = true; s.particles = particles; s.n = n; s.capacity = n; s.grid = grid;
     const size_t bytes = (size_t)(n > 0 ? n : 1) * 16 + 64;          // + 4 slots: the neighbour loops read up to 3 slots past a row
     CWA_CUDA(cudaMalloc(&s.consts, sizeof(Sph3Const)));
-    CWA_CUDA(cudaMalloc(&s.packA, bytes));
-    CWA_CUDA(cudaMalloc(&s.packB, bytes));
+    if (grid >= 0) CWA_CUDA(cudaMalloc(&s.pack, 2 * bytes));
+    else CWA_CUDA(cudaMalloc(&s.scratch, bytes));
     if (grid >= 0) {
         CWA_CUDA(cudaMalloc(&s.posS, bytes));
         CWA_CUDA(cudaMemsetAsync(s.posS, 0, bytes, ctx->stream));     // the 4 pad slots are read (and masked out) by the neighbour loops
@@ -1445,9 +1298,9 @@ extern "C" int cwa_sph_create(cwa_ctx* ctx, cwa_buf particles, int n, cwa_grid g
         CWA_CUDA(cudaMalloc(&s.pairV, bytes / 2));
         CWA_CUDA(cudaMalloc(&s.nbr_list, (size_t)(n > 0 ? n : 1) * NBR_K * 4));
         CWA_CUDA(cudaMalloc(&s.nbr_count, (size_t)(n > 0 ? n : 1) * 4));
-        CWA_CUDA(cudaMalloc(&s.heavy_queue, (size_t)(n > 0 ? n : 1) * 2 * 4));
         CWA_CUDA(cudaMalloc(&s.heavy_count, 2 * 4));
         CWA_CUDA(cudaMemsetAsync(s.heavy_count, 0, 8, ctx->stream));
+        CWA_CUDA(cudaMalloc(&s.heavy_queue, (size_t)(n > 0 ? n : 1) * 2 * 4));
     }
     ctx->sphs.push_back(s);
     *out = (int)ctx->sphs.size() - 1;
@@ -1459,8 +1312,8 @@ extern "C" int cwa_sph_destroy(cwa_ctx* ctx, cwa_sph h)
     SphObj* s = get_sph(ctx, h);
     CWA_CHECK(s, "invalid sph handle %d", h);
     CWA_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(s->packA); cudaFree(s->packB); cudaFree(s->posS); cudaFree(s->velS); cudaFree(s->forceS); cudaFree(s->miscS);
-    cudaFree(s->pairP); cudaFree(s->pairV); cudaFree(s->consts); cudaFree(s->nbr_list); cudaFree(s->nbr_count); cudaFree(s->heavy_queue); cudaFree(s->heavy_count);
+    cudaFree(s->pack); cudaFree(s->scratch); cudaFree(s->posS); cudaFree(s->velS); cudaFree(s->forceS); cudaFree(s->miscS);
+    cudaFree(s->pairP); cudaFree(s->pairV); cudaFree(s->consts); cudaFree(s->nbr_list); cudaFree(s->nbr_count); cudaFree(s->heavy_count); cudaFree(s->heavy_queue);
     s->live = false;
     if (ctx->bound_sph == h) ctx->bound_sph = -1;
     return 0;

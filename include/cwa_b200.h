@@ -92,7 +92,8 @@ CWA_API const char* cwa_profile_kernel_name(int id);
 CWA_API int  cwa_profile_begin(cwa_ctx* ctx);
 CWA_API int  cwa_profile_end(cwa_ctx* ctx, float* ms, int* launches, int cap);   /* synchronises */
 /* kernel-variant / staging knobs of the neighbour loops (no reference counterpart: the GLSL has one variant).
- * keys: "nb_config" (0..6 lanes kernels, 7..9 rows + neighbour-list kernels), "nb_cap_d", "nb_cap_f", "nb_cap_r" (staged slots),
+ * keys: "nb_config" (7: neighbour-list kernels, the default; 0..6: shared-memory-staged "lanes" kernels),
+ *       "nb_cap_d", "nb_cap_f" (staged slots of the lanes kernels),
  *       "fused_order" (1: canonical ordering fused into the reorder pass). */
 CWA_API int  cwa_set_tuning(cwa_ctx* ctx, const char* key, int value);
 
