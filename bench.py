@@ -402,6 +402,18 @@ def run_native_distributed(args, world, rank, local_rank, torch, dist, cwa):
             print(f"[debug rank {rank}] frame {fr + 1}: owned range {be.n_owned} live {q.size} ghosts {be.n_ghost} migrated_in {be.migrated_in} "
                   f"z [{np.nanmin(zz):.5f}, {np.nanmax(zz):.5f}] slab [{plan.z_lo:.5f}, {plan.z_hi:.5f}] vmax {np.nanmax(np.abs(q['vel'][:, :3])):.3f} "
                   f"nan {int(np.isnan(zz).sum())}", flush=True)
+    if os.environ.get("CWA_BENCH_TRACE"):
+        # diagnostic only: device time and per-kernel split of every 5th frame of the first 80
+        for fr in range(80):
+            if fr % 5 == 0:
+                ctx.profile_begin()
+                t0 = time.perf_counter(); drv.step(1, COUPLING); ctx.synchronize(); wall = time.perf_counter() - t0
+                pr = ctx.profile_end()
+                ksum = sum(v[0] for v in pr.values())
+                print(f"[trace rank {rank}] frame {fr}: wall {wall * 1e6:.0f} us, kernels {ksum * 1e3:.0f} us, owned {be.n_owned} ghosts {be.n_ghost} | "
+                      + ", ".join(f"{k} {v[0] * 1e3:.0f}" for k, v in sorted(pr.items(), key=lambda kv: -kv[1][0])[:6]), flush=True)
+            else:
+                drv.step(1, COUPLING)
     drv.step(W, COUPLING)
     ctx.synchronize()
     if os.environ.get("CWA_BENCH_PHASES"):
@@ -415,6 +427,11 @@ def run_native_distributed(args, world, rank, local_rank, torch, dist, cwa):
             drv._wave_halo_refresh(); be.bind_texture_unit(); ctx.synchronize(); t4 = time.perf_counter()
             acc["exchange"] += t1 - t0; acc["sph"] += t2 - t1; acc["wave"] += t3 - t2; acc["halo"] += t4 - t3
         print(f"[phases rank {rank}] " + ", ".join(f"{k} {v / nfr * 1e6:.0f} us" for k, v in acc.items()), flush=True)
+        ctx.profile_begin()
+        drv.step(10, COUPLING)
+        pr = ctx.profile_end()
+        print(f"[early kernels rank {rank}] owned {be.n_owned} ghosts {be.n_ghost} "
+              + ", ".join(f"{k} {v[0] / v[1] * 1e3:.0f}us x{v[1] // 10}" for k, v in sorted(pr.items(), key=lambda kv: -kv[1][0])[:14]), flush=True)
     if rank == 0:
         sampler.start()
     dist.barrier(); ctx.synchronize()
@@ -441,7 +458,7 @@ def run_native_distributed(args, world, rank, local_rank, torch, dist, cwa):
         q = be.download_owned()
         cnt = be.grid.read(cwa.GRID_COUNTER, be.grid.num_cells_total)
         print(f"[kernels rank {rank}] owned {q.size} ghosts {be.n_ghost} max/cell {int(cnt.max())} cells>64: {int((cnt > 64).sum())} "
-              + ", ".join(f"{k} {v[0] / v[1] * 1e3:.0f}us" for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:6]), flush=True)
+              + ", ".join(f"{k} {v[0] / v[1] * 1e3:.0f}us" for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:14]), flush=True)
 
     # end to end: every rank's particle slab and wave rows live in pinned HOST buffers between steps
     import ctypes as C

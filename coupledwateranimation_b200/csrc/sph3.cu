@@ -1031,7 +1031,7 @@ sph3_init_cube_kernel(float4* __restrict__ aos, int nx, int ny, int nz, ParamPtr
 // ---------------------------------------------------------------------------------------------
 constexpr int DENS_CAP_MAX = 3072;        // staged slots (16 B each): at most 48 KB
 constexpr int FORCE_CAP_MAX = 2048;       // staged slots (32 B each): at most 64 KB
-constexpr int DENS_CAP_DEFAULT = 2048;    // 32 KB/CTA: measured best occupancy/staging trade-off on C4 (profiles/r1_tuning.md)
+constexpr int DENS_CAP_DEFAULT = 2048;    // 32 KB/CTA: measured best occupancy/staging trade-off of the lanes kernels on C4 (profiles/r1/tuning.md)
 constexpr int FORCE_CAP_DEFAULT = 1536;   // 48 KB/CTA
 
 static int env_int(const char* name, int dflt, int lo, int hi)
