@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcwa_b200.so")
+LIB_PATH = os.environ.get("CWA_LIB_PATH") or os.path.join(HERE, "libcwa_b200.so")   # CWA_LIB_PATH: another build of the same library (tuning runs)
 
 
 class CwaError(RuntimeError):

@@ -274,6 +274,7 @@ extern "C" int cwa_buffer_sub_data(cwa_ctx* ctx, cwa_buf b, size_t off, size_t b
     CWA_CUDA(cudaMemcpyAsync((char*)o->ptr + off, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     // a particle upload invalidates any cell-ordered snapshot built from this buffer
     for (auto& s : ctx->sphs) if (s.live && s.particles == b) s.snapshot_valid = false;
+    for (int i = 0; i < 8; i++) if (ctx->ubo_binding[i] == b) ctx->params_epoch++;      // a parameter block changed
     return 0;
 }
 
@@ -294,6 +295,7 @@ extern "C" int cwa_buffer_copy(cwa_ctx* ctx, cwa_buf src, cwa_buf dst, size_t so
     CWA_CHECK(s && d, "invalid buffer handle");
     CWA_CHECK(soff + bytes <= s->bytes && doff + bytes <= d->bytes, "cwa_buffer_copy: range outside buffer");
     CWA_CUDA(cudaMemcpyAsync((char*)d->ptr + doff, (const char*)s->ptr + soff, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    for (int i = 0; i < 8; i++) if (ctx->ubo_binding[i] == dst) ctx->params_epoch++;
     return 0;
 }
 
@@ -307,6 +309,7 @@ extern "C" int cwa_buffer_bind_base(cwa_ctx* ctx, int target, int binding, cwa_b
     } else if (target == CWA_TARGET_UBO) {
         CWA_CHECK(binding >= 0 && binding < 8, "UBO binding %d out of range", binding);
         ctx->ubo_binding[binding] = (b == -1) ? ctx->default_ubo[binding] : b;
+        ctx->params_epoch++;
     } else {
         CWA_CHECK(false, "unknown buffer target %d", target);
     }

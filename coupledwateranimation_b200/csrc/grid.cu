@@ -57,7 +57,10 @@ grid_hash_count_kernel(const char* __restrict__ particles, int stride_bytes, int
 // ---------------------------------------------------------------------------------------------
 // (2) decoupled look-back exclusive scan (single pass, any n)
 // ---------------------------------------------------------------------------------------------
-constexpr int SCAN_THREADS = 256;
+#ifndef CWA_SCAN_THREADS
+#define CWA_SCAN_THREADS 256
+#endif
+constexpr int SCAN_THREADS = CWA_SCAN_THREADS;
 constexpr int SCAN_ITEMS = 16;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;   // 4096 ints per tile
 
@@ -324,7 +327,7 @@ extern "C" int cwa_grid_create(cwa_ctx* ctx, int dim, const float* mn, const flo
     g.view.dim = dim; g.view.num_cells = (int)C; g.view.kstride = kstride;
 
     const size_t tiles = scan_num_tiles((int)C);
-    // [counter C ints (padded to 8 B)][ticket 2 ints][tile_state tiles x 8 B]
+    // [counter C ints (padded to 16 B)][4 ints: scan ticket, -, queue counters of the heavy SPH kernels][tile_state tiles x 8 B]
     const size_t counter_bytes = (((size_t)C * 4 + 15) / 16) * 16;
     g.clear_bytes = counter_bytes + 16 + tiles * 8;
     char* blk = nullptr;

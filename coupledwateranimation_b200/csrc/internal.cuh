@@ -142,7 +142,9 @@ struct SphObj {
     float2 *pairV = nullptr;                     //                                   (visc.y, visc.z)
     int   *nbr_list = nullptr, *nbr_count = nullptr;   // neighbour lists of the density pass ([slot][K]) and true counts
     bool   nbr_lists_valid = false;
-    int   *heavy_queue = nullptr, *heavy_count = nullptr;   // targets finished one warp each: [0,cap) density pass, [cap,2cap) force pass; two counters
+    int   *heavy_queue = nullptr;                           // targets finished one warp each: [0,cap) density pass, [cap,2cap) force pass;
+                                                            // the two counters live in the grid's clear block (ticket + 2, + 3)
+    unsigned long long consts_epoch = 0;                    // params_epoch the prepared constants were derived from
     void*  consts = nullptr;                     // Sph3Const prepared on the device once per dispatch
     bool snapshot_valid = false;
     bool pair_sums_valid = false;
@@ -190,6 +192,7 @@ struct cwa_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
     unsigned long long launches = 0;
+    unsigned long long params_epoch = 1;   // bumped whenever a parameter block may have changed (UBO write / bind)
     std::vector<BufferObj> buffers;
     std::vector<GridObj>   grids;
     std::vector<WaveObj>   waves;

@@ -106,12 +106,9 @@ __device__ __forceinline__ Sph3Const load_consts(const ParamPtrs& prm)
     return c;
 }
 
-__global__ void sph3_prepare_kernel(ParamPtrs prm, Sph3Const* __restrict__ out, int* __restrict__ heavy_count)
+__global__ void sph3_prepare_kernel(ParamPtrs prm, Sph3Const* __restrict__ out)
 {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        *out = load_consts(prm);
-        if (heavy_count) { heavy_count[0] = heavy_count[1] = 0; }     // queues of the heavy kernels (density pass, force pass)
-    }
+    if (threadIdx.x == 0 && blockIdx.x == 0) *out = load_consts(prm);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -602,8 +599,9 @@ sph3_density_list_kernel(const float4* __restrict__ posS, const float4* __restri
     const float4 p = __ldg(posS + slot);
     const Query3 q = list_query(g, p.x, p.y, p.z, h);
     const RowBounds rb = rows_load(g, offset, q);
-    if (rb.total > EXTREME_CANDIDATES) {               // a big clump: finished by sph3_density_heavy_kernel, one CTA per target
-        heavy_queue[atomicAdd(heavy_count, 1)] = slot;
+    if (rb.total > EXTREME_CANDIDATES) {               // a big clump: finished by sph3_density_heavy_kernel, one warp per target
+        const int qi = atomicAdd(heavy_count, 1);
+        if (qi < n_max) heavy_queue[qi] = slot;
         return;
     }
 #pragma unroll
@@ -663,12 +661,12 @@ sph3_density_list_kernel(const float4* __restrict__ posS, const float4* __restri
 template <bool LOCAL>
 __global__ void __launch_bounds__(128)
 sph3_density_heavy_kernel(const float4* __restrict__ posS, const float4* __restrict__ velS, float4* __restrict__ pack,
-                          int* __restrict__ nbr_count, const int* __restrict__ heavy_queue, const int* __restrict__ heavy_count,
+                          int* __restrict__ nbr_count, const int* __restrict__ heavy_queue, const int* __restrict__ heavy_count, int cap,
                           GridView g, const int* __restrict__ offset, const Sph3Const* __restrict__ cc, TexView tex)
 {
     const int lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int total = __ldg(heavy_count);
+    const int total = min(__ldg(heavy_count), cap);
     const float h = cc->h, accept_r2 = cc->accept_r2, h2 = cc->h2, poly6 = cc->poly6;
     for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < total; e += nwarps) {
         const int slot = __ldg(heavy_queue + e);
@@ -722,7 +720,11 @@ sph3_force_list_kernel(const float4* __restrict__ pack, const int* __restrict__ 
     const int n = min(n_max, __ldg(offset + g.num_cells));   // inserted particles
     if (slot >= n) return;
     const int cnt = __ldg(nbr_count + slot);
-    if (cnt > K) { heavy_queue[atomicAdd(heavy_count, 1)] = slot; return; }       // list overflow / extreme target: sph3_force_heavy_kernel
+    if (cnt > K) {                                     // list overflow / extreme target: sph3_force_heavy_kernel
+        const int qi = atomicAdd(heavy_count, 1);
+        if (qi < n_max) heavy_queue[qi] = slot;     // (a pass dispatched twice without a grid build in between re-queues: same results)
+        return;
+    }
     const Sph3Const c = *cc;
     const f4x2 own = cwa_ldg256(pack + 2 * (size_t)slot);
     const float4 pa = own.a, pb = own.b;
@@ -749,13 +751,13 @@ sph3_force_list_kernel(const float4* __restrict__ pack, const int* __restrict__ 
 // Queued targets of the force pass (list overflow, clumps): one WARP per target re-scans the grid; lanes 0..8 fetch the row bounds in
 // parallel, lane l takes every 32nd candidate of a row, the six sums are combined with warp shuffles.
 __global__ void __launch_bounds__(128)
-sph3_force_heavy_kernel(const float4* __restrict__ pack, const int* __restrict__ heavy_queue, const int* __restrict__ heavy_count,
+sph3_force_heavy_kernel(const float4* __restrict__ pack, const int* __restrict__ heavy_queue, const int* __restrict__ heavy_count, int cap,
                         float4* __restrict__ pairP, float2* __restrict__ pairV, GridView g,
                         const int* __restrict__ offset, const Sph3Const* __restrict__ cc)
 {
     const int lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int total = __ldg(heavy_count);
+    const int total = min(__ldg(heavy_count), cap);
     const Sph3Const c = *cc;
     for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < total; e += nwarps) {
         const int slot = __ldg(heavy_queue + e);
@@ -1109,20 +1111,21 @@ static int launch_density_list(cwa_ctx* ctx, SphObj* s, GridObj* g, TexView tex)
     const Sph3Const* cc = (const Sph3Const*)s->consts;
     const int ntiles = ceil_div(s->n, TILE_P);
     const bool local = tex_view_is_local(tex);
+    int* const hc = g->ticket + 2;                       // queue counter, zeroed by the grid build's memset
     { KScope k(ctx, KID_DENSITY);
       if (local)
           sph3_density_list_kernel<NBR_K, true><<<ntiles, TILE_P, 0, ctx->stream>>>(
-              s->posS, s->velS, s->pack, s->nbr_list, s->nbr_count, s->heavy_queue, s->heavy_count, s->n, g->view, g->offset, cc, tex);
+              s->posS, s->velS, s->pack, s->nbr_list, s->nbr_count, s->heavy_queue, hc, s->n, g->view, g->offset, cc, tex);
       else
           sph3_density_list_kernel<NBR_K, false><<<ntiles, TILE_P, 0, ctx->stream>>>(
-              s->posS, s->velS, s->pack, s->nbr_list, s->nbr_count, s->heavy_queue, s->heavy_count, s->n, g->view, g->offset, cc, tex); }
+              s->posS, s->velS, s->pack, s->nbr_list, s->nbr_count, s->heavy_queue, hc, s->n, g->view, g->offset, cc, tex); }
     { KScope k(ctx, KID_HEAVY);
       if (local)
           sph3_density_heavy_kernel<true><<<heavy_grid(ctx), 128, 0, ctx->stream>>>(
-              s->posS, s->velS, s->pack, s->nbr_count, s->heavy_queue, s->heavy_count, g->view, g->offset, cc, tex);
+              s->posS, s->velS, s->pack, s->nbr_count, s->heavy_queue, hc, s->n, g->view, g->offset, cc, tex);
       else
           sph3_density_heavy_kernel<false><<<heavy_grid(ctx), 128, 0, ctx->stream>>>(
-              s->posS, s->velS, s->pack, s->nbr_count, s->heavy_queue, s->heavy_count, g->view, g->offset, cc, tex); }
+              s->posS, s->velS, s->pack, s->nbr_count, s->heavy_queue, hc, s->n, g->view, g->offset, cc, tex); }
     s->nbr_lists_valid = true;
     return 0;
 }
@@ -1132,11 +1135,11 @@ static int launch_force_list(cwa_ctx* ctx, SphObj* s, GridObj* g)
     int* fq = s->heavy_queue + s->capacity;              // second half: the force pass's queue
     { KScope k(ctx, KID_FORCE);
       sph3_force_list_kernel<NBR_K><<<ceil_div(s->n, TILE_P), TILE_P, 0, ctx->stream>>>(
-          s->pack, s->nbr_list, s->nbr_count, fq, s->heavy_count + 1, s->pairP, s->pairV, s->n, g->view, g->offset,
+          s->pack, s->nbr_list, s->nbr_count, fq, g->ticket + 3, s->pairP, s->pairV, s->n, g->view, g->offset,
           (const Sph3Const*)s->consts); }
     { KScope k(ctx, KID_HEAVY);
       sph3_force_heavy_kernel<<<heavy_grid(ctx), 128, 0, ctx->stream>>>(
-          s->pack, fq, s->heavy_count + 1, s->pairP, s->pairV, g->view, g->offset, (const Sph3Const*)s->consts); }
+          s->pack, fq, g->ticket + 3, s->n, s->pairP, s->pairV, g->view, g->offset, (const Sph3Const*)s->consts); }
     return 0;
 }
 
@@ -1164,10 +1167,20 @@ static int sph_snapshot(cwa_ctx* ctx, SphObj* s)
     return 0;
 }
 
+// Derived constants are recomputed only when a parameter block may have changed: every library call that writes or
+// rebinds a UBO bumps ctx->params_epoch.  A block that lives in wrapped (application-owned) memory can change behind
+// the library's back, so it is re-read every time.
 static int sph_prepare(cwa_ctx* ctx, SphObj* s)
 {
+    bool external = false;
+    for (int i = 1; i <= 4; i++) {
+        BufferObj* o = get_buffer(ctx, ctx->ubo_binding[i]);
+        if (o && !o->owned) external = true;
+    }
+    if (!external && s->consts_epoch == ctx->params_epoch) return 0;
     KScope k(ctx, KID_OTHER);
-    sph3_prepare_kernel<<<1, 32, 0, ctx->stream>>>(current_params(ctx), (Sph3Const*)s->consts, s->heavy_count);
+    sph3_prepare_kernel<<<1, 32, 0, ctx->stream>>>(current_params(ctx), (Sph3Const*)s->consts);
+    s->consts_epoch = ctx->params_epoch;
     return 0;
 }
 
@@ -1298,8 +1311,6 @@ extern "C" int cwa_sph_create(cwa_ctx* ctx, cwa_buf particles, int n, cwa_grid g
         CWA_CUDA(cudaMalloc(&s.pairV, bytes / 2));
         CWA_CUDA(cudaMalloc(&s.nbr_list, (size_t)(n > 0 ? n : 1) * NBR_K * 4));
         CWA_CUDA(cudaMalloc(&s.nbr_count, (size_t)(n > 0 ? n : 1) * 4));
-        CWA_CUDA(cudaMalloc(&s.heavy_count, 2 * 4));
-        CWA_CUDA(cudaMemsetAsync(s.heavy_count, 0, 8, ctx->stream));
         CWA_CUDA(cudaMalloc(&s.heavy_queue, (size_t)(n > 0 ? n : 1) * 2 * 4));
     }
     ctx->sphs.push_back(s);
@@ -1313,7 +1324,7 @@ extern "C" int cwa_sph_destroy(cwa_ctx* ctx, cwa_sph h)
     CWA_CHECK(s, "invalid sph handle %d", h);
     CWA_CUDA(cudaStreamSynchronize(ctx->stream));
     cudaFree(s->pack); cudaFree(s->scratch); cudaFree(s->posS); cudaFree(s->velS); cudaFree(s->forceS); cudaFree(s->miscS);
-    cudaFree(s->pairP); cudaFree(s->pairV); cudaFree(s->consts); cudaFree(s->nbr_list); cudaFree(s->nbr_count); cudaFree(s->heavy_count); cudaFree(s->heavy_queue);
+    cudaFree(s->pairP); cudaFree(s->pairV); cudaFree(s->consts); cudaFree(s->nbr_list); cudaFree(s->nbr_count); cudaFree(s->heavy_queue);
     s->live = false;
     if (ctx->bound_sph == h) ctx->bound_sph = -1;
     return 0;

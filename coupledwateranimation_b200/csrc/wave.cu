@@ -14,11 +14,25 @@
 #include <cudaTypedefs.h>
 
 constexpr int WT_W = 128;               // tile width  (cells)
-constexpr int WT_H = 16;                // tile height (cells)
+#ifndef CWA_WT_H
+#define CWA_WT_H 16
+#endif
+#ifndef CWA_WT_STAGES
+#define CWA_WT_STAGES 3
+#endif
+#ifndef CWA_WT_THREADS
+#define CWA_WT_THREADS 128
+#endif
+#ifndef CWA_WT_CTAS_PER_SM
+#define CWA_WT_CTAS_PER_SM 4
+#endif
+constexpr int WT_H = CWA_WT_H;          // tile height (cells)
 constexpr int WT_HALO_W = WT_W + 8;     // halo box: 4 cells of left pad keep float4 alignment
 constexpr int WT_HALO_H = WT_H + 2;
-constexpr int WT_STAGES = 3;
-constexpr int WT_THREADS = 128;
+constexpr int WT_STAGES = CWA_WT_STAGES;
+constexpr int WT_THREADS = CWA_WT_THREADS;
+constexpr int WT_WARPS = WT_THREADS / 32;
+static_assert(WT_H % WT_WARPS == 0, "tile rows must divide evenly among the warps");
 constexpr int WT_HALO_BYTES = WT_HALO_W * WT_HALO_H * 4;                 // 9792
 constexpr int WT_HALO_BYTES_PAD = ((WT_HALO_BYTES + 127) / 128) * 128;   // 9856
 constexpr int WT_CORE_BYTES = WT_W * WT_H * 4;                           // 8192
@@ -137,8 +151,8 @@ wave_evolve_tma_kernel(const __grid_constant__ CUtensorMap tm_halo,   // u^{t-1}
 
         const int gx = x0 + 4 * lane;
 #pragma unroll
-        for (int rr = 0; rr < WT_H / 4; rr++) {
-            const int r = warp + 4 * rr;
+        for (int rr = 0; rr < WT_H / WT_WARPS; rr++) {
+            const int r = warp + WT_WARPS * rr;
             const int gy = y0 + r;
             if (gy < H && gx < W) {
                 const int hr = r + 1;
@@ -335,7 +349,7 @@ int wave_dispatch_mode(cwa_ctx* ctx, WaveObj* w, int mode)
             }
             const int tiles_x = ceil_div(w->w, WT_W), tiles_y = ceil_div(w->h, WT_H);
             const int num_tiles = tiles_x * tiles_y;
-            int grid = ctx->sm_count * 4;
+            int grid = ctx->sm_count * CWA_WT_CTAS_PER_SM;
             if (grid > num_tiles) grid = num_tiles;
             wave_evolve_tma_kernel<<<grid, WT_THREADS, WT_SMEM_BYTES, ctx->stream>>>(
                 w->tmap_halo[in0], w->tmap_core[in1], w->image[outi], w->w, w->h, attr, w->variant, tiles_x, num_tiles);

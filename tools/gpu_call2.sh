@@ -1,4 +1,4 @@
-mkdir -p gpurun_out/r1u
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r1u/pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r1u/pytest.log
-tail -4 gpurun_out/r1u/pytest.log
-python tools/state_evolution.py 10 60 200 1000 3000 5000 > gpurun_out/r1u/state_evolution.log 2>&1; cat gpurun_out/r1u/state_evolution.log
+mkdir -p gpurun_out/r1z
+echo "[default h16 t128 s3 c4]"; python tools/wave_bench.py
+for v in build/variants/wave_*.so; do echo "[$v]"; CWA_LIB_PATH=/root/repo/$v python tools/wave_bench.py; done
+timeout 300 python -m pytest tests/test_gpu_wave.py -m gpu -x -q 2>&1 | tail -2
