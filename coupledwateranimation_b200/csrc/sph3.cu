@@ -705,16 +705,41 @@ sph3_density_heavy_kernel(const float4* __restrict__ posS, const float4* __restr
     }
 }
 
+// Arguments of the fused tail of a full step (force epilogue + integrate + write-back of the 64-byte record): when
+// sph_step runs all three passes the force kernels finish the particle themselves, so the neighbour sums never
+// travel through memory and the separate integrate kernel (and its re-read of the pack) disappears.
+struct FinishArgs {
+    const float4* forceS;        // previous frame's force (torque term, crest rule)
+    const float4* miscS;         // (pos.w, vel.w, extras.z, extras.w): carried through unchanged
+    const int*    index_list;    // cell-ordered slot -> particle id
+    float4*       aos;           // the particle SSBO
+    TexView       tex;
+};
+
+template <bool LOCAL>
+__device__ __forceinline__ void finish_particle(const Sph3Const& c, const FinishArgs& fa, int slot, const float4 pa, const float4 pb,
+                                                float fpx, float fpy, float fpz, float fvx, float fvy, float fvz)
+{
+    const float4 m = __ldg(fa.miscS + slot);
+    float4 f = force_epilogue<LOCAL>(c, fa.tex, pa.x, pa.y, pa.z, pb.x, pb.y, pb.z, pb.w, __ldg(fa.forceS + slot), fpx, fpy, fpz, fvx, fvy, fvz);
+    float4 pos = make_float4(pa.x, pa.y, pa.z, m.x), vel = make_float4(pb.x, pb.y, pb.z, m.y);
+    float rho = pb.w, prs = pa.w;
+    integrate_particle<LOCAL>(c, fa.tex, pos, vel, f, rho, prs);
+    float4* o = fa.aos + (size_t)__ldg(fa.index_list + slot) * 4;
+    cwa_stg256(o, pos, vel);
+    cwa_stg256(o + 2, f, make_float4(rho, prs, m.z, m.w));
+}
+
 // Force pass over the neighbour lists of the density pass: neighbour sums of force_comp.glsl:74-88.  One thread
 // per target, no shared memory; a neighbour's (pos, p | vel, rho) record is one sector fetched with one 256-bit
 // load, and consecutive cell-ordered targets share most of their neighbours, so the gathers hit L1/L2.  A target
 // whose list overflowed (more than K neighbours) or that the density pass marked extreme is queued for the heavy kernel.
-template <int K>
+template <int K, bool FUSED, bool LOCAL>
 __global__ void __launch_bounds__(TILE_P, 6)
 sph3_force_list_kernel(const float4* __restrict__ pack, const int* __restrict__ nbr_list, const int* __restrict__ nbr_count,
                        int* __restrict__ heavy_queue, int* __restrict__ heavy_count,
                        float4* __restrict__ pairP, float2* __restrict__ pairV, int n_max,
-                       GridView g, const int* __restrict__ offset, const Sph3Const* __restrict__ cc)
+                       GridView g, const int* __restrict__ offset, const Sph3Const* __restrict__ cc, FinishArgs fa)
 {
     const int slot = blockIdx.x * TILE_P + threadIdx.x;
     const int n = min(n_max, __ldg(offset + g.num_cells));   // inserted particles
@@ -744,21 +769,32 @@ sph3_force_list_kernel(const float4* __restrict__ pack, const int* __restrict__ 
         for (int u = 0; u < 4; u++)
             if (j[u] != slot) pair_force(c, pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, qa[u], qb[u], fpx, fpy, fpz, fvx, fvy, fvz);
     }
-    pairP[slot] = make_float4(fpx, fpy, fpz, fvx);
-    pairV[slot] = make_float2(fvy, fvz);
+    if (FUSED) {
+        finish_particle<LOCAL>(c, fa, slot, pa, pb, fpx, fpy, fpz, fvx, fvy, fvz);
+    } else {
+        pairP[slot] = make_float4(fpx, fpy, fpz, fvx);
+        pairV[slot] = make_float2(fvy, fvz);
+    }
 }
 
 // Queued targets of the force pass (list overflow, clumps): one WARP per target re-scans the grid; lanes 0..8 fetch the row bounds in
 // parallel, lane l takes every 32nd candidate of a row, the six sums are combined with warp shuffles.
+template <bool FUSED, bool LOCAL>
 __global__ void __launch_bounds__(128)
 sph3_force_heavy_kernel(const float4* __restrict__ pack, const int* __restrict__ heavy_queue, const int* __restrict__ heavy_count, int cap,
                         float4* __restrict__ pairP, float2* __restrict__ pairV, GridView g,
-                        const int* __restrict__ offset, const Sph3Const* __restrict__ cc)
+                        const int* __restrict__ offset, const Sph3Const* __restrict__ cc, FinishArgs fa)
 {
     const int lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int total = min(__ldg(heavy_count), cap);
     const Sph3Const c = *cc;
+    // fused tail: lane k keeps the result of the warp's k-th target, and the (up to 32) kept targets are finished by
+    // all lanes at once -- the per-particle epilogue is as long as a short neighbour scan, one lane at a time would
+    // leave the warp 31/32 idle when many targets are queued
+    int kept = 0, k_slot = 0;
+    float4 k_pa = make_float4(0.f, 0.f, 0.f, 0.f), k_pb = k_pa;
+    float k0 = 0.f, k1 = 0.f, k2 = 0.f, k3 = 0.f, k4 = 0.f, k5 = 0.f;
     for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < total; e += nwarps) {
         const int slot = __ldg(heavy_queue + e);
         const f4x2 own = cwa_ldg256(pack + 2 * (size_t)slot);
@@ -791,11 +827,20 @@ sph3_force_heavy_kernel(const float4* __restrict__ pack, const int* __restrict__
             s2 += __shfl_xor_sync(0xffffffffu, s2, d); s3 += __shfl_xor_sync(0xffffffffu, s3, d);
             s4 += __shfl_xor_sync(0xffffffffu, s4, d); s5 += __shfl_xor_sync(0xffffffffu, s5, d);
         }
-        if (lane == 0) {
-            pairP[slot] = make_float4(s0, s1, s2, s3);
-            pairV[slot] = make_float2(s4, s5);
+        if (!FUSED) {
+            if (lane == 0) {
+                pairP[slot] = make_float4(s0, s1, s2, s3);
+                pairV[slot] = make_float2(s4, s5);
+            }
+        } else {
+            if (lane == kept) { k_slot = slot; k_pa = pa; k_pb = pb; k0 = s0; k1 = s1; k2 = s2; k3 = s3; k4 = s4; k5 = s5; }
+            if (++kept == 32) {
+                finish_particle<LOCAL>(c, fa, k_slot, k_pa, k_pb, k0, k1, k2, k3, k4, k5);
+                kept = 0;
+            }
         }
     }
+    if (FUSED && lane < kept) finish_particle<LOCAL>(c, fa, k_slot, k_pa, k_pb, k0, k1, k2, k3, k4, k5);
 }
 
 // force epilogue + integrate on the cell-ordered snapshot; one thread per particle writes the full
@@ -1054,11 +1099,12 @@ static int env_int(const char* name, int dflt, int lo, int hi)
 //   cap_d / cap_f: staging budgets of the lanes kernels in slots (0 disables staging)
 constexpr int NB_CONFIG_DEFAULT = 7;
 constexpr int NBR_K = 64;                 // neighbour-list entries per target (self included); longer lists fall back to a grid scan
-struct NbTuning { int config = -1, cap_d = -1, cap_f = -1, fused_order = -1; };
+struct NbTuning { int config = -1, cap_d = -1, cap_f = -1, fused_order = -1, fused_integrate = -1; };
 static NbTuning g_tune;
 static int nb_config() { if (g_tune.config < 0) g_tune.config = env_int("CWA_NB_CONFIG", NB_CONFIG_DEFAULT, 0, 7); return g_tune.config; }
 static int dens_cap() { if (g_tune.cap_d < 0) g_tune.cap_d = env_int("CWA_NB_CAP_D", DENS_CAP_DEFAULT, 0, DENS_CAP_MAX); return g_tune.cap_d; }
 static int force_cap() { if (g_tune.cap_f < 0) g_tune.cap_f = env_int("CWA_NB_CAP_F", FORCE_CAP_DEFAULT, 0, FORCE_CAP_MAX); return g_tune.cap_f; }
+static bool fused_integrate() { if (g_tune.fused_integrate < 0) g_tune.fused_integrate = env_int("CWA_FUSED_INTEGRATE", 0, 0, 1); return g_tune.fused_integrate != 0; }
 static bool fused_order() { if (g_tune.fused_order < 0) g_tune.fused_order = env_int("CWA_FUSED_ORDER", 1, 0, 1); return g_tune.fused_order != 0; }
 
 extern "C" int cwa_set_tuning(cwa_ctx* ctx, const char* key, int value)
@@ -1069,6 +1115,7 @@ extern "C" int cwa_set_tuning(cwa_ctx* ctx, const char* key, int value)
     else if (k == "nb_cap_d") { CWA_CHECK(value >= 0 && value <= DENS_CAP_MAX, "nb_cap_d %d out of range", value); g_tune.cap_d = value; }
     else if (k == "nb_cap_f") { CWA_CHECK(value >= 0 && value <= FORCE_CAP_MAX, "nb_cap_f %d out of range", value); g_tune.cap_f = value; }
     else if (k == "fused_order") { g_tune.fused_order = value ? 1 : 0; }
+    else if (k == "fused_integrate") { g_tune.fused_integrate = value ? 1 : 0; }
     else CWA_CHECK(false, "cwa_set_tuning: unknown key '%s'", key);
     return 0;
 }
@@ -1130,16 +1177,24 @@ static int launch_density_list(cwa_ctx* ctx, SphObj* s, GridObj* g, TexView tex)
     return 0;
 }
 
-static int launch_force_list(cwa_ctx* ctx, SphObj* s, GridObj* g)
+// fused = true: full step, the force kernels also run the force epilogue + integrate and write the SSBO records
+static int launch_force_list(cwa_ctx* ctx, SphObj* s, GridObj* g, bool fused, float4* aos, TexView tex)
 {
     int* fq = s->heavy_queue + s->capacity;              // second half: the force pass's queue
+    const Sph3Const* cc = (const Sph3Const*)s->consts;
+    const FinishArgs fa{s->forceS, s->miscS, g->index_list, aos, tex};
+    const int blocks = ceil_div(s->n, TILE_P);
+    const bool local = tex_view_is_local(tex);
+#define CWA_FORCE_LIST(F, L) sph3_force_list_kernel<NBR_K, F, L><<<blocks, TILE_P, 0, ctx->stream>>>( \
+        s->pack, s->nbr_list, s->nbr_count, fq, g->ticket + 3, s->pairP, s->pairV, s->n, g->view, g->offset, cc, fa)
+#define CWA_FORCE_HEAVY(F, L) sph3_force_heavy_kernel<F, L><<<heavy_grid(ctx), 128, 0, ctx->stream>>>( \
+        s->pack, fq, g->ticket + 3, s->n, s->pairP, s->pairV, g->view, g->offset, cc, fa)
     { KScope k(ctx, KID_FORCE);
-      sph3_force_list_kernel<NBR_K><<<ceil_div(s->n, TILE_P), TILE_P, 0, ctx->stream>>>(
-          s->pack, s->nbr_list, s->nbr_count, fq, g->ticket + 3, s->pairP, s->pairV, s->n, g->view, g->offset,
-          (const Sph3Const*)s->consts); }
+      if (!fused) CWA_FORCE_LIST(false, false); else if (local) CWA_FORCE_LIST(true, true); else CWA_FORCE_LIST(true, false); }
     { KScope k(ctx, KID_HEAVY);
-      sph3_force_heavy_kernel<<<heavy_grid(ctx), 128, 0, ctx->stream>>>(
-          s->pack, fq, g->ticket + 3, s->n, s->pairP, s->pairV, g->view, g->offset, (const Sph3Const*)s->consts); }
+      if (!fused) CWA_FORCE_HEAVY(false, false); else if (local) CWA_FORCE_HEAVY(true, true); else CWA_FORCE_HEAVY(true, false); }
+#undef CWA_FORCE_LIST
+#undef CWA_FORCE_HEAVY
     return 0;
 }
 
@@ -1226,6 +1281,7 @@ int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which)
     CWA_CHECK(g && g->dim == 3, "sph: the bound grid must be a 3-D grid");
     const bool full = (which == 7);
     const int cfg = nb_config();
+    const bool fused_tail = full && cfg == 7 && fused_integrate();   // the force kernels finish the particle (epilogue + integrate + write-back)
     if (which & 1) {
         CWA_TRY(sph_snapshot(ctx, s));                             // positions changed since the last frame
         switch (cfg) {
@@ -1254,17 +1310,20 @@ int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which)
         case 6: CWA_TRY((launch_force<256, 2>(ctx, s, g))); break;
         case 7:
             CWA_CHECK(s->nbr_lists_valid, "force pass: the neighbour lists of the density pass are missing");
-            CWA_TRY(launch_force_list(ctx, s, g)); break;
+            CWA_TRY(launch_force_list(ctx, s, g, fused_tail, aos, tex)); break;
         default: CWA_TRY((launch_force<128, 4>(ctx, s, g))); break;
         }
-        s->pair_sums_valid = true;
+        s->pair_sums_valid = !fused_tail;
         if (!full) {
             KScope k(ctx, KID_OTHER);
             sph3_finalize_force_sorted_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(
                 s->pack, s->forceS, s->pairP, s->pairV, g->index_list, g->offset + g->view.num_cells, aos, cc, tex);
         }
     }
-    if (which & 4) {
+    if ((which & 4) && fused_tail) {
+        s->snapshot_valid = false;                                 // positions moved (inside the force kernels)
+        s->pair_sums_valid = false;
+    } else if (which & 4) {
         KScope k(ctx, KID_INTEGRATE);
         if (full) {
             if (tex_view_is_local(tex))

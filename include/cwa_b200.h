@@ -94,7 +94,9 @@ CWA_API int  cwa_profile_end(cwa_ctx* ctx, float* ms, int* launches, int cap);  
 /* kernel-variant / staging knobs of the neighbour loops (no reference counterpart: the GLSL has one variant).
  * keys: "nb_config" (7: neighbour-list kernels, the default; 0..6: shared-memory-staged "lanes" kernels),
  *       "nb_cap_d", "nb_cap_f" (staged slots of the lanes kernels),
- *       "fused_order" (1: canonical ordering fused into the reorder pass). */
+ *       "fused_order" (1: canonical ordering fused into the reorder pass),
+ *       "fused_integrate" (1: in a full step the force kernels also run the epilogue + integrate; default 0:
+ *       measured 6 us faster per C4 frame while few targets are queued, 120 us slower once clumps dominate). */
 CWA_API int  cwa_set_tuning(cwa_ctx* ctx, const char* key, int value);
 
 /* ---- Buffer: Init / BufferSubData / BindBufferBase / DebugRead*  (SphWave2D/Buffer.cpp:5-83) -- */

@@ -131,3 +131,27 @@ def test_fused_order_reorder_is_canonical(cwa, tuned, oracle, fused, cluster):
         assert_close(got["force"][ok, :3], ref["force"][ok, :3], what="force.xyz")
     finally:
         tuned.set_tuning(fused_order=1)
+
+
+@pytest.mark.parametrize("cluster", [False, True])
+def test_fused_integrate_tail_equals_separate_kernels(cwa, tuned, oracle, cluster):
+    """Full step: the force kernels may finish the particle themselves (force epilogue + integrate + record
+    write-back); the result must be the one of the separate integrate kernel (same device functions)."""
+    try:
+        tuned.set_tuning(nb_config=7, fused_integrate=0)
+        prm, p, tex, sph = _scene(cwa, tuned, oracle, "h+", cluster=cluster)
+        sph.step(2)
+        a = sph.download()
+        tuned.set_tuning(fused_integrate=1)
+        sph.upload(p)
+        sph.step(2)
+        b = sph.download()
+        for f in ("pos", "vel", "force", "extras"):
+            assert_close(b[f], a[f], rtol=5e-6, what=f)
+        ref = p.copy()
+        for _ in range(2):
+            oracle.sph3_rho_pres(ref, prm, tex); oracle.sph3_force(ref, prm, tex); oracle.sph3_integrate(ref, prm, tex)
+        if not cluster:
+            assert_close(b["pos"][:, :3], ref["pos"][:, :3], scale=1e-3, rtol=1e-3, what="pos vs oracle")
+    finally:
+        tuned.set_tuning(fused_integrate=0)
