@@ -105,6 +105,7 @@ class DistributedCoupled:
         self.dist = dist                       # torch.distributed module (None: single rank)
         self.world, self.rank = plan.world, plan.rank
         plan.validate()
+        self._halo_pending = False
         self._nbr_plans = {r: SlabPlan.make(plan.world, r, plan.wave_w, plan.wave_h, plan.uv_scale, plan.h)
                            for r in (plan.rank - 1, plan.rank + 1) if 0 <= r < plan.world}
 
@@ -122,52 +123,72 @@ class DistributedCoupled:
                 w.wait()
 
     # ---- one frame -----------------------------------------------------------------------------
-    def _particle_exchange(self):
+    def _wave_pairs(self):
+        """P2P operations that refresh the halo rows of the newest level and distribute the global last row."""
+        p, b = self.plan, self.b
+        img = b.newest_image()
+        pairs = []
+        if p.has_left:
+            lp = self._nbr_plans[self.rank - 1]
+            n_up = lp.store_hi - lp.row_hi           # my first owned rows are the left neighbour's upper halo
+            pairs.append((b.wave_rows(img, p.row_lo, n_up), b.wave_rows(img, p.store_lo, p.row_lo - p.store_lo), self.rank - 1))
+        if p.has_right:
+            rp = self._nbr_plans[self.rank + 1]
+            n_dn = rp.row_lo - rp.store_lo           # my last owned rows are the right neighbour's lower halo
+            pairs.append((b.wave_rows(img, p.row_hi - n_dn, n_dn), b.wave_rows(img, p.row_hi, p.store_hi - p.row_hi), self.rank + 1))
+        # global last row: WaveNormal's uv + (0,1) tap clamps to it from everywhere (force_comp.glsl:136); the last rank
+        # sends it to every other rank inside the same group (a handful of small messages, no separate collective)
+        last = self.world - 1
+        if self.rank == last:
+            b.copy_own_last_row(img)
+            pairs += [(b.last_row(img), None, r) for r in range(last)]
+        else:
+            pairs.append((None, b.last_row(img), last))
+        return pairs
+
+    def _exchange(self, particles: bool, wave: bool):
+        """ONE grouped NCCL call per frame: migrants + ghosts of this frame and -- deferred from the end of the previous
+        frame -- the wave halo rows / last row the SPH passes are about to sample."""
         p, b = self.plan, self.b
         if self.world == 1:
-            b.no_exchange()
+            if particles:
+                b.no_exchange()
             return
         with b.comm_stream():
-            send_l, send_r = b.pack(p.z_lo, p.z_hi, p.ghost_width, p.has_left, p.has_right)
-            recv_l, recv_r = b.recv_buffers(p.has_left, p.has_right)
             pairs = []
-            if p.has_left:
-                pairs.append((send_l, recv_l, self.rank - 1))
-            if p.has_right:
-                pairs.append((send_r, recv_r, self.rank + 1))
+            if particles:
+                send_l, send_r = b.pack(p.z_lo, p.z_hi, p.ghost_width, p.has_left, p.has_right)
+                recv_l, recv_r = b.recv_buffers(p.has_left, p.has_right)
+                if p.has_left:
+                    pairs.append((send_l, recv_l, self.rank - 1))
+                if p.has_right:
+                    pairs.append((send_r, recv_r, self.rank + 1))
+            if wave:
+                pairs += self._wave_pairs()
             self._p2p(pairs)
-            b.unpack(p.has_left, p.has_right)
+            if particles:
+                b.unpack(p.has_left, p.has_right)
+
+    def _particle_exchange(self):
+        self._exchange(True, False)
 
     def _wave_halo_refresh(self):
-        """After a stencil step: overwrite the halo rows of the newest level and refresh the global last row."""
-        p, b = self.plan, self.b
-        if self.world == 1:
-            return
-        img = b.newest_image()
-        with b.comm_stream():
-            pairs = []
-            if p.has_left:
-                lp = self._nbr_plans[self.rank - 1]
-                n_up = lp.store_hi - lp.row_hi           # my first owned rows are the left neighbour's upper halo
-                pairs.append((b.wave_rows(img, p.row_lo, n_up), b.wave_rows(img, p.store_lo, p.row_lo - p.store_lo), self.rank - 1))
-            if p.has_right:
-                rp = self._nbr_plans[self.rank + 1]
-                n_dn = rp.row_lo - rp.store_lo           # my last owned rows are the right neighbour's lower halo
-                pairs.append((b.wave_rows(img, p.row_hi - n_dn, n_dn), b.wave_rows(img, p.row_hi, p.store_hi - p.row_hi), self.rank + 1))
-            self._p2p(pairs)
-            if self.rank == self.world - 1:
-                b.copy_own_last_row(img)
-            self.dist.broadcast(b.last_row(img), src=self.world - 1)
+        self._exchange(False, True)
 
     def step(self, nframes: int = 1, coupling: int = COUPLING_AS_SHIPPED):
         b = self.b
-        for _ in range(nframes):
-            self._particle_exchange()
+        for f in range(nframes):
+            # the halo refresh of the previous frame's stencil step travels with this frame's particles
+            self._exchange(True, self._halo_pending)
+            self._halo_pending = False
             image = b.newest_image() if coupling == COUPLING_LATEST else b.tex_unit0()
             b.sph_step(image)                      # idle(): rho_pres, force, integrate  (Main.cpp:549-557)
             b.wave_step()                          # Module::sComputeAll               (Main.cpp:560)
-            self._wave_halo_refresh()
             b.bind_texture_unit()                  # display(): GetReadImage(0).BindTextureUnit()  (Main.cpp:413)
+            self._halo_pending = True
+        if self._halo_pending:                     # leave a consistent field behind (reads, checks, the next call)
+            self._exchange(False, True)
+            self._halo_pending = False
 
     def init_wave_halos(self):
         """Init() wrote both read levels from global coordinates, so only the last rows need the broadcast."""
