@@ -57,13 +57,13 @@ ALGO_BYTES = {
     "clear(memset)": (0, 4, 0),
     "grid_hash_count": (24, 0, 0),     # pos 16 B read, cell id 4 B + arrival rank 4 B written
     "scan_lookback": (0, 8, 0),        # 4 B read + 4 B written per cell, single pass
-    "grid_insert": (16, 0, 0),         # cell id, rank, offset read; index written
+    "grid_insert": (24, 0, 0),         # count-ahead frames: slot's cell id, rank, old index + offset read; cell_of and arrival list written (plain frames: 16)
     "grid_cell_order": (16, 0, 0),     # (stand-alone grid builds only) cell id + offset read, arrival list read, index written
     "reorder": (148, 0, 0),            # fused ordering + reorder: arrival 4 + cell id 4 + offsets 8 + record 64 read; index 4 + snapshot 64 written
     "density": (124, 0, 0),            # pos+vel 32 B read, pack 32 B + count 4 B + neighbour list ~56 B (13.4 entries) written; the loop itself is FP32/L1 bound
     "force": (116, 0, 0),              # pack 32 B + count 4 B + list ~56 B read, pair sums 24 B written; neighbour gathers hit L1/L2
     "heavy_targets": (0, 0, 0),        # clump targets (> 192 candidates / > 64 neighbours) finished one warp each, both passes
-    "integrate": (156, 0, 0),          # pack 32 + force 16 + misc 16 + pair sums 24 + index 4 read, 64 B record written to the SSBO
+    "integrate": (164, 0, 0),          # pack 32 + force 16 + misc 16 + pair sums 24 + index 4 read, 64 B record written to the SSBO, + next frame's cell id and arrival rank (8 B, count-ahead)
     "wave_evolve": (0, 0, 12),         # u(t-1) read once, u(t-2) read, u(t) written
 }
 
@@ -273,39 +273,67 @@ def run_native(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end through the C ABI with HOST buffers -------------------------------------------
-    pin_p = torch.empty(N_PARTICLES * cwa.PARTICLE.itemsize, dtype=torch.uint8).pin_memory()
-    pin_w = [torch.empty(WAVE * WAVE, dtype=torch.float32).pin_memory() for _ in range(2)]
-    host_p = pin_p.numpy().view(cwa.PARTICLE)
-    host_w = [w_.numpy().reshape(WAVE, WAVE) for w_ in pin_w]
-    host_p[:] = sph.download()
-    host_w[0][:] = wave.read_role(0)
-    host_w[1][:] = wave.read_role(1)
+    # Every step: particle SSBO + the two wave levels the stencil reads go up from pinned host memory, one coupled frame runs,
+    # the particle SSBO + the new wave level come back.  Two scene streams (two library contexts = two CUDA streams, each with
+    # its own device objects and pinned buffers) alternate, so the upload of step k+1 overlaps the frame and the read-back of
+    # step k on the two copy engines of the PCIe link; a step is complete when its results are in host memory
+    # (cwa_synchronize of its context, called before the slot is reused and at the end of the timed region).
     import ctypes as C
-    lib, h = ctx.lib, ctx.h
 
-    def e2e_step():
-        # inputs: particle SSBO + the two wave levels the stencil reads; outputs: particle SSBO + the new wave level
-        cwa.check(lib.cwa_buffer_sub_data(h, sph.buffer.h, 0, host_p.nbytes, C.c_void_p(host_p.ctypes.data)))
-        cwa.check(lib.cwa_wave_write_image(h, wave.h, wave.role_image(0), C.c_void_p(host_w[0].ctypes.data)))
-        cwa.check(lib.cwa_wave_write_image(h, wave.h, wave.role_image(1), C.c_void_p(host_w[1].ctypes.data)))
-        cwa.check(lib.cwa_coupled_step(h, sph.h, wave.h, 1, COUPLING))
-        cwa.check(lib.cwa_buffer_read(h, sph.buffer.h, 0, host_p.nbytes, C.c_void_p(host_p.ctypes.data)))
-        host_w[0], host_w[1] = host_w[1], host_w[0]               # the previous newest level becomes u(t-2) ...
-        cwa.check(lib.cwa_wave_read_image(h, wave.h, wave.role_image(0), C.c_void_p(host_w[0].ctypes.data)))   # ... and the new level is read back
-    for _ in range(3):
-        e2e_step()
-    barrier(); ctx.synchronize()
+    class Slot:
+        def __init__(self, c, sp, wv):
+            self.ctx, self.sph, self.wave = c, sp, wv
+            self.pin_p = torch.empty(N_PARTICLES * cwa.PARTICLE.itemsize, dtype=torch.uint8).pin_memory()
+            self.pin_w = [torch.empty(WAVE * WAVE, dtype=torch.float32).pin_memory() for _ in range(2)]
+            self.host_p = self.pin_p.numpy().view(cwa.PARTICLE)
+            self.host_w = [w_.numpy().reshape(WAVE, WAVE) for w_ in self.pin_w]
+
+        def submit(self):
+            lib, h, sp, wv = self.ctx.lib, self.ctx.h, self.sph, self.wave
+            hp, hw = self.host_p, self.host_w
+            cwa.check(lib.cwa_buffer_sub_data(h, sp.buffer.h, 0, hp.nbytes, C.c_void_p(hp.ctypes.data)))
+            cwa.check(lib.cwa_wave_write_image(h, wv.h, wv.role_image(0), C.c_void_p(hw[0].ctypes.data)))
+            cwa.check(lib.cwa_wave_write_image(h, wv.h, wv.role_image(1), C.c_void_p(hw[1].ctypes.data)))
+            cwa.check(lib.cwa_coupled_step(h, sp.h, wv.h, 1, COUPLING))
+            cwa.check(lib.cwa_buffer_read_async(h, sp.buffer.h, 0, hp.nbytes, C.c_void_p(hp.ctypes.data)))
+            hw[0], hw[1] = hw[1], hw[0]                   # the previous newest level becomes u(t-2) ...
+            cwa.check(lib.cwa_wave_read_image_async(h, wv.h, wv.role_image(0), C.c_void_p(hw[0].ctypes.data)))   # ... and the new level is read back
+
+    ctx2 = cwa.Context(local_rank)
+    grid2, sph2, wave2 = build_scene(cwa, ctx2)
+    slots = [Slot(ctx, sph, wave), Slot(ctx2, sph2, wave2)]
+    state_p, state_w0, state_w1 = sph.download(), wave.read_role(0), wave.read_role(1)
+    for sl in slots:
+        sl.host_p[:] = state_p
+        sl.host_w[0][:] = state_w0
+        sl.host_w[1][:] = state_w1
+    for k in range(4):
+        slots[k % 2].ctx.synchronize()
+        slots[k % 2].submit()
+    for sl in slots:
+        sl.ctx.synchronize()
+    barrier()
     t0 = time.perf_counter()
-    for _ in range(K):
-        e2e_step()
-    ctx.synchronize()
+    for k in range(K):
+        sl = slots[k % 2]
+        sl.ctx.synchronize()                              # the slot's previous step is complete: its results are in host memory
+        sl.submit()
+    for sl in slots:
+        sl.ctx.synchronize()
     e2e_s = time.perf_counter() - t0
+    # the same loop without overlap (one slot, blocking read-backs), for the record
+    t0 = time.perf_counter()
+    n_serial = max(5, K // 10)
+    for _ in range(n_serial):
+        slots[0].submit()
+        slots[0].ctx.synchronize()
+    e2e_serial_s = (time.perf_counter() - t0) / n_serial
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
-    h2d = host_p.nbytes + 2 * WAVE * WAVE * 4
-    d2h = host_p.nbytes + WAVE * WAVE * 4
+    h2d = slots[0].host_p.nbytes + 2 * WAVE * WAVE * 4
+    d2h = slots[0].host_p.nbytes + WAVE * WAVE * 4
 
     if rank != 0:
         if world > 1:
@@ -349,7 +377,9 @@ def run_native(args):
                    "timing": "cudaEvent on the context stream around K coupled frames, max over ranks"},
         "clocks": clocks,
         "e2e": {"value": world * N_PARTICLES * K / e2e_s, "unit": "particle-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_s / K * 1e3},
+                "ms_per_step": e2e_s / K * 1e3, "ms_per_step_unpipelined": e2e_serial_s * 1e3,
+                "how": "C ABI, pinned host buffers; two scene streams alternate so step k+1's upload overlaps step k's frame and read-back; "
+                       "a step counts when its results are in host memory"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "roofline_kernels": kern,

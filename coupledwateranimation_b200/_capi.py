@@ -64,6 +64,7 @@ SIGNATURES = {
     "cwa_buffer_destroy": (_I, [_P, _I]),
     "cwa_buffer_sub_data": (_I, [_P, _I, _Z, _Z, _P]),
     "cwa_buffer_read": (_I, [_P, _I, _Z, _Z, _P]),
+    "cwa_buffer_read_async": (_I, [_P, _I, _Z, _Z, _P]),
     "cwa_buffer_copy": (_I, [_P, _I, _I, _Z, _Z, _Z]),
     "cwa_buffer_bind_base": (_I, [_P, _I, _I, _I]),
     "cwa_buffer_device_ptr": (_I, [_P, _I, C.POINTER(_P), C.POINTER(_Z)]),
@@ -88,6 +89,7 @@ SIGNATURES = {
     "cwa_wave_bind_texture_unit": (_I, [_P, _I]),
     "cwa_wave_read_image": (_I, [_P, _I, _I, _P]),
     "cwa_wave_write_image": (_I, [_P, _I, _I, _P]),
+    "cwa_wave_read_image_async": (_I, [_P, _I, _I, _P]),
     "cwa_wave_role_image": (_I, [_P, _I, _I, _IP]),
     "cwa_wave_image_buffer": (_I, [_P, _I, _I, _IP]),
     "cwa_wave_size": (_I, [_P, _I, _IP, _IP, _IP]),

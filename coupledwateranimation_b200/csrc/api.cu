@@ -107,6 +107,8 @@ extern "C" int cwa_create(int device, cwa_ctx** out)
     CWA_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CWA_CUDA(cudaEventCreate(&ctx->ev0));
     CWA_CUDA(cudaEventCreate(&ctx->ev1));
+    for (int i = 0; i < 2; i++) CWA_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 4; i++) CWA_CUDA(cudaEventCreateWithFlags(&ctx->ev_pipe[i], cudaEventDisableTiming));
     for (int i = 0; i < 16; i++) ctx->ssbo_binding[i] = -1;
     for (int i = 0; i < 8; i++) { ctx->ubo_binding[i] = -1; ctx->default_ubo[i] = -1; }
 
@@ -153,6 +155,8 @@ extern "C" void cwa_destroy(cwa_ctx* ctx)
     if (ctx->scan_ticket) cudaFree(ctx->scan_ticket);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
+    for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->ev_pipe[i]);
+    for (int i = 0; i < 2; i++) { cudaStreamSynchronize(ctx->side_stream[i]); cudaStreamDestroy(ctx->side_stream[i]); }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -285,6 +289,18 @@ extern "C" int cwa_buffer_read(cwa_ctx* ctx, cwa_buf b, size_t off, size_t bytes
     CWA_CHECK(host && off + bytes <= o->bytes, "cwa_buffer_read: range outside buffer");
     CWA_CUDA(cudaMemcpyAsync(host, (const char*)o->ptr + off, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CWA_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// Read-back that does not block: enqueued behind the work already on the context stream; the host memory (pinned, or the copy
+// degrades to a synchronous one) holds the data after the next cwa_synchronize().  The GL analogue is glGetNamedBufferSubData
+// into a persistently mapped / pixel-pack buffer followed by a fence.
+extern "C" int cwa_buffer_read_async(cwa_ctx* ctx, cwa_buf b, size_t off, size_t bytes, void* host)
+{
+    BufferObj* o = get_buffer(ctx, b);
+    CWA_CHECK(o, "invalid buffer handle %d", b);
+    CWA_CHECK(host && off + bytes <= o->bytes, "cwa_buffer_read_async: range outside buffer");
+    CWA_CUDA(cudaMemcpyAsync(host, (const char*)o->ptr + off, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return 0;
 }
 

@@ -253,28 +253,60 @@ grid_cell_order_kernel(const int* __restrict__ cell_of, const int* __restrict__ 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-int grid_build_internal(cwa_ctx* ctx, GridObj* g, const void* particles, int stride_bytes, int n, bool canonical_order)
+// Count-ahead insert: the previous frame's integrate pass already hashed and counted the new positions (slot-indexed cell id and
+// arrival rank); after the scan the particle of old slot s goes to arrival[offset[cell] + rank].  Coalesced reads, and the
+// public cell_of[] array (original particle order) is kept up to date for the reorder pass and cwa_grid_read.
+__global__ void __launch_bounds__(256)
+grid_insert_ahead_kernel(const int* __restrict__ cell_s, const int* __restrict__ rank_s, const int* __restrict__ old_index_list,
+                         const int* __restrict__ offset, int n, int* __restrict__ cell_of, int* __restrict__ arrival)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int c = __ldg(cell_s + s);
+    if (c == -2) return;                                           // slot beyond the previous build's inserted count
+    const int id = __ldg(old_index_list + s);
+    cell_of[id] = c;
+    if (c >= 0) arrival[__ldg(offset + c) + __ldg(rank_s + s)] = id;
+}
+
+int grid_build_internal(cwa_ctx* ctx, GridObj* g, const void* particles, int stride_bytes, int n, const GridBuildOpts& opts)
 {
     CWA_CHECK(n >= 0 && n <= g->max_particles, "grid build: %d particles exceed the grid's capacity %d", n, g->max_particles);
     CWA_CHECK(stride_bytes >= 16 && stride_bytes % 16 == 0, "grid build: particle stride must be a multiple of 16 bytes");
+    const bool ahead = opts.ahead_cell != nullptr && opts.ahead_rank != nullptr;
     g->n_built = n;
-    { KScope k(ctx, KID_CLEAR);                                                // ClearCounter + scan state, one memset
-      CWA_CUDA(cudaMemsetAsync(g->counter, 0, g->clear_bytes, ctx->stream)); }
     const int C = g->view.num_cells;
-    if (n > 0) {
-        KScope k(ctx, KID_HASH_COUNT);
-        if (g->dim == 2)
-            grid_hash_count_kernel<2><<<ceil_div(n, 256), 256, 0, ctx->stream>>>((const char*)particles, stride_bytes, n, g->view, g->counter, g->cell_of, g->rank);
-        else
-            grid_hash_count_kernel<3><<<ceil_div(n, 256), 256, 0, ctx->stream>>>((const char*)particles, stride_bytes, n, g->view, g->counter, g->cell_of, g->rank);
-        CWA_CUDA(cudaGetLastError());
+    if (!ahead) {
+        { KScope k(ctx, KID_CLEAR);                                            // ClearCounter + scan state, one memset
+          CWA_CUDA(cudaMemsetAsync(g->counter, 0, g->clear_bytes, ctx->stream)); }
+        if (n > 0) {
+            KScope k(ctx, KID_HASH_COUNT);
+            if (g->dim == 2)
+                grid_hash_count_kernel<2><<<ceil_div(n, 256), 256, 0, ctx->stream>>>((const char*)particles, stride_bytes, n, g->view, g->counter, g->cell_of, g->rank);
+            else
+                grid_hash_count_kernel<3><<<ceil_div(n, 256), 256, 0, ctx->stream>>>((const char*)particles, stride_bytes, n, g->view, g->counter, g->cell_of, g->rank);
+            CWA_CUDA(cudaGetLastError());
+        }
     }
     CWA_TRY(scan_exclusive_launch(ctx, g->counter, g->offset, C, g->ticket, g->tile_state));
+    if (opts.clear_after_scan) {
+        // the NEXT build is counted ahead by this frame's integrate pass: counter and scan state are free once the scan is done,
+        // so they are cleared on a side stream while the insert / reorder passes run (ev_pipe[1] = cleared)
+        CWA_CUDA(cudaEventRecord(ctx->ev_pipe[0], ctx->stream));
+        CWA_CUDA(cudaStreamWaitEvent(ctx->side_stream[1], ctx->ev_pipe[0], 0));
+        { StreamScope ss(ctx, ctx->side_stream[1]);
+          KScope k(ctx, KID_CLEAR);
+          CWA_CUDA(cudaMemsetAsync(g->counter, 0, g->clear_bytes, ctx->stream)); }
+        CWA_CUDA(cudaEventRecord(ctx->ev_pipe[1], ctx->side_stream[1]));
+    }
     if (n > 0) {
         { KScope k(ctx, KID_INSERT);
-          grid_insert_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(g->cell_of, g->rank, g->offset, n, g->arrival); }
+          if (ahead)
+              grid_insert_ahead_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(opts.ahead_cell, opts.ahead_rank, g->index_list, g->offset, n, g->cell_of, g->arrival);
+          else
+              grid_insert_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(g->cell_of, g->rank, g->offset, n, g->arrival); }
         CWA_CUDA(cudaGetLastError());
-        if (canonical_order) {
+        if (opts.canonical_order) {
             KScope k(ctx, KID_CELL_ORDER);
             grid_cell_order_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(g->cell_of, g->offset, g->arrival, n, g->index_list);
         }

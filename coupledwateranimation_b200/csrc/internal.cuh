@@ -142,8 +142,14 @@ struct SphObj {
     float2 *pairV = nullptr;                     //                                   (visc.y, visc.z)
     int   *nbr_list = nullptr, *nbr_count = nullptr;   // neighbour lists of the density pass ([slot][K]) and true counts
     bool   nbr_lists_valid = false;
-    int   *heavy_queue = nullptr;                           // targets finished one warp each: [0,cap) density pass, [cap,2cap) force pass;
-                                                            // the two counters live in the grid's clear block (ticket + 2, + 3)
+    int   *heavy_queue = nullptr;                           // targets finished one warp each: [0,cap) density pass, [cap,2cap) force pass
+    int   *heavy_cnt = nullptr;                             // the two queue counters (density, force); reset by the reorder kernel of every snapshot
+    // count-ahead (frames in the middle of one cwa_coupled_step call): the integrate pass hashes the NEW position of the
+    // particle in cell-ordered slot s, counts it into the grid's (pre-cleared) counter and leaves (cell, arrival rank) here,
+    // so the next frame's grid build starts at the scan
+    int   *cell_next = nullptr, *rank_next = nullptr;
+    bool   counts_ahead = false;                            // the grid counter already holds the counts of the current positions
+    cudaEvent_t wait_before_sampling = nullptr;             // transient: the first kernel that samples the wave field waits for it
     unsigned long long consts_epoch = 0;                    // params_epoch the prepared constants were derived from
     void*  consts = nullptr;                     // Sph3Const prepared on the device once per dispatch
     bool snapshot_valid = false;
@@ -190,6 +196,8 @@ struct cwa_ctx {
     int cc_major = 0, cc_minor = 0;
     size_t total_mem = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t side_stream[2] = {nullptr, nullptr};   // frame pipelining inside cwa_coupled_step: [0] wave stencil, [1] grid clears
+    cudaEvent_t  ev_pipe[4] = {nullptr, nullptr, nullptr, nullptr};   // scan done, clear done, integrate done, wave done
     cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
     unsigned long long launches = 0;
     unsigned long long params_epoch = 1;   // bumped whenever a parameter block may have changed (UBO write / bind)
@@ -224,14 +232,29 @@ ParamPtrs  current_params(cwa_ctx* ctx);
 int  scan_exclusive_launch(cwa_ctx* ctx, const int* in, int* out, int n, int* ticket,
                            unsigned long long* tile_state);          // grid.cu; out has n+1 entries
 size_t scan_num_tiles(int n);
-int  grid_build_internal(cwa_ctx* ctx, GridObj* g, const void* particles, int stride_bytes, int n, bool canonical_order = true);
-// canonical_order = false stops after the arrival-order insert: the caller's fused kernel ranks and reorders in one pass
+struct GridBuildOpts {
+    bool canonical_order = true;       // false: stop after the arrival-order insert (the caller's fused kernel ranks and reorders in one pass)
+    // count-ahead: the counter already holds this build's counts; cell id and arrival rank of the particle that sat in
+    // cell-ordered slot s of the PREVIOUS build are in ahead_cell[s] / ahead_rank[s] (-1: not inserted), s < n
+    const int* ahead_cell = nullptr;
+    const int* ahead_rank = nullptr;
+    bool clear_after_scan = false;     // the next build is counted ahead: clear counter + scan state right after this scan (side stream)
+};
+int  grid_build_internal(cwa_ctx* ctx, GridObj* g, const void* particles, int stride_bytes, int n, const GridBuildOpts& opts = GridBuildOpts());
 TexView wave_tex_view(cwa_ctx* ctx, cwa_wave w, int image);           // wave.cu
 int  wave_step_internal(cwa_ctx* ctx, WaveObj* w);
 int  wave_dispatch_mode(cwa_ctx* ctx, WaveObj* w, int mode);           // kernel for uMode on units 0/1/2, no rotation                   // one EVOLVE dispatch + PingPong
-int  sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which /*bit0 rho, bit1 force, bit2 integrate*/);
+int  sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which /*bit0 rho, bit1 force, bit2 integrate*/, bool count_ahead = false);
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// Everything launched inside the scope (kernels, memsets, the KScope events around them) goes to `s` instead of the
+// context's main stream; ordering against the main stream is the caller's business (events).
+struct StreamScope {
+    cwa_ctx* ctx; cudaStream_t saved;
+    StreamScope(cwa_ctx* c, cudaStream_t s) : ctx(c), saved(c->stream) { c->stream = s; }
+    ~StreamScope() { ctx->stream = saved; }
+};
 
 // RAII bracket around one launch (or memset): counts it and, while a profile is being taken,
 // records a CUDA-event pair on the launching stream.

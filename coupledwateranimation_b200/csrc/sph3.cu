@@ -236,9 +236,10 @@ __device__ __forceinline__ void integrate_particle(const Sph3Const& c, const Tex
 __global__ void __launch_bounds__(256)
 sph3_reorder_kernel(const float4* __restrict__ aos, const int* __restrict__ index_list, const int* __restrict__ count,
                     float4* __restrict__ posS, float4* __restrict__ velS, float4* __restrict__ forceS,
-                    float4* __restrict__ miscS)
+                    float4* __restrict__ miscS, int* __restrict__ heavy_cnt)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) { heavy_cnt[0] = 0; heavy_cnt[1] = 0; }   // clump queues of the density / force passes that follow this snapshot
     const int s = t >> 2, q = t & 3;
     const int n = __ldg(count);                  // inserted particles (NaN positions are left out)
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -265,9 +266,10 @@ __global__ void __launch_bounds__(256)
 sph3_order_reorder_kernel(const float4* __restrict__ aos, const int* __restrict__ arrival, const int* __restrict__ cell_of,
                           const int* __restrict__ offset, const int* __restrict__ count, int* __restrict__ index_list,
                           float4* __restrict__ posS, float4* __restrict__ velS, float4* __restrict__ forceS,
-                          float4* __restrict__ miscS)
+                          float4* __restrict__ miscS, int* __restrict__ heavy_cnt)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s == 0) { heavy_cnt[0] = 0; heavy_cnt[1] = 0; }   // clump queues of the density / force passes that follow this snapshot
     if (s >= __ldg(count)) return;                 // inserted particles (NaN positions are left out)
     const int id = __ldg(arrival + s);
     const float4* rec = aos + (size_t)id * 4;
@@ -845,27 +847,57 @@ sph3_force_heavy_kernel(const float4* __restrict__ pack, const int* __restrict__
 
 // force epilogue + integrate on the cell-ordered snapshot; one thread per particle writes the full
 // 64-B record back to the particle SSBO in its original order.
-template <bool LOCAL>
+// AHEAD (frames in the middle of one cwa_coupled_step call): the thread also does the NEXT frame's cell hash + count on
+// the position it just wrote -- the same cwa_cell3 on the same stored floats as grid_hash_count_kernel, warp-aggregated
+// (threads are in cell order, so most lanes of a warp share a few cells) -- and leaves cell id and arrival rank indexed
+// by its slot: the next grid build starts at the scan and never re-reads the particle records for the hash.
+template <bool LOCAL, bool AHEAD>
 __global__ void __launch_bounds__(128, 10)          // latency-bound gathers and scatters: favour occupancy over registers
 sph3_finalize_integrate_sorted_kernel(const float4* __restrict__ pack,
                                       const float4* __restrict__ forceS, const float4* __restrict__ miscS,
                                       const float4* __restrict__ pairP, const float2* __restrict__ pairV,
                                       const int* __restrict__ index_list, const int* __restrict__ count, float4* __restrict__ aos,
-                                      const Sph3Const* __restrict__ cc, TexView tex)
+                                      const Sph3Const* __restrict__ cc, TexView tex,
+                                      GridView g, int n, int* __restrict__ counter, int* __restrict__ cell_next, int* __restrict__ rank_next)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= __ldg(count)) return;
-    const Sph3Const c = *cc;
-    const f4x2 ab = cwa_ldg256(pack + 2 * (size_t)s);
-    const float4 a = ab.a, b = ab.b, m = __ldg(miscS + s), pp = __ldg(pairP + s);
-    const float2 pv = __ldg(pairV + s);
-    float4 f = force_epilogue<LOCAL>(c, tex, a.x, a.y, a.z, b.x, b.y, b.z, b.w, __ldg(forceS + s), pp.x, pp.y, pp.z, pp.w, pv.x, pv.y);
-    float4 pos = make_float4(a.x, a.y, a.z, m.x), vel = make_float4(b.x, b.y, b.z, m.y);
-    float rho = b.w, prs = a.w;
-    integrate_particle<LOCAL>(c, tex, pos, vel, f, rho, prs);
-    float4* o = aos + (size_t)__ldg(index_list + s) * 4;      // 64-byte record = two 256-bit stores (two full sectors)
-    cwa_stg256(o, pos, vel);
-    cwa_stg256(o + 2, f, make_float4(rho, prs, m.z, m.w));
+    const bool live = s < __ldg(count);
+    if (!AHEAD && !live) return;
+    int cell = -2;                                  // -2: slot beyond the inserted particles, -1: position became NaN
+    if (live) {
+        const Sph3Const c = *cc;
+        const f4x2 ab = cwa_ldg256(pack + 2 * (size_t)s);
+        const float4 a = ab.a, b = ab.b, m = __ldg(miscS + s), pp = __ldg(pairP + s);
+        const float2 pv = __ldg(pairV + s);
+        float4 f = force_epilogue<LOCAL>(c, tex, a.x, a.y, a.z, b.x, b.y, b.z, b.w, __ldg(forceS + s), pp.x, pp.y, pp.z, pp.w, pv.x, pv.y);
+        float4 pos = make_float4(a.x, a.y, a.z, m.x), vel = make_float4(b.x, b.y, b.z, m.y);
+        float rho = b.w, prs = a.w;
+        integrate_particle<LOCAL>(c, tex, pos, vel, f, rho, prs);
+        float4* o = aos + (size_t)__ldg(index_list + s) * 4;      // 64-byte record = two 256-bit stores (two full sectors)
+        cwa_stg256(o, pos, vel);
+        cwa_stg256(o + 2, f, make_float4(rho, prs, m.z, m.w));
+        if (AHEAD) {
+            cell = -1;
+            if (pos.x == pos.x && pos.y == pos.y && pos.z == pos.z) {          // as grid_hash_count_kernel<3>
+                int ci, cj, ck;
+                cwa_cell3(g, pos.x, pos.y, pos.z, ci, cj, ck);
+                cell = (ci * g.n[1] + cj) * g.kstride + ck;
+            }
+        }
+    }
+    if (AHEAD) {
+        const unsigned lane = threadIdx.x & 31u;
+        const unsigned peers = __match_any_sync(0xffffffffu, cell);
+        const int leader = __ffs(peers) - 1;
+        const int my_rank = __popc(peers & ((1u << lane) - 1u));
+        int base = 0;
+        if (cell >= 0 && (int)lane == leader) base = atomicAdd(&counter[cell], __popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (s < n) {
+            cell_next[s] = cell;
+            rank_next[s] = base + my_rank;
+        }
+    }
 }
 
 // individually dispatched passes: commit one pass result to the SSBO
@@ -1099,12 +1131,15 @@ static int env_int(const char* name, int dflt, int lo, int hi)
 //   cap_d / cap_f: staging budgets of the lanes kernels in slots (0 disables staging)
 constexpr int NB_CONFIG_DEFAULT = 7;
 constexpr int NBR_K = 64;                 // neighbour-list entries per target (self included); longer lists fall back to a grid scan
-struct NbTuning { int config = -1, cap_d = -1, cap_f = -1, fused_order = -1, fused_integrate = -1; };
+struct NbTuning { int config = -1, cap_d = -1, cap_f = -1, fused_order = -1, fused_integrate = -1, pipeline = -1; };
 static NbTuning g_tune;
 static int nb_config() { if (g_tune.config < 0) g_tune.config = env_int("CWA_NB_CONFIG", NB_CONFIG_DEFAULT, 0, 7); return g_tune.config; }
 static int dens_cap() { if (g_tune.cap_d < 0) g_tune.cap_d = env_int("CWA_NB_CAP_D", DENS_CAP_DEFAULT, 0, DENS_CAP_MAX); return g_tune.cap_d; }
 static int force_cap() { if (g_tune.cap_f < 0) g_tune.cap_f = env_int("CWA_NB_CAP_F", FORCE_CAP_DEFAULT, 0, FORCE_CAP_MAX); return g_tune.cap_f; }
 static bool fused_integrate() { if (g_tune.fused_integrate < 0) g_tune.fused_integrate = env_int("CWA_FUSED_INTEGRATE", 0, 0, 1); return g_tune.fused_integrate != 0; }
+// pipeline (cwa_coupled_step with several frames per call): bit 0 = the wave stencil of frame f runs on a side stream next to the
+// grid build of frame f+1; bit 1 = count-ahead (integrate of frame f does the cell hash + count of frame f+1)
+static int pipeline_mode() { if (g_tune.pipeline < 0) g_tune.pipeline = env_int("CWA_PIPELINE", 3, 0, 3); return g_tune.pipeline; }
 static bool fused_order() { if (g_tune.fused_order < 0) g_tune.fused_order = env_int("CWA_FUSED_ORDER", 1, 0, 1); return g_tune.fused_order != 0; }
 
 extern "C" int cwa_set_tuning(cwa_ctx* ctx, const char* key, int value)
@@ -1116,6 +1151,7 @@ extern "C" int cwa_set_tuning(cwa_ctx* ctx, const char* key, int value)
     else if (k == "nb_cap_f") { CWA_CHECK(value >= 0 && value <= FORCE_CAP_MAX, "nb_cap_f %d out of range", value); g_tune.cap_f = value; }
     else if (k == "fused_order") { g_tune.fused_order = value ? 1 : 0; }
     else if (k == "fused_integrate") { g_tune.fused_integrate = value ? 1 : 0; }
+    else if (k == "pipeline") { CWA_CHECK(value >= 0 && value <= 3, "pipeline %d out of range", value); g_tune.pipeline = value; }
     else CWA_CHECK(false, "cwa_set_tuning: unknown key '%s'", key);
     return 0;
 }
@@ -1158,7 +1194,7 @@ static int launch_density_list(cwa_ctx* ctx, SphObj* s, GridObj* g, TexView tex)
     const Sph3Const* cc = (const Sph3Const*)s->consts;
     const int ntiles = ceil_div(s->n, TILE_P);
     const bool local = tex_view_is_local(tex);
-    int* const hc = g->ticket + 2;                       // queue counter, zeroed by the grid build's memset
+    int* const hc = s->heavy_cnt;                        // queue counter, zeroed by the reorder pass of this snapshot
     { KScope k(ctx, KID_DENSITY);
       if (local)
           sph3_density_list_kernel<NBR_K, true><<<ntiles, TILE_P, 0, ctx->stream>>>(
@@ -1186,9 +1222,9 @@ static int launch_force_list(cwa_ctx* ctx, SphObj* s, GridObj* g, bool fused, fl
     const int blocks = ceil_div(s->n, TILE_P);
     const bool local = tex_view_is_local(tex);
 #define CWA_FORCE_LIST(F, L) sph3_force_list_kernel<NBR_K, F, L><<<blocks, TILE_P, 0, ctx->stream>>>( \
-        s->pack, s->nbr_list, s->nbr_count, fq, g->ticket + 3, s->pairP, s->pairV, s->n, g->view, g->offset, cc, fa)
+        s->pack, s->nbr_list, s->nbr_count, fq, s->heavy_cnt + 1, s->pairP, s->pairV, s->n, g->view, g->offset, cc, fa)
 #define CWA_FORCE_HEAVY(F, L) sph3_force_heavy_kernel<F, L><<<heavy_grid(ctx), 128, 0, ctx->stream>>>( \
-        s->pack, fq, g->ticket + 3, s->n, s->pairP, s->pairV, g->view, g->offset, cc, fa)
+        s->pack, fq, s->heavy_cnt + 1, s->n, s->pairP, s->pairV, g->view, g->offset, cc, fa)
     { KScope k(ctx, KID_FORCE);
       if (!fused) CWA_FORCE_LIST(false, false); else if (local) CWA_FORCE_LIST(true, true); else CWA_FORCE_LIST(true, false); }
     { KScope k(ctx, KID_HEAVY);
@@ -1198,22 +1234,26 @@ static int launch_force_list(cwa_ctx* ctx, SphObj* s, GridObj* g, bool fused, fl
     return 0;
 }
 
-static int sph_snapshot(cwa_ctx* ctx, SphObj* s)
+static int sph_snapshot(cwa_ctx* ctx, SphObj* s, bool count_next_ahead = false)
 {
     GridObj* g = get_grid(ctx, s->grid);
     BufferObj* pb = get_buffer(ctx, s->particles);
     CWA_CHECK(g && pb, "sph: grid or particle buffer vanished");
+    GridBuildOpts opts;
+    opts.canonical_order = !fused_order();
+    if (s->counts_ahead) { opts.ahead_cell = s->cell_next; opts.ahead_rank = s->rank_next; }
+    opts.clear_after_scan = count_next_ahead;
+    s->counts_ahead = false;
+    CWA_TRY(grid_build_internal(ctx, g, pb->ptr, 64, s->n, opts));
     if (fused_order()) {
-        CWA_TRY(grid_build_internal(ctx, g, pb->ptr, 64, s->n, false));
         KScope k(ctx, KID_REORDER);
-        sph3_order_reorder_kernel<<<ceil_div(s->n, 256), 256, 0, ctx->stream>>>(
+        sph3_order_reorder_kernel<<<ceil_div(s->n > 0 ? s->n : 1, 256), 256, 0, ctx->stream>>>(
             (const float4*)pb->ptr, g->arrival, g->cell_of, g->offset, g->offset + g->view.num_cells, g->index_list,
-            s->posS, s->velS, s->forceS, s->miscS);
+            s->posS, s->velS, s->forceS, s->miscS, s->heavy_cnt);
     } else {
-        CWA_TRY(grid_build_internal(ctx, g, pb->ptr, 64, s->n));
         KScope k(ctx, KID_REORDER);
-        sph3_reorder_kernel<<<ceil_div((long long)s->n * 4, 256), 256, 0, ctx->stream>>>(
-            (const float4*)pb->ptr, g->index_list, g->offset + g->view.num_cells, s->posS, s->velS, s->forceS, s->miscS);
+        sph3_reorder_kernel<<<ceil_div((long long)(s->n > 0 ? s->n : 1) * 4, 256), 256, 0, ctx->stream>>>(
+            (const float4*)pb->ptr, g->index_list, g->offset + g->view.num_cells, s->posS, s->velS, s->forceS, s->miscS, s->heavy_cnt);
     }
     CWA_CUDA(cudaGetLastError());
     s->snapshot_valid = true;
@@ -1244,7 +1284,9 @@ static float4* sph_scratch_force(SphObj* s) { return s->scratch; }
 
 // which: bit0 rho_pres, bit1 force, bit2 integrate.  In grid mode a full step (7) keeps every
 // intermediate in the cell-ordered snapshot and writes the SSBO once, at the end.
-int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which)
+// count_ahead (set by cwa_coupled_step for frames that are followed by another frame of the same call): the integrate pass also
+// hashes + counts the new positions for the next frame's grid build.
+int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which, bool count_ahead)
 {
     BufferObj* pb = get_buffer(ctx, s->particles);
     CWA_CHECK(pb, "sph: particle buffer vanished");
@@ -1282,8 +1324,13 @@ int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which)
     const bool full = (which == 7);
     const int cfg = nb_config();
     const bool fused_tail = full && cfg == 7 && fused_integrate();   // the force kernels finish the particle (epilogue + integrate + write-back)
+    count_ahead = count_ahead && full && !fused_tail;
     if (which & 1) {
-        CWA_TRY(sph_snapshot(ctx, s));                             // positions changed since the last frame
+        CWA_TRY(sph_snapshot(ctx, s, count_ahead));                // positions changed since the last frame
+        if (s->wait_before_sampling) {                             // the wave level this frame samples may still be in flight on the side stream
+            CWA_CUDA(cudaStreamWaitEvent(ctx->stream, s->wait_before_sampling, 0));
+            s->wait_before_sampling = nullptr;
+        }
         switch (cfg) {
         case 1: CWA_TRY((launch_density<128, 2>(ctx, s, g, tex))); break;
         case 2: CWA_TRY((launch_density<64, 4>(ctx, s, g, tex))); break;
@@ -1324,14 +1371,17 @@ int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which)
         s->snapshot_valid = false;                                 // positions moved (inside the force kernels)
         s->pair_sums_valid = false;
     } else if (which & 4) {
+        if (count_ahead) CWA_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_pipe[1], 0));   // counter cleared (side stream) after this frame's scan
         KScope k(ctx, KID_INTEGRATE);
         if (full) {
-            if (tex_view_is_local(tex))
-                sph3_finalize_integrate_sorted_kernel<true><<<ceil_div(n, 128), 128, 0, ctx->stream>>>(
-                    s->pack, s->forceS, s->miscS, s->pairP, s->pairV, g->index_list, g->offset + g->view.num_cells, aos, cc, tex);
-            else
-                sph3_finalize_integrate_sorted_kernel<false><<<ceil_div(n, 128), 128, 0, ctx->stream>>>(
-                    s->pack, s->forceS, s->miscS, s->pairP, s->pairV, g->index_list, g->offset + g->view.num_cells, aos, cc, tex);
+            const bool local = tex_view_is_local(tex);
+#define CWA_FIN_INT(L, A) sph3_finalize_integrate_sorted_kernel<L, A><<<ceil_div(n, 128), 128, 0, ctx->stream>>>( \
+                    s->pack, s->forceS, s->miscS, s->pairP, s->pairV, g->index_list, g->offset + g->view.num_cells, aos, cc, tex, \
+                    g->view, n, g->counter, s->cell_next, s->rank_next)
+            if (local) { if (count_ahead) CWA_FIN_INT(true, true); else CWA_FIN_INT(true, false); }
+            else       { if (count_ahead) CWA_FIN_INT(false, true); else CWA_FIN_INT(false, false); }
+#undef CWA_FIN_INT
+            s->counts_ahead = count_ahead;
         } else {
             sph3_integrate_aos_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(aos, n, cc, tex);
         }
@@ -1371,6 +1421,10 @@ extern "C" int cwa_sph_create(cwa_ctx* ctx, cwa_buf particles, int n, cwa_grid g
         CWA_CUDA(cudaMalloc(&s.nbr_list, (size_t)(n > 0 ? n : 1) * NBR_K * 4));
         CWA_CUDA(cudaMalloc(&s.nbr_count, (size_t)(n > 0 ? n : 1) * 4));
         CWA_CUDA(cudaMalloc(&s.heavy_queue, (size_t)(n > 0 ? n : 1) * 2 * 4));
+        CWA_CUDA(cudaMalloc(&s.heavy_cnt, 16));
+        CWA_CUDA(cudaMemsetAsync(s.heavy_cnt, 0, 16, ctx->stream));
+        CWA_CUDA(cudaMalloc(&s.cell_next, (size_t)(n > 0 ? n : 1) * 4));
+        CWA_CUDA(cudaMalloc(&s.rank_next, (size_t)(n > 0 ? n : 1) * 4));
     }
     ctx->sphs.push_back(s);
     *out = (int)ctx->sphs.size() - 1;
@@ -1384,6 +1438,7 @@ extern "C" int cwa_sph_destroy(cwa_ctx* ctx, cwa_sph h)
     CWA_CUDA(cudaStreamSynchronize(ctx->stream));
     cudaFree(s->pack); cudaFree(s->scratch); cudaFree(s->posS); cudaFree(s->velS); cudaFree(s->forceS); cudaFree(s->miscS);
     cudaFree(s->pairP); cudaFree(s->pairV); cudaFree(s->consts); cudaFree(s->nbr_list); cudaFree(s->nbr_count); cudaFree(s->heavy_queue);
+    cudaFree(s->heavy_cnt); cudaFree(s->cell_next); cudaFree(s->rank_next);
     s->live = false;
     if (ctx->bound_sph == h) ctx->bound_sph = -1;
     return 0;
@@ -1484,6 +1539,14 @@ extern "C" int cwa_coupled_step(cwa_ctx* ctx, cwa_sph hs, cwa_wave hw, int nfram
     WaveObj* w = get_wave(ctx, hw);
     CWA_CHECK(s && w, "cwa_coupled_step: invalid sph (%d) or wave (%d) handle", hs, hw);
     CWA_CHECK(coupling == CWA_COUPLING_AS_SHIPPED || coupling == CWA_COUPLING_LATEST, "unknown coupling mode %d", coupling);
+    // Frame pipelining (results identical to the plain sequence, tested both ways): inside one call nothing but this loop touches
+    // the state, so (a) the wave stencil of frame f -- which no SPH pass of frame f may overtake, but which is independent of the
+    // grid build of frame f+1 -- runs on a side stream and the first sampling kernel of frame f+1 waits for it, and (b) the
+    // integrate pass of frame f counts the particles into the cells of frame f+1 (count-ahead).  The last frame of the call runs the
+    // plain sequence, so every array an application can read afterwards is in the state the sequential code leaves.
+    const int pipe = (nframes > 1) ? pipeline_mode() : 0;
+    bool wave_in_flight = false;
+    s->counts_ahead = false;
     for (int f = 0; f < nframes; f++) {
         int image;
         if (coupling == CWA_COUPLING_LATEST) {
@@ -1493,9 +1556,31 @@ extern "C" int cwa_coupled_step(cwa_ctx* ctx, cwa_sph hs, cwa_wave hw, int nfram
             image = w->tex_unit0;                                            // whatever display() last bound to texture unit 0
         }
         s->wave = hw; s->wave_image = image;
-        CWA_TRY(sph_passes_internal(ctx, s, wave_tex_view(ctx, hw, image), 7));   // :549-557
-        if (w->evolve) CWA_TRY(wave_step_internal(ctx, w));                      // Module::sComputeAll :560
+        const bool more = f + 1 < nframes;
+        s->wait_before_sampling = wave_in_flight ? ctx->ev_pipe[3] : nullptr;
+        const int rc = sph_passes_internal(ctx, s, wave_tex_view(ctx, hw, image), 7, more && (pipe & 2) && s->grid >= 0);   // :549-557
+        if (s->wait_before_sampling) {                                       // not consumed (all-pairs mode, n == 0): wait here
+            cudaStreamWaitEvent(ctx->stream, s->wait_before_sampling, 0);
+            s->wait_before_sampling = nullptr;
+        }
+        wave_in_flight = false;
+        if (rc != 0) { s->counts_ahead = false; return rc; }
+        if (w->evolve) {                                                         // Module::sComputeAll :560
+            if (more && (pipe & 1)) {
+                CWA_CUDA(cudaEventRecord(ctx->ev_pipe[2], ctx->stream));         // this frame's SPH passes are done with the field
+                CWA_CUDA(cudaStreamWaitEvent(ctx->side_stream[0], ctx->ev_pipe[2], 0));
+                int wrc;
+                { StreamScope ss(ctx, ctx->side_stream[0]); wrc = wave_step_internal(ctx, w); }
+                CWA_CUDA(cudaEventRecord(ctx->ev_pipe[3], ctx->side_stream[0]));
+                wave_in_flight = true;
+                CWA_TRY(wrc);
+            } else {
+                CWA_TRY(wave_step_internal(ctx, w));
+            }
+        }
         CWA_TRY(cwa_wave_bind_texture_unit(ctx, hw));                            // display() :413
     }
+    if (wave_in_flight) CWA_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_pipe[3], 0));
+    s->counts_ahead = false;
     return 0;
 }

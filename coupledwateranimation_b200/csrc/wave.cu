@@ -531,6 +531,16 @@ extern "C" int cwa_wave_read_image(cwa_ctx* ctx, cwa_wave h, int image, float* h
     return 0;
 }
 
+extern "C" int cwa_wave_read_image_async(cwa_ctx* ctx, cwa_wave h, int image, float* host)
+{
+    WaveObj* w = get_wave(ctx, h);
+    CWA_CHECK(w && host, "invalid wave handle %d", h);
+    const int i = resolve_image(w, image);
+    CWA_CHECK(i >= 0, "image index %d out of range", image);
+    CWA_CUDA(cudaMemcpyAsync(host, w->image[i], (size_t)w->w * w->h * w->ch * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    return 0;
+}
+
 extern "C" int cwa_wave_write_image(cwa_ctx* ctx, cwa_wave h, int image, const float* host)
 {
     WaveObj* w = get_wave(ctx, h);

@@ -96,7 +96,10 @@ CWA_API int  cwa_profile_end(cwa_ctx* ctx, float* ms, int* launches, int cap);  
  *       "nb_cap_d", "nb_cap_f" (staged slots of the lanes kernels),
  *       "fused_order" (1: canonical ordering fused into the reorder pass),
  *       "fused_integrate" (1: in a full step the force kernels also run the epilogue + integrate; default 0:
- *       measured 6 us faster per C4 frame while few targets are queued, 120 us slower once clumps dominate). */
+ *       measured 6 us faster per C4 frame while few targets are queued, 120 us slower once clumps dominate),
+ *       "pipeline" (frames of ONE cwa_coupled_step call; bit 0: the wave stencil of frame f runs on a side stream next to
+ *       the grid build of frame f+1, bit 1: the integrate pass of frame f does the cell hash + count of frame f+1;
+ *       default 3; results and every readable array are bit-identical to 0). */
 CWA_API int  cwa_set_tuning(cwa_ctx* ctx, const char* key, int value);
 
 /* ---- Buffer: Init / BufferSubData / BindBufferBase / DebugRead*  (SphWave2D/Buffer.cpp:5-83) -- */
@@ -105,6 +108,7 @@ CWA_API int cwa_buffer_wrap(cwa_ctx* ctx, void* device_ptr, size_t bytes, cwa_bu
 CWA_API int cwa_buffer_destroy(cwa_ctx* ctx, cwa_buf b);                                             /* glDeleteBuffers */
 CWA_API int cwa_buffer_sub_data(cwa_ctx* ctx, cwa_buf b, size_t off, size_t bytes, const void* host);/* glNamedBufferSubData */
 CWA_API int cwa_buffer_read(cwa_ctx* ctx, cwa_buf b, size_t off, size_t bytes, void* host);          /* glGetNamedBufferSubData; synchronises */
+CWA_API int cwa_buffer_read_async(cwa_ctx* ctx, cwa_buf b, size_t off, size_t bytes, void* host);    /* same, enqueued only: `host` (pinned) is valid after cwa_synchronize */
 CWA_API int cwa_buffer_copy(cwa_ctx* ctx, cwa_buf src, cwa_buf dst, size_t soff, size_t doff, size_t bytes); /* glCopyNamedBufferSubData */
 CWA_API int cwa_buffer_bind_base(cwa_ctx* ctx, int target, int binding, cwa_buf b);                  /* glBindBufferBase */
 CWA_API int cwa_buffer_device_ptr(cwa_ctx* ctx, cwa_buf b, void** ptr, size_t* bytes);
@@ -144,6 +148,7 @@ CWA_API int cwa_wave_state(cwa_ctx* ctx, cwa_wave w, int read_index[2], int* wri
 CWA_API int cwa_wave_bind_texture_unit(cwa_ctx* ctx, cwa_wave w);
 /* image by physical index 0..2 (ImageTexture), or by role: 0 newest, 1 previous, 2 next output */
 CWA_API int cwa_wave_read_image(cwa_ctx* ctx, cwa_wave w, int image, float* host);       /* synchronises */
+CWA_API int cwa_wave_read_image_async(cwa_ctx* ctx, cwa_wave w, int image, float* host); /* enqueued only: valid after cwa_synchronize */
 CWA_API int cwa_wave_write_image(cwa_ctx* ctx, cwa_wave w, int image, const float* host);
 CWA_API int cwa_wave_role_image(cwa_ctx* ctx, cwa_wave w, int role, int* image);
 CWA_API int cwa_wave_image_buffer(cwa_ctx* ctx, cwa_wave w, int image, cwa_buf* out);    /* GetTexture() for interop */

@@ -155,3 +155,50 @@ def test_fused_integrate_tail_equals_separate_kernels(cwa, tuned, oracle, cluste
             assert_close(b["pos"][:, :3], ref["pos"][:, :3], scale=1e-3, rtol=1e-3, what="pos vs oracle")
     finally:
         tuned.set_tuning(fused_integrate=0)
+
+
+@pytest.mark.parametrize("coupling", ["as_shipped", "latest"])
+@pytest.mark.parametrize("cluster", [False, True])
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_pipelined_frames_equal_the_plain_sequence(cwa, tuned, oracle, mode, cluster, coupling):
+    """cwa_coupled_step(K > 1) pipelines the frames of one call (wave stencil of frame f on a side stream next to
+    the grid build of frame f+1; integrate of frame f counts the particles into the cells of frame f+1).  Nothing
+    an application can read afterwards may differ from the plain sequence: particle records, all three wave
+    levels and the triple-buffer state, and every grid array -- bit for bit."""
+    cpl = cwa.COUPLING_AS_SHIPPED if coupling == "as_shipped" else cwa.COUPLING_LATEST
+    frames = 7
+
+    def run(pipeline):
+        tuned.set_tuning(nb_config=7, pipeline=pipeline)
+        prm, p, tex, sph = _scene(cwa, tuned, oracle, "h+", cluster=cluster)
+        p["pos"][5, 0] = np.nan                    # never inserted
+        p["vel"][::11, :3] *= np.float32(40.0)     # some particles change cells every frame
+        sph.upload(p)
+        wave = cwa.StencilImage2DTripleBuffered(tuned, 96, 64, 1, cwa.WAVE_COUPLED)
+        sph.coupled_step(wave, frames, cpl)
+        g = sph.grid
+        ncell = g.num_cells_total
+        out = dict(p=sph.download(), state=wave.state(), waves=[wave.read_image(i) for i in range(3)],
+                   counter=g.read(cwa.GRID_COUNTER, ncell), offset=g.read(cwa.GRID_OFFSET, ncell + 1),
+                   cell_of=g.read(cwa.GRID_CELL_OF, p.size))
+        n_ins = int(out["offset"][-1])
+        out["index"] = g.read(cwa.GRID_INDEX_LIST, n_ins)
+        # one more call continues from the pipelined state exactly like from the plain one
+        sph.coupled_step(wave, 2, cpl)
+        out["p2"] = sph.download()
+        return out
+
+    try:
+        a = run(0)
+        b = run(mode)
+    finally:
+        tuned.set_tuning(pipeline=3)
+    assert a["state"] == b["state"]
+    for i in range(3):
+        assert np.array_equal(a["waves"][i].view(np.uint32), b["waves"][i].view(np.uint32)), f"wave image {i}"
+    for k in ("counter", "offset", "cell_of", "index"):
+        assert np.array_equal(a[k], b[k]), k
+    assert int(a["counter"].sum()) == int(a["offset"][-1])
+    for k in ("p", "p2"):
+        for f in ("pos", "vel", "force", "extras"):
+            assert np.array_equal(a[k][f].view(np.uint32), b[k][f].view(np.uint32)), f"{k}.{f}"
