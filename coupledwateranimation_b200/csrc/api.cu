@@ -279,6 +279,7 @@ extern "C" int cwa_buffer_sub_data(cwa_ctx* ctx, cwa_buf b, size_t off, size_t b
     // a particle upload invalidates any cell-ordered snapshot built from this buffer
     for (auto& s : ctx->sphs) if (s.live && s.particles == b) s.snapshot_valid = false;
     for (int i = 0; i < 8; i++) if (ctx->ubo_binding[i] == b) ctx->params_epoch++;      // a parameter block changed
+    wave_touch_buffer(ctx, b, false);                                                    // a wave image written through its buffer handle
     return 0;
 }
 
@@ -312,6 +313,7 @@ extern "C" int cwa_buffer_copy(cwa_ctx* ctx, cwa_buf src, cwa_buf dst, size_t so
     CWA_CHECK(soff + bytes <= s->bytes && doff + bytes <= d->bytes, "cwa_buffer_copy: range outside buffer");
     CWA_CUDA(cudaMemcpyAsync((char*)d->ptr + doff, (const char*)s->ptr + soff, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     for (int i = 0; i < 8; i++) if (ctx->ubo_binding[i] == dst) ctx->params_epoch++;
+    wave_touch_buffer(ctx, dst, false);
     return 0;
 }
 
@@ -338,6 +340,7 @@ extern "C" int cwa_buffer_device_ptr(cwa_ctx* ctx, cwa_buf b, void** ptr, size_t
     CWA_CHECK(o, "invalid buffer handle %d", b);
     if (ptr) *ptr = o->ptr;
     if (bytes) *bytes = o->bytes;
+    wave_touch_buffer(ctx, b, true);              // a raw pointer to a wave image leaves the library: its contents can change unseen
     return 0;
 }
 

@@ -57,14 +57,28 @@ grid_hash_count_kernel(const char* __restrict__ particles, int stride_bytes, int
 // ---------------------------------------------------------------------------------------------
 // (2) decoupled look-back exclusive scan (single pass, any n)
 // ---------------------------------------------------------------------------------------------
-#ifndef CWA_SCAN_THREADS
-#define CWA_SCAN_THREADS 256
-#endif
-constexpr int SCAN_THREADS = CWA_SCAN_THREADS;
-constexpr int SCAN_ITEMS = 16;
-constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;   // 4096 ints per tile
+// Tile shapes (cwa_set_tuning "scan_config"): the look-back is a serial chain over the tiles in front of a tile, 32 per step, and with
+// a few million cells every tile of the grid is resident at once -- so the chain length, not the bandwidth, sets the time.  Large tiles
+// (16 K items: 279 tiles for the 4.6 M cells of C4 instead of 1116) shorten it 4x.
+//   0: 256 threads x 16 items, blocked (thread t owns 16 consecutive items)
+//   1: 512 x 32 blocked
+//   2: 512 x 32 warp-striped (a warp owns 1024 consecutive items; lane l loads the int4 at 4*(32 q + l), q = 0..7: every load
+//      instruction of a warp covers 512 contiguous bytes)
+//   3: 1024 x 16 warp-striped
+constexpr int SCAN_MIN_TILE = 4096;                     // smallest tile of any configuration: sizes the tile-state arrays
+static int g_scan_config = -1;
+static int scan_config()
+{
+    if (g_scan_config < 0) {
+        const char* e = getenv("CWA_SCAN_CONFIG");
+        const int v = e ? atoi(e) : 2;
+        g_scan_config = (v < 0 || v > 3) ? 2 : v;
+    }
+    return g_scan_config;
+}
+int scan_set_config(int v) { if (v < 0 || v > 3) return -1; g_scan_config = v; return 0; }
 
-size_t scan_num_tiles(int n) { return (size_t)((n + SCAN_TILE - 1) / SCAN_TILE); }
+size_t scan_num_tiles(int n) { return (size_t)((n + SCAN_MIN_TILE - 1) / SCAN_MIN_TILE); }
 
 // tile_state word: [63:62] flag (0 invalid, 1 aggregate, 2 inclusive prefix) | [31:0] value
 __device__ __forceinline__ unsigned long long scan_pack(unsigned flag, int v)
@@ -72,107 +86,162 @@ __device__ __forceinline__ unsigned long long scan_pack(unsigned flag, int v)
     return ((unsigned long long)flag << 62) | (unsigned long long)(unsigned)v;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS)
+template <int THREADS, int ITEMS, bool STRIPED>
+__global__ void __launch_bounds__(THREADS)
 scan_lookback_kernel(const int* __restrict__ in, int* __restrict__ out, int n, int write_total,
                      int* __restrict__ ticket, volatile unsigned long long* __restrict__ tile_state)
 {
+    constexpr int TILE = THREADS * ITEMS;
+    constexpr int WARPS = THREADS / 32;
+    constexpr int Q = ITEMS / 4;
     __shared__ int s_tile;
-    __shared__ int s_warp[SCAN_THREADS / 32];
-    __shared__ int s_prefix;
+    __shared__ int s_warp[WARPS];
+    __shared__ int s_excl[WARPS];
+    __shared__ int s_flag[WARPS];
+    __shared__ int s_prefix, s_done, s_aggregate, s_prefix_final;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(ticket, 1);        // tiles are handed out in start order
     __syncthreads();
     const int tile = s_tile;
-    const long long base = (long long)tile * SCAN_TILE + (long long)tid * SCAN_ITEMS;
+    const long long tile_base = (long long)tile * TILE;
+    // first item of this thread's q-th int4: blocked = consecutive per thread, striped = consecutive per warp instruction
+    const long long base = STRIPED ? tile_base + (long long)wid * (32 * ITEMS) + 4 * lane
+                                   : tile_base + (long long)tid * ITEMS;
+    constexpr int QSTRIDE = STRIPED ? 128 : 4;
+    const bool full_tile = tile_base + TILE <= n;
 
-    int v[SCAN_ITEMS];
-    if (base + SCAN_ITEMS <= n) {
-        const int4* p = reinterpret_cast<const int4*>(in + base);
+    int v[ITEMS];
+    if (full_tile) {
 #pragma unroll
-        for (int q = 0; q < SCAN_ITEMS / 4; q++) {
-            int4 t = __ldg(p + q);
+        for (int q = 0; q < Q; q++) {
+            const int4 t = __ldg(reinterpret_cast<const int4*>(in + base + q * QSTRIDE));
             v[4 * q + 0] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
         }
     } else {
 #pragma unroll
-        for (int q = 0; q < SCAN_ITEMS; q++) v[q] = (base + q < n) ? __ldg(in + base + q) : 0;
-    }
-    int tsum = 0;
+        for (int q = 0; q < Q; q++)
 #pragma unroll
-    for (int q = 0; q < SCAN_ITEMS; q++) tsum += v[q];
-
-    // block-wide exclusive scan of the thread sums
-    int incl = tsum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
-    }
-    if (lane == 31) s_warp[wid] = incl;
-    __syncthreads();
-    if (wid == 0) {
-        int w = (lane < SCAN_THREADS / 32) ? s_warp[lane] : 0;
-        int wi = w;
-#pragma unroll
-        for (int d = 1; d < SCAN_THREADS / 32; d <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, wi, d);
-            if (lane >= d) wi += t;
-        }
-        if (lane < SCAN_THREADS / 32) s_warp[lane] = wi - w;          // exclusive warp offsets
-        const int aggregate = __shfl_sync(0xffffffffu, wi, SCAN_THREADS / 32 - 1);
-
-        // publish, then look back over the predecessors 32 tiles at a time
-        int exclusive = 0;
-        if (tile == 0) {
-            if (lane == 0) tile_state[0] = scan_pack(2u, aggregate);
-        } else {
-            if (lane == 0) tile_state[tile] = scan_pack(1u, aggregate);
-            int look = tile - 1;
-            while (true) {
-                const int idx = look - lane;
-                unsigned long long st = scan_pack(2u, 0);              // tiles before 0: prefix 0
-                if (idx >= 0) {
-                    do { st = tile_state[idx]; } while ((st >> 62) == 0ull);
-                }
-                const unsigned flag = (unsigned)(st >> 62);
-                const int val = (int)(unsigned)(st & 0xffffffffull);
-                const unsigned has_prefix = __ballot_sync(0xffffffffu, flag == 2u);
-                // sum the values from lane 0 up to and including the first lane holding a prefix
-                const int first = has_prefix ? (__ffs(has_prefix) - 1) : 31;
-                int contrib = (lane <= first) ? val : 0;
-#pragma unroll
-                for (int d = 16; d >= 1; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
-                exclusive += contrib;
-                if (has_prefix) break;
-                look -= 32;
+            for (int e = 0; e < 4; e++) {
+                const long long idx = base + q * QSTRIDE + e;
+                v[4 * q + e] = (idx < n) ? __ldg(in + idx) : 0;
             }
-            if (lane == 0) tile_state[tile] = scan_pack(2u, exclusive + aggregate);
-        }
-        if (lane == 0) s_prefix = exclusive;
     }
-    __syncthreads();
 
-    int run = s_prefix + s_warp[wid] + (incl - tsum);
-    if (base + SCAN_ITEMS <= n) {
-        int4* o = reinterpret_cast<int4*>(out + base);
+    // exclusive offset of each of the thread's int4 groups inside the warp's segment (striped) / of the thread's run (blocked)
+    int gexcl[Q];
+    int incl;            // inclusive scan of the per-thread totals across the warp, in item order
+    int tsum = 0;
+    if (STRIPED) {
+        int carry = 0;   // items of the warp's strips 0..q-1
 #pragma unroll
-        for (int q = 0; q < SCAN_ITEMS / 4; q++) {
-            int4 t;
-            t.x = run; run += v[4 * q + 0];
-            t.y = run; run += v[4 * q + 1];
-            t.z = run; run += v[4 * q + 2];
-            t.w = run; run += v[4 * q + 3];
-            o[q] = t;
+        for (int q = 0; q < Q; q++) {
+            const int g4 = v[4 * q] + v[4 * q + 1] + v[4 * q + 2] + v[4 * q + 3];
+            int sc = g4;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, sc, d);
+                if (lane >= d) sc += t;
+            }
+            gexcl[q] = carry + sc - g4;
+            carry += __shfl_sync(0xffffffffu, sc, 31);
         }
+        tsum = carry;    // the whole warp's total (same on every lane)
+        incl = carry;
     } else {
 #pragma unroll
-        for (int q = 0; q < SCAN_ITEMS; q++) {
-            if (base + q < n) out[base + q] = run;
-            run += v[q];
+        for (int q = 0; q < Q; q++) {
+            gexcl[q] = tsum;
+            tsum += v[4 * q] + v[4 * q + 1] + v[4 * q + 2] + v[4 * q + 3];
+        }
+        incl = tsum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
         }
     }
-    // the thread that owns element n-1 also writes the grand total to out[n]
-    if (write_total && base <= (long long)n - 1 && (long long)n - 1 < base + SCAN_ITEMS) out[n] = run;
+    if (lane == 31) s_warp[wid] = incl;                 // warp total
+    __syncthreads();
+    int warp_excl = 0;
+    if (wid == 0) {
+        const int w = (lane < WARPS) ? s_warp[lane] : 0;
+        int wi = w;
+#pragma unroll
+        for (int d = 1; d < WARPS; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += t;
+        }
+        if (lane < WARPS) s_excl[lane] = wi - w;          // exclusive warp offsets
+        const int aggregate = __shfl_sync(0xffffffffu, wi, WARPS - 1);
+        if (lane == 0) {
+            s_aggregate = aggregate;
+            tile_state[tile] = scan_pack(tile == 0 ? 2u : 1u, aggregate);      // publish first, then look back
+        }
+    }
+    __syncthreads();
+    warp_excl = s_excl[wid];
+
+    // Look-back over the predecessors, THREADS tiles per step (one tile state per thread): with every tile of a few-million-cell
+    // grid resident at once the look-back is a pure latency chain, so its length is what counts -- 279 tiles of 16 K items are
+    // covered in ONE step.  Per step: every thread waits for its predecessor's word, each warp reduces (values up to and including
+    // its nearest inclusive prefix | all values), thread 0 walks the warps from the nearest tile backwards.
+    if (tile > 0) {
+        int exclusive = 0;
+        int look = tile - 1;
+        while (true) {
+            const int idx = look - tid;
+            unsigned long long st = scan_pack(2u, 0);                  // tiles before 0: prefix 0
+            if (idx >= 0) {
+                do { st = tile_state[idx]; } while ((st >> 62) == 0ull);
+            }
+            const unsigned flag = (unsigned)(st >> 62);
+            const int val = (int)(unsigned)(st & 0xffffffffull);
+            const unsigned has_prefix = __ballot_sync(0xffffffffu, flag == 2u);
+            const int first = has_prefix ? (__ffs(has_prefix) - 1) : 31;
+            int contrib = (lane <= first) ? val : 0;
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+            __syncthreads();                                           // s_warp / s_flag of the previous step are consumed
+            if (lane == 0) { s_warp[wid] = contrib; s_flag[wid] = has_prefix != 0u; }
+            __syncthreads();
+            if (tid == 0) {
+                int acc = 0, done = 0;
+                for (int wq = 0; wq < WARPS; wq++) { acc += s_warp[wq]; if (s_flag[wq]) { done = 1; break; } }
+                s_prefix = acc; s_done = done;
+            }
+            __syncthreads();
+            exclusive += s_prefix;
+            if (s_done) break;
+            look -= THREADS;
+        }
+        if (tid == 0) tile_state[tile] = scan_pack(2u, exclusive + s_aggregate);
+        s_prefix_final = exclusive;      // every thread holds the same value; written by all, read by all after the barrier below
+    } else if (tid == 0) {
+        s_prefix_final = 0;
+    }
+    __syncthreads();
+
+    const int thread_base = s_prefix_final + warp_excl + (STRIPED ? 0 : (incl - tsum));
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        int run = thread_base + gexcl[q];
+        int4 t;
+        t.x = run; run += v[4 * q + 0];
+        t.y = run; run += v[4 * q + 1];
+        t.z = run; run += v[4 * q + 2];
+        t.w = run; run += v[4 * q + 3];
+        const long long idx = base + q * QSTRIDE;
+        if (full_tile) {
+            *reinterpret_cast<int4*>(out + idx) = t;
+        } else {
+            if (idx + 0 < n) out[idx + 0] = t.x;
+            if (idx + 1 < n) out[idx + 1] = t.y;
+            if (idx + 2 < n) out[idx + 2] = t.z;
+            if (idx + 3 < n) out[idx + 3] = t.w;
+        }
+        // the thread whose group holds element n-1 also writes the grand total to out[n] (elements past n are zeros)
+        if (write_total && idx <= (long long)n - 1 && (long long)n - 1 < idx + 4) out[n] = run;
+    }
 }
 
 int scan_exclusive_launch(cwa_ctx* ctx, const int* in, int* out, int n, int* ticket, unsigned long long* tile_state)
@@ -180,9 +249,13 @@ int scan_exclusive_launch(cwa_ctx* ctx, const int* in, int* out, int n, int* tic
     // n < 0 encodes "do not write the total at out[|n|]"
     const int write_total = n > 0;
     if (n < 0) n = -n;
-    const int tiles = (int)scan_num_tiles(n);
-    { KScope k(ctx, KID_SCAN);
-      scan_lookback_kernel<<<tiles, SCAN_THREADS, 0, ctx->stream>>>(in, out, n, write_total, ticket, tile_state); }
+    KScope k(ctx, KID_SCAN);
+    switch (scan_config()) {
+    case 0: scan_lookback_kernel<256, 16, false><<<ceil_div(n, 256 * 16), 256, 0, ctx->stream>>>(in, out, n, write_total, ticket, tile_state); break;
+    case 1: scan_lookback_kernel<512, 32, false><<<ceil_div(n, 512 * 32), 512, 0, ctx->stream>>>(in, out, n, write_total, ticket, tile_state); break;
+    case 3: scan_lookback_kernel<1024, 16, true><<<ceil_div(n, 1024 * 16), 1024, 0, ctx->stream>>>(in, out, n, write_total, ticket, tile_state); break;
+    default: scan_lookback_kernel<512, 32, true><<<ceil_div(n, 512 * 32), 512, 0, ctx->stream>>>(in, out, n, write_total, ticket, tile_state); break;
+    }
     CWA_CUDA(cudaGetLastError());
     return 0;
 }

@@ -56,6 +56,12 @@ struct TexView {
     int w, h, ch;
     int row0, h_global;
     const float* last_row;
+    // local single-channel fast path (tex_view_is_local): texel (i, j) = tdata[i * tsi + j * tsj].  Row-major as stored
+    // (tsi = 1, tsj = w), or the TRANSPOSED sampling copy (tsi = h, tsj = 1): the uniform grid runs fastest along z, which
+    // maps to the texture's t axis, so a warp of cell-ordered particles walks down a texture COLUMN -- 32 rows = 32 cache
+    // lines per tap in the row-major image, a handful in the transposed one.
+    const float* tdata;
+    int tsi, tsj;
 };
 
 // UniformGridInfo as the kernels see it.
@@ -124,6 +130,12 @@ struct WaveObj {
     CUtensorMap tmap_halo[3];
     CUtensorMap tmap_core[3];
     bool tma_ok = false;
+    // transposed sampling copy of ONE image (the one the SPH passes sample), refreshed when that image changed
+    unsigned long long version[3] = {1, 1, 1};    // bumped by every library path that writes image i
+    float* imageT = nullptr;
+    int    imageT_of = -1;
+    unsigned long long imageT_version = 0;
+    bool   raw_exposed = false;                   // an application holds a raw pointer to an image: contents can change unseen
 };
 
 struct SphObj {
@@ -232,6 +244,7 @@ ParamPtrs  current_params(cwa_ctx* ctx);
 int  scan_exclusive_launch(cwa_ctx* ctx, const int* in, int* out, int n, int* ticket,
                            unsigned long long* tile_state);          // grid.cu; out has n+1 entries
 size_t scan_num_tiles(int n);
+int  scan_set_config(int v);                                           // tile shape of the look-back scan (0..3)
 struct GridBuildOpts {
     bool canonical_order = true;       // false: stop after the arrival-order insert (the caller's fused kernel ranks and reorders in one pass)
     // count-ahead: the counter already holds this build's counts; cell id and arrival rank of the particle that sat in
@@ -242,6 +255,9 @@ struct GridBuildOpts {
 };
 int  grid_build_internal(cwa_ctx* ctx, GridObj* g, const void* particles, int stride_bytes, int n, const GridBuildOpts& opts = GridBuildOpts());
 TexView wave_tex_view(cwa_ctx* ctx, cwa_wave w, int image);           // wave.cu
+int  wave_sampling_copy(cwa_ctx* ctx, cwa_wave w, int image, TexView* tex);   // points tex->tdata at the (refreshed) transposed copy when it pays
+int  wave_set_transpose(int on);
+void wave_touch_buffer(cwa_ctx* ctx, cwa_buf b, bool raw);             // a buffer was written through the Buffer API / its raw pointer handed out
 int  wave_step_internal(cwa_ctx* ctx, WaveObj* w);
 int  wave_dispatch_mode(cwa_ctx* ctx, WaveObj* w, int mode);           // kernel for uMode on units 0/1/2, no rotation                   // one EVOLVE dispatch + PingPong
 int  sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which /*bit0 rho, bit1 force, bit2 integrate*/, bool count_ahead = false);
@@ -383,9 +399,10 @@ __device__ __forceinline__ float cwa_tex_bilinear_local(const TexView& t, float 
     const float wm = fW - 1.0f, hm = fH - 1.0f;
     const int i0 = (int)fminf(fmaxf(fu, 0.0f), wm), i1 = (int)fminf(fmaxf(fu + 1.0f, 0.0f), wm);
     const int j0 = (int)fminf(fmaxf(fv, 0.0f), hm), j1 = (int)fminf(fmaxf(fv + 1.0f, 0.0f), hm);
-    const float* p0 = t.data + j0 * t.w;
-    const float* p1 = t.data + j1 * t.w;
-    const float t00 = __ldg(p0 + i0), t10 = __ldg(p0 + i1), t01 = __ldg(p1 + i0), t11 = __ldg(p1 + i1);
+    const float* p0 = t.tdata + j0 * t.tsj;
+    const float* p1 = t.tdata + j1 * t.tsj;
+    const int o0 = i0 * t.tsi, o1 = i1 * t.tsi;
+    const float t00 = __ldg(p0 + o0), t10 = __ldg(p0 + o1), t01 = __ldg(p1 + o0), t11 = __ldg(p1 + o1);
     const float r0 = __fadd_rn(t00, __fmul_rn(a, __fsub_rn(t10, t00)));
     const float r1 = __fadd_rn(t01, __fmul_rn(a, __fsub_rn(t11, t01)));
     return __fadd_rn(r0, __fmul_rn(b, __fsub_rn(r1, r0)));

@@ -1151,6 +1151,8 @@ extern "C" int cwa_set_tuning(cwa_ctx* ctx, const char* key, int value)
     else if (k == "nb_cap_f") { CWA_CHECK(value >= 0 && value <= FORCE_CAP_MAX, "nb_cap_f %d out of range", value); g_tune.cap_f = value; }
     else if (k == "fused_order") { g_tune.fused_order = value ? 1 : 0; }
     else if (k == "fused_integrate") { g_tune.fused_integrate = value ? 1 : 0; }
+    else if (k == "wave_transpose") { wave_set_transpose(value); }
+    else if (k == "scan_config") { CWA_CHECK(scan_set_config(value) == 0, "scan_config %d out of range", value); }
     else if (k == "pipeline") { CWA_CHECK(value >= 0 && value <= 3, "pipeline %d out of range", value); g_tune.pipeline = value; }
     else CWA_CHECK(false, "cwa_set_tuning: unknown key '%s'", key);
     return 0;
@@ -1325,12 +1327,14 @@ int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which, bool co
     const int cfg = nb_config();
     const bool fused_tail = full && cfg == 7 && fused_integrate();   // the force kernels finish the particle (epilogue + integrate + write-back)
     count_ahead = count_ahead && full && !fused_tail;
+    if (!(which & 1)) CWA_TRY(wave_sampling_copy(ctx, s->wave, s->wave_image, &tex));
     if (which & 1) {
         CWA_TRY(sph_snapshot(ctx, s, count_ahead));                // positions changed since the last frame
         if (s->wait_before_sampling) {                             // the wave level this frame samples may still be in flight on the side stream
             CWA_CUDA(cudaStreamWaitEvent(ctx->stream, s->wait_before_sampling, 0));
             s->wait_before_sampling = nullptr;
         }
+        CWA_TRY(wave_sampling_copy(ctx, s->wave, s->wave_image, &tex));   // transposed copy of the sampled level (rebuilt only when it changed)
         switch (cfg) {
         case 1: CWA_TRY((launch_density<128, 2>(ctx, s, g, tex))); break;
         case 2: CWA_TRY((launch_density<64, 4>(ctx, s, g, tex))); break;

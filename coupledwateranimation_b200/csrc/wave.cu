@@ -264,9 +264,65 @@ wave_init_from_texture_kernel(float* __restrict__ out, int W, int H, int ch, con
     if (ch == 4) { o[1] = v.y; o[2] = v.z; o[3] = v.w; }
 }
 
+// Transposed sampling copy: out[x * H + y] = in[y * W + x] (32 x 32 tiles through shared memory, both sides coalesced)
+__global__ void __launch_bounds__(256)
+wave_transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int W, int H)
+{
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int x = x0 + tx, y = y0 + r;
+        if (x < W && y < H) tile[r][tx] = __ldg(in + (size_t)y * W + x);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int x = x0 + r, y = y0 + tx;
+        if (x < W && y < H) out[(size_t)x * H + y] = tile[tx][r];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host object
 // ---------------------------------------------------------------------------------------------
+static int g_wave_transpose = -1;
+static bool wave_transpose_on()
+{
+    if (g_wave_transpose < 0) { const char* e = getenv("CWA_WAVE_TRANSPOSE"); g_wave_transpose = e ? (atoi(e) != 0) : 1; }
+    return g_wave_transpose != 0;
+}
+int wave_set_transpose(int on) { g_wave_transpose = on ? 1 : 0; return 0; }
+
+void wave_touch_buffer(cwa_ctx* ctx, cwa_buf b, bool raw)
+{
+    for (auto& w : ctx->waves) {
+        if (!w.live) continue;
+        for (int i = 0; i < 3; i++)
+            if (w.image_buf[i] == b) { w.version[i]++; if (raw) w.raw_exposed = true; }
+    }
+}
+
+// The SPH passes sample ONE image per frame.  When the field is local, scalar and large enough for the access pattern to
+// matter, they read a transposed copy (TexView::tdata); it is rebuilt only when the sampled image changed -- once every three
+// frames under the as-shipped binding schedule.  Same texels, same arithmetic: results are bit-identical.
+int wave_sampling_copy(cwa_ctx* ctx, cwa_wave h, int image, TexView* tex)
+{
+    WaveObj* w = get_wave(ctx, h);
+    if (!w || image < 0 || image >= 3 || !wave_transpose_on() || w->raw_exposed) return 0;
+    if (!tex_view_is_local(*tex) || tex->data != w->image[image] || (long long)w->w * w->h < 256 * 256) return 0;
+    if (w->imageT == nullptr) CWA_CUDA(cudaMalloc(&w->imageT, (size_t)w->w * w->h * 4));
+    if (w->imageT_of != image || w->imageT_version != w->version[image]) {
+        KScope k(ctx, KID_OTHER);
+        wave_transpose_kernel<<<dim3(ceil_div(w->w, 32), ceil_div(w->h, 32)), 256, 0, ctx->stream>>>(w->image[image], w->imageT, w->w, w->h);
+        CWA_CUDA(cudaGetLastError());
+        w->imageT_of = image; w->imageT_version = w->version[image];
+    }
+    tex->tdata = w->imageT; tex->tsi = w->h; tex->tsj = 1;
+    return 0;
+}
+
 static int image_with_unit(const WaveObj* w, int u)
 {
     for (int i = 0; i < 3; i++) if (w->unit[i] == u) return i;
@@ -311,6 +367,7 @@ static int wave_alloc_images(cwa_ctx* ctx, WaveObj* w)
     for (int i = 0; i < 3; i++) {
         CWA_CUDA(cudaMalloc(&w->image[i], bytes));
         CWA_CUDA(cudaMemsetAsync(w->image[i], 0, bytes, ctx->stream));   // glTextureStorage2D: treat as zero
+        w->version[i]++;
         if (w->image_buf[i] >= 0 && get_buffer(ctx, w->image_buf[i])) {
             BufferObj* b = get_buffer(ctx, w->image_buf[i]);
             b->ptr = w->image[i]; b->bytes = bytes;
@@ -337,6 +394,7 @@ int wave_dispatch_mode(cwa_ctx* ctx, WaveObj* w, int mode)
     const float4* attr = wave_attr_ptr(ctx, w);
     if (mode == CWA_MODE_TEST) return 0;                           // MODE_TEST does nothing (wave_comp.glsl:71-72)
     CWA_CHECK(mode == CWA_MODE_INIT || mode == CWA_MODE_EVOLVE, "wave dispatch: unsupported uMode %d", mode);
+    w->version[outi]++;
     KScope kscope(ctx, mode == CWA_MODE_EVOLVE ? KID_WAVE : KID_OTHER);
     if (mode == CWA_MODE_INIT) {
         wave_init_kernel<<<ggrid, gblock, 0, ctx->stream>>>(w->image[outi], w->w, w->h, w->ch, attr, w->variant, w->row0, w->h_global);
@@ -371,11 +429,12 @@ int wave_step_internal(cwa_ctx* ctx, WaveObj* w)
 
 TexView wave_tex_view(cwa_ctx* ctx, cwa_wave h, int image)
 {
-    TexView t{nullptr, 1, 1, 1, 0, 1, nullptr};
+    TexView t{nullptr, 1, 1, 1, 0, 1, nullptr, nullptr, 1, 1};
     WaveObj* w = get_wave(ctx, h);
     if (w && image >= 0 && image < 3) {
         t.data = w->image[image]; t.w = w->w; t.h = w->h; t.ch = w->ch;
         t.row0 = w->row0; t.h_global = w->h_global; t.last_row = w->last_row[image];
+        t.tdata = t.data; t.tsi = 1; t.tsj = w->w;
     }
     return t;
 }
@@ -409,6 +468,7 @@ extern "C" int cwa_wave_destroy(cwa_ctx* ctx, cwa_wave h)
         if (BufferObj* b = get_buffer(ctx, w->image_buf[i])) b->live = false;
     }
     cudaFree(w->simp_params);
+    cudaFree(w->imageT); w->imageT = nullptr;
     for (int i = 0; i < 3; i++) {
         if (w->last_row[i]) cudaFree(w->last_row[i]);
         if (BufferObj* b = get_buffer(ctx, w->last_row_buf[i])) b->live = false;
@@ -438,6 +498,7 @@ extern "C" int cwa_wave_reinit_from_texture(cwa_ctx* ctx, cwa_wave h, const floa
     CWA_CUDA(cudaMalloc(&dtex, bytes));
     CWA_CUDA(cudaMemcpyAsync(dtex, rgba, bytes, cudaMemcpyHostToDevice, ctx->stream));
     const int outi = image_with_unit(w, 2);
+    w->version[outi]++;
     const dim3 gblock(256), ggrid(ceil_div(w->w, 32), ceil_div(w->h, 8));
     { KScope k(ctx, KID_OTHER);
       wave_init_from_texture_kernel<<<ggrid, gblock, 0, ctx->stream>>>(w->image[outi], w->w, w->h, w->ch, dtex, tw, th,
@@ -490,6 +551,7 @@ extern "C" int cwa_wave_resize(cwa_ctx* ctx, cwa_wave h, int nw, int nh)
     CWA_CHECK(nw >= 1 && nh >= 1, "cwa_wave_resize: bad size");
     CWA_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < 3; i++) { cudaFree(w->image[i]); w->image[i] = nullptr; }
+    cudaFree(w->imageT); w->imageT = nullptr; w->imageT_of = -1;
     CWA_CHECK(w->row0 == 0 && w->h == w->h_global, "cwa_wave_resize: not supported on a row-block wave object");
     w->w = nw; w->h = nh; w->h_global = nh;
     return wave_alloc_images(ctx, w);                                // ImageTexture::Resize: new storage, contents cleared
@@ -548,6 +610,7 @@ extern "C" int cwa_wave_write_image(cwa_ctx* ctx, cwa_wave h, int image, const f
     const int i = resolve_image(w, image);
     CWA_CHECK(i >= 0, "image index %d out of range", image);
     CWA_CUDA(cudaMemcpyAsync(w->image[i], host, (size_t)w->w * w->h * w->ch * 4, cudaMemcpyHostToDevice, ctx->stream));
+    w->version[i]++;
     return 0;
 }
 

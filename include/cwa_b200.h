@@ -99,7 +99,11 @@ CWA_API int  cwa_profile_end(cwa_ctx* ctx, float* ms, int* launches, int cap);  
  *       measured 6 us faster per C4 frame while few targets are queued, 120 us slower once clumps dominate),
  *       "pipeline" (frames of ONE cwa_coupled_step call; bit 0: the wave stencil of frame f runs on a side stream next to
  *       the grid build of frame f+1, bit 1: the integrate pass of frame f does the cell hash + count of frame f+1;
- *       default 3; results and every readable array are bit-identical to 0). */
+ *       default 3; results and every readable array are bit-identical to 0),
+ *       "scan_config" (tile shape of the look-back scan: 0 = 256 threads x 16 items, 1 = 512 x 32, 2 = 512 x 32 with
+ *       warp-striped loads (default), 3 = 1024 x 16 warp-striped),
+ *       "wave_transpose" (1, default: the SPH passes sample a transposed copy of the bound wave level -- the grid runs fastest along
+ *       z = the texture's t axis -- rebuilt only when that level changed; same texels, bit-identical results). */
 CWA_API int  cwa_set_tuning(cwa_ctx* ctx, const char* key, int value);
 
 /* ---- Buffer: Init / BufferSubData / BindBufferBase / DebugRead*  (SphWave2D/Buffer.cpp:5-83) -- */

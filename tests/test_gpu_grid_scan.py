@@ -32,6 +32,26 @@ def test_scan_random_counts_any_length(cwa, ctx, oracle, n):
     assert out[n] == int(x.sum())
 
 
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3])
+@pytest.mark.parametrize("n", [1, 5, 127, 4096, 16383, 16384, 16385, 50001, 3 * 16384, (1 << 22) + 77])
+def test_scan_every_tile_shape(cwa, ctx, oracle, cfg, n):
+    """cwa_set_tuning("scan_config"): blocked and warp-striped tiles of 4 K and 16 K items -- same integers."""
+    ctx.set_tuning(scan_config=cfg)
+    try:
+        rng = np.random.default_rng(1000 * cfg + n)
+        x = rng.integers(0, 9, n, dtype=np.int32)
+        x[rng.integers(0, n, max(1, n // 50))] = 700          # a few crowded cells
+        out = _scan(cwa, ctx, x)
+        ref = oracle.scan_exclusive(x)
+        assert np.array_equal(out[:n], ref)
+        assert out[n] == int(x.sum())
+        b = cwa.Buffer(ctx, data=x)
+        ctx.scan_exclusive(b, b, n)                           # in place, no total slot
+        assert np.array_equal(b.read(np.int32, n), ref)
+    finally:
+        ctx.set_tuning(scan_config=2)
+
+
 def test_scan_matches_reference_blelloch_on_pow2(cwa, ctx, oracle):
     x = np.random.default_rng(3).integers(0, 50, 1 << 14, dtype=np.int32)
     assert np.array_equal(_scan(cwa, ctx, x)[:-1], oracle.scan_blelloch(x))

@@ -202,3 +202,42 @@ def test_pipelined_frames_equal_the_plain_sequence(cwa, tuned, oracle, mode, clu
     for k in ("p", "p2"):
         for f in ("pos", "vel", "force", "extras"):
             assert np.array_equal(a[k][f].view(np.uint32), b[k][f].view(np.uint32)), f"{k}.{f}"
+
+
+@pytest.mark.parametrize("coupling", ["as_shipped", "latest"])
+def test_transposed_sampling_copy_is_bit_identical(cwa, tuned, oracle, coupling):
+    """The SPH passes may sample a transposed copy of the bound wave level (the grid runs fastest along z = the
+    texture's t axis).  Same texels, same arithmetic: every particle bit must agree with direct sampling, across
+    wave steps, image uploads and buffer-level writes that change the sampled level."""
+    cpl = cwa.COUPLING_AS_SHIPPED if coupling == "as_shipped" else cwa.COUPLING_LATEST
+
+    def run(on):
+        tuned.set_tuning(nb_config=7, wave_transpose=on, pipeline=3)
+        prm, p, tex, sph = _scene(cwa, tuned, oracle, "h+")
+        wave = cwa.StencilImage2DTripleBuffered(tuned, 320, 272, 1, cwa.WAVE_COUPLED)   # non-square, above the 256^2 threshold
+        for i in range(3):
+            wave.write_image(i, smooth_field(272, 320, 1, amp=0.01 * (i + 1)))
+        wave.bind_texture_unit()
+        outs = []
+        sph.coupled_step(wave, 5, cpl)
+        outs.append(sph.download())
+        st = wave.state()
+        bound = st["tex_unit0"] if st["tex_unit0"] >= 0 else wave.role_image(0)
+        wave.write_image(bound, smooth_field(272, 320, 1, amp=0.025))      # the sampled level changes behind the copy
+        sph.coupled_step(wave, 1, cpl)
+        outs.append(sph.download())
+        sph.bind_wave(wave, wave.role_image(0))
+        sph.rho_pres(); sph.force(); sph.integrate()          # separately dispatched passes sample the same copy
+        outs.append(sph.download())
+        outs.append(wave.read_role(0))
+        return outs
+
+    try:
+        a = run(0)
+        b = run(1)
+    finally:
+        tuned.set_tuning(wave_transpose=1)
+    for k in range(3):
+        for f in ("pos", "vel", "force", "extras"):
+            assert np.array_equal(a[k][f].view(np.uint32), b[k][f].view(np.uint32)), f"stage {k} {f}"
+    assert np.array_equal(a[3].view(np.uint32), b[3].view(np.uint32))
