@@ -154,15 +154,30 @@ def build_scene(cwa, ctx):
 
 
 def scaled_scene(world: int):
-    """The workload of `--gpus world`: C4 itself for 1 GPU, C4 grown by sqrt(world) in x and z otherwise (weak scaling)."""
-    if world <= 1:
-        return dict(nx=NX, ny=NY, nz=NZ, wave=WAVE, uv=UV_SCALE, box=BOX_UPPER[0], gmin=GRID_MIN, gmax=GRID_MAX, gn=GRID_N)
+    """The workload of `--gpus world` (weak scaling): C4 grown by sqrt(world) in x and z -- lattice, tank, uniform grid and wave field
+    (texel size, cell size and lattice pitch are C4's) -- with ONE constant adjusted: force_comp.glsl:103-104 adds
+    torque = 0.25 * cross(pos, force_prev) to every particle, a feedback on last frame's force whose gain 0.25 * |pos| grows with the
+    distance from the origin.  C4's far corner sits at gain 1.36 and survives; in a tank sqrt(2) wider the sheet blows up within 20
+    frames (|v| ~ 1e6, a fifth of the particles NaN in two corner cells: tools/blast_probe.py), which would benchmark the NaN
+    handling, not the simulation step.  So torque_coeff = 0.25 / sqrt(world) keeps the far-corner gain at C4's value."""
     import math
-    f = math.sqrt(world)
+    w = max(1, world)
+    f = math.sqrt(w)
+    if w == 1:
+        return dict(nx=NX, ny=NY, nz=NZ, wave_w=WAVE, wave_h=WAVE, uv=UV_SCALE, uv_z=0.0, torque=0.0, box_x=BOX_UPPER[0], box_z=BOX_UPPER[2],
+                    gmin=GRID_MIN, gmax=GRID_MAX, gn=GRID_N)
     n = int(round(64 * S * f))
     box = 0.55 * S * f
-    return dict(nx=n, ny=NY, nz=n, wave=int(round(WAVE * f / 4)) * 4, uv=2.0 / (S * f), box=box,
+    wave = int(round(WAVE * f / 4)) * 4
+    torque = 0.25 / f if os.environ.get("CWA_SCALE_TORQUE", "1") != "0" else 0.0
+    return dict(nx=n, ny=NY, nz=n, wave_w=wave, wave_h=wave, uv=2.0 / (S * f), uv_z=0.0, torque=torque, box_x=box, box_z=box,
                 gmin=(0.0, -0.02, 0.0), gmax=(box, GRID_MAX[1], box), gn=(int(round(GRID_N[0] * f)), GRID_N[1], int(round(GRID_N[2] * f))))
+
+
+def scaled_workload(world: int) -> str:
+    sc = scaled_scene(world)
+    return (f"C4 grown by sqrt({world}) in x and z (weak scaling; torque_coeff 0.25/sqrt({world})): {sc['nx'] * sc['ny'] * sc['nz']} particles ({sc['nx']}x{sc['ny']}x{sc['nz']} lattice), "
+            f"wave {sc['wave_w']}x{sc['wave_h']} scalar, coupling AS_SHIPPED, grid {sc['gn'][0]}x{sc['gn'][1]}x{sc['gn'][2]} {GRID_DESC}")
 
 
 def oracle_scene(O, world: int = 1):
@@ -171,10 +186,12 @@ def oracle_scene(O, world: int = 1):
     for a in range(4):
         prm.upper[a] = BOX_UPPER[a]
         prm.lower[a] = BOX_LOWER[a]
-    prm.upper[0] = prm.upper[2] = sc["box"]
+    prm.upper[0], prm.upper[2] = sc["box_x"], sc["box_z"]
     prm.uv_scale = sc["uv"]
+    prm.uv_scale_z = sc["uv_z"]
+    prm.torque_coeff = sc["torque"]
     n = sc["nx"] * sc["ny"] * sc["nz"]
-    oc = O.Coupled(n, sc["wave"], sc["wave"], 1, prm, COUPLING, grid=(sc["gmin"], sc["gmax"], sc["gn"]))
+    oc = O.Coupled(n, sc["wave_w"], sc["wave_h"], 1, prm, COUPLING, grid=(sc["gmin"], sc["gmax"], sc["gn"]))
     oc.particles[:] = O.make_cube(sc["nx"], sc["ny"], sc["nz"], prm)
     return oc, n
 
@@ -210,7 +227,7 @@ def run_reference(args):
         "impl": "reference", "metric": "particle_updates_per_sec", "value": value, "unit": "particle-updates/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "steps_per_sec": 1e3 / ms,
-        "config": {"workload": WORKLOAD if world == 1 else f"C4 scaled by sqrt({world}) in x and z: {n_ref} particles (weak-scaling workload of --gpus {world})",
+        "config": {"workload": WORKLOAD if world == 1 else scaled_workload(world),
                    "note": "CPU restatement of the reference GLSL (no Mesa/llvmpipe in image)"},
         "cpu_baseline": {"value": value, "unit": "particle-updates/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -392,43 +409,47 @@ def run_native(args):
 
 def run_native_distributed(args, world, rank, local_rank, torch, dist, cwa):
     """N > 1: weak scaling of the slab-decomposed coupled step (coupledwateranimation_b200.distributed).
-    The scene grows by sqrt(N) in x and z (lattice, box, wave grid, uv scale), so every GPU keeps about
-    one C4 worth of work: ~1 M particles and ~2048^2/N... wave rows x sqrt(N) wider."""
+    The scene is C4 grown by sqrt(N) in x and z (scaled_scene): every GPU keeps about one C4 worth of particles, grid cells and wave
+    cells."""
     import math
 
     from coupledwateranimation_b200.distributed import CudaBackend, DistributedCoupled, SlabPlan
 
     K, W = max(1, args.steps), max(3, args.warmup)
-    f = math.sqrt(world)
-    s_n = S * f
-    nxg = nzg = int(round(64 * S * f))
-    wave_n = int(round(WAVE * f / 4)) * 4
-    uv = 2.0 / s_n
-    box = 0.55 * s_n
+    sc = scaled_scene(world)
+    nxg, nzg = sc["nx"], sc["nz"]
+    wave_w, wave_h = sc["wave_w"], sc["wave_h"]
+    uv, uv_z = sc["uv"], sc["uv_z"] or sc["uv"]
+    box_x, box_z = sc["box_x"], sc["box_z"]
     h = 0.01
-    plan = SlabPlan.make(world, rank, wave_n, wave_n, uv, h)
     sp = np.float32(np.float32(2.0 * 0.85) * np.float32(0.005))
     ks = np.arange(nzg, dtype=np.float32) * sp
+    # slabs with equal particle counts: the texture's t range [0, 1] covers z in [0, 0.5 * S * world] only, the lattice reaches
+    # 0.544 * S * world, so equal ROW blocks would give the last rank more particles than the others
+    row_bounds = SlabPlan.balanced_row_bounds(world, wave_h, uv_z, ks - np.float32(0.5) * sp)
+    plan = SlabPlan.make(world, rank, wave_w, wave_h, uv_z, h, row_bounds)
     kk = np.nonzero((ks >= plan.z_lo) & (ks < plan.z_hi))[0]
-    i, j, k = np.meshgrid(np.arange(nxg, dtype=np.float32), np.arange(NY, dtype=np.float32), kk.astype(np.float32), indexing="ij")
+    i, j, k = np.meshgrid(np.arange(nxg, dtype=np.float32), np.arange(sc["ny"], dtype=np.float32), kk.astype(np.float32), indexing="ij")
     own = np.zeros(i.size, cwa.PARTICLE)
     own["pos"][:, 0] = i.ravel() * sp; own["pos"][:, 1] = j.ravel() * sp; own["pos"][:, 2] = k.ravel() * sp; own["pos"][:, 3] = 1.0
     own["extras"][:] = (1000.0, 0.0, 500.0, 50.0)
     del i, j, k
 
     ctx = cwa.Context(local_rank)
-    ctx.set_boundary(upper=(box, 1.0, box, 500.0), lower=BOX_LOWER)
-    ctx.set_sim_constants(uv_scale=uv)
+    ctx.set_boundary(upper=(box_x, 1.0, box_z, 500.0), lower=BOX_LOWER)
+    ctx.set_sim_constants(uv_scale=uv, uv_scale_z=sc["uv_z"], torque_coeff=sc["torque"])
     zl = max(0.0, plan.z_lo - 0.06) if rank > 0 else 0.0
-    zh = min(box, plan.z_hi + 0.06) if rank < world - 1 else box
-    ncx = int(round(384 * f))
-    ncz = max(4, int(math.ceil((zh - zl) / (box / ncx))))
+    zh = min(box_z, plan.z_hi + 0.06) if rank < world - 1 else box_z
+    ncx = sc["gn"][0]
+    ncz = max(4, int(math.ceil((zh - zl) / (box_x / ncx))))
     # the shipped parameters make the over-dense sheet blast apart (|v| in the thousands within ten frames), so tens of
-    # thousands of particles cross a slab face per frame: generous fixed-size messages (8 MB per neighbour)
-    be = CudaBackend(cwa, ctx, plan, int(own.size * 1.3) + 400000, (0.0, -0.02, zl), (box, GRID_MAX[1], zh), (ncx, GRID_N[1], ncz),
-                     cap_mig=65536, cap_ghost=65536)
+    # thousands of particles cross a slab face per frame: generous fixed-size messages
+    # (a slab face grows with sqrt(world))
+    cap = int(32768 * math.sqrt(world) + 4095) // 4096 * 4096
+    be = CudaBackend(cwa, ctx, plan, int(own.size * 1.3) + 6 * cap + 8192, (0.0, -0.02, zl), (box_x, sc["gmax"][1], zh), (ncx, sc["gn"][1], ncz),
+                     cap_mig=cap, cap_ghost=cap)
     be.upload_owned(own)
-    n_global = nxg * NY * nzg
+    n_global = nxg * sc["ny"] * nzg
     drv = DistributedCoupled(be, plan, dist)
     drv.init_wave_halos()
 
@@ -503,10 +524,10 @@ def run_native_distributed(args, world, rank, local_rank, torch, dist, cwa):
     import ctypes as C
     cap = be.capacity
     pin_p = torch.empty(cap * cwa.PARTICLE.itemsize, dtype=torch.uint8).pin_memory()
-    row_bytes = wave_n * 4
-    pin_w = [torch.empty(plan.rows_stored * wave_n, dtype=torch.float32).pin_memory() for _ in range(2)]
+    row_bytes = wave_w * 4
+    pin_w = [torch.empty(plan.rows_stored * wave_w, dtype=torch.float32).pin_memory() for _ in range(2)]
     host_p = pin_p.numpy().view(cwa.PARTICLE)
-    host_w = [w_.numpy().reshape(plan.rows_stored, wave_n) for w_ in pin_w]
+    host_w = [w_.numpy().reshape(plan.rows_stored, wave_w) for w_ in pin_w]
     host_p[:be.n_owned] = be.buffer.read(cwa.PARTICLE, be.n_owned)       # the owned RANGE (dead slots included), as the device holds it
     host_w[0][:] = be.wave.read_role(0); host_w[1][:] = be.wave.read_role(1)
     lib, hnd = ctx.lib, ctx.h
@@ -544,7 +565,7 @@ def run_native_distributed(args, world, rank, local_rank, torch, dist, cwa):
         peak, peak_src = measured_peaks()
         n_local = be.n_owned + be.n_ghost
         c_cells = be.grid.num_cells_total
-        g_local = plan.rows_stored * wave_n
+        g_local = plan.rows_stored * wave_w
         kern = []
         tot_ms = sum(v[0] for v in prof.values()) or 1.0
         for name, (ms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
@@ -560,8 +581,7 @@ def run_native_distributed(args, world, rank, local_rank, torch, dist, cwa):
             "metric": "particle_updates_per_sec", "value": n_global * K / (ms_total * 1e-3), "unit": "particle-updates/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "steps_per_sec": 1e3 / ms_step,
-            "config": {"workload": f"C4 scaled by sqrt({world}) in x and z: {n_global} particles ({nxg}x{NY}x{nzg} lattice), wave {wave_n}^2 scalar, "
-                                   f"coupling AS_SHIPPED, grid {GRID_DESC}", "per_gpu_particles": n_global // world,
+            "config": {"workload": scaled_workload(world), "per_gpu_particles": n_global // world,
                        "parallelism": f"z-slab decomposition x{world}: ghost layer 2h + migration (NCCL p2p), wave row blocks with sampling halos + last-row broadcast",
                        "l2": "working set > 126 MB L2 per GPU: inputs larger than L2, no flush needed",
                        "timing": "cudaEvent on each rank's context stream around K coupled frames (communication included), max over ranks"},

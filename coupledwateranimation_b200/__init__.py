@@ -132,8 +132,8 @@ class Context:
         self.default_ubo(UBO_WAVE).sub_data(a)
 
     def set_sim_constants(self, particle_radius=0.005, gas_const=4000.0, dt=0.00005, gravity_y=-9806.65,
-                          damping=0.3, crest_threshold=0.01, foam_speed=25.0, uv_scale=2.0):
-        a = np.array([particle_radius, gas_const, dt, gravity_y, damping, crest_threshold, foam_speed, uv_scale], np.float32)
+                          damping=0.3, crest_threshold=0.01, foam_speed=25.0, uv_scale=2.0, uv_scale_z=0.0, torque_coeff=0.0):
+        a = np.array([particle_radius, gas_const, dt, gravity_y, damping, crest_threshold, foam_speed, uv_scale, uv_scale_z, torque_coeff, 0.0, 0.0], np.float32)
         self.default_ubo(UBO_SIM).sub_data(a)
 
     def set_params_from_oracle(self, prm):
@@ -142,7 +142,7 @@ class Context:
         self.set_boundary(tuple(prm.upper), tuple(prm.lower))
         self.set_wave_uniforms(tuple(prm.attributes), tuple(prm.mesh_ws_pos))
         self.set_sim_constants(prm.particle_radius, prm.gas_const, prm.dt, prm.gravity_y, prm.damping,
-                               prm.crest_threshold, prm.foam_speed, prm.uv_scale)
+                               prm.crest_threshold, prm.foam_speed, prm.uv_scale, getattr(prm, "uv_scale_z", 0.0), getattr(prm, "torque_coeff", 0.0))
 
     def bind_scene(self, sph: "Sph | None", wave: "StencilImage2DTripleBuffered | None"):
         check(self.lib.cwa_bind_scene(self.h, sph.h if sph else -1, wave.h if wave else -1))

@@ -34,7 +34,8 @@ class WaveUniforms(C.Structure):
 
 class SimConstants(C.Structure):
     _fields_ = [("particle_radius", C.c_float), ("gas_const", C.c_float), ("dt", C.c_float), ("gravity_y", C.c_float),
-                ("damping", C.c_float), ("crest_threshold", C.c_float), ("foam_speed", C.c_float), ("uv_scale", C.c_float)]
+                ("damping", C.c_float), ("crest_threshold", C.c_float), ("foam_speed", C.c_float), ("uv_scale", C.c_float),
+                ("uv_scale_z", C.c_float), ("torque_coeff", C.c_float), ("pad1", C.c_float), ("pad2", C.c_float)]
 
 
 # name -> (restype, argtypes); every symbol include/cwa_b200.h declares
@@ -89,6 +90,7 @@ SIGNATURES = {
     "cwa_wave_bind_texture_unit": (_I, [_P, _I]),
     "cwa_wave_read_image": (_I, [_P, _I, _I, _P]),
     "cwa_wave_write_image": (_I, [_P, _I, _I, _P]),
+    "cwa_wave_mark_written": (_I, [_P, _I, _I]),
     "cwa_wave_read_image_async": (_I, [_P, _I, _I, _P]),
     "cwa_wave_role_image": (_I, [_P, _I, _I, _IP]),
     "cwa_wave_image_buffer": (_I, [_P, _I, _I, _IP]),
@@ -109,6 +111,7 @@ SIGNATURES = {
     "cwa_sph_set_count": (_I, [_P, _I, _I]),
     "cwa_particles_copy_if": (_I, [_P, _I, _I, _I, _I, _F, _F, _I, _I, _IP]),
     "cwa_slab_pack": (_I, [_P, _I, _I, _F, _F, _F, _I, _I, _I, _I]),
+    "cwa_sph_step_slab": (_I, [_P, _I, _I, _F, _F, _F, _I, _I, _I, _I]),
     "cwa_slab_unpack": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _IP]),
     "cwa_slab_compact": (_I, [_P, _I, _I, _I, _IP]),
     "cwa_wave_create_block": (_I, [_P, _I, _I, _I, _I, _I, _I, _IP]),

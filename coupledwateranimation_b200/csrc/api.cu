@@ -125,7 +125,7 @@ extern "C" int cwa_create(int device, cwa_ctx** out)
     cwa_constants_uniform cu = {0.02f, 2.0f, 3000.0f, 1000.0f};
     cwa_boundary_uniform bu = {{0.48f, 1.0f, 0.48f, 500.0f}, {0.0f, -0.02f, 0.0f, 50.0f}};
     cwa_wave_uniforms wu = {{0.01f, 0.985f, 0.001f, 1.0f}, {2.0f, 0.35f, -1.0f, 0.0f}};
-    cwa_sim_constants sc = {0.005f, 4000.0f, 0.00005f, -9806.65f, 0.3f, 0.01f, 25.0f, 2.0f};
+    cwa_sim_constants sc = {0.005f, 4000.0f, 0.00005f, -9806.65f, 0.3f, 0.01f, 25.0f, 2.0f, 0.0f, 0.0f, 0.0f, 0.0f};
     int rc = 0;
     rc |= cwa_buffer_create(ctx, sizeof(cu), &cu, &ctx->default_ubo[CWA_UBO_CONSTANTS]);
     rc |= cwa_buffer_create(ctx, sizeof(bu), &bu, &ctx->default_ubo[CWA_UBO_BOUNDARY]);
@@ -277,7 +277,7 @@ extern "C" int cwa_buffer_sub_data(cwa_ctx* ctx, cwa_buf b, size_t off, size_t b
     CWA_CHECK(host && off + bytes <= o->bytes, "cwa_buffer_sub_data: range [%zu,%zu) outside buffer of %zu bytes", off, off + bytes, o->bytes);
     CWA_CUDA(cudaMemcpyAsync((char*)o->ptr + off, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     // a particle upload invalidates any cell-ordered snapshot built from this buffer
-    for (auto& s : ctx->sphs) if (s.live && s.particles == b) s.snapshot_valid = false;
+    sph_invalidate_for_buffer(ctx, b);
     for (int i = 0; i < 8; i++) if (ctx->ubo_binding[i] == b) ctx->params_epoch++;      // a parameter block changed
     wave_touch_buffer(ctx, b, false);                                                    // a wave image written through its buffer handle
     return 0;
@@ -313,6 +313,7 @@ extern "C" int cwa_buffer_copy(cwa_ctx* ctx, cwa_buf src, cwa_buf dst, size_t so
     CWA_CHECK(soff + bytes <= s->bytes && doff + bytes <= d->bytes, "cwa_buffer_copy: range outside buffer");
     CWA_CUDA(cudaMemcpyAsync((char*)d->ptr + doff, (const char*)s->ptr + soff, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     for (int i = 0; i < 8; i++) if (ctx->ubo_binding[i] == dst) ctx->params_epoch++;
+    sph_invalidate_for_buffer(ctx, dst);
     wave_touch_buffer(ctx, dst, false);
     return 0;
 }
@@ -341,6 +342,7 @@ extern "C" int cwa_buffer_device_ptr(cwa_ctx* ctx, cwa_buf b, void** ptr, size_t
     if (ptr) *ptr = o->ptr;
     if (bytes) *bytes = o->bytes;
     wave_touch_buffer(ctx, b, true);              // a raw pointer to a wave image leaves the library: its contents can change unseen
+    sph_invalidate_for_buffer(ctx, b);
     return 0;
 }
 

@@ -135,7 +135,8 @@ struct WaveObj {
     float* imageT = nullptr;
     int    imageT_of = -1;
     unsigned long long imageT_version = 0;
-    bool   raw_exposed = false;                   // an application holds a raw pointer to an image: contents can change unseen
+    bool   raw_exposed = false;                   // an application holds a raw pointer to an image: contents can change unseen ...
+    bool   explicit_touch = false;                // ... unless it reports its writes with cwa_wave_mark_written
 };
 
 struct SphObj {
@@ -162,6 +163,14 @@ struct SphObj {
     int   *cell_next = nullptr, *rank_next = nullptr;
     bool   counts_ahead = false;                            // the grid counter already holds the counts of the current positions
     cudaEvent_t wait_before_sampling = nullptr;             // transient: the first kernel that samples the wave field waits for it
+    // slab decomposition: the integrate pass of cwa_sph_step_slab already packed the migrant / ghost messages of the NEXT exchange
+    // (same selection as slab_pack_kernel, on the records it just wrote); cwa_slab_pack with the same arguments is then a no-op
+    struct SlabPacked {
+        bool valid = false;
+        cwa_buf particles = -1, msg_left = -1, msg_right = -1;
+        int n_owned = 0, cap_mig = 0, cap_ghost = 0;
+        float z_lo = 0.f, z_hi = 0.f, band = 0.f;
+    } slab_packed;
     unsigned long long consts_epoch = 0;                    // params_epoch the prepared constants were derived from
     void*  consts = nullptr;                     // Sph3Const prepared on the device once per dispatch
     bool snapshot_valid = false;
@@ -260,7 +269,17 @@ int  wave_set_transpose(int on);
 void wave_touch_buffer(cwa_ctx* ctx, cwa_buf b, bool raw);             // a buffer was written through the Buffer API / its raw pointer handed out
 int  wave_step_internal(cwa_ctx* ctx, WaveObj* w);
 int  wave_dispatch_mode(cwa_ctx* ctx, WaveObj* w, int mode);           // kernel for uMode on units 0/1/2, no rotation                   // one EVOLVE dispatch + PingPong
-int  sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which /*bit0 rho, bit1 force, bit2 integrate*/, bool count_ahead = false);
+// slab pack fused into the integrate pass (multi.cu: cwa_sph_step_slab); all-zero = off
+struct SlabPackArgs {
+    int n_owned = 0;
+    float z_lo = 0.f, z_hi = 0.f, band = 0.f;
+    float4* msg_l = nullptr;
+    float4* msg_r = nullptr;
+    int cap_mig = 0, cap_ghost = 0;
+};
+int  sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which /*bit0 rho, bit1 force, bit2 integrate*/, bool count_ahead = false,
+                         const SlabPackArgs* slab = nullptr);
+void sph_invalidate_for_buffer(cwa_ctx* ctx, cwa_buf particles);       // the particle buffer was written behind the SPH object's back
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
@@ -354,33 +373,33 @@ __device__ __forceinline__ int cwa_tex_index(float f, int n)
     return (int)f;
 }
 
-__device__ __forceinline__ const float* cwa_tex_row(const TexView& t, int j)
+// texel (i, j) of a (possibly row-block) view, j a GLOBAL row: the local block (row-major, or its transposed sampling copy),
+// else the replicated global last row, else the nearest local row (only reachable when the caller under-sized the sampling halo)
+__device__ __forceinline__ float cwa_texel(const TexView& t, int i, int j)
 {
-    const int l = j - t.row0;
-    if ((unsigned)l < (unsigned)t.h) return t.data + (size_t)l * t.w * t.ch;
-    if (j == t.h_global - 1 && t.last_row != nullptr) return t.last_row;
-    return t.data + (size_t)(l < 0 ? 0 : t.h - 1) * t.w * t.ch;
+    int l = j - t.row0;
+    if ((unsigned)l >= (unsigned)t.h) {
+        if (j == t.h_global - 1 && t.last_row != nullptr) return __ldg(t.last_row + (size_t)i * t.ch);
+        l = l < 0 ? 0 : t.h - 1;
+    }
+    return __ldg(t.tdata + (size_t)i * t.tsi + (size_t)l * t.tsj);
 }
 
 // texture(wave_tex, (s,t)).r : GL_LINEAR, GL_CLAMP_TO_EDGE, LOD 0, full FP32 weights
 __device__ __forceinline__ float cwa_tex_bilinear(const TexView& t, float s, float tt)
 {
     if (t.data == nullptr) return 0.0f;
-    const int W = t.w, H = t.h_global, C = t.ch;
+    const int W = t.w, H = t.h_global;
     float u = __fsub_rn(__fmul_rn(s, (float)W), 0.5f);
     float v = __fsub_rn(__fmul_rn(tt, (float)H), 0.5f);
     float fu = floorf(u), fv = floorf(v);
     float a = __fsub_rn(u, fu), b = __fsub_rn(v, fv);
     int i0 = cwa_tex_index(fu, W), i1 = cwa_tex_index(fu + 1.0f, W);
     int j0 = cwa_tex_index(fv, H), j1 = cwa_tex_index(fv + 1.0f, H);
-    // global row -> storage: local block, else the replicated global last row, else the nearest
-    // local row (only reachable when the caller under-sized the sampling halo)
-    const float* p0 = cwa_tex_row(t, j0);
-    const float* p1 = cwa_tex_row(t, j1);
-    float t00 = __ldg(p0 + (size_t)i0 * C);
-    float t10 = __ldg(p0 + (size_t)i1 * C);
-    float t01 = __ldg(p1 + (size_t)i0 * C);
-    float t11 = __ldg(p1 + (size_t)i1 * C);
+    float t00 = cwa_texel(t, i0, j0);
+    float t10 = cwa_texel(t, i1, j0);
+    float t01 = cwa_texel(t, i0, j1);
+    float t11 = cwa_texel(t, i1, j1);
     float r0 = __fadd_rn(t00, __fmul_rn(a, __fsub_rn(t10, t00)));
     float r1 = __fadd_rn(t01, __fmul_rn(a, __fsub_rn(t11, t01)));
     return __fadd_rn(r0, __fmul_rn(b, __fsub_rn(r1, r0)));

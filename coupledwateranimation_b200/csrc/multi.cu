@@ -110,7 +110,7 @@ extern "C" int cwa_sph_set_count(cwa_ctx* ctx, cwa_sph h, int n)
     }
     s->n = n;
     s->snapshot_valid = false;
-    return 0;
+    return 0;                                              // (a pending slab pack stays valid: it only covers the owned range)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -200,6 +200,17 @@ extern "C" int cwa_slab_pack(cwa_ctx* ctx, cwa_buf particles, int n_owned, float
     const size_t need = (size_t)(1 + cap_mig + cap_ghost) * 64;
     CWA_CHECK((msg_left == -1 || (ml && ml->bytes >= need)) && (msg_right == -1 || (mr && mr->bytes >= need)),
               "cwa_slab_pack: message buffers smaller than %zu bytes", need);
+    // the integrate pass of cwa_sph_step_slab may already have packed exactly these messages
+    for (auto& s : ctx->sphs) {
+        if (!s.live || s.particles != particles || !s.slab_packed.valid) continue;
+        const SphObj::SlabPacked& k = s.slab_packed;
+        if (k.msg_left == msg_left && k.msg_right == msg_right && k.n_owned == n_owned && k.cap_mig == cap_mig && k.cap_ghost == cap_ghost &&
+            k.z_lo == z_lo && k.z_hi == z_hi && k.band == band) {
+            s.slab_packed.valid = false;                     // consumed: the messages are about to be sent
+            s.snapshot_valid = false;
+            return 0;
+        }
+    }
     if (ml) CWA_CUDA(cudaMemsetAsync(ml->ptr, 0, 64, ctx->stream));
     if (mr) CWA_CUDA(cudaMemsetAsync(mr->ptr, 0, 64, ctx->stream));
     if (n_owned == 0 || (!ml && !mr)) return 0;
@@ -207,7 +218,37 @@ extern "C" int cwa_slab_pack(cwa_ctx* ctx, cwa_buf particles, int n_owned, float
     slab_pack_kernel<<<ceil_div(n_owned, 256), 256, 0, ctx->stream>>>((float4*)p->ptr, n_owned, z_lo, z_hi, band, ml != nullptr, mr != nullptr,
                                                                      ml ? (float4*)ml->ptr : nullptr, mr ? (float4*)mr->ptr : nullptr, cap_mig, cap_ghost);
     CWA_CUDA(cudaGetLastError());
-    for (auto& s : ctx->sphs) if (s.live && s.particles == particles) s.snapshot_valid = false;
+    sph_invalidate_for_buffer(ctx, particles);
+    return 0;
+}
+
+// One SPH frame (rho_pres, force, integrate on `n_total` = owned + ghost particles) whose integrate pass also packs the messages of
+// the NEXT exchange: owned particles (original slot < n_owned) that end the frame within `band` of a face or beyond it.  The next
+// cwa_slab_pack call with the same arguments finds its work done -- one pass over the particle SSBO less per frame.
+extern "C" int cwa_sph_step_slab(cwa_ctx* ctx, cwa_sph h, int n_owned, float z_lo, float z_hi, float band,
+                                 cwa_buf msg_left, cwa_buf msg_right, int cap_mig, int cap_ghost)
+{
+    SphObj* s = get_sph(ctx, h);
+    CWA_CHECK(s, "invalid sph handle %d", h);
+    CWA_CHECK(s->grid >= 0, "cwa_sph_step_slab: the SPH object needs a uniform grid");
+    BufferObj* ml = get_buffer(ctx, msg_left);
+    BufferObj* mr = get_buffer(ctx, msg_right);
+    const size_t need = (size_t)(1 + cap_mig + cap_ghost) * 64;
+    CWA_CHECK(n_owned >= 0 && n_owned <= s->n, "cwa_sph_step_slab: owned range %d exceeds the particle count %d", n_owned, s->n);
+    CWA_CHECK((msg_left == -1 || (ml && ml->bytes >= need)) && (msg_right == -1 || (mr && mr->bytes >= need)),
+              "cwa_sph_step_slab: message buffers smaller than %zu bytes", need);
+    if (ml) CWA_CUDA(cudaMemsetAsync(ml->ptr, 0, 64, ctx->stream));
+    if (mr) CWA_CUDA(cudaMemsetAsync(mr->ptr, 0, 64, ctx->stream));
+    SlabPackArgs a;
+    a.n_owned = n_owned; a.z_lo = z_lo; a.z_hi = z_hi; a.band = band;
+    a.msg_l = ml ? (float4*)ml->ptr : nullptr; a.msg_r = mr ? (float4*)mr->ptr : nullptr;
+    a.cap_mig = cap_mig; a.cap_ghost = cap_ghost;
+    CWA_TRY(sph_passes_internal(ctx, s, wave_tex_view(ctx, s->wave, s->wave_image), 7, false, &a));
+    if (s->n > 0 && (ml || mr)) {
+        SphObj::SlabPacked& k = s->slab_packed;
+        k.valid = true; k.particles = s->particles; k.msg_left = msg_left; k.msg_right = msg_right;
+        k.n_owned = n_owned; k.cap_mig = cap_mig; k.cap_ghost = cap_ghost; k.z_lo = z_lo; k.z_hi = z_hi; k.band = band;
+    }
     return 0;
 }
 
@@ -233,7 +274,7 @@ extern "C" int cwa_slab_unpack(cwa_ctx* ctx, cwa_buf particles, int n_owned, cwa
     CWA_CUDA(cudaGetLastError());
     CWA_CUDA(cudaMemcpyAsync(counts_host, sc->flags, 16, cudaMemcpyDeviceToHost, ctx->stream));
     CWA_CUDA(cudaStreamSynchronize(ctx->stream));          // the one host synchronisation of a distributed frame
-    for (auto& s : ctx->sphs) if (s.live && s.particles == particles) s.snapshot_valid = false;
+    sph_invalidate_for_buffer(ctx, particles);
     return 0;
 }
 
@@ -266,6 +307,7 @@ extern "C" int cwa_slab_compact(cwa_ctx* ctx, cwa_buf particles, int n_owned, cw
     CWA_CUDA(cudaMemcpyAsync(&total, sc->pos + n_owned, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CWA_CUDA(cudaStreamSynchronize(ctx->stream));
     if (total > 0) CWA_CUDA(cudaMemcpyAsync(p->ptr, s->ptr, (size_t)total * 64, cudaMemcpyDeviceToDevice, ctx->stream));
+    sph_invalidate_for_buffer(ctx, particles);
     *n_live = total;
     return 0;
 }

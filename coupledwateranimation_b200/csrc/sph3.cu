@@ -65,7 +65,7 @@ struct Sph3Const {
     float mass, rho0, visc_coeff;
     float poly6;                   // mass*315 / (64*PI*h^9)
     float spiky, laplacian;        // -20/(PI*h^6), +20/(PI*h^6)
-    float gas, radius, dt, gravity_y, damping, crest, foam_speed, uv_scale;
+    float gas, radius, dt, gravity_y, damping, crest, foam_speed, uv_scale, uv_scale_z, torque;
     float wave_type;
     float upper[3], lower[3];
 };
@@ -100,6 +100,8 @@ __device__ __forceinline__ Sph3Const load_consts(const ParamPtrs& prm)
     c.laplacian = -c.spiky;                                        // :69
     c.gas = sc.gas_const; c.radius = sc.particle_radius; c.dt = sc.dt; c.gravity_y = sc.gravity_y;
     c.damping = sc.damping; c.crest = sc.crest_threshold; c.foam_speed = sc.foam_speed; c.uv_scale = sc.uv_scale;
+    c.uv_scale_z = (sc.uv_scale_z != 0.0f) ? sc.uv_scale_z : sc.uv_scale;
+    c.torque = (sc.torque_coeff != 0.0f) ? sc.torque_coeff : 0.25f;
     c.wave_type = prm.wave->attributes[3];
 #pragma unroll
     for (int a = 0; a < 3; a++) { c.upper[a] = prm.boundary->upper[a]; c.lower[a] = prm.boundary->lower[a]; }
@@ -154,7 +156,7 @@ __device__ __forceinline__ void density_epilogue(const Sph3Const& c, const TexVi
                                                  float& rho_out, float& prs_out)
 {
     float pressure = fmaxf(c.gas * (rho - c.rho0), 0.0f);
-    const float height = cwa_tex_sample<LOCAL>(tex, c.uv_scale * px, c.uv_scale * pz);
+    const float height = cwa_tex_sample<LOCAL>(tex, c.uv_scale * px, c.uv_scale_z * pz);
     const float wave_force = height * rho;
     pressure += wave_force;
     rho += __fdiv_rn(wave_force, c.gas * c.radius);
@@ -176,12 +178,12 @@ __device__ __forceinline__ float4 force_epilogue(const Sph3Const& c, const TexVi
         fvx *= 0.5f; fvy *= 0.5f; fvz *= 0.5f;
     }
     fvx *= c.visc_coeff; fvy *= c.visc_coeff; fvz *= c.visc_coeff; // :97
-    const float cu = px * c.uv_scale, cv = pz * c.uv_scale;        // :99
+    const float cu = px * c.uv_scale, cv = pz * c.uv_scale_z;        // :99
     const float height = cwa_tex_sample<LOCAL>(tex, cu, cv);            // :100
     // torque = 0.25 * cross(pos, force_prev.xyz)  :103-104
-    const float tx = 0.25f * (py * fprev.z - pz * fprev.y);
-    const float ty = 0.25f * (pz * fprev.x - px * fprev.z);
-    const float tz = 0.25f * (px * fprev.y - py * fprev.x);
+    const float tx = c.torque * (py * fprev.z - pz * fprev.y);
+    const float ty = c.torque * (pz * fprev.x - px * fprev.z);
+    const float tz = c.torque * (px * fprev.y - py * fprev.x);
     // WaveVelocity :117-128
     const float hX = cwa_tex_sample<LOCAL>(tex, cu + 0.01f, cv);
     const float hY = cwa_tex_sample<LOCAL>(tex, cu, cv + 0.01f);
@@ -215,7 +217,7 @@ __device__ __forceinline__ void integrate_particle(const Sph3Const& c, const Tex
         rho *= 0.1f; prs *= 0.25f;
         nvx *= 0.1f; nvy *= 0.1f; nvz *= 0.1f;
     }
-    const float th = cwa_tex_sample<LOCAL>(tex, npx * c.uv_scale, npz * c.uv_scale);   // :79
+    const float th = cwa_tex_sample<LOCAL>(tex, npx * c.uv_scale, npz * c.uv_scale_z);   // :79
     if (npy < th) npy = th - c.radius;                                            // :80-83
     const float D = c.damping;
     if (npx < c.lower[0]) { npx = c.lower[0]; nvx *= -D; } else if (npx > c.upper[0]) { npx = c.upper[0]; nvx *= -D; }
@@ -851,15 +853,21 @@ sph3_force_heavy_kernel(const float4* __restrict__ pack, const int* __restrict__
 // the position it just wrote -- the same cwa_cell3 on the same stored floats as grid_hash_count_kernel, warp-aggregated
 // (threads are in cell order, so most lanes of a warp share a few cells) -- and leaves cell id and arrival rank indexed
 // by its slot: the next grid build starts at the scan and never re-reads the particle records for the hash.
-template <bool LOCAL, bool AHEAD>
+// MODE 2 (slab decomposition, cwa_sph_step_slab): an OWNED particle (original slot < n_owned) that ends the frame within `band` of a
+// slab face, or beyond it, is also copied into the message for that neighbour -- the selection, message layout and dead-slot marking
+// of slab_pack_kernel (multi.cu), applied to the record in registers instead of a second pass over the SSBO.
+#define CWA_DEAD_W_SPH (-1.0f)
+template <bool LOCAL, int MODE>
 __global__ void __launch_bounds__(128, 10)          // latency-bound gathers and scatters: favour occupancy over registers
 sph3_finalize_integrate_sorted_kernel(const float4* __restrict__ pack,
                                       const float4* __restrict__ forceS, const float4* __restrict__ miscS,
                                       const float4* __restrict__ pairP, const float2* __restrict__ pairV,
                                       const int* __restrict__ index_list, const int* __restrict__ count, float4* __restrict__ aos,
                                       const Sph3Const* __restrict__ cc, TexView tex,
-                                      GridView g, int n, int* __restrict__ counter, int* __restrict__ cell_next, int* __restrict__ rank_next)
+                                      GridView g, int n, int* __restrict__ counter, int* __restrict__ cell_next, int* __restrict__ rank_next,
+                                      SlabPackArgs sp)
 {
+    constexpr bool AHEAD = (MODE == 1);
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = s < __ldg(count);
     if (!AHEAD && !live) return;
@@ -873,9 +881,32 @@ sph3_finalize_integrate_sorted_kernel(const float4* __restrict__ pack,
         float4 pos = make_float4(a.x, a.y, a.z, m.x), vel = make_float4(b.x, b.y, b.z, m.y);
         float rho = b.w, prs = a.w;
         integrate_particle<LOCAL>(c, tex, pos, vel, f, rho, prs);
-        float4* o = aos + (size_t)__ldg(index_list + s) * 4;      // 64-byte record = two 256-bit stores (two full sectors)
-        cwa_stg256(o, pos, vel);
-        cwa_stg256(o + 2, f, make_float4(rho, prs, m.z, m.w));
+        const int id = __ldg(index_list + s);
+        float4* o = aos + (size_t)id * 4;                          // 64-byte record = two 256-bit stores (two full sectors)
+        const float4 ex = make_float4(rho, prs, m.z, m.w);
+        float4 pos_out = pos;
+        if (MODE == 2 && id < sp.n_owned) {
+            const float z = pos.z;                                 // NaN z: every test below is false -> stays
+            float4* msg = nullptr;
+            bool migrate = false;
+            if (sp.msg_l != nullptr && z < sp.z_lo + sp.band) { msg = sp.msg_l; migrate = z < sp.z_lo; }
+            else if (sp.msg_r != nullptr && z >= sp.z_hi - sp.band) { msg = sp.msg_r; migrate = z >= sp.z_hi; }
+            if (msg != nullptr) {
+                int* hdr = reinterpret_cast<int*>(msg);
+                const int mslot = atomicAdd(hdr + (migrate ? 0 : 1), 1);
+                const int cap = migrate ? sp.cap_mig : sp.cap_ghost;
+                if (mslot >= cap) {
+                    atomicExch(hdr + 2, 1);                        // overflow: reported to the host, particle stays put
+                } else {
+                    float4* d = msg + 4 * (size_t)(1 + (migrate ? 0 : sp.cap_mig) + mslot);
+                    cwa_stg256(d, pos, vel);
+                    cwa_stg256(d + 2, f, ex);
+                    if (migrate) pos_out = make_float4(__int_as_float(0x7fffffff), __int_as_float(0x7fffffff), __int_as_float(0x7fffffff), CWA_DEAD_W_SPH);
+                }
+            }
+        }
+        cwa_stg256(o, pos_out, vel);
+        cwa_stg256(o + 2, f, ex);
         if (AHEAD) {
             cell = -1;
             if (pos.x == pos.x && pos.y == pos.y && pos.z == pos.z) {          // as grid_hash_count_kernel<3>
@@ -1288,8 +1319,15 @@ static float4* sph_scratch_force(SphObj* s) { return s->scratch; }
 // intermediate in the cell-ordered snapshot and writes the SSBO once, at the end.
 // count_ahead (set by cwa_coupled_step for frames that are followed by another frame of the same call): the integrate pass also
 // hashes + counts the new positions for the next frame's grid build.
-int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which, bool count_ahead)
+void sph_invalidate_for_buffer(cwa_ctx* ctx, cwa_buf particles)
 {
+    for (auto& s : ctx->sphs)
+        if (s.live && s.particles == particles) { s.snapshot_valid = false; s.slab_packed.valid = false; s.counts_ahead = false; }
+}
+
+int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which, bool count_ahead, const SlabPackArgs* slab)
+{
+    s->slab_packed.valid = false;                                  // whatever was packed described the previous positions
     BufferObj* pb = get_buffer(ctx, s->particles);
     CWA_CHECK(pb, "sph: particle buffer vanished");
     float4* aos = (float4*)pb->ptr;
@@ -1326,7 +1364,8 @@ int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which, bool co
     const bool full = (which == 7);
     const int cfg = nb_config();
     const bool fused_tail = full && cfg == 7 && fused_integrate();   // the force kernels finish the particle (epilogue + integrate + write-back)
-    count_ahead = count_ahead && full && !fused_tail;
+    count_ahead = count_ahead && full && !fused_tail && slab == nullptr;
+    CWA_CHECK(slab == nullptr || (full && !fused_tail), "slab pack: needs a full step with the separate integrate kernel (fused_integrate = 0)");
     if (!(which & 1)) CWA_TRY(wave_sampling_copy(ctx, s->wave, s->wave_image, &tex));
     if (which & 1) {
         CWA_TRY(sph_snapshot(ctx, s, count_ahead));                // positions changed since the last frame
@@ -1379,11 +1418,13 @@ int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which, bool co
         KScope k(ctx, KID_INTEGRATE);
         if (full) {
             const bool local = tex_view_is_local(tex);
-#define CWA_FIN_INT(L, A) sph3_finalize_integrate_sorted_kernel<L, A><<<ceil_div(n, 128), 128, 0, ctx->stream>>>( \
+            const SlabPackArgs spa = slab ? *slab : SlabPackArgs();
+            const int mode = slab ? 2 : (count_ahead ? 1 : 0);
+#define CWA_FIN_INT(L, M) sph3_finalize_integrate_sorted_kernel<L, M><<<ceil_div(n, 128), 128, 0, ctx->stream>>>( \
                     s->pack, s->forceS, s->miscS, s->pairP, s->pairV, g->index_list, g->offset + g->view.num_cells, aos, cc, tex, \
-                    g->view, n, g->counter, s->cell_next, s->rank_next)
-            if (local) { if (count_ahead) CWA_FIN_INT(true, true); else CWA_FIN_INT(true, false); }
-            else       { if (count_ahead) CWA_FIN_INT(false, true); else CWA_FIN_INT(false, false); }
+                    g->view, n, g->counter, s->cell_next, s->rank_next, spa)
+            if (local) { if (mode == 2) CWA_FIN_INT(true, 2); else if (mode == 1) CWA_FIN_INT(true, 1); else CWA_FIN_INT(true, 0); }
+            else       { if (mode == 2) CWA_FIN_INT(false, 2); else if (mode == 1) CWA_FIN_INT(false, 1); else CWA_FIN_INT(false, 0); }
 #undef CWA_FIN_INT
             s->counts_ahead = count_ahead;
         } else {
@@ -1530,7 +1571,7 @@ extern "C" int cwa_sph_init_cube(cwa_ctx* ctx, cwa_sph h, int nx, int ny, int nz
     { KScope k(ctx, KID_OTHER);
       sph3_init_cube_kernel<<<ceil_div(s->n, 256), 256, 0, ctx->stream>>>((float4*)pb->ptr, nx, ny, nz, current_params(ctx)); }
     CWA_CUDA(cudaGetLastError());
-    s->snapshot_valid = false;
+    sph_invalidate_for_buffer(ctx, s->particles);
     return 0;
 }
 

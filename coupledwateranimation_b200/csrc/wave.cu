@@ -310,8 +310,9 @@ void wave_touch_buffer(cwa_ctx* ctx, cwa_buf b, bool raw)
 int wave_sampling_copy(cwa_ctx* ctx, cwa_wave h, int image, TexView* tex)
 {
     WaveObj* w = get_wave(ctx, h);
-    if (!w || image < 0 || image >= 3 || !wave_transpose_on() || w->raw_exposed) return 0;
-    if (!tex_view_is_local(*tex) || tex->data != w->image[image] || (long long)w->w * w->h < 256 * 256) return 0;
+    if (!w || image < 0 || image >= 3 || !wave_transpose_on() || (w->raw_exposed && !w->explicit_touch)) return 0;
+    // any scalar view (whole field or row block) that is 32-bit indexable and large enough for the access pattern to matter
+    if (tex->ch != 1 || tex->data != w->image[image] || (long long)w->w * w->h < 256 * 256 || (long long)w->w * w->h >= (1ll << 30)) return 0;
     if (w->imageT == nullptr) CWA_CUDA(cudaMalloc(&w->imageT, (size_t)w->w * w->h * 4));
     if (w->imageT_of != image || w->imageT_version != w->version[image]) {
         KScope k(ctx, KID_OTHER);
@@ -434,7 +435,7 @@ TexView wave_tex_view(cwa_ctx* ctx, cwa_wave h, int image)
     if (w && image >= 0 && image < 3) {
         t.data = w->image[image]; t.w = w->w; t.h = w->h; t.ch = w->ch;
         t.row0 = w->row0; t.h_global = w->h_global; t.last_row = w->last_row[image];
-        t.tdata = t.data; t.tsi = 1; t.tsj = w->w;
+        t.tdata = t.data; t.tsi = w->ch; t.tsj = w->w * w->ch;      // row-major as stored (.r channel of texel (i, j))
     }
     return t;
 }
@@ -610,6 +611,19 @@ extern "C" int cwa_wave_write_image(cwa_ctx* ctx, cwa_wave h, int image, const f
     const int i = resolve_image(w, image);
     CWA_CHECK(i >= 0, "image index %d out of range", image);
     CWA_CUDA(cudaMemcpyAsync(w->image[i], host, (size_t)w->w * w->h * w->ch * 4, cudaMemcpyHostToDevice, ctx->stream));
+    w->version[i]++;
+    return 0;
+}
+
+// An application that writes an image through a raw device pointer (cwa_buffer_device_ptr: CUDA-GL interop maps, NCCL receives
+// into halo rows) reports it here; without such reports the library stops keeping derived copies of that object's images.
+extern "C" int cwa_wave_mark_written(cwa_ctx* ctx, cwa_wave h, int image)
+{
+    WaveObj* w = get_wave(ctx, h);
+    CWA_CHECK(w, "invalid wave handle %d", h);
+    const int i = resolve_image(w, image);
+    CWA_CHECK(i >= 0, "image index %d out of range", image);
+    w->explicit_touch = true;
     w->version[i]++;
     return 0;
 }

@@ -54,13 +54,23 @@ class SlabPlan:
     halo_hi: int = 0
     store_lo: int = 0             # stored rows [store_lo, store_hi)
     store_hi: int = 0
+    row_bounds: tuple = None      # the row blocks of all ranks when they are not the even split
 
     @staticmethod
-    def make(world: int, rank: int, wave_w: int, wave_h: int, uv_scale: float, h: float) -> "SlabPlan":
+    def make(world: int, rank: int, wave_w: int, wave_h: int, uv_scale: float, h: float, row_bounds=None) -> "SlabPlan":
+        """row_bounds: optional world+1 ascending row indices (0 ... wave_h) = the row blocks of the ranks, e.g. chosen so
+        that the z slabs hold equal particle counts (balanced_row_bounds); default: equal row counts."""
         p = SlabPlan(world, rank, wave_w, wave_h, uv_scale, h)
-        base, rem = divmod(wave_h, world)
-        p.row_lo = rank * base + min(rank, rem)
-        p.row_hi = p.row_lo + base + (1 if rank < rem else 0)
+        if row_bounds is not None:
+            rb = [int(v) for v in row_bounds]
+            assert len(rb) == world + 1 and rb[0] == 0 and rb[-1] == wave_h and all(b > a for a, b in zip(rb, rb[1:])), \
+                f"row_bounds must be {world + 1} ascending rows from 0 to {wave_h}: {rb}"
+            p.row_lo, p.row_hi = rb[rank], rb[rank + 1]
+            p.row_bounds = tuple(rb)
+        else:
+            base, rem = divmod(wave_h, world)
+            p.row_lo = rank * base + min(rank, rem)
+            p.row_hi = p.row_lo + base + (1 if rank < rem else 0)
         # texture t = uv_scale * z, texel row = t * H - 0.5: row boundary b  <->  z = b / (H * uv_scale)
         scale = wave_h * uv_scale
         p.z_lo = -math.inf if rank == 0 else p.row_lo / scale
@@ -71,6 +81,21 @@ class SlabPlan:
         p.store_lo = max(0, p.row_lo - p.halo_lo)
         p.store_hi = min(wave_h, p.row_hi + p.halo_hi)
         return p
+
+    @staticmethod
+    def balanced_row_bounds(world: int, wave_h: int, uv_scale: float, z_sorted_sample: np.ndarray):
+        """Row blocks whose z slabs hold about equal shares of the particles (z_sorted_sample: ascending z of the particles or
+        of a representative sample).  The wave rows follow the particles: a few per cent more stencil rows on some ranks
+        cost microseconds, a few per cent more particles cost tens."""
+        scale = wave_h * uv_scale
+        rb = [0]
+        n = len(z_sorted_sample)
+        for r in range(1, world):
+            zc = float(z_sorted_sample[min(n - 1, (n * r) // world)])
+            row = int(round(zc * scale))
+            rb.append(min(max(row, rb[-1] + 1), wave_h - (world - r)))
+        rb.append(wave_h)
+        return rb
 
     @property
     def ghost_width(self) -> float:
@@ -106,7 +131,7 @@ class DistributedCoupled:
         self.world, self.rank = plan.world, plan.rank
         plan.validate()
         self._halo_pending = False
-        self._nbr_plans = {r: SlabPlan.make(plan.world, r, plan.wave_w, plan.wave_h, plan.uv_scale, plan.h)
+        self._nbr_plans = {r: SlabPlan.make(plan.world, r, plan.wave_w, plan.wave_h, plan.uv_scale, plan.h, plan.row_bounds)
                            for r in (plan.rank - 1, plan.rank + 1) if 0 <= r < plan.world}
 
     def _p2p(self, pairs):
@@ -166,6 +191,8 @@ class DistributedCoupled:
             if wave:
                 pairs += self._wave_pairs()
             self._p2p(pairs)
+            if wave:
+                b.wave_written(b.newest_image())       # halo rows of the newest level were received into the image
             if particles:
                 b.unpack(p.has_left, p.has_right)
 
@@ -182,7 +209,10 @@ class DistributedCoupled:
             self._exchange(True, self._halo_pending)
             self._halo_pending = False
             image = b.newest_image() if coupling == COUPLING_LATEST else b.tex_unit0()
-            b.sph_step(image)                      # idle(): rho_pres, force, integrate  (Main.cpp:549-557)
+            # idle(): rho_pres, force, integrate (Main.cpp:549-557).  When another frame of this call follows, the integrate
+            # pass may already pack that frame's migrant / ghost messages (the last frame leaves every particle in its
+            # owner's buffer, so reads and checks between calls see a complete state)
+            b.sph_step(image, pack_next=(f + 1 < nframes))
             b.wave_step()                          # Module::sComputeAll               (Main.cpp:560)
             b.bind_texture_unit()                  # display(): GetReadImage(0).BindTextureUnit()  (Main.cpp:413)
             self._halo_pending = True
@@ -236,6 +266,8 @@ class CudaBackend:
         self.n_ghost = 0
         self.migrated_in = 0
         self._stream = torch.cuda.ExternalStream(ctx.stream, device=self.device)
+        import os
+        self.fused_pack = os.environ.get("CWA_FUSED_PACK", "1") != "0"   # integrate packs the next exchange's messages (cwa_sph_step_slab)
 
     def _tensor(self, buf, offset_bytes: int, nbytes: int):
         if nbytes == 0:
@@ -303,11 +335,19 @@ class CudaBackend:
         self.migrated_in += counts[3]
 
     # ---- simulation -------------------------------------------------------------------------------
-    def sph_step(self, image: int):
+    def sph_step(self, image: int, pack_next: bool = False):
         n = self.n_owned + self.n_ghost
         self.cwa.check(self.ctx.lib.cwa_sph_set_count(self.ctx.h, self.sph.h, n))
         self.sph.bind_wave(self.wave if image >= 0 else None, image)
-        self.sph.step(1)
+        p = self.plan
+        if p.world > 1 and self.fused_pack and pack_next:
+            # the integrate pass packs the migrant / ghost messages of the NEXT exchange (pack() then finds its work done)
+            f = lambda v: max(min(v, 3.0e38), -3.0e38)
+            self.cwa.check(self.ctx.lib.cwa_sph_step_slab(self.ctx.h, self.sph.h, self.n_owned, f(p.z_lo), f(p.z_hi), p.ghost_width,
+                                                          self.msg["sl"].h if p.has_left else -1, self.msg["sr"].h if p.has_right else -1,
+                                                          self.cap_mig, self.cap_ghost))
+        else:
+            self.sph.step(1)
 
     def wave_step(self):
         self.wave.Compute(1)
@@ -317,6 +357,10 @@ class CudaBackend:
 
     def newest_image(self) -> int:
         return self.wave.role_image(0)
+
+    def wave_written(self, image: int):
+        """Rows of `image` were written through its raw device pointer (NCCL receive): derived copies are stale."""
+        self.cwa.check(self.ctx.lib.cwa_wave_mark_written(self.ctx.h, self.wave.h, image))
 
     def tex_unit0(self) -> int:
         return self.wave.state()["tex_unit0"]

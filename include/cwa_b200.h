@@ -52,6 +52,9 @@ typedef struct { float attributes[4], mesh_ws_pos[4]; } cwa_wave_uniforms;      
 typedef struct {
     float particle_radius, gas_const, dt, gravity_y;
     float damping, crest_threshold, foam_speed, uv_scale;
+    float uv_scale_z;        /* texture t = uv_scale_z * pos.z; 0 (default) = uv_scale, the reference's 2.0*pos.xz */
+    float torque_coeff;      /* torque = torque_coeff * cross(pos, force_prev), force_comp.glsl:103-104; 0 (default) = the reference's 0.25 */
+    float pad1, pad2;
 } cwa_sim_constants;                                                                         /* binding 4 (extension) */
 /* UniformGridInfo: 2-D SphWave2D/UniformGridGpu2D.h:89-94, 3-D UniformGrid2D/UniformGridParticles3D.h:60-67 */
 typedef struct { float min[4], max[4]; int num_cells[4]; float cell_size[4]; } cwa_grid_info;
@@ -153,6 +156,7 @@ CWA_API int cwa_wave_bind_texture_unit(cwa_ctx* ctx, cwa_wave w);
 /* image by physical index 0..2 (ImageTexture), or by role: 0 newest, 1 previous, 2 next output */
 CWA_API int cwa_wave_read_image(cwa_ctx* ctx, cwa_wave w, int image, float* host);       /* synchronises */
 CWA_API int cwa_wave_read_image_async(cwa_ctx* ctx, cwa_wave w, int image, float* host); /* enqueued only: valid after cwa_synchronize */
+CWA_API int cwa_wave_mark_written(cwa_ctx* ctx, cwa_wave w, int image);  /* image was written through a raw device pointer (interop map, NCCL receive) */
 CWA_API int cwa_wave_write_image(cwa_ctx* ctx, cwa_wave w, int image, const float* host);
 CWA_API int cwa_wave_role_image(cwa_ctx* ctx, cwa_wave w, int role, int* image);
 CWA_API int cwa_wave_image_buffer(cwa_ctx* ctx, cwa_wave w, int image, cwa_buf* out);    /* GetTexture() for interop */
@@ -193,6 +197,11 @@ CWA_API int cwa_particles_copy_if(cwa_ctx* ctx, cwa_buf src, int n, int axis, in
  * [1+cap_mig, 1+cap_mig+cap_ghost) ghosts (within `band` of the face).  msg_left / msg_right = -1: no neighbour there. */
 CWA_API int cwa_slab_pack(cwa_ctx* ctx, cwa_buf particles, int n_owned, float z_lo, float z_hi, float band,
                           cwa_buf msg_left, cwa_buf msg_right, int cap_mig, int cap_ghost);
+/* cwa_sph_step(1) on the bound wave whose integrate pass ALSO packs the messages of the next exchange (owned = original slots
+ * [0, n_owned); same selection, layout and dead-slot marking as cwa_slab_pack, applied to the records while they are in registers).
+ * The next cwa_slab_pack call with the same arguments is then a no-op. */
+CWA_API int cwa_sph_step_slab(cwa_ctx* ctx, cwa_sph s, int n_owned, float z_lo, float z_hi, float band,
+                              cwa_buf msg_left, cwa_buf msg_right, int cap_mig, int cap_ghost);
 /* append the received migrants behind the owned range, then the ghosts: the received ones plus the migrants of this
  * rank's own outgoing messages (sent_*; still neighbours here this frame).  counts[4] = {owned range, owned + ghosts,
  * flags (1: a sender overflowed, 2: capacity exceeded), migrants adopted}; the one host synchronisation of a frame */

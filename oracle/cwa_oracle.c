@@ -63,6 +63,9 @@ static inline int cell_coord(float q, int n)
 /* ------------------------------------------------------------------------------------------ */
 /* parameters                                                                                  */
 /* ------------------------------------------------------------------------------------------ */
+/* texture t scale: uv_scale_z when set, else the reference's single factor (2.0*pos.xz) */
+static float orc_uvz(const orc_params3* p) { return p->uv_scale_z != 0.0f ? p->uv_scale_z : p->uv_scale; }
+
 void orc_params3_default(orc_params3* p)
 {
     /* CoupledWaterAnimation/Main.cpp:184-204 */
@@ -73,7 +76,7 @@ void orc_params3_default(orc_params3* p)
     p->mesh_ws_pos[0] = 2.0f; p->mesh_ws_pos[1] = 0.35f; p->mesh_ws_pos[2] = -1.0f; p->mesh_ws_pos[3] = 0.0f;
     /* shader constants: rho_pres_comp.glsl:5,41,43; force_comp.glsl:7,52,55; integrate_comp.glsl:8,51,69 */
     p->particle_radius = 0.005f; p->gas_const = 4000.0f; p->dt = 0.00005f; p->gravity_y = -9806.65f;
-    p->damping = 0.3f; p->crest_threshold = 0.01f; p->foam_speed = 25.0f; p->uv_scale = 2.0f;
+    p->damping = 0.3f; p->crest_threshold = 0.01f; p->foam_speed = 25.0f; p->uv_scale = 2.0f; p->uv_scale_z = 0.0f; p->torque_coeff = 0.0f;
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -432,7 +435,7 @@ void orc_sph3_rho_pres(orc_particle3* p, int n, const orc_params3* prm, const or
         }
 #undef ORC_RHO_PAIR
         float pressure = fmaxf(prm->gas_const * (rho - prm->resting_rho), 0.0f); /* :70 */
-        float height = orc_tex_bilinear(tex, prm->uv_scale * pi[0], prm->uv_scale * pi[2]); /* :72-73 */
+        float height = orc_tex_bilinear(tex, prm->uv_scale * pi[0], orc_uvz(prm) * pi[2]); /* :72-73 */
         float wave_force = height * rho;                                          /* :75 */
         pressure += wave_force;                                                   /* :76 */
         rho += wave_force / (prm->gas_const * prm->particle_radius);              /* :77 */
@@ -548,11 +551,12 @@ void orc_sph3_force(orc_particle3* p, int n, const orc_params3* prm, const orc_t
             for (int c = 0; c < 3; c++) visc[c] *= 0.5f;
         }
         for (int c = 0; c < 3; c++) visc[c] *= prm->visc;        /* :97 */
-        float cu = pi[0] * prm->uv_scale, cv = pi[2] * prm->uv_scale; /* :99 */
+        float cu = pi[0] * prm->uv_scale, cv = pi[2] * orc_uvz(prm); /* :99 */
         float height = orc_tex_bilinear(tex, cu, cv);           /* :100 */
         /* torque = 0.25*cross(pos, force_mem.xyz) :103-104 */
         float tq[3] = { pi[1] * fm[2] - pi[2] * fm[1], pi[2] * fm[0] - pi[0] * fm[2], pi[0] * fm[1] - pi[1] * fm[0] };
-        for (int c = 0; c < 3; c++) tq[c] *= 0.25f;
+        const float tqc = prm->torque_coeff != 0.0f ? prm->torque_coeff : 0.25f;
+        for (int c = 0; c < 3; c++) tq[c] *= tqc;
         float wv[3]; wave_velocity(tex, cu, cv, prm->dt, wv);    /* :107 */
         float drag[3];
         for (int c = 0; c < 3; c++) drag[c] = -0.25f * (vi[c] - wv[c]); /* :107-108 */
@@ -587,7 +591,7 @@ void orc_sph3_integrate(orc_particle3* p, int n, const orc_params3* prm, const o
             q->extras[1] *= 0.25f;
             for (int c = 0; c < 3; c++) nv[c] *= 0.1f;
         }
-        float tex_height = orc_tex_bilinear(tex, np[0] * prm->uv_scale, np[2] * prm->uv_scale); /* :79 */
+        float tex_height = orc_tex_bilinear(tex, np[0] * prm->uv_scale, np[2] * orc_uvz(prm)); /* :79 */
         if (np[1] < tex_height) np[1] = tex_height - prm->particle_radius;   /* :80-83 */
         /* CheckBoundary :137-168 */
         for (int c = 0; c < 3; c++) {

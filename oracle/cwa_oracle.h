@@ -62,6 +62,8 @@ typedef struct {
     float crest_threshold;   /* CREST_THRESHOLD 0.01 */
     float foam_speed;        /* 25.0 */
     float uv_scale;          /* 2.0: coord = 2*pos.xz */
+    float uv_scale_z;        /* extension: t = uv_scale_z * pos.z; 0 = uv_scale (the reference) */
+    float torque_coeff;      /* extension: force_comp.glsl:103 literal 0.25; 0 = 0.25 (the reference) */
 } orc_params3;
 
 void orc_params3_default(orc_params3* p);

@@ -29,6 +29,7 @@ class Params3(C.Structure):
         ("attributes", C.c_float * 4), ("mesh_ws_pos", C.c_float * 4),
         ("particle_radius", C.c_float), ("gas_const", C.c_float), ("dt", C.c_float), ("gravity_y", C.c_float),
         ("damping", C.c_float), ("crest_threshold", C.c_float), ("foam_speed", C.c_float), ("uv_scale", C.c_float),
+        ("uv_scale_z", C.c_float), ("torque_coeff", C.c_float),
     ]
 
 

@@ -122,7 +122,7 @@ class OracleBackend:
             tex[pl.wave_h - 1] = self.last[image]
         return tex
 
-    def sph_step(self, image):
+    def sph_step(self, image, pack_next=False):
         n = self.n_owned + self.n_ghost
         tex = self._global_texture(image)
         q = self.p[:n].copy()
@@ -147,6 +147,9 @@ class OracleBackend:
 
     def newest_image(self):
         return self.unit.index(0)
+
+    def wave_written(self, image):
+        pass
 
     def tex_unit0(self):
         return self._tex0

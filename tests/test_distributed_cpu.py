@@ -52,7 +52,7 @@ def test_slab_plan_covers_rows_and_sizes_halos():
         SlabPlan.make(64, 3, 32, 96, 2.0, 0.01).validate()     # slabs thinner than two ghost layers
 
 
-def _worker(rank, world, coupling, init_file, out_dir):
+def _worker(rank, world, coupling, init_file, out_dir, balanced=False):
     import torch.distributed as dist
     from oracle_backend import OracleBackend
     from coupledwateranimation_b200.distributed import DistributedCoupled, SlabPlan
@@ -60,7 +60,8 @@ def _worker(rank, world, coupling, init_file, out_dir):
         dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
     prm, p = scene()
     h = prm.smoothing_coeff * prm.particle_radius
-    plan = SlabPlan.make(world, rank, WAVE_W, WAVE_H, prm.uv_scale, h)
+    bounds = SlabPlan.balanced_row_bounds(world, WAVE_H, prm.uv_scale, np.sort(p["pos"][:, 2])) if balanced else None
+    plan = SlabPlan.make(world, rank, WAVE_W, WAVE_H, prm.uv_scale, h, bounds)
     be = OracleBackend(plan, p.size + 4096, prm, GRID)
     z = p["pos"][:, 2]
     be.upload_owned(p[(z >= plan.z_lo) & (z < plan.z_hi)])
@@ -73,14 +74,14 @@ def _worker(rank, world, coupling, init_file, out_dir):
         dist.destroy_process_group()
 
 
-def _run(world, coupling):
+def _run(world, coupling, balanced=False):
     import torch.multiprocessing as mp
     with tempfile.TemporaryDirectory() as d:
         init_file = os.path.join(d, "rendezvous")
         if world == 1:
             _worker(0, 1, coupling, init_file, d)
         else:
-            mp.spawn(_worker, args=(world, coupling, init_file, d), nprocs=world, join=True)
+            mp.spawn(_worker, args=(world, coupling, init_file, d, balanced), nprocs=world, join=True)
         parts, waves, moved = [], [], 0
         for r in range(world):
             f = np.load(os.path.join(d, f"rank{r}.npz"))
@@ -130,9 +131,28 @@ def test_single_rank_driver_equals_the_oracle_coupled_driver():
     oc.close()
 
 
-def test_three_ranks_reproduce_one_rank():
+def test_balanced_row_bounds_equalise_particle_counts():
+    from coupledwateranimation_b200.distributed import SlabPlan
+    rng = np.random.default_rng(1)
+    z = np.sort(np.concatenate([rng.uniform(0.0, 2.0, 30000), rng.uniform(2.0, 5.4, 10000)]))   # the texture covers z < 4.9 only
+    uv, H = 2.0 / 9.8, 2896
+    for world in (2, 4, 8):
+        rb = SlabPlan.balanced_row_bounds(world, H, uv, z)
+        plans = [SlabPlan.make(world, r, 2896, H, uv, 0.01, rb) for r in range(world)]
+        counts = [int(((z >= p.z_lo) & (z < p.z_hi)).sum()) for p in plans]
+        assert sum(counts) == z.size and max(counts) - min(counts) <= 0.02 * z.size / world, counts
+        for a, b in zip(plans[:-1], plans[1:]):
+            assert a.row_hi == b.row_lo
+        for p in plans:
+            p.validate()
+    with pytest.raises(AssertionError):
+        SlabPlan.make(2, 0, 64, 64, 1.0, 0.01, [0, 64, 64])
+
+
+@pytest.mark.parametrize("balanced", [False, True])
+def test_three_ranks_reproduce_one_rank(balanced):
     ref, ref_wave, _ = _run(1, 1)
-    got, got_wave, _ = _run(3, 1)
+    got, got_wave, _ = _run(3, 1, balanced)
     assert got.size == ref.size and np.array_equal(got["extras"][:, 3], ref["extras"][:, 3])
     assert np.array_equal(got_wave.view(np.uint32), ref_wave.view(np.uint32))
     ok = ~np.isnan(ref["pos"]).any(1)

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+echo "== plain"; timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 100 --warmup 5 2>gpurun_out/bench_n2.err | tee gpurun_out/bench_n2.json | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('ms/step', d['ms_per_step'], 'value', d['value']); print({k['kernel']: round(k['avg_us'],1) for k in d['roofline_kernels']})"
+echo "== steady (after 45 extra frames)"; CWA_BENCH_PHASES=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 100 --warmup 5 2>&1 | grep -E "^\{|phases|kernels rank" | cut -c1-420

@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+echo "== probe 2 tanks on one GPU"; timeout 300 python tools/blast_probe.py 2 2>&1 | awk 'NR%3==0' | cut -c1-200 | tail -14
+echo "== dist_check"; timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py 2>&1 | grep -E '^\{|Error|error' | head -4
+echo "== bench N=2"; timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 100 --warmup 5 2>gpurun_out/bench_n2.err | tee gpurun_out/bench_n2.json | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('ms/step', d['ms_per_step'], 'value', d['value'], 'e2e ms', d['e2e']['ms_per_step']); print({k['kernel']: round(k['avg_us'],1) for k in d['roofline_kernels']})"
+tail -c 300 gpurun_out/bench_n2.err
