@@ -215,6 +215,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm is the one process that should use every host core
+    # (set before the oracle library -- and with it libgomp -- is loaded)
+    if os.environ.get("OMP_NUM_THREADS", "") in ("", "1"):
+        os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     steps, warmup = max(1, args.steps), max(0, args.warmup)
     # bounded: a full C4 frame costs a few seconds on the host cores; cap the frame count so the run ends in minutes
     world = max(1, args.gpus)

@@ -155,6 +155,7 @@ struct SphObj {
     float2 *pairV = nullptr;                     //                                   (visc.y, visc.z)
     int   *nbr_list = nullptr, *nbr_count = nullptr;   // neighbour lists of the density pass ([slot][K]) and true counts
     bool   nbr_lists_valid = false;
+    int    nbr_k_alloc = 0, nbr_k_used = 0;                 // list capacity the array was sized for / the density pass built the lists with
     int   *heavy_queue = nullptr;                           // targets finished one warp each: [0,cap) density pass, [cap,2cap) force pass
     int   *heavy_cnt = nullptr;                             // the two queue counters (density, force); reset by the reorder kernel of every snapshot
     // count-ahead (frames in the middle of one cwa_coupled_step call): the integrate pass hashes the NEW position of the

@@ -587,12 +587,13 @@ __device__ __forceinline__ RowBounds rows_load(const GridView& g, const int* __r
 // the L1 cache.  An accepted candidate (self included) is appended to the target's own row of K entries in
 // global memory ([slot][K], a private 128-byte line that stays in L2 until the force pass reads it) with one
 // predicated store; count[slot] keeps counting past K, and the force pass re-scans the grid for such a target.
-template <int K, bool LOCAL>
+template <bool LOCAL>
 __global__ void __launch_bounds__(TILE_P)
 sph3_density_list_kernel(const float4* __restrict__ posS, const float4* __restrict__ velS, float4* __restrict__ pack,
                          int* __restrict__ nbr_list, int* __restrict__ nbr_count,
                          int* __restrict__ heavy_queue, int* __restrict__ heavy_count,
-                         int n_max, GridView g, const int* __restrict__ offset, const Sph3Const* __restrict__ cc, TexView tex)
+                         int n_max, GridView g, const int* __restrict__ offset, const Sph3Const* __restrict__ cc, TexView tex,
+                         const int K, const int extreme_candidates)
 {
     __shared__ int2 tab[RT_ROWS * TILE_P];             // (first slot, length) of the 3 x 3 rows of every target
     const int tid = threadIdx.x;
@@ -603,7 +604,7 @@ sph3_density_list_kernel(const float4* __restrict__ posS, const float4* __restri
     const float4 p = __ldg(posS + slot);
     const Query3 q = list_query(g, p.x, p.y, p.z, h);
     const RowBounds rb = rows_load(g, offset, q);
-    if (rb.total > EXTREME_CANDIDATES) {               // a big clump: finished by sph3_density_heavy_kernel, one warp per target
+    if (rb.total > extreme_candidates) {               // a big clump: finished by sph3_density_heavy_kernel, one warp per target
         const int qi = atomicAdd(heavy_count, 1);
         if (qi < n_max) heavy_queue[qi] = slot;
         return;
@@ -738,12 +739,12 @@ __device__ __forceinline__ void finish_particle(const Sph3Const& c, const Finish
 // per target, no shared memory; a neighbour's (pos, p | vel, rho) record is one sector fetched with one 256-bit
 // load, and consecutive cell-ordered targets share most of their neighbours, so the gathers hit L1/L2.  A target
 // whose list overflowed (more than K neighbours) or that the density pass marked extreme is queued for the heavy kernel.
-template <int K, bool FUSED, bool LOCAL>
+template <bool FUSED, bool LOCAL>
 __global__ void __launch_bounds__(TILE_P, 6)
 sph3_force_list_kernel(const float4* __restrict__ pack, const int* __restrict__ nbr_list, const int* __restrict__ nbr_count,
                        int* __restrict__ heavy_queue, int* __restrict__ heavy_count,
                        float4* __restrict__ pairP, float2* __restrict__ pairV, int n_max,
-                       GridView g, const int* __restrict__ offset, const Sph3Const* __restrict__ cc, FinishArgs fa)
+                       GridView g, const int* __restrict__ offset, const Sph3Const* __restrict__ cc, FinishArgs fa, const int K)
 {
     const int slot = blockIdx.x * TILE_P + threadIdx.x;
     const int n = min(n_max, __ldg(offset + g.num_cells));   // inserted particles
@@ -1161,8 +1162,9 @@ static int env_int(const char* name, int dflt, int lo, int hi)
 //              target combined with warp shuffles, the force pass scans the candidates again
 //   cap_d / cap_f: staging budgets of the lanes kernels in slots (0 disables staging)
 constexpr int NB_CONFIG_DEFAULT = 7;
-constexpr int NBR_K = 64;                 // neighbour-list entries per target (self included); longer lists fall back to a grid scan
-struct NbTuning { int config = -1, cap_d = -1, cap_f = -1, fused_order = -1, fused_integrate = -1, pipeline = -1; };
+constexpr int NBR_K_DEFAULT = 64;         // neighbour-list entries per target (self included); longer lists fall back to a grid scan
+constexpr int NBR_K_MAX = 256;
+struct NbTuning { int config = -1, cap_d = -1, cap_f = -1, fused_order = -1, fused_integrate = -1, pipeline = -1, nbr_k = -1, extreme = -1; };
 static NbTuning g_tune;
 static int nb_config() { if (g_tune.config < 0) g_tune.config = env_int("CWA_NB_CONFIG", NB_CONFIG_DEFAULT, 0, 7); return g_tune.config; }
 static int dens_cap() { if (g_tune.cap_d < 0) g_tune.cap_d = env_int("CWA_NB_CAP_D", DENS_CAP_DEFAULT, 0, DENS_CAP_MAX); return g_tune.cap_d; }
@@ -1171,6 +1173,9 @@ static bool fused_integrate() { if (g_tune.fused_integrate < 0) g_tune.fused_int
 // pipeline (cwa_coupled_step with several frames per call): bit 0 = the wave stencil of frame f runs on a side stream next to the
 // grid build of frame f+1; bit 1 = count-ahead (integrate of frame f does the cell hash + count of frame f+1)
 static int pipeline_mode() { if (g_tune.pipeline < 0) g_tune.pipeline = env_int("CWA_PIPELINE", 3, 0, 3); return g_tune.pipeline; }
+// nbr_k: list capacity per target (multiple of 4, <= 256); extreme: candidate count above which the density pass hands a target to a whole warp
+static int nbr_k() { if (g_tune.nbr_k < 0) g_tune.nbr_k = env_int("CWA_NBR_K", NBR_K_DEFAULT, 8, NBR_K_MAX) & ~3; return g_tune.nbr_k; }
+static int extreme_candidates() { if (g_tune.extreme < 0) g_tune.extreme = env_int("CWA_EXTREME", EXTREME_CANDIDATES, 16, 1 << 20); return g_tune.extreme; }
 static bool fused_order() { if (g_tune.fused_order < 0) g_tune.fused_order = env_int("CWA_FUSED_ORDER", 1, 0, 1); return g_tune.fused_order != 0; }
 
 extern "C" int cwa_set_tuning(cwa_ctx* ctx, const char* key, int value)
@@ -1182,6 +1187,8 @@ extern "C" int cwa_set_tuning(cwa_ctx* ctx, const char* key, int value)
     else if (k == "nb_cap_f") { CWA_CHECK(value >= 0 && value <= FORCE_CAP_MAX, "nb_cap_f %d out of range", value); g_tune.cap_f = value; }
     else if (k == "fused_order") { g_tune.fused_order = value ? 1 : 0; }
     else if (k == "fused_integrate") { g_tune.fused_integrate = value ? 1 : 0; }
+    else if (k == "nbr_k") { CWA_CHECK(value >= 8 && value <= NBR_K_MAX && value % 4 == 0, "nbr_k %d: multiple of 4 in [8, %d]", value, NBR_K_MAX); g_tune.nbr_k = value; }
+    else if (k == "extreme_candidates") { CWA_CHECK(value >= 16, "extreme_candidates %d too small", value); g_tune.extreme = value; }
     else if (k == "wave_transpose") { wave_set_transpose(value); }
     else if (k == "scan_config") { CWA_CHECK(scan_set_config(value) == 0, "scan_config %d out of range", value); }
     else if (k == "pipeline") { CWA_CHECK(value >= 0 && value <= 3, "pipeline %d out of range", value); g_tune.pipeline = value; }
@@ -1228,13 +1235,21 @@ static int launch_density_list(cwa_ctx* ctx, SphObj* s, GridObj* g, TexView tex)
     const int ntiles = ceil_div(s->n, TILE_P);
     const bool local = tex_view_is_local(tex);
     int* const hc = s->heavy_cnt;                        // queue counter, zeroed by the reorder pass of this snapshot
+    const int K = nbr_k();
+    if (s->nbr_k_alloc < K) {                            // the list capacity was raised after the object was created
+        CWA_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(s->nbr_list);
+        CWA_CUDA(cudaMalloc(&s->nbr_list, (size_t)(s->capacity > 0 ? s->capacity : 1) * K * 4));
+        s->nbr_k_alloc = K;
+    }
+    s->nbr_k_used = K;
     { KScope k(ctx, KID_DENSITY);
       if (local)
-          sph3_density_list_kernel<NBR_K, true><<<ntiles, TILE_P, 0, ctx->stream>>>(
-              s->posS, s->velS, s->pack, s->nbr_list, s->nbr_count, s->heavy_queue, hc, s->n, g->view, g->offset, cc, tex);
+          sph3_density_list_kernel<true><<<ntiles, TILE_P, 0, ctx->stream>>>(
+              s->posS, s->velS, s->pack, s->nbr_list, s->nbr_count, s->heavy_queue, hc, s->n, g->view, g->offset, cc, tex, K, extreme_candidates());
       else
-          sph3_density_list_kernel<NBR_K, false><<<ntiles, TILE_P, 0, ctx->stream>>>(
-              s->posS, s->velS, s->pack, s->nbr_list, s->nbr_count, s->heavy_queue, hc, s->n, g->view, g->offset, cc, tex); }
+          sph3_density_list_kernel<false><<<ntiles, TILE_P, 0, ctx->stream>>>(
+              s->posS, s->velS, s->pack, s->nbr_list, s->nbr_count, s->heavy_queue, hc, s->n, g->view, g->offset, cc, tex, K, extreme_candidates()); }
     { KScope k(ctx, KID_HEAVY);
       if (local)
           sph3_density_heavy_kernel<true><<<heavy_grid(ctx), 128, 0, ctx->stream>>>(
@@ -1254,8 +1269,8 @@ static int launch_force_list(cwa_ctx* ctx, SphObj* s, GridObj* g, bool fused, fl
     const FinishArgs fa{s->forceS, s->miscS, g->index_list, aos, tex};
     const int blocks = ceil_div(s->n, TILE_P);
     const bool local = tex_view_is_local(tex);
-#define CWA_FORCE_LIST(F, L) sph3_force_list_kernel<NBR_K, F, L><<<blocks, TILE_P, 0, ctx->stream>>>( \
-        s->pack, s->nbr_list, s->nbr_count, fq, s->heavy_cnt + 1, s->pairP, s->pairV, s->n, g->view, g->offset, cc, fa)
+#define CWA_FORCE_LIST(F, L) sph3_force_list_kernel<F, L><<<blocks, TILE_P, 0, ctx->stream>>>( \
+        s->pack, s->nbr_list, s->nbr_count, fq, s->heavy_cnt + 1, s->pairP, s->pairV, s->n, g->view, g->offset, cc, fa, s->nbr_k_used)
 #define CWA_FORCE_HEAVY(F, L) sph3_force_heavy_kernel<F, L><<<heavy_grid(ctx), 128, 0, ctx->stream>>>( \
         s->pack, fq, s->heavy_cnt + 1, s->n, s->pairP, s->pairV, g->view, g->offset, cc, fa)
     { KScope k(ctx, KID_FORCE);
@@ -1463,7 +1478,8 @@ extern "C" int cwa_sph_create(cwa_ctx* ctx, cwa_buf particles, int n, cwa_grid g
         CWA_CUDA(cudaMalloc(&s.miscS, bytes));
         CWA_CUDA(cudaMalloc(&s.pairP, bytes));
         CWA_CUDA(cudaMalloc(&s.pairV, bytes / 2));
-        CWA_CUDA(cudaMalloc(&s.nbr_list, (size_t)(n > 0 ? n : 1) * NBR_K * 4));
+        s.nbr_k_alloc = nbr_k();
+        CWA_CUDA(cudaMalloc(&s.nbr_list, (size_t)(n > 0 ? n : 1) * s.nbr_k_alloc * 4));
         CWA_CUDA(cudaMalloc(&s.nbr_count, (size_t)(n > 0 ? n : 1) * 4));
         CWA_CUDA(cudaMalloc(&s.heavy_queue, (size_t)(n > 0 ? n : 1) * 2 * 4));
         CWA_CUDA(cudaMalloc(&s.heavy_cnt, 16));
