@@ -35,9 +35,11 @@ WAVE_COUPLED, WAVE_SIMP = 0, 1
 COUPLING_AS_SHIPPED, COUPLING_LATEST = 0, 1
 SPH2_KOSCHIER, SPH2_WAVE = 0, 1
 GRID_COUNTER, GRID_OFFSET, GRID_INDEX_LIST, GRID_CELL_OF = 0, 1, 2, 3
+STENCIL1D_SHALLOW, STENCIL1D_WAVE = 0, 1
+BC_REFLECT, BC_FREE, BC_FIXED = 0, 1, 2
 
 __all__ = [
-    "Context", "Buffer", "UniformGrid", "StencilImage2DTripleBuffered", "Sph", "SphUgrid", "ComputeShader",
+    "Context", "Buffer", "UniformGrid", "StencilImage2DTripleBuffered", "ImageStencil", "Sph", "SphUgrid", "ComputeShader",
     "CwaError", "PARTICLE", "PARTICLE2D",
 ]
 
@@ -427,6 +429,67 @@ class SphUgrid:
 
     def destroy(self):
         check(self.ctx.lib.cwa_sph2_destroy(self.ctx.h, self.h))
+
+
+class ImageStencil:
+    """ImageStencil (SphWave2D/StencilImage2D.h:10-66) on a 1-D RGBA32F image, driving Shallow1D_cs.glsl (double buffered,
+    modes 2,3 per frame) or Wave1D_cs.glsl (triple buffered, 10 substeps of mode 2) -- the wave the 2-D SPH couples to."""
+
+    def __init__(self, ctx: Context, shader: int, width: int):
+        self.ctx, self.shader, self.w = ctx, shader, width
+        o = C.c_int(-1)
+        check(ctx.lib.cwa_stencil1d_create(ctx.h, shader, width, C.byref(o)))
+        self.h = o.value
+        self.num_images = self.state()["num_images"]
+
+    def Reinit(self):
+        check(self.ctx.lib.cwa_stencil1d_reinit(self.ctx.h, self.h))
+
+    def ReinitFromTexture(self, rgba: np.ndarray):
+        rgba = np.ascontiguousarray(rgba, np.float32).reshape(-1, 4)
+        check(self.ctx.lib.cwa_stencil1d_reinit_from_texture(self.ctx.h, self.h, _vp(rgba), rgba.shape[0]))
+
+    def Compute(self, nframes=1):
+        check(self.ctx.lib.cwa_stencil1d_compute(self.ctx.h, self.h, nframes))
+
+    def ComputeFunc(self, mode: int):
+        check(self.ctx.lib.cwa_stencil1d_compute_func(self.ctx.h, self.h, mode))
+
+    def SetSubsteps(self, s: int):
+        check(self.ctx.lib.cwa_stencil1d_set_substeps(self.ctx.h, self.h, s))
+
+    def set_iterate(self, on: bool):
+        check(self.ctx.lib.cwa_stencil1d_set_iterate(self.ctx.h, self.h, int(on)))
+
+    def set_params(self, lam, dx_or_atten, beta, boundary=(0.0, 0.0), bc=BC_FREE):
+        check(self.ctx.lib.cwa_stencil1d_set_params(self.ctx.h, self.h, lam, dx_or_atten, beta, boundary[0], boundary[1], bc))
+
+    def state(self):
+        n = C.c_int(); ri = (C.c_int * 2)(); wi = C.c_int(); un = (C.c_int * 3)()
+        check(self.ctx.lib.cwa_stencil1d_state(self.ctx.h, self.h, C.byref(n), ri, C.byref(wi), un))
+        return {"num_images": n.value, "read_index": list(ri)[:n.value - 1], "write_index": wi.value, "unit": list(un)[:n.value]}
+
+    def read_image(self, image: int) -> np.ndarray:
+        out = np.empty((self.w, 4), np.float32)
+        check(self.ctx.lib.cwa_stencil1d_read_image(self.ctx.h, self.h, image, _vp(out)))
+        return out
+
+    def write_image(self, image: int, rgba: np.ndarray):
+        rgba = np.ascontiguousarray(rgba, np.float32)
+        assert rgba.shape == (self.w, 4)
+        check(self.ctx.lib.cwa_stencil1d_write_image(self.ctx.h, self.h, image, _vp(rgba)))
+
+    def GetReadImage(self, i: int = 0) -> np.ndarray:
+        return self.read_image(self.state()["read_index"][i])
+
+    def read_buffer(self, i: int = 0) -> Buffer:
+        """GetReadImage(i) as a Buffer (what SphUgrid.bind_wave1d takes: wave1d.GetReadImage(0).BindTextureUnit(), Main.cpp:240)."""
+        b = C.c_int()
+        check(self.ctx.lib.cwa_stencil1d_image_buffer(self.ctx.h, self.h, self.state()["read_index"][i], C.byref(b)))
+        return Buffer(self.ctx, handle=b.value, nbytes=self.w * 16)
+
+    def destroy(self):
+        check(self.ctx.lib.cwa_stencil1d_destroy(self.ctx.h, self.h))
 
 
 class ComputeShader:

@@ -110,6 +110,19 @@ SIGNATURES = {
     "wave_step": (_I, [_P, _I]),
     "cwa_sph_set_count": (_I, [_P, _I, _I]),
     "cwa_particles_copy_if": (_I, [_P, _I, _I, _I, _I, _F, _F, _I, _I, _IP]),
+    "cwa_stencil1d_create": (_I, [_P, _I, _I, _P]),
+    "cwa_stencil1d_destroy": (_I, [_P, _I]),
+    "cwa_stencil1d_reinit": (_I, [_P, _I]),
+    "cwa_stencil1d_reinit_from_texture": (_I, [_P, _I, _P, _I]),
+    "cwa_stencil1d_compute": (_I, [_P, _I, _I]),
+    "cwa_stencil1d_compute_func": (_I, [_P, _I, _I]),
+    "cwa_stencil1d_set_params": (_I, [_P, _I, _F, _F, _F, _F, _F, _I]),
+    "cwa_stencil1d_set_substeps": (_I, [_P, _I, _I]),
+    "cwa_stencil1d_set_iterate": (_I, [_P, _I, _I]),
+    "cwa_stencil1d_state": (_I, [_P, _I, _P, _P, _P, _P]),
+    "cwa_stencil1d_image_buffer": (_I, [_P, _I, _I, _P]),
+    "cwa_stencil1d_read_image": (_I, [_P, _I, _I, _P]),
+    "cwa_stencil1d_write_image": (_I, [_P, _I, _I, _P]),
     "cwa_slab_pack": (_I, [_P, _I, _I, _F, _F, _F, _I, _I, _I, _I]),
     "cwa_sph_step_slab": (_I, [_P, _I, _I, _F, _F, _F, _I, _I, _I, _I]),
     "cwa_slab_unpack": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _IP]),

@@ -150,6 +150,7 @@ extern "C" void cwa_destroy(cwa_ctx* ctx)
     for (size_t i = 0; i < ctx->sphs.size(); i++) if (ctx->sphs[i].live) cwa_sph_destroy(ctx, (int)i);
     for (size_t i = 0; i < ctx->sph2s.size(); i++) if (ctx->sph2s[i].live) cwa_sph2_destroy(ctx, (int)i);
     for (size_t i = 0; i < ctx->waves.size(); i++) if (ctx->waves[i].live) cwa_wave_destroy(ctx, (int)i);
+    for (size_t i = 0; i < ctx->stencil1ds.size(); i++) if (ctx->stencil1ds[i].live) cwa_stencil1d_destroy(ctx, (int)i);
     for (size_t i = 0; i < ctx->grids.size(); i++) if (ctx->grids[i].live) cwa_grid_destroy(ctx, (int)i);
     for (auto& b : ctx->buffers) if (b.live && b.owned && b.ptr) cudaFree(b.ptr);
     if (ctx->scan_ticket) cudaFree(ctx->scan_ticket);

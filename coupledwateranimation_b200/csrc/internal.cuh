@@ -191,6 +191,19 @@ struct Sph2Obj {
     float4 *posS = nullptr, *velS = nullptr, *accS = nullptr;   // cell-ordered snapshot of the read buffer
 };
 
+// ImageStencil driving Shallow1D_cs / Wave1D_cs (SphWave2D/StencilImage2D.h:10-66)
+struct Stencil1dObj {
+    bool live = false;
+    int  shader = 0, w = 1, num_images = 2;
+    float4* image[3] = {nullptr, nullptr, nullptr};      // RGBA32F texels
+    cwa_buf image_buf[3] = {-1, -1, -1};
+    int  read_index[2] = {0, 1}, write_index = 1, unit[3] = {0, 1, 2};
+    int  substeps = 1, mode_iter_first = 2, mode_iter_last = 2;
+    bool iterate = true;
+    float lambda = 0.001f, dx_or_atten = 0.1f, beta = 0.001f, boundary[2] = {0.0f, 0.0f};
+    int  bc = CWA_BC_FREE;
+};
+
 struct ShaderObj {
     bool live = false;
     std::string name;
@@ -228,6 +241,7 @@ struct cwa_ctx {
     std::vector<WaveObj>   waves;
     std::vector<SphObj>    sphs;
     std::vector<Sph2Obj>   sph2s;
+    std::vector<Stencil1dObj> stencil1ds;
     std::vector<ShaderObj> shaders;
     cwa_buf ssbo_binding[16];
     cwa_buf ubo_binding[8];

@@ -35,6 +35,7 @@ typedef int cwa_buf;    /* Buffer                        (SphWave2D/Buffer.h:5-2
 typedef int cwa_wave;   /* StencilImage2DTripleBuffered  (StencilImage2DTripleBuffered.h:8-41)       */
 typedef int cwa_grid;   /* UniformGridSph2D / UgridParticles3D (UniformGridGpu2D.h:82-142, UniformGridParticles3D.h:50-130) */
 typedef int cwa_sph;    /* the 3 SPH compute programs + particle SSBO of Main.cpp:540-557           */
+typedef int cwa_stencil1d; /* ImageStencil on a 1-D image  (SphWave2D/StencilImage2D.h:10-66)         */
 typedef int cwa_sph2;   /* SphUgrid                      (SphWave2D/StencilBuffer.h:64-79)           */
 typedef int cwa_shader; /* ComputeShader                 (CoupledWaterAnimation/ComputeShader.h:7-39) */
 
@@ -226,6 +227,29 @@ CWA_API int cwa_sph2_compute(cwa_ctx* ctx, cwa_sph2 s, int nframes);            
 CWA_API int cwa_sph2_read(cwa_ctx* ctx, cwa_sph2 s, cwa_particle2d* host);               /* GetReadBuffer(); synchronises */
 CWA_API int cwa_sph2_write(cwa_ctx* ctx, cwa_sph2 s, const cwa_particle2d* host);
 CWA_API int cwa_sph2_read_buffer(cwa_ctx* ctx, cwa_sph2 s, cwa_buf* out);
+
+/* ---- ImageStencil + the 1-D wave shaders of the 2-D app ---------------------------------------------------------
+ * Shallow1D_cs.glsl (two-phase Lax-Wendroff shallow water, RGBA32F texel = (h, uh, hm, uhm), double buffered, modes 2,3 per frame:
+ * SphWave2D/Main.cpp:77-97) and Wave1D_cs.glsl (damped wave equation, texel = (u, v, a, -), triple buffered, 10 substeps:
+ * Main.cpp:63-75).  The object reproduces ImageStencil's bookkeeping (mReadIndex / mWriteIndex / per-image unit, PingPong as
+ * written); the shaders address the images by unit.  A whole Compute() call is one kernel launch. */
+enum { CWA_STENCIL1D_SHALLOW = 0, CWA_STENCIL1D_WAVE = 1 };
+enum { CWA_BC_REFLECT = 0, CWA_BC_FREE = 1, CWA_BC_FIXED = 2 };       /* shader const BC = FREE (Shallow1D_cs.glsl:84-87), promoted */
+CWA_API int cwa_stencil1d_create(cwa_ctx* ctx, int shader, int width, cwa_stencil1d* out);   /* SetShader + SetNumBuffers + SetGridSize + Init (ends with Reinit) */
+CWA_API int cwa_stencil1d_destroy(cwa_ctx* ctx, cwa_stencil1d s);
+CWA_API int cwa_stencil1d_reinit(cwa_ctx* ctx, cwa_stencil1d s);                             /* Reinit :85-105 */
+CWA_API int cwa_stencil1d_reinit_from_texture(cwa_ctx* ctx, cwa_stencil1d s, const float* rgba, int width); /* ReinitFromTexture :122-140; synchronises */
+CWA_API int cwa_stencil1d_compute(cwa_ctx* ctx, cwa_stencil1d s, int nframes);               /* Compute :142-164, nframes times */
+CWA_API int cwa_stencil1d_compute_func(cwa_ctx* ctx, cwa_stencil1d s, int mode);             /* ComputeFunc(mode) :107-120, e.g. Splash = mode 1 */
+/* uniforms at locations 2..5 (lambda; dx for the shallow-water shader, atten for the wave shader; beta; boundary) + the BC const */
+CWA_API int cwa_stencil1d_set_params(cwa_ctx* ctx, cwa_stencil1d s, float lambda, float dx_or_atten, float beta,
+                                     float boundary0, float boundary1, int bc);
+CWA_API int cwa_stencil1d_set_substeps(cwa_ctx* ctx, cwa_stencil1d s, int substeps);         /* SetSubsteps */
+CWA_API int cwa_stencil1d_set_iterate(cwa_ctx* ctx, cwa_stencil1d s, int iterate);           /* mIterate (GUI checkbox) */
+CWA_API int cwa_stencil1d_state(cwa_ctx* ctx, cwa_stencil1d s, int* num_images, int read_index[2], int* write_index, int unit[3]);
+CWA_API int cwa_stencil1d_image_buffer(cwa_ctx* ctx, cwa_stencil1d s, int image, cwa_buf* out); /* GetReadImage(i) = image read_index[i]; bind with cwa_sph2_bind_wave1d */
+CWA_API int cwa_stencil1d_read_image(cwa_ctx* ctx, cwa_stencil1d s, int image, float* host_rgba);        /* synchronises */
+CWA_API int cwa_stencil1d_write_image(cwa_ctx* ctx, cwa_stencil1d s, int image, const float* host_rgba); /* synchronises */
 
 /* ---- ComputeShader: Init / SetMode / SetGridSize / Dispatch (ComputeShader.cpp:9-56) ----------- */
 /* glsl_filename selects the CUDA kernel set that replaces that shader; unknown names fail like

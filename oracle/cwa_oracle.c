@@ -18,6 +18,153 @@
 
 #define ORC_PI 3.141592741f /* rho_pres_comp.glsl:8, force_comp.glsl:12 */
 
+/* ------------------------------------------------------------------------------------------ */
+/* 1-D wave substrates (SphWave2D/Shallow1D_cs.glsl, Wave1D_cs.glsl)               */
+/* ------------------------------------------------------------------------------------------ */
+void orc_stencil1d_params_default(orc_stencil1d_params* p, int shader)
+{
+    p->lambda = shader == 0 ? 0.001f : 0.01f;          /* Shallow1D_cs.glsl:23 / Wave1D_cs.glsl:19 */
+    p->dx_or_atten = shader == 0 ? 0.1f : 0.9995f;     /* :24 / :20 */
+    p->beta = 0.001f;                                  /* :25 / :21 */
+    p->boundary[0] = p->boundary[1] = 0.0f;            /* :26 / :22 */
+    p->bc = ORC_BC_FREE;                               /* const int BC = FREE */
+}
+
+/* imageLoad with out-of-range coordinates returns zeros */
+static inline void load4(const float* img, int w, int x, float v[4])
+{
+    if (x < 0 || x >= w) { v[0] = v[1] = v[2] = v[3] = 0.0f; return; }
+    memcpy(v, img + 4 * (size_t)x, 16);
+}
+static inline void store4(float* img, int x, const float v[4]) { memcpy(img + 4 * (size_t)x, v, 16); }
+static inline float signf_glsl(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
+/* exp() of the shaders: evaluated in double and rounded once, so CPU and GPU agree to the last bit
+ * (GLSL leaves the precision of exp implementation-defined) */
+static inline float expf_canon(float x) { return (float)exp((double)x); }
+
+/* EnforceBC of both shaders (Shallow1D_cs.glsl:169-235, Wave1D_cs.glsl:132-196).  `negate_all`: Wave1D's ReflectBC stores -c,
+ * Shallow1D's reflects the velocity channel only.  Stores happen in program order: own texel first, boundary copies after. */
+static void enforce_bc(float* out, int w, int coord, const float c[4], const orc_stencil1d_params* p, int negate_all)
+{
+    const float boundary_scale = 0.1f;
+    if (p->bc == ORC_BC_FIXED) {                                         /* FixedBC */
+        if (coord == 0)     { const float l[4] = { p->boundary[0] * boundary_scale, 0, 0, 0 }; store4(out, coord, l); return; }
+        if (coord == w - 1) { const float r[4] = { p->boundary[1] * boundary_scale, 0, 0, 0 }; store4(out, coord, r); return; }
+        store4(out, coord, c);
+        return;
+    }
+    if (coord == 0 || coord == w - 1) return;                            /* neighbours write the boundary values */
+    store4(out, coord, c);
+    float b[4] = { c[0], c[1], c[2], c[3] };
+    if (p->bc == ORC_BC_REFLECT) {
+        if (negate_all) { for (int k = 0; k < 4; k++) b[k] = -b[k]; } else b[1] = -b[1];
+    }
+    if (coord == 1) store4(out, 0, b);
+    if (coord == w - 2) store4(out, w - 1, b);
+}
+
+void orc_shallow1d_dispatch(const float* in, float* out, int w, int mode, const orc_stencil1d_params* p)
+{
+    const float VIEW_HEIGHT = 2.0f * 4.8f;
+    const float G = 9.8f;
+    const float lambda = p->lambda, dx = p->dx_or_atten;
+    /* Two sweeps reproduce the store order of a lock-step GPU: within one invocation the stores happen in program order, and an
+     * invocation's LATER store wins over a neighbour's EARLIER one to the same texel (ITERATE0's unconditional final store of the
+     * half-step values, :160, lands after every EnforceBC copy). */
+    for (int coord = 0; coord < w; coord++) {
+        if (mode == 0) {                                                 /* InitWave :120-134 */
+            float v[4] = { 0, 0, 0, 0 };
+            const float x = (float)coord / (float)(w - 1);
+            const float xc = x - 0.5f;
+            const float h_free = VIEW_HEIGHT * 0.5f;
+            const float h = (VIEW_HEIGHT * 0.1f) * expf_canon(-xc * xc / 0.005f);
+            v[0] = h_free + h;
+            v[1] = 0.5f * fabsf(h) * signf_glsl(xc);
+            store4(out, coord, v);
+        } else if (mode == 1) {                                          /* Splash :103-118 */
+            float v[4]; load4(in, w, coord, v);
+            const float x = (float)coord / (float)(w - 1);
+            const float xc = x - 0.5f;
+            const float h = (-VIEW_HEIGHT * 0.1f) * expf_canon(-xc * xc / 0.005f);
+            v[0] += h;
+            v[1] += 0.2f * fabsf(h) * signf_glsl(xc);
+            store4(out, coord, v);
+        } else if (mode == 2 || mode == 3) {                             /* IterateWave :136-167 */
+            float c[4], e[4], ww[4];
+            load4(in, w, coord, c); load4(in, w, coord + 1, e); load4(in, w, coord - 1, ww);
+            float r[4] = { c[0], c[1], c[2], c[3] };
+            if (mode == 2) {
+                const float hm = (c[0] + e[0]) / 2.0f - lambda / 2.0f * (e[1] - c[1]) / dx;
+                const float uhm = (c[1] + e[1]) / 2.0f
+                                - lambda / 2.0f * (e[1] * e[1] / e[0] + 0.5f * G * e[0] * e[0] - c[1] * c[1] / c[0] - 0.5f * G * c[0] * c[0]) / dx;
+                r[2] = hm; r[3] = uhm;
+                enforce_bc(out, w, coord, r, p, 0);
+            } else {
+                const float h = c[0] - lambda * (c[3] - ww[3]) / dx;
+                const float uh = c[1] - lambda * (c[3] * c[3] / c[2] + 0.5f * G * c[2] * c[2] - ww[3] * ww[3] / ww[2] - 0.5f * G * ww[2] * ww[2]) / dx;
+                r[0] = h; r[1] = uh;
+                enforce_bc(out, w, coord, r, p, 0);
+            }
+        }
+    }
+    if (mode == 2) {                                                     /* :160 "no BC needed for half values": every invocation, last */
+        for (int coord = 0; coord < w; coord++) {
+            float c[4], e[4];
+            load4(in, w, coord, c); load4(in, w, coord + 1, e);
+            float r[4] = { c[0], c[1], 0, 0 };
+            r[2] = (c[0] + e[0]) / 2.0f - lambda / 2.0f * (e[1] - c[1]) / dx;
+            r[3] = (c[1] + e[1]) / 2.0f
+                 - lambda / 2.0f * (e[1] * e[1] / e[0] + 0.5f * G * e[0] * e[0] - c[1] * c[1] / c[0] - 0.5f * G * c[0] * c[0]) / dx;
+            store4(out, coord, r);
+        }
+    }
+}
+
+void orc_wave1d_dispatch(const float* in0, const float* in1, float* out, int w, int mode, const orc_stencil1d_params* p)
+{
+    const float lambda = p->lambda, atten = p->dx_or_atten, beta = p->beta;
+    const float boundary_scale = 0.1f;
+    if (mode == 0 || mode == 1) {                                        /* InitWave :98-121 */
+        /* sweep 1: every invocation's first store (the initial profile) ... */
+        for (int coord = 0; coord < w; coord++) {
+            float v[4] = { 0, 0, 0, 0 };
+            const int cen = (int)(0.25f * (float)w) + 1 * mode;
+            const int x = cen - coord;
+            float d0 = 0.0f;
+            if (p->bc == ORC_BC_FIXED) {
+                const float a = p->boundary[0] * boundary_scale, b = p->boundary[1] * boundary_scale, t = (float)coord / (float)(w - 1);
+                d0 = a * (1.0f - t) + b * t;                              /* mix(a, b, t) */
+            }
+            v[0] = d0 + 0.1f * expf_canon((float)(-x * x) / 5000.0f);
+            store4(out, coord, v);
+        }
+        if (mode == 1) {                                                 /* ... sweep 2: MODE_INIT_1 then steps once from the INPUT images */
+            for (int coord = 0; coord < w; coord++) {
+                float c1[4], c0[4], e0[4], w0[4], r[4];
+                load4(in1, w, coord, c1); load4(in0, w, coord, c0); load4(in0, w, coord + 1, e0); load4(in0, w, coord - 1, w0);
+                for (int k = 0; k < 4; k++) r[k] = c0[k] - (0.5f * lambda) * (e0[k] - 2.0f * c0[k] + w0[k]);
+                const float rx = r[0];
+                r[1] = (rx - c1[0]) / 2.0f;                               /* ComputeVelocityAcceleration :73-79 */
+                r[2] = (rx - 2.0f * c0[0] + c1[0]);
+                enforce_bc(out, w, coord, r, p, 1);
+            }
+        }
+        return;
+    }
+    if (mode != 2) return;
+    const float kc = 2.0f - 2.0f * lambda - beta, k1 = 1.0f - beta;
+    for (int coord = 0; coord < w; coord++) {                            /* IterateWave :123-130 */
+        float c1[4], c0[4], e0[4], w0[4], r[4];
+        load4(in1, w, coord, c1); load4(in0, w, coord, c0); load4(in0, w, coord + 1, e0); load4(in0, w, coord - 1, w0);
+        for (int k = 0; k < 4; k++) r[k] = atten * (kc * c0[k] + lambda * (e0[k] + w0[k]) - k1 * c1[k]);
+        const float rx = r[0];
+        r[1] = (rx - c1[0]) / 2.0f;
+        r[2] = (rx - 2.0f * c0[0] + c1[0]);
+        enforce_bc(out, w, coord, r, p, 1);
+    }
+}
+
+
 int orc_num_threads(void)
 {
 #ifdef _OPENMP

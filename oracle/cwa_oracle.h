@@ -155,6 +155,25 @@ int orc_sph2_step(orc_particle2* buf0, orc_particle2* buf1, int read_index, int 
                   const orc_params2* prm, const orc_tex* wave1d, const orc_grid2* g,
                   int* counter, int* offset, int* index_list, int* cell_of);
 
+/* ---- the 1-D wave substrates of the 2-D app -----------------------------------
+ * SphWave2D/Shallow1D_cs.glsl (two-phase Lax-Wendroff shallow water, RGBA32F texel = (h, uh, hm, uhm), double buffered) and
+ * SphWave2D/Wave1D_cs.glsl (damped 1-D wave equation, texel = (u, v, a, -), triple buffered), driven by ImageStencil
+ * (SphWave2D/StencilImage2D.cpp:67-164).  One call = ONE dispatch of the shader: `out` holds the previous contents of the output
+ * image (texels the shader does not store stay as they are); imageLoad outside the image returns 0 (GL robust access). */
+enum { ORC_BC_REFLECT = 0, ORC_BC_FREE = 1, ORC_BC_FIXED = 2 };          /* Shallow1D_cs.glsl:84-87: const int BC = FREE */
+typedef struct {
+    float lambda;        /* location 2: 0.001 (shallow) / 0.01 (wave) */
+    float dx_or_atten;   /* location 3: dx = 0.1 (shallow) / atten = 0.9995 (wave) */
+    float beta;          /* location 4: 0.001 */
+    float boundary[2];   /* location 5: vec2(0) */
+    int   bc;            /* shader const BC, promoted; FREE as shipped */
+} orc_stencil1d_params;
+void orc_stencil1d_params_default(orc_stencil1d_params* p, int shader /*0 shallow, 1 wave*/);
+/* uMode: 0 InitWave, 1 Splash, 2 ITERATE0, 3 ITERATE1 (Shallow1D_cs.glsl:11-15,57-76) */
+void orc_shallow1d_dispatch(const float* in, float* out, int w, int mode, const orc_stencil1d_params* p);
+/* uMode: 0 / 1 InitWave, 2 ITERATE; in0 = t-1 (unit 0), in1 = t-2 (unit 1) (Wave1D_cs.glsl:11-14,57-71) */
+void orc_wave1d_dispatch(const float* in0, const float* in1, float* out, int w, int mode, const orc_stencil1d_params* p);
+
 int orc_num_threads(void);
 
 #ifdef __cplusplus

@@ -33,6 +33,10 @@ class Params3(C.Structure):
     ]
 
 
+class Stencil1DParams(C.Structure):
+    _fields_ = [("lam", C.c_float), ("dx_or_atten", C.c_float), ("beta", C.c_float), ("boundary", C.c_float * 2), ("bc", C.c_int)]
+
+
 class Params2(C.Structure):
     _fields_ = [("variant", C.c_int), ("time", C.c_float), ("bottom", C.c_float), ("psi", C.c_float),
                 ("init_width", C.c_int), ("view_width", C.c_float)]
@@ -88,6 +92,9 @@ def lib():
         L.orc_coupled_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Params3), C.c_int, C.c_int,
                                          C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_coupled_destroy.argtypes = [C.c_void_p]
+        L.orc_stencil1d_params_default.argtypes = [C.POINTER(Stencil1DParams), C.c_int]
+        L.orc_shallow1d_dispatch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(Stencil1DParams)]
+        L.orc_wave1d_dispatch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(Stencil1DParams)]
         L.orc_coupled_particles.restype = C.c_void_p
         L.orc_coupled_particles.argtypes = [C.c_void_p]
         L.orc_coupled_wave.restype = C.c_void_p
@@ -359,3 +366,106 @@ def ref_grid2d_build(xy: np.ndarray, mn, mx, ncells):
     if rc != 0:
         raise RuntimeError("reference grid build failed")
     return counter, offset, index_list, cs
+
+
+# ------------------------------------------------------------------------------------------------
+# 1-D wave substrates + ImageStencil (SphWave2D/StencilImage2D.cpp:67-164)
+# ------------------------------------------------------------------------------------------------
+STENCIL1D_SHALLOW, STENCIL1D_WAVE = 0, 1
+BC_REFLECT, BC_FREE, BC_FIXED = 0, 1, 2
+
+
+def default_stencil1d_params(shader: int) -> Stencil1DParams:
+    p = Stencil1DParams()
+    lib().orc_stencil1d_params_default(C.byref(p), C.c_int(shader))
+    return p
+
+
+def shallow1d_dispatch(inp: np.ndarray, out: np.ndarray, mode: int, prm: Stencil1DParams) -> None:
+    """One dispatch of Shallow1D_cs.glsl; `out` ([w,4] float32) is updated in place (unwritten texels keep their value)."""
+    assert inp.dtype == np.float32 and out.dtype == np.float32 and inp.shape == out.shape and inp.shape[1] == 4
+    lib().orc_shallow1d_dispatch(_ptr(np.ascontiguousarray(inp)), _ptr(out), inp.shape[0], mode, C.byref(prm))
+
+
+def wave1d_dispatch(in0: np.ndarray, in1: np.ndarray, out: np.ndarray, mode: int, prm: Stencil1DParams) -> None:
+    assert in0.shape == in1.shape == out.shape and out.shape[1] == 4
+    lib().orc_wave1d_dispatch(_ptr(np.ascontiguousarray(in0)), _ptr(np.ascontiguousarray(in1)), _ptr(out), out.shape[0], mode, C.byref(prm))
+
+
+class ImageStencil:
+    """Host bookkeeping of ImageStencil restated line by line: N RGBA32F 1-D images, mReadIndex / mWriteIndex, per-image
+    unit (SwapUnits), Reinit / Compute / ComputeFunc / ReinitFromTexture.  The shader addresses images by UNIT
+    (Shallow1D: input 0, output 1; Wave1D: input0 0, input1 1, output 2), which is what the dispatch below does."""
+
+    def __init__(self, shader: int, width: int, prm: Stencil1DParams | None = None):
+        self.shader, self.w = shader, width
+        self.prm = prm if prm is not None else default_stencil1d_params(shader)
+        self.substeps = 1
+        self.iterate = True
+        if shader == STENCIL1D_SHALLOW:                       # InitShallowWaterEquation, SphWave2D/Main.cpp:77-97
+            n, self.mode_iter_first, self.mode_iter_last = 2, 2, 3
+        else:                                                 # InitWaveEquation, SphWave2D/Main.cpp:63-75
+            n, self.mode_iter_first, self.mode_iter_last = 3, 2, 2
+            self.substeps = 10
+        self.mode_init_first = 0
+        self.set_num_buffers(n)
+        self.image = [np.zeros((width, 4), np.float32) for _ in range(self.num_images)]     # fresh texture storage: zeros
+        self.unit = list(range(self.num_images))              # Init(): mImage[i].SetUnit(i)
+        self.reinit()
+
+    def set_num_buffers(self, n: int):                        # StencilImage2D.cpp:38-65
+        self.num_images = max(1, n)
+        if self.num_images == 1:
+            self.read_index, self.write_index = [0], 0
+        else:
+            self.read_index, self.write_index = list(range(self.num_images - 1)), self.num_images - 1
+
+    def pingpong(self):                                       # :67-83
+        if self.num_images == 1:
+            return
+        r = self.read_index
+        self.write_index, r[0] = r[0], self.write_index
+        for i in range(len(r) - 1):
+            r[i], r[i + 1] = r[i + 1], r[i]
+        u = self.unit
+        u[self.write_index], u[r[0]] = u[r[0]], u[self.write_index]
+        for i in range(len(r) - 1):
+            u[r[i]], u[r[i + 1]] = u[r[i + 1]], u[r[i]]
+
+    def _with_unit(self, k: int) -> int:
+        return self.unit.index(k)
+
+    def dispatch(self, mode: int):
+        if self.shader == STENCIL1D_SHALLOW:
+            shallow1d_dispatch(self.image[self._with_unit(0)], self.image[self._with_unit(1)], mode, self.prm)
+        else:
+            wave1d_dispatch(self.image[self._with_unit(0)], self.image[self._with_unit(1)], self.image[self._with_unit(2)], mode, self.prm)
+
+    def compute_func(self, mode: int):                        # :107-120
+        self.dispatch(mode)
+        self.pingpong()
+
+    def reinit(self):                                         # :85-105
+        for i in range(len(self.read_index)):
+            self.compute_func(self.mode_init_first + i)
+
+    def reinit_from_texture(self, rgba: np.ndarray):          # :122-140, mode -1: texelFetch(uInitImage, coord)
+        out = self.image[self._with_unit(len(self.unit) - 1 if self.shader == STENCIL1D_WAVE else 1)]
+        n = min(self.w, rgba.shape[0])
+        out[:] = 0.0
+        out[:n] = rgba[:n]
+        self.pingpong()
+
+    def compute(self, nframes: int = 1):                      # :142-164
+        if not self.iterate:
+            return
+        for _ in range(nframes):
+            for _ in range(self.substeps):
+                for m in range(self.mode_iter_first, self.mode_iter_last + 1):
+                    self.compute_func(m)
+
+    def read_image(self, i: int) -> np.ndarray:               # GetReadImage(i)
+        return self.image[self.read_index[i]]
+
+    def write_image(self) -> np.ndarray:
+        return self.image[self.write_index]

@@ -255,3 +255,67 @@ def test_sph2_goldens_and_constants(oracle):
     assert p["pos"][0, 0] == np.float32(0.025) and abs(p["pos"][0, 1] - 4.45) < 1e-6
     assert abs(p["pos"][1, 0] - (0.025 + 9.6 / 128)) < 1e-6 and abs(p["pos"][128, 1] - (4.45 + 1.8 / 32)) < 1e-6
     assert (p["acc"][:, 3] == 1000.0).all()
+
+
+# ---- 1-D wave substrates -----------------------------------------------------------
+def test_image_stencil_bookkeeping_as_written(oracle):
+    """ImageStencil::PingPong (StencilImage2D.cpp:67-83) rotates the UNITS cyclically (output -> 0 -> 1 -> output) while the
+    index arrays follow a different permutation for three buffers -- reproduced as written."""
+    s = oracle.ImageStencil(oracle.STENCIL1D_WAVE, 64)
+    assert (s.unit, s.read_index, s.write_index) == ([2, 0, 1], [2, 0], 1)          # after Init() = Reinit(): two dispatches
+    for _ in range(9):
+        before = list(s.unit)
+        s.pingpong()
+        assert s.unit == [0 if u == 2 else u + 1 for u in before]
+    d = oracle.ImageStencil(oracle.STENCIL1D_SHALLOW, 16)
+    assert (d.unit, d.read_index, d.write_index) == ([1, 0], [1], 0)
+
+
+def test_shallow1d_init_profile_and_conservation(oracle):
+    s = oracle.ImageStencil(oracle.STENCIL1D_SHALLOW, 128)
+    im = s.read_image(0)
+    x = np.arange(128, dtype=np.float32) / np.float32(127)
+    h = 9.6 * 0.1 * np.exp(-((x - 0.5) ** 2) / 0.005)
+    assert np.allclose(im[:, 0], 4.8 + h, rtol=1e-6) and np.allclose(im[:, 1], 0.5 * h * np.sign(x - 0.5), rtol=1e-5, atol=1e-7)
+    assert not im[:, 2:].any()
+    m0 = im[1:-1, 0].astype(np.float64).sum()
+    s.compute(500)
+    r = s.read_image(0)
+    assert np.isfinite(r[:, :2]).all() and abs(r[1:-1, 0].astype(np.float64).sum() - m0) < 1e-3 * m0
+    # free boundary: the end texels are copies of their neighbours (FreeBC, Shallow1D_cs.glsl:176-193)
+    assert np.array_equal(r[0], r[1]) and np.array_equal(r[-1], r[-2])
+
+
+def test_shallow1d_half_step_store_wins_over_boundary_copies(oracle):
+    """ITERATE0 ends with an unconditional imageStore of the half-step values (:160): texel 0 holds its OWN (hm, uhm), not the copy
+    of texel 1 that FreeBC wrote earlier, and texel w-1 the values computed against the zero read beyond the image (uhm = NaN)."""
+    prm = oracle.default_stencil1d_params(oracle.STENCIL1D_SHALLOW)
+    rng = np.random.default_rng(7)
+    inp = np.zeros((16, 4), np.float32)
+    inp[:, 0] = rng.uniform(4.5, 5.5, 16); inp[:, 1] = rng.uniform(-0.5, 0.5, 16)
+    out = np.full((16, 4), 7.0, np.float32)
+    oracle.shallow1d_dispatch(inp, out, 2, prm)
+    hm0 = np.float32((inp[0, 0] + inp[1, 0]) / np.float32(2)) - np.float32(np.float32(0.001) / np.float32(2) * (inp[1, 1] - inp[0, 1])) / np.float32(0.1)
+    assert out[0, 2] == np.float32(hm0) and out[0, 0] == inp[0, 0]
+    assert np.isnan(out[15, 3]) and np.isfinite(out[15, 2])
+    out2 = np.full((16, 4), 7.0, np.float32)
+    oracle.shallow1d_dispatch(out, out2, 3, prm)
+    assert np.isfinite(out2).all() and np.array_equal(out2[15], out2[14]) and np.array_equal(out2[0], out2[1])
+
+
+def test_wave1d_iterate_matches_the_formula_and_damps(oracle):
+    prm = oracle.default_stencil1d_params(oracle.STENCIL1D_WAVE)
+    rng = np.random.default_rng(9)
+    u0 = np.zeros((32, 4), np.float32); u1 = np.zeros((32, 4), np.float32)
+    u0[:, 0] = rng.uniform(-0.1, 0.1, 32); u1[:, 0] = rng.uniform(-0.1, 0.1, 32)
+    out = np.zeros((32, 4), np.float32)
+    oracle.wave1d_dispatch(u0, u1, out, 2, prm)
+    lam, att, beta = 0.01, 0.9995, 0.001
+    ref = att * ((2 - 2 * lam - beta) * u0[1:-1, 0].astype(np.float64) + lam * (u0[2:, 0].astype(np.float64) + u0[:-2, 0]) - (1 - beta) * u1[1:-1, 0])
+    assert np.allclose(out[1:-1, 0], ref, rtol=1e-5, atol=1e-7)
+    assert np.allclose(out[1:-1, 1], (out[1:-1, 0] - u1[1:-1, 0]) / 2, rtol=1e-5, atol=1e-7)
+    assert np.array_equal(out[0], out[1]) and np.array_equal(out[-1], out[-2])
+    w = oracle.ImageStencil(oracle.STENCIL1D_WAVE, 1024)
+    e0 = float(np.abs(w.image[w._with_unit(0)][:, 0]).max())
+    w.compute(100)                                    # 1000 damped steps
+    assert float(np.abs(w.image[w._with_unit(0)][:, 0]).max()) < e0
