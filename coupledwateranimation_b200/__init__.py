@@ -146,6 +146,33 @@ class Context:
         self.set_sim_constants(prm.particle_radius, prm.gas_const, prm.dt, prm.gravity_y, prm.damping,
                                prm.crest_threshold, prm.foam_speed, prm.uv_scale, getattr(prm, "uv_scale_z", 0.0), getattr(prm, "torque_coeff", 0.0))
 
+    # ---- parameter reflection (name -> field of the bound parameter blocks) ---------------------------------------------
+    def params(self) -> list:
+        """[(name, ubo_binding, byte_offset, origin)] of every run-time parameter."""
+        out = []
+        for i in range(self.lib.cwa_param_count()):
+            name, origin = C.c_char_p(), C.c_char_p()
+            ubo, off = C.c_int(), C.c_int()
+            check(self.lib.cwa_param_info(i, C.byref(name), C.byref(ubo), C.byref(off), C.byref(origin)))
+            out.append((name.value.decode(), ubo.value, off.value, origin.value.decode()))
+        return out
+
+    def param_set(self, name: str, value: float):
+        check(self.lib.cwa_param_set(self.h, name.encode(), float(value)))
+
+    def param_get(self, name: str) -> float:
+        v = C.c_float()
+        check(self.lib.cwa_param_get(self.h, name.encode(), C.byref(v)))
+        return v.value
+
+    def checkpoint_save(self, sph: "Sph", wave: "StencilImage2DTripleBuffered", frame: int, path: str):
+        check(self.lib.cwa_checkpoint_save(self.h, sph.h, wave.h, int(frame), path.encode()))
+
+    def checkpoint_load(self, sph: "Sph", wave: "StencilImage2DTripleBuffered", path: str) -> int:
+        fr = C.c_ulonglong()
+        check(self.lib.cwa_checkpoint_load(self.h, sph.h, wave.h, path.encode(), C.byref(fr)))
+        return fr.value
+
     def bind_scene(self, sph: "Sph | None", wave: "StencilImage2DTripleBuffered | None"):
         check(self.lib.cwa_bind_scene(self.h, sph.h if sph else -1, wave.h if wave else -1))
 
@@ -454,6 +481,9 @@ class ImageStencil:
 
     def ComputeFunc(self, mode: int):
         check(self.ctx.lib.cwa_stencil1d_compute_func(self.ctx.h, self.h, mode))
+
+    def PingPong(self):
+        check(self.ctx.lib.cwa_stencil1d_pingpong(self.ctx.h, self.h))
 
     def SetSubsteps(self, s: int):
         check(self.ctx.lib.cwa_stencil1d_set_substeps(self.ctx.h, self.h, s))

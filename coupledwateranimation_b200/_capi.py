@@ -117,12 +117,19 @@ SIGNATURES = {
     "cwa_stencil1d_compute": (_I, [_P, _I, _I]),
     "cwa_stencil1d_compute_func": (_I, [_P, _I, _I]),
     "cwa_stencil1d_set_params": (_I, [_P, _I, _F, _F, _F, _F, _F, _I]),
+    "cwa_stencil1d_pingpong": (_I, [_P, _I]),
     "cwa_stencil1d_set_substeps": (_I, [_P, _I, _I]),
     "cwa_stencil1d_set_iterate": (_I, [_P, _I, _I]),
     "cwa_stencil1d_state": (_I, [_P, _I, _P, _P, _P, _P]),
     "cwa_stencil1d_image_buffer": (_I, [_P, _I, _I, _P]),
     "cwa_stencil1d_read_image": (_I, [_P, _I, _I, _P]),
     "cwa_stencil1d_write_image": (_I, [_P, _I, _I, _P]),
+    "cwa_param_count": (_I, []),
+    "cwa_param_info": (_I, [_I, _P, _P, _P, _P]),
+    "cwa_param_set": (_I, [_P, C.c_char_p, _F]),
+    "cwa_param_get": (_I, [_P, C.c_char_p, _P]),
+    "cwa_checkpoint_save": (_I, [_P, _I, _I, C.c_ulonglong, C.c_char_p]),
+    "cwa_checkpoint_load": (_I, [_P, _I, _I, C.c_char_p, _P]),
     "cwa_slab_pack": (_I, [_P, _I, _I, _F, _F, _F, _I, _I, _I, _I]),
     "cwa_sph_step_slab": (_I, [_P, _I, _I, _F, _F, _F, _I, _I, _I, _I]),
     "cwa_slab_unpack": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _IP]),

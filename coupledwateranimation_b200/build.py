@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcwa_b200.so")
-SOURCES = ["api.cu", "grid.cu", "wave.cu", "sph3.cu", "sph2.cu", "multi.cu", "stencil1d.cu"]
+SOURCES = ["api.cu", "grid.cu", "wave.cu", "sph3.cu", "sph2.cu", "multi.cu", "stencil1d.cu", "state.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared",

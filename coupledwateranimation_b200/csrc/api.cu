@@ -403,7 +403,7 @@ extern "C" int wave_step(cwa_ctx* ctx, int nsteps)
 // ---------------------------------------------------------------------------------------------
 // ComputeShader  (CoupledWaterAnimation/ComputeShader.cpp:9-56)
 // ---------------------------------------------------------------------------------------------
-enum ShaderKind { SK_RHO = 0, SK_FORCE, SK_INTEGRATE, SK_WAVE, SK_WAVE_SIMP, SK_PREFIX };
+enum ShaderKind { SK_RHO = 0, SK_FORCE, SK_INTEGRATE, SK_WAVE, SK_WAVE_SIMP, SK_PREFIX, SK_SHALLOW1D, SK_WAVE1D };
 
 extern "C" int cwa_shader_create(cwa_ctx* ctx, const char* glsl_filename, cwa_shader* out)
 {
@@ -419,6 +419,8 @@ extern "C" int cwa_shader_create(cwa_ctx* ctx, const char* glsl_filename, cwa_sh
     else if (n == "wave_comp.glsl") kind = SK_WAVE;
     else if (n == "Wave2D_cs.glsl") kind = SK_WAVE_SIMP;
     else if (n == "prefix_sum_cs.glsl") kind = SK_PREFIX;
+    else if (n == "Shallow1D_cs.glsl") kind = SK_SHALLOW1D;
+    else if (n == "Wave1D_cs.glsl") kind = SK_WAVE1D;
     // InitShader() returns -1 for a shader it cannot build (InitShader.cpp:105)
     CWA_CHECK(kind >= 0, "cwa_shader_create: no CUDA kernel set replaces shader '%s'", glsl_filename);
     ShaderObj s;
@@ -492,6 +494,11 @@ extern "C" int cwa_shader_dispatch(cwa_ctx* ctx, cwa_shader s, int gx, int gy, i
         // Dispatch alone runs the kernel for the current uMode on the images at units 0/1/2 and
         // does NOT rotate (StencilImage2DTripleBuffered::Compute rotates after Dispatch).
         return wave_dispatch_mode(ctx, w, o->mode);
+    }
+    case SK_SHALLOW1D: case SK_WAVE1D: {
+        // one dispatch in the current uMode on the ImageStencil object bound to the shader (cwa_shader_bind_object); like the wave
+        // shaders it does not rotate -- ImageStencil::Compute / ComputeFunc call PingPong after Dispatch (cwa_stencil1d_pingpong)
+        return stencil1d_dispatch_mode(ctx, o->object, o->mode, o->kind == SK_SHALLOW1D ? CWA_STENCIL1D_SHALLOW : CWA_STENCIL1D_WAVE);
     }
     case SK_PREFIX: {
         // one Blelloch level of prefix_sum_cs.glsl:18-43 on the buffer at SSBO binding 1

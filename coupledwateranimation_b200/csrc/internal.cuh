@@ -281,6 +281,7 @@ int  grid_build_internal(cwa_ctx* ctx, GridObj* g, const void* particles, int st
 TexView wave_tex_view(cwa_ctx* ctx, cwa_wave w, int image);           // wave.cu
 int  wave_sampling_copy(cwa_ctx* ctx, cwa_wave w, int image, TexView* tex);   // points tex->tdata at the (refreshed) transposed copy when it pays
 int  wave_set_transpose(int on);
+int  stencil1d_dispatch_mode(cwa_ctx* ctx, int handle, int mode, int shader);   // stencil1d.cu: one dispatch, no PingPong
 void wave_touch_buffer(cwa_ctx* ctx, cwa_buf b, bool raw);             // a buffer was written through the Buffer API / its raw pointer handed out
 int  wave_step_internal(cwa_ctx* ctx, WaveObj* w);
 int  wave_dispatch_mode(cwa_ctx* ctx, WaveObj* w, int mode);           // kernel for uMode on units 0/1/2, no rotation                   // one EVOLVE dispatch + PingPong

@@ -51,13 +51,6 @@ __device__ __forceinline__ void s1d_enforce_bc(float4* out, int w, int coord, fl
     if (coord == w - 2) out[w - 1] = c;
 }
 
-// flux term of the Lax-Wendroff steps: uh*uh/h + 0.5*G*h*h, left to right as written
-__device__ __forceinline__ float s1d_flux(float uh, float h)
-{
-    const float G = 9.8f;
-    return ADD(DIV(MUL(uh, uh), h), MUL(MUL(MUL(0.5f, G), h), h));
-}
-
 // One invocation of Shallow1D_cs.glsl main() for `coord`.  Stores of several invocations to the same texel are resolved the way a
 // lock-step GPU resolves them (later in program order wins): in ITERATE0 the unconditional final store (:160) overwrites every
 // EnforceBC copy, so only it is issued.
@@ -269,6 +262,33 @@ static int s1d_run(cwa_ctx* ctx, Stencil1dObj* s, int mode0, int nmodes, int ndi
         CWA_CUDA(cudaGetLastError());
         s1d_pingpong(s);
     }
+    return 0;
+}
+
+// ComputeShader::Dispatch on a bound ImageStencil object: one dispatch, roles untouched
+int stencil1d_dispatch_mode(cwa_ctx* ctx, int handle, int mode, int shader)
+{
+    Stencil1dObj* s = get_s1d(ctx, handle);
+    CWA_CHECK(s, "dispatch of a 1-D wave shader: no ImageStencil object bound to the shader (cwa_shader_bind_object)");
+    CWA_CHECK(s->shader == shader, "dispatch: the bound ImageStencil object was created for the other 1-D shader");
+    CWA_CHECK(mode >= 0 && mode <= 3, "dispatch: unsupported uMode %d", mode);
+    const int N = s->num_images, w = s->w;
+    const Stencil1dParams p = s1d_params(s);
+    const float4* in0 = s->image[s1d_image_with_unit(s, 0)];
+    const float4* in1 = (N == 3) ? s->image[s1d_image_with_unit(s, 1)] : in0;
+    float4* out = s->image[s1d_image_with_unit(s, N - 1)];
+    KScope k(ctx, KID_WAVE);
+    if (s->shader == S1D_SHALLOW) stencil1d_dispatch_kernel<S1D_SHALLOW><<<ceil_div(w, 256), 256, 0, ctx->stream>>>(in0, in1, out, w, mode, p);
+    else stencil1d_dispatch_kernel<S1D_WAVE><<<ceil_div(w, 256), 256, 0, ctx->stream>>>(in0, in1, out, w, mode, p);
+    CWA_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int cwa_stencil1d_pingpong(cwa_ctx* ctx, cwa_stencil1d h)
+{
+    Stencil1dObj* s = get_s1d(ctx, h);
+    CWA_CHECK(s, "invalid stencil1d handle %d", h);
+    s1d_pingpong(s);
     return 0;
 }
 

@@ -244,6 +244,7 @@ CWA_API int cwa_stencil1d_compute_func(cwa_ctx* ctx, cwa_stencil1d s, int mode);
 /* uniforms at locations 2..5 (lambda; dx for the shallow-water shader, atten for the wave shader; beta; boundary) + the BC const */
 CWA_API int cwa_stencil1d_set_params(cwa_ctx* ctx, cwa_stencil1d s, float lambda, float dx_or_atten, float beta,
                                      float boundary0, float boundary1, int bc);
+CWA_API int cwa_stencil1d_pingpong(cwa_ctx* ctx, cwa_stencil1d s);                           /* PingPong :67-83 (after a ComputeShader dispatch) */
 CWA_API int cwa_stencil1d_set_substeps(cwa_ctx* ctx, cwa_stencil1d s, int substeps);         /* SetSubsteps */
 CWA_API int cwa_stencil1d_set_iterate(cwa_ctx* ctx, cwa_stencil1d s, int iterate);           /* mIterate (GUI checkbox) */
 CWA_API int cwa_stencil1d_state(cwa_ctx* ctx, cwa_stencil1d s, int* num_images, int read_index[2], int* write_index, int unit[3]);
@@ -251,11 +252,26 @@ CWA_API int cwa_stencil1d_image_buffer(cwa_ctx* ctx, cwa_stencil1d s, int image,
 CWA_API int cwa_stencil1d_read_image(cwa_ctx* ctx, cwa_stencil1d s, int image, float* host_rgba);        /* synchronises */
 CWA_API int cwa_stencil1d_write_image(cwa_ctx* ctx, cwa_stencil1d s, int image, const float* host_rgba); /* synchronises */
 
+/* ---- parameter reflection (the reference's UniformGui lists a program's uniforms with glGetActiveUniform) --------
+ * name -> field of the block currently bound at UBO 1..4: "mass", "smoothing_coeff", "visc", "resting_rho", "upper.x" .. "lower.w",
+ * "wave.lambda", "wave.atten", "wave.beta", "wave.type", "mesh_ws_pos.x" .., "particle_radius", "gas_const", "dt", "gravity_y",
+ * "damping", "crest_threshold", "foam_speed", "uv_scale", "uv_scale_z", "torque_coeff". */
+CWA_API int cwa_param_count(void);
+CWA_API int cwa_param_info(int index, const char** name, int* ubo_binding, int* byte_offset, const char** origin);
+CWA_API int cwa_param_set(cwa_ctx* ctx, const char* name, float value);
+CWA_API int cwa_param_get(cwa_ctx* ctx, const char* name, float* value);                 /* synchronises */
+/* ---- checkpoint: one little-endian file {256-byte header: magic "CWACKPT1", frame, sizes, triple-buffer bookkeeping,
+ * the four parameter blocks; particle SSBO; the three physical wave images}.  Loading into objects of the same sizes resumes the run
+ * bit for bit (layout: csrc/state.cu, reader/writer for tools: coupledwateranimation_b200/checkpoint.py). */
+CWA_API int cwa_checkpoint_save(cwa_ctx* ctx, cwa_sph s, cwa_wave w, unsigned long long frame, const char* path);   /* synchronises */
+CWA_API int cwa_checkpoint_load(cwa_ctx* ctx, cwa_sph s, cwa_wave w, const char* path, unsigned long long* frame);  /* synchronises */
+
 /* ---- ComputeShader: Init / SetMode / SetGridSize / Dispatch (ComputeShader.cpp:9-56) ----------- */
 /* glsl_filename selects the CUDA kernel set that replaces that shader; unknown names fail like
  * InitShader() returning -1.  Dispatch acts on the currently bound buffers/images like
  * glDispatchCompute.  Supported: rho_pres_comp.glsl, force_comp.glsl, integrate_comp.glsl,
- * wave_comp.glsl, Wave2D_cs.glsl, prefix_sum_cs.glsl. */
+ * wave_comp.glsl, Wave2D_cs.glsl, prefix_sum_cs.glsl, Shallow1D_cs.glsl, Wave1D_cs.glsl (the last two dispatch on the
+ * cwa_stencil1d object given to cwa_shader_bind_object, with that object's parameters). */
 CWA_API int cwa_shader_create(cwa_ctx* ctx, const char* glsl_filename, cwa_shader* out);
 CWA_API int cwa_shader_set_mode(cwa_ctx* ctx, cwa_shader s, int mode);
 CWA_API int cwa_shader_set_uniform_i(cwa_ctx* ctx, cwa_shader s, int location, int v);

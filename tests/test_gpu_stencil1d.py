@@ -87,6 +87,29 @@ def test_splash_compute_func_and_reinit_from_texture(cwa, ctx, oracle):
     assert _bits_equal(before, g.GetReadImage(0))
 
 
+@pytest.mark.parametrize("shader", [0, 1])
+def test_compute_shader_dispatch_plus_pingpong_equals_compute_func(cwa, ctx, shader):
+    """Driving the object the way ImageStencil::ComputeFunc does -- SetMode, Dispatch, PingPong (StencilImage2D.cpp:107-120)."""
+    name = "Shallow1D_cs.glsl" if shader == 0 else "Wave1D_cs.glsl"
+    a = cwa.ImageStencil(ctx, shader, 256)
+    b = cwa.ImageStencil(ctx, shader, 256)
+    cs = cwa.ComputeShader(ctx, name)
+    cs.bind_object(b)
+    modes = [2, 3, 2, 3, 1] if shader == 0 else [2, 2, 2]
+    for m in modes:
+        a.ComputeFunc(m)
+        cs.SetMode(m)
+        cs.Dispatch(1, 1, 1)
+        b.PingPong()
+    assert a.state() == b.state()
+    for i in range(a.num_images):
+        assert _bits_equal(a.read_image(i), b.read_image(i))
+    with pytest.raises(cwa.CwaError):
+        other = cwa.ComputeShader(ctx, "Wave1D_cs.glsl" if shader == 0 else "Shallow1D_cs.glsl")
+        other.bind_object(b)
+        other.Dispatch(1, 1, 1)
+
+
 def test_shallow_water_stays_finite_and_drains_only_through_the_free_ends(cwa, ctx):
     g = cwa.ImageStencil(ctx, cwa.STENCIL1D_SHALLOW, 128)
     h0 = g.GetReadImage(0)[:, 0].astype(np.float64)
