@@ -295,9 +295,9 @@ def run_native(args):
 
     # ---- end to end through the C ABI with HOST buffers -------------------------------------------
     # Every step: particle SSBO + the two wave levels the stencil reads go up from pinned host memory, one coupled frame runs,
-    # the particle SSBO + the new wave level come back.  Two scene streams (two library contexts = two CUDA streams, each with
-    # its own device objects and pinned buffers) alternate, so the upload of step k+1 overlaps the frame and the read-back of
-    # step k on the two copy engines of the PCIe link; a step is complete when its results are in host memory
+    # the particle SSBO + the new wave level come back.  A few scene streams (library contexts = CUDA streams, each with its
+    # own device objects and pinned buffers; CWA_E2E_SLOTS, default 3) take turns, so the upload of step k+1 overlaps the frame and
+    # the read-back of step k on the two copy engines of the PCIe link; a step is complete when its results are in host memory
     # (cwa_synchronize of its context, called before the slot is reused and at the end of the timed region).
     import ctypes as C
 
@@ -320,23 +320,27 @@ def run_native(args):
             hw[0], hw[1] = hw[1], hw[0]                   # the previous newest level becomes u(t-2) ...
             cwa.check(lib.cwa_wave_read_image_async(h, wv.h, wv.role_image(0), C.c_void_p(hw[0].ctypes.data)))   # ... and the new level is read back
 
-    ctx2 = cwa.Context(local_rank)
-    grid2, sph2, wave2 = build_scene(cwa, ctx2)
-    slots = [Slot(ctx, sph, wave), Slot(ctx2, sph2, wave2)]
+    n_slots = max(2, min(4, int(os.environ.get("CWA_E2E_SLOTS", "3"))))
+    slots = [Slot(ctx, sph, wave)]
+    extra = []
+    for _ in range(n_slots - 1):
+        cx = cwa.Context(local_rank)
+        extra.append((cx,) + tuple(build_scene(cwa, cx)))
+        slots.append(Slot(cx, extra[-1][2], extra[-1][3]))
     state_p, state_w0, state_w1 = sph.download(), wave.read_role(0), wave.read_role(1)
     for sl in slots:
         sl.host_p[:] = state_p
         sl.host_w[0][:] = state_w0
         sl.host_w[1][:] = state_w1
-    for k in range(4):
-        slots[k % 2].ctx.synchronize()
-        slots[k % 2].submit()
+    for k in range(2 * n_slots):
+        slots[k % n_slots].ctx.synchronize()
+        slots[k % n_slots].submit()
     for sl in slots:
         sl.ctx.synchronize()
     barrier()
     t0 = time.perf_counter()
     for k in range(K):
-        sl = slots[k % 2]
+        sl = slots[k % n_slots]
         sl.ctx.synchronize()                              # the slot's previous step is complete: its results are in host memory
         sl.submit()
     for sl in slots:
@@ -399,7 +403,7 @@ def run_native(args):
         "clocks": clocks,
         "e2e": {"value": world * N_PARTICLES * K / e2e_s, "unit": "particle-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s / K * 1e3, "ms_per_step_unpipelined": e2e_serial_s * 1e3,
-                "how": "C ABI, pinned host buffers; two scene streams alternate so step k+1's upload overlaps step k's frame and read-back; "
+                "how": f"C ABI, pinned host buffers; {n_slots} scene streams take turns so step k+1's upload overlaps step k's frame and read-back; "
                        "a step counts when its results are in host memory"},
         "gpu_launches": int(launches),
         "roofline": roofline,

@@ -657,6 +657,43 @@ sph3_density_list_kernel(const float4* __restrict__ posS, const float4* __restri
     nbr_count[slot] = cnt;
 }
 
+// Candidate enumeration of the heavy kernels (one warp per target).  The rows of a query are short where particles pile up on a wall
+// (two or three cells along k, each crowded), so walking them one after the other leaves a single load in flight per lane and a partly
+// filled warp at every row end.  Instead lanes 0..nrows-1 fetch the row bounds, a warp scan turns the row lengths into a flat index
+// space [0, total) (prefix + first slot of each row parked in 2 x 33 ints of shared memory per warp), and lane l takes the flat
+// candidates l, l + 32, ... four at a time: four independent loads in flight, every lane busy until the last trip.
+struct HeavyRows { int total; };
+constexpr int HEAVY_WARPS = 4;            // warps per CTA of the heavy kernels (128 threads)
+
+__device__ __forceinline__ int heavy_rows_setup(const GridView& g, const int* __restrict__ offset, const Query3& q, int nj, int nrows, int lane,
+                                                int* sP, int* sG)
+{
+    int g0 = 0, len = 0;
+    if (lane < nrows) {
+        const int base = ((q.i0 + lane / nj) * g.n[1] + (q.j0 + lane % nj)) * g.kstride;
+        g0 = __ldg(offset + base + q.k0);
+        len = __ldg(offset + base + q.k1 + 1) - g0;
+    }
+    int incl = len;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    __syncwarp();                          // the previous target's reads of sP / sG are done
+    sP[lane] = incl - len; sG[lane] = g0;
+    if (lane == 31) sP[32] = incl;
+    __syncwarp();
+    return __shfl_sync(0xffffffffu, incl, 31);
+}
+
+// flat candidate f -> cell-ordered slot; `r` is the lane's current row and only moves forward (f grows)
+__device__ __forceinline__ int heavy_candidate(const int* sP, const int* sG, int f, int& r)
+{
+    while (f >= sP[r + 1]) r++;
+    return sG[r] + (f - sP[r]);
+}
+
 // Extreme targets of the density pass (a clump: hundreds to thousands of candidates; left to one thread each they
 // would outlast the rest of the kernel): one WARP per queued target, spread over the whole GPU.  Lanes 0..8 fetch the
 // bounds of the nine rows in parallel; then lane l takes every 32nd candidate of each row (coalesced 16-byte loads),
@@ -673,13 +710,39 @@ sph3_density_heavy_kernel(const float4* __restrict__ posS, const float4* __restr
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int total = min(__ldg(heavy_count), cap);
     const float h = cc->h, accept_r2 = cc->accept_r2, h2 = cc->h2, poly6 = cc->poly6;
+    __shared__ int s_rows[HEAVY_WARPS][2][33];
+    int* const sP = s_rows[(threadIdx.x >> 5) % HEAVY_WARPS][0];
+    int* const sG = s_rows[(threadIdx.x >> 5) % HEAVY_WARPS][1];
     for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < total; e += nwarps) {
         const int slot = __ldg(heavy_queue + e);
         const float4 p = __ldg(posS + slot);
         const Query3 q = list_query(g, p.x, p.y, p.z, h);
         const int nj = q.j1 - q.j0 + 1, nrows = (q.i1 - q.i0 + 1) * nj;
         float part = 0.0f;
-        for (int r0 = 0; r0 < nrows; r0 += 32) {           // 32 rows per round (nine in the usual 3 x 3 x 3 query)
+        if (nrows <= 32) {
+            const int ncand = heavy_rows_setup(g, offset, q, nj, nrows, lane, sP, sG);
+            int r = 0;
+            for (int f0 = lane; f0 < ncand; f0 += 128) {
+                int c[4];
+                bool ok[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int f = f0 + 32 * u;
+                    ok[u] = f < ncand;
+                    c[u] = ok[u] ? heavy_candidate(sP, sG, f, r) : slot;
+                }
+                float4 qp[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) qp[u] = __ldg(posS + c[u]);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const float r2 = cwa_len3sq(p.x - qp[u].x, p.y - qp[u].y, p.z - qp[u].z);
+                    const float d = (ok[u] && r2 <= accept_r2) ? (h2 - r2) : 0.0f;
+                    part = fmaf(poly6, d * d * d, part);
+                }
+            }
+        } else
+        for (int r0 = 0; r0 < nrows; r0 += 32) {           // generic wide query (h > cell): 32 rows per round, row after row
             int g0 = 0, g1 = 0;
             if (r0 + lane < nrows) {
                 const int r = r0 + lane;
@@ -800,6 +863,9 @@ sph3_force_heavy_kernel(const float4* __restrict__ pack, const int* __restrict__
     int kept = 0, k_slot = 0;
     float4 k_pa = make_float4(0.f, 0.f, 0.f, 0.f), k_pb = k_pa;
     float k0 = 0.f, k1 = 0.f, k2 = 0.f, k3 = 0.f, k4 = 0.f, k5 = 0.f;
+    __shared__ int s_rows[HEAVY_WARPS][2][33];
+    int* const sP = s_rows[(threadIdx.x >> 5) % HEAVY_WARPS][0];
+    int* const sG = s_rows[(threadIdx.x >> 5) % HEAVY_WARPS][1];
     for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < total; e += nwarps) {
         const int slot = __ldg(heavy_queue + e);
         const f4x2 own = cwa_ldg256(pack + 2 * (size_t)slot);
@@ -807,6 +873,27 @@ sph3_force_heavy_kernel(const float4* __restrict__ pack, const int* __restrict__
         const Query3 q = list_query(g, pa.x, pa.y, pa.z, c.h);
         const int nj = q.j1 - q.j0 + 1, nrows = (q.i1 - q.i0 + 1) * nj;
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f, s5 = 0.f;
+        if (nrows <= 32) {
+            const int ncand = heavy_rows_setup(g, offset, q, nj, nrows, lane, sP, sG);
+            int r = 0;
+            for (int f0 = lane; f0 < ncand; f0 += 128) {
+                int cand[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int f = f0 + 32 * u;
+                    cand[u] = (f < ncand) ? heavy_candidate(sP, sG, f, r) : slot;        // past the end: the target itself, skipped below
+                }
+                f4x2 rec[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) rec[u] = cwa_ldg256(pack + 2 * (size_t)cand[u]);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const float r2 = cwa_len3sq(pa.x - rec[u].a.x, pa.y - rec[u].a.y, pa.z - rec[u].a.z);
+                    if (r2 <= c.accept_r2 && cand[u] != slot)
+                        pair_force(c, pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, rec[u].a, rec[u].b, s0, s1, s2, s3, s4, s5);
+                }
+            }
+        } else
         for (int r0 = 0; r0 < nrows; r0 += 32) {
             int g0 = 0, g1 = 0;
             if (r0 + lane < nrows) {
