@@ -57,13 +57,13 @@ ALGO_BYTES = {
     "clear(memset)": (0, 4, 0),
     "grid_hash_count": (24, 0, 0),     # pos 16 B read, cell id 4 B + arrival rank 4 B written
     "scan_lookback": (0, 8, 0),        # 4 B read + 4 B written per cell, single pass
-    "grid_insert": (24, 0, 0),         # count-ahead frames: slot's cell id, rank, old index + offset read; cell_of and arrival list written (plain frames: 16)
+    "grid_insert": (16, 0, 0),         # cell id, rank, offset read; index written
     "grid_cell_order": (16, 0, 0),     # (stand-alone grid builds only) cell id + offset read, arrival list read, index written
     "reorder": (148, 0, 0),            # fused ordering + reorder: arrival 4 + cell id 4 + offsets 8 + record 64 read; index 4 + snapshot 64 written
     "density": (124, 0, 0),            # pos+vel 32 B read, pack 32 B + count 4 B + neighbour list ~56 B (13.4 entries) written; the loop itself is FP32/L1 bound
     "force": (116, 0, 0),              # pack 32 B + count 4 B + list ~56 B read, pair sums 24 B written; neighbour gathers hit L1/L2
     "heavy_targets": (0, 0, 0),        # clump targets (> 192 candidates / > 64 neighbours) finished one warp each, both passes
-    "integrate": (164, 0, 0),          # pack 32 + force 16 + misc 16 + pair sums 24 + index 4 read, 64 B record written to the SSBO, + next frame's cell id and arrival rank (8 B, count-ahead)
+    "integrate": (156, 0, 0),          # pack 32 + force 16 + misc 16 + pair sums 24 + index 4 read, 64 B record written to the SSBO
     "wave_evolve": (0, 0, 12),         # u(t-1) read once, u(t-2) read, u(t) written
 }
 
@@ -283,9 +283,14 @@ def run_native(args):
     ms_total = float(t.item())
     # ---- per-kernel profile over the next K steps (CUDA events around every launch): same regime of the simulated
     # state as the timed region (the cost of a frame drifts as the fluid clumps, tools/state_evolution.py)
+    # ... taken with the frames run back to back on ONE stream (pipeline 0): in the timed region the wave stencil and the grid clear
+    # of a frame overlap other kernels on side streams and the cell hash rides in the integrate pass, so a CUDA-event bracket
+    # there would time two kernels sharing the GPU; here every kernel runs alone and the bracket is that kernel's own time
+    ctx.set_tuning(pipeline=0)
     ctx.profile_begin()
     sph.coupled_step(wave, K, COUPLING)
     prof = ctx.profile_end()
+    ctx.set_tuning(pipeline=3)
     # keep the same kernels running a little longer so the 50 ms clock sampler sees them under load
     t_end = time.time() + 1.0
     while time.time() < t_end:
@@ -381,7 +386,8 @@ def run_native(args):
     roofline = {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": dom["frac"], "traffic": ncu_traffic(dom["kernel"]), "peak_source": peak_src,
                 "note": "the density pass is bound by FP32 issue and L1 (ncu: issue 63 %, L1TEX 67 %), not by HBM (its DRAM traffic is about 1.3x its algorithmic bytes); "
-                        "every kernel is listed in roofline_kernels"}
+                        "every kernel is listed in roofline_kernels, each timed alone (frames of the profile window run on one stream; the timed region "
+                        "overlaps the wave stencil and the grid clear with other kernels and folds the cell hash into the integrate pass)"}
 
     # ---- CPU baseline on the host cores (bounded sample) --------------------------------------------
     cpu = None

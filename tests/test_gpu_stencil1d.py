@@ -66,6 +66,29 @@ def test_compute_is_bit_exact(cwa, ctx, oracle, shader, width, frames, bc):
         assert _bits_equal(g2.read_image(i), g3.read_image(i))
 
 
+@pytest.mark.parametrize("bc", [0, 1, 2])
+@pytest.mark.parametrize("shader,name,width,frames", [(0, "shallow", 128, 40), (1, "wave", 1024, 5)])
+def test_committed_golden_vectors(cwa, ctx, shader, name, width, frames, bc):
+    """From the committed one-frame state to the committed many-frames state (tests/golden/golden_v2_stencil1d.npz), bit for bit."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v2_stencil1d.npz"))
+    g = cwa.ImageStencil(ctx, shader, width)
+    lam, p3 = (0.001, 0.1) if shader == 0 else (0.01, 0.9995)
+    g.set_params(lam, p3, 0.001, (0.3, -0.2), bc)
+    start, want = gold[f"{name}_bc{bc}_1frame_images"], gold[f"{name}_bc{bc}_{frames}frames_images"]
+    # a fresh object has done Reinit (nread dispatches); the golden state has done one frame more.  Bring the roles in line first.
+    g.Compute(1)
+    st = g.state()
+    assert st["unit"] + st["read_index"] + [st["write_index"]] == gold[f"{name}_bc{bc}_1frame_state"].tolist()
+    for i in range(g.num_images):
+        g.write_image(i, start[i])
+    g.Compute(frames - 1)
+    st = g.state()
+    assert st["unit"] + st["read_index"] + [st["write_index"]] == gold[f"{name}_bc{bc}_{frames}frames_state"].tolist()
+    for i in range(g.num_images):
+        assert _bits_equal(g.read_image(i), want[i]), f"image {i}"
+
+
 def test_splash_compute_func_and_reinit_from_texture(cwa, ctx, oracle):
     g = cwa.ImageStencil(ctx, cwa.STENCIL1D_SHALLOW, 128)
     o = oracle.ImageStencil(oracle.STENCIL1D_SHALLOW, 128)

@@ -319,3 +319,31 @@ def test_wave1d_iterate_matches_the_formula_and_damps(oracle):
     e0 = float(np.abs(w.image[w._with_unit(0)][:, 0]).max())
     w.compute(100)                                    # 1000 damped steps
     assert float(np.abs(w.image[w._with_unit(0)][:, 0]).max()) < e0
+
+
+def _stencil_from_golden(oracle, gold, key, shader, width, bc):
+    s = oracle.ImageStencil(shader, width)
+    s.prm.bc = bc; s.prm.boundary[0] = 0.3; s.prm.boundary[1] = -0.2
+    n = s.num_images
+    for i in range(n):
+        s.image[i][:] = gold[key + "_images"][i]
+    st = gold[key + "_state"].tolist()
+    s.unit, s.read_index, s.write_index = st[:n], st[n:2 * n - 1], st[-1]
+    return s
+
+
+def test_stencil1d_goldens(oracle):
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v2_stencil1d.npz"))
+    for shader, name, width, frames in ((oracle.STENCIL1D_SHALLOW, "shallow", 128, 40), (oracle.STENCIL1D_WAVE, "wave", 1024, 5)):
+        fresh = oracle.ImageStencil(shader, width)
+        got, ref = np.stack(fresh.image), gold[f"{name}_init_images"]
+        assert np.all(np.abs(got.view(np.int32).astype(np.int64) - ref.view(np.int32).astype(np.int64)) <= 1), "init profile (exp): 1 ulp"
+        for bc in (0, 1, 2):
+            s = _stencil_from_golden(oracle, gold, f"{name}_bc{bc}_1frame", shader, width, bc)
+            s.compute(frames - 1)
+            ref = gold[f"{name}_bc{bc}_{frames}frames_images"]
+            got = np.stack(s.image)
+            nan = np.isnan(ref)
+            assert np.array_equal(np.isnan(got), nan) and np.array_equal(got[~nan], ref[~nan]), (name, bc)
+            n = s.num_images
+            assert list(s.unit) + list(s.read_index) + [s.write_index] == gold[f"{name}_bc{bc}_{frames}frames_state"].tolist()
