@@ -449,23 +449,28 @@ def run_native_distributed(args, world, rank, local_rank, torch, dist, cwa):
     own["extras"][:] = (1000.0, 0.0, 500.0, 50.0)
     del i, j, k
 
-    ctx = cwa.Context(local_rank)
-    ctx.set_boundary(upper=(box_x, 1.0, box_z, 500.0), lower=BOX_LOWER)
-    ctx.set_sim_constants(uv_scale=uv, uv_scale_z=sc["uv_z"], torque_coeff=sc["torque"])
-    zl = max(0.0, plan.z_lo - 0.06) if rank > 0 else 0.0
-    zh = min(box_z, plan.z_hi + 0.06) if rank < world - 1 else box_z
-    ncx = sc["gn"][0]
-    ncz = max(4, int(math.ceil((zh - zl) / (box_x / ncx))))
     # the shipped parameters make the over-dense sheet blast apart (|v| in the thousands within ten frames), so tens of
-    # thousands of particles cross a slab face per frame: generous fixed-size messages
-    # (a slab face grows with sqrt(world))
+    # thousands of particles cross a slab face per frame: generous fixed-size messages (a slab face grows with sqrt(world))
     cap = int(32768 * math.sqrt(world) + 4095) // 4096 * 4096
-    be = CudaBackend(cwa, ctx, plan, int(own.size * 1.3) + 6 * cap + 8192, (0.0, -0.02, zl), (box_x, sc["gmax"][1], zh), (ncx, sc["gn"][1], ncz),
-                     cap_mig=cap, cap_ghost=cap)
-    be.upload_owned(own)
     n_global = nxg * sc["ny"] * nzg
-    drv = DistributedCoupled(be, plan, dist)
-    drv.init_wave_halos()
+
+    def build_rank():
+        """This rank's share of the scene in a context of its own: (context, backend, driver)."""
+        c = cwa.Context(local_rank)
+        c.set_boundary(upper=(box_x, 1.0, box_z, 500.0), lower=BOX_LOWER)
+        c.set_sim_constants(uv_scale=uv, uv_scale_z=sc["uv_z"], torque_coeff=sc["torque"])
+        zl = max(0.0, plan.z_lo - 0.06) if rank > 0 else 0.0
+        zh = min(box_z, plan.z_hi + 0.06) if rank < world - 1 else box_z
+        ncx = sc["gn"][0]
+        ncz = max(4, int(math.ceil((zh - zl) / (box_x / ncx))))
+        b = CudaBackend(cwa, c, plan, int(own.size * 1.3) + 6 * cap + 8192, (0.0, -0.02, zl), (box_x, sc["gmax"][1], zh), (ncx, sc["gn"][1], ncz),
+                        cap_mig=cap, cap_ghost=cap)
+        b.upload_owned(own)
+        d = DistributedCoupled(b, plan, dist)
+        d.init_wave_halos()
+        return c, b, d
+
+    ctx, be, drv = build_rank()
 
     sampler = ClockSampler(local_rank)
     if os.environ.get("CWA_BENCH_DEBUG"):
@@ -534,39 +539,60 @@ def run_native_distributed(args, world, rank, local_rank, torch, dist, cwa):
         print(f"[kernels rank {rank}] owned {q.size} ghosts {be.n_ghost} max/cell {int(cnt.max())} cells>64: {int((cnt > 64).sum())} "
               + ", ".join(f"{k} {v[0] / v[1] * 1e3:.0f}us" for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:14]), flush=True)
 
-    # end to end: every rank's particle slab and wave rows live in pinned HOST buffers between steps
+    # end to end: every rank's particle slab and wave rows live in pinned HOST buffers between steps.  Two scene streams per rank
+    # (two contexts, each with its own backend, driver and pinned buffers) take turns, so one step's upload overlaps the other
+    # stream's frame and read-back; a step counts when its results are in host memory.
     import ctypes as C
-    cap = be.capacity
-    pin_p = torch.empty(cap * cwa.PARTICLE.itemsize, dtype=torch.uint8).pin_memory()
     row_bytes = wave_w * 4
-    pin_w = [torch.empty(plan.rows_stored * wave_w, dtype=torch.float32).pin_memory() for _ in range(2)]
-    host_p = pin_p.numpy().view(cwa.PARTICLE)
-    host_w = [w_.numpy().reshape(plan.rows_stored, wave_w) for w_ in pin_w]
-    host_p[:be.n_owned] = be.buffer.read(cwa.PARTICLE, be.n_owned)       # the owned RANGE (dead slots included), as the device holds it
-    host_w[0][:] = be.wave.read_role(0); host_w[1][:] = be.wave.read_role(1)
-    lib, hnd = ctx.lib, ctx.h
     moved = [0, 0]
 
-    def e2e_step():
-        n = be.n_owned
-        cwa.check(lib.cwa_buffer_sub_data(hnd, be.buffer.h, 0, n * 64, C.c_void_p(host_p.ctypes.data)))
-        cwa.check(lib.cwa_wave_write_image(hnd, be.wave.h, be.wave.role_image(0), C.c_void_p(host_w[0].ctypes.data)))
-        cwa.check(lib.cwa_wave_write_image(hnd, be.wave.h, be.wave.role_image(1), C.c_void_p(host_w[1].ctypes.data)))
-        drv.step(1, COUPLING)
-        n2 = be.n_owned
-        cwa.check(lib.cwa_buffer_read(hnd, be.buffer.h, 0, n2 * 64, C.c_void_p(host_p.ctypes.data)))
-        host_w[0], host_w[1] = host_w[1], host_w[0]
-        cwa.check(lib.cwa_wave_read_image(hnd, be.wave.h, be.wave.role_image(0), C.c_void_p(host_w[0].ctypes.data)))
-        moved[0] += n * 64 + 2 * plan.rows_stored * row_bytes
-        moved[1] += n2 * 64 + plan.rows_stored * row_bytes
-    for _ in range(3):
-        e2e_step()
+    class SlotD:
+        def __init__(self, c, b, d):
+            self.ctx, self.be, self.drv = c, b, d
+            self.pin_p = torch.empty(b.capacity * cwa.PARTICLE.itemsize, dtype=torch.uint8).pin_memory()
+            self.pin_w = [torch.empty(plan.rows_stored * wave_w, dtype=torch.float32).pin_memory() for _ in range(2)]
+            self.host_p = self.pin_p.numpy().view(cwa.PARTICLE)
+            self.host_w = [w_.numpy().reshape(plan.rows_stored, wave_w) for w_ in self.pin_w]
+
+        def submit(self):
+            c, b, hp, hw = self.ctx, self.be, self.host_p, self.host_w
+            lib, hnd = c.lib, c.h
+            n = b.n_owned
+            cwa.check(lib.cwa_buffer_sub_data(hnd, b.buffer.h, 0, n * 64, C.c_void_p(hp.ctypes.data)))
+            cwa.check(lib.cwa_wave_write_image(hnd, b.wave.h, b.wave.role_image(0), C.c_void_p(hw[0].ctypes.data)))
+            cwa.check(lib.cwa_wave_write_image(hnd, b.wave.h, b.wave.role_image(1), C.c_void_p(hw[1].ctypes.data)))
+            self.drv.step(1, COUPLING)
+            n2 = b.n_owned
+            cwa.check(lib.cwa_buffer_read_async(hnd, b.buffer.h, 0, n2 * 64, C.c_void_p(hp.ctypes.data)))
+            hw[0], hw[1] = hw[1], hw[0]
+            cwa.check(lib.cwa_wave_read_image_async(hnd, b.wave.h, b.wave.role_image(0), C.c_void_p(hw[0].ctypes.data)))
+            moved[0] += n * 64 + 2 * plan.rows_stored * row_bytes
+            moved[1] += n2 * 64 + plan.rows_stored * row_bytes
+
+    slots = [SlotD(ctx, be, drv)]
+    if os.environ.get("CWA_E2E_SLOTS", "2") != "1":
+        slots.append(SlotD(*build_rank()))
+    owned_now = be.buffer.read(cwa.PARTICLE, be.n_owned)                 # the owned RANGE (dead slots included), as the device holds it
+    w0_now, w1_now = be.wave.read_role(0), be.wave.read_role(1)
+    for sl in slots:
+        sl.be.n_owned, sl.be.n_ghost = be.n_owned, 0
+        sl.host_p[:be.n_owned] = owned_now
+        sl.host_w[0][:] = w0_now; sl.host_w[1][:] = w1_now
+    ns = len(slots)
+    for k in range(2 * ns):
+        slots[k % ns].ctx.synchronize()
+        slots[k % ns].submit()
+    for sl in slots:
+        sl.ctx.synchronize()
     moved[0] = moved[1] = 0
-    dist.barrier(); ctx.synchronize()
+    dist.barrier()
     t0 = time.perf_counter()
-    for _ in range(K):
-        e2e_step()
-    ctx.synchronize()
+    for k in range(K):
+        sl = slots[k % ns]
+        sl.ctx.synchronize()                              # the slot's previous step is complete: its results are in host memory
+        sl.submit()
+    for sl in slots:
+        sl.ctx.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s, float(moved[0]) / K, float(moved[1]) / K], dtype=torch.float64, device="cuda")
     tm = t.clone()
@@ -601,7 +627,8 @@ def run_native_distributed(args, world, rank, local_rank, torch, dist, cwa):
                        "timing": "cudaEvent on each rank's context stream around K coupled frames (communication included), max over ranks"},
             "clocks": clocks,
             "e2e": {"value": n_global * K / e2e_s, "unit": "particle-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_s / K * 1e3},
+                    "ms_per_step": e2e_s / K * 1e3,
+                    "how": f"C ABI, pinned host buffers; {ns} scene streams per rank take turns; a step counts when its results are in host memory"},
             "gpu_launches": int(lt.item()),
             "roofline": {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
                          "traffic": ncu_traffic(dom["kernel"]), "peak_source": peak_src, "note": "rank 0's kernels; neighbour loops are FP32-issue / L1 bound"},
