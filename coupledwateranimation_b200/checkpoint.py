@@ -22,11 +22,13 @@ def read(path: str) -> dict:
         if h["magic"] != MAGIC or h["version"] != 1 or h["header_bytes"] != 256:
             raise ValueError(f"{path} is not a version-1 checkpoint")
         n, w, hh, ch = int(h["n_particles"]), int(h["wave_w"]), int(h["wave_h"]), int(h["wave_ch"])
-        particles = np.frombuffer(f.read(n * 64), PARTICLE).copy()
-        shape = (hh, w) if ch == 1 else (hh, w, ch)
-        images = [np.frombuffer(f.read(w * hh * ch * 4), "<f4").reshape(shape).copy() for _ in range(3)]
-        if particles.size != n or any(im.size != w * hh * ch for im in images):
+        raw_p = f.read(n * 64)
+        raw_i = [f.read(w * hh * ch * 4) for _ in range(3)]
+        if len(raw_p) != n * 64 or any(len(r) != w * hh * ch * 4 for r in raw_i):
             raise ValueError(f"{path} is truncated")
+        particles = np.frombuffer(raw_p, PARTICLE).copy()
+        shape = (hh, w) if ch == 1 else (hh, w, ch)
+        images = [np.frombuffer(r, "<f4").reshape(shape).copy() for r in raw_i]
     return {"header": h, "frame": int(h["frame"]), "particles": particles, "images": images}
 
 
