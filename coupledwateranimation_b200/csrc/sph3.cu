@@ -802,8 +802,11 @@ __device__ __forceinline__ void finish_particle(const Sph3Const& c, const Finish
 // per target, no shared memory; a neighbour's (pos, p | vel, rho) record is one sector fetched with one 256-bit
 // load, and consecutive cell-ordered targets share most of their neighbours, so the gathers hit L1/L2.  A target
 // whose list overflowed (more than K neighbours) or that the density pass marked extreme is queued for the heavy kernel.
+#ifndef CWA_FORCE_MINB
+#define CWA_FORCE_MINB 6                  // resident CTAs per SM the force list kernel is compiled for (76 registers; 8 -> 64: measured, tuning.md)
+#endif
 template <bool FUSED, bool LOCAL>
-__global__ void __launch_bounds__(TILE_P, 6)
+__global__ void __launch_bounds__(TILE_P, CWA_FORCE_MINB)
 sph3_force_list_kernel(const float4* __restrict__ pack, const int* __restrict__ nbr_list, const int* __restrict__ nbr_count,
                        int* __restrict__ heavy_queue, int* __restrict__ heavy_count,
                        float4* __restrict__ pairP, float2* __restrict__ pairV, int n_max,
