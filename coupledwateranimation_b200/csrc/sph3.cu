@@ -614,13 +614,24 @@ sph3_density_list_kernel(const float4* __restrict__ posS, const float4* __restri
 
     float rho = 0.0f;
     int cnt = 0;
-    int* const gl = nbr_list + (size_t)slot * K;       // the target's own row of K entries
-    auto step = [&](const float4 qp, int j, bool valid) {
+    int* gl = nbr_list + (size_t)slot * K;             // the target's own row of K entries
+    asm volatile("" : "+l"(gl));                       // keep the row pointer in a register pair: entry address = one IMAD.WIDE
+    const int last = K - 1;
+    // The append is ONE predicated store, no branch and no capacity test: entry min(cnt, K-1) is written, so a target with more
+    // than K neighbours keeps overwriting its last entry -- its count ends above K, which tells the force pass to ignore the list.
+    // The predicate is formed inside the asm from the same compare the accumulation uses (r2 <= accept_r2 [and valid]).
+    auto step = [&](const float4 qp, int j, bool valid, bool masked) {
         const float r2 = cwa_len3sq(p.x - qp.x, p.y - qp.y, p.z - qp.z);
         const bool ok = (r2 <= accept_r2) && valid;
         const float d = ok ? (h2 - r2) : 0.0f;
         rho = fmaf(poly6, d * d * d, rho);             // weight 0 when rejected: no branch around the arithmetic
-        if (ok && cnt < K) gl[cnt] = j;
+        int* const w = gl + min(cnt, last);
+        if (masked)
+            asm volatile("{\n\t.reg .pred q;\n\tsetp.le.f32 q, %2, %3;\n\tsetp.ne.and.b32 q, %4, 0, q;\n\t@q st.global.b32 [%0], %1;\n\t}"
+                         :: "l"(w), "r"(j), "f"(r2), "f"(accept_r2), "r"((int)valid) : "memory");
+        else
+            asm volatile("{\n\t.reg .pred q;\n\tsetp.le.f32 q, %2, %3;\n\t@q st.global.b32 [%0], %1;\n\t}"
+                         :: "l"(w), "r"(j), "f"(r2), "f"(accept_r2) : "memory");
         cnt += ok ? 1 : 0;
     };
     // Four candidates per trip.  `j` is even: the two 256-bit loads fetch the pairs (j, j+1) and (j+2, j+3),
@@ -630,7 +641,7 @@ sph3_density_list_kernel(const float4* __restrict__ posS, const float4* __restri
         const f4x2 lo = cwa_ldg256(posS + j), hi = cwa_ldg256(posS + j + 2);
         const float4 qp[4] = {lo.a, lo.b, hi.a, hi.b};
 #pragma unroll
-        for (int u = 0; u < 4; u++) step(qp[u], j + u, !masked || (unsigned)(j + u - first) < (unsigned)len);
+        for (int u = 0; u < 4; u++) step(qp[u], j + u, !masked || (unsigned)(j + u - first) < (unsigned)len, masked);
     };
 #pragma unroll 1
     for (int r = 0; r < RT_ROWS; r++) {
@@ -647,7 +658,7 @@ sph3_density_list_kernel(const float4* __restrict__ posS, const float4* __restri
             for (int j = q.j0; j <= q.j1; j++) {
                 const int base = (i * g.n[1] + j) * g.kstride;
                 const int g0 = __ldg(offset + base + q.k0), g1 = __ldg(offset + base + q.k1 + 1);
-                for (int c = g0; c < g1; c++) step(__ldg(posS + c), c, true);
+                for (int c = g0; c < g1; c++) step(__ldg(posS + c), c, true, false);
             }
     }
     float rho_out, prs_out;
