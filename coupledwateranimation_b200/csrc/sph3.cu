@@ -585,8 +585,8 @@ __device__ __forceinline__ RowBounds rows_load(const GridView& g, const int* __r
 // Density pass + neighbour lists.  Candidates are read through L1 with 256-bit loads (a pair of cell-ordered
 // positions is one sector); shared memory only holds the row table, which leaves most of the SM's 228 KB to
 // the L1 cache.  An accepted candidate (self included) is appended to the target's own row of K entries in
-// global memory ([slot][K], a private 128-byte line that stays in L2 until the force pass reads it) with one
-// predicated store; count[slot] keeps counting past K, and the force pass re-scans the grid for such a target.
+// global memory ([slot][K], K = 64 by default: two private 128-byte lines that stay in L2 until the force pass reads
+// them) with one predicated store; count[slot] keeps counting past K, and the force pass re-scans the grid for such a target.
 template <bool LOCAL>
 __global__ void __launch_bounds__(TILE_P)
 sph3_density_list_kernel(const float4* __restrict__ posS, const float4* __restrict__ velS, float4* __restrict__ pack,
@@ -620,28 +620,27 @@ sph3_density_list_kernel(const float4* __restrict__ posS, const float4* __restri
     // The append is ONE predicated store, no branch and no capacity test: entry min(cnt, K-1) is written, so a target with more
     // than K neighbours keeps overwriting its last entry -- its count ends above K, which tells the force pass to ignore the list.
     // The predicate is formed inside the asm from the same compare the accumulation uses (r2 <= accept_r2 [and valid]).
-    auto step = [&](const float4 qp, int j, bool valid, bool masked) {
-        const float r2 = cwa_len3sq(p.x - qp.x, p.y - qp.y, p.z - qp.z);
-        const bool ok = (r2 <= accept_r2) && valid;
+    auto step = [&](const float4 qp, int j, bool valid) {
+        float r2 = cwa_len3sq(p.x - qp.x, p.y - qp.y, p.z - qp.z);
+        r2 = valid ? r2 : CUDART_INF_F;                // a slot outside the row can never be accepted: one compare serves both
+        const bool ok = r2 <= accept_r2;
         const float d = ok ? (h2 - r2) : 0.0f;
         rho = fmaf(poly6, d * d * d, rho);             // weight 0 when rejected: no branch around the arithmetic
         int* const w = gl + min(cnt, last);
-        if (masked)
-            asm volatile("{\n\t.reg .pred q;\n\tsetp.le.f32 q, %2, %3;\n\tsetp.ne.and.b32 q, %4, 0, q;\n\t@q st.global.b32 [%0], %1;\n\t}"
-                         :: "l"(w), "r"(j), "f"(r2), "f"(accept_r2), "r"((int)valid) : "memory");
-        else
-            asm volatile("{\n\t.reg .pred q;\n\tsetp.le.f32 q, %2, %3;\n\t@q st.global.b32 [%0], %1;\n\t}"
-                         :: "l"(w), "r"(j), "f"(r2), "f"(accept_r2) : "memory");
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.le.f32 q, %2, %3;\n\t@q st.global.b32 [%0], %1;\n\t}"
+                     :: "l"(w), "r"(j), "f"(r2), "f"(accept_r2) : "memory");
         cnt += ok ? 1 : 0;
     };
     // Four candidates per trip.  `j` is even: the two 256-bit loads fetch the pairs (j, j+1) and (j+2, j+3),
     // both issued before the first use.  Candidates outside [first, first + len) -- the slot before an odd row
-    // start, the slots after the row end (the cell-ordered array is padded by 4) -- are masked out.
+    // start, the slots after the row end (the cell-ordered array is padded by 4) -- are masked out: candidate u of the
+    // trip is valid iff lo <= u < hi, two trip-level bounds compared against constants.
     auto quad = [&](int j, int first, int len, bool masked) {
-        const f4x2 lo = cwa_ldg256(posS + j), hi = cwa_ldg256(posS + j + 2);
-        const float4 qp[4] = {lo.a, lo.b, hi.a, hi.b};
+        const f4x2 lo2 = cwa_ldg256(posS + j), hi2 = cwa_ldg256(posS + j + 2);
+        const float4 qp[4] = {lo2.a, lo2.b, hi2.a, hi2.b};
+        const int lo = first - j, hi = first + len - j;
 #pragma unroll
-        for (int u = 0; u < 4; u++) step(qp[u], j + u, !masked || (unsigned)(j + u - first) < (unsigned)len, masked);
+        for (int u = 0; u < 4; u++) step(qp[u], j + u, !masked || (lo <= u && u < hi));
     };
 #pragma unroll 1
     for (int r = 0; r < RT_ROWS; r++) {
@@ -658,7 +657,7 @@ sph3_density_list_kernel(const float4* __restrict__ posS, const float4* __restri
             for (int j = q.j0; j <= q.j1; j++) {
                 const int base = (i * g.n[1] + j) * g.kstride;
                 const int g0 = __ldg(offset + base + q.k0), g1 = __ldg(offset + base + q.k1 + 1);
-                for (int c = g0; c < g1; c++) step(__ldg(posS + c), c, true, false);
+                for (int c = g0; c < g1; c++) step(__ldg(posS + c), c, true);
             }
     }
     float rho_out, prs_out;

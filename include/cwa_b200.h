@@ -106,6 +106,8 @@ CWA_API int  cwa_profile_end(cwa_ctx* ctx, float* ms, int* launches, int cap);  
  *       default 3; results and every readable array are bit-identical to 0),
  *       "scan_config" (tile shape of the look-back scan: 0 = 256 threads x 16 items, 1 = 512 x 32, 2 = 512 x 32 with
  *       warp-striped loads (default), 3 = 1024 x 16 warp-striped),
+ *       "nbr_k" (neighbour-list entries per target, multiple of 4 in [8, 256], default 64; set before the SPH object is used) and
+ *       "extreme_candidates" (a target with more candidates is finished by a whole warp, default 192),
  *       "wave_transpose" (1, default: the SPH passes sample a transposed copy of the bound wave level -- the grid runs fastest along
  *       z = the texture's t axis -- rebuilt only when that level changed; same texels, bit-identical results). */
 CWA_API int  cwa_set_tuning(cwa_ctx* ctx, const char* key, int value);

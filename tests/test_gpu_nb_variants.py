@@ -79,7 +79,7 @@ def test_variant_with_partial_or_no_staging(cwa, tuned, oracle, cfg, grid_key, c
 @pytest.mark.parametrize("grid_key", ["2h", "h+", "h/1.5"])
 @pytest.mark.parametrize("cfg", [1, 7])
 def test_variant_dense_cluster(cwa, tuned, oracle, cfg, grid_key):
-    """A 300-particle clump: neighbour counts far above the neighbour-list capacity (K = 32 -> the force pass
+    """A 300-particle clump: neighbour counts far above the neighbour-list capacity (K = 64 -> the force pass
     re-scans the grid for those targets) and rows that overflow the staging budget of the lanes kernels."""
     tuned.set_tuning(nb_config=cfg)
     prm, p, tex, sph = _scene(cwa, tuned, oracle, grid_key, cluster=True)
