@@ -1018,16 +1018,23 @@ sph3_finalize_integrate_sorted_kernel(const float4* __restrict__ pack,
         }
     }
     if (AHEAD) {
+        // Warp aggregation by RUNS: the threads are in cell order and a particle moves a fraction of a cell per frame, so lanes
+        // that end up in the same cell are almost always neighbours.  One shuffle + one ballot find the runs of equal cells, the
+        // first lane of a run adds the run length to the cell's counter and the others take base + position in the run (a cell
+        // that shows up in two separate runs simply gets two atomics).  Cheaper than __match_any_sync, which loops over the
+        // distinct values of the warp.
         const unsigned lane = threadIdx.x & 31u;
-        const unsigned peers = __match_any_sync(0xffffffffu, cell);
-        const int leader = __ffs(peers) - 1;
-        const int my_rank = __popc(peers & ((1u << lane) - 1u));
+        const int prev = __shfl_up_sync(0xffffffffu, cell, 1);
+        const unsigned heads = __ballot_sync(0xffffffffu, lane == 0u || cell != prev);
+        const int start = 31 - __clz(heads & (0xffffffffu >> (31u - lane)));           // first lane of my run
+        const unsigned after = heads & ~(0xffffffffu >> (31u - lane));                  // run heads behind me
+        const int end = after ? (__ffs(after) - 1) : 32;                                // one past the last lane of my run
         int base = 0;
-        if (cell >= 0 && (int)lane == leader) base = atomicAdd(&counter[cell], __popc(peers));
-        base = __shfl_sync(0xffffffffu, base, leader);
+        if (cell >= 0 && (int)lane == start) base = atomicAdd(&counter[cell], end - start);
+        base = __shfl_sync(0xffffffffu, base, start);
         if (s < n) {
             cell_next[s] = cell;
-            rank_next[s] = base + my_rank;
+            rank_next[s] = base + ((int)lane - start);
         }
     }
 }
@@ -1718,9 +1725,15 @@ extern "C" int cwa_coupled_step(cwa_ctx* ctx, cwa_sph hs, cwa_wave hw, int nfram
         }
         s->wave = hw; s->wave_image = image;
         const bool more = f + 1 < nframes;
-        s->wait_before_sampling = wave_in_flight ? ctx->ev_pipe[3] : nullptr;
+        // the previous frame's wave stencil may still be running on the side stream: in grid mode the wait is placed behind the grid
+        // build (the first kernel that samples the field is the density pass); the all-pairs passes sample from their first kernel on
+        s->wait_before_sampling = nullptr;
+        if (wave_in_flight) {
+            if (s->grid >= 0 && s->n > 0) s->wait_before_sampling = ctx->ev_pipe[3];
+            else CWA_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_pipe[3], 0));
+        }
         const int rc = sph_passes_internal(ctx, s, wave_tex_view(ctx, hw, image), 7, more && (pipe & 2) && s->grid >= 0);   // :549-557
-        if (s->wait_before_sampling) {                                       // not consumed (all-pairs mode, n == 0): wait here
+        if (s->wait_before_sampling) {                                       // not consumed (the call failed early): wait here
             cudaStreamWaitEvent(ctx->stream, s->wait_before_sampling, 0);
             s->wait_before_sampling = nullptr;
         }

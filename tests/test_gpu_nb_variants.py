@@ -241,3 +241,33 @@ def test_transposed_sampling_copy_is_bit_identical(cwa, tuned, oracle, coupling)
         for f in ("pos", "vel", "force", "extras"):
             assert np.array_equal(a[k][f].view(np.uint32), b[k][f].view(np.uint32)), f"stage {k} {f}"
     assert np.array_equal(a[3].view(np.uint32), b[3].view(np.uint32))
+
+
+@pytest.mark.parametrize("coupling", ["as_shipped", "latest"])
+def test_pipelined_frames_all_pairs_mode(cwa, tuned, oracle, coupling):
+    """The as-shipped configuration (no uniform grid): the all-pairs passes sample the wave field from their first kernel on, so the
+    wait for the previous frame's stencil (side stream) sits in front of them.  Pipelined == plain, bit for bit."""
+    cpl = cwa.COUPLING_AS_SHIPPED if coupling == "as_shipped" else cwa.COUPLING_LATEST
+
+    def run(pipeline):
+        tuned.set_tuning(pipeline=pipeline)
+        prm = _params(oracle)
+        tuned.set_params_from_oracle(prm)
+        p = jittered_block(oracle, NX, NY, NZ, prm, seed=11, vel=0.5)
+        sph = cwa.Sph(tuned, p.size, None, particles=p)
+        wave = cwa.StencilImage2DTripleBuffered(tuned, 1024, 768, 1, cwa.WAVE_COUPLED)
+        for i in range(3):
+            wave.write_image(i, smooth_field(768, 1024, 1, amp=0.01 * (i + 1)))
+        sph.coupled_step(wave, 6, cpl)
+        return sph.download(), [wave.read_image(i) for i in range(3)], wave.state()
+
+    try:
+        a = run(0)
+        b = run(3)
+    finally:
+        tuned.set_tuning(pipeline=3)
+    assert a[2] == b[2]
+    for f in ("pos", "vel", "force", "extras"):
+        assert np.array_equal(a[0][f].view(np.uint32), b[0][f].view(np.uint32)), f
+    for x, y in zip(a[1], b[1]):
+        assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
