@@ -5,11 +5,13 @@
   python bench.py --impl reference --steps K --warmup W    reference arm: the CPU restatement of the
                                                            reference GLSL (oracle) on the host cores
 
-A "step" is one coupled frame of config C4 (SURVEY 8d): 448x5x448 = 1 003 520 particles on a
-192x51x192 uniform grid + a 2048^2 scalar wave height field: grid build -> density -> force ->
+A "step" is one coupled frame of config C4 (SURVEY 8d, DESIGN.md section 6): 448x5x448 = 1 003 520 particles on a
+384x31x384 uniform grid of ~h cells + a 2048^2 scalar wave height field: grid build -> density -> force ->
 integrate -> wave stencil -> display() texture bind.  `value` is particle-updates/s with all state
-resident in HBM; `e2e` is the same metric through the C ABI with the particle state and wave levels
-in pinned HOST buffers, copied in and out inside the timed region every step.
+resident in HBM (K frames in one cwa_coupled_step call); `e2e` is the same metric through the C ABI with the
+particle state and wave levels in pinned HOST buffers, copied in and out inside the timed region every step (a few
+scene streams take turns, so one step's upload overlaps another's frame and read-back).  `--gpus N` (N > 1) runs the
+slab-decomposed weak-scaling scene (scaled_scene) under torch.distributed / NCCL.
 """
 from __future__ import annotations
 
