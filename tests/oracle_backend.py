@@ -63,7 +63,18 @@ class OracleBackend:
         import contextlib
         return contextlib.nullcontext()
 
+    fused_pack = True          # like CudaBackend: sph_step(pack_next=True) packs the next exchange's messages, pack() then finds its work done
+    _packed_for = None
+
     def pack(self, z_lo, z_hi, band, has_left, has_right):
+        if self._packed_for == (self.n_owned, z_lo, z_hi, band, has_left, has_right):      # cwa_slab_pack after cwa_sph_step_slab: no-op
+            self._packed_for = None
+            f = lambda k: torch.from_numpy(self.msgs[k].view(np.uint8).reshape(-1))
+            return (f("sl") if has_left else None, f("sr") if has_right else None)
+        self._packed_for = None
+        return self._pack_now(z_lo, z_hi, band, has_left, has_right)
+
+    def _pack_now(self, z_lo, z_hi, band, has_left, has_right):
         q = self.p[:self.n_owned]
         live = ~self._dead(q)
         z = q["pos"][:, 2]
@@ -133,6 +144,11 @@ class OracleBackend:
         O.sph3_force(q, self.prm, tex, grid)
         O.sph3_integrate(q, self.prm, tex)
         self.p[:n] = q
+        self._packed_for = None
+        pl = self.plan
+        if pack_next and self.fused_pack and pl.world > 1:        # cwa_sph_step_slab: the integrate pass packs the owned range
+            self._pack_now(pl.z_lo, pl.z_hi, pl.ghost_width, pl.has_left, pl.has_right)
+            self._packed_for = (self.n_owned, pl.z_lo, pl.z_hi, pl.ghost_width, pl.has_left, pl.has_right)
 
     def wave_step(self):
         in0, in1, out = self.unit.index(0), self.unit.index(1), self.unit.index(2)

@@ -52,7 +52,7 @@ def test_slab_plan_covers_rows_and_sizes_halos():
         SlabPlan.make(64, 3, 32, 96, 2.0, 0.01).validate()     # slabs thinner than two ghost layers
 
 
-def _worker(rank, world, coupling, init_file, out_dir, balanced=False):
+def _worker(rank, world, coupling, init_file, out_dir, balanced=False, fused_pack=True):
     import torch.distributed as dist
     from oracle_backend import OracleBackend
     from coupledwateranimation_b200.distributed import DistributedCoupled, SlabPlan
@@ -63,6 +63,7 @@ def _worker(rank, world, coupling, init_file, out_dir, balanced=False):
     bounds = SlabPlan.balanced_row_bounds(world, WAVE_H, prm.uv_scale, np.sort(p["pos"][:, 2])) if balanced else None
     plan = SlabPlan.make(world, rank, WAVE_W, WAVE_H, prm.uv_scale, h, bounds)
     be = OracleBackend(plan, p.size + 4096, prm, GRID)
+    be.fused_pack = fused_pack
     z = p["pos"][:, 2]
     be.upload_owned(p[(z >= plan.z_lo) & (z < plan.z_hi)])
     drv = DistributedCoupled(be, plan, dist if world > 1 else None)
@@ -74,14 +75,14 @@ def _worker(rank, world, coupling, init_file, out_dir, balanced=False):
         dist.destroy_process_group()
 
 
-def _run(world, coupling, balanced=False):
+def _run(world, coupling, balanced=False, fused_pack=True):
     import torch.multiprocessing as mp
     with tempfile.TemporaryDirectory() as d:
         init_file = os.path.join(d, "rendezvous")
         if world == 1:
             _worker(0, 1, coupling, init_file, d)
         else:
-            mp.spawn(_worker, args=(world, coupling, init_file, d, balanced), nprocs=world, join=True)
+            mp.spawn(_worker, args=(world, coupling, init_file, d, balanced, fused_pack), nprocs=world, join=True)
         parts, waves, moved = [], [], 0
         for r in range(world):
             f = np.load(os.path.join(d, f"rank{r}.npz"))
@@ -117,6 +118,15 @@ def test_two_ranks_reproduce_one_rank(coupling):
     assert np.array_equal(nan_ref, nan_got)
     ok = ~nan_ref
     _assert_states_match(got, ref, ok)
+
+
+def test_pack_fused_into_the_step_equals_the_separate_pack():
+    """The driver lets the integrate pass of every frame but the last pack the next exchange (pack_next): same particles, same
+    migration, same wave as packing in a separate pass right before the exchange."""
+    a, aw, am = _run(2, 0, fused_pack=True)
+    b, bw, bm = _run(2, 0, fused_pack=False)
+    assert am == bm and am > 0
+    assert np.array_equal(a.view(np.uint8), b.view(np.uint8)) and np.array_equal(aw, bw)
 
 
 def test_single_rank_driver_equals_the_oracle_coupled_driver():
