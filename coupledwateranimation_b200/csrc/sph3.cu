@@ -1719,6 +1719,17 @@ extern "C" int cwa_coupled_step(cwa_ctx* ctx, cwa_sph hs, cwa_wave hw, int nfram
     const int pipe = (nframes > 1) ? pipeline_mode() : 0;
     bool wave_in_flight = false;
     s->counts_ahead = false;
+    // whichever way the call ends (an error included): the main stream is behind everything a side stream was given, and no
+    // count-ahead state outlives the call
+    struct Leave {
+        cwa_ctx* ctx; SphObj* s; bool* in_flight;
+        ~Leave()
+        {
+            if (*in_flight) cudaStreamWaitEvent(ctx->stream, ctx->ev_pipe[3], 0);
+            s->counts_ahead = false;
+            s->wait_before_sampling = nullptr;
+        }
+    } leave{ctx, s, &wave_in_flight};
     for (int f = 0; f < nframes; f++) {
         int image;
         if (coupling == CWA_COUPLING_LATEST) {
@@ -1742,7 +1753,7 @@ extern "C" int cwa_coupled_step(cwa_ctx* ctx, cwa_sph hs, cwa_wave hw, int nfram
             s->wait_before_sampling = nullptr;
         }
         wave_in_flight = false;
-        if (rc != 0) { s->counts_ahead = false; return rc; }
+        if (rc != 0) return rc;
         if (w->evolve) {                                                         // Module::sComputeAll :560
             if (more && (pipe & 1)) {
                 CWA_CUDA(cudaEventRecord(ctx->ev_pipe[2], ctx->stream));         // this frame's SPH passes are done with the field
@@ -1758,7 +1769,5 @@ extern "C" int cwa_coupled_step(cwa_ctx* ctx, cwa_sph hs, cwa_wave hw, int nfram
         }
         CWA_TRY(cwa_wave_bind_texture_unit(ctx, hw));                            // display() :413
     }
-    if (wave_in_flight) CWA_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_pipe[3], 0));
-    s->counts_ahead = false;
-    return 0;
+    return 0;                                                                    // (Leave joins the side stream)
 }
