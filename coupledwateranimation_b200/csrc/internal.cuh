@@ -253,6 +253,7 @@ struct cwa_ctx {
     unsigned long long* scan_state = nullptr;
     size_t scan_state_tiles = 0;
     void* encode_tiled = nullptr;  // PFN cuTensorMapEncodeTiled
+    std::vector<const void*> smem_attr_done;   // kernels whose dynamic shared-memory limit was raised on THIS context's device
 };
 
 // handle helpers (defined in api.cu)
@@ -298,6 +299,18 @@ int  sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which /*bit0 
 void sph_invalidate_for_buffer(cwa_ctx* ctx, cwa_buf particles);       // the particle buffer was written behind the SPH object's back
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device setting: remember it per context, not in a process-wide static
+// (a host may hold contexts on several devices)
+template <class K>
+static inline int ensure_dynamic_smem(cwa_ctx* ctx, K kernel, int bytes)
+{
+    const void* key = reinterpret_cast<const void*>(kernel);
+    for (const void* k : ctx->smem_attr_done) if (k == key) return 0;
+    CWA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    ctx->smem_attr_done.push_back(key);
+    return 0;
+}
 
 // Everything launched inside the scope (kernels, memsets, the KScope events around them) goes to `s` instead of the
 // context's main stream; ordering against the main stream is the caller's business (events).

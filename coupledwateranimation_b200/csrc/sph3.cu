@@ -1310,11 +1310,7 @@ extern "C" int cwa_set_tuning(cwa_ctx* ctx, const char* key, int value)
 template <int P, int L>
 static int launch_density(cwa_ctx* ctx, SphObj* s, GridObj* g, TexView tex)
 {
-    static bool attr = false;
-    if (!attr) {
-        CWA_CUDA(cudaFuncSetAttribute(sph3_density_grid_kernel<P, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, DENS_CAP_MAX * 16));
-        attr = true;
-    }
+    CWA_TRY(ensure_dynamic_smem(ctx, sph3_density_grid_kernel<P, L>, DENS_CAP_MAX * 16));
     KScope k(ctx, KID_DENSITY);
     sph3_density_grid_kernel<P, L><<<ceil_div(s->n, P), P * L, dens_cap() * 16, ctx->stream>>>(
         s->posS, s->velS, s->pack, s->n, g->view, g->offset, (const Sph3Const*)s->consts, tex, dens_cap());
@@ -1324,11 +1320,7 @@ static int launch_density(cwa_ctx* ctx, SphObj* s, GridObj* g, TexView tex)
 template <int P, int L>
 static int launch_force(cwa_ctx* ctx, SphObj* s, GridObj* g)
 {
-    static bool attr = false;
-    if (!attr) {
-        CWA_CUDA(cudaFuncSetAttribute(sph3_force_grid_kernel<P, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, FORCE_CAP_MAX * 32));
-        attr = true;
-    }
+    CWA_TRY(ensure_dynamic_smem(ctx, sph3_force_grid_kernel<P, L>, FORCE_CAP_MAX * 32));
     KScope k(ctx, KID_FORCE);
     sph3_force_grid_kernel<P, L><<<ceil_div(s->n, P), P * L, force_cap() * 32, ctx->stream>>>(
         s->pack, s->pairP, s->pairV, s->n, g->view, g->offset, (const Sph3Const*)s->consts, force_cap());

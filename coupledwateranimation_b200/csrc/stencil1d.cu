@@ -239,12 +239,10 @@ static int s1d_run(cwa_ctx* ctx, Stencil1dObj* s, int mode0, int nmodes, int ndi
         for (int u = 0; u < N; u++) by_unit[u] = s->image[s1d_image_with_unit(s, u)];
         KScope k(ctx, KID_WAVE);
         if (s->shader == S1D_SHALLOW) {
-            static bool attr = false;
-            if (!attr) { CWA_CUDA(cudaFuncSetAttribute(stencil1d_fused_kernel<S1D_SHALLOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+            CWA_TRY(ensure_dynamic_smem(ctx, stencil1d_fused_kernel<S1D_SHALLOW>, 200 * 1024));
             stencil1d_fused_kernel<S1D_SHALLOW><<<1, S1D_THREADS, smem, ctx->stream>>>(by_unit[0], by_unit[1], nullptr, w, mode0, nmodes, ndispatch, p);
         } else {
-            static bool attr = false;
-            if (!attr) { CWA_CUDA(cudaFuncSetAttribute(stencil1d_fused_kernel<S1D_WAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+            CWA_TRY(ensure_dynamic_smem(ctx, stencil1d_fused_kernel<S1D_WAVE>, 200 * 1024));
             stencil1d_fused_kernel<S1D_WAVE><<<1, S1D_THREADS, smem, ctx->stream>>>(by_unit[0], by_unit[1], by_unit[2], w, mode0, nmodes, ndispatch, p);
         }
         CWA_CUDA(cudaGetLastError());

@@ -401,11 +401,7 @@ int wave_dispatch_mode(cwa_ctx* ctx, WaveObj* w, int mode)
         wave_init_kernel<<<ggrid, gblock, 0, ctx->stream>>>(w->image[outi], w->w, w->h, w->ch, attr, w->variant, w->row0, w->h_global);
     } else if (mode == CWA_MODE_EVOLVE) {
         if (w->tma_ok) {
-            static bool attr_set = false;
-            if (!attr_set) {
-                CWA_CUDA(cudaFuncSetAttribute(wave_evolve_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_BYTES));
-                attr_set = true;
-            }
+            CWA_TRY(ensure_dynamic_smem(ctx, wave_evolve_tma_kernel, WT_SMEM_BYTES));
             const int tiles_x = ceil_div(w->w, WT_W), tiles_y = ceil_div(w->h, WT_H);
             const int num_tiles = tiles_x * tiles_y;
             int grid = ctx->sm_count * CWA_WT_CTAS_PER_SM;
