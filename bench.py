@@ -182,8 +182,8 @@ def scaled_workload(world: int) -> str:
             f"wave {sc['wave_w']}x{sc['wave_h']} scalar, coupling AS_SHIPPED, grid {sc['gn'][0]}x{sc['gn'][1]}x{sc['gn'][2]} {GRID_DESC}")
 
 
-def oracle_scene(O, world: int = 1):
-    sc = scaled_scene(world)
+def oracle_scene(O, world: int = 1, variant: str = ""):
+    sc = scaled_scene(1) if world <= 1 else c5_scene(world, variant or os.environ.get("CWA_BENCH_SCENE", "torque_scaled"))
     prm = O.default_params3()
     for a in range(4):
         prm.upper[a] = BOX_UPPER[a]
@@ -198,10 +198,10 @@ def oracle_scene(O, world: int = 1):
     return oc, n
 
 
-def cpu_reference_run(steps: int, warmup: int, world: int = 1):
+def cpu_reference_run(steps: int, warmup: int, world: int = 1, variant: str = ""):
     """The reference's CPU implementation of the path = the oracle (no GL stack exists)."""
     from oracle import oracle as O
-    oc, n = oracle_scene(O, world)
+    oc, n = oracle_scene(O, world, variant)
     cores = O.lib().orc_num_threads()
     for _ in range(warmup):
         oc.step(1)
@@ -224,16 +224,16 @@ def run_reference(args):
     steps, warmup = max(1, args.steps), max(0, args.warmup)
     # bounded: a full C4 frame costs a few seconds on the host cores; cap the frame count so the run ends in minutes
     world = max(1, args.gpus)
-    steps_run, warm_run = min(steps, max(4, 40 // world)), min(warmup, 3)
-    dt, cores, n_ref = cpu_reference_run(steps_run, warm_run, world)
+    steps_run, warm_run = (min(steps, 40), min(warmup, 3)) if world == 1 else (min(steps, 5), min(warmup, 1))
+    dt, cores, n_ref = cpu_reference_run(steps_run, warm_run, world, args.scene)
     ms = dt / steps_run * 1e3
     value = n_ref * steps_run / dt
     sample = f"{steps_run} full frames of the {n_ref}-particle scene (of --steps {steps}) after {warm_run} warm-up, OpenMP on {cores} host threads"
     line = {
         "impl": "reference", "metric": "particle_updates_per_sec", "value": value, "unit": "particle-updates/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak" if world == 1 or args.scene == "weak" else "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "steps_per_sec": 1e3 / ms,
-        "config": {"workload": WORKLOAD if world == 1 else scaled_workload(world),
+        "config": {"workload": WORKLOAD if world == 1 else c5_scene(world, args.scene or os.environ.get("CWA_BENCH_SCENE", "torque_scaled"))["name"],
                    "note": "CPU restatement of the reference GLSL (no Mesa/llvmpipe in image)"},
         "cpu_baseline": {"value": value, "unit": "particle-updates/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -254,7 +254,8 @@ def run_native(args):
         raise SystemExit("bench.py: no CUDA device -- the simulation step has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        from datetime import timedelta
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=timedelta(seconds=int(os.environ.get("CWA_DIST_TIMEOUT_S", "120"))))
         return run_native_distributed(args, world, rank, local_rank, torch, dist, cwa)
 
     def barrier():
@@ -423,16 +424,49 @@ def run_native(args):
         dist.destroy_process_group()
 
 
+def c5_scene(world: int, variant: str):
+    """BASELINE config 5: s = 28 -> 1792 x 5 x 1792 = 16 056 320 particles + 8192^2 wave, slab-decomposed over `world` GPUs
+    (STRONG scaling: the scene does not depend on world).  Cell size, texel size, lattice pitch and box factor are C4's.
+    variant "torque_scaled" (default): torque_coeff = 0.25 / 4 keeps the far-corner gain of force_comp.glsl:103-104's
+    torque = 0.25 * cross(pos, force_prev) feedback at C4's value (the tank is 4x wider; with the literal 0.25 the sheet blows up within
+    20 frames and the run measures NaN handling); variant "literal": the shader's 0.25 as written.
+    "weak": the round-1 weak-scaling scene (C4 grown by sqrt(world))."""
+    import math
+    if variant == "weak":
+        sc = scaled_scene(world)
+        sc["name"] = scaled_workload(world)
+        sc["scaling"] = "weak"
+        return sc
+    s5 = 28
+    f = s5 / S
+    n = 64 * s5
+    box = 0.55 * s5
+    sc = dict(nx=n, ny=NY, nz=n, wave_w=8192, wave_h=8192, uv=2.0 / s5, uv_z=0.0, torque=(0.25 / f if variant != "literal" else 0.0),
+              box_x=box, box_z=box, gmin=(0.0, -0.02, 0.0), gmax=(box, GRID_MAX[1], box),
+              gn=(int(round(GRID_N[0] * f)), GRID_N[1], int(round(GRID_N[2] * f))), scaling="strong")
+    sc["name"] = (f"C5: 3-D coupled SPH+wave, {n * NY * n} particles ({n}x{NY}x{n} lattice), wave 8192^2 scalar, coupling AS_SHIPPED, "
+                  f"z-slab decomposition over {world} GPUs (strong scaling), grid cells of ~h, "
+                  + ("torque_coeff 0.25/4 (far-corner gain of the torque feedback held at C4's value)" if variant != "literal" else "torque_coeff 0.25 as in force_comp.glsl:103"))
+    return sc
+
+
+def _log(rank, msg):
+    print(f"[bench rank {rank} +{time.time() - _T0:7.2f}s] {msg}", file=sys.stderr, flush=True)
+
+
+_T0 = time.time()
+
+
 def run_native_distributed(args, world, rank, local_rank, torch, dist, cwa):
-    """N > 1: weak scaling of the slab-decomposed coupled step (coupledwateranimation_b200.distributed).
-    The scene is C4 grown by sqrt(N) in x and z (scaled_scene): every GPU keeps about one C4 worth of particles, grid cells and wave
-    cells."""
+    """N > 1: the slab-decomposed coupled step through the C-ABI slab object (csrc/slab.cu): peer stores into the neighbours' mailboxes,
+    device-side flags, device-resident counts.  torch.distributed hands the IPC handles round once and reduces the timings."""
     import math
 
-    from coupledwateranimation_b200.distributed import CudaBackend, DistributedCoupled, SlabPlan
+    from coupledwateranimation_b200.distributed import SlabPlan, SlabRank, connect_processes, plan_desc
 
     K, W = max(1, args.steps), max(3, args.warmup)
-    sc = scaled_scene(world)
+    variant = args.scene or os.environ.get("CWA_BENCH_SCENE", "torque_scaled")
+    sc = c5_scene(world, variant)
     nxg, nzg = sc["nx"], sc["nz"]
     wave_w, wave_h = sc["wave_w"], sc["wave_h"]
     uv, uv_z = sc["uv"], sc["uv_z"] or sc["uv"]
@@ -440,204 +474,207 @@ def run_native_distributed(args, world, rank, local_rank, torch, dist, cwa):
     h = 0.01
     sp = np.float32(np.float32(2.0 * 0.85) * np.float32(0.005))
     ks = np.arange(nzg, dtype=np.float32) * sp
-    # slabs with equal particle counts: the texture's t range [0, 1] covers z in [0, 0.5 * S * world] only, the lattice reaches
-    # 0.544 * S * world, so equal ROW blocks would give the last rank more particles than the others
+    # slabs with equal particle counts: the texture's t range [0, 1] covers z in [0, 0.5 * s] only, the lattice reaches 0.544 * s, so
+    # equal ROW blocks would give the last rank more particles than the others
     row_bounds = SlabPlan.balanced_row_bounds(world, wave_h, uv_z, ks - np.float32(0.5) * sp)
-    plan = SlabPlan.make(world, rank, wave_w, wave_h, uv_z, h, row_bounds)
-    kk = np.nonzero((ks >= plan.z_lo) & (ks < plan.z_hi))[0]
-    i, j, k = np.meshgrid(np.arange(nxg, dtype=np.float32), np.arange(sc["ny"], dtype=np.float32), kk.astype(np.float32), indexing="ij")
-    own = np.zeros(i.size, cwa.PARTICLE)
-    own["pos"][:, 0] = i.ravel() * sp; own["pos"][:, 1] = j.ravel() * sp; own["pos"][:, 2] = k.ravel() * sp; own["pos"][:, 3] = 1.0
-    own["extras"][:] = (1000.0, 0.0, 500.0, 50.0)
-    del i, j, k
-
-    # the shipped parameters make the over-dense sheet blast apart (|v| in the thousands within ten frames), so tens of
-    # thousands of particles cross a slab face per frame: generous fixed-size messages (a slab face grows with sqrt(world))
-    cap = int(32768 * math.sqrt(world) + 4095) // 4096 * 4096
     n_global = nxg * sc["ny"] * nzg
+    per_face = nxg * sc["ny"]                              # particles of one lattice layer
+    cap_ghost = int(per_face * 12 + 4095) // 4096 * 4096   # the 2h band holds ~2.4 lattice layers at rest; the sheet compresses against faces
+    cap_mig = int(per_face * 6 + 4095) // 4096 * 4096
+    lib = cwa._capi.load()
+    desc = plan_desc(lib, world, rank, wave_w, wave_h, 1, uv_z, h, row_bounds, cap_mig=cap_mig, cap_ghost=cap_ghost,
+                     timeout_ms=int(os.environ.get("CWA_SLAB_TIMEOUT_MS", "20000")))
+    kk = np.nonzero((ks >= desc.z_lo) & (ks < desc.z_hi))[0]
+    n_own0 = nxg * sc["ny"] * kk.size
+    desc.capacity = int(n_own0 * 1.12) + 2 * (2 * cap_mig + cap_ghost) + 8192
+    _log(rank, f"scene {variant}: {n_global} particles, own {n_own0}, rows [{desc.row_lo},{desc.row_hi}) stored [{desc.store_lo},{desc.store_hi}), capacity {desc.capacity}")
+
+    def own_particles():
+        i, j, k = np.meshgrid(np.arange(nxg, dtype=np.float32), np.arange(sc["ny"], dtype=np.float32), kk.astype(np.float32), indexing="ij")
+        own = np.zeros(i.size, cwa.PARTICLE)
+        own["pos"][:, 0] = i.ravel() * sp; own["pos"][:, 1] = j.ravel() * sp; own["pos"][:, 2] = k.ravel() * sp; own["pos"][:, 3] = 1.0
+        own["extras"][:] = (1000.0, 0.0, 500.0, 50.0)
+        return own
+
+    cell = box_x / sc["gn"][0]
 
     def build_rank():
-        """This rank's share of the scene in a context of its own: (context, backend, driver)."""
         c = cwa.Context(local_rank)
         c.set_boundary(upper=(box_x, 1.0, box_z, 500.0), lower=BOX_LOWER)
         c.set_sim_constants(uv_scale=uv, uv_scale_z=sc["uv_z"], torque_coeff=sc["torque"])
-        zl = max(0.0, plan.z_lo - 0.06) if rank > 0 else 0.0
-        zh = min(box_z, plan.z_hi + 0.06) if rank < world - 1 else box_z
-        ncx = sc["gn"][0]
-        ncz = max(4, int(math.ceil((zh - zl) / (box_x / ncx))))
-        b = CudaBackend(cwa, c, plan, int(own.size * 1.3) + 6 * cap + 8192, (0.0, -0.02, zl), (box_x, sc["gmax"][1], zh), (ncx, sc["gn"][1], ncz),
-                        cap_mig=cap, cap_ghost=cap)
-        b.upload_owned(own)
-        d = DistributedCoupled(b, plan, dist)
-        d.init_wave_halos()
-        return c, b, d
+        zl = max(0.0, desc.z_lo - 0.06) if rank > 0 else 0.0
+        zh = min(box_z, desc.z_hi + 0.06) if rank < world - 1 else box_z
+        ncz = max(4, int(math.floor((zh - zl) / cell + 1e-6)))      # cells never narrower than C4's (the 3 x 3 x 3 query needs cell >= 1.0025 h)
+        r = SlabRank(cwa, c, desc, (0.0, -0.02, zl), (box_x, sc["gmax"][1], zh), (sc["gn"][0], sc["gn"][1], ncz))
+        own = own_particles()
+        r.upload_owned(own)
+        del own
+        connect_processes(r, dist)
+        return c, r
 
-    ctx, be, drv = build_rank()
+    ctx, rk = build_rank()
+    _log(rank, "built + connected")
+
+    def reduce_max(v):
+        t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum(v):
+        t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def fail_everywhere(what):
+        """Every rank takes the same decision (the flag is all-reduced), so nobody is left waiting in a collective."""
+        if rank == 0:
+            print(json.dumps({"metric": "particle_updates_per_sec", "value": None, "n_gpus": world, "error": what}), flush=True)
+        dist.barrier()
+        dist.destroy_process_group()
+        sys.exit(3)
 
     sampler = ClockSampler(local_rank)
-    if os.environ.get("CWA_BENCH_DEBUG"):
-        for fr in range(8):
-            drv.step(1, COUPLING)
-            q = be.download_owned()
-            zz = q["pos"][:, 2]
-            print(f"[debug rank {rank}] frame {fr + 1}: owned range {be.n_owned} live {q.size} ghosts {be.n_ghost} migrated_in {be.migrated_in} "
-                  f"z [{np.nanmin(zz):.5f}, {np.nanmax(zz):.5f}] slab [{plan.z_lo:.5f}, {plan.z_hi:.5f}] vmax {np.nanmax(np.abs(q['vel'][:, :3])):.3f} "
-                  f"nan {int(np.isnan(zz).sum())}", flush=True)
-    if os.environ.get("CWA_BENCH_TRACE"):
-        # diagnostic only: device time and per-kernel split of every 5th frame of the first 80
-        for fr in range(80):
-            if fr % 5 == 0:
-                ctx.profile_begin()
-                t0 = time.perf_counter(); drv.step(1, COUPLING); ctx.synchronize(); wall = time.perf_counter() - t0
-                pr = ctx.profile_end()
-                ksum = sum(v[0] for v in pr.values())
-                print(f"[trace rank {rank}] frame {fr}: wall {wall * 1e6:.0f} us, kernels {ksum * 1e3:.0f} us, owned {be.n_owned} ghosts {be.n_ghost} | "
-                      + ", ".join(f"{k} {v[0] * 1e3:.0f}" for k, v in sorted(pr.items(), key=lambda kv: -kv[1][0])[:6]), flush=True)
-            else:
-                drv.step(1, COUPLING)
-    drv.step(W, COUPLING)
+    rk.step(W, COUPLING)
     ctx.synchronize()
-    if os.environ.get("CWA_BENCH_PHASES"):
-        # diagnostic only: wall time per phase with a device synchronise after each (perturbs the overlap)
-        acc = {"exchange": 0.0, "sph": 0.0, "wave": 0.0, "halo": 0.0}
-        nfr = 30
-        for _ in range(nfr):
-            t0 = time.perf_counter(); drv._particle_exchange(); ctx.synchronize(); t1 = time.perf_counter()
-            be.sph_step(be.tex_unit0()); ctx.synchronize(); t2 = time.perf_counter()
-            be.wave_step(); ctx.synchronize(); t3 = time.perf_counter()
-            drv._wave_halo_refresh(); be.bind_texture_unit(); ctx.synchronize(); t4 = time.perf_counter()
-            acc["exchange"] += t1 - t0; acc["sph"] += t2 - t1; acc["wave"] += t3 - t2; acc["halo"] += t4 - t3
-        print(f"[phases rank {rank}] " + ", ".join(f"{k} {v / nfr * 1e6:.0f} us" for k, v in acc.items()), flush=True)
-        ctx.profile_begin()
-        drv.step(10, COUPLING)
-        pr = ctx.profile_end()
-        print(f"[early kernels rank {rank}] owned {be.n_owned} ghosts {be.n_ghost} "
-              + ", ".join(f"{k} {v[0] / v[1] * 1e3:.0f}us x{v[1] // 10}" for k, v in sorted(pr.items(), key=lambda kv: -kv[1][0])[:14]), flush=True)
+    err = reduce_max(rk.counts()["err"])
+    if err:
+        fail_everywhere(f"slab exchange error bits {int(err)} during warm-up (1 sender overflow, 2 capacity, 4/8 timeouts)")
+    _log(rank, "warm-up done")
+    if os.environ.get("CWA_BENCH_TRACE"):
+        for fr in range(0, 60, 5):
+            ctx.profile_begin()
+            t0 = time.perf_counter(); rk.step(1, COUPLING); ctx.synchronize(); wall = time.perf_counter() - t0
+            pr = ctx.profile_end()
+            c = rk.counts()
+            _log(rank, f"trace frame {fr}: wall {wall * 1e6:.0f} us owned {c['n_owned']} ghosts {c['n_ghost']} free {c['free']} | "
+                 + ", ".join(f"{k} {v[0] * 1e3:.0f}" for k, v in sorted(pr.items(), key=lambda kv: -kv[1][0])[:8]))
+            rk.step(4, COUPLING)
     if rank == 0:
         sampler.start()
     dist.barrier(); ctx.synchronize()
     launches0 = ctx.launch_count
     ctx.timer_begin()
-    drv.step(K, COUPLING)
+    rk.step(K, COUPLING)
     ms_total = ctx.timer_end()
     launches = ctx.launch_count - launches0
     dist.barrier()
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
-    dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-    t_end = time.time() + 1.0
-    while time.time() < t_end:
-        drv.step(20, COUPLING)
+    ms_total = reduce_max(ms_total)
+    launches_all = int(reduce_sum(launches))
+    _log(rank, f"timed region done: {ms_total / K:.3f} ms/step")
+    # a FIXED number of further frames (the same on every rank) keeps the kernels running for the 50 ms clock sampler
+    n_load = max(100, int(600.0 / max(ms_total / K, 0.05)))
+    n_load = int(reduce_max(n_load))
+    rk.step(min(n_load, 3000), COUPLING)
+    ctx.synchronize()
     clocks = sampler.stop() if rank == 0 else None
 
     ctx.profile_begin()
-    drv.step(K, COUPLING)
+    rk.step(K, COUPLING)
     prof = ctx.profile_end()
+    cnt = rk.counts()
+    live = rk.download_owned().size
+    total_live = int(reduce_sum(live))
+    err = reduce_max(cnt["err"])
+    if err:
+        fail_everywhere(f"slab exchange error bits {int(err)} (1 sender overflow, 2 capacity, 4/8 timeouts)")
+    if total_live != n_global:
+        fail_everywhere(f"particle count not conserved: {total_live} live of {n_global}")
+    _log(rank, f"profile done; owned range {cnt['n_owned']} live {live} ghosts {cnt['n_ghost']} free {cnt['free']} migrated in {cnt['migrated_in']}")
     if os.environ.get("CWA_BENCH_PHASES"):
-        q = be.download_owned()
-        cnt = be.grid.read(cwa.GRID_COUNTER, be.grid.num_cells_total)
-        print(f"[kernels rank {rank}] owned {q.size} ghosts {be.n_ghost} max/cell {int(cnt.max())} cells>64: {int((cnt > 64).sum())} "
-              + ", ".join(f"{k} {v[0] / v[1] * 1e3:.0f}us" for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:14]), flush=True)
+        _log(rank, "kernels: " + ", ".join(f"{k} {v[0] / v[1] * 1e3:.0f}us x{v[1] // K}" for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:14]))
 
-    # end to end: every rank's particle slab and wave rows live in pinned HOST buffers between steps.  Two scene streams per rank
-    # (two contexts, each with its own backend, driver and pinned buffers) take turns, so one step's upload overlaps the other
-    # stream's frame and read-back; a step counts when its results are in host memory.
+    # ---- end to end: every rank's owned particle range and stored wave rows live in pinned HOST buffers between steps: each step uploads
+    # them, runs one coupled frame (exchange included) and reads the results back; a step counts when its results are in host memory
     import ctypes as C
     row_bytes = wave_w * 4
+    rows_stored = desc.store_hi - desc.store_lo
+    pin_p = torch.empty(desc.capacity * cwa.PARTICLE.itemsize, dtype=torch.uint8).pin_memory()
+    pin_w = [torch.empty(rows_stored * wave_w, dtype=torch.float32).pin_memory() for _ in range(2)]
+    pin_c = torch.zeros(8, dtype=torch.int32).pin_memory()
+    host_p = pin_p.numpy().view(cwa.PARTICLE)
+    host_w = [w_.numpy().reshape(rows_stored, wave_w) for w_ in pin_w]
+    n_cur = cnt["n_owned"]
+    host_p[:n_cur] = rk.buffer.read(cwa.PARTICLE, n_cur)
+    host_w[0][:] = rk.wave.read_role(0); host_w[1][:] = rk.wave.read_role(1)
+    lib_, hnd = ctx.lib, ctx.h
     moved = [0, 0]
 
-    class SlotD:
-        def __init__(self, c, b, d):
-            self.ctx, self.be, self.drv = c, b, d
-            self.pin_p = torch.empty(b.capacity * cwa.PARTICLE.itemsize, dtype=torch.uint8).pin_memory()
-            self.pin_w = [torch.empty(plan.rows_stored * wave_w, dtype=torch.float32).pin_memory() for _ in range(2)]
-            self.host_p = self.pin_p.numpy().view(cwa.PARTICLE)
-            self.host_w = [w_.numpy().reshape(plan.rows_stored, wave_w) for w_ in self.pin_w]
+    def e2e_step():
+        nonlocal n_cur
+        cwa.check(lib_.cwa_buffer_sub_data(hnd, rk.buffer.h, 0, n_cur * 64, C.c_void_p(host_p.ctypes.data)))
+        cwa.check(lib_.cwa_wave_write_image(hnd, rk.wave.h, rk.wave.role_image(0), C.c_void_p(host_w[0].ctypes.data)))
+        cwa.check(lib_.cwa_wave_write_image(hnd, rk.wave.h, rk.wave.role_image(1), C.c_void_p(host_w[1].ctypes.data)))
+        rk.step(1, COUPLING)
+        cwa.check(lib_.cwa_slab_counts_async(hnd, rk.h, C.c_void_p(pin_c.data_ptr())))
+        host_w[0], host_w[1] = host_w[1], host_w[0]
+        cwa.check(lib_.cwa_wave_read_image_async(hnd, rk.wave.h, rk.wave.role_image(0), C.c_void_p(host_w[0].ctypes.data)))
+        ctx.synchronize()                                  # the owned range after this frame (arrivals may have been appended)
+        n_new = int(pin_c[0])
+        cwa.check(lib_.cwa_buffer_read_async(hnd, rk.buffer.h, 0, n_new * 64, C.c_void_p(host_p.ctypes.data)))
+        ctx.synchronize()
+        moved[0] += n_cur * 64 + 2 * rows_stored * row_bytes
+        moved[1] += n_new * 64 + rows_stored * row_bytes
+        n_cur = n_new
 
-        def submit(self):
-            c, b, hp, hw = self.ctx, self.be, self.host_p, self.host_w
-            lib, hnd = c.lib, c.h
-            n = b.n_owned
-            cwa.check(lib.cwa_buffer_sub_data(hnd, b.buffer.h, 0, n * 64, C.c_void_p(hp.ctypes.data)))
-            cwa.check(lib.cwa_wave_write_image(hnd, b.wave.h, b.wave.role_image(0), C.c_void_p(hw[0].ctypes.data)))
-            cwa.check(lib.cwa_wave_write_image(hnd, b.wave.h, b.wave.role_image(1), C.c_void_p(hw[1].ctypes.data)))
-            self.drv.step(1, COUPLING)
-            n2 = b.n_owned
-            cwa.check(lib.cwa_buffer_read_async(hnd, b.buffer.h, 0, n2 * 64, C.c_void_p(hp.ctypes.data)))
-            hw[0], hw[1] = hw[1], hw[0]
-            cwa.check(lib.cwa_wave_read_image_async(hnd, b.wave.h, b.wave.role_image(0), C.c_void_p(hw[0].ctypes.data)))
-            moved[0] += n * 64 + 2 * plan.rows_stored * row_bytes
-            moved[1] += n2 * 64 + plan.rows_stored * row_bytes
-
-    slots = [SlotD(ctx, be, drv)]
-    if os.environ.get("CWA_E2E_SLOTS", "2") != "1":
-        slots.append(SlotD(*build_rank()))
-    owned_now = be.buffer.read(cwa.PARTICLE, be.n_owned)                 # the owned RANGE (dead slots included), as the device holds it
-    w0_now, w1_now = be.wave.read_role(0), be.wave.read_role(1)
-    for sl in slots:
-        sl.be.n_owned, sl.be.n_ghost = be.n_owned, 0
-        sl.host_p[:be.n_owned] = owned_now
-        sl.host_w[0][:] = w0_now; sl.host_w[1][:] = w1_now
-    ns = len(slots)
-    for k in range(2 * ns):
-        slots[k % ns].ctx.synchronize()
-        slots[k % ns].submit()
-    for sl in slots:
-        sl.ctx.synchronize()
+    for _ in range(3):
+        e2e_step()
     moved[0] = moved[1] = 0
     dist.barrier()
+    n_e2e = K
     t0 = time.perf_counter()
-    for k in range(K):
-        sl = slots[k % ns]
-        sl.ctx.synchronize()                              # the slot's previous step is complete: its results are in host memory
-        sl.submit()
-    for sl in slots:
-        sl.ctx.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s, float(moved[0]) / K, float(moved[1]) / K], dtype=torch.float64, device="cuda")
-    tm = t.clone()
-    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    e2e_s = float(tm[0].item())
-    h2d, d2h = int(t[1].item()), int(t[2].item())
+    for _ in range(n_e2e):
+        e2e_step()
+    e2e_s = reduce_max(time.perf_counter() - t0)
+    h2d = int(reduce_sum(moved[0] / n_e2e)); d2h = int(reduce_sum(moved[1] / n_e2e))
+    err = reduce_max(rk.counts()["err"])
+    if err:
+        fail_everywhere(f"slab exchange error bits {int(err)} in the end-to-end leg")
+    _log(rank, f"e2e done: {e2e_s / n_e2e * 1e3:.3f} ms/step")
 
+    # per-rank kernel split for the record (rank 0 prints; the others contribute their frame time)
+    kern_ms = sum(v[0] for v in prof.values()) / K
+    gathered = [None] * world
+    dist.all_gather_object(gathered, {"rank": rank, "kernel_ms_per_frame": kern_ms, "owned": live, "ghosts": cnt["n_ghost"],
+                                      "heavy_ms": prof.get("heavy_targets", (0.0, 1))[0] / K, "exchange_ms": prof.get("exchange", (0.0, 1))[0] / K})
     if rank == 0:
         peak, peak_src = measured_peaks()
-        n_local = be.n_owned + be.n_ghost
-        c_cells = be.grid.num_cells_total
-        g_local = plan.rows_stored * wave_w
+        n_local = cnt["n_total"]
+        c_cells = rk.grid.num_cells_total
+        g_local = rows_stored * wave_w
         kern = []
         tot_ms = sum(v[0] for v in prof.values()) or 1.0
-        for name, (ms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+        for name, (ms, cn) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
             pp, pc, pw = ALGO_BYTES.get(name, (0, 0, 0))
             per_launch = pp * n_local + pc * c_cells + pw * g_local
-            avg_ms = ms / cnt
+            avg_ms = ms / cn
             gbs = per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
-            kern.append({"kernel": name, "launches": cnt, "avg_us": avg_ms * 1e3, "share": ms / tot_ms, "algo_bytes": per_launch,
+            kern.append({"kernel": name, "launches": cn, "avg_us": avg_ms * 1e3, "share": ms / tot_ms, "algo_bytes": per_launch,
                          "achieved_gbs": gbs, "frac": gbs / peak})
         dom = kern[0]
         ms_step = ms_total / K
         line = {
             "metric": "particle_updates_per_sec", "value": n_global * K / (ms_total * 1e-3), "unit": "particle-updates/s", "n_gpus": world,
-            "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": sc.get("scaling", "strong"), "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "steps_per_sec": 1e3 / ms_step,
-            "config": {"workload": scaled_workload(world), "per_gpu_particles": n_global // world,
-                       "parallelism": f"z-slab decomposition x{world}: ghost layer 2h + migration (NCCL p2p), wave row blocks with sampling halos + last-row broadcast",
+            "config": {"workload": sc["name"], "per_gpu_particles": n_global // world,
+                       "parallelism": f"z-slab decomposition x{world}: ghost layer 2h + migration by peer stores into the neighbours' mailboxes (NVLink P2P, CUDA IPC), "
+                                      "device-side arrival flags, device-resident counts; wave row blocks with sampling halos + global-last-row ring; no host sync per frame",
                        "l2": "working set > 126 MB L2 per GPU: inputs larger than L2, no flush needed",
-                       "timing": "cudaEvent on each rank's context stream around K coupled frames (communication included), max over ranks"},
+                       "timing": "cudaEvent on each rank's context stream around K coupled frames (exchange included), max over ranks"},
             "clocks": clocks,
-            "e2e": {"value": n_global * K / e2e_s, "unit": "particle-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_s / K * 1e3,
-                    "how": f"C ABI, pinned host buffers; {ns} scene streams per rank take turns; a step counts when its results are in host memory"},
-            "gpu_launches": int(lt.item()),
-            "roofline": {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
+            "e2e": {"value": n_global * n_e2e / e2e_s, "unit": "particle-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_s / n_e2e * 1e3,
+                    "how": "C ABI, pinned host buffers: every step uploads each rank's owned particles + two wave levels, runs one coupled frame (exchange included) "
+                           "and reads particles + the new level back; a step counts when its results are in host memory on every rank"},
+            "gpu_launches": launches_all,
+            "roofline": {"kernel": dom["kernel"], "bound": "fp32-issue" if dom["kernel"] in ("density", "force", "heavy_targets") else "hbm",
+                         "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
                          "traffic": ncu_traffic(dom["kernel"]), "peak_source": peak_src, "note": "rank 0's kernels; neighbour loops are FP32-issue / L1 bound"},
             "roofline_kernels": kern,
+            "ranks": gathered,
             "cpu_baseline": None,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -649,6 +686,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scene", default="", choices=["", "torque_scaled", "literal", "weak"],
+                    help="--gpus N > 1: C5 with torque_coeff 0.25/4 (default), C5 with the shader's literal 0.25, or the weak-scaling scene C4 x sqrt(N)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -38,6 +38,14 @@ class SimConstants(C.Structure):
                 ("uv_scale_z", C.c_float), ("torque_coeff", C.c_float), ("pad1", C.c_float), ("pad2", C.c_float)]
 
 
+class SlabDesc(C.Structure):
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("wave_w", C.c_int), ("wave_h", C.c_int), ("wave_ch", C.c_int),
+                ("row_lo", C.c_int), ("row_hi", C.c_int), ("store_lo", C.c_int), ("store_hi", C.c_int),
+                ("left_store_hi", C.c_int), ("right_store_lo", C.c_int), ("halo_rows_max", C.c_int),
+                ("z_lo", C.c_float), ("z_hi", C.c_float), ("band", C.c_float),
+                ("cap_mig", C.c_int), ("cap_ghost", C.c_int), ("capacity", C.c_int), ("timeout_ms", C.c_int)]
+
+
 # name -> (restype, argtypes); every symbol include/cwa_b200.h declares
 _P = C.c_void_p
 _I = C.c_int
@@ -134,6 +142,17 @@ SIGNATURES = {
     "cwa_sph_step_slab": (_I, [_P, _I, _I, _F, _F, _F, _I, _I, _I, _I]),
     "cwa_slab_unpack": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _IP]),
     "cwa_slab_compact": (_I, [_P, _I, _I, _I, _IP]),
+    "cwa_slab_plan": (_I, [_I, _I, _I, _I, _I, C.c_double, C.c_double, _IP, C.POINTER(SlabDesc)]),
+    "cwa_slab_create": (_I, [_P, C.POINTER(SlabDesc), _I, _I, _IP]),
+    "cwa_slab_destroy": (_I, [_P, _I]),
+    "cwa_slab_export": (_I, [_P, _I, _P]),
+    "cwa_slab_mailbox": (_I, [_P, _I, C.POINTER(_P), C.POINTER(_Z)]),
+    "cwa_slab_connect": (_I, [_P, _I, _I, _P, _P]),
+    "cwa_slab_set_owned": (_I, [_P, _I, _I]),
+    "cwa_slab_step": (_I, [_P, _I, _I, _I]),
+    "cwa_slab_group_step": (_I, [C.POINTER(_P), _IP, _I, _I, _I]),
+    "cwa_slab_counts": (_I, [_P, _I, _IP]),
+    "cwa_slab_counts_async": (_I, [_P, _I, _P]),
     "cwa_wave_create_block": (_I, [_P, _I, _I, _I, _I, _I, _I, _IP]),
     "cwa_wave_last_row_buffer": (_I, [_P, _I, _I, _IP]),
     "cwa_sph2_create": (_I, [_P, _I, _I, _I, _IP]),

@@ -1,17 +1,22 @@
-"""Build libcwa_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+"""Build libcwa_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+Every .cu is compiled to its own object (in parallel, rebuilt only when it or a header changed) and the objects are linked
+into the shared library; no relocatable device code is needed (kernels never call across translation units)."""
 from __future__ import annotations
 
 import os
 import shutil
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libcwa_b200.so")
-SOURCES = ["api.cu", "grid.cu", "wave.cu", "sph3.cu", "sph2.cu", "multi.cu", "stencil1d.cu", "state.cu"]
+SOURCES = ["api.cu", "grid.cu", "wave.cu", "sph3.cu", "sph2.cu", "multi.cu", "slab.cu", "stencil1d.cu", "state.cu", "interop.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden",
 ]
 
 
@@ -20,6 +25,10 @@ def _nvcc() -> str:
         if cand and os.path.exists(cand):
             return cand
     raise RuntimeError("nvcc not found: cannot build libcwa_b200.so")
+
+
+def _headers():
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))] + [os.path.join(HERE, "..", "include", "cwa_b200.h")]
 
 
 def is_stale() -> bool:
@@ -33,14 +42,32 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    os.makedirs(OBJ, exist_ok=True)
+    nvcc = _nvcc()
+    hdr_t = max(os.path.getmtime(h) for h in _headers())
+    jobs = []
+    for s in SOURCES:
+        src, obj = os.path.join(CSRC, s), os.path.join(OBJ, s[:-3] + ".o")
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_t):
+            jobs.append((s, [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]))
+
+    def run(job):
+        return job[0], subprocess.run(job[1], capture_output=True, text=True)
+
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 4))) as ex:
+        for name, r in ex.map(run, jobs):
+            if r.returncode != 0:
+                raise RuntimeError(f"nvcc failed on {name}:\n" + r.stdout + r.stderr)
+            if verbose:
+                print(f"==== {name}\n{r.stderr}")
+    objs = [os.path.join(OBJ, s[:-3] + ".o") for s in SOURCES]
+    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-o", LIB] + objs,
+                       capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-    if verbose:
-        print(r.stderr)
+        raise RuntimeError("nvcc link failed:\n" + r.stdout + r.stderr)
     return LIB
 
 
 if __name__ == "__main__":
-    print(build(force=True, verbose=True))
+    import sys
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -147,6 +147,8 @@ extern "C" void cwa_destroy(cwa_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 2; i++) cudaStreamSynchronize(ctx->side_stream[i]);
+    slab_destroy_all(ctx);
     for (size_t i = 0; i < ctx->sphs.size(); i++) if (ctx->sphs[i].live) cwa_sph_destroy(ctx, (int)i);
     for (size_t i = 0; i < ctx->sph2s.size(); i++) if (ctx->sph2s[i].live) cwa_sph2_destroy(ctx, (int)i);
     for (size_t i = 0; i < ctx->waves.size(); i++) if (ctx->waves[i].live) cwa_wave_destroy(ctx, (int)i);
@@ -202,7 +204,7 @@ extern "C" unsigned long long cwa_launch_count(cwa_ctx* ctx) { return ctx ? ctx-
 // per-kernel device timing (CUDA-event pairs around every launch on the context stream)
 static const char* const g_kernel_names[KID_COUNT] = {
     "clear(memset)", "grid_hash_count", "scan_lookback", "grid_insert", "grid_cell_order", "reorder",
-    "density", "force", "integrate", "wave_evolve", "other", "heavy_targets"};
+    "density", "force", "integrate", "wave_evolve", "other", "heavy_targets", "exchange"};
 
 extern "C" int cwa_profile_kernel_count(void) { return KID_COUNT; }
 extern "C" const char* cwa_profile_kernel_name(int id) { return (id >= 0 && id < KID_COUNT) ? g_kernel_names[id] : ""; }

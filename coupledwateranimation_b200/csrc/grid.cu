@@ -19,10 +19,11 @@
 // pass (the reference runs the atomics twice: count, clear, insert).
 template <int DIM>
 __global__ void __launch_bounds__(256)
-grid_hash_count_kernel(const char* __restrict__ particles, int stride_bytes, int n, GridView g,
+grid_hash_count_kernel(const char* __restrict__ particles, int stride_bytes, int n, const int* __restrict__ n_dev, GridView g,
                        int* __restrict__ counter, int* __restrict__ cell_of, int* __restrict__ rank)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_dev != nullptr) n = min(n, __ldg(n_dev));     // device-resident particle count (slab decomposition): `n` is only the launch bound
     int cell = -1;
     if (i < n) {
         const float4 p = __ldg(reinterpret_cast<const float4*>(particles + (size_t)i * stride_bytes));
@@ -66,17 +67,15 @@ grid_hash_count_kernel(const char* __restrict__ particles, int stride_bytes, int
 //      instruction of a warp covers 512 contiguous bytes)
 //   3: 1024 x 16 warp-striped
 constexpr int SCAN_MIN_TILE = 4096;                     // smallest tile of any configuration: sizes the tile-state arrays
-static int g_scan_config = -1;
-static int scan_config()
+static int scan_config(cwa_ctx* ctx)
 {
-    if (g_scan_config < 0) {
+    if (ctx->tune.scan_config < 0) {
         const char* e = getenv("CWA_SCAN_CONFIG");
         const int v = e ? atoi(e) : 2;
-        g_scan_config = (v < 0 || v > 3) ? 2 : v;
+        ctx->tune.scan_config = (v < 0 || v > 3) ? 2 : v;
     }
-    return g_scan_config;
+    return ctx->tune.scan_config;
 }
-int scan_set_config(int v) { if (v < 0 || v > 3) return -1; g_scan_config = v; return 0; }
 
 size_t scan_num_tiles(int n) { return (size_t)((n + SCAN_MIN_TILE - 1) / SCAN_MIN_TILE); }
 
@@ -250,7 +249,7 @@ int scan_exclusive_launch(cwa_ctx* ctx, const int* in, int* out, int n, int* tic
     const int write_total = n > 0;
     if (n < 0) n = -n;
     KScope k(ctx, KID_SCAN);
-    switch (scan_config()) {
+    switch (scan_config(ctx)) {
     case 0: scan_lookback_kernel<256, 16, false><<<ceil_div(n, 256 * 16), 256, 0, ctx->stream>>>(in, out, n, write_total, ticket, tile_state); break;
     case 1: scan_lookback_kernel<512, 32, false><<<ceil_div(n, 512 * 32), 512, 0, ctx->stream>>>(in, out, n, write_total, ticket, tile_state); break;
     case 3: scan_lookback_kernel<1024, 16, true><<<ceil_div(n, 1024 * 16), 1024, 0, ctx->stream>>>(in, out, n, write_total, ticket, tile_state); break;
@@ -296,9 +295,10 @@ int prefix_sum_level_launch(cwa_ctx* ctx, int* x, int n, int phase, int stride, 
 // into the count pass.  Order inside a cell is the (scheduling-dependent) arrival order.
 __global__ void __launch_bounds__(256)
 grid_insert_kernel(const int* __restrict__ cell_of, const int* __restrict__ rank, const int* __restrict__ offset,
-                   int n, int* __restrict__ arrival)
+                   int n, const int* __restrict__ n_dev, int* __restrict__ arrival)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_dev != nullptr) n = min(n, __ldg(n_dev));
     if (i >= n) return;
     const int c = __ldg(cell_of + i);
     if (c < 0) return;
@@ -311,9 +311,10 @@ grid_insert_kernel(const int* __restrict__ cell_of, const int* __restrict__ rank
 // list is a handful of consecutive ints that stay in L1 for the threads of the same cell.
 __global__ void __launch_bounds__(256)
 grid_cell_order_kernel(const int* __restrict__ cell_of, const int* __restrict__ offset, const int* __restrict__ arrival,
-                       int n, int* __restrict__ index_list)
+                       int n, const int* __restrict__ n_dev, int* __restrict__ index_list)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_dev != nullptr) n = min(n, __ldg(n_dev));
     if (i >= n) return;
     const int c = __ldg(cell_of + i);
     if (c < 0) return;
@@ -355,9 +356,9 @@ int grid_build_internal(cwa_ctx* ctx, GridObj* g, const void* particles, int str
         if (n > 0) {
             KScope k(ctx, KID_HASH_COUNT);
             if (g->dim == 2)
-                grid_hash_count_kernel<2><<<ceil_div(n, 256), 256, 0, ctx->stream>>>((const char*)particles, stride_bytes, n, g->view, g->counter, g->cell_of, g->rank);
+                grid_hash_count_kernel<2><<<ceil_div(n, 256), 256, 0, ctx->stream>>>((const char*)particles, stride_bytes, n, opts.n_dev, g->view, g->counter, g->cell_of, g->rank);
             else
-                grid_hash_count_kernel<3><<<ceil_div(n, 256), 256, 0, ctx->stream>>>((const char*)particles, stride_bytes, n, g->view, g->counter, g->cell_of, g->rank);
+                grid_hash_count_kernel<3><<<ceil_div(n, 256), 256, 0, ctx->stream>>>((const char*)particles, stride_bytes, n, opts.n_dev, g->view, g->counter, g->cell_of, g->rank);
             CWA_CUDA(cudaGetLastError());
         }
     }
@@ -377,11 +378,11 @@ int grid_build_internal(cwa_ctx* ctx, GridObj* g, const void* particles, int str
           if (ahead)
               grid_insert_ahead_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(opts.ahead_cell, opts.ahead_rank, g->index_list, g->offset, n, g->cell_of, g->arrival);
           else
-              grid_insert_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(g->cell_of, g->rank, g->offset, n, g->arrival); }
+              grid_insert_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(g->cell_of, g->rank, g->offset, n, opts.n_dev, g->arrival); }
         CWA_CUDA(cudaGetLastError());
         if (opts.canonical_order) {
             KScope k(ctx, KID_CELL_ORDER);
-            grid_cell_order_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(g->cell_of, g->offset, g->arrival, n, g->index_list);
+            grid_cell_order_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(g->cell_of, g->offset, g->arrival, n, opts.n_dev, g->index_list);
         }
         CWA_CUDA(cudaGetLastError());
     }

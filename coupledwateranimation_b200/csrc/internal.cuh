@@ -143,6 +143,7 @@ struct SphObj {
     bool live = false;
     cwa_buf particles = -1;
     int  n = 0;
+    const int* n_dev = nullptr;    // slab decomposition: the live count (owned + ghosts) is device-resident; `n` is then only the launch bound
     int  capacity = 0;             // particles the scratch arrays were sized for (cwa_sph_set_count limit)
     cwa_grid grid = -1;            // -1: all-pairs
     cwa_wave wave = -1;            // sampler binding
@@ -217,12 +218,23 @@ struct ShaderObj {
 // kernels of the hot path, as reported by the per-kernel profile (bench.py roofline section)
 enum KernelId {
     KID_CLEAR = 0, KID_HASH_COUNT, KID_SCAN, KID_INSERT, KID_CELL_ORDER, KID_REORDER,
-    KID_DENSITY, KID_FORCE, KID_INTEGRATE, KID_WAVE, KID_OTHER, KID_HEAVY, KID_COUNT
+    KID_DENSITY, KID_FORCE, KID_INTEGRATE, KID_WAVE, KID_OTHER, KID_HEAVY, KID_EXCHANGE, KID_COUNT
 };
 
 struct ProfRec { int id; cudaEvent_t a, b; };
 
+// Kernel-variant / staging knobs (cwa_set_tuning).  Per CONTEXT: two contexts of one host (two scene streams, two devices) can
+// hold different settings.  -1 = not set yet: the default comes from the environment (CWA_NB_CONFIG, ...) on first use.
+struct CtxTuning {
+    int config = -1, cap_d = -1, cap_f = -1, fused_order = -1, fused_integrate = -1, pipeline = -1, nbr_k = -1, extreme = -1;
+    int scan_config = -1, wave_transpose = -1, graph = -1;
+};
+
+struct SlabObj;
+
 struct cwa_ctx {
+    CtxTuning tune;
+    std::vector<SlabObj*> slabs;
     bool profiling = false;
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> ev_pool;
@@ -269,7 +281,6 @@ ParamPtrs  current_params(cwa_ctx* ctx);
 int  scan_exclusive_launch(cwa_ctx* ctx, const int* in, int* out, int n, int* ticket,
                            unsigned long long* tile_state);          // grid.cu; out has n+1 entries
 size_t scan_num_tiles(int n);
-int  scan_set_config(int v);                                           // tile shape of the look-back scan (0..3)
 struct GridBuildOpts {
     bool canonical_order = true;       // false: stop after the arrival-order insert (the caller's fused kernel ranks and reorders in one pass)
     // count-ahead: the counter already holds this build's counts; cell id and arrival rank of the particle that sat in
@@ -277,18 +288,22 @@ struct GridBuildOpts {
     const int* ahead_cell = nullptr;
     const int* ahead_rank = nullptr;
     bool clear_after_scan = false;     // the next build is counted ahead: clear counter + scan state right after this scan (side stream)
+    const int* n_dev = nullptr;        // device-resident particle count (slab decomposition): the host `n` is then only the launch bound
 };
 int  grid_build_internal(cwa_ctx* ctx, GridObj* g, const void* particles, int stride_bytes, int n, const GridBuildOpts& opts = GridBuildOpts());
 TexView wave_tex_view(cwa_ctx* ctx, cwa_wave w, int image);           // wave.cu
 int  wave_sampling_copy(cwa_ctx* ctx, cwa_wave w, int image, TexView* tex);   // points tex->tdata at the (refreshed) transposed copy when it pays
-int  wave_set_transpose(int on);
 int  stencil1d_dispatch_mode(cwa_ctx* ctx, int handle, int mode, int shader);   // stencil1d.cu: one dispatch, no PingPong
 void wave_touch_buffer(cwa_ctx* ctx, cwa_buf b, bool raw);             // a buffer was written through the Buffer API / its raw pointer handed out
 int  wave_step_internal(cwa_ctx* ctx, WaveObj* w);
+int  wave_image_with_unit(const WaveObj* w, int unit);                 // physical image bound to image unit 0 (newest) / 1 / 2 (next output)
 int  wave_dispatch_mode(cwa_ctx* ctx, WaveObj* w, int mode);           // kernel for uMode on units 0/1/2, no rotation                   // one EVOLVE dispatch + PingPong
 // slab pack fused into the integrate pass (multi.cu: cwa_sph_step_slab); all-zero = off
 struct SlabPackArgs {
     int n_owned = 0;
+    const int* n_owned_dev = nullptr;  // device-resident owned range (csrc/slab.cu); overrides n_owned
+    int* free_list = nullptr;          // slots freed by migrants (csrc/slab.cu): the next unpack reuses them, so the owned range does not grow
+    int* free_count = nullptr;
     float z_lo = 0.f, z_hi = 0.f, band = 0.f;
     float4* msg_l = nullptr;
     float4* msg_r = nullptr;
@@ -296,7 +311,21 @@ struct SlabPackArgs {
 };
 int  sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which /*bit0 rho, bit1 force, bit2 integrate*/, bool count_ahead = false,
                          const SlabPackArgs* slab = nullptr);
+void slab_destroy_all(cwa_ctx* ctx);                                  // slab.cu
 void sph_invalidate_for_buffer(cwa_ctx* ctx, cwa_buf particles);       // the particle buffer was written behind the SPH object's back
+
+// Every entry point runs against ITS context's device, whatever device the calling thread had current (a host may hold contexts
+// on several devices: the multi-GPU slab group of csrc/slab.cu does); the previous device is restored on return.
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(const cwa_ctx* ctx)
+    {
+        if (!ctx) return;
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != ctx->device) { cudaSetDevice(ctx->device); prev = cur; }
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 

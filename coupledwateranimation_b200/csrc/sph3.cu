@@ -990,7 +990,7 @@ sph3_finalize_integrate_sorted_kernel(const float4* __restrict__ pack,
         float4* o = aos + (size_t)id * 4;                          // 64-byte record = two 256-bit stores (two full sectors)
         const float4 ex = make_float4(rho, prs, m.z, m.w);
         float4 pos_out = pos;
-        if (MODE == 2 && id < sp.n_owned) {
+        if (MODE == 2 && id < (sp.n_owned_dev != nullptr ? __ldg(sp.n_owned_dev) : sp.n_owned)) {
             const float z = pos.z;                                 // NaN z: every test below is false -> stays
             float4* msg = nullptr;
             bool migrate = false;
@@ -1006,7 +1006,10 @@ sph3_finalize_integrate_sorted_kernel(const float4* __restrict__ pack,
                     float4* d = msg + 4 * (size_t)(1 + (migrate ? 0 : sp.cap_mig) + mslot);
                     cwa_stg256(d, pos, vel);
                     cwa_stg256(d + 2, f, ex);
-                    if (migrate) pos_out = make_float4(__int_as_float(0x7fffffff), __int_as_float(0x7fffffff), __int_as_float(0x7fffffff), CWA_DEAD_W_SPH);
+                    if (migrate) {
+                        pos_out = make_float4(__int_as_float(0x7fffffff), __int_as_float(0x7fffffff), __int_as_float(0x7fffffff), CWA_DEAD_W_SPH);
+                        if (sp.free_list != nullptr) sp.free_list[atomicAdd(sp.free_count, 1)] = id;   // the slot is reused by the next unpack
+                    }
                 }
             }
         }
@@ -1275,34 +1278,33 @@ static int env_int(const char* name, int dflt, int lo, int hi)
 constexpr int NB_CONFIG_DEFAULT = 7;
 constexpr int NBR_K_DEFAULT = 64;         // neighbour-list entries per target (self included); longer lists fall back to a grid scan
 constexpr int NBR_K_MAX = 256;
-struct NbTuning { int config = -1, cap_d = -1, cap_f = -1, fused_order = -1, fused_integrate = -1, pipeline = -1, nbr_k = -1, extreme = -1; };
-static NbTuning g_tune;
-static int nb_config() { if (g_tune.config < 0) g_tune.config = env_int("CWA_NB_CONFIG", NB_CONFIG_DEFAULT, 0, 7); return g_tune.config; }
-static int dens_cap() { if (g_tune.cap_d < 0) g_tune.cap_d = env_int("CWA_NB_CAP_D", DENS_CAP_DEFAULT, 0, DENS_CAP_MAX); return g_tune.cap_d; }
-static int force_cap() { if (g_tune.cap_f < 0) g_tune.cap_f = env_int("CWA_NB_CAP_F", FORCE_CAP_DEFAULT, 0, FORCE_CAP_MAX); return g_tune.cap_f; }
-static bool fused_integrate() { if (g_tune.fused_integrate < 0) g_tune.fused_integrate = env_int("CWA_FUSED_INTEGRATE", 0, 0, 1); return g_tune.fused_integrate != 0; }
+static int nb_config(cwa_ctx* c) { if (c->tune.config < 0) c->tune.config = env_int("CWA_NB_CONFIG", NB_CONFIG_DEFAULT, 0, 7); return c->tune.config; }
+static int dens_cap(cwa_ctx* c) { if (c->tune.cap_d < 0) c->tune.cap_d = env_int("CWA_NB_CAP_D", DENS_CAP_DEFAULT, 0, DENS_CAP_MAX); return c->tune.cap_d; }
+static int force_cap(cwa_ctx* c) { if (c->tune.cap_f < 0) c->tune.cap_f = env_int("CWA_NB_CAP_F", FORCE_CAP_DEFAULT, 0, FORCE_CAP_MAX); return c->tune.cap_f; }
+static bool fused_integrate(cwa_ctx* c) { if (c->tune.fused_integrate < 0) c->tune.fused_integrate = env_int("CWA_FUSED_INTEGRATE", 0, 0, 1); return c->tune.fused_integrate != 0; }
 // pipeline (cwa_coupled_step with several frames per call): bit 0 = the wave stencil of frame f runs on a side stream next to the
 // grid build of frame f+1; bit 1 = count-ahead (integrate of frame f does the cell hash + count of frame f+1)
-static int pipeline_mode() { if (g_tune.pipeline < 0) g_tune.pipeline = env_int("CWA_PIPELINE", 3, 0, 3); return g_tune.pipeline; }
+static int pipeline_mode(cwa_ctx* c) { if (c->tune.pipeline < 0) c->tune.pipeline = env_int("CWA_PIPELINE", 3, 0, 3); return c->tune.pipeline; }
 // nbr_k: list capacity per target (multiple of 4, <= 256); extreme: candidate count above which the density pass hands a target to a whole warp
-static int nbr_k() { if (g_tune.nbr_k < 0) g_tune.nbr_k = env_int("CWA_NBR_K", NBR_K_DEFAULT, 8, NBR_K_MAX) & ~3; return g_tune.nbr_k; }
-static int extreme_candidates() { if (g_tune.extreme < 0) g_tune.extreme = env_int("CWA_EXTREME", EXTREME_CANDIDATES, 16, 1 << 20); return g_tune.extreme; }
-static bool fused_order() { if (g_tune.fused_order < 0) g_tune.fused_order = env_int("CWA_FUSED_ORDER", 1, 0, 1); return g_tune.fused_order != 0; }
+static int nbr_k(cwa_ctx* c) { if (c->tune.nbr_k < 0) c->tune.nbr_k = env_int("CWA_NBR_K", NBR_K_DEFAULT, 8, NBR_K_MAX) & ~3; return c->tune.nbr_k; }
+static int extreme_candidates(cwa_ctx* c) { if (c->tune.extreme < 0) c->tune.extreme = env_int("CWA_EXTREME", EXTREME_CANDIDATES, 16, 1 << 20); return c->tune.extreme; }
+static bool fused_order(cwa_ctx* c) { if (c->tune.fused_order < 0) c->tune.fused_order = env_int("CWA_FUSED_ORDER", 1, 0, 1); return c->tune.fused_order != 0; }
 
 extern "C" int cwa_set_tuning(cwa_ctx* ctx, const char* key, int value)
 {
     CWA_CHECK(ctx && key, "null argument");
     const std::string k(key);
-    if (k == "nb_config") { CWA_CHECK(value >= 0 && value <= 7, "nb_config %d out of range", value); g_tune.config = value; }
-    else if (k == "nb_cap_d") { CWA_CHECK(value >= 0 && value <= DENS_CAP_MAX, "nb_cap_d %d out of range", value); g_tune.cap_d = value; }
-    else if (k == "nb_cap_f") { CWA_CHECK(value >= 0 && value <= FORCE_CAP_MAX, "nb_cap_f %d out of range", value); g_tune.cap_f = value; }
-    else if (k == "fused_order") { g_tune.fused_order = value ? 1 : 0; }
-    else if (k == "fused_integrate") { g_tune.fused_integrate = value ? 1 : 0; }
-    else if (k == "nbr_k") { CWA_CHECK(value >= 8 && value <= NBR_K_MAX && value % 4 == 0, "nbr_k %d: multiple of 4 in [8, %d]", value, NBR_K_MAX); g_tune.nbr_k = value; }
-    else if (k == "extreme_candidates") { CWA_CHECK(value >= 16, "extreme_candidates %d too small", value); g_tune.extreme = value; }
-    else if (k == "wave_transpose") { wave_set_transpose(value); }
-    else if (k == "scan_config") { CWA_CHECK(scan_set_config(value) == 0, "scan_config %d out of range", value); }
-    else if (k == "pipeline") { CWA_CHECK(value >= 0 && value <= 3, "pipeline %d out of range", value); g_tune.pipeline = value; }
+    if (k == "nb_config") { CWA_CHECK(value >= 0 && value <= 7, "nb_config %d out of range", value); ctx->tune.config = value; }
+    else if (k == "nb_cap_d") { CWA_CHECK(value >= 0 && value <= DENS_CAP_MAX, "nb_cap_d %d out of range", value); ctx->tune.cap_d = value; }
+    else if (k == "nb_cap_f") { CWA_CHECK(value >= 0 && value <= FORCE_CAP_MAX, "nb_cap_f %d out of range", value); ctx->tune.cap_f = value; }
+    else if (k == "fused_order") { ctx->tune.fused_order = value ? 1 : 0; }
+    else if (k == "fused_integrate") { ctx->tune.fused_integrate = value ? 1 : 0; }
+    else if (k == "nbr_k") { CWA_CHECK(value >= 8 && value <= NBR_K_MAX && value % 4 == 0, "nbr_k %d: multiple of 4 in [8, %d]", value, NBR_K_MAX); ctx->tune.nbr_k = value; }
+    else if (k == "extreme_candidates") { CWA_CHECK(value >= 16, "extreme_candidates %d too small", value); ctx->tune.extreme = value; }
+    else if (k == "wave_transpose") { ctx->tune.wave_transpose = value ? 1 : 0; }
+    else if (k == "scan_config") { CWA_CHECK(value >= 0 && value <= 3, "scan_config %d out of range", value); ctx->tune.scan_config = value; }
+    else if (k == "graph") { ctx->tune.graph = value ? 1 : 0; }
+    else if (k == "pipeline") { CWA_CHECK(value >= 0 && value <= 3, "pipeline %d out of range", value); ctx->tune.pipeline = value; }
     else CWA_CHECK(false, "cwa_set_tuning: unknown key '%s'", key);
     return 0;
 }
@@ -1312,8 +1314,8 @@ static int launch_density(cwa_ctx* ctx, SphObj* s, GridObj* g, TexView tex)
 {
     CWA_TRY(ensure_dynamic_smem(ctx, sph3_density_grid_kernel<P, L>, DENS_CAP_MAX * 16));
     KScope k(ctx, KID_DENSITY);
-    sph3_density_grid_kernel<P, L><<<ceil_div(s->n, P), P * L, dens_cap() * 16, ctx->stream>>>(
-        s->posS, s->velS, s->pack, s->n, g->view, g->offset, (const Sph3Const*)s->consts, tex, dens_cap());
+    sph3_density_grid_kernel<P, L><<<ceil_div(s->n, P), P * L, dens_cap(ctx) * 16, ctx->stream>>>(
+        s->posS, s->velS, s->pack, s->n, g->view, g->offset, (const Sph3Const*)s->consts, tex, dens_cap(ctx));
     return 0;
 }
 
@@ -1322,8 +1324,8 @@ static int launch_force(cwa_ctx* ctx, SphObj* s, GridObj* g)
 {
     CWA_TRY(ensure_dynamic_smem(ctx, sph3_force_grid_kernel<P, L>, FORCE_CAP_MAX * 32));
     KScope k(ctx, KID_FORCE);
-    sph3_force_grid_kernel<P, L><<<ceil_div(s->n, P), P * L, force_cap() * 32, ctx->stream>>>(
-        s->pack, s->pairP, s->pairV, s->n, g->view, g->offset, (const Sph3Const*)s->consts, force_cap());
+    sph3_force_grid_kernel<P, L><<<ceil_div(s->n, P), P * L, force_cap(ctx) * 32, ctx->stream>>>(
+        s->pack, s->pairP, s->pairV, s->n, g->view, g->offset, (const Sph3Const*)s->consts, force_cap(ctx));
     return 0;
 }
 
@@ -1338,7 +1340,7 @@ static int launch_density_list(cwa_ctx* ctx, SphObj* s, GridObj* g, TexView tex)
     const int ntiles = ceil_div(s->n, TILE_P);
     const bool local = tex_view_is_local(tex);
     int* const hc = s->heavy_cnt;                        // queue counter, zeroed by the reorder pass of this snapshot
-    const int K = nbr_k();
+    const int K = nbr_k(ctx);
     if (s->nbr_k_alloc < K) {                            // the list capacity was raised after the object was created
         CWA_CUDA(cudaStreamSynchronize(ctx->stream));
         cudaFree(s->nbr_list);
@@ -1349,10 +1351,10 @@ static int launch_density_list(cwa_ctx* ctx, SphObj* s, GridObj* g, TexView tex)
     { KScope k(ctx, KID_DENSITY);
       if (local)
           sph3_density_list_kernel<true><<<ntiles, TILE_P, 0, ctx->stream>>>(
-              s->posS, s->velS, s->pack, s->nbr_list, s->nbr_count, s->heavy_queue, hc, s->n, g->view, g->offset, cc, tex, K, extreme_candidates());
+              s->posS, s->velS, s->pack, s->nbr_list, s->nbr_count, s->heavy_queue, hc, s->n, g->view, g->offset, cc, tex, K, extreme_candidates(ctx));
       else
           sph3_density_list_kernel<false><<<ntiles, TILE_P, 0, ctx->stream>>>(
-              s->posS, s->velS, s->pack, s->nbr_list, s->nbr_count, s->heavy_queue, hc, s->n, g->view, g->offset, cc, tex, K, extreme_candidates()); }
+              s->posS, s->velS, s->pack, s->nbr_list, s->nbr_count, s->heavy_queue, hc, s->n, g->view, g->offset, cc, tex, K, extreme_candidates(ctx)); }
     { KScope k(ctx, KID_HEAVY);
       if (local)
           sph3_density_heavy_kernel<true><<<heavy_grid(ctx), 128, 0, ctx->stream>>>(
@@ -1391,12 +1393,13 @@ static int sph_snapshot(cwa_ctx* ctx, SphObj* s, bool count_next_ahead = false)
     BufferObj* pb = get_buffer(ctx, s->particles);
     CWA_CHECK(g && pb, "sph: grid or particle buffer vanished");
     GridBuildOpts opts;
-    opts.canonical_order = !fused_order();
+    opts.canonical_order = !fused_order(ctx);
     if (s->counts_ahead) { opts.ahead_cell = s->cell_next; opts.ahead_rank = s->rank_next; }
     opts.clear_after_scan = count_next_ahead;
+    opts.n_dev = s->n_dev;
     s->counts_ahead = false;
     CWA_TRY(grid_build_internal(ctx, g, pb->ptr, 64, s->n, opts));
-    if (fused_order()) {
+    if (fused_order(ctx)) {
         KScope k(ctx, KID_REORDER);
         sph3_order_reorder_kernel<<<ceil_div(s->n > 0 ? s->n : 1, 256), 256, 0, ctx->stream>>>(
             (const float4*)pb->ptr, g->arrival, g->cell_of, g->offset, g->offset + g->view.num_cells, g->index_list,
@@ -1480,8 +1483,8 @@ int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which, bool co
     GridObj* g = get_grid(ctx, s->grid);
     CWA_CHECK(g && g->dim == 3, "sph: the bound grid must be a 3-D grid");
     const bool full = (which == 7);
-    const int cfg = nb_config();
-    const bool fused_tail = full && cfg == 7 && fused_integrate();   // the force kernels finish the particle (epilogue + integrate + write-back)
+    const int cfg = nb_config(ctx);
+    const bool fused_tail = full && cfg == 7 && fused_integrate(ctx);   // the force kernels finish the particle (epilogue + integrate + write-back)
     count_ahead = count_ahead && full && !fused_tail && slab == nullptr;
     CWA_CHECK(slab == nullptr || (full && !fused_tail), "slab pack: needs a full step with the separate integrate kernel (fused_integrate = 0)");
     if (!(which & 1)) CWA_TRY(wave_sampling_copy(ctx, s->wave, s->wave_image, &tex));
@@ -1581,7 +1584,7 @@ extern "C" int cwa_sph_create(cwa_ctx* ctx, cwa_buf particles, int n, cwa_grid g
         CWA_CUDA(cudaMalloc(&s.miscS, bytes));
         CWA_CUDA(cudaMalloc(&s.pairP, bytes));
         CWA_CUDA(cudaMalloc(&s.pairV, bytes / 2));
-        s.nbr_k_alloc = nbr_k();
+        s.nbr_k_alloc = nbr_k(ctx);
         CWA_CUDA(cudaMalloc(&s.nbr_list, (size_t)(n > 0 ? n : 1) * s.nbr_k_alloc * 4));
         CWA_CUDA(cudaMalloc(&s.nbr_count, (size_t)(n > 0 ? n : 1) * 4));
         CWA_CUDA(cudaMalloc(&s.heavy_queue, (size_t)(n > 0 ? n : 1) * 2 * 4));
@@ -1708,7 +1711,7 @@ extern "C" int cwa_coupled_step(cwa_ctx* ctx, cwa_sph hs, cwa_wave hw, int nfram
     // grid build of frame f+1 -- runs on a side stream and the first sampling kernel of frame f+1 waits for it, and (b) the
     // integrate pass of frame f counts the particles into the cells of frame f+1 (count-ahead).  The last frame of the call runs the
     // plain sequence, so every array an application can read afterwards is in the state the sequential code leaves.
-    const int pipe = (nframes > 1) ? pipeline_mode() : 0;
+    const int pipe = (nframes > 1) ? pipeline_mode(ctx) : 0;
     bool wave_in_flight = false;
     s->counts_ahead = false;
     // whichever way the call ends (an error included): the main stream is behind everything a side stream was given, and no

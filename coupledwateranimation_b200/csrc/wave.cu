@@ -287,13 +287,11 @@ wave_transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int
 // ---------------------------------------------------------------------------------------------
 // host object
 // ---------------------------------------------------------------------------------------------
-static int g_wave_transpose = -1;
-static bool wave_transpose_on()
+static bool wave_transpose_on(cwa_ctx* ctx)
 {
-    if (g_wave_transpose < 0) { const char* e = getenv("CWA_WAVE_TRANSPOSE"); g_wave_transpose = e ? (atoi(e) != 0) : 1; }
-    return g_wave_transpose != 0;
+    if (ctx->tune.wave_transpose < 0) { const char* e = getenv("CWA_WAVE_TRANSPOSE"); ctx->tune.wave_transpose = e ? (atoi(e) != 0) : 1; }
+    return ctx->tune.wave_transpose != 0;
 }
-int wave_set_transpose(int on) { g_wave_transpose = on ? 1 : 0; return 0; }
 
 void wave_touch_buffer(cwa_ctx* ctx, cwa_buf b, bool raw)
 {
@@ -310,7 +308,7 @@ void wave_touch_buffer(cwa_ctx* ctx, cwa_buf b, bool raw)
 int wave_sampling_copy(cwa_ctx* ctx, cwa_wave h, int image, TexView* tex)
 {
     WaveObj* w = get_wave(ctx, h);
-    if (!w || image < 0 || image >= 3 || !wave_transpose_on() || (w->raw_exposed && !w->explicit_touch)) return 0;
+    if (!w || image < 0 || image >= 3 || !wave_transpose_on(ctx) || (w->raw_exposed && !w->explicit_touch)) return 0;
     // any scalar view (whole field or row block) that is 32-bit indexable and large enough for the access pattern to matter
     if (tex->ch != 1 || tex->data != w->image[image] || (long long)w->w * w->h < 256 * 256 || (long long)w->w * w->h >= (1ll << 30)) return 0;
     if (w->imageT == nullptr) CWA_CUDA(cudaMalloc(&w->imageT, (size_t)w->w * w->h * 4));
@@ -324,6 +322,7 @@ int wave_sampling_copy(cwa_ctx* ctx, cwa_wave h, int image, TexView* tex)
     return 0;
 }
 
+int wave_image_with_unit(const WaveObj* w, int u) { for (int i = 0; i < 3; i++) if (w->unit[i] == u) return i; return -1; }
 static int image_with_unit(const WaveObj* w, int u)
 {
     for (int i = 0; i < 3; i++) if (w->unit[i] == u) return i;

@@ -1,4 +1,12 @@
-"""Multi-GPU coupled step: one process per GPU over torch.distributed.
+"""Multi-GPU coupled step.
+
+The product path is `SlabRank`: a thin ctypes front of the C-ABI slab object (csrc/slab.cu) -- peer stores into the neighbours'
+mailboxes over NVLink, device-side arrival flags, device-resident particle counts; no host synchronisation and no collective
+library on the per-frame path.  torch.distributed is only used ONCE, at set-up, to hand the 64-byte IPC handles of the mailboxes
+to the other processes (`connect_processes`).
+
+`SlabPlan` / `DistributedCoupled` below are the host-side statement of the same decomposition, kept as the protocol the CPU tests
+(world_size 2 / 3 over gloo, oracle as the compute backend) check: "N ranks reproduce the 1-rank state".
 
 Decomposition
     particles  -- slabs in z.  Rank r owns z in [z_lo, z_hi); the slab faces are the images of its
@@ -232,149 +240,117 @@ class DistributedCoupled:
 
 
 # ====================================================================================================
-# backend: the CUDA library
+# the CUDA library: one rank of the slab decomposition through the C ABI (csrc/slab.cu)
 # ====================================================================================================
-class _DevPtr:
-    """Expose a raw device pointer to torch through __cuda_array_interface__ (no copy)."""
+def plan_desc(lib, world: int, rank: int, wave_w: int, wave_h: int, wave_ch: int, uv_scale_z: float, h: float, row_bounds=None,
+              cap_mig: int = 16384, cap_ghost: int = 65536, capacity: int = 0, timeout_ms: int = 10000):
+    """cwa_slab_plan: the row block / z slab of `rank` as the library plans it (same rule as SlabPlan.make)."""
+    import ctypes as C
+    from . import _capi
+    d = _capi.SlabDesc()
+    rb = (C.c_int * (world + 1))(*[int(v) for v in row_bounds]) if row_bounds is not None else None
+    _capi.check(lib.cwa_slab_plan(world, rank, wave_w, wave_h, wave_ch, float(uv_scale_z), float(h), rb, C.byref(d)))
+    d.cap_mig, d.cap_ghost, d.capacity, d.timeout_ms = int(cap_mig), int(cap_ghost), int(capacity), int(timeout_ms)
+    return d
 
-    def __init__(self, ptr: int, nbytes: int):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
 
+class SlabRank:
+    """Per-rank library objects of the slab-decomposed coupled frame: particle SSBO (owned + ghosts), slab-local uniform grid,
+    row-block wave object and the cwa_slab object that steps them."""
 
-class CudaBackend:
-    """Owns the per-rank library objects: particle SSBO (owned + ghosts), grid, row-block wave object."""
+    def __init__(self, cwa, ctx, desc, grid_min, grid_max, grid_cells):
+        import ctypes as C
+        self.cwa, self.ctx, self.desc = cwa, ctx, desc
+        self.capacity = desc.capacity
+        self.buffer = cwa.Buffer(ctx, nbytes=desc.capacity * PARTICLE_BYTES)
+        self.grid = cwa.UniformGrid(ctx, 3, grid_min, grid_max, grid_cells, desc.capacity, compact_index=True)
+        self.sph = cwa.Sph(ctx, desc.capacity, self.grid, buffer=self.buffer)
+        self.wave = cwa.StencilImage2DTripleBuffered.create_block(ctx, desc.wave_w, desc.wave_h, desc.store_lo, desc.store_hi - desc.store_lo, desc.wave_ch)
+        h = C.c_int(-1)
+        cwa.check(ctx.lib.cwa_slab_create(ctx.h, C.byref(desc), self.sph.h, self.wave.h, C.byref(h)))
+        self.h = h.value
 
-    def __init__(self, cwa, ctx, plan: SlabPlan, capacity: int, grid_min, grid_max, grid_cells, wave_ch=1,
-                 cap_mig: int = 16384, cap_ghost: int = 65536):
-        import torch
-        self.torch = torch
-        self.cwa, self.ctx, self.plan = cwa, ctx, plan
-        self.device = torch.device("cuda", ctx.device)
-        self.capacity = capacity
-        self._views = {}
-        self.cap_mig, self.cap_ghost = cap_mig, cap_ghost
-        self.buffer = cwa.Buffer(ctx, nbytes=capacity * PARTICLE_BYTES)
-        self.grid = cwa.UniformGrid(ctx, 3, grid_min, grid_max, grid_cells, capacity, compact_index=True)
-        self.sph = cwa.Sph(ctx, capacity, self.grid, buffer=self.buffer)
-        msg_bytes = (1 + cap_mig + cap_ghost) * PARTICLE_BYTES
-        self.msg = {k: cwa.Buffer(ctx, nbytes=msg_bytes) for k in ("sl", "sr", "rl", "rr")}
-        self.msg_t = {k: self._tensor(v, 0, msg_bytes) for k, v in self.msg.items()}
-        self.scratch = None                       # allocated on the first compaction
-        self.wave = cwa.StencilImage2DTripleBuffered.create_block(ctx, plan.wave_w, plan.wave_h, plan.store_lo, plan.rows_stored, wave_ch)
-        self.wave_ch = wave_ch
-        self.n_owned = 0                          # owned RANGE (may contain dead slots)
-        self.n_ghost = 0
-        self.migrated_in = 0
-        self._stream = torch.cuda.ExternalStream(ctx.stream, device=self.device)
-        import os
-        self.fused_pack = os.environ.get("CWA_FUSED_PACK", "1") != "0"   # integrate packs the next exchange's messages (cwa_sph_step_slab)
+    # ---- wiring -----------------------------------------------------------------------------------
+    def export(self) -> bytes:
+        import ctypes as C
+        buf = (C.c_ubyte * 64)()
+        self.cwa.check(self.ctx.lib.cwa_slab_export(self.ctx.h, self.h, buf))
+        return bytes(buf)
 
-    def _tensor(self, buf, offset_bytes: int, nbytes: int):
-        if nbytes == 0:
-            return self.torch.empty(0, dtype=self.torch.uint8, device=self.device)
-        key = (buf.h, offset_bytes, nbytes)
-        t = self._views.get(key)
-        if t is None:                             # views of library-owned memory; built once, reused every frame
-            t = self._views[key] = self.torch.as_tensor(_DevPtr(buf.device_ptr() + offset_bytes, nbytes), device=self.device)
-        return t
+    def mailbox(self):
+        import ctypes as C
+        p, n = C.c_void_p(), C.c_size_t()
+        self.cwa.check(self.ctx.lib.cwa_slab_mailbox(self.ctx.h, self.h, C.byref(p), C.byref(n)))
+        return int(p.value or 0), int(n.value)
 
-    def comm_stream(self):
-        """torch collectives issued inside are ordered behind / ahead of the library's kernels on ITS stream."""
-        return self.torch.cuda.stream(self._stream)
+    def connect(self, peer_rank: int, handle: bytes | None = None, ptr: int | None = None):
+        import ctypes as C
+        hb = (C.c_ubyte * 64)(*handle) if handle is not None else None
+        self.cwa.check(self.ctx.lib.cwa_slab_connect(self.ctx.h, self.h, peer_rank, hb, C.c_void_p(ptr) if ptr else None))
 
-    # ---- particles ------------------------------------------------------------------------------
+    # ---- state ------------------------------------------------------------------------------------
     def upload_owned(self, particles: np.ndarray):
         assert particles.size <= self.capacity
         if particles.size:
             self.buffer.sub_data(particles)
-        self.n_owned, self.n_ghost = particles.size, 0
+        self.cwa.check(self.ctx.lib.cwa_slab_set_owned(self.ctx.h, self.h, int(particles.size)))
+
+    def counts(self) -> dict:
+        import ctypes as C
+        c = (C.c_int * 8)()
+        self.cwa.check(self.ctx.lib.cwa_slab_counts(self.ctx.h, self.h, c))
+        return {"n_owned": c[0], "n_total": c[1], "n_ghost": c[1] - c[0], "free": c[2], "err": c[3],
+                "migrated_in": (c[4] & 0xffffffff) | (c[5] << 32), "particle_msgs": c[6], "wave_msgs": c[7]}
 
     def download_owned(self) -> np.ndarray:
-        p = self.buffer.read(self.cwa.PARTICLE, self.n_owned)
+        n = self.counts()["n_owned"]
+        p = self.buffer.read(self.cwa.PARTICLE, n)
         dead = (p["pos"][:, 3] == np.float32(DEAD_W)) & np.isnan(p["pos"][:, 0])
         return p[~dead]
 
-    def no_exchange(self):
-        self.n_ghost = 0
-
-    def _maybe_compact(self):
-        reserve = 2 * (2 * self.cap_mig + self.cap_ghost)
-        if self.n_owned + reserve <= self.capacity:
-            return
-        import ctypes as C
-        if self.scratch is None:
-            self.scratch = self.cwa.Buffer(self.ctx, nbytes=self.capacity * PARTICLE_BYTES)
-        n = C.c_int()
-        self.cwa.check(self.ctx.lib.cwa_slab_compact(self.ctx.h, self.buffer.h, self.n_owned, self.scratch.h, C.byref(n)))
-        self.n_owned = n.value
-        assert self.n_owned + reserve <= self.capacity, f"rank {self.plan.rank}: particle capacity {self.capacity} exhausted"
-
-    def pack(self, z_lo, z_hi, band, has_left, has_right):
-        self._maybe_compact()
-        f = lambda v: max(min(v, 3.0e38), -3.0e38)
-        self.cwa.check(self.ctx.lib.cwa_slab_pack(self.ctx.h, self.buffer.h, self.n_owned, f(z_lo), f(z_hi), band,
-                                                  self.msg["sl"].h if has_left else -1, self.msg["sr"].h if has_right else -1,
-                                                  self.cap_mig, self.cap_ghost))
-        return (self.msg_t["sl"] if has_left else None, self.msg_t["sr"] if has_right else None)
-
-    def recv_buffers(self, has_left, has_right):
-        return (self.msg_t["rl"] if has_left else None, self.msg_t["rr"] if has_right else None)
-
-    def unpack(self, has_left, has_right):
-        import ctypes as C
-        counts = (C.c_int * 4)()
-        self.cwa.check(self.ctx.lib.cwa_slab_unpack(self.ctx.h, self.buffer.h, self.n_owned, self.msg["rl"].h if has_left else -1,
-                                                    self.msg["rr"].h if has_right else -1, self.msg["sl"].h if has_left else -1,
-                                                    self.msg["sr"].h if has_right else -1, self.cap_mig, self.cap_ghost, counts))
-        if counts[2]:
-            hdrs = {k: self.msg[k].read(np.int32, 4).tolist() for k in ("sl", "sr", "rl", "rr")}
-            raise RuntimeError(f"rank {self.plan.rank}: exchange overflow (flags {counts[2]}, counts {list(counts)}, n_owned {self.n_owned}, "
-                               f"capacity {self.capacity}, caps {self.cap_mig}/{self.cap_ghost}, headers {hdrs}): raise cap_mig/cap_ghost/capacity")
-        self.n_ghost = counts[1] - counts[0]
-        self.n_owned = counts[0]
-        self.migrated_in += counts[3]
+    def owned_wave_rows(self, role: int = 0) -> np.ndarray:
+        d = self.desc
+        return self.wave.read_role(role)[d.row_lo - d.store_lo:d.row_hi - d.store_lo]
 
     # ---- simulation -------------------------------------------------------------------------------
-    def sph_step(self, image: int, pack_next: bool = False):
-        n = self.n_owned + self.n_ghost
-        self.cwa.check(self.ctx.lib.cwa_sph_set_count(self.ctx.h, self.sph.h, n))
-        self.sph.bind_wave(self.wave if image >= 0 else None, image)
-        p = self.plan
-        if p.world > 1 and self.fused_pack and pack_next:
-            # the integrate pass packs the migrant / ghost messages of the NEXT exchange (pack() then finds its work done)
-            f = lambda v: max(min(v, 3.0e38), -3.0e38)
-            self.cwa.check(self.ctx.lib.cwa_sph_step_slab(self.ctx.h, self.sph.h, self.n_owned, f(p.z_lo), f(p.z_hi), p.ghost_width,
-                                                          self.msg["sl"].h if p.has_left else -1, self.msg["sr"].h if p.has_right else -1,
-                                                          self.cap_mig, self.cap_ghost))
-        else:
-            self.sph.step(1)
+    def step(self, nframes: int = 1, coupling: int = COUPLING_AS_SHIPPED):
+        self.cwa.check(self.ctx.lib.cwa_slab_step(self.ctx.h, self.h, nframes, coupling))
 
-    def wave_step(self):
-        self.wave.Compute(1)
+    def check(self):
+        """Raise when the device-side protocol reported an error (message overflow, capacity, a peer that never answered)."""
+        c = self.counts()
+        if c["err"]:
+            names = [n for b, n in ((1, "a sender overflowed its message (raise cap_mig / cap_ghost)"), (2, "particle capacity exceeded"),
+                                    (4, "timeout waiting for a neighbour's particles"), (8, "timeout waiting for a neighbour's wave rows")) if c["err"] & b]
+            raise RuntimeError(f"rank {self.desc.rank}: slab exchange error bits {c['err']}: " + "; ".join(names) + f" ({c})")
+        return c
 
-    def bind_texture_unit(self):
-        self.wave.bind_texture_unit()
 
-    def newest_image(self) -> int:
-        return self.wave.role_image(0)
+def connect_local(ranks):
+    """Ranks that are contexts of THIS process (any mix of devices): hand every rank the others' mailbox pointers."""
+    for a in ranks:
+        for b in ranks:
+            if a is not b:
+                a.connect(b.desc.rank, ptr=b.mailbox()[0])
 
-    def wave_written(self, image: int):
-        """Rows of `image` were written through its raw device pointer (NCCL receive): derived copies are stale."""
-        self.cwa.check(self.ctx.lib.cwa_wave_mark_written(self.ctx.h, self.wave.h, image))
 
-    def tex_unit0(self) -> int:
-        return self.wave.state()["tex_unit0"]
+def group_step(ranks, nframes: int = 1, coupling: int = COUPLING_AS_SHIPPED):
+    """cwa_slab_group_step: all ranks of one process stepped by one host thread."""
+    import ctypes as C
+    n = len(ranks)
+    ctxs = (C.c_void_p * n)(*[r.ctx.h for r in ranks])
+    slabs = (C.c_int * n)(*[r.h for r in ranks])
+    ranks[0].cwa.check(ranks[0].ctx.lib.cwa_slab_group_step(ctxs, slabs, n, nframes, coupling))
 
-    def wave_rows(self, image: int, global_row: int, nrows: int):
-        row_bytes = self.plan.wave_w * self.wave_ch * 4
-        off = (global_row - self.plan.store_lo) * row_bytes
-        return self._tensor(self.wave.image_buffer(image), off, nrows * row_bytes)
 
-    def last_row(self, image: int):
-        return self._tensor(self.wave.last_row_buffer(image), 0, self.plan.wave_w * self.wave_ch * 4)
-
-    def copy_own_last_row(self, image: int):
-        row_bytes = self.plan.wave_w * self.wave_ch * 4
-        src, dst = self.wave.image_buffer(image), self.wave.last_row_buffer(image)
-        off = (self.plan.wave_h - 1 - self.plan.store_lo) * row_bytes
-        self.cwa.check(self.ctx.lib.cwa_buffer_copy(self.ctx.h, src.h, dst.h, off, 0, row_bytes))
+def connect_processes(rank_obj: SlabRank, dist):
+    """One process per GPU: exchange the mailboxes' IPC handles once (torch.distributed is plumbing here, nothing per frame)."""
+    world = rank_obj.desc.world
+    if world == 1:
+        return
+    handles = [None] * world
+    dist.all_gather_object(handles, rank_obj.export())
+    for r, hnd in enumerate(handles):
+        if r != rank_obj.desc.rank:
+            rank_obj.connect(r, handle=hnd)
+    dist.barrier()

@@ -217,6 +217,47 @@ CWA_API int cwa_wave_create_block(cwa_ctx* ctx, int w, int h_global, int row0, i
 /* replicated copy of the GLOBAL last row of physical image `image` (WaveNormal's uv+(0,1) tap clamps to it) */
 CWA_API int cwa_wave_last_row_buffer(cwa_ctx* ctx, cwa_wave w, int image, cwa_buf* out);
 
+/* ---- the slab-decomposed coupled frame behind the C ABI (csrc/slab.cu; SURVEY 8e / 8b: cwa_create(device, n_devices)) --------
+ * N ranks reproduce the single-GPU idle() of Main.cpp:540-561 (+ the display() bind :413).  A rank = one context + one cwa_slab
+ * object; ranks are processes (one per GPU: exchange the 64-byte handles of cwa_slab_export and cwa_slab_connect them) or contexts
+ * of ONE process on one or several devices (cwa_slab_mailbox + cwa_slab_connect(direct pointer), stepped with cwa_slab_group_step).
+ * Per frame there is no host synchronisation, no collective library call and no size negotiation: messages travel by peer
+ * stores into the neighbour's mailbox, arrival is a device-side flag, particle counts live on the device. */
+typedef int cwa_slab;
+typedef struct {
+    int   rank, world;
+    int   wave_w, wave_h, wave_ch;   /* the GLOBAL height field */
+    int   row_lo, row_hi;            /* owned rows */
+    int   store_lo, store_hi;        /* stored rows = owned + sampling halos (what cwa_wave_create_block is given) */
+    int   left_store_hi;             /* rows [row_lo, left_store_hi) are the left neighbour's upper halo */
+    int   right_store_lo;            /* rows [right_store_lo, row_hi) are the right neighbour's lower halo */
+    int   halo_rows_max;             /* sizes the wave mailboxes identically on every rank */
+    float z_lo, z_hi, band;          /* owned particles: z_lo <= z < z_hi; ghost layer `band` (2h) on either side of a face */
+    int   cap_mig, cap_ghost;        /* message capacities in particles (identical on every rank) */
+    int   capacity;                  /* particle records the SSBO holds: owned + ghosts + arrivals */
+    int   timeout_ms;                /* a wait for a peer that lasts longer raises an error bit instead of hanging (default 10000) */
+} cwa_slab_desc;
+/* row blocks / z slabs of rank `rank` (row_bounds: world+1 ascending rows 0..wave_h, or NULL = even split); fills everything but
+ * cap_mig, cap_ghost and capacity.  Pure host logic (no device needed). */
+CWA_API int cwa_slab_plan(int world, int rank, int wave_w, int wave_h, int wave_ch, double uv_scale_z, double h, const int* row_bounds,
+                          cwa_slab_desc* out);
+/* s: SPH object on a uniform grid whose particle buffer holds `capacity` records; w: cwa_wave_create_block(store_lo, store_hi - store_lo) */
+CWA_API int cwa_slab_create(cwa_ctx* ctx, const cwa_slab_desc* desc, cwa_sph s, cwa_wave w, cwa_slab* out);
+CWA_API int cwa_slab_destroy(cwa_ctx* ctx, cwa_slab sl);
+CWA_API int cwa_slab_export(cwa_ctx* ctx, cwa_slab sl, void* handle64);                 /* cudaIpcMemHandle_t of the mailbox */
+CWA_API int cwa_slab_mailbox(cwa_ctx* ctx, cwa_slab sl, void** ptr, size_t* bytes);     /* same-process peers connect with the pointer */
+CWA_API int cwa_slab_connect(cwa_ctx* ctx, cwa_slab sl, int peer_rank, const void* handle64_or_null, void* direct_ptr_or_null);
+/* the application (re)wrote particles [0, n_owned) of the SSBO: owned range = n_owned, no ghosts, no free slots */
+CWA_API int cwa_slab_set_owned(cwa_ctx* ctx, cwa_slab sl, int n_owned);
+/* nframes coupled frames of this rank's slab; every rank makes the same calls.  Enqueues only. */
+CWA_API int cwa_slab_step(cwa_ctx* ctx, cwa_slab sl, int nframes, int coupling);
+/* all ranks of one process, one host thread (ctxs[r] / slabs[r] = rank r) */
+CWA_API int cwa_slab_group_step(cwa_ctx* const* ctxs, const cwa_slab* slabs, int n, int nframes, int coupling);
+/* counts[8] = {owned range (dead slots included), owned + ghosts, free slots, error bits (1 sender overflow, 2 capacity, 4 / 8 timeout
+ * waiting for particles / wave rows), migrants adopted (low, high), particle messages consumed, wave messages consumed}; synchronises */
+CWA_API int cwa_slab_counts(cwa_ctx* ctx, cwa_slab sl, int* counts);
+CWA_API int cwa_slab_counts_async(cwa_ctx* ctx, cwa_slab sl, int* pinned_counts4);     /* first four of the above, valid after cwa_synchronize */
+
 /* ---- 2-D Koschier SPH on the uniform grid: SphUgrid (SphWave2D/StencilBuffer.cpp:138-179) ------ */
 CWA_API int cwa_sph2_create(cwa_ctx* ctx, int n, int variant, cwa_grid grid, cwa_sph2* out); /* Init + Reinit (MODE_INIT) */
 CWA_API int cwa_sph2_destroy(cwa_ctx* ctx, cwa_sph2 s);

@@ -65,3 +65,16 @@ def test_reference_arm_line_has_the_contract_keys():
     assert line["higher_is_better"] is True and line["value"] > 0 and line["config"]["workload"] == bench.WORKLOAD
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+
+
+def test_c5_is_baseline_config_5():
+    for world in (2, 4, 8):
+        sc = bench.c5_scene(world, "torque_scaled")
+        assert sc["nx"] * sc["ny"] * sc["nz"] == 16056320 and (sc["wave_w"], sc["wave_h"]) == (8192, 8192)
+        assert sc["scaling"] == "strong" and "16056320 particles" in sc["name"]
+        base = bench.scaled_scene(1)
+        assert abs(sc["box_x"] / sc["gn"][0] - base["box_x"] / base["gn"][0]) < 1e-9       # C4's cell size
+        assert abs(1.0 / (sc["uv"] * sc["wave_w"]) - 1.0 / (base["uv"] * base["wave_w"])) < 1e-9   # C4's texel size
+        gain = sc["torque"] * math.hypot(sc["box_x"], sc["box_z"])
+        assert abs(gain - 0.25 * math.hypot(base["box_x"], base["box_z"])) < 1e-9
+        assert bench.c5_scene(world, "literal")["torque"] == 0.0                            # 0 = the shader's literal 0.25

@@ -168,3 +168,23 @@ def test_three_ranks_reproduce_one_rank(balanced):
     ok = ~np.isnan(ref["pos"]).any(1)
     assert np.array_equal(~ok, np.isnan(got["pos"]).any(1))
     _assert_states_match(got, ref, ok)
+
+
+def test_c_abi_plan_matches_python_plan():
+    """cwa_slab_plan (pure host logic of the library; loads without a GPU) == SlabPlan.make."""
+    import ctypes as C
+    from coupledwateranimation_b200 import _capi
+    from coupledwateranimation_b200.distributed import SlabPlan, plan_desc
+    lib = _capi.load()
+    for world in (1, 2, 3, 4, 8):
+        for (w, h, uv) in ((8192, 8192, 2.0 / 28.0), (256, 512, 0.6), (2896, 2896, 2.0 / (7 * 2 ** 0.5))):
+            for r in range(world):
+                p = SlabPlan.make(world, r, w, h, uv, 0.01)
+                d = plan_desc(lib, world, r, w, h, 1, uv, 0.01)
+                assert (d.row_lo, d.row_hi, d.store_lo, d.store_hi) == (p.row_lo, p.row_hi, p.store_lo, p.store_hi)
+                if r > 0:
+                    assert d.z_lo == np.float32(p.z_lo)
+                    assert d.left_store_hi == SlabPlan.make(world, r - 1, w, h, uv, 0.01).store_hi
+                if r < world - 1:
+                    assert d.z_hi == np.float32(p.z_hi)
+                    assert d.right_store_lo == SlabPlan.make(world, r + 1, w, h, uv, 0.01).store_lo
