@@ -144,6 +144,7 @@ extern "C" int cwa_create(int device, cwa_ctx** out)
 
 extern "C" void cwa_destroy(cwa_ctx* ctx)
 {
+    DeviceGuard _dg(ctx);
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
@@ -166,6 +167,7 @@ extern "C" void cwa_destroy(cwa_ctx* ctx)
 
 extern "C" int cwa_synchronize(cwa_ctx* ctx)
 {
+    DeviceGuard _dg(ctx);
     CWA_CHECK(ctx, "null context");
     CWA_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -175,6 +177,7 @@ extern "C" void* cwa_stream(cwa_ctx* ctx) { return ctx ? (void*)ctx->stream : nu
 
 extern "C" int cwa_device_info(cwa_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem)
 {
+    DeviceGuard _dg(ctx);
     CWA_CHECK(ctx, "null context");
     if (sm_count) *sm_count = ctx->sm_count;
     if (cc_major) *cc_major = ctx->cc_major;
@@ -185,6 +188,7 @@ extern "C" int cwa_device_info(cwa_ctx* ctx, int* sm_count, int* cc_major, int* 
 
 extern "C" int cwa_timer_begin(cwa_ctx* ctx)
 {
+    DeviceGuard _dg(ctx);
     CWA_CHECK(ctx, "null context");
     CWA_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
     return 0;
@@ -192,6 +196,7 @@ extern "C" int cwa_timer_begin(cwa_ctx* ctx)
 
 extern "C" int cwa_timer_end(cwa_ctx* ctx, float* ms)
 {
+    DeviceGuard _dg(ctx);
     CWA_CHECK(ctx && ms, "null argument");
     CWA_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     CWA_CUDA(cudaEventSynchronize(ctx->ev1));
@@ -211,6 +216,7 @@ extern "C" const char* cwa_profile_kernel_name(int id) { return (id >= 0 && id <
 
 extern "C" int cwa_profile_begin(cwa_ctx* ctx)
 {
+    DeviceGuard _dg(ctx);
     CWA_CHECK(ctx, "null context");
     CWA_CUDA(cudaStreamSynchronize(ctx->stream));
     for (auto& r : ctx->prof) { ctx->ev_pool.push_back(r.a); ctx->ev_pool.push_back(r.b); }
@@ -221,6 +227,7 @@ extern "C" int cwa_profile_begin(cwa_ctx* ctx)
 
 extern "C" int cwa_profile_end(cwa_ctx* ctx, float* ms, int* launches, int cap)
 {
+    DeviceGuard _dg(ctx);
     CWA_CHECK(ctx && ms && launches && cap >= KID_COUNT, "cwa_profile_end: need arrays of %d entries", KID_COUNT);
     ctx->profiling = false;
     CWA_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -240,6 +247,7 @@ extern "C" int cwa_profile_end(cwa_ctx* ctx, float* ms, int* launches, int cap)
 // ---------------------------------------------------------------------------------------------
 extern "C" int cwa_buffer_create(cwa_ctx* ctx, size_t bytes, const void* host, cwa_buf* out)
 {
+    DeviceGuard _dg(ctx);
     CWA_CHECK(ctx && out, "null argument");
     CWA_CHECK(bytes > 0, "cwa_buffer_create: zero size");
     void* p = nullptr;
@@ -252,6 +260,7 @@ extern "C" int cwa_buffer_create(cwa_ctx* ctx, size_t bytes, const void* host, c
 
 extern "C" int cwa_buffer_wrap(cwa_ctx* ctx, void* device_ptr, size_t bytes, cwa_buf* out)
 {
+    DeviceGuard _dg(ctx);
     CWA_CHECK(ctx && out && device_ptr, "null argument");
     cudaPointerAttributes attr;
     CWA_CUDA(cudaPointerGetAttributes(&attr, device_ptr));
@@ -263,6 +272,7 @@ extern "C" int cwa_buffer_wrap(cwa_ctx* ctx, void* device_ptr, size_t bytes, cwa
 
 extern "C" int cwa_buffer_destroy(cwa_ctx* ctx, cwa_buf b)
 {
+    DeviceGuard _dg(ctx);
     BufferObj* o = get_buffer(ctx, b);
     CWA_CHECK(o, "invalid buffer handle %d", b);
     CWA_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -275,6 +285,7 @@ extern "C" int cwa_buffer_destroy(cwa_ctx* ctx, cwa_buf b)
 
 extern "C" int cwa_buffer_sub_data(cwa_ctx* ctx, cwa_buf b, size_t off, size_t bytes, const void* host)
 {
+    DeviceGuard _dg(ctx);
     BufferObj* o = get_buffer(ctx, b);
     CWA_CHECK(o, "invalid buffer handle %d", b);
     CWA_CHECK(host && off + bytes <= o->bytes, "cwa_buffer_sub_data: range [%zu,%zu) outside buffer of %zu bytes", off, off + bytes, o->bytes);
@@ -288,6 +299,7 @@ extern "C" int cwa_buffer_sub_data(cwa_ctx* ctx, cwa_buf b, size_t off, size_t b
 
 extern "C" int cwa_buffer_read(cwa_ctx* ctx, cwa_buf b, size_t off, size_t bytes, void* host)
 {
+    DeviceGuard _dg(ctx);
     BufferObj* o = get_buffer(ctx, b);
     CWA_CHECK(o, "invalid buffer handle %d", b);
     CWA_CHECK(host && off + bytes <= o->bytes, "cwa_buffer_read: range outside buffer");
@@ -301,6 +313,7 @@ extern "C" int cwa_buffer_read(cwa_ctx* ctx, cwa_buf b, size_t off, size_t bytes
 // into a persistently mapped / pixel-pack buffer followed by a fence.
 extern "C" int cwa_buffer_read_async(cwa_ctx* ctx, cwa_buf b, size_t off, size_t bytes, void* host)
 {
+    DeviceGuard _dg(ctx);
     BufferObj* o = get_buffer(ctx, b);
     CWA_CHECK(o, "invalid buffer handle %d", b);
     CWA_CHECK(host && off + bytes <= o->bytes, "cwa_buffer_read_async: range outside buffer");
@@ -310,6 +323,7 @@ extern "C" int cwa_buffer_read_async(cwa_ctx* ctx, cwa_buf b, size_t off, size_t
 
 extern "C" int cwa_buffer_copy(cwa_ctx* ctx, cwa_buf src, cwa_buf dst, size_t soff, size_t doff, size_t bytes)
 {
+    DeviceGuard _dg(ctx);
     BufferObj* s = get_buffer(ctx, src);
     BufferObj* d = get_buffer(ctx, dst);
     CWA_CHECK(s && d, "invalid buffer handle");
@@ -323,6 +337,7 @@ extern "C" int cwa_buffer_copy(cwa_ctx* ctx, cwa_buf src, cwa_buf dst, size_t so
 
 extern "C" int cwa_buffer_bind_base(cwa_ctx* ctx, int target, int binding, cwa_buf b)
 {
+    DeviceGuard _dg(ctx);
     CWA_CHECK(ctx, "null context");
     CWA_CHECK(b == -1 || get_buffer(ctx, b), "invalid buffer handle %d", b);
     if (target == CWA_TARGET_SSBO) {
@@ -340,6 +355,7 @@ extern "C" int cwa_buffer_bind_base(cwa_ctx* ctx, int target, int binding, cwa_b
 
 extern "C" int cwa_buffer_device_ptr(cwa_ctx* ctx, cwa_buf b, void** ptr, size_t* bytes)
 {
+    DeviceGuard _dg(ctx);
     BufferObj* o = get_buffer(ctx, b);
     CWA_CHECK(o, "invalid buffer handle %d", b);
     if (ptr) *ptr = o->ptr;
@@ -351,6 +367,7 @@ extern "C" int cwa_buffer_device_ptr(cwa_ctx* ctx, cwa_buf b, void** ptr, size_t
 
 extern "C" int cwa_default_ubo(cwa_ctx* ctx, int binding, cwa_buf* out)
 {
+    DeviceGuard _dg(ctx);
     CWA_CHECK(ctx && out, "null argument");
     CWA_CHECK(binding >= 1 && binding <= 4, "no default block for UBO binding %d", binding);
     *out = ctx->default_ubo[binding];
@@ -362,6 +379,7 @@ extern "C" int cwa_default_ubo(cwa_ctx* ctx, int binding, cwa_buf* out)
 // ---------------------------------------------------------------------------------------------
 extern "C" int cwa_scan_exclusive(cwa_ctx* ctx, cwa_buf in, cwa_buf out, int n)
 {
+    DeviceGuard _dg(ctx);
     BufferObj* i = get_buffer(ctx, in);
     BufferObj* o = get_buffer(ctx, out);
     CWA_CHECK(i && o, "invalid buffer handle");
@@ -380,6 +398,7 @@ extern "C" int cwa_scan_exclusive(cwa_ctx* ctx, cwa_buf in, cwa_buf out, int n)
 // ---------------------------------------------------------------------------------------------
 extern "C" int cwa_bind_scene(cwa_ctx* ctx, cwa_sph s, cwa_wave w)
 {
+    DeviceGuard _dg(ctx);
     CWA_CHECK(ctx, "null context");
     CWA_CHECK(s == -1 || get_sph(ctx, s), "invalid sph handle %d", s);
     CWA_CHECK(w == -1 || get_wave(ctx, w), "invalid wave handle %d", w);
@@ -390,6 +409,7 @@ extern "C" int cwa_bind_scene(cwa_ctx* ctx, cwa_sph s, cwa_wave w)
 
 extern "C" int sph_step(cwa_ctx* ctx, int nsteps)
 {
+    DeviceGuard _dg(ctx);
     CWA_CHECK(ctx, "null context");
     CWA_CHECK(get_sph(ctx, ctx->bound_sph), "sph_step: no SPH object bound (cwa_bind_scene)");
     return cwa_sph_step(ctx, ctx->bound_sph, nsteps);
@@ -397,6 +417,7 @@ extern "C" int sph_step(cwa_ctx* ctx, int nsteps)
 
 extern "C" int wave_step(cwa_ctx* ctx, int nsteps)
 {
+    DeviceGuard _dg(ctx);
     CWA_CHECK(ctx, "null context");
     CWA_CHECK(get_wave(ctx, ctx->bound_wave), "wave_step: no wave object bound (cwa_bind_scene)");
     return cwa_wave_compute(ctx, ctx->bound_wave, nsteps);
@@ -409,6 +430,7 @@ enum ShaderKind { SK_RHO = 0, SK_FORCE, SK_INTEGRATE, SK_WAVE, SK_WAVE_SIMP, SK_
 
 extern "C" int cwa_shader_create(cwa_ctx* ctx, const char* glsl_filename, cwa_shader* out)
 {
+    DeviceGuard _dg(ctx);
     CWA_CHECK(ctx && out && glsl_filename, "null argument");
     *out = -1;
     std::string n(glsl_filename);
@@ -441,6 +463,7 @@ static ShaderObj* get_shader(cwa_ctx* ctx, cwa_shader s)
 
 extern "C" int cwa_shader_set_mode(cwa_ctx* ctx, cwa_shader s, int mode)
 {
+    DeviceGuard _dg(ctx);
     ShaderObj* o = get_shader(ctx, s);
     CWA_CHECK(o, "invalid shader handle %d", s);
     o->mode = mode;
@@ -449,6 +472,7 @@ extern "C" int cwa_shader_set_mode(cwa_ctx* ctx, cwa_shader s, int mode)
 
 extern "C" int cwa_shader_set_uniform_i(cwa_ctx* ctx, cwa_shader s, int location, int v)
 {
+    DeviceGuard _dg(ctx);
     ShaderObj* o = get_shader(ctx, s);
     CWA_CHECK(o, "invalid shader handle %d", s);
     CWA_CHECK(location >= 0 && location < 8, "uniform location %d out of range", location);
@@ -458,6 +482,7 @@ extern "C" int cwa_shader_set_uniform_i(cwa_ctx* ctx, cwa_shader s, int location
 
 extern "C" int cwa_shader_set_uniform_f(cwa_ctx* ctx, cwa_shader s, int location, float v)
 {
+    DeviceGuard _dg(ctx);
     ShaderObj* o = get_shader(ctx, s);
     CWA_CHECK(o, "invalid shader handle %d", s);
     CWA_CHECK(location >= 0 && location < 8, "uniform location %d out of range", location);
@@ -467,6 +492,7 @@ extern "C" int cwa_shader_set_uniform_f(cwa_ctx* ctx, cwa_shader s, int location
 
 extern "C" int cwa_shader_bind_object(cwa_ctx* ctx, cwa_shader s, int object_handle)
 {
+    DeviceGuard _dg(ctx);
     ShaderObj* o = get_shader(ctx, s);
     CWA_CHECK(o, "invalid shader handle %d", s);
     o->object = object_handle;
@@ -477,6 +503,7 @@ int prefix_sum_level_launch(cwa_ctx* ctx, int* x, int n, int phase, int stride, 
 
 extern "C" int cwa_shader_dispatch(cwa_ctx* ctx, cwa_shader s, int gx, int gy, int gz)
 {
+    DeviceGuard _dg(ctx);
     ShaderObj* o = get_shader(ctx, s);
     CWA_CHECK(o, "invalid shader handle %d", s);
     (void)gy; (void)gz;

@@ -392,6 +392,7 @@ int grid_build_internal(cwa_ctx* ctx, GridObj* g, const void* particles, int str
 extern "C" int cwa_grid_create(cwa_ctx* ctx, int dim, const float* mn, const float* mx, const int* num_cells,
                                int max_particles, cwa_grid* out)
 {
+    DeviceGuard _dg(ctx);
     CWA_CHECK(ctx && mn && mx && num_cells && out, "null argument");
     CWA_CHECK((dim & 15) == 2 || (dim & 15) == 3, "cwa_grid_create: dim must be 2 or 3");
     CWA_CHECK(max_particles > 0, "cwa_grid_create: max_particles must be positive");
@@ -460,6 +461,7 @@ extern "C" int cwa_grid_create(cwa_ctx* ctx, int dim, const float* mn, const flo
 
 extern "C" int cwa_grid_destroy(cwa_ctx* ctx, cwa_grid h)
 {
+    DeviceGuard _dg(ctx);
     GridObj* g = get_grid(ctx, h);
     CWA_CHECK(g, "invalid grid handle %d", h);
     CWA_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -472,6 +474,7 @@ extern "C" int cwa_grid_destroy(cwa_ctx* ctx, cwa_grid h)
 
 extern "C" int cwa_grid_get_info(cwa_ctx* ctx, cwa_grid h, cwa_grid_info* out, int* num_cells_total)
 {
+    DeviceGuard _dg(ctx);
     GridObj* g = get_grid(ctx, h);
     CWA_CHECK(g, "invalid grid handle %d", h);
     if (out) *out = g->info;
@@ -481,6 +484,7 @@ extern "C" int cwa_grid_get_info(cwa_ctx* ctx, cwa_grid h, cwa_grid_info* out, i
 
 extern "C" int cwa_grid_build(cwa_ctx* ctx, cwa_grid h, cwa_buf particles, int stride_bytes, int n)
 {
+    DeviceGuard _dg(ctx);
     GridObj* g = get_grid(ctx, h);
     CWA_CHECK(g, "invalid grid handle %d", h);
     BufferObj* p = get_buffer(ctx, particles);
@@ -491,6 +495,7 @@ extern "C" int cwa_grid_build(cwa_ctx* ctx, cwa_grid h, cwa_buf particles, int s
 
 extern "C" int cwa_grid_read(cwa_ctx* ctx, cwa_grid h, int which, int* host, int count)
 {
+    DeviceGuard _dg(ctx);
     GridObj* g = get_grid(ctx, h);
     CWA_CHECK(g && host, "invalid grid handle %d", h);
     const int* src = nullptr; int avail = 0;
@@ -509,6 +514,7 @@ extern "C" int cwa_grid_read(cwa_ctx* ctx, cwa_grid h, int which, int* host, int
 
 extern "C" int cwa_grid_buffer(cwa_ctx* ctx, cwa_grid h, int which, cwa_buf* out)
 {
+    DeviceGuard _dg(ctx);
     GridObj* g = get_grid(ctx, h);
     CWA_CHECK(g && out, "invalid grid handle %d", h);
     switch (which) {

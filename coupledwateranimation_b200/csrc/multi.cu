@@ -70,6 +70,7 @@ static MultiScratch* multi_scratch(cwa_ctx* ctx, int n)
 extern "C" int cwa_particles_copy_if(cwa_ctx* ctx, cwa_buf src, int n, int axis, int kind, float a, float b,
                                      cwa_buf dst, int dst_offset, int* count_out)
 {
+    DeviceGuard _dg(ctx);
     BufferObj* s = get_buffer(ctx, src);
     BufferObj* d = get_buffer(ctx, dst);
     CWA_CHECK(s && d && count_out, "cwa_particles_copy_if: invalid buffer handle or null count");
@@ -99,6 +100,7 @@ extern "C" int cwa_particles_copy_if(cwa_ctx* ctx, cwa_buf src, int n, int axis,
 
 extern "C" int cwa_sph_set_count(cwa_ctx* ctx, cwa_sph h, int n)
 {
+    DeviceGuard _dg(ctx);
     SphObj* s = get_sph(ctx, h);
     CWA_CHECK(s, "invalid sph handle %d", h);
     BufferObj* pb = get_buffer(ctx, s->particles);
@@ -193,6 +195,7 @@ slab_unpack_kernel(float4* __restrict__ aos, int n_owned, int capacity, const fl
 extern "C" int cwa_slab_pack(cwa_ctx* ctx, cwa_buf particles, int n_owned, float z_lo, float z_hi, float band,
                              cwa_buf msg_left, cwa_buf msg_right, int cap_mig, int cap_ghost)
 {
+    DeviceGuard _dg(ctx);
     BufferObj* p = get_buffer(ctx, particles);
     BufferObj* ml = get_buffer(ctx, msg_left);
     BufferObj* mr = get_buffer(ctx, msg_right);
@@ -228,6 +231,7 @@ extern "C" int cwa_slab_pack(cwa_ctx* ctx, cwa_buf particles, int n_owned, float
 extern "C" int cwa_sph_step_slab(cwa_ctx* ctx, cwa_sph h, int n_owned, float z_lo, float z_hi, float band,
                                  cwa_buf msg_left, cwa_buf msg_right, int cap_mig, int cap_ghost)
 {
+    DeviceGuard _dg(ctx);
     SphObj* s = get_sph(ctx, h);
     CWA_CHECK(s, "invalid sph handle %d", h);
     CWA_CHECK(s->grid >= 0, "cwa_sph_step_slab: the SPH object needs a uniform grid");
@@ -256,6 +260,7 @@ extern "C" int cwa_sph_step_slab(cwa_ctx* ctx, cwa_sph h, int n_owned, float z_l
 extern "C" int cwa_slab_unpack(cwa_ctx* ctx, cwa_buf particles, int n_owned, cwa_buf rcv_left, cwa_buf rcv_right,
                                cwa_buf sent_left, cwa_buf sent_right, int cap_mig, int cap_ghost, int* counts_host)
 {
+    DeviceGuard _dg(ctx);
     BufferObj* p = get_buffer(ctx, particles);
     BufferObj* rl = get_buffer(ctx, rcv_left);
     BufferObj* rr = get_buffer(ctx, rcv_right);
@@ -289,6 +294,7 @@ multi_flag_live_kernel(const float4* __restrict__ aos, int n, int* __restrict__ 
 
 extern "C" int cwa_slab_compact(cwa_ctx* ctx, cwa_buf particles, int n_owned, cwa_buf scratch, int* n_live)
 {
+    DeviceGuard _dg(ctx);
     BufferObj* p = get_buffer(ctx, particles);
     BufferObj* s = get_buffer(ctx, scratch);
     CWA_CHECK(p && s && n_live && (size_t)n_owned * 64 <= p->bytes && (size_t)n_owned * 64 <= s->bytes, "cwa_slab_compact: bad buffers");

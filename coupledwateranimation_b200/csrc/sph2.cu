@@ -299,6 +299,7 @@ static void sph2_pingpong(Sph2Obj* s) { std::swap(s->read_index, s->write_index)
 
 extern "C" int cwa_sph2_reinit(cwa_ctx* ctx, cwa_sph2 h)
 {
+    DeviceGuard _dg(ctx);
     Sph2Obj* s = get_sph2(ctx, h);
     CWA_CHECK(s, "invalid sph2 handle %d", h);
     BufferObj* wb = get_buffer(ctx, s->buffer[s->write_index]);
@@ -313,6 +314,7 @@ extern "C" int cwa_sph2_reinit(cwa_ctx* ctx, cwa_sph2 h)
 
 extern "C" int cwa_sph2_create(cwa_ctx* ctx, int n, int variant, cwa_grid grid, cwa_sph2* out)
 {
+    DeviceGuard _dg(ctx);
     CWA_CHECK(ctx && out, "null argument");
     *out = -1;
     CWA_CHECK(n > 0, "cwa_sph2_create: n must be positive");
@@ -334,6 +336,7 @@ extern "C" int cwa_sph2_create(cwa_ctx* ctx, int n, int variant, cwa_grid grid, 
 
 extern "C" int cwa_sph2_destroy(cwa_ctx* ctx, cwa_sph2 h)
 {
+    DeviceGuard _dg(ctx);
     Sph2Obj* s = get_sph2(ctx, h);
     CWA_CHECK(s, "invalid sph2 handle %d", h);
     CWA_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -345,6 +348,7 @@ extern "C" int cwa_sph2_destroy(cwa_ctx* ctx, cwa_sph2 h)
 
 extern "C" int cwa_sph2_set_substeps(cwa_ctx* ctx, cwa_sph2 h, int substeps)
 {
+    DeviceGuard _dg(ctx);
     Sph2Obj* s = get_sph2(ctx, h);
     CWA_CHECK(s && substeps >= 0, "invalid sph2 handle %d or substeps", h);
     s->substeps = substeps;
@@ -353,6 +357,7 @@ extern "C" int cwa_sph2_set_substeps(cwa_ctx* ctx, cwa_sph2 h, int substeps)
 
 extern "C" int cwa_sph2_set_uniforms(cwa_ctx* ctx, cwa_sph2 h, float time, float bottom, float psi, int init_width)
 {
+    DeviceGuard _dg(ctx);
     Sph2Obj* s = get_sph2(ctx, h);
     CWA_CHECK(s, "invalid sph2 handle %d", h);
     s->time = time; s->bottom = bottom; s->psi = psi;
@@ -362,6 +367,7 @@ extern "C" int cwa_sph2_set_uniforms(cwa_ctx* ctx, cwa_sph2 h, float time, float
 
 extern "C" int cwa_sph2_set_view_width(cwa_ctx* ctx, cwa_sph2 h, float view_width)
 {
+    DeviceGuard _dg(ctx);
     Sph2Obj* s = get_sph2(ctx, h);
     CWA_CHECK(s && view_width > 0.0f, "invalid sph2 handle %d or view width", h);
     s->view_width = view_width;
@@ -370,6 +376,7 @@ extern "C" int cwa_sph2_set_view_width(cwa_ctx* ctx, cwa_sph2 h, float view_widt
 
 extern "C" int cwa_sph2_bind_wave1d(cwa_ctx* ctx, cwa_sph2 h, cwa_buf rgba, int width)
 {
+    DeviceGuard _dg(ctx);
     Sph2Obj* s = get_sph2(ctx, h);
     CWA_CHECK(s, "invalid sph2 handle %d", h);
     if (rgba == -1) { s->wave1d = -1; s->wave1d_width = 0; return 0; }
@@ -381,6 +388,7 @@ extern "C" int cwa_sph2_bind_wave1d(cwa_ctx* ctx, cwa_sph2 h, cwa_buf rgba, int 
 
 extern "C" int cwa_sph2_compute(cwa_ctx* ctx, cwa_sph2 h, int nframes)
 {
+    DeviceGuard _dg(ctx);
     Sph2Obj* s = get_sph2(ctx, h);
     CWA_CHECK(s, "invalid sph2 handle %d", h);
     GridObj* g = get_grid(ctx, s->grid);
@@ -418,6 +426,7 @@ extern "C" int cwa_sph2_compute(cwa_ctx* ctx, cwa_sph2 h, int nframes)
 
 extern "C" int cwa_sph2_read(cwa_ctx* ctx, cwa_sph2 h, cwa_particle2d* host)
 {
+    DeviceGuard _dg(ctx);
     Sph2Obj* s = get_sph2(ctx, h);
     CWA_CHECK(s && host, "invalid sph2 handle %d", h);
     return cwa_buffer_read(ctx, s->buffer[s->read_index], 0, (size_t)s->n * sizeof(cwa_particle2d), host);
@@ -425,6 +434,7 @@ extern "C" int cwa_sph2_read(cwa_ctx* ctx, cwa_sph2 h, cwa_particle2d* host)
 
 extern "C" int cwa_sph2_write(cwa_ctx* ctx, cwa_sph2 h, const cwa_particle2d* host)
 {
+    DeviceGuard _dg(ctx);
     Sph2Obj* s = get_sph2(ctx, h);
     CWA_CHECK(s && host, "invalid sph2 handle %d", h);
     return cwa_buffer_sub_data(ctx, s->buffer[s->read_index], 0, (size_t)s->n * sizeof(cwa_particle2d), host);
@@ -432,6 +442,7 @@ extern "C" int cwa_sph2_write(cwa_ctx* ctx, cwa_sph2 h, const cwa_particle2d* ho
 
 extern "C" int cwa_sph2_read_buffer(cwa_ctx* ctx, cwa_sph2 h, cwa_buf* out)
 {
+    DeviceGuard _dg(ctx);
     Sph2Obj* s = get_sph2(ctx, h);
     CWA_CHECK(s && out, "invalid sph2 handle %d", h);
     *out = s->buffer[s->read_index];

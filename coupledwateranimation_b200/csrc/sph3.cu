@@ -1292,6 +1292,7 @@ static bool fused_order(cwa_ctx* c) { if (c->tune.fused_order < 0) c->tune.fused
 
 extern "C" int cwa_set_tuning(cwa_ctx* ctx, const char* key, int value)
 {
+    DeviceGuard _dg(ctx);
     CWA_CHECK(ctx && key, "null argument");
     const std::string k(key);
     if (k == "nb_config") { CWA_CHECK(value >= 0 && value <= 7, "nb_config %d out of range", value); ctx->tune.config = value; }
@@ -1560,6 +1561,7 @@ int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which, bool co
 
 extern "C" int cwa_sph_create(cwa_ctx* ctx, cwa_buf particles, int n, cwa_grid grid, cwa_sph* out)
 {
+    DeviceGuard _dg(ctx);
     CWA_CHECK(ctx && out, "null argument");
     *out = -1;
     BufferObj* pb = get_buffer(ctx, particles);
@@ -1600,6 +1602,7 @@ extern "C" int cwa_sph_create(cwa_ctx* ctx, cwa_buf particles, int n, cwa_grid g
 
 extern "C" int cwa_sph_destroy(cwa_ctx* ctx, cwa_sph h)
 {
+    DeviceGuard _dg(ctx);
     SphObj* s = get_sph(ctx, h);
     CWA_CHECK(s, "invalid sph handle %d", h);
     CWA_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1613,6 +1616,7 @@ extern "C" int cwa_sph_destroy(cwa_ctx* ctx, cwa_sph h)
 
 extern "C" int cwa_sph_bind_wave(cwa_ctx* ctx, cwa_sph h, cwa_wave w, int image)
 {
+    DeviceGuard _dg(ctx);
     SphObj* s = get_sph(ctx, h);
     CWA_CHECK(s, "invalid sph handle %d", h);
     CWA_CHECK(w == -1 || get_wave(ctx, w), "invalid wave handle %d", w);
@@ -1628,6 +1632,7 @@ static TexView sph_current_tex(cwa_ctx* ctx, SphObj* s)
 
 extern "C" int cwa_sph_rho_pres(cwa_ctx* ctx, cwa_sph h)
 {
+    DeviceGuard _dg(ctx);
     SphObj* s = get_sph(ctx, h);
     CWA_CHECK(s, "invalid sph handle %d", h);
     return sph_passes_internal(ctx, s, sph_current_tex(ctx, s), 1);
@@ -1635,6 +1640,7 @@ extern "C" int cwa_sph_rho_pres(cwa_ctx* ctx, cwa_sph h)
 
 extern "C" int cwa_sph_force(cwa_ctx* ctx, cwa_sph h)
 {
+    DeviceGuard _dg(ctx);
     SphObj* s = get_sph(ctx, h);
     CWA_CHECK(s, "invalid sph handle %d", h);
     return sph_passes_internal(ctx, s, sph_current_tex(ctx, s), 2);
@@ -1642,6 +1648,7 @@ extern "C" int cwa_sph_force(cwa_ctx* ctx, cwa_sph h)
 
 extern "C" int cwa_sph_integrate(cwa_ctx* ctx, cwa_sph h)
 {
+    DeviceGuard _dg(ctx);
     SphObj* s = get_sph(ctx, h);
     CWA_CHECK(s, "invalid sph handle %d", h);
     return sph_passes_internal(ctx, s, sph_current_tex(ctx, s), 4);
@@ -1649,6 +1656,7 @@ extern "C" int cwa_sph_integrate(cwa_ctx* ctx, cwa_sph h)
 
 extern "C" int cwa_sph_step(cwa_ctx* ctx, cwa_sph h, int nsteps)
 {
+    DeviceGuard _dg(ctx);
     SphObj* s = get_sph(ctx, h);
     CWA_CHECK(s, "invalid sph handle %d", h);
     for (int k = 0; k < nsteps; k++) CWA_TRY(sph_passes_internal(ctx, s, sph_current_tex(ctx, s), 7));
@@ -1657,6 +1665,7 @@ extern "C" int cwa_sph_step(cwa_ctx* ctx, cwa_sph h, int nsteps)
 
 extern "C" int cwa_sph_neighbour_count(cwa_ctx* ctx, cwa_sph h, int* host)
 {
+    DeviceGuard _dg(ctx);
     SphObj* s = get_sph(ctx, h);
     CWA_CHECK(s && host, "invalid sph handle %d", h);
     BufferObj* pb = get_buffer(ctx, s->particles);
@@ -1685,6 +1694,7 @@ extern "C" int cwa_sph_neighbour_count(cwa_ctx* ctx, cwa_sph h, int* host)
 
 extern "C" int cwa_sph_init_cube(cwa_ctx* ctx, cwa_sph h, int nx, int ny, int nz)
 {
+    DeviceGuard _dg(ctx);
     SphObj* s = get_sph(ctx, h);
     CWA_CHECK(s, "invalid sph handle %d", h);
     CWA_CHECK(nx > 0 && ny > 0 && nz > 0 && (long long)nx * ny * nz == s->n, "cwa_sph_init_cube: %dx%dx%d != %d particles", nx, ny, nz, s->n);
@@ -1702,6 +1712,7 @@ extern "C" int cwa_sph_init_cube(cwa_ctx* ctx, cwa_sph h, int nx, int ny, int nz
 // ---------------------------------------------------------------------------------------------
 extern "C" int cwa_coupled_step(cwa_ctx* ctx, cwa_sph hs, cwa_wave hw, int nframes, int coupling)
 {
+    DeviceGuard _dg(ctx);
     SphObj* s = get_sph(ctx, hs);
     WaveObj* w = get_wave(ctx, hw);
     CWA_CHECK(s && w, "cwa_coupled_step: invalid sph (%d) or wave (%d) handle", hs, hw);

@@ -63,6 +63,7 @@ extern "C" int cwa_param_info(int index, const char** name, int* ubo_binding, in
 // writes the field of the block CURRENTLY BOUND at that UBO binding (like a GUI slider writing through glProgramUniform / the UBO)
 extern "C" int cwa_param_set(cwa_ctx* ctx, const char* name, float value)
 {
+    DeviceGuard _dg(ctx);
     CWA_CHECK(ctx, "null context");
     const ParamField* f = find_param(name);
     CWA_CHECK(f, "cwa_param_set: unknown parameter '%s'", name ? name : "(null)");
@@ -71,6 +72,7 @@ extern "C" int cwa_param_set(cwa_ctx* ctx, const char* name, float value)
 
 extern "C" int cwa_param_get(cwa_ctx* ctx, const char* name, float* value)          // synchronises
 {
+    DeviceGuard _dg(ctx);
     CWA_CHECK(ctx && value, "null argument");
     const ParamField* f = find_param(name);
     CWA_CHECK(f, "cwa_param_get: unknown parameter '%s'", name ? name : "(null)");
@@ -104,6 +106,7 @@ static_assert(sizeof(CkptHeader) == 256, "checkpoint header layout");
 
 extern "C" int cwa_checkpoint_save(cwa_ctx* ctx, cwa_sph hs, cwa_wave hw, unsigned long long frame, const char* path)
 {
+    DeviceGuard _dg(ctx);
     SphObj* s = get_sph(ctx, hs);
     WaveObj* w = get_wave(ctx, hw);
     CWA_CHECK(s && w && path, "cwa_checkpoint_save: invalid sph (%d) / wave (%d) handle or path", hs, hw);
@@ -144,6 +147,7 @@ extern "C" int cwa_checkpoint_save(cwa_ctx* ctx, cwa_sph hs, cwa_wave hw, unsign
 // Restores particles, wave levels, bookkeeping and the four parameter blocks into EXISTING objects of matching sizes.
 extern "C" int cwa_checkpoint_load(cwa_ctx* ctx, cwa_sph hs, cwa_wave hw, const char* path, unsigned long long* frame)
 {
+    DeviceGuard _dg(ctx);
     SphObj* s = get_sph(ctx, hs);
     WaveObj* w = get_wave(ctx, hw);
     CWA_CHECK(s && w && path, "cwa_checkpoint_load: invalid sph (%d) / wave (%d) handle or path", hs, hw);

@@ -284,6 +284,7 @@ int stencil1d_dispatch_mode(cwa_ctx* ctx, int handle, int mode, int shader)
 
 extern "C" int cwa_stencil1d_pingpong(cwa_ctx* ctx, cwa_stencil1d h)
 {
+    DeviceGuard _dg(ctx);
     Stencil1dObj* s = get_s1d(ctx, h);
     CWA_CHECK(s, "invalid stencil1d handle %d", h);
     s1d_pingpong(s);
@@ -292,6 +293,7 @@ extern "C" int cwa_stencil1d_pingpong(cwa_ctx* ctx, cwa_stencil1d h)
 
 extern "C" int cwa_stencil1d_create(cwa_ctx* ctx, int shader, int width, cwa_stencil1d* out)
 {
+    DeviceGuard _dg(ctx);
     CWA_CHECK(ctx && out, "null argument");
     *out = -1;
     CWA_CHECK(shader == S1D_SHALLOW || shader == S1D_WAVE, "cwa_stencil1d_create: unknown shader %d", shader);
@@ -321,6 +323,7 @@ extern "C" int cwa_stencil1d_create(cwa_ctx* ctx, int shader, int width, cwa_ste
 
 extern "C" int cwa_stencil1d_destroy(cwa_ctx* ctx, cwa_stencil1d h)
 {
+    DeviceGuard _dg(ctx);
     Stencil1dObj* s = get_s1d(ctx, h);
     CWA_CHECK(s, "invalid stencil1d handle %d", h);
     CWA_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -335,6 +338,7 @@ extern "C" int cwa_stencil1d_destroy(cwa_ctx* ctx, cwa_stencil1d h)
 // Reinit :85-105: one init dispatch per read image (modes mMODE_INIT_FIRST + i), PingPong after each
 extern "C" int cwa_stencil1d_reinit(cwa_ctx* ctx, cwa_stencil1d h)
 {
+    DeviceGuard _dg(ctx);
     Stencil1dObj* s = get_s1d(ctx, h);
     CWA_CHECK(s, "invalid stencil1d handle %d", h);
     const int nread = s->num_images - 1;
@@ -344,6 +348,7 @@ extern "C" int cwa_stencil1d_reinit(cwa_ctx* ctx, cwa_stencil1d h)
 // ReinitFromTexture :122-140 (mode -1: texelFetch(uInitImage, coord) -> output image), then PingPong
 extern "C" int cwa_stencil1d_reinit_from_texture(cwa_ctx* ctx, cwa_stencil1d h, const float* rgba, int width)
 {
+    DeviceGuard _dg(ctx);
     Stencil1dObj* s = get_s1d(ctx, h);
     CWA_CHECK(s && rgba && width >= 1, "cwa_stencil1d_reinit_from_texture: invalid handle %d or texture", h);
     float4* out = s->image[s1d_image_with_unit(s, s->num_images - 1)];
@@ -358,6 +363,7 @@ extern "C" int cwa_stencil1d_reinit_from_texture(cwa_ctx* ctx, cwa_stencil1d h, 
 // Compute :142-164: nframes x substeps x (modes MODE_ITERATE_FIRST..LAST), one launch
 extern "C" int cwa_stencil1d_compute(cwa_ctx* ctx, cwa_stencil1d h, int nframes)
 {
+    DeviceGuard _dg(ctx);
     Stencil1dObj* s = get_s1d(ctx, h);
     CWA_CHECK(s && nframes >= 0, "invalid stencil1d handle %d", h);
     if (!s->iterate) return 0;                   // mIterate == false :144
@@ -374,6 +380,7 @@ extern "C" int cwa_stencil1d_compute(cwa_ctx* ctx, cwa_stencil1d h, int nframes)
 // ComputeFunc(mode) :107-120: one dispatch in `mode` (e.g. Splash = MODE_INIT_1 of Shallow1D) + PingPong
 extern "C" int cwa_stencil1d_compute_func(cwa_ctx* ctx, cwa_stencil1d h, int mode)
 {
+    DeviceGuard _dg(ctx);
     Stencil1dObj* s = get_s1d(ctx, h);
     CWA_CHECK(s, "invalid stencil1d handle %d", h);
     CWA_CHECK(mode >= 0 && mode <= 3, "cwa_stencil1d_compute_func: unsupported uMode %d", mode);
@@ -383,6 +390,7 @@ extern "C" int cwa_stencil1d_compute_func(cwa_ctx* ctx, cwa_stencil1d h, int mod
 extern "C" int cwa_stencil1d_set_params(cwa_ctx* ctx, cwa_stencil1d h, float lambda, float dx_or_atten, float beta,
                                         float boundary0, float boundary1, int bc)
 {
+    DeviceGuard _dg(ctx);
     Stencil1dObj* s = get_s1d(ctx, h);
     CWA_CHECK(s, "invalid stencil1d handle %d", h);
     CWA_CHECK(bc == CWA_BC_REFLECT || bc == CWA_BC_FREE || bc == CWA_BC_FIXED, "cwa_stencil1d_set_params: unknown boundary condition %d", bc);
@@ -392,6 +400,7 @@ extern "C" int cwa_stencil1d_set_params(cwa_ctx* ctx, cwa_stencil1d h, float lam
 
 extern "C" int cwa_stencil1d_set_substeps(cwa_ctx* ctx, cwa_stencil1d h, int substeps)
 {
+    DeviceGuard _dg(ctx);
     Stencil1dObj* s = get_s1d(ctx, h);
     CWA_CHECK(s && substeps >= 0, "invalid stencil1d handle %d or substep count", h);
     s->substeps = substeps;
@@ -400,6 +409,7 @@ extern "C" int cwa_stencil1d_set_substeps(cwa_ctx* ctx, cwa_stencil1d h, int sub
 
 extern "C" int cwa_stencil1d_set_iterate(cwa_ctx* ctx, cwa_stencil1d h, int iterate)
 {
+    DeviceGuard _dg(ctx);
     Stencil1dObj* s = get_s1d(ctx, h);
     CWA_CHECK(s, "invalid stencil1d handle %d", h);
     s->iterate = iterate != 0;
@@ -408,6 +418,7 @@ extern "C" int cwa_stencil1d_set_iterate(cwa_ctx* ctx, cwa_stencil1d h, int iter
 
 extern "C" int cwa_stencil1d_state(cwa_ctx* ctx, cwa_stencil1d h, int* num_images, int read_index[2], int* write_index, int unit[3])
 {
+    DeviceGuard _dg(ctx);
     Stencil1dObj* s = get_s1d(ctx, h);
     CWA_CHECK(s, "invalid stencil1d handle %d", h);
     if (num_images) *num_images = s->num_images;
@@ -420,6 +431,7 @@ extern "C" int cwa_stencil1d_state(cwa_ctx* ctx, cwa_stencil1d h, int* num_image
 // storage image `image` (0..N-1) as a Buffer: GetReadImage(i) is image read_index[i]; bind it with cwa_sph2_bind_wave1d
 extern "C" int cwa_stencil1d_image_buffer(cwa_ctx* ctx, cwa_stencil1d h, int image, cwa_buf* out)
 {
+    DeviceGuard _dg(ctx);
     Stencil1dObj* s = get_s1d(ctx, h);
     CWA_CHECK(s && out, "invalid stencil1d handle %d", h);
     CWA_CHECK(image >= 0 && image < s->num_images, "image index %d out of range", image);
@@ -429,6 +441,7 @@ extern "C" int cwa_stencil1d_image_buffer(cwa_ctx* ctx, cwa_stencil1d h, int ima
 
 extern "C" int cwa_stencil1d_read_image(cwa_ctx* ctx, cwa_stencil1d h, int image, float* host)
 {
+    DeviceGuard _dg(ctx);
     Stencil1dObj* s = get_s1d(ctx, h);
     CWA_CHECK(s && host, "invalid stencil1d handle %d", h);
     CWA_CHECK(image >= 0 && image < s->num_images, "image index %d out of range", image);
@@ -439,6 +452,7 @@ extern "C" int cwa_stencil1d_read_image(cwa_ctx* ctx, cwa_stencil1d h, int image
 
 extern "C" int cwa_stencil1d_write_image(cwa_ctx* ctx, cwa_stencil1d h, int image, const float* host)
 {
+    DeviceGuard _dg(ctx);
     Stencil1dObj* s = get_s1d(ctx, h);
     CWA_CHECK(s && host, "invalid stencil1d handle %d", h);
     CWA_CHECK(image >= 0 && image < s->num_images, "image index %d out of range", image);

@@ -437,6 +437,7 @@ TexView wave_tex_view(cwa_ctx* ctx, cwa_wave h, int image)
 
 extern "C" int cwa_wave_create(cwa_ctx* ctx, int width, int height, int channels, int variant, cwa_wave* out)
 {
+    DeviceGuard _dg(ctx);
     CWA_CHECK(ctx && out, "null argument");
     *out = -1;
     CWA_CHECK(width >= 1 && height >= 1, "cwa_wave_create: bad size %dx%d", width, height);
@@ -456,6 +457,7 @@ extern "C" int cwa_wave_create(cwa_ctx* ctx, int width, int height, int channels
 
 extern "C" int cwa_wave_destroy(cwa_ctx* ctx, cwa_wave h)
 {
+    DeviceGuard _dg(ctx);
     WaveObj* w = get_wave(ctx, h);
     CWA_CHECK(w, "invalid wave handle %d", h);
     CWA_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -475,6 +477,7 @@ extern "C" int cwa_wave_destroy(cwa_ctx* ctx, cwa_wave h)
 
 extern "C" int cwa_wave_reinit(cwa_ctx* ctx, cwa_wave h)
 {
+    DeviceGuard _dg(ctx);
     WaveObj* w = get_wave(ctx, h);
     CWA_CHECK(w, "invalid wave handle %d", h);
     for (int i = 0; i < 2; i++) {                                    // Reinit :49-58: two INIT passes
@@ -486,6 +489,7 @@ extern "C" int cwa_wave_reinit(cwa_ctx* ctx, cwa_wave h)
 
 extern "C" int cwa_wave_reinit_from_texture(cwa_ctx* ctx, cwa_wave h, const float* rgba, int tw, int th)
 {
+    DeviceGuard _dg(ctx);
     WaveObj* w = get_wave(ctx, h);
     CWA_CHECK(w && rgba, "invalid wave handle %d or null texture", h);
     CWA_CHECK(tw >= 1 && th >= 1, "bad texture size");
@@ -508,6 +512,7 @@ extern "C" int cwa_wave_reinit_from_texture(cwa_ctx* ctx, cwa_wave h, const floa
 
 extern "C" int cwa_wave_compute(cwa_ctx* ctx, cwa_wave h, int nsteps)
 {
+    DeviceGuard _dg(ctx);
     WaveObj* w = get_wave(ctx, h);
     CWA_CHECK(w, "invalid wave handle %d", h);
     if (!w->evolve) return 0;                                        // Compute() :81
@@ -517,6 +522,7 @@ extern "C" int cwa_wave_compute(cwa_ctx* ctx, cwa_wave h, int nsteps)
 
 extern "C" int cwa_wave_pingpong(cwa_ctx* ctx, cwa_wave h)
 {
+    DeviceGuard _dg(ctx);
     WaveObj* w = get_wave(ctx, h);
     CWA_CHECK(w, "invalid wave handle %d", h);
     wave_pingpong(w);
@@ -525,6 +531,7 @@ extern "C" int cwa_wave_pingpong(cwa_ctx* ctx, cwa_wave h)
 
 extern "C" int cwa_wave_set_evolve(cwa_ctx* ctx, cwa_wave h, int evolve)
 {
+    DeviceGuard _dg(ctx);
     WaveObj* w = get_wave(ctx, h);
     CWA_CHECK(w, "invalid wave handle %d", h);
     w->evolve = evolve != 0;
@@ -533,6 +540,7 @@ extern "C" int cwa_wave_set_evolve(cwa_ctx* ctx, cwa_wave h, int evolve)
 
 extern "C" int cwa_wave_set_params(cwa_ctx* ctx, cwa_wave h, float lambda, float atten, float beta)
 {
+    DeviceGuard _dg(ctx);
     WaveObj* w = get_wave(ctx, h);
     CWA_CHECK(w, "invalid wave handle %d", h);
     const float p[4] = {lambda, atten, beta, 1.0f};
@@ -542,6 +550,7 @@ extern "C" int cwa_wave_set_params(cwa_ctx* ctx, cwa_wave h, float lambda, float
 
 extern "C" int cwa_wave_resize(cwa_ctx* ctx, cwa_wave h, int nw, int nh)
 {
+    DeviceGuard _dg(ctx);
     WaveObj* w = get_wave(ctx, h);
     CWA_CHECK(w, "invalid wave handle %d", h);
     CWA_CHECK(nw >= 1 && nh >= 1, "cwa_wave_resize: bad size");
@@ -555,6 +564,7 @@ extern "C" int cwa_wave_resize(cwa_ctx* ctx, cwa_wave h, int nw, int nh)
 
 extern "C" int cwa_wave_state(cwa_ctx* ctx, cwa_wave h, int read_index[2], int* write_index, int unit[3], int* tex_unit0_image)
 {
+    DeviceGuard _dg(ctx);
     WaveObj* w = get_wave(ctx, h);
     CWA_CHECK(w, "invalid wave handle %d", h);
     if (read_index) { read_index[0] = w->read_index[0]; read_index[1] = w->read_index[1]; }
@@ -566,6 +576,7 @@ extern "C" int cwa_wave_state(cwa_ctx* ctx, cwa_wave h, int read_index[2], int* 
 
 extern "C" int cwa_wave_bind_texture_unit(cwa_ctx* ctx, cwa_wave h)
 {
+    DeviceGuard _dg(ctx);
     WaveObj* w = get_wave(ctx, h);
     CWA_CHECK(w, "invalid wave handle %d", h);
     const int ri0 = w->read_index[0];
@@ -580,6 +591,7 @@ static int resolve_image(WaveObj* w, int image)
 
 extern "C" int cwa_wave_read_image(cwa_ctx* ctx, cwa_wave h, int image, float* host)
 {
+    DeviceGuard _dg(ctx);
     WaveObj* w = get_wave(ctx, h);
     CWA_CHECK(w && host, "invalid wave handle %d", h);
     const int i = resolve_image(w, image);
@@ -591,6 +603,7 @@ extern "C" int cwa_wave_read_image(cwa_ctx* ctx, cwa_wave h, int image, float* h
 
 extern "C" int cwa_wave_read_image_async(cwa_ctx* ctx, cwa_wave h, int image, float* host)
 {
+    DeviceGuard _dg(ctx);
     WaveObj* w = get_wave(ctx, h);
     CWA_CHECK(w && host, "invalid wave handle %d", h);
     const int i = resolve_image(w, image);
@@ -601,6 +614,7 @@ extern "C" int cwa_wave_read_image_async(cwa_ctx* ctx, cwa_wave h, int image, fl
 
 extern "C" int cwa_wave_write_image(cwa_ctx* ctx, cwa_wave h, int image, const float* host)
 {
+    DeviceGuard _dg(ctx);
     WaveObj* w = get_wave(ctx, h);
     CWA_CHECK(w && host, "invalid wave handle %d", h);
     const int i = resolve_image(w, image);
@@ -614,6 +628,7 @@ extern "C" int cwa_wave_write_image(cwa_ctx* ctx, cwa_wave h, int image, const f
 // into halo rows) reports it here; without such reports the library stops keeping derived copies of that object's images.
 extern "C" int cwa_wave_mark_written(cwa_ctx* ctx, cwa_wave h, int image)
 {
+    DeviceGuard _dg(ctx);
     WaveObj* w = get_wave(ctx, h);
     CWA_CHECK(w, "invalid wave handle %d", h);
     const int i = resolve_image(w, image);
@@ -625,6 +640,7 @@ extern "C" int cwa_wave_mark_written(cwa_ctx* ctx, cwa_wave h, int image)
 
 extern "C" int cwa_wave_role_image(cwa_ctx* ctx, cwa_wave h, int role, int* image)
 {
+    DeviceGuard _dg(ctx);
     WaveObj* w = get_wave(ctx, h);
     CWA_CHECK(w && image, "invalid wave handle %d", h);
     CWA_CHECK(role >= 0 && role < 3, "role %d out of range", role);
@@ -634,6 +650,7 @@ extern "C" int cwa_wave_role_image(cwa_ctx* ctx, cwa_wave h, int role, int* imag
 
 extern "C" int cwa_wave_image_buffer(cwa_ctx* ctx, cwa_wave h, int image, cwa_buf* out)
 {
+    DeviceGuard _dg(ctx);
     WaveObj* w = get_wave(ctx, h);
     CWA_CHECK(w && out, "invalid wave handle %d", h);
     CWA_CHECK(image >= 0 && image < 3, "image index %d out of range", image);
@@ -643,6 +660,7 @@ extern "C" int cwa_wave_image_buffer(cwa_ctx* ctx, cwa_wave h, int image, cwa_bu
 
 extern "C" int cwa_wave_size(cwa_ctx* ctx, cwa_wave h, int* width, int* height, int* channels)
 {
+    DeviceGuard _dg(ctx);
     WaveObj* w = get_wave(ctx, h);
     CWA_CHECK(w, "invalid wave handle %d", h);
     if (width) *width = w->w;
@@ -659,6 +677,7 @@ extern "C" int cwa_wave_size(cwa_ctx* ctx, cwa_wave h, int* width, int* height, 
 // ---------------------------------------------------------------------------------------------
 extern "C" int cwa_wave_create_block(cwa_ctx* ctx, int width, int h_global, int row0, int rows, int channels, int variant, cwa_wave* out)
 {
+    DeviceGuard _dg(ctx);
     CWA_CHECK(ctx && out, "null argument");
     *out = -1;
     CWA_CHECK(width >= 1 && h_global >= 1 && rows >= 1 && row0 >= 0 && row0 + rows <= h_global,
@@ -685,6 +704,7 @@ extern "C" int cwa_wave_create_block(cwa_ctx* ctx, int width, int h_global, int 
 
 extern "C" int cwa_wave_last_row_buffer(cwa_ctx* ctx, cwa_wave h, int image, cwa_buf* out)
 {
+    DeviceGuard _dg(ctx);
     WaveObj* w = get_wave(ctx, h);
     CWA_CHECK(w && out, "invalid wave handle %d", h);
     CWA_CHECK(image >= 0 && image < 3, "image index %d out of range", image);
