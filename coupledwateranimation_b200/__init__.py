@@ -118,7 +118,7 @@ class Context:
     def default_ubo(self, binding: int) -> "Buffer":
         b = C.c_int()
         check(self.lib.cwa_default_ubo(self.h, binding, C.byref(b)))
-        sizes = {1: 16, 2: 32, 3: 32, 4: 32}
+        sizes = {1: 16, 2: 32, 3: 32, 4: 48}
         return Buffer(self, handle=b.value, nbytes=sizes[binding])
 
     def set_constants(self, mass=0.02, smoothing_coeff=2.0, visc=3000.0, resting_rho=1000.0):

@@ -153,6 +153,14 @@ SIGNATURES = {
     "cwa_slab_group_step": (_I, [C.POINTER(_P), _IP, _I, _I, _I]),
     "cwa_slab_counts": (_I, [_P, _I, _IP]),
     "cwa_slab_counts_async": (_I, [_P, _I, _P]),
+    "cwa_gl_available": (_I, []),
+    "cwa_gl_register_buffer": (_I, [_P, C.c_uint, _IP]),
+    "cwa_gl_map_buffer": (_I, [_P, _I, _IP]),
+    "cwa_gl_unmap": (_I, [_P, _I]),
+    "cwa_gl_register_image": (_I, [_P, C.c_uint, C.c_uint, _IP]),
+    "cwa_gl_copy_wave_to_image": (_I, [_P, _I, _I, _I]),
+    "cwa_gl_unregister": (_I, [_P, _I]),
+    "cwa_wave_reinit_from_rgba8": (_I, [_P, _I, _P, _I, _I]),
     "cwa_wave_create_block": (_I, [_P, _I, _I, _I, _I, _I, _I, _IP]),
     "cwa_wave_last_row_buffer": (_I, [_P, _I, _I, _IP]),
     "cwa_sph2_create": (_I, [_P, _I, _I, _I, _IP]),

@@ -27,6 +27,14 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: cannot build libcwa_b200.so")
 
 
+def _gl_flags():
+    """cuda_gl_interop.h includes <GL/gl.h>; machines without OpenGL headers (this image) get the two-typedef stand-in."""
+    for d in ("/usr/include", "/usr/local/include", "/usr/include/x86_64-linux-gnu"):
+        if os.path.exists(os.path.join(d, "GL", "gl.h")):
+            return []
+    return ["-I", os.path.join(CSRC, "gl_compat")]
+
+
 def _headers():
     return [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))] + [os.path.join(HERE, "..", "include", "cwa_b200.h")]
 
@@ -49,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for s in SOURCES:
         src, obj = os.path.join(CSRC, s), os.path.join(OBJ, s[:-3] + ".o")
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_t):
-            jobs.append((s, [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]))
+            jobs.append((s, [nvcc] + NVCC_FLAGS + _gl_flags() + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]))
 
     def run(job):
         return job[0], subprocess.run(job[1], capture_output=True, text=True)

@@ -157,6 +157,7 @@ extern "C" void cwa_destroy(cwa_ctx* ctx)
     for (size_t i = 0; i < ctx->grids.size(); i++) if (ctx->grids[i].live) cwa_grid_destroy(ctx, (int)i);
     for (auto& b : ctx->buffers) if (b.live && b.owned && b.ptr) cudaFree(b.ptr);
     if (ctx->scan_ticket) cudaFree(ctx->scan_ticket);
+    cudaFree(ctx->multi.flags); cudaFree(ctx->multi.pos); cudaFree(ctx->multi.ticket);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->ev_pipe[i]);

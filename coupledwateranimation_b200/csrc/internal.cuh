@@ -232,7 +232,27 @@ struct CtxTuning {
 
 struct SlabObj;
 
+// scratch of the multi-GPU primitives in multi.cu (flags, scan output, scan state); owned by the context, freed in cwa_destroy
+struct MultiScratch {
+    int* flags = nullptr;
+    int* pos = nullptr;           // n + 1 entries
+    int* ticket = nullptr;
+    unsigned long long* state = nullptr;
+    size_t cap = 0, tiles = 0;
+};
+
+// a GL object registered with cudaGraphicsGLRegister* (interop.cu)
+struct GlResource {
+    bool live = false;
+    bool is_image = false;
+    void* res = nullptr;              // cudaGraphicsResource_t
+    bool mapped = false;
+    cwa_buf mapped_buf = -1;
+};
+
 struct cwa_ctx {
+    MultiScratch multi;
+    std::vector<GlResource> gl_resources;
     CtxTuning tune;
     std::vector<SlabObj*> slabs;
     bool profiling = false;

@@ -1,8 +1,11 @@
-// multi.cu -- device primitives of the multi-GPU decomposition: selecting ghost
-// particles near a slab face and splitting off particles that migrated out of the slab.
-// Both are a STABLE copy_if on one coordinate of the particle position (flags -> the same
-// single-pass look-back scan the grid uses -> 64-byte record copy), so results do not depend on
-// scheduling and the packed send buffers are contiguous (one NCCL send per neighbour).
+// multi.cu -- stand-alone device primitives of the multi-GPU decomposition; the per-frame protocol built on the same
+// message layout lives in slab.cu.
+//   cwa_particles_copy_if / cwa_slab_compact: STABLE copy_if on one coordinate of the particle position (flags -> the single-pass
+//     look-back scan the grid uses -> 64-byte record copy): results do not depend on scheduling.
+//   cwa_slab_pack / the pack fused into the integrate pass: message slots are handed out with atomicAdd, so the ORDER of the
+//     migrants and ghosts inside a message depends on scheduling.  The set does not.  Adopted particles get buffer slots in that
+//     order and the grid's canonical order is ascending slot inside a cell, so the FP summation order of the neighbour loops --
+//     and with it the last bits of a multi-GPU run -- can differ from run to run; single-GPU runs and checkpoints stay bit-exact.
 #include "internal.cuh"
 #include <math_constants.h>
 
@@ -44,26 +47,25 @@ multi_scatter_kernel(const float4* __restrict__ aos, int n, const int* __restric
     if (d < out_capacity) out[(size_t)d * 4 + q] = __ldg(aos + (size_t)i * 4 + q);
 }
 
-struct MultiScratch {
-    int* flags = nullptr;
-    int* pos = nullptr;           // n + 1 entries
-    int* ticket = nullptr;
-    unsigned long long* state = nullptr;
-    size_t cap = 0, tiles = 0;
-};
-
 static MultiScratch* multi_scratch(cwa_ctx* ctx, int n)
 {
-    static MultiScratch table[64];                 // one per device
-    MultiScratch* s = &table[ctx->device & 63];
+    MultiScratch* s = &ctx->multi;
     if ((size_t)n <= s->cap) return s;
-    if (s->flags) { cudaFree(s->flags); cudaFree(s->pos); cudaFree(s->ticket); }
-    s->cap = (size_t)n + (size_t)n / 4 + 1024;
-    s->tiles = scan_num_tiles((int)s->cap);
-    if (cudaMalloc(&s->flags, s->cap * 4) != cudaSuccess) return nullptr;
-    if (cudaMalloc(&s->pos, (s->cap + 1) * 4) != cudaSuccess) return nullptr;
-    if (cudaMalloc(&s->ticket, 16 + s->tiles * 8) != cudaSuccess) return nullptr;
-    s->state = (unsigned long long*)((char*)s->ticket + 16);
+    cudaStreamSynchronize(ctx->stream);                      // nothing in flight still uses the old arrays
+    cudaFree(s->flags); cudaFree(s->pos); cudaFree(s->ticket);
+    *s = MultiScratch();
+    MultiScratch t;
+    const size_t cap = (size_t)n + (size_t)n / 4 + 1024;
+    t.tiles = scan_num_tiles((int)cap);
+    if (cudaMalloc(&t.flags, cap * 4) != cudaSuccess || cudaMalloc(&t.pos, (cap + 1) * 4) != cudaSuccess ||
+        cudaMalloc(&t.ticket, 16 + t.tiles * 8) != cudaSuccess) {
+        (void)cudaGetLastError();
+        cudaFree(t.flags); cudaFree(t.pos); cudaFree(t.ticket);
+        return nullptr;
+    }
+    t.state = (unsigned long long*)((char*)t.ticket + 16);
+    t.cap = cap;                                             // only now: every array exists
+    *s = t;
     return s;
 }
 
@@ -299,6 +301,10 @@ extern "C" int cwa_slab_compact(cwa_ctx* ctx, cwa_buf particles, int n_owned, cw
     BufferObj* s = get_buffer(ctx, scratch);
     CWA_CHECK(p && s && n_live && (size_t)n_owned * 64 <= p->bytes && (size_t)n_owned * 64 <= s->bytes, "cwa_slab_compact: bad buffers");
     *n_live = 0;
+    for (auto& so : ctx->sphs)
+        CWA_CHECK(!(so.live && so.particles == particles && so.slab_packed.valid),
+                  "cwa_slab_compact: the integrate pass already packed the next exchange's messages from this buffer (cwa_sph_step_slab): "
+                  "compacting now would drop the migrants it marked; compact before the step or after cwa_slab_pack");
     if (n_owned == 0) return 0;
     MultiScratch* sc = multi_scratch(ctx, n_owned);
     CWA_CHECK(sc, "cwa_slab_compact: out of device memory");

@@ -172,7 +172,24 @@ extern "C" int cwa_checkpoint_load(cwa_ctx* ctx, cwa_sph hs, cwa_wave hw, const 
             CWA_CHECK(false, "cwa_checkpoint_load: corrupt triple-buffer bookkeeping in '%s'", path);
         }
     }
+    if (w->row0 != 0 || w->h != w->h_global) {                      // same rule as cwa_checkpoint_save: a row block is not a whole field
+        std::fclose(f);
+        CWA_CHECK(false, "cwa_checkpoint_load: the wave object is a row block of a larger field");
+    }
     const size_t pbytes = (size_t)s->n * 64, ibytes = (size_t)w->w * w->h * w->ch * 4;
+    // the whole payload must be there BEFORE any live object is touched: a truncated file leaves the state as it was
+    {
+        const long here = std::ftell(f);
+        bool size_ok = here >= 0 && std::fseek(f, 0, SEEK_END) == 0;
+        const long end = size_ok ? std::ftell(f) : -1;
+        size_ok = size_ok && end >= 0 && (unsigned long long)end >= (unsigned long long)h.header_bytes + pbytes + 3ull * ibytes &&
+                  std::fseek(f, here, SEEK_SET) == 0;
+        if (!size_ok) {
+            std::fclose(f);
+            CWA_CHECK(false, "cwa_checkpoint_load: '%s' is truncated (needs %llu bytes); nothing was restored", path,
+                      (unsigned long long)h.header_bytes + pbytes + 3ull * ibytes);
+        }
+    }
     std::vector<char> host(pbytes > ibytes ? pbytes : ibytes);
     bool ok = true;
     if (pbytes) {

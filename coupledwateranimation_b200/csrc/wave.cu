@@ -461,6 +461,7 @@ extern "C" int cwa_wave_destroy(cwa_ctx* ctx, cwa_wave h)
     WaveObj* w = get_wave(ctx, h);
     CWA_CHECK(w, "invalid wave handle %d", h);
     CWA_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 2; i++) CWA_CUDA(cudaStreamSynchronize(ctx->side_stream[i]));
     for (int i = 0; i < 3; i++) {
         cudaFree(w->image[i]);
         if (BufferObj* b = get_buffer(ctx, w->image_buf[i])) b->live = false;
@@ -554,10 +555,15 @@ extern "C" int cwa_wave_resize(cwa_ctx* ctx, cwa_wave h, int nw, int nh)
     WaveObj* w = get_wave(ctx, h);
     CWA_CHECK(w, "invalid wave handle %d", h);
     CWA_CHECK(nw >= 1 && nh >= 1, "cwa_wave_resize: bad size");
-    CWA_CUDA(cudaStreamSynchronize(ctx->stream));
-    for (int i = 0; i < 3; i++) { cudaFree(w->image[i]); w->image[i] = nullptr; }
-    cudaFree(w->imageT); w->imageT = nullptr; w->imageT_of = -1;
     CWA_CHECK(w->row0 == 0 && w->h == w->h_global, "cwa_wave_resize: not supported on a row-block wave object");
+    CWA_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 2; i++) CWA_CUDA(cudaStreamSynchronize(ctx->side_stream[i]));   // a pipelined stencil step / grid clear may still run there
+    w->tma_ok = false;
+    for (int i = 0; i < 3; i++) {
+        cudaFree(w->image[i]); w->image[i] = nullptr;
+        if (BufferObj* b = get_buffer(ctx, w->image_buf[i])) { b->ptr = nullptr; b->bytes = 0; }    // until wave_alloc_images re-points them
+    }
+    cudaFree(w->imageT); w->imageT = nullptr; w->imageT_of = -1;
     w->w = nw; w->h = nh; w->h_global = nh;
     return wave_alloc_images(ctx, w);                                // ImageTexture::Resize: new storage, contents cleared
 }

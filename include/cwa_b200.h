@@ -258,6 +258,23 @@ CWA_API int cwa_slab_group_step(cwa_ctx* const* ctxs, const cwa_slab* slabs, int
 CWA_API int cwa_slab_counts(cwa_ctx* ctx, cwa_slab sl, int* counts);
 CWA_API int cwa_slab_counts_async(cwa_ctx* ctx, cwa_slab sl, int* pinned_counts4);     /* first four of the above, valid after cwa_synchronize */
 
+/* ---- CUDA-GL interop hand-off (csrc/interop.cu).  The renderer keeps its GL objects; none of this is on the timed path.
+ * cwa_gl_available() = 1 when the library was built with cuda_gl_interop.h; the calls need a current GL context on the calling thread
+ * and fail with the CUDA error text otherwise. */
+CWA_API int cwa_gl_available(void);
+/* the particle SSBO / vertex buffer of init_particles() (Main.cpp:779-790): register once, map every frame, build the SPH object on
+ * the cwa_buf the map returns (same handle every frame), unmap before the draw calls */
+CWA_API int cwa_gl_register_buffer(cwa_ctx* ctx, unsigned gl_buffer, int* resource);
+CWA_API int cwa_gl_map_buffer(cwa_ctx* ctx, int resource, cwa_buf* out);
+CWA_API int cwa_gl_unmap(cwa_ctx* ctx, int resource);
+/* a wave level's GL texture (ImageTexture::GetTexture(), RGBA32F as shipped or R32F; gl_target 0 = GL_TEXTURE_2D) and the per-frame
+ * copy that replaces display()'s GetReadImage(0).BindTextureUnit() (Main.cpp:413) */
+CWA_API int cwa_gl_register_image(cwa_ctx* ctx, unsigned gl_texture, unsigned gl_target, int* resource);
+CWA_API int cwa_gl_copy_wave_to_image(cwa_ctx* ctx, int resource, cwa_wave w, int image);
+CWA_API int cwa_gl_unregister(cwa_ctx* ctx, int resource);
+/* ReinitFromTexture (StencilImage2DTripleBuffered.cpp:61-77) from the decoded bytes of an RGBA8 init texture (init-textures/*.png) */
+CWA_API int cwa_wave_reinit_from_rgba8(cwa_ctx* ctx, cwa_wave w, const unsigned char* rgba8, int tw, int th);
+
 /* ---- 2-D Koschier SPH on the uniform grid: SphUgrid (SphWave2D/StencilBuffer.cpp:138-179) ------ */
 CWA_API int cwa_sph2_create(cwa_ctx* ctx, int n, int variant, cwa_grid grid, cwa_sph2* out); /* Init + Reinit (MODE_INIT) */
 CWA_API int cwa_sph2_destroy(cwa_ctx* ctx, cwa_sph2 s);

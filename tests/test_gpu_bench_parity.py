@@ -1,0 +1,138 @@
+"""Parity ON the configurations bench.py times ("the benchmarked configuration is not parity-tested"):
+
+* C4 exactly as bench.py builds it -- 1 003 520 particles, the 384 x 31 x 384 grid of ~h cells with the clamped y extent, AS_SHIPPED
+  coupling, frames pipelined inside one cwa_coupled_step call -- compared with the oracle over ALL particles, frame 1 at 1e-4, later
+  frames at 1e-3 (rounding differences of the summation order are amplified by the blast of the over-dense sheet: measured 3e-7 after
+  one frame, 3e-5 after two, ~1e-3 after eight, tools/dist_diag.py), plus a variant with thousands of particles ABOVE the grid's y
+  extent (clamped into the top cell layer, UniformGrid2D/ugrid_particles_cs.glsl:97-103);
+* C3 (Wave2D_cs.glsl 4096^2) bit-exact over the whole field, several steps;
+* D (the shipped scene: 20 480 particles all-pairs + 64^2 RGBA wave, Main.cpp:28-35) for 1000 frames: mass (finite-particle count),
+  kinetic energy and height-field RMS statistics of the CUDA run against the oracle run, within 1 % (north-star).
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from util import assert_close, rel_err
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _compare_particles(got, ref, rtol, what, outlier_frac=0.0):
+    nan_r = np.isnan(ref["pos"][:, :3]).any(1)
+    nan_g = np.isnan(got["pos"][:, :3]).any(1)
+    assert np.array_equal(nan_r, nan_g), f"{what}: NaN sets differ ({int(nan_r.sum())} vs {int(nan_g.sum())})"
+    ok = ~nan_r
+    worst = {}
+    for name, a, b, scale in (("rho", got["extras"][ok, 0], ref["extras"][ok, 0], None), ("pres", got["extras"][ok, 1], ref["extras"][ok, 1], None),
+                              ("force", got["force"][ok, :3], ref["force"][ok, :3], None), ("pos", got["pos"][ok, :3], ref["pos"][ok, :3], 1e-3),
+                              ("vel", got["vel"][ok, :3], ref["vel"][ok, :3], None)):
+        e = rel_err(a, b, scale)
+        e = e[np.isfinite(e)]
+        worst[name] = float(e.max()) if e.size else 0.0
+        bad = float((e > rtol).mean()) if e.size else 0.0
+        assert bad <= outlier_frac, f"{what}: {name} max rel err {worst[name]:.3e}, {bad * 100:.4f} % of entries above {rtol:.0e}"
+    assert np.array_equal(got["force"][ok, 3], ref["force"][ok, 3]), f"{what}: force.w carried bit for bit"
+    return worst
+
+
+def _bench_scene(cwa, ctx, oracle, lift=0):
+    import bench
+    grid, sph, wave = bench.build_scene(cwa, ctx)
+    oc, n = bench.oracle_scene(oracle)
+    assert n == bench.N_PARTICLES == 1003520 and grid.num_cells == (384, 31, 384)
+    if lift:
+        # a few thousand particles above the grid's y extent (0.30): ComputeCellIndex clamps them into the top layer
+        p = sph.download()
+        rng = np.random.default_rng(4)
+        ids = rng.choice(p.size, lift, replace=False)
+        p["pos"][ids, 1] = rng.uniform(0.31, 0.62, lift).astype(np.float32)
+        p["pos"][ids[: lift // 2], 0] += np.float32(0.003)                        # some of them close enough to interact up there
+        sph.upload(p)
+    if lift:
+        oc.particles[:] = sph.download()
+    else:
+        assert np.array_equal(sph.download().view(np.uint8), np.ascontiguousarray(oc.particles).view(np.uint8)), "make_cube bytes"
+    return bench, grid, sph, wave, oc
+
+
+def test_c4_as_benchmarked_matches_the_oracle_on_every_particle(cwa, ctx, oracle):
+    bench, grid, sph, wave, oc = _bench_scene(cwa, ctx, oracle)
+    sph.coupled_step(wave, 1, bench.COUPLING); oc.step(1)
+    w = _compare_particles(sph.download(), oc.particles, 1e-4, "C4 frame 1")
+    assert np.array_equal(wave.read_role(0).view(np.uint32), oc.wave(0).view(np.uint32)), "wave level bit-exact"
+    # frames 2..10 in ONE call: count-ahead and the side-stream stencil are active (pipeline 3, the bench's path)
+    sph.coupled_step(wave, 9, bench.COUPLING); oc.step(9)
+    assert wave.state()["tex_unit0"] == oc.sampled_image()
+    assert np.array_equal(wave.read_role(0).view(np.uint32), oc.wave(0).view(np.uint32)), "wave level bit-exact after 10 frames"
+    _compare_particles(sph.download(), oc.particles, 1e-3, "C4 frame 10", outlier_frac=5e-4)
+    oc.close()
+
+
+def test_c4_with_particles_above_the_grid_extent(cwa, ctx, oracle):
+    bench, grid, sph, wave, oc = _bench_scene(cwa, ctx, oracle, lift=6000)
+    assert (sph.download()["pos"][:, 1] > 0.30).sum() == 6000
+    sph.coupled_step(wave, 1, bench.COUPLING); oc.step(1)
+    _compare_particles(sph.download(), oc.particles, 1e-4, "C4 + lifted particles, frame 1")
+    sph.coupled_step(wave, 2, bench.COUPLING); oc.step(2)
+    _compare_particles(sph.download(), oc.particles, 1e-3, "C4 + lifted particles, frame 3", outlier_frac=1e-4)
+    oc.close()
+
+
+def test_c3_full_field_is_bit_exact(cwa, ctx, oracle):
+    n = 4096
+    wave = cwa.StencilImage2DTripleBuffered(ctx, n, n, 1, cwa.WAVE_SIMP)
+    u0 = oracle.wave_init(n, n, 1, oracle.WAVE_SIMP)
+    assert np.array_equal(wave.read_role(0).view(np.uint32), u0.view(np.uint32)), "Init(): both read levels hold the bump"
+    rng = np.random.default_rng(3)
+    u0 = u0 + (0.05 * rng.standard_normal((n, n))).astype(np.float32)          # a non-trivial field everywhere, borders included
+    u1 = (0.05 * rng.standard_normal((n, n))).astype(np.float32)
+    wave.write_role(0, u0); wave.write_role(1, u1)
+    for step in range(3):
+        wave.Compute(1)
+        nxt = oracle.wave_evolve(u0, u1, oracle.WAVE_SIMP, 0.01, 0.9995, 0.001)
+        got = wave.read_role(0)
+        assert np.array_equal(got.view(np.uint32), nxt.view(np.uint32)), f"C3 step {step + 1}: all 16 777 216 cells bit-exact"
+        u0, u1 = nxt, u0
+
+
+def _stats(p, wave_field):
+    pos, vel = p["pos"][:, :3].astype(np.float64), p["vel"][:, :3].astype(np.float64)
+    fin = np.isfinite(pos).all(1) & np.isfinite(vel).all(1)
+    ke = 0.5 * 0.02 * float((vel[fin] ** 2).sum())
+    return {"finite": int(fin.sum()), "kinetic": ke, "wave_rms": float(np.sqrt(np.mean(wave_field.astype(np.float64) ** 2))),
+            "mean_y": float(pos[fin, 1].mean()), "rho_mean": float(p["extras"][fin, 0].astype(np.float64).mean())}
+
+
+def test_default_scene_1000_frames_statistics(cwa, ctx, oracle):
+    """Config 1 of BASELINE.json: the shipped scene, 1000 headless frames, AS_SHIPPED coupling, all-pairs passes.
+    Trajectories are chaotic (the sheet blasts apart in the first frames), so the check is statistical, as the north-star words it:
+    mass conserved (same number of finite particles; NaN particles are the reference's own), kinetic energy and
+    height-field RMS within 1 %.  The wave field does not depend on the particles: it must stay bit-exact."""
+    prm = oracle.default_params3()
+    ctx.set_params_from_oracle(prm)
+    p = oracle.make_cube(64, 5, 64, prm)
+    oc = oracle.Coupled(p.size, 64, 64, 4, prm, oracle.COUPLING_AS_SHIPPED)
+    oc.particles[:] = p
+    sph = cwa.Sph(ctx, p.size, None, particles=p)
+    wave = cwa.StencilImage2DTripleBuffered(ctx, 64, 64, 4, cwa.WAVE_COUPLED)
+    hist = []
+    for block in range(10):
+        sph.coupled_step(wave, 100, cwa.COUPLING_AS_SHIPPED)
+        oc.step(100)
+        g, r = _stats(sph.download(), wave.read_role(0)[..., 0]), _stats(oc.particles, oc.wave(0)[..., 0])
+        hist.append((g, r))
+        assert np.array_equal(wave.read_role(0).view(np.uint32), oc.wave(0).view(np.uint32)), f"wave field after {100 * (block + 1)} frames"
+    print("\nframes  finite(cuda/oracle)  kinetic(cuda/oracle)  wave_rms")
+    for k, (g, r) in enumerate(hist):
+        print(f"{100 * (k + 1):5d}   {g['finite']:6d} / {r['finite']:6d}    {g['kinetic']:.6e} / {r['kinetic']:.6e}   {g['wave_rms']:.6e}")
+    g, r = hist[-1]
+    assert g["wave_rms"] == r["wave_rms"]
+    assert abs(g["finite"] - r["finite"]) <= 0.01 * r["finite"], (g, r)
+    assert abs(g["kinetic"] - r["kinetic"]) <= 0.01 * r["kinetic"], (g, r)
+    assert abs(g["mean_y"] - r["mean_y"]) <= 0.01 * abs(r["mean_y"]) + 1e-4, (g, r)
+    oc.close()
