@@ -23,6 +23,7 @@ void cwa_set_error(const char* fmt, ...);
         cudaError_t _e = (expr);                                                                \
         if (_e != cudaSuccess) {                                                                \
             cwa_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            (void)cudaGetLastError();   /* reported: a non-sticky error must not resurface in a later, unrelated call */ \
             return -2;                                                                          \
         }                                                                                       \
     } while (0)
@@ -156,6 +157,7 @@ struct SphObj {
     float2 *pairV = nullptr;                     //                                   (visc.y, visc.z)
     int   *nbr_list = nullptr, *nbr_count = nullptr;   // neighbour lists of the density pass ([slot][K]) and true counts
     bool   nbr_lists_valid = false;
+    bool   nbr_rows_fmt = false;               // nbr_list holds row masks ([tile of 32][9 rows][lane] (first slot, accept mask)) instead of index lists
     int    nbr_k_alloc = 0, nbr_k_used = 0;                 // list capacity the array was sized for / the density pass built the lists with
     int   *heavy_queue = nullptr;                           // targets finished one warp each: [0,cap) density pass, [cap,2cap) force pass
     int   *heavy_cnt = nullptr;                             // the two queue counters (density, force); reset by the reorder kernel of every snapshot
@@ -173,6 +175,14 @@ struct SphObj {
         int n_owned = 0, cap_mig = 0, cap_ghost = 0;
         float z_lo = 0.f, z_hi = 0.f, band = 0.f;
     } slab_packed;
+    // CUDA graphs of one all-pairs coupled frame (cwa_coupled_step, tuning "graph"): the shipped scene is 6 launches of a few
+    // microseconds each, i.e. launch latency; one graph per state of the wave rotation / sampler binding (they cycle with period 3)
+    struct FrameGraph {
+        bool valid = false;
+        long long key[16] = {};
+        void* exec = nullptr;                               // cudaGraphExec_t
+        unsigned nodes = 0;
+    } frame_graph[6];
     unsigned long long consts_epoch = 0;                    // params_epoch the prepared constants were derived from
     void*  consts = nullptr;                     // Sph3Const prepared on the device once per dispatch
     bool snapshot_valid = false;
@@ -317,6 +327,7 @@ int  stencil1d_dispatch_mode(cwa_ctx* ctx, int handle, int mode, int shader);   
 void wave_touch_buffer(cwa_ctx* ctx, cwa_buf b, bool raw);             // a buffer was written through the Buffer API / its raw pointer handed out
 int  wave_step_internal(cwa_ctx* ctx, WaveObj* w);
 int  wave_image_with_unit(const WaveObj* w, int unit);                 // physical image bound to image unit 0 (newest) / 1 / 2 (next output)
+void wave_pingpong_internal(WaveObj* w);                               // PingPong(): host bookkeeping only
 int  wave_dispatch_mode(cwa_ctx* ctx, WaveObj* w, int mode);           // kernel for uMode on units 0/1/2, no rotation                   // one EVOLVE dispatch + PingPong
 // slab pack fused into the integrate pass (multi.cu: cwa_sph_step_slab); all-zero = off
 struct SlabPackArgs {

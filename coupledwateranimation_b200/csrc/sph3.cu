@@ -671,6 +671,176 @@ sph3_density_list_kernel(const float4* __restrict__ posS, const float4* __restri
     nbr_count[slot] = cnt;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Row-mask neighbour kernels (nb_config 8, the default).  Same thread-per-target walk as the list kernels above, rebuilt around
+// what ncu showed about sph3_density_list_kernel on C4 (profiles/r2/density_r1_vs_r2.md): the L1 data pipe, not the issue slots,
+// was the limit (l1tex wavefronts 77 % of peak) and 45 % of its wavefronts were the neighbour-list appends -- one 4-byte store per
+// accepted pair, every lane into its own 256-byte list row, i.e. one wavefront and one 32-byte sector per ENTRY.
+//  * Neighbours are recorded as one 32-bit ACCEPT MASK per row of the query (bit b = slot first + b of the row), kept in a register
+//    while the row is walked: accepting a candidate is one predicated OR, no address arithmetic, no store.  A target leaves at most
+//    nine (first slot, mask) pairs, written once, coalesced ([tile of 32 targets][row][lane]): 72 bytes per target instead of
+//    ~54 scattered ones, and the force pass reads them back with nine coalesced loads instead of 32-line index gathers.
+//  * ONE loop over all rows of the target instead of a loop nest.  In a nest every lane waits at the end of each row for the longest row of the
+//    warp (cost = sum over rows of the warp-wide maximum); in the flat loop a lane moves on to its next row on its own (cost = the
+//    warp-wide maximum of the TOTAL, which varies far less than the individual rows).  The row advance is branch-free (in almost
+//    every trip SOME lane of the warp advances: a branch would run both sides every time with a handful of lanes active).
+//  * two candidates per trip (one 256-bit load = one sector), the next pair loaded before the current one is used; rows are six candidates
+//    long on average, so four-wide trips spent a third of their slots outside the row.
+//  * the query is narrowed per row with the target's position inside its cell: a neighbour row (i', j') whose footprint is farther than h
+//    in (x, y) is dropped, and its k range keeps cell ck -+ 1 only when that cell's nearest point is closer than h.  Cells of ~h: 20.6 of
+//    the 27 cells survive on average.  The test is conservative (margin 2.5e-3 h against the rounding of the hash), and a dropped cell only
+//    holds particles farther than h, so the accepted set -- and with it every result -- is unchanged.
+// Targets the scheme does not cover -- more than EXTREME_CANDIDATES candidates, a row longer than 31 slots, cells smaller than h
+// (more than 3 x 3 rows) -- go to the heavy kernels (one warp per target, generic loops).
+// ---------------------------------------------------------------------------------------------
+constexpr int ROW_MASK_BITS = 31;         // longest row a mask records: with an odd first slot the pair loop shifts by (length + 1) - 1 at most
+struct FlatRows { int b[RT_ROWS], e[RT_ROWS]; int total; bool heavy; };
+
+__device__ __forceinline__ FlatRows flat_rows_load(const GridView& g, const int* __restrict__ offset, float x, float y, float z, float h)
+{
+    FlatRows fr;
+    const float hm = h * (1.0f + 2.5e-3f), hx = h * 1.25f;
+    const bool fast = hm <= g.cell[0] && hm <= g.cell[1] && hm <= g.cell[2] && g.cell[0] <= hx && g.cell[1] <= hx && g.cell[2] <= hx;
+    fr.total = 0;
+#pragma unroll
+    for (int r = 0; r < RT_ROWS; r++) { fr.b[r] = 0; fr.e[r] = 0; }
+    if (!fast) {                                           // generic query: rows_load semantics (more than 3 x 3 rows -> heavy kernels)
+        const Query3 q = make_query(g, x, y, z, h);
+        const RowBounds rb = rows_load(g, offset, q);
+#pragma unroll
+        for (int r = 0; r < RT_ROWS; r++) { fr.b[r] = rb.b[r]; fr.e[r] = rb.e[r]; }
+        fr.total = rb.total; fr.heavy = rb.wide;
+    } else {
+        fr.heavy = false;
+        const int ci = approx_cell(x, g.min[0], g.inv_cell[0], 0.0f, g.n[0]);
+        const int cj = approx_cell(y, g.min[1], g.inv_cell[1], 0.0f, g.n[1]);
+        const int ck = approx_cell(z, g.min[2], g.inv_cell[2], 0.0f, g.n[2]);
+        const int kl = max(ck - 1, 0), kh = min(ck + 1, g.n[2] - 1);
+        // squared distance (minus the margin) from the target to the lower / upper neighbour slab of its cell, per axis
+        const float m = 2.5e-3f * h, h2 = h * h;
+        float dl[3], dh[3];
+        const float pos[3] = {x, y, z};
+        const int cc[3] = {ci, cj, ck};
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const float lo = fmaf((float)cc[a], g.cell[a], g.min[a]);
+            const float l = fmaxf(pos[a] - lo - m, 0.0f), u = fmaxf(lo + g.cell[a] - pos[a] - m, 0.0f);
+            dl[a] = l * l; dh[a] = u * u;
+        }
+#pragma unroll
+        for (int r = 0; r < RT_ROWS; r++) {
+            const int di = r / 3 - 1, dj = r % 3 - 1;
+            const int i = ci + di, j = cj + dj;
+            const float s = (di < 0 ? dl[0] : (di > 0 ? dh[0] : 0.0f)) + (dj < 0 ? dl[1] : (dj > 0 ? dh[1] : 0.0f));
+            if (i >= 0 && i < g.n[0] && j >= 0 && j < g.n[1] && s < h2) {
+                const int k0 = (s + dl[2] < h2) ? kl : ck;
+                const int k1 = (s + dh[2] < h2) ? kh : ck;
+                const int base = (i * g.n[1] + j) * g.kstride;
+                fr.b[r] = __ldg(offset + base + k0);
+                fr.e[r] = __ldg(offset + base + k1 + 1);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RT_ROWS; r++) fr.total += fr.e[r] - fr.b[r];
+    }
+#pragma unroll
+    for (int r = 0; r < RT_ROWS; r++) fr.heavy = fr.heavy || (fr.e[r] - fr.b[r] > ROW_MASK_BITS);
+    return fr;
+}
+
+// (first slot, accept mask) pairs of a target: [tile of 32 targets][row][lane]
+__device__ __forceinline__ int2* rows_of(int2* nbr_rows, int slot) { return nbr_rows + ((size_t)(slot >> 5) * RT_ROWS) * 32 + (slot & 31); }
+
+template <bool LOCAL>
+__global__ void __launch_bounds__(TILE_P)
+sph3_density_flat_kernel(const float4* __restrict__ posS, const float4* __restrict__ velS, float4* __restrict__ pack,
+                         int2* __restrict__ nbr_rows, int* __restrict__ nbr_count,
+                         int* __restrict__ heavy_queue, int* __restrict__ heavy_count,
+                         int n_max, GridView g, const int* __restrict__ offset, const Sph3Const* __restrict__ cc, TexView tex,
+                         const int extreme_candidates)
+{
+    __shared__ int2 tab[(RT_ROWS + 1) * TILE_P];       // non-empty rows of every target, compacted: (first slot, end slot), later (first slot, mask)
+    const int tid = threadIdx.x;
+    const int slot = blockIdx.x * TILE_P + tid;
+    const int n = min(n_max, __ldg(offset + g.num_cells));   // inserted particles
+    if (slot >= n) return;
+    const float h = cc->h, accept_r2 = cc->accept_r2, h2 = cc->h2, poly6 = cc->poly6;
+    const float4 p = __ldg(posS + slot);
+    const FlatRows fr = flat_rows_load(g, offset, p.x, p.y, p.z, h);
+    if (fr.heavy || fr.total > extreme_candidates) {   // clump, long row or generic wide query: sph3_density_heavy_kernel, one warp per target
+        const int qi = atomicAdd(heavy_count, 1);
+        if (qi < n_max) heavy_queue[qi] = slot;
+        return;
+    }
+    int nr = 0;
+#pragma unroll
+    for (int r = 0; r < RT_ROWS; r++)
+        if (fr.e[r] > fr.b[r]) { tab[nr * TILE_P + tid] = make_int2(fr.b[r], fr.e[r]); nr++; }
+
+    float rho = 0.0f;
+    unsigned mask = 0u;
+    // One candidate: accepted <=> inside the row (head: j >= bound, tail: j < bound) and r2 <= accept_r2; the mask bit and the poly6
+    // weight hang on the same predicate, formed once -- nothing branches.
+    auto step = [&](const float4 qp, int j, int bound, unsigned bit, const bool head) {
+        const float r2 = cwa_len3sq(p.x - qp.x, p.y - qp.y, p.z - qp.z);
+        const float hd = h2 - r2;
+        float d;
+        if (head)
+            asm("{\n\t.reg .pred v, q;\n\tsetp.ge.s32 v, %4, %5;\n\tsetp.le.and.f32 q, %2, %3, v;\n\t@q or.b32 %0, %0, %6;\n\t"
+                "selp.f32 %1, %7, 0f00000000, q;\n\t}"
+                : "+r"(mask), "=f"(d) : "f"(r2), "f"(accept_r2), "r"(j), "r"(bound), "r"(bit), "f"(hd));
+        else
+            asm("{\n\t.reg .pred v, q;\n\tsetp.lt.s32 v, %4, %5;\n\tsetp.le.and.f32 q, %2, %3, v;\n\t@q or.b32 %0, %0, %6;\n\t"
+                "selp.f32 %1, %7, 0f00000000, q;\n\t}"
+                : "+r"(mask), "=f"(d) : "f"(r2), "f"(accept_r2), "r"(j), "r"(bound), "r"(bit), "f"(hd));
+        rho = fmaf(poly6, d * d * d, rho);
+    };
+    if (nr > 0) {
+        int2* tp = tab + tid;                          // the lane's current row in the table; rows are TILE_P entries apart
+        const int2* const tp_last = tab + (nr - 1) * TILE_P + tid;
+        int2 row = *tp;
+        int j = row.x & ~1;
+        f4x2 A = cwa_ldg256(posS + j), B = A;
+        // One stage: find where the NEXT pair comes from (the same row, or the first pair of the lane's next row), issue its load into
+        // NXT, then evaluate the pair held in CUR; a finished row leaves its mask in the table.  Two stages per trip ping-pong between
+        // A and B, so no pair is ever copied.  The table has one spare row: the entry behind the last row is read, never used.
+#define CWA_FLAT_STAGE(CUR, NXT)                                                                   \
+        {                                                                                          \
+            const bool adv = j + 2 >= row.y;                                                       \
+            const bool more = !adv || tp != tp_last;                                               \
+            int2* const tp_cur = tp;                                                               \
+            tp += adv ? TILE_P : 0;                                                                \
+            const int2 cand = *tp;                                                                 \
+            const int2 rown = adv ? cand : row;                                                    \
+            const int jn = adv ? (cand.x & ~1) : j + 2;                                            \
+            if (more) NXT = cwa_ldg256(posS + jn);                                                 \
+            const unsigned bit1 = 1u << (j + 1 - row.x);      /* j + 1 >= first slot, always */    \
+            step(CUR.a, j, row.x, bit1 >> 1, true);   /* the slot before an odd row start */       \
+            step(CUR.b, j + 1, row.y, bit1, false);   /* the slot after the row end (padded) */    \
+            if (adv) { tp_cur->y = (int)mask; mask = 0u; }                                         \
+            if (!more) break;                                                                      \
+            j = jn; row = rown;                                                                    \
+        }
+        while (true) {
+            CWA_FLAT_STAGE(A, B)
+            CWA_FLAT_STAGE(B, A)
+        }
+#undef CWA_FLAT_STAGE
+    }
+    float rho_out, prs_out;
+    density_epilogue<LOCAL>(*cc, tex, p.x, p.z, rho, rho_out, prs_out);
+    const float4 v = __ldg(velS + slot);
+    cwa_stg256(pack + 2 * (size_t)slot, make_float4(p.x, p.y, p.z, prs_out), make_float4(v.x, v.y, v.z, rho_out));
+    // the rows that accepted somebody, compacted
+    int2* out = rows_of(nbr_rows, slot);
+    int oc = 0;
+    for (int r = 0; r < nr; r++) {
+        const int2 e = tab[r * TILE_P + tid];
+        if (e.y != 0) { out[oc * 32] = e; oc++; }
+    }
+    nbr_count[slot] = oc;
+}
+
 // Candidate enumeration of the heavy kernels (one warp per target).  The rows of a query are short where particles pile up on a wall
 // (two or three cells along k, each crowded), so walking them one after the other leaves a single load in flight per lane and a partly
 // filled warp at every row end.  Instead lanes 0..nrows-1 fetch the row bounds, a warp scan turns the row lengths into a flat index
@@ -853,6 +1023,72 @@ sph3_force_list_kernel(const float4* __restrict__ pack, const int* __restrict__ 
 #pragma unroll
         for (int u = 0; u < 4; u++)
             if (j[u] != slot) pair_force(c, pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, qa[u], qb[u], fpx, fpy, fpz, fvx, fvy, fvz);
+    }
+    if (FUSED) {
+        finish_particle<LOCAL>(c, fa, slot, pa, pb, fpx, fpy, fpz, fvx, fvy, fvz);
+    } else {
+        pairP[slot] = make_float4(fpx, fpy, fpz, fvx);
+        pairV[slot] = make_float2(fvy, fvz);
+    }
+}
+
+// Force pass over the row masks of sph3_density_flat_kernel: neighbour sums of force_comp.glsl:74-88, one thread per target.
+// The (first slot, mask) pairs are copied into shared memory with coalesced loads; the lane then walks the set bits of its
+// masks in ONE loop (branch-free move to the next row), gathering each neighbour's (pos, p | vel, rho) record -- one sector --
+// one neighbour ahead of the pair evaluation.
+template <bool FUSED, bool LOCAL>
+__global__ void __launch_bounds__(TILE_P)
+sph3_force_rows_kernel(const float4* __restrict__ pack, const int2* __restrict__ nbr_rows, const int* __restrict__ nbr_count,
+                       int* __restrict__ heavy_queue, int* __restrict__ heavy_count,
+                       float4* __restrict__ pairP, float2* __restrict__ pairV, int n_max,
+                       GridView g, const int* __restrict__ offset, const Sph3Const* __restrict__ cc, FinishArgs fa)
+{
+    __shared__ int2 tab[(RT_ROWS + 1) * TILE_P];
+    const int tid = threadIdx.x;
+    const int slot = blockIdx.x * TILE_P + tid;
+    const int n = min(n_max, __ldg(offset + g.num_cells));   // inserted particles
+    if (slot >= n) return;
+    const int nr = __ldg(nbr_count + slot);
+    if (nr > RT_ROWS) {                                // marked by the density pass: sph3_force_heavy_kernel
+        const int qi = atomicAdd(heavy_count, 1);
+        if (qi < n_max) heavy_queue[qi] = slot;        // (a pass dispatched twice without a grid build in between re-queues: same results)
+        return;
+    }
+    const int2* rows = rows_of(const_cast<int2*>(nbr_rows), slot);
+#pragma unroll
+    for (int r = 0; r < RT_ROWS; r++)
+        if (r < nr) tab[r * TILE_P + tid] = __ldg(rows + r * 32);
+    const Sph3Const c = *cc;
+    const f4x2 own = cwa_ldg256(pack + 2 * (size_t)slot);
+    const float4 pa = own.a, pb = own.b;
+    float fpx = 0.f, fpy = 0.f, fpz = 0.f, fvx = 0.f, fvy = 0.f, fvz = 0.f;
+    if (nr > 0) {
+        const int2* tp = tab + tid;
+        const int2* const tp_last = tab + (nr - 1) * TILE_P + tid;
+        int2 row = *tp;                                // (first slot, mask != 0)
+        unsigned mask = (unsigned)row.y;
+        int j = row.x + __ffs((int)mask) - 1;
+        mask &= mask - 1u;
+        f4x2 A = cwa_ldg256(pack + 2 * (size_t)j), B = A;
+#define CWA_ROWS_STAGE(CUR, NXT)                                                                   \
+        {                                                                                          \
+            const bool adv = mask == 0u;                                                           \
+            const bool more = !adv || tp != tp_last;                                               \
+            tp += adv ? TILE_P : 0;                                                                \
+            const int2 cand = *tp;                                                                 \
+            if (adv) { row = cand; mask = (unsigned)cand.y; }                                      \
+            const int jn = row.x + __ffs((int)mask) - 1;                                           \
+            mask &= mask - 1u;                                                                     \
+            if (more) NXT = cwa_ldg256(pack + 2 * (size_t)jn);                                     \
+            if (j != slot) pair_force(c, pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, CUR.a, CUR.b, fpx, fpy, fpz, fvx, fvy, fvz); \
+            if (!more) break;                                                                      \
+            j = jn;                                                                                \
+        }
+        while (true) {
+            CWA_ROWS_STAGE(A, B)
+            CWA_ROWS_STAGE(B, A)
+        }
+#undef CWA_ROWS_STAGE
     }
     if (FUSED) {
         finish_particle<LOCAL>(c, fa, slot, pa, pb, fpx, fpy, fpz, fvx, fvy, fvz);
@@ -1270,15 +1506,16 @@ static int env_int(const char* name, int dflt, int lo, int hi)
 // Tuning knobs of the neighbour kernels.  Defaults come from the environment (CWA_NB_CONFIG, CWA_NB_CAP_D / _F,
 // CWA_FUSED_ORDER) the first time they are needed; cwa_set_tuning() overrides them at run time (used by the
 // parity tests to cover every kernel variant in one process).
-//   nb_config: 7 (default) = neighbour-list kernels, one thread per target, candidates through L1;
+//   nb_config: 8 (default) = neighbour-list kernels with the "flat" density pass (sph3_density_flat_kernel);
+//              7 = neighbour-list kernels with the round-1 density pass (row loop nest, four candidates per trip);
 //              0..6 = "lanes" kernels (targets per CTA x lanes per target: 0: 128x4, 1: 128x2, 2: 64x4, 3: 256x1,
 //              4: 128x1, 5: 64x2, 6: 256x2): neighbour rows staged in shared memory by TMA bulk copies, lanes of a
 //              target combined with warp shuffles, the force pass scans the candidates again
 //   cap_d / cap_f: staging budgets of the lanes kernels in slots (0 disables staging)
-constexpr int NB_CONFIG_DEFAULT = 7;
+constexpr int NB_CONFIG_DEFAULT = 8;
 constexpr int NBR_K_DEFAULT = 64;         // neighbour-list entries per target (self included); longer lists fall back to a grid scan
 constexpr int NBR_K_MAX = 256;
-static int nb_config(cwa_ctx* c) { if (c->tune.config < 0) c->tune.config = env_int("CWA_NB_CONFIG", NB_CONFIG_DEFAULT, 0, 7); return c->tune.config; }
+static int nb_config(cwa_ctx* c) { if (c->tune.config < 0) c->tune.config = env_int("CWA_NB_CONFIG", NB_CONFIG_DEFAULT, 0, 8); return c->tune.config; }
 static int dens_cap(cwa_ctx* c) { if (c->tune.cap_d < 0) c->tune.cap_d = env_int("CWA_NB_CAP_D", DENS_CAP_DEFAULT, 0, DENS_CAP_MAX); return c->tune.cap_d; }
 static int force_cap(cwa_ctx* c) { if (c->tune.cap_f < 0) c->tune.cap_f = env_int("CWA_NB_CAP_F", FORCE_CAP_DEFAULT, 0, FORCE_CAP_MAX); return c->tune.cap_f; }
 static bool fused_integrate(cwa_ctx* c) { if (c->tune.fused_integrate < 0) c->tune.fused_integrate = env_int("CWA_FUSED_INTEGRATE", 0, 0, 1); return c->tune.fused_integrate != 0; }
@@ -1295,7 +1532,7 @@ extern "C" int cwa_set_tuning(cwa_ctx* ctx, const char* key, int value)
     DeviceGuard _dg(ctx);
     CWA_CHECK(ctx && key, "null argument");
     const std::string k(key);
-    if (k == "nb_config") { CWA_CHECK(value >= 0 && value <= 7, "nb_config %d out of range", value); ctx->tune.config = value; }
+    if (k == "nb_config") { CWA_CHECK(value >= 0 && value <= 8, "nb_config %d out of range", value); ctx->tune.config = value; }
     else if (k == "nb_cap_d") { CWA_CHECK(value >= 0 && value <= DENS_CAP_MAX, "nb_cap_d %d out of range", value); ctx->tune.cap_d = value; }
     else if (k == "nb_cap_f") { CWA_CHECK(value >= 0 && value <= FORCE_CAP_MAX, "nb_cap_f %d out of range", value); ctx->tune.cap_f = value; }
     else if (k == "fused_order") { ctx->tune.fused_order = value ? 1 : 0; }
@@ -1335,7 +1572,14 @@ static int launch_force(cwa_ctx* ctx, SphObj* s, GridObj* g)
 // heavy kernels: a fixed grid of warps walks the device-side queue (no host round trip)
 static int heavy_grid(cwa_ctx* ctx) { return ctx->sm_count * 16; }     // x 4 warps: every resident warp slot of the GPU
 
-static int launch_density_list(cwa_ctx* ctx, SphObj* s, GridObj* g, TexView tex)
+// bytes of the neighbour structure of `n` targets: index lists [slot][K] (nb_config 7) or row masks [tile of 32][9 rows][lane] (nb_config 8)
+static size_t nbr_bytes(int n, int K)
+{
+    const size_t per = (size_t)K * 4 > (size_t)RT_ROWS * 8 ? (size_t)K * 4 : (size_t)RT_ROWS * 8;
+    return (((size_t)(n > 0 ? n : 1) + 31) / 32 * 32) * per;
+}
+
+static int launch_density_list(cwa_ctx* ctx, SphObj* s, GridObj* g, TexView tex, bool flat)
 {
     const Sph3Const* cc = (const Sph3Const*)s->consts;
     const int ntiles = ceil_div(s->n, TILE_P);
@@ -1345,11 +1589,22 @@ static int launch_density_list(cwa_ctx* ctx, SphObj* s, GridObj* g, TexView tex)
     if (s->nbr_k_alloc < K) {                            // the list capacity was raised after the object was created
         CWA_CUDA(cudaStreamSynchronize(ctx->stream));
         cudaFree(s->nbr_list);
-        CWA_CUDA(cudaMalloc(&s->nbr_list, (size_t)(s->capacity > 0 ? s->capacity : 1) * K * 4));
+        CWA_CUDA(cudaMalloc(&s->nbr_list, nbr_bytes(s->capacity, K)));
         s->nbr_k_alloc = K;
     }
     s->nbr_k_used = K;
-    { KScope k(ctx, KID_DENSITY);
+    s->nbr_rows_fmt = flat;
+    if (flat) {
+        KScope k(ctx, KID_DENSITY);
+        int2* rows = reinterpret_cast<int2*>(s->nbr_list);
+        if (local)
+            sph3_density_flat_kernel<true><<<ntiles, TILE_P, 0, ctx->stream>>>(
+                s->posS, s->velS, s->pack, rows, s->nbr_count, s->heavy_queue, hc, s->n, g->view, g->offset, cc, tex, extreme_candidates(ctx));
+        else
+            sph3_density_flat_kernel<false><<<ntiles, TILE_P, 0, ctx->stream>>>(
+                s->posS, s->velS, s->pack, rows, s->nbr_count, s->heavy_queue, hc, s->n, g->view, g->offset, cc, tex, extreme_candidates(ctx));
+    } else {
+      KScope k(ctx, KID_DENSITY);
       if (local)
           sph3_density_list_kernel<true><<<ntiles, TILE_P, 0, ctx->stream>>>(
               s->posS, s->velS, s->pack, s->nbr_list, s->nbr_count, s->heavy_queue, hc, s->n, g->view, g->offset, cc, tex, K, extreme_candidates(ctx));
@@ -1379,11 +1634,18 @@ static int launch_force_list(cwa_ctx* ctx, SphObj* s, GridObj* g, bool fused, fl
         s->pack, s->nbr_list, s->nbr_count, fq, s->heavy_cnt + 1, s->pairP, s->pairV, s->n, g->view, g->offset, cc, fa, s->nbr_k_used)
 #define CWA_FORCE_HEAVY(F, L) sph3_force_heavy_kernel<F, L><<<heavy_grid(ctx), 128, 0, ctx->stream>>>( \
         s->pack, fq, s->heavy_cnt + 1, s->n, s->pairP, s->pairV, g->view, g->offset, cc, fa)
-    { KScope k(ctx, KID_FORCE);
+#define CWA_FORCE_ROWS(F, L) sph3_force_rows_kernel<F, L><<<blocks, TILE_P, 0, ctx->stream>>>( \
+        s->pack, reinterpret_cast<const int2*>(s->nbr_list), s->nbr_count, fq, s->heavy_cnt + 1, s->pairP, s->pairV, s->n, g->view, g->offset, cc, fa)
+    if (s->nbr_rows_fmt) {
+      KScope k(ctx, KID_FORCE);
+      if (!fused) CWA_FORCE_ROWS(false, false); else if (local) CWA_FORCE_ROWS(true, true); else CWA_FORCE_ROWS(true, false);
+    } else {
+      KScope k(ctx, KID_FORCE);
       if (!fused) CWA_FORCE_LIST(false, false); else if (local) CWA_FORCE_LIST(true, true); else CWA_FORCE_LIST(true, false); }
     { KScope k(ctx, KID_HEAVY);
       if (!fused) CWA_FORCE_HEAVY(false, false); else if (local) CWA_FORCE_HEAVY(true, true); else CWA_FORCE_HEAVY(true, false); }
 #undef CWA_FORCE_LIST
+#undef CWA_FORCE_ROWS
 #undef CWA_FORCE_HEAVY
     return 0;
 }
@@ -1485,7 +1747,8 @@ int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which, bool co
     CWA_CHECK(g && g->dim == 3, "sph: the bound grid must be a 3-D grid");
     const bool full = (which == 7);
     const int cfg = nb_config(ctx);
-    const bool fused_tail = full && cfg == 7 && fused_integrate(ctx);   // the force kernels finish the particle (epilogue + integrate + write-back)
+    const bool lists = cfg >= 7;                                   // neighbour-list kernels (7: round-1 density pass, 8: flat density pass)
+    const bool fused_tail = full && lists && fused_integrate(ctx);   // the force kernels finish the particle (epilogue + integrate + write-back)
     count_ahead = count_ahead && full && !fused_tail && slab == nullptr;
     CWA_CHECK(slab == nullptr || (full && !fused_tail), "slab pack: needs a full step with the separate integrate kernel (fused_integrate = 0)");
     if (!(which & 1)) CWA_TRY(wave_sampling_copy(ctx, s->wave, s->wave_image, &tex));
@@ -1503,7 +1766,8 @@ int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which, bool co
         case 4: CWA_TRY((launch_density<128, 1>(ctx, s, g, tex))); break;
         case 5: CWA_TRY((launch_density<64, 2>(ctx, s, g, tex))); break;
         case 6: CWA_TRY((launch_density<256, 2>(ctx, s, g, tex))); break;
-        case 7: CWA_TRY(launch_density_list(ctx, s, g, tex)); break;
+        case 7: CWA_TRY(launch_density_list(ctx, s, g, tex, false)); break;
+        case 8: CWA_TRY(launch_density_list(ctx, s, g, tex, true)); break;
         default: CWA_TRY((launch_density<128, 4>(ctx, s, g, tex))); break;
         }
         if (!full) {
@@ -1520,7 +1784,7 @@ int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which, bool co
         case 4: CWA_TRY((launch_force<128, 1>(ctx, s, g))); break;
         case 5: CWA_TRY((launch_force<64, 2>(ctx, s, g))); break;
         case 6: CWA_TRY((launch_force<256, 2>(ctx, s, g))); break;
-        case 7:
+        case 7: case 8:
             CWA_CHECK(s->nbr_lists_valid, "force pass: the neighbour lists of the density pass are missing");
             CWA_TRY(launch_force_list(ctx, s, g, fused_tail, aos, tex)); break;
         default: CWA_TRY((launch_force<128, 4>(ctx, s, g))); break;
@@ -1587,7 +1851,7 @@ extern "C" int cwa_sph_create(cwa_ctx* ctx, cwa_buf particles, int n, cwa_grid g
         CWA_CUDA(cudaMalloc(&s.pairP, bytes));
         CWA_CUDA(cudaMalloc(&s.pairV, bytes / 2));
         s.nbr_k_alloc = nbr_k(ctx);
-        CWA_CUDA(cudaMalloc(&s.nbr_list, (size_t)(n > 0 ? n : 1) * s.nbr_k_alloc * 4));
+        CWA_CUDA(cudaMalloc(&s.nbr_list, nbr_bytes(n, s.nbr_k_alloc)));
         CWA_CUDA(cudaMalloc(&s.nbr_count, (size_t)(n > 0 ? n : 1) * 4));
         CWA_CUDA(cudaMalloc(&s.heavy_queue, (size_t)(n > 0 ? n : 1) * 2 * 4));
         CWA_CUDA(cudaMalloc(&s.heavy_cnt, 16));
@@ -1609,6 +1873,7 @@ extern "C" int cwa_sph_destroy(cwa_ctx* ctx, cwa_sph h)
     cudaFree(s->pack); cudaFree(s->scratch); cudaFree(s->posS); cudaFree(s->velS); cudaFree(s->forceS); cudaFree(s->miscS);
     cudaFree(s->pairP); cudaFree(s->pairV); cudaFree(s->consts); cudaFree(s->nbr_list); cudaFree(s->nbr_count); cudaFree(s->heavy_queue);
     cudaFree(s->heavy_cnt); cudaFree(s->cell_next); cudaFree(s->rank_next);
+    for (auto& g : s->frame_graph) if (g.valid) { cudaGraphExecDestroy((cudaGraphExec_t)g.exec); g.valid = false; }
     s->live = false;
     if (ctx->bound_sph == h) ctx->bound_sph = -1;
     return 0;
@@ -1710,6 +1975,62 @@ extern "C" int cwa_sph_init_cube(cwa_ctx* ctx, cwa_sph h, int nx, int ny, int nz
 // ---------------------------------------------------------------------------------------------
 // coupled frame: idle() of Main.cpp:530-562 followed by the display() bind of Main.cpp:413
 // ---------------------------------------------------------------------------------------------
+static bool graph_mode(cwa_ctx* c) { if (c->tune.graph < 0) c->tune.graph = env_int("CWA_GRAPH", 1, 0, 1); return c->tune.graph != 0; }
+
+// The all-pairs frame (the shipped scene: 20 480 particles, 64^2 field) as ONE graph launch: rho_pres + commit, force + commit,
+// integrate, wave stencil.  Everything the kernels read is addressed through pointers that stay valid between frames (particle
+// SSBO, parameter blocks, the three wave images); what changes from frame to frame is WHICH image plays which role and which one
+// the sampler is bound to -- that is the key, and it cycles with period 3, so at most a handful of graphs are ever captured.
+// Returns 1 when the frame was not run through a graph (the caller runs the plain sequence), 0 on success, < 0 on error.
+static int coupled_frame_graph(cwa_ctx* ctx, SphObj* s, WaveObj* w, cwa_wave hw, int image)
+{
+    BufferObj* pb = get_buffer(ctx, s->particles);
+    if (!pb || s->n == 0) return 1;
+    CWA_TRY(sph_prepare(ctx, s));                                    // derived constants: outside the graph (runs only when a block changed)
+    long long key[16] = {};
+    key[0] = (long long)(intptr_t)pb->ptr; key[1] = s->n; key[2] = image; key[3] = w->evolve ? 1 : 0;
+    key[4] = wave_image_with_unit(w, 0); key[5] = wave_image_with_unit(w, 1); key[6] = wave_image_with_unit(w, 2);
+    key[7] = (long long)(intptr_t)w->image[0]; key[8] = w->w; key[9] = w->h; key[10] = w->ch;
+    for (int b = 1; b <= 4; b++) key[10 + b] = ctx->ubo_binding[b];
+    key[15] = hw;
+    SphObj::FrameGraph* slot = nullptr;
+    for (auto& g : s->frame_graph)
+        if (g.valid && memcmp(g.key, key, sizeof(key)) == 0) { slot = &g; break; }
+    const int outi = wave_image_with_unit(w, 2);
+    if (slot == nullptr) {
+        for (auto& g : s->frame_graph) if (!g.valid) { slot = &g; break; }
+        if (slot == nullptr) {                                       // table full (objects were rebound many times): recycle entry 0
+            slot = &s->frame_graph[0];
+            cudaGraphExecDestroy((cudaGraphExec_t)slot->exec);
+            slot->valid = false;
+        }
+        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { (void)cudaGetLastError(); return 1; }
+        const unsigned long long l0 = ctx->launches;
+        int rc = sph_passes_internal(ctx, s, wave_tex_view(ctx, hw, image), 7);
+        if (rc == 0 && w->evolve) rc = wave_dispatch_mode(ctx, w, CWA_MODE_EVOLVE);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ee = cudaStreamEndCapture(ctx->stream, &graph);
+        if (rc != 0 || ee != cudaSuccess || graph == nullptr) {
+            (void)cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+            ctx->launches = l0;
+            return rc != 0 ? rc : 1;
+        }
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) { (void)cudaGetLastError(); ctx->launches = l0; return 1; }
+        slot->valid = true; memcpy(slot->key, key, sizeof(key)); slot->exec = exec; slot->nodes = (unsigned)(ctx->launches - l0);
+        ctx->launches = l0;                                          // counted below, like every replay
+    } else if (w->evolve) {
+        w->version[outi]++;                                          // what wave_dispatch_mode does on the host besides launching
+    }
+    CWA_CUDA(cudaGraphLaunch((cudaGraphExec_t)slot->exec, ctx->stream));
+    ctx->launches += slot->nodes;
+    if (w->evolve) wave_pingpong_internal(w);
+    return 0;
+}
+
 extern "C" int cwa_coupled_step(cwa_ctx* ctx, cwa_sph hs, cwa_wave hw, int nframes, int coupling)
 {
     DeviceGuard _dg(ctx);
@@ -1745,6 +2066,14 @@ extern "C" int cwa_coupled_step(cwa_ctx* ctx, cwa_sph hs, cwa_wave hw, int nfram
             image = w->tex_unit0;                                            // whatever display() last bound to texture unit 0
         }
         s->wave = hw; s->wave_image = image;
+        if (s->grid < 0 && !ctx->profiling && graph_mode(ctx)) {                 // all-pairs frame through a CUDA graph
+            const int grc = coupled_frame_graph(ctx, s, w, hw, image);
+            if (grc < 0) return grc;
+            if (grc == 0) {
+                CWA_TRY(cwa_wave_bind_texture_unit(ctx, hw));                        // display() :413
+                continue;
+            }
+        }
         const bool more = f + 1 < nframes;
         // the previous frame's wave stencil may still be running on the side stream: in grid mode the wait is placed behind the grid
         // build (the first kernel that samples the field is the density pass); the all-pairs passes sample from their first kernel on

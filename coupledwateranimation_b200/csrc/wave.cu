@@ -387,6 +387,8 @@ static void wave_pingpong(WaveObj* w)
     std::swap(w->unit[w->read_index[0]], w->unit[w->read_index[1]]);
 }
 
+void wave_pingpong_internal(WaveObj* w) { wave_pingpong(w); }
+
 int wave_dispatch_mode(cwa_ctx* ctx, WaveObj* w, int mode)
 {
     const int in0 = image_with_unit(w, 0), in1 = image_with_unit(w, 1), outi = image_with_unit(w, 2);

@@ -21,7 +21,7 @@ GRIDS = {
 @pytest.fixture()
 def tuned(ctx):
     yield ctx
-    ctx.set_tuning(nb_config=7, nb_cap_d=2048, nb_cap_f=1536)
+    ctx.set_tuning(nb_config=8, nb_cap_d=2048, nb_cap_f=1536)
 
 
 def _scene(cwa, ctx, oracle, grid_key, cluster=False, seed=1234):
@@ -58,7 +58,7 @@ def _check(oracle, prm, p, tex, sph):
 
 
 @pytest.mark.parametrize("grid_key", list(GRIDS))
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 7, 8])
 def test_variant_matches_oracle(cwa, tuned, oracle, cfg, grid_key):
     tuned.set_tuning(nb_config=cfg)
     prm, p, tex, sph = _scene(cwa, tuned, oracle, grid_key)
@@ -69,7 +69,7 @@ def test_variant_matches_oracle(cwa, tuned, oracle, cfg, grid_key):
 
 @pytest.mark.parametrize("cap", [0, 96, 1536])
 @pytest.mark.parametrize("grid_key", ["2h", "h+"])
-@pytest.mark.parametrize("cfg", [1, 7])
+@pytest.mark.parametrize("cfg", [1, 7, 8])
 def test_variant_with_partial_or_no_staging(cwa, tuned, oracle, cfg, grid_key, cap):
     tuned.set_tuning(nb_config=cfg, nb_cap_d=cap, nb_cap_f=cap)
     prm, p, tex, sph = _scene(cwa, tuned, oracle, grid_key)
@@ -77,7 +77,7 @@ def test_variant_with_partial_or_no_staging(cwa, tuned, oracle, cfg, grid_key, c
 
 
 @pytest.mark.parametrize("grid_key", ["2h", "h+", "h/1.5"])
-@pytest.mark.parametrize("cfg", [1, 7])
+@pytest.mark.parametrize("cfg", [1, 7, 8])
 def test_variant_dense_cluster(cwa, tuned, oracle, cfg, grid_key):
     """A 300-particle clump: neighbour counts far above the neighbour-list capacity (K = 64 -> the force pass
     re-scans the grid for those targets) and rows that overflow the staging budget of the lanes kernels."""
@@ -88,7 +88,7 @@ def test_variant_dense_cluster(cwa, tuned, oracle, cfg, grid_key):
     _check(oracle, prm, p, tex, sph)
 
 
-@pytest.mark.parametrize("cfg", [7])
+@pytest.mark.parametrize("cfg", [7, 8])
 def test_rows_variant_full_frames_equal_lanes_variant(cwa, tuned, oracle, cfg):
     """3 fused frames: rows kernels vs the lanes kernels (same physics, summation order differs)."""
     tuned.set_tuning(nb_config=1)
@@ -108,7 +108,7 @@ def test_rows_variant_full_frames_equal_lanes_variant(cwa, tuned, oracle, cfg):
 def test_fused_order_reorder_is_canonical(cwa, tuned, oracle, fused, cluster):
     """The SPH snapshot path may fuse the canonical per-cell ordering into the reorder pass; the index list
     it leaves behind must be the same bit-exact list (ascending id inside a cell) as the stand-alone build."""
-    tuned.set_tuning(fused_order=fused, nb_config=7)
+    tuned.set_tuning(fused_order=fused, nb_config=8)
     try:
         prm, p, tex, sph = _scene(cwa, tuned, oracle, "h+", cluster=cluster)
         p["pos"][5, 0] = np.nan                    # a NaN particle is left out of the grid
@@ -138,7 +138,7 @@ def test_fused_integrate_tail_equals_separate_kernels(cwa, tuned, oracle, cluste
     """Full step: the force kernels may finish the particle themselves (force epilogue + integrate + record
     write-back); the result must be the one of the separate integrate kernel (same device functions)."""
     try:
-        tuned.set_tuning(nb_config=7, fused_integrate=0)
+        tuned.set_tuning(nb_config=8, fused_integrate=0)
         prm, p, tex, sph = _scene(cwa, tuned, oracle, "h+", cluster=cluster)
         sph.step(2)
         a = sph.download()
@@ -169,7 +169,7 @@ def test_pipelined_frames_equal_the_plain_sequence(cwa, tuned, oracle, mode, clu
     frames = 7
 
     def run(pipeline):
-        tuned.set_tuning(nb_config=7, pipeline=pipeline)
+        tuned.set_tuning(nb_config=8, pipeline=pipeline)
         prm, p, tex, sph = _scene(cwa, tuned, oracle, "h+", cluster=cluster)
         p["pos"][5, 0] = np.nan                    # never inserted
         p["vel"][::11, :3] *= np.float32(40.0)     # some particles change cells every frame
@@ -212,7 +212,7 @@ def test_transposed_sampling_copy_is_bit_identical(cwa, tuned, oracle, coupling)
     cpl = cwa.COUPLING_AS_SHIPPED if coupling == "as_shipped" else cwa.COUPLING_LATEST
 
     def run(on):
-        tuned.set_tuning(nb_config=7, wave_transpose=on, pipeline=3)
+        tuned.set_tuning(nb_config=8, wave_transpose=on, pipeline=3)
         prm, p, tex, sph = _scene(cwa, tuned, oracle, "h+")
         wave = cwa.StencilImage2DTripleBuffered(tuned, 320, 272, 1, cwa.WAVE_COUPLED)   # non-square, above the 256^2 threshold
         for i in range(3):

@@ -25,7 +25,7 @@ def test_two_contexts_hold_different_tuning(cwa, oracle):
     kernels with pipelining, interleaved in one process -- both must produce what they produce alone."""
     a, b = cwa.Context(0), cwa.Context(0)
     a.set_tuning(nb_config=0, pipeline=0, scan_config=0, wave_transpose=0)
-    b.set_tuning(nb_config=7, pipeline=3, scan_config=2, wave_transpose=1)
+    b.set_tuning(nb_config=8, pipeline=3, scan_config=2, wave_transpose=1)
     pa, ga, sa, wa = _small_scene(cwa, a, oracle)
     pb, gb, sb, wb = _small_scene(cwa, b, oracle)
     for _ in range(3):
@@ -34,7 +34,7 @@ def test_two_contexts_hold_different_tuning(cwa, oracle):
     ra, rb = sa.download(), sb.download()
     # reference runs, each alone in a fresh context with the same knobs
     out = []
-    for knobs in (dict(nb_config=0, pipeline=0, scan_config=0, wave_transpose=0), dict(nb_config=7, pipeline=3, scan_config=2, wave_transpose=1)):
+    for knobs in (dict(nb_config=0, pipeline=0, scan_config=0, wave_transpose=0), dict(nb_config=8, pipeline=3, scan_config=2, wave_transpose=1)):
         c = cwa.Context(0)
         c.set_tuning(**knobs)
         p, g, s, w = _small_scene(cwa, c, oracle)
