@@ -264,8 +264,17 @@ def run_native(args):
 
     K, W = max(1, args.steps), max(3, args.warmup)
     ctx = cwa.Context(local_rank)
+    if args.config != "C4":
+        return run_other_config(args, cwa, ctx, torch, K, W, local_rank)
     grid, sph, wave = build_scene(cwa, ctx)
     ctx.synchronize()
+    if args.state_frame > 0:                               # late-state row: the same scene, advanced (untimed) to the requested frame
+        done = 0
+        while done < args.state_frame:
+            step = min(500, args.state_frame - done)
+            sph.coupled_step(wave, step, COUPLING)
+            ctx.synchronize()
+            done += step
 
     # ---- device-resident timing: W warm-up steps, then EXACTLY K steps ---------------------------
     sampler = ClockSampler(local_rank)
@@ -400,6 +409,13 @@ def run_native(args):
         cpu = {"value": N_PARTICLES * n_cpu / dt, "unit": "particle-updates/s", "cores": cores, "kind": "port",
                "sample": f"{n_cpu} full C4 frames after 1 warm-up frame, CPU restatement of the reference GLSL (OpenMP, {cores} threads)"}
 
+    other = None
+    if not args.no_other_configs and args.state_frame == 0:
+        import bench_configs
+        for sl in slots[1:]:
+            sl.ctx.close()
+        other = bench_configs.brief_rows(cwa, ctx, torch, peak, peak_src)
+
     ms_step = ms_total / K
     value = world * N_PARTICLES * K / (ms_total * 1e-3)
     line = {
@@ -419,9 +435,35 @@ def run_native(args):
         "roofline_kernels": kern,
         "cpu_baseline": cpu,
     }
+    if args.state_frame > 0:
+        line["config"]["state_frame"] = args.state_frame
+        line["config"]["workload"] += f", state advanced to frame {args.state_frame} before the timed region"
+    if other is not None:
+        line["other_configs"] = other
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_other_config(args, cwa, ctx, torch, K, W, local_rank):
+    """BASELINE.json configs 1-3 (bench_configs.py) with the same JSON contract as the C4 line."""
+    import bench_configs
+    from oracle import oracle as O
+    peak, peak_src = measured_peaks()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t0 = time.time()
+    r = bench_configs.RUNNERS[args.config](cwa, ctx, torch, K, W, peak, peak_src, brief=args.no_cpu_baseline, oracle=O)
+    if time.time() - t0 < 0.6:                             # a run shorter than a few sampler periods: repeat it (untimed) so the clocks are seen under load
+        bench_configs.RUNNERS[args.config](cwa, ctx, torch, max(K, 2000 if args.config != "C3" else 200), W, peak, peak_src, brief=True)
+    clocks = sampler.stop()
+    line = {"metric": r["metric"], "value": r["value"], "unit": r["unit"], "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": r["dtype"], "data": "synthetic", "steps_per_sec": r["steps_per_sec"], "config": r["config"], "clocks": clocks,
+            "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "roofline": r["roofline"], "roofline_kernels": r["roofline_kernels"], "cpu_baseline": r["cpu_baseline"]}
+    for k in ("rgba32f_compat", "ms_per_step_without_graph"):
+        if k in r:
+            line[k] = r[k]
+    print(json.dumps(line))
 
 
 def c5_scene(world: int, variant: str):
@@ -686,6 +728,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="C4", choices=["C4", "D", "C2", "C3"],
+                    help="BASELINE.json config at --gpus 1: C4 (default, the metric's configuration), D (shipped scene), C2 (2-D Koschier 64k), C3 (4096^2 wave)")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short D / C2 / C3 rows added to the default C4 line")
+    ap.add_argument("--state-frame", type=int, default=0,
+                    help="C4: advance the simulation to this frame before the timed region (the cost of a frame drifts as the fluid clumps); 0 = early state")
     ap.add_argument("--scene", default="", choices=["", "torque_scaled", "literal", "weak"],
                     help="--gpus N > 1: C5 with torque_coeff 0.25/4 (default), C5 with the shader's literal 0.25, or the weak-scaling scene C4 x sqrt(N)")
     args = ap.parse_args()
