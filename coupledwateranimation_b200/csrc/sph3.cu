@@ -1062,31 +1062,41 @@ sph3_force_rows_kernel(const float4* __restrict__ pack, const int2* __restrict__
     const f4x2 own = cwa_ldg256(pack + 2 * (size_t)slot);
     const float4 pa = own.a, pb = own.b;
     float fpx = 0.f, fpy = 0.f, fpz = 0.f, fvx = 0.f, fvy = 0.f, fvz = 0.f;
-    if (nr > 0) {
-        const int2* tp = tab + tid;
-        const int2* const tp_last = tab + (nr - 1) * TILE_P + tid;
-        int2 row = *tp;                                // (first slot, mask != 0)
-        unsigned mask = (unsigned)row.y;
-        int j = row.x + __ffs((int)mask) - 1;
-        mask &= mask - 1u;
-        f4x2 A = cwa_ldg256(pack + 2 * (size_t)j), B = A;
-#define CWA_ROWS_STAGE(CUR, NXT)                                                                   \
+    {
+        // The lane walks the set bits of its masks in ONE loop; moving to the next row is branch-free (pointer + 0 or one table row, entry
+        // read unconditionally and selected).  Records are gathered TWO neighbours ahead of the pair evaluation (three buffers in
+        // rotation): the gathers are L2 / DRAM latency and one thread has little else to overlap them with.
+        int trow = -1;                                 // current table row of the lane
+        const int last = nr - 1;
+        int first = 0;
+        unsigned mask = 0u;
+        auto next = [&](int& j) -> bool {
+            const bool adv = mask == 0u;
+            const bool none = adv && trow == last;
+            const bool go = adv && !none;
+            trow += go ? 1 : 0;
+            const int2 cand = tab[max(trow, 0) * TILE_P + tid];
+            if (go) { first = cand.x; mask = (unsigned)cand.y; }
+            j = first + __ffs((int)mask) - 1;
+            mask &= mask - 1u;
+            return !none;
+        };
+        int j0, j1, j2;
+        bool v0 = next(j0), v1 = next(j1), v2;
+        f4x2 X0 = own, X1 = own, X2 = own;
+        if (v0) X0 = cwa_ldg256(pack + 2 * (size_t)j0);
+        if (v1) X1 = cwa_ldg256(pack + 2 * (size_t)j1);
+#define CWA_ROWS_STAGE(JC, VC, XC, JN, VN, XN)                                                     \
         {                                                                                          \
-            const bool adv = mask == 0u;                                                           \
-            const bool more = !adv || tp != tp_last;                                               \
-            tp += adv ? TILE_P : 0;                                                                \
-            const int2 cand = *tp;                                                                 \
-            if (adv) { row = cand; mask = (unsigned)cand.y; }                                      \
-            const int jn = row.x + __ffs((int)mask) - 1;                                           \
-            mask &= mask - 1u;                                                                     \
-            if (more) NXT = cwa_ldg256(pack + 2 * (size_t)jn);                                     \
-            if (j != slot) pair_force(c, pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, CUR.a, CUR.b, fpx, fpy, fpz, fvx, fvy, fvz); \
-            if (!more) break;                                                                      \
-            j = jn;                                                                                \
+            if (!VC) break;                                                                        \
+            VN = next(JN);                                                                         \
+            if (VN) XN = cwa_ldg256(pack + 2 * (size_t)JN);                                        \
+            if (JC != slot) pair_force(c, pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, XC.a, XC.b, fpx, fpy, fpz, fvx, fvy, fvz); \
         }
         while (true) {
-            CWA_ROWS_STAGE(A, B)
-            CWA_ROWS_STAGE(B, A)
+            CWA_ROWS_STAGE(j0, v0, X0, j2, v2, X2)
+            CWA_ROWS_STAGE(j1, v1, X1, j0, v0, X0)
+            CWA_ROWS_STAGE(j2, v2, X2, j1, v1, X1)
         }
 #undef CWA_ROWS_STAGE
     }
@@ -1506,7 +1516,7 @@ static int env_int(const char* name, int dflt, int lo, int hi)
 // Tuning knobs of the neighbour kernels.  Defaults come from the environment (CWA_NB_CONFIG, CWA_NB_CAP_D / _F,
 // CWA_FUSED_ORDER) the first time they are needed; cwa_set_tuning() overrides them at run time (used by the
 // parity tests to cover every kernel variant in one process).
-//   nb_config: 8 (default) = neighbour-list kernels with the "flat" density pass (sph3_density_flat_kernel);
+//   nb_config: 8 (default) = row-mask kernels, one target per thread (sph3_density_flat_kernel + sph3_force_rows_kernel);
 //              7 = neighbour-list kernels with the round-1 density pass (row loop nest, four candidates per trip);
 //              0..6 = "lanes" kernels (targets per CTA x lanes per target: 0: 128x4, 1: 128x2, 2: 64x4, 3: 256x1,
 //              4: 128x1, 5: 64x2, 6: 256x2): neighbour rows staged in shared memory by TMA bulk copies, lanes of a
@@ -1579,7 +1589,7 @@ static size_t nbr_bytes(int n, int K)
     return (((size_t)(n > 0 ? n : 1) + 31) / 32 * 32) * per;
 }
 
-static int launch_density_list(cwa_ctx* ctx, SphObj* s, GridObj* g, TexView tex, bool flat)
+static int launch_density_list(cwa_ctx* ctx, SphObj* s, GridObj* g, TexView tex, int variant)   // 0: index lists, 1: row masks
 {
     const Sph3Const* cc = (const Sph3Const*)s->consts;
     const int ntiles = ceil_div(s->n, TILE_P);
@@ -1593,6 +1603,7 @@ static int launch_density_list(cwa_ctx* ctx, SphObj* s, GridObj* g, TexView tex,
         s->nbr_k_alloc = K;
     }
     s->nbr_k_used = K;
+    const bool flat = variant != 0;
     s->nbr_rows_fmt = flat;
     if (flat) {
         KScope k(ctx, KID_DENSITY);
@@ -1766,8 +1777,8 @@ int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which, bool co
         case 4: CWA_TRY((launch_density<128, 1>(ctx, s, g, tex))); break;
         case 5: CWA_TRY((launch_density<64, 2>(ctx, s, g, tex))); break;
         case 6: CWA_TRY((launch_density<256, 2>(ctx, s, g, tex))); break;
-        case 7: CWA_TRY(launch_density_list(ctx, s, g, tex, false)); break;
-        case 8: CWA_TRY(launch_density_list(ctx, s, g, tex, true)); break;
+        case 7: CWA_TRY(launch_density_list(ctx, s, g, tex, 0)); break;
+        case 8: CWA_TRY(launch_density_list(ctx, s, g, tex, 1)); break;
         default: CWA_TRY((launch_density<128, 4>(ctx, s, g, tex))); break;
         }
         if (!full) {
