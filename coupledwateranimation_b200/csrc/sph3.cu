@@ -693,8 +693,10 @@ sph3_density_list_kernel(const float4* __restrict__ posS, const float4* __restri
 // Targets the scheme does not cover -- more than EXTREME_CANDIDATES candidates, a row longer than 31 slots, cells smaller than h
 // (more than 3 x 3 rows) -- go to the heavy kernels (one warp per target, generic loops).
 // ---------------------------------------------------------------------------------------------
+constexpr int INPLACE_MARK = EXTREME_MARK + 1; // neighbour count of a clump target the density pass finished in place, without masks
+constexpr int INPLACE_MAX = 1024;         // candidates up to which the density pass finishes a clump target in place (tuning "inplace_max"; beyond: one warp per target)
 constexpr int ROW_MASK_BITS = 31;         // longest row a mask records: with an odd first slot the pair loop shifts by (length + 1) - 1 at most
-struct FlatRows { int b[RT_ROWS], e[RT_ROWS]; int total; bool heavy; };
+struct FlatRows { int b[RT_ROWS], e[RT_ROWS]; int total; bool wide, longrow; int cell_lin; };   // cell_lin: the target's cell (fast path), -1 = generic query
 
 __device__ __forceinline__ FlatRows flat_rows_load(const GridView& g, const int* __restrict__ offset, float x, float y, float z, float h)
 {
@@ -702,6 +704,7 @@ __device__ __forceinline__ FlatRows flat_rows_load(const GridView& g, const int*
     const float hm = h * (1.0f + 2.5e-3f), hx = h * 1.25f;
     const bool fast = hm <= g.cell[0] && hm <= g.cell[1] && hm <= g.cell[2] && g.cell[0] <= hx && g.cell[1] <= hx && g.cell[2] <= hx;
     fr.total = 0;
+    fr.cell_lin = -1;
 #pragma unroll
     for (int r = 0; r < RT_ROWS; r++) { fr.b[r] = 0; fr.e[r] = 0; }
     if (!fast) {                                           // generic query: rows_load semantics (more than 3 x 3 rows -> heavy kernels)
@@ -709,13 +712,14 @@ __device__ __forceinline__ FlatRows flat_rows_load(const GridView& g, const int*
         const RowBounds rb = rows_load(g, offset, q);
 #pragma unroll
         for (int r = 0; r < RT_ROWS; r++) { fr.b[r] = rb.b[r]; fr.e[r] = rb.e[r]; }
-        fr.total = rb.total; fr.heavy = rb.wide;
+        fr.total = rb.total; fr.wide = rb.wide;
     } else {
-        fr.heavy = false;
+        fr.wide = false;
         const int ci = approx_cell(x, g.min[0], g.inv_cell[0], 0.0f, g.n[0]);
         const int cj = approx_cell(y, g.min[1], g.inv_cell[1], 0.0f, g.n[1]);
         const int ck = approx_cell(z, g.min[2], g.inv_cell[2], 0.0f, g.n[2]);
         const int kl = max(ck - 1, 0), kh = min(ck + 1, g.n[2] - 1);
+        fr.cell_lin = (ci * g.n[1] + cj) * g.kstride + ck;
         // squared distance (minus the margin) from the target to the lower / upper neighbour slab of its cell, per axis
         const float m = 2.5e-3f * h, h2 = h * h;
         float dl[3], dh[3];
@@ -743,8 +747,9 @@ __device__ __forceinline__ FlatRows flat_rows_load(const GridView& g, const int*
 #pragma unroll
         for (int r = 0; r < RT_ROWS; r++) fr.total += fr.e[r] - fr.b[r];
     }
+    fr.longrow = false;
 #pragma unroll
-    for (int r = 0; r < RT_ROWS; r++) fr.heavy = fr.heavy || (fr.e[r] - fr.b[r] > ROW_MASK_BITS);
+    for (int r = 0; r < RT_ROWS; r++) fr.longrow = fr.longrow || (fr.e[r] - fr.b[r] > ROW_MASK_BITS);
     return fr;
 }
 
@@ -757,7 +762,7 @@ sph3_density_flat_kernel(const float4* __restrict__ posS, const float4* __restri
                          int2* __restrict__ nbr_rows, int* __restrict__ nbr_count,
                          int* __restrict__ heavy_queue, int* __restrict__ heavy_count,
                          int n_max, GridView g, const int* __restrict__ offset, const Sph3Const* __restrict__ cc, TexView tex,
-                         const int extreme_candidates)
+                         const int extreme_candidates, const int inplace_max)
 {
     __shared__ int2 tab[(RT_ROWS + 1) * TILE_P];       // non-empty rows of every target, compacted: (first slot, end slot), later (first slot, mask)
     const int tid = threadIdx.x;
@@ -767,7 +772,15 @@ sph3_density_flat_kernel(const float4* __restrict__ posS, const float4* __restri
     const float h = cc->h, accept_r2 = cc->accept_r2, h2 = cc->h2, poly6 = cc->poly6;
     const float4 p = __ldg(posS + slot);
     const FlatRows fr = flat_rows_load(g, offset, p.x, p.y, p.z, h);
-    if (fr.heavy || fr.total > extreme_candidates) {   // clump, long row or generic wide query: sph3_density_heavy_kernel, one warp per target
+    // Three kinds of targets.  maskable: the usual case, neighbours recorded as row masks.  in place: a clump target (more candidates than
+    // `extreme_candidates`, or a row too long for a mask) walks its rows like everybody else, only without masks: the density loop has no
+    // divergent part, clump targets come in runs of consecutive slots (lanes read the same candidates), and the per-target set-up of the
+    // one-warp-per-target kernel -- half its instructions for targets of a few hundred candidates -- is not paid.  The FORCE pass of such a
+    // target goes to sph3_force_heavy_kernel (measured, profiles/r2/tuning.md: one thread alone with the divergent pair term of a few
+    // hundred candidates is a 50-150 us tail, in its own warp or from a queue).  heavy: a generic wide query or more than `inplace_max`
+    // candidates -- sph3_density_heavy_kernel, one warp per target.
+    const bool maskable = !fr.wide && !fr.longrow && fr.total <= extreme_candidates;
+    if (!maskable && (fr.wide || fr.cell_lin < 0 || fr.total > inplace_max)) {
         const int qi = atomicAdd(heavy_count, 1);
         if (qi < n_max) heavy_queue[qi] = slot;
         return;
@@ -831,6 +844,7 @@ sph3_density_flat_kernel(const float4* __restrict__ posS, const float4* __restri
     density_epilogue<LOCAL>(*cc, tex, p.x, p.z, rho, rho_out, prs_out);
     const float4 v = __ldg(velS + slot);
     cwa_stg256(pack + 2 * (size_t)slot, make_float4(p.x, p.y, p.z, prs_out), make_float4(v.x, v.y, v.z, rho_out));
+    if (!maskable) { nbr_count[slot] = INPLACE_MARK; return; }
     // the rows that accepted somebody, compacted
     int2* out = rows_of(nbr_rows, slot);
     int oc = 0;
@@ -1049,7 +1063,7 @@ sph3_force_rows_kernel(const float4* __restrict__ pack, const int2* __restrict__
     const int n = min(n_max, __ldg(offset + g.num_cells));   // inserted particles
     if (slot >= n) return;
     const int nr = __ldg(nbr_count + slot);
-    if (nr > RT_ROWS) {                                // marked by the density pass: sph3_force_heavy_kernel
+    if (nr > RT_ROWS) {                                // clump target (INPLACE_MARK or EXTREME_MARK): sph3_force_heavy_kernel
         const int qi = atomicAdd(heavy_count, 1);
         if (qi < n_max) heavy_queue[qi] = slot;        // (a pass dispatched twice without a grid build in between re-queues: same results)
         return;
@@ -1535,6 +1549,7 @@ static int pipeline_mode(cwa_ctx* c) { if (c->tune.pipeline < 0) c->tune.pipelin
 // nbr_k: list capacity per target (multiple of 4, <= 256); extreme: candidate count above which the density pass hands a target to a whole warp
 static int nbr_k(cwa_ctx* c) { if (c->tune.nbr_k < 0) c->tune.nbr_k = env_int("CWA_NBR_K", NBR_K_DEFAULT, 8, NBR_K_MAX) & ~3; return c->tune.nbr_k; }
 static int extreme_candidates(cwa_ctx* c) { if (c->tune.extreme < 0) c->tune.extreme = env_int("CWA_EXTREME", EXTREME_CANDIDATES, 16, 1 << 20); return c->tune.extreme; }
+static int inplace_max(cwa_ctx* c) { if (c->tune.inplace_max < 0) c->tune.inplace_max = env_int("CWA_INPLACE_MAX", INPLACE_MAX, 0, 1 << 20); return c->tune.inplace_max; }
 static bool fused_order(cwa_ctx* c) { if (c->tune.fused_order < 0) c->tune.fused_order = env_int("CWA_FUSED_ORDER", 1, 0, 1); return c->tune.fused_order != 0; }
 
 extern "C" int cwa_set_tuning(cwa_ctx* ctx, const char* key, int value)
@@ -1548,6 +1563,7 @@ extern "C" int cwa_set_tuning(cwa_ctx* ctx, const char* key, int value)
     else if (k == "fused_order") { ctx->tune.fused_order = value ? 1 : 0; }
     else if (k == "fused_integrate") { ctx->tune.fused_integrate = value ? 1 : 0; }
     else if (k == "nbr_k") { CWA_CHECK(value >= 8 && value <= NBR_K_MAX && value % 4 == 0, "nbr_k %d: multiple of 4 in [8, %d]", value, NBR_K_MAX); ctx->tune.nbr_k = value; }
+    else if (k == "inplace_max") { CWA_CHECK(value >= 0, "inplace_max %d negative", value); ctx->tune.inplace_max = value; }
     else if (k == "extreme_candidates") { CWA_CHECK(value >= 16, "extreme_candidates %d too small", value); ctx->tune.extreme = value; }
     else if (k == "wave_transpose") { ctx->tune.wave_transpose = value ? 1 : 0; }
     else if (k == "scan_config") { CWA_CHECK(value >= 0 && value <= 3, "scan_config %d out of range", value); ctx->tune.scan_config = value; }
@@ -1610,10 +1626,10 @@ static int launch_density_list(cwa_ctx* ctx, SphObj* s, GridObj* g, TexView tex,
         int2* rows = reinterpret_cast<int2*>(s->nbr_list);
         if (local)
             sph3_density_flat_kernel<true><<<ntiles, TILE_P, 0, ctx->stream>>>(
-                s->posS, s->velS, s->pack, rows, s->nbr_count, s->heavy_queue, hc, s->n, g->view, g->offset, cc, tex, extreme_candidates(ctx));
+                s->posS, s->velS, s->pack, rows, s->nbr_count, s->heavy_queue, hc, s->n, g->view, g->offset, cc, tex, extreme_candidates(ctx), inplace_max(ctx));
         else
             sph3_density_flat_kernel<false><<<ntiles, TILE_P, 0, ctx->stream>>>(
-                s->posS, s->velS, s->pack, rows, s->nbr_count, s->heavy_queue, hc, s->n, g->view, g->offset, cc, tex, extreme_candidates(ctx));
+                s->posS, s->velS, s->pack, rows, s->nbr_count, s->heavy_queue, hc, s->n, g->view, g->offset, cc, tex, extreme_candidates(ctx), inplace_max(ctx));
     } else {
       KScope k(ctx, KID_DENSITY);
       if (local)
