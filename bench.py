@@ -524,23 +524,17 @@ def run_native_distributed(args, world, rank, local_rank, torch, dist, cwa):
     cap_ghost = int(per_face * 12 + 4095) // 4096 * 4096   # the 2h band holds ~2.4 lattice layers at rest; the sheet compresses against faces
     cap_mig = int(per_face * 6 + 4095) // 4096 * 4096
     lib = cwa._capi.load()
-    desc = plan_desc(lib, world, rank, wave_w, wave_h, 1, uv_z, h, row_bounds, cap_mig=cap_mig, cap_ghost=cap_ghost,
-                     timeout_ms=int(os.environ.get("CWA_SLAB_TIMEOUT_MS", "20000")))
-    kk = np.nonzero((ks >= desc.z_lo) & (ks < desc.z_hi))[0]
-    n_own0 = nxg * sc["ny"] * kk.size
-    desc.capacity = int(n_own0 * 1.12) + 2 * (2 * cap_mig + cap_ghost) + 8192
-    _log(rank, f"scene {variant}: {n_global} particles, own {n_own0}, rows [{desc.row_lo},{desc.row_hi}) stored [{desc.store_lo},{desc.store_hi}), capacity {desc.capacity}")
-
-    def own_particles():
-        i, j, k = np.meshgrid(np.arange(nxg, dtype=np.float32), np.arange(sc["ny"], dtype=np.float32), kk.astype(np.float32), indexing="ij")
-        own = np.zeros(i.size, cwa.PARTICLE)
-        own["pos"][:, 0] = i.ravel() * sp; own["pos"][:, 1] = j.ravel() * sp; own["pos"][:, 2] = k.ravel() * sp; own["pos"][:, 3] = 1.0
-        own["extras"][:] = (1000.0, 0.0, 500.0, 50.0)
-        return own
-
     cell = box_x / sc["gn"][0]
+    keep_alive = []
 
-    def build_rank():
+    def build_rank(rb):
+        """Library objects of this rank for the row blocks `rb` (world + 1 ascending rows), particles on the lattice, peers connected."""
+        desc = plan_desc(lib, world, rank, wave_w, wave_h, 1, uv_z, h, rb, cap_mig=cap_mig, cap_ghost=cap_ghost,
+                         timeout_ms=int(os.environ.get("CWA_SLAB_TIMEOUT_MS", "20000")))
+        kk = np.nonzero((ks >= desc.z_lo) & (ks < desc.z_hi))[0]
+        n_own0 = nxg * sc["ny"] * kk.size
+        desc.capacity = int(n_own0 * 1.12) + 2 * (2 * cap_mig + cap_ghost) + 8192
+        _log(rank, f"scene {variant}: {n_global} particles, own {n_own0}, rows [{desc.row_lo},{desc.row_hi}) stored [{desc.store_lo},{desc.store_hi}), capacity {desc.capacity}")
         c = cwa.Context(local_rank)
         c.set_boundary(upper=(box_x, 1.0, box_z, 500.0), lower=BOX_LOWER)
         c.set_sim_constants(uv_scale=uv, uv_scale_z=sc["uv_z"], torque_coeff=sc["torque"])
@@ -548,14 +542,15 @@ def run_native_distributed(args, world, rank, local_rank, torch, dist, cwa):
         zh = min(box_z, desc.z_hi + 0.06) if rank < world - 1 else box_z
         ncz = max(4, int(math.floor((zh - zl) / cell + 1e-6)))      # cells never narrower than C4's (the 3 x 3 x 3 query needs cell >= 1.0025 h)
         r = SlabRank(cwa, c, desc, (0.0, -0.02, zl), (box_x, sc["gmax"][1], zh), (sc["gn"][0], sc["gn"][1], ncz))
-        own = own_particles()
+        i, j, k = np.meshgrid(np.arange(nxg, dtype=np.float32), np.arange(sc["ny"], dtype=np.float32), kk.astype(np.float32), indexing="ij")
+        own = np.zeros(i.size, cwa.PARTICLE)
+        own["pos"][:, 0] = i.ravel() * sp; own["pos"][:, 1] = j.ravel() * sp; own["pos"][:, 2] = k.ravel() * sp; own["pos"][:, 3] = 1.0
+        own["extras"][:] = (1000.0, 0.0, 500.0, 50.0)
         r.upload_owned(own)
-        del own
+        del own, i, j, k
         connect_processes(r, dist)
-        return c, r
-
-    ctx, rk = build_rank()
-    _log(rank, "built + connected")
+        keep_alive.append((c, r))                                   # earlier builds stay alive: their mailboxes are mapped by the peers
+        return desc, c, r
 
     def reduce_max(v):
         t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
@@ -575,7 +570,36 @@ def run_native_distributed(args, world, rank, local_rank, torch, dist, cwa):
         dist.destroy_process_group()
         sys.exit(3)
 
+    # Slabs balanced by MEASURED cost: the first cut gives every rank the same number of particles; the ranks that own a wall (the sheet is
+    # pressed flat there and the clump kernels run) then take longer than the others, and everybody waits for them at the exchange.  After
+    # the warm-up frames each rank times its own kernels (exchange waits excluded), the row blocks are re-cut so that the costs are equal,
+    # and the scene is rebuilt from the lattice with the new blocks (at most CWA_BENCH_REBALANCE times, default 2).
     sampler = ClockSampler(local_rank)
+    balance_log = []
+    n_rebalance = max(0, int(os.environ.get("CWA_BENCH_REBALANCE", "2")))
+    for attempt in range(1 + n_rebalance):
+        desc, ctx, rk = build_rank(row_bounds)
+        _log(rank, "built + connected")
+        rk.step(W, COUPLING)
+        ctx.synchronize()
+        err = reduce_max(rk.counts()["err"])
+        if err:
+            fail_everywhere(f"slab exchange error bits {int(err)} during warm-up (1 sender overflow, 2 capacity, 4/8 timeouts)")
+        ctx.profile_begin()
+        rk.step(K, COUPLING)
+        pr = ctx.profile_end()
+        busy = sum(v[0] for name, v in pr.items() if name != "exchange") / K
+        costs = [None] * world
+        dist.all_gather_object(costs, float(busy))
+        imbalance = max(costs) / (sum(costs) / world)
+        balance_log.append({"row_bounds": [int(v) for v in row_bounds], "busy_ms": [round(c, 4) for c in costs], "max_over_mean": round(imbalance, 4)})
+        _log(rank, f"balance attempt {attempt}: busy {busy:.3f} ms/frame, max/mean {imbalance:.3f}")
+        if imbalance < 1.03 or attempt == n_rebalance:
+            break
+        row_bounds = SlabPlan.cost_balanced_row_bounds(row_bounds, costs, min_rows=int(math.ceil(max(4.5 * h, 2.0 * h + 0.01 / uv_z) * wave_h * uv_z)) + 8, damping=0.8)
+    # the cut is chosen: the measured run starts over from the lattice, W warm-up frames, then the timed region (frames W .. W + K, the
+    # same window of the simulated state as the single-GPU line)
+    desc, ctx, rk = build_rank(row_bounds)
     rk.step(W, COUPLING)
     ctx.synchronize()
     err = reduce_max(rk.counts()["err"])
@@ -714,6 +738,7 @@ def run_native_distributed(args, world, rank, local_rank, torch, dist, cwa):
                          "traffic": ncu_traffic(dom["kernel"]), "peak_source": peak_src, "note": "rank 0's kernels; neighbour loops are FP32-issue / L1 bound"},
             "roofline_kernels": kern,
             "ranks": gathered,
+            "slab_balance": balance_log,
             "cpu_baseline": None,
         }
         print(json.dumps(line), flush=True)

@@ -105,6 +105,34 @@ class SlabPlan:
         rb.append(wave_h)
         return rb
 
+    @staticmethod
+    def cost_balanced_row_bounds(row_bounds, costs, min_rows: int = 8, damping: float = 1.0):
+        """Row blocks re-cut so that every rank carries the same MEASURED cost.  `costs[r]` is the busy time of rank r under `row_bounds`
+        (its kernels without the waits on its neighbours); the cost is taken as uniform inside a rank's block, the cumulative cost over
+        the rows is inverted at k / world.  A rank that owns a wall -- where the sheet is pressed flat and the clump kernels run -- ends
+        up with fewer rows.  damping < 1 moves only part of the way (the cost of a wall region does not shrink with the block)."""
+        rb = [int(v) for v in row_bounds]
+        world = len(rb) - 1
+        assert len(costs) == world and all(c > 0 for c in costs)
+        cum = [0.0]
+        for c in costs:
+            cum.append(cum[-1] + float(c))
+        total = cum[-1]
+        out = [rb[0]]
+        for k in range(1, world):
+            target = total * k / world
+            r = max(i for i in range(world) if cum[i] <= target)
+            frac = (target - cum[r]) / (cum[r + 1] - cum[r])
+            row = rb[r] + frac * (rb[r + 1] - rb[r])
+            row = rb[k] + damping * (row - rb[k])
+            out.append(int(round(row)))
+        out.append(rb[-1])
+        for k in range(1, world):                       # keep every block at least min_rows tall, bounds ascending
+            out[k] = max(out[k], out[k - 1] + min_rows)
+        for k in range(world - 1, 0, -1):
+            out[k] = min(out[k], out[k + 1] - min_rows)
+        return out
+
     @property
     def ghost_width(self) -> float:
         return 2.0 * self.h

@@ -188,3 +188,25 @@ def test_c_abi_plan_matches_python_plan():
                 if r < world - 1:
                     assert d.z_hi == np.float32(p.z_hi)
                     assert d.right_store_lo == SlabPlan.make(world, r + 1, w, h, uv, 0.01).store_lo
+
+
+def test_cost_balanced_row_bounds_equalise_a_measured_imbalance():
+    """bench.py --gpus N re-cuts the row blocks from the busy time every rank measured: the rank that owns the wall (slower per row)
+    gets fewer rows; a second pass on the re-measured costs converges; bounds stay ascending with a minimum block height."""
+    from coupledwateranimation_b200.distributed import SlabPlan
+    rb = [0, 1000, 2000, 3000, 4000]
+    per_row = lambda row: 2.0e-3 if row < 300 else 1.0e-3            # the first 300 rows (a wall region) cost twice as much
+    cost = lambda b: [sum(per_row(r) for r in range(b[k], b[k + 1])) for k in range(4)]
+    c0 = cost(rb)
+    assert max(c0) / (sum(c0) / 4) > 1.2
+    rb1 = SlabPlan.cost_balanced_row_bounds(rb, c0)
+    assert rb1[0] == 0 and rb1[-1] == 4000 and all(b - a >= 8 for a, b in zip(rb1, rb1[1:]))
+    assert rb1[1] < 1000                                            # the expensive rank shrinks
+    rb2 = SlabPlan.cost_balanced_row_bounds(rb1, cost(rb1))
+    c2 = cost(rb2)
+    assert max(c2) / (sum(c2) / 4) < 1.03, (rb2, c2)
+    # damping moves part of the way; min_rows is honoured even for absurd costs
+    rbd = SlabPlan.cost_balanced_row_bounds(rb, c0, damping=0.5)
+    assert rb1[1] < rbd[1] < 1000
+    tight = SlabPlan.cost_balanced_row_bounds(rb, [1000.0, 1.0, 1.0, 1.0], min_rows=100)
+    assert all(b - a >= 100 for a, b in zip(tight, tight[1:]))
