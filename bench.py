@@ -222,6 +222,17 @@ def run_reference(args):
     if os.environ.get("OMP_NUM_THREADS", "") in ("", "1"):
         os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     steps, warmup = max(1, args.steps), max(0, args.warmup)
+    if args.config != "C4" and max(1, args.gpus) == 1:     # configs 1-3: the same CPU restatement, bounded to a few dozen steps
+        import bench_configs
+        from oracle import oracle as O
+        n_run = min(steps, 40 if args.config != "C3" else 20)
+        metric, unit, value, ms, cores, sample, workload = bench_configs.cpu_reference(args.config, O, n_run)
+        print(json.dumps({"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": ms,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "steps_per_sec": 1e3 / ms,
+                          "config": {"workload": workload, "note": "CPU restatement of the reference GLSL (no Mesa/llvmpipe in image)"},
+                          "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+                          "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
     # bounded: a full C4 frame costs a few seconds on the host cores; cap the frame count so the run ends in minutes
     world = max(1, args.gpus)
     steps_run, warm_run = (min(steps, 40), min(warmup, 3)) if world == 1 else (min(steps, 5), min(warmup, 1))

@@ -257,3 +257,46 @@ def brief_rows(cwa, ctx, torch, peak, peak_src):
         except Exception as e:                      # a side row must never take the headline line down
             out[name] = {"error": str(e)[:200]}
     return out
+
+
+def cpu_reference(config: str, oracle, steps: int):
+    """The reference arm of configs 1-3 (`bench.py --impl reference --config X`): the CPU restatement of the reference on the host cores,
+    bounded to `steps` steps.  Returns (metric, unit, value, ms_per_step, cores, sample, workload)."""
+    cores = oracle.lib().orc_num_threads()
+    if config == "D":
+        n, wv = 20480, 64
+        prm = oracle.default_params3()
+        oc = oracle.Coupled(n, wv, wv, 4, prm, oracle.COUPLING_AS_SHIPPED)
+        oc.particles[:] = oracle.make_cube(64, 5, 64, prm)
+        oc.step(2)
+        t0 = time.perf_counter(); oc.step(steps); dt = time.perf_counter() - t0
+        oc.close()
+        return ("particle_updates_per_sec", "particle-updates/s", n * steps / dt, dt / steps * 1e3, cores,
+                f"{steps} full frames of the shipped scene after 2 warm-up frames, OpenMP on {cores} host threads",
+                f"D: the shipped scene, {n} particles (64x5x64 lattice) all-pairs + {wv}^2 RGBA32F wave, coupling AS_SHIPPED (Main.cpp:28-35,184-204)")
+    if config == "C2":
+        n, ext = 65536, ((0.0, 0.0), (38.4, 9.6), (128, 32))
+        prm = oracle.default_params2(1)
+        prm.init_width = 512
+        prm.view_width = 38.4
+        b0 = oracle.sph2_init(n, prm); b1 = np.zeros_like(b0)
+        g = oracle.grid2(*ext)
+        r, _ = oracle.sph2_step(b0, b1, 0, 2, prm, None, g)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            r, _ = oracle.sph2_step(b0, b1, r, 2, prm, None, g)
+        dt = time.perf_counter() - t0
+        return ("particle_updates_per_sec", "particle-updates/s (one update = one frame = 2 substeps)", n * steps / dt, dt / steps * 1e3, cores,
+                f"{steps} frames (2 substeps each) after 1 warm-up frame, {cores} host threads",
+                f"C2: SphWave2D Koschier 2-D SPH (wave variant) on the uniform grid + prefix scan, {n} particles (512x128 lattice), 128x32 cells of 0.3, 2 substeps per frame")
+    if config == "C3":
+        size = 4096
+        u0 = oracle.wave_init(size, size, 1, oracle.WAVE_SIMP); u1 = u0.copy()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            u0, u1 = oracle.wave_evolve(u0, u1, oracle.WAVE_SIMP, 0.01, 0.9995, 0.001), u0
+        dt = time.perf_counter() - t0
+        return ("wave_cell_updates_per_sec", "cell-updates/s", size * size * steps / dt, dt / steps * 1e3, cores,
+                f"{steps} steps of the {size}^2 field, {cores} host threads",
+                f"C3: Wave2DSimp {size}^2 triple-buffered wave stencil (Wave2D_cs.glsl:78-103), scalar R32F; RGBA32F-compatible row beside it")
+    raise ValueError(config)

@@ -694,7 +694,7 @@ sph3_density_list_kernel(const float4* __restrict__ posS, const float4* __restri
 // (more than 3 x 3 rows) -- go to the heavy kernels (one warp per target, generic loops).
 // ---------------------------------------------------------------------------------------------
 constexpr int INPLACE_MARK = EXTREME_MARK + 1; // neighbour count of a clump target the density pass finished in place, without masks
-constexpr int INPLACE_MAX = 1024;         // candidates up to which the density pass finishes a clump target in place (tuning "inplace_max"; beyond: one warp per target)
+constexpr int INPLACE_MAX = 640;          // candidates up to which the density pass finishes a clump target in place (tuning "inplace_max"; beyond: one warp per target)
 constexpr int ROW_MASK_BITS = 31;         // longest row a mask records: with an odd first slot the pair loop shifts by (length + 1) - 1 at most
 struct FlatRows { int b[RT_ROWS], e[RT_ROWS]; int total; bool wide, longrow; int cell_lin; };   // cell_lin: the target's cell (fast path), -1 = generic query
 
@@ -1444,6 +1444,117 @@ sph3_force_allpairs_kernel(const float4* __restrict__ aos, int n, const Sph3Cons
     }
 }
 
+// SM-balanced all-pairs kernels (used when the targets of one SM fit one CTA: n <= 1024 x SMs; the shipped scene has 138 per SM).
+// The kernels above cut the targets into tiles of 64: 20 480 targets = 320 CTAs on 148 SMs = 2.16 per SM, i.e. the SMs that get three
+// CTAs set the time and the rest idle a third of it.  Here ONE CTA per SM owns ceil(n / SMs) consecutive targets and spends its up to
+// 1024 threads on them, L lanes each (L need not be a power of two: the partial sums meet in shared memory, fixed order); every
+// candidate tile is staged once per SM.  The density accumulation is branch-free (weight 0 when rejected).
+constexpr int APB_THREADS = 1024;
+constexpr int APB_TILE = 256;         // candidates per tile: at most 64 per lane (the force kernel's accept mask) for L >= 4
+
+__global__ void __launch_bounds__(APB_THREADS)
+sph3_density_allpairs_bal_kernel(const float4* __restrict__ aos, int n, int tpc, int L, const Sph3Const* __restrict__ cc, TexView tex,
+                                 float2* __restrict__ out_rp)
+{
+    __shared__ float4 tile[APB_TILE];
+    __shared__ float part[APB_THREADS];
+    const int tid = threadIdx.x;
+    const int tl = tid / L, sub = tid - tl * L;
+    const int i = blockIdx.x * tpc + tl;
+    const bool active = tl < tpc && i < n;
+    const float accept_r2 = cc->accept_r2, h2 = cc->h2, poly6 = cc->poly6;
+    const float4 p = active ? aos[(size_t)i * 4] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float rho = 0.0f;
+    for (int j0 = 0; j0 < n; j0 += APB_TILE) {
+        if (tid < APB_TILE) {
+            const int j = j0 + tid;
+            tile[tid] = (j < n) ? aos[(size_t)j * 4] : make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f);
+        }
+        __syncthreads();
+        if (active) {
+#pragma unroll 4
+            for (int q = sub; q < APB_TILE; q += L) {
+                const float4 c = tile[q];
+                const float r2 = cwa_len3sq(p.x - c.x, p.y - c.y, p.z - c.z);
+                const float d = (r2 <= accept_r2) ? (h2 - r2) : 0.0f;
+                rho = fmaf(poly6, d * d * d, rho);
+            }
+        }
+        __syncthreads();
+    }
+    part[tid] = rho;
+    __syncthreads();
+    if (active && sub == 0) {
+        float sum = 0.0f;
+        for (int l = 0; l < L; l++) sum += part[tid + l];
+        float rho_out, prs_out;
+        density_epilogue(*cc, tex, p.x, p.z, sum, rho_out, prs_out);
+        out_rp[i] = make_float2(rho_out, prs_out);     // committed to the SSBO after the pass
+    }
+}
+
+__global__ void __launch_bounds__(APB_THREADS)
+sph3_force_allpairs_bal_kernel(const float4* __restrict__ aos, int n, int tpc, int L, const Sph3Const* __restrict__ cc, TexView tex,
+                               float4* __restrict__ out_force)
+{
+    __shared__ float4 tileA[APB_TILE];
+    __shared__ float4 tileB[APB_TILE];
+    __shared__ float part[6][APB_THREADS];
+    const int tid = threadIdx.x;
+    const int tl = tid / L, sub = tid - tl * L;
+    const int i = blockIdx.x * tpc + tl;
+    const bool active = tl < tpc && i < n;
+    const Sph3Const c = *cc;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f), v = p, e = p;
+    if (active) { p = aos[(size_t)i * 4]; v = aos[(size_t)i * 4 + 1]; e = aos[(size_t)i * 4 + 3]; }
+    float fpx = 0.f, fpy = 0.f, fpz = 0.f, fvx = 0.f, fvy = 0.f, fvz = 0.f;
+    const int per_lane = (APB_TILE + L - 1) / L;       // <= 64: the launcher keeps L >= 4
+    for (int j0 = 0; j0 < n; j0 += APB_TILE) {
+        if (tid < APB_TILE) {
+            const int j = j0 + tid;
+            if (j < n) {
+                const float4 qp = aos[(size_t)j * 4], qv = aos[(size_t)j * 4 + 1], qe = aos[(size_t)j * 4 + 3];
+                tileA[tid] = make_float4(qp.x, qp.y, qp.z, qe.y);
+                tileB[tid] = make_float4(qv.x, qv.y, qv.z, qe.x);
+            } else {
+                tileA[tid] = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f);
+                tileB[tid] = make_float4(0.f, 0.f, 0.f, 1.f);
+            }
+        }
+        __syncthreads();
+        if (active) {
+            // two phases: mark the accepted candidates of the lane (cheap, every candidate), then evaluate only those
+            unsigned long long mask = 0ull;
+#pragma unroll 4
+            for (int t = 0; t < per_lane; t++) {
+                const int q = sub + t * L;
+                if (q < APB_TILE) {
+                    const float4 qa = tileA[q];
+                    const float r2 = cwa_len3sq(p.x - qa.x, p.y - qa.y, p.z - qa.z);
+                    if (r2 <= c.accept_r2 && (j0 + q) != i) mask |= (1ull << t);
+                }
+            }
+            while (mask) {
+                const int t = __ffsll((long long)mask) - 1;
+                mask &= mask - 1ull;
+                const int q = sub + t * L;
+                pair_force(c, p.x, p.y, p.z, e.y, v.x, v.y, v.z, tileA[q], tileB[q], fpx, fpy, fpz, fvx, fvy, fvz);
+            }
+        }
+        __syncthreads();
+    }
+    part[0][tid] = fpx; part[1][tid] = fpy; part[2][tid] = fpz; part[3][tid] = fvx; part[4][tid] = fvy; part[5][tid] = fvz;
+    __syncthreads();
+    if (active && sub == 0) {
+        float sm[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int l = 0; l < L; l++)
+#pragma unroll
+            for (int k = 0; k < 6; k++) sm[k] += part[k][tid + l];
+        const float4 fprev = aos[(size_t)i * 4 + 2];
+        out_force[i] = force_epilogue(c, tex, p.x, p.y, p.z, v.x, v.y, v.z, e.x, fprev, sm[0], sm[1], sm[2], sm[3], sm[4], sm[5]);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 sph3_commit_force_kernel(const float4* __restrict__ f, int n, float4* __restrict__ aos)
 {
@@ -1550,6 +1661,7 @@ static int pipeline_mode(cwa_ctx* c) { if (c->tune.pipeline < 0) c->tune.pipelin
 static int nbr_k(cwa_ctx* c) { if (c->tune.nbr_k < 0) c->tune.nbr_k = env_int("CWA_NBR_K", NBR_K_DEFAULT, 8, NBR_K_MAX) & ~3; return c->tune.nbr_k; }
 static int extreme_candidates(cwa_ctx* c) { if (c->tune.extreme < 0) c->tune.extreme = env_int("CWA_EXTREME", EXTREME_CANDIDATES, 16, 1 << 20); return c->tune.extreme; }
 static int inplace_max(cwa_ctx* c) { if (c->tune.inplace_max < 0) c->tune.inplace_max = env_int("CWA_INPLACE_MAX", INPLACE_MAX, 0, 1 << 20); return c->tune.inplace_max; }
+static bool allpairs_balanced(cwa_ctx* c) { if (c->tune.allpairs_bal < 0) c->tune.allpairs_bal = env_int("CWA_ALLPAIRS_BALANCED", 1, 0, 2); return c->tune.allpairs_bal != 0; }
 static bool fused_order(cwa_ctx* c) { if (c->tune.fused_order < 0) c->tune.fused_order = env_int("CWA_FUSED_ORDER", 1, 0, 1); return c->tune.fused_order != 0; }
 
 extern "C" int cwa_set_tuning(cwa_ctx* ctx, const char* key, int value)
@@ -1563,6 +1675,7 @@ extern "C" int cwa_set_tuning(cwa_ctx* ctx, const char* key, int value)
     else if (k == "fused_order") { ctx->tune.fused_order = value ? 1 : 0; }
     else if (k == "fused_integrate") { ctx->tune.fused_integrate = value ? 1 : 0; }
     else if (k == "nbr_k") { CWA_CHECK(value >= 8 && value <= NBR_K_MAX && value % 4 == 0, "nbr_k %d: multiple of 4 in [8, %d]", value, NBR_K_MAX); ctx->tune.nbr_k = value; }
+    else if (k == "allpairs_balanced") { CWA_CHECK(value >= 0 && value <= 2, "allpairs_balanced %d: 0 off, 1 density pass, 2 both passes", value); ctx->tune.allpairs_bal = value; }
     else if (k == "inplace_max") { CWA_CHECK(value >= 0, "inplace_max %d negative", value); ctx->tune.inplace_max = value; }
     else if (k == "extreme_candidates") { CWA_CHECK(value >= 16, "extreme_candidates %d too small", value); ctx->tune.extreme = value; }
     else if (k == "wave_transpose") { ctx->tune.wave_transpose = value ? 1 : 0; }
@@ -1749,15 +1862,24 @@ int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which, bool co
 
     if (s->grid < 0) {                                             // ---- all-pairs, as shipped
         const int blocks = ceil_div(n, AP_TT);
+        // one CTA per SM with an equal share of the targets when that share fits a CTA with at least 4 lanes per target
+        const int tpc = ceil_div(n, ctx->sm_count);
+        const int lanes = tpc > 0 ? (APB_THREADS / tpc < 32 ? APB_THREADS / tpc : 32) : 0;
+        const bool balanced = lanes >= 4 && allpairs_balanced(ctx);
+        const int bal_blocks = balanced ? ceil_div(n, tpc) : 0;
         if (which & 1) {
             { KScope k(ctx, KID_DENSITY);
-              sph3_density_allpairs_kernel<<<blocks, AP_TT * AP_L, 0, ctx->stream>>>(aos, n, cc, tex, sph_scratch_rp(s)); }
+              if (balanced) sph3_density_allpairs_bal_kernel<<<bal_blocks, APB_THREADS, 0, ctx->stream>>>(aos, n, tpc, lanes, cc, tex, sph_scratch_rp(s));
+              else sph3_density_allpairs_kernel<<<blocks, AP_TT * AP_L, 0, ctx->stream>>>(aos, n, cc, tex, sph_scratch_rp(s)); }
             { KScope k(ctx, KID_OTHER);
               sph3_commit_rho_pres_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(sph_scratch_rp(s), n, aos); }
         }
         if (which & 2) {
             { KScope k(ctx, KID_FORCE);
-              sph3_force_allpairs_kernel<<<blocks, AP_TT * AP_L, 0, ctx->stream>>>(aos, n, cc, tex, sph_scratch_force(s)); }
+              // (the SM-balanced force variant measured slower on the shipped scene: 461 vs 448 us -- 62 registers x 1024 threads leave one CTA
+              // per SM; it is kept behind the tuning value 2 for other shapes)
+              if (balanced && ctx->tune.allpairs_bal == 2) sph3_force_allpairs_bal_kernel<<<bal_blocks, APB_THREADS, 0, ctx->stream>>>(aos, n, tpc, lanes, cc, tex, sph_scratch_force(s));
+              else sph3_force_allpairs_kernel<<<blocks, AP_TT * AP_L, 0, ctx->stream>>>(aos, n, cc, tex, sph_scratch_force(s)); }
             { KScope k(ctx, KID_OTHER);
               sph3_commit_force_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(sph_scratch_force(s), n, aos); }
         }
