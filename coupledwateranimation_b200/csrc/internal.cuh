@@ -151,6 +151,8 @@ struct SphObj {
     int  wave_image = -1;          // physical image, -1 unbound
     // cell-ordered snapshot (grid mode) -- see DESIGN.md "data layout"
     float4 *posS = nullptr, *velS = nullptr, *forceS = nullptr, *miscS = nullptr;
+    float  *xyzS = nullptr;                        // x | y | z coordinate streams of the snapshot (each xyz_stride floats): the density pass's candidates
+    size_t  xyz_stride = 0;
     float4 *pack = nullptr;                      // per slot two float4: (pos.xyz, p) at 2s and (vel.xyz, rho) at 2s+1 -- one 32-byte sector
     float4 *scratch = nullptr;                   // all-pairs mode: pass results before they are committed to the SSBO
     float4 *pairP = nullptr;                     // neighbour sums of the force pass: (pres.xyz, visc.x)

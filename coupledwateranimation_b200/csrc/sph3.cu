@@ -242,7 +242,7 @@ __device__ __forceinline__ void integrate_particle(const Sph3Const& c, const Tex
 __global__ void __launch_bounds__(256)
 sph3_reorder_kernel(const float4* __restrict__ aos, const int* __restrict__ index_list, const int* __restrict__ count,
                     float4* __restrict__ posS, float4* __restrict__ velS, float4* __restrict__ forceS,
-                    float4* __restrict__ miscS, int* __restrict__ heavy_cnt)
+                    float4* __restrict__ miscS, int* __restrict__ heavy_cnt, float* __restrict__ xyzS, size_t xyz_stride)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t == 0) { heavy_cnt[0] = 0; heavy_cnt[1] = 0; }   // clump queues of the density / force passes that follow this snapshot
@@ -258,7 +258,7 @@ sph3_reorder_kernel(const float4* __restrict__ aos, const int* __restrict__ inde
     const float pw = __shfl_sync(0xffffffffu, v.w, quad + 0);
     const float vw = __shfl_sync(0xffffffffu, v.w, quad + 1);
     if (s >= n) return;
-    if (q == 0) posS[s] = v;
+    if (q == 0) { posS[s] = v; xyzS[s] = v.x; xyzS[xyz_stride + s] = v.y; xyzS[2 * xyz_stride + s] = v.z; }
     else if (q == 1) velS[s] = v;
     else if (q == 2) forceS[s] = v;
     else miscS[s] = make_float4(pw, vw, v.z, v.w);      // (pos.w, vel.w, extras.z, extras.w)
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(256)
 sph3_order_reorder_kernel(const float4* __restrict__ aos, const int* __restrict__ arrival, const int* __restrict__ cell_of,
                           const int* __restrict__ offset, const int* __restrict__ count, int* __restrict__ index_list,
                           float4* __restrict__ posS, float4* __restrict__ velS, float4* __restrict__ forceS,
-                          float4* __restrict__ miscS, int* __restrict__ heavy_cnt)
+                          float4* __restrict__ miscS, int* __restrict__ heavy_cnt, float* __restrict__ xyzS, size_t xyz_stride)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s == 0) { heavy_cnt[0] = 0; heavy_cnt[1] = 0; }   // clump queues of the density / force passes that follow this snapshot
@@ -290,6 +290,7 @@ sph3_order_reorder_kernel(const float4* __restrict__ aos, const int* __restrict_
     index_list[t] = id;
     posS[t] = r0; velS[t] = r1; forceS[t] = r2;
     miscS[t] = make_float4(r0.w, r1.w, r3.z, r3.w);          // (pos.w, vel.w, extras.z, extras.w)
+    xyzS[t] = r0.x; xyzS[xyz_stride + t] = r0.y; xyzS[2 * xyz_stride + t] = r0.z;   // coordinate streams of the density pass
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -695,6 +696,14 @@ sph3_density_list_kernel(const float4* __restrict__ posS, const float4* __restri
 // ---------------------------------------------------------------------------------------------
 constexpr int INPLACE_MARK = EXTREME_MARK + 1; // neighbour count of a clump target the density pass finished in place, without masks
 constexpr int INPLACE_MAX = 640;          // candidates up to which the density pass finishes a clump target in place (tuning "inplace_max"; beyond: one warp per target)
+// packed FP32 pairs (sm_100: FADD2 / FMUL2 / FFMA2; each half is rounded like the scalar instruction)
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned long long f2_sub(unsigned long long a, unsigned long long b) { unsigned long long r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) { unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) { unsigned long long r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ unsigned long long f2_ldg(const float* p) { unsigned long long r; asm("ld.global.nc.b64 %0, [%1];" : "=l"(r) : "l"(p)); return r; }
+
 constexpr int ROW_MASK_BITS = 31;         // longest row a mask records: with an odd first slot the pair loop shifts by (length + 1) - 1 at most
 struct FlatRows { int b[RT_ROWS], e[RT_ROWS]; int total; bool wide, longrow; int cell_lin; };   // cell_lin: the target's cell (fast path), -1 = generic query
 
@@ -758,7 +767,8 @@ __device__ __forceinline__ int2* rows_of(int2* nbr_rows, int slot) { return nbr_
 
 template <bool LOCAL>
 __global__ void __launch_bounds__(TILE_P)
-sph3_density_flat_kernel(const float4* __restrict__ posS, const float4* __restrict__ velS, float4* __restrict__ pack,
+sph3_density_flat_kernel(const float4* __restrict__ posS, const float* __restrict__ xyzS, const size_t xyz_stride,
+                         const float4* __restrict__ velS, float4* __restrict__ pack,
                          int2* __restrict__ nbr_rows, int* __restrict__ nbr_count,
                          int* __restrict__ heavy_queue, int* __restrict__ heavy_count,
                          int n_max, GridView g, const int* __restrict__ offset, const Sph3Const* __restrict__ cc, TexView tex,
@@ -790,34 +800,42 @@ sph3_density_flat_kernel(const float4* __restrict__ posS, const float4* __restri
     for (int r = 0; r < RT_ROWS; r++)
         if (fr.e[r] > fr.b[r]) { tab[nr * TILE_P + tid] = make_int2(fr.b[r], fr.e[r]); nr++; }
 
-    float rho = 0.0f;
+    // The candidates come as three coordinate streams (x | y | z, written by the reorder pass next to posS): a pair of consecutive slots
+    // is one aligned 64-bit word per coordinate -- 24 bytes per pair through the L1 data pipe (the limit of this kernel, profiles/r2)
+    // instead of the 32 of two float4 -- and lands in a register pair, so the whole distance evaluation runs on Blackwell's packed
+    // FP32 instructions (sub / mul / fma .f32x2 = FADD2 / FMUL2 / FFMA2: both candidates of the pair per issue slot, each lane rounded
+    // exactly like the scalar instruction, so the accept test is bit-identical to cwa_len3sq of the oracle).
+    unsigned long long rho2 = 0ull;                    // partial sums of the two slots of a pair
     unsigned mask = 0u;
-    // One candidate: accepted <=> inside the row (head: j >= bound, tail: j < bound) and r2 <= accept_r2; the mask bit and the poly6
-    // weight hang on the same predicate, formed once -- nothing branches.
-    auto step = [&](const float4 qp, int j, int bound, unsigned bit, const bool head) {
-        const float r2 = cwa_len3sq(p.x - qp.x, p.y - qp.y, p.z - qp.z);
-        const float hd = h2 - r2;
-        float d;
-        if (head)
-            asm("{\n\t.reg .pred v, q;\n\tsetp.ge.s32 v, %4, %5;\n\tsetp.le.and.f32 q, %2, %3, v;\n\t@q or.b32 %0, %0, %6;\n\t"
-                "selp.f32 %1, %7, 0f00000000, q;\n\t}"
-                : "+r"(mask), "=f"(d) : "f"(r2), "f"(accept_r2), "r"(j), "r"(bound), "r"(bit), "f"(hd));
-        else
-            asm("{\n\t.reg .pred v, q;\n\tsetp.lt.s32 v, %4, %5;\n\tsetp.le.and.f32 q, %2, %3, v;\n\t@q or.b32 %0, %0, %6;\n\t"
-                "selp.f32 %1, %7, 0f00000000, q;\n\t}"
-                : "+r"(mask), "=f"(d) : "f"(r2), "f"(accept_r2), "r"(j), "r"(bound), "r"(bit), "f"(hd));
-        rho = fmaf(poly6, d * d * d, rho);
+    const unsigned long long px2 = f2_pack(p.x, p.x), py2 = f2_pack(p.y, p.y), pz2 = f2_pack(p.z, p.z);
+    const unsigned long long h22 = f2_pack(h2, h2), poly2 = f2_pack(poly6, poly6);
+    const float* const xs = xyzS; const float* const ys = xyzS + xyz_stride; const float* const zs = xyzS + 2 * xyz_stride;
+    // one pair (slots j, j + 1) against the target; slot j counts iff j >= first (head), slot j + 1 iff j + 1 < end (tail)
+    auto step2 = [&](unsigned long long X, unsigned long long Y, unsigned long long Z, int j, int first, int end, unsigned bit1) {
+        const unsigned long long dx = f2_sub(px2, X), dy = f2_sub(py2, Y), dz = f2_sub(pz2, Z);
+        const unsigned long long r2 = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
+        const unsigned long long hd = f2_sub(h22, r2);
+        float r2a, r2b, hda, hdb, da, db;
+        f2_unpack(r2, r2a, r2b); f2_unpack(hd, hda, hdb);
+        asm("{\n\t.reg .pred v, q;\n\tsetp.ge.s32 v, %4, %5;\n\tsetp.le.and.f32 q, %2, %3, v;\n\t@q or.b32 %0, %0, %6;\n\t"
+            "selp.f32 %1, %7, 0f00000000, q;\n\t}"
+            : "+r"(mask), "=f"(da) : "f"(r2a), "f"(accept_r2), "r"(j), "r"(first), "r"(bit1 >> 1), "f"(hda));
+        asm("{\n\t.reg .pred v, q;\n\tsetp.lt.s32 v, %4, %5;\n\tsetp.le.and.f32 q, %2, %3, v;\n\t@q or.b32 %0, %0, %6;\n\t"
+            "selp.f32 %1, %7, 0f00000000, q;\n\t}"
+            : "+r"(mask), "=f"(db) : "f"(r2b), "f"(accept_r2), "r"(j + 1), "r"(end), "r"(bit1), "f"(hdb));
+        const unsigned long long d = f2_pack(da, db);
+        rho2 = f2_fma(poly2, f2_mul(f2_mul(d, d), d), rho2);
     };
     if (nr > 0) {
         int2* tp = tab + tid;                          // the lane's current row in the table; rows are TILE_P entries apart
         const int2* const tp_last = tab + (nr - 1) * TILE_P + tid;
         int2 row = *tp;
         int j = row.x & ~1;
-        f4x2 A = cwa_ldg256(posS + j), B = A;
-        // One stage: find where the NEXT pair comes from (the same row, or the first pair of the lane's next row), issue its load into
+        unsigned long long AX = f2_ldg(xs + j), AY = f2_ldg(ys + j), AZ = f2_ldg(zs + j), BX = AX, BY = AY, BZ = AZ;
+        // One stage: find where the NEXT pair comes from (the same row, or the first pair of the lane's next row), issue its loads into
         // NXT, then evaluate the pair held in CUR; a finished row leaves its mask in the table.  Two stages per trip ping-pong between
         // A and B, so no pair is ever copied.  The table has one spare row: the entry behind the last row is read, never used.
-#define CWA_FLAT_STAGE(CUR, NXT)                                                                   \
+#define CWA_FLAT_STAGE(CX, CY, CZ, NX, NY, NZ)                                                     \
         {                                                                                          \
             const bool adv = j + 2 >= row.y;                                                       \
             const bool more = !adv || tp != tp_last;                                               \
@@ -826,20 +844,21 @@ sph3_density_flat_kernel(const float4* __restrict__ posS, const float4* __restri
             const int2 cand = *tp;                                                                 \
             const int2 rown = adv ? cand : row;                                                    \
             const int jn = adv ? (cand.x & ~1) : j + 2;                                            \
-            if (more) NXT = cwa_ldg256(posS + jn);                                                 \
-            const unsigned bit1 = 1u << (j + 1 - row.x);      /* j + 1 >= first slot, always */    \
-            step(CUR.a, j, row.x, bit1 >> 1, true);   /* the slot before an odd row start */       \
-            step(CUR.b, j + 1, row.y, bit1, false);   /* the slot after the row end (padded) */    \
+            if (more) { NX = f2_ldg(xs + jn); NY = f2_ldg(ys + jn); NZ = f2_ldg(zs + jn); }        \
+            step2(CX, CY, CZ, j, row.x, row.y, 1u << (j + 1 - row.x));                             \
             if (adv) { tp_cur->y = (int)mask; mask = 0u; }                                         \
             if (!more) break;                                                                      \
             j = jn; row = rown;                                                                    \
         }
         while (true) {
-            CWA_FLAT_STAGE(A, B)
-            CWA_FLAT_STAGE(B, A)
+            CWA_FLAT_STAGE(AX, AY, AZ, BX, BY, BZ)
+            CWA_FLAT_STAGE(BX, BY, BZ, AX, AY, AZ)
         }
 #undef CWA_FLAT_STAGE
     }
+    float rho_lo, rho_hi;
+    f2_unpack(rho2, rho_lo, rho_hi);
+    const float rho = rho_lo + rho_hi;
     float rho_out, prs_out;
     density_epilogue<LOCAL>(*cc, tex, p.x, p.z, rho, rho_out, prs_out);
     const float4 v = __ldg(velS + slot);
@@ -1739,10 +1758,10 @@ static int launch_density_list(cwa_ctx* ctx, SphObj* s, GridObj* g, TexView tex,
         int2* rows = reinterpret_cast<int2*>(s->nbr_list);
         if (local)
             sph3_density_flat_kernel<true><<<ntiles, TILE_P, 0, ctx->stream>>>(
-                s->posS, s->velS, s->pack, rows, s->nbr_count, s->heavy_queue, hc, s->n, g->view, g->offset, cc, tex, extreme_candidates(ctx), inplace_max(ctx));
+                s->posS, s->xyzS, s->xyz_stride, s->velS, s->pack, rows, s->nbr_count, s->heavy_queue, hc, s->n, g->view, g->offset, cc, tex, extreme_candidates(ctx), inplace_max(ctx));
         else
             sph3_density_flat_kernel<false><<<ntiles, TILE_P, 0, ctx->stream>>>(
-                s->posS, s->velS, s->pack, rows, s->nbr_count, s->heavy_queue, hc, s->n, g->view, g->offset, cc, tex, extreme_candidates(ctx), inplace_max(ctx));
+                s->posS, s->xyzS, s->xyz_stride, s->velS, s->pack, rows, s->nbr_count, s->heavy_queue, hc, s->n, g->view, g->offset, cc, tex, extreme_candidates(ctx), inplace_max(ctx));
     } else {
       KScope k(ctx, KID_DENSITY);
       if (local)
@@ -1806,11 +1825,11 @@ static int sph_snapshot(cwa_ctx* ctx, SphObj* s, bool count_next_ahead = false)
         KScope k(ctx, KID_REORDER);
         sph3_order_reorder_kernel<<<ceil_div(s->n > 0 ? s->n : 1, 256), 256, 0, ctx->stream>>>(
             (const float4*)pb->ptr, g->arrival, g->cell_of, g->offset, g->offset + g->view.num_cells, g->index_list,
-            s->posS, s->velS, s->forceS, s->miscS, s->heavy_cnt);
+            s->posS, s->velS, s->forceS, s->miscS, s->heavy_cnt, s->xyzS, s->xyz_stride);
     } else {
         KScope k(ctx, KID_REORDER);
         sph3_reorder_kernel<<<ceil_div((long long)(s->n > 0 ? s->n : 1) * 4, 256), 256, 0, ctx->stream>>>(
-            (const float4*)pb->ptr, g->index_list, g->offset + g->view.num_cells, s->posS, s->velS, s->forceS, s->miscS, s->heavy_cnt);
+            (const float4*)pb->ptr, g->index_list, g->offset + g->view.num_cells, s->posS, s->velS, s->forceS, s->miscS, s->heavy_cnt, s->xyzS, s->xyz_stride);
     }
     CWA_CUDA(cudaGetLastError());
     s->snapshot_valid = true;
@@ -1994,6 +2013,9 @@ extern "C" int cwa_sph_create(cwa_ctx* ctx, cwa_buf particles, int n, cwa_grid g
     if (grid >= 0) {
         CWA_CUDA(cudaMalloc(&s.posS, bytes));
         CWA_CUDA(cudaMemsetAsync(s.posS, 0, bytes, ctx->stream));     // the 4 pad slots are read (and masked out) by the neighbour loops
+        s.xyz_stride = ((size_t)(n > 0 ? n : 1) + 4 + 31) / 32 * 32;    // x | y | z streams, each padded like posS and 128-byte aligned
+        CWA_CUDA(cudaMalloc(&s.xyzS, 3 * s.xyz_stride * sizeof(float)));
+        CWA_CUDA(cudaMemsetAsync(s.xyzS, 0, 3 * s.xyz_stride * sizeof(float), ctx->stream));
         CWA_CUDA(cudaMalloc(&s.velS, bytes));
         CWA_CUDA(cudaMalloc(&s.forceS, bytes));
         CWA_CUDA(cudaMalloc(&s.miscS, bytes));
@@ -2019,7 +2041,7 @@ extern "C" int cwa_sph_destroy(cwa_ctx* ctx, cwa_sph h)
     SphObj* s = get_sph(ctx, h);
     CWA_CHECK(s, "invalid sph handle %d", h);
     CWA_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(s->pack); cudaFree(s->scratch); cudaFree(s->posS); cudaFree(s->velS); cudaFree(s->forceS); cudaFree(s->miscS);
+    cudaFree(s->pack); cudaFree(s->scratch); cudaFree(s->posS); cudaFree(s->xyzS); cudaFree(s->velS); cudaFree(s->forceS); cudaFree(s->miscS);
     cudaFree(s->pairP); cudaFree(s->pairV); cudaFree(s->consts); cudaFree(s->nbr_list); cudaFree(s->nbr_count); cudaFree(s->heavy_queue);
     cudaFree(s->heavy_cnt); cudaFree(s->cell_next); cudaFree(s->rank_next);
     for (auto& g : s->frame_graph) if (g.valid) { cudaGraphExecDestroy((cudaGraphExec_t)g.exec); g.valid = false; }

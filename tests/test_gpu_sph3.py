@@ -86,6 +86,27 @@ def test_force_pass(cwa, ctx, oracle, use_grid):
     assert np.array_equal(got["pos"], p["pos"]) and np.array_equal(got["vel"], p["vel"])
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_allpairs_kernel_variants(cwa, ctx, oracle, mode):
+    """The all-pairs passes have two CTA shapes: tiles of 64 targets (0), and one CTA per SM with an equal share of the targets for the
+    density pass (1, the default) or both passes (2).  2880 particles / 148 SMs = 20 targets per CTA, 32 lanes each."""
+    try:
+        ctx.set_tuning(allpairs_balanced=mode)
+        prm, p, tex, sph, wave = _scene(cwa, ctx, oracle, False)
+        sph.rho_pres()
+        sph.force()
+        got = sph.download()
+        ref = p.copy()
+        oracle.sph3_rho_pres(ref, prm, tex)
+        oracle.sph3_force(ref, prm, tex)
+        assert_close(got["extras"][:, 0], ref["extras"][:, 0], what="rho")
+        assert_close(got["extras"][:, 1], ref["extras"][:, 1], what="pressure")
+        assert_close(got["force"][:, :3], ref["force"][:, :3], what="force.xyz")
+        assert np.array_equal(got["force"][:, 3], ref["force"][:, 3])
+    finally:
+        ctx.set_tuning(allpairs_balanced=1)
+
+
 @pytest.mark.parametrize("use_grid", [False, True])
 def test_integrate_pass_and_branch_decisions(cwa, ctx, oracle, use_grid):
     prm, p, tex, sph, wave = _scene(cwa, ctx, oracle, use_grid, vel=40.0)      # some |v| > 25: foam rule fires
