@@ -332,15 +332,27 @@ grid_cell_order_kernel(const int* __restrict__ cell_of, const int* __restrict__ 
 // public cell_of[] array (original particle order) is kept up to date for the reorder pass and cwa_grid_read.
 __global__ void __launch_bounds__(256)
 grid_insert_ahead_kernel(const int* __restrict__ cell_s, const int* __restrict__ rank_s, const int* __restrict__ old_index_list,
-                         const int* __restrict__ offset, int n, int* __restrict__ cell_of, int* __restrict__ arrival)
+                         const int* __restrict__ offset, int n, int* __restrict__ cell_of, int* __restrict__ arrival, bool keep_vanished)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const int c = __ldg(cell_s + s);
     if (c == -2) return;                                           // slot beyond the previous build's inserted count
     const int id = __ldg(old_index_list + s);
-    cell_of[id] = c;
+    if (c >= 0 || !keep_vanished) cell_of[id] = c;                 // (slab frames: the slot of a particle that left may already hold an arrival)
     if (c >= 0) arrival[__ldg(offset + c) + __ldg(rank_s + s)] = id;
+}
+
+// arrivals of a slab exchange (hashed and counted by the unpack kernel): same insert, indexed by particle id
+__global__ void __launch_bounds__(256)
+grid_insert_arrivals_kernel(const int* __restrict__ ids, const int* __restrict__ count, int max_count, const int* __restrict__ cell_of,
+                            const int* __restrict__ rank, const int* __restrict__ offset, int* __restrict__ arrival)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= min(__ldg(count), max_count)) return;
+    const int id = __ldg(ids + u);
+    const int c = __ldg(cell_of + id);
+    if (c >= 0) arrival[__ldg(offset + c) + __ldg(rank + id)] = id;
 }
 
 int grid_build_internal(cwa_ctx* ctx, GridObj* g, const void* particles, int stride_bytes, int n, const GridBuildOpts& opts)
@@ -351,8 +363,12 @@ int grid_build_internal(cwa_ctx* ctx, GridObj* g, const void* particles, int str
     g->n_built = n;
     const int C = g->view.num_cells;
     if (!ahead) {
-        { KScope k(ctx, KID_CLEAR);                                            // ClearCounter + scan state, one memset
-          CWA_CUDA(cudaMemsetAsync(g->counter, 0, g->clear_bytes, ctx->stream)); }
+        if (g->cleared_ahead) {                                                // the previous build of this grid cleared them behind its scan (side stream)
+            CWA_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_pipe[1], 0));
+        } else {
+            KScope k(ctx, KID_CLEAR);                                          // ClearCounter + scan state, one memset
+            CWA_CUDA(cudaMemsetAsync(g->counter, 0, g->clear_bytes, ctx->stream));
+        }
         if (n > 0) {
             KScope k(ctx, KID_HASH_COUNT);
             if (g->dim == 2)
@@ -373,10 +389,17 @@ int grid_build_internal(cwa_ctx* ctx, GridObj* g, const void* particles, int str
           CWA_CUDA(cudaMemsetAsync(g->counter, 0, g->clear_bytes, ctx->stream)); }
         CWA_CUDA(cudaEventRecord(ctx->ev_pipe[1], ctx->side_stream[1]));
     }
+    g->cleared_ahead = opts.clear_after_scan && opts.clear_is_for_next_build;
     if (n > 0) {
         { KScope k(ctx, KID_INSERT);
           if (ahead)
-              grid_insert_ahead_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(opts.ahead_cell, opts.ahead_rank, g->index_list, g->offset, n, g->cell_of, g->arrival);
+          {
+              grid_insert_ahead_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(opts.ahead_cell, opts.ahead_rank, g->index_list, g->offset, n, g->cell_of, g->arrival,
+                                                                                  opts.arrivals != nullptr);
+              if (opts.arrivals != nullptr && opts.arrivals_max > 0)
+                  grid_insert_arrivals_kernel<<<ceil_div(opts.arrivals_max, 256), 256, 0, ctx->stream>>>(opts.arrivals, opts.arrivals_count, opts.arrivals_max,
+                                                                                                          g->cell_of, g->rank, g->offset, g->arrival);
+          }
           else
               grid_insert_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(g->cell_of, g->rank, g->offset, n, opts.n_dev, g->arrival); }
         CWA_CUDA(cudaGetLastError());

@@ -97,6 +97,7 @@ struct GridObj {
     GridView view{};
     int  max_particles = 0;
     int  n_built = 0;              // particle count of the last build
+    bool cleared_ahead = false;    // counter + scan state were cleared behind the last build's scan: the next build waits for ev_pipe[1] instead of clearing
     // one allocation, cleared by a single memset per build: [counter C][ticket][tile_state]
     int* counter = nullptr;        // int[C]
     int* ticket = nullptr;         // scan tile ticket
@@ -158,6 +159,8 @@ struct SphObj {
     float4 *pairP = nullptr;                     // neighbour sums of the force pass: (pres.xyz, visc.x)
     float2 *pairV = nullptr;                     //                                   (visc.y, visc.z)
     int   *nbr_list = nullptr, *nbr_count = nullptr;   // neighbour lists of the density pass ([slot][K]) and true counts
+    // slab frames: ids of the particles the last exchange brought in, hashed and counted by the unpack kernel (count-ahead across the exchange)
+    const int* arrivals = nullptr; const int* arrivals_count = nullptr; int arrivals_max = 0;
     bool   nbr_lists_valid = false;
     bool   nbr_rows_fmt = false;               // nbr_list holds row masks ([tile of 32][9 rows][lane] (first slot, accept mask)) instead of index lists
     int    nbr_k_alloc = 0, nbr_k_used = 0;                 // list capacity the array was sized for / the density pass built the lists with
@@ -239,7 +242,7 @@ struct ProfRec { int id; cudaEvent_t a, b; };
 // hold different settings.  -1 = not set yet: the default comes from the environment (CWA_NB_CONFIG, ...) on first use.
 struct CtxTuning {
     int config = -1, cap_d = -1, cap_f = -1, fused_order = -1, fused_integrate = -1, pipeline = -1, nbr_k = -1, extreme = -1;
-    int scan_config = -1, wave_transpose = -1, graph = -1, inplace_max = -1, allpairs_bal = -1;
+    int scan_config = -1, wave_transpose = -1, graph = -1, inplace_max = -1, allpairs_bal = -1, slab_ahead = -1;
 };
 
 struct SlabObj;
@@ -319,8 +322,14 @@ struct GridBuildOpts {
     // cell-ordered slot s of the PREVIOUS build are in ahead_cell[s] / ahead_rank[s] (-1: not inserted), s < n
     const int* ahead_cell = nullptr;
     const int* ahead_rank = nullptr;
-    bool clear_after_scan = false;     // the next build is counted ahead: clear counter + scan state right after this scan (side stream)
+    bool clear_after_scan = false;     // clear counter + scan state right after this scan (side stream): the next build is counted ahead ...
+    bool clear_is_for_next_build = false;   // ... or (slab frames) the next build starts from the cleared arrays instead of clearing them itself
     const int* n_dev = nullptr;        // device-resident particle count (slab decomposition): the host `n` is then only the launch bound
+    // count-ahead across a slab exchange: particles that ARRIVED after the counting integrate pass (migrants, ghosts) were hashed and
+    // counted by the unpack kernel (cell_of[id], rank[id]); their ids are arrivals[0 .. *arrivals_count)
+    const int* arrivals = nullptr;
+    const int* arrivals_count = nullptr;
+    int arrivals_max = 0;
 };
 int  grid_build_internal(cwa_ctx* ctx, GridObj* g, const void* particles, int stride_bytes, int n, const GridBuildOpts& opts = GridBuildOpts());
 TexView wave_tex_view(cwa_ctx* ctx, cwa_wave w, int image);           // wave.cu

@@ -53,6 +53,8 @@ struct SlabObj {
     float4* send[2] = {nullptr, nullptr};   // local send buffers: to the left / to the right neighbour
     SlabState* state = nullptr;       // [2], alternating with the particle message number
     int*   free_list = nullptr;       // slots of the owned range vacated by emigrants (stack)
+    int*   arrivals = nullptr;        // [max arrivals + 1]: ids of the particles the last unpack placed, [max] = their number (count-ahead across the exchange)
+    int    arrivals_max = 0;
     int*   err = nullptr;             // sticky error bits
     unsigned* done = nullptr;         // last-block-done counters of the push kernels
     unsigned long long* stats = nullptr;   // [0] migrants adopted
@@ -178,11 +180,22 @@ slab_push_particles_kernel(const float4* __restrict__ send_l, const float4* __re
 // range: the received ghosts AND the particles this rank itself just sent away as migrants (the new owner packed its ghost list
 // before adopting them, so they are not in it this frame, but they still sit within 2h of the face and are neighbours here).
 // 4 lanes per record.  `sin` is read only; lane 0 writes the new counts to `sout` (the SPH frame reads them from there).
+// count-ahead across the exchange (all null: off)
+struct SlabAheadArgs {
+    GridView g;
+    int* counter = nullptr;           // cell counters, already holding the particles that stayed
+    int* cell_of = nullptr;           // per particle id
+    int* rank = nullptr;              // arrival rank inside the cell, per particle id
+    int* arrivals = nullptr;          // ids placed by this unpack; [arrivals_max] = their number
+    int  arrivals_max = 0;
+};
+
 __global__ void __launch_bounds__(256)
 slab2_unpack_kernel(float4* __restrict__ aos, int capacity, const float4* __restrict__ rcv_l, const float4* __restrict__ rcv_r,
                     const float4* __restrict__ snd_l, const float4* __restrict__ snd_r, int cap_mig, int cap_ghost,
                     const SlabState* __restrict__ sin, SlabState* __restrict__ sout, const int* __restrict__ free_list,
-                    int* __restrict__ err, unsigned long long* __restrict__ stats)
+                    int* __restrict__ err, unsigned long long* __restrict__ stats,
+                    SlabAheadArgs ah)
 {
     const int* hl = reinterpret_cast<const int*>(rcv_l);
     const int* hr = reinterpret_cast<const int*>(rcv_r);
@@ -206,6 +219,7 @@ slab2_unpack_kernel(float4* __restrict__ aos, int capacity, const float4* __rest
         sout->free_count = over ? F : F - k;
         sout->pad = 0;
         if (!over) stats[0] += (unsigned long long)m_in;
+        if (ah.arrivals != nullptr) ah.arrivals[ah.arrivals_max] = over ? 0 : min(m_in + G, ah.arrivals_max);   // how many ids follow
     }
     if (over) return;
     const int u = (int)(t >> 2), q = (int)(t & 3);
@@ -223,7 +237,22 @@ slab2_unpack_kernel(float4* __restrict__ aos, int capacity, const float4* __rest
         else src = snd_r + 4 * (size_t)(1 + (v - sl));
         dest = n_owned2 + (u - m_in);
     }
-    aos[(size_t)dest * 4 + q] = src[q];
+    const float4 v = src[q];
+    aos[(size_t)dest * 4 + q] = v;
+    // count-ahead across the exchange: the integrate pass of the last frame counted the particles that stayed; an arrival is hashed and
+    // counted here (the same cwa_cell3 on the same stored floats as grid_hash_count_kernel<3>), so the grid build starts at the scan
+    if (ah.counter != nullptr && q == 0 && u < ah.arrivals_max) {
+        int cell = -1, rank = 0;
+        if (v.x == v.x && v.y == v.y && v.z == v.z) {
+            int ci, cj, ck;
+            cwa_cell3(ah.g, v.x, v.y, v.z, ci, cj, ck);
+            cell = (ci * ah.g.n[1] + cj) * ah.g.kstride + ck;
+            rank = atomicAdd(ah.counter + cell, 1);
+        }
+        ah.cell_of[dest] = cell;
+        ah.rank[dest] = rank;
+        ah.arrivals[u] = dest;
+    }
 }
 
 // generic "copy rows to a peer, then release a flag" (wave halos, global last row)
@@ -359,6 +388,9 @@ extern "C" int cwa_slab_create(cwa_ctx* ctx, const cwa_slab_desc* desc, cwa_sph 
     sl->stats = reinterpret_cast<unsigned long long*>(blk + 128);
     sl->done = reinterpret_cast<unsigned*>(blk + 192);
     if (cudaMalloc(&sl->free_list, (size_t)d.capacity * 4) != cudaSuccess) return fail("free list");
+    sl->arrivals_max = 2 * (2 * d.cap_mig + d.cap_ghost);
+    if (cudaMalloc(&sl->arrivals, ((size_t)sl->arrivals_max + 1) * 4) != cudaSuccess) return fail("arrival list");
+    cudaMemset(sl->arrivals, 0, ((size_t)sl->arrivals_max + 1) * 4);
     CWA_CUDA(cudaEventCreateWithFlags(&sl->ev_pack, cudaEventDisableTiming));
     CWA_CUDA(cudaEventCreateWithFlags(&sl->ev_int, cudaEventDisableTiming));
     CWA_CUDA(cudaEventCreateWithFlags(&sl->ev_wave, cudaEventDisableTiming));
@@ -376,7 +408,7 @@ static void slab_free(SlabObj* sl)
     if (!sl) return;
     for (int r = 0; r < SLAB_MAX_WORLD; r++)
         if (sl->peer_ipc[r] && sl->peer[r]) cudaIpcCloseMemHandle(sl->peer[r]);
-    cudaFree(sl->mail); cudaFree(sl->send[0]); cudaFree(sl->send[1]); cudaFree(sl->state); cudaFree(sl->free_list);
+    cudaFree(sl->mail); cudaFree(sl->send[0]); cudaFree(sl->send[1]); cudaFree(sl->state); cudaFree(sl->free_list); cudaFree(sl->arrivals);
     if (sl->ev_pack) cudaEventDestroy(sl->ev_pack);
     if (sl->ev_int) cudaEventDestroy(sl->ev_int);
     if (sl->ev_wave) cudaEventDestroy(sl->ev_wave);
@@ -647,6 +679,13 @@ static int slab_frame_pack_first(cwa_ctx* ctx, SlabObj* sl)
     return 0;
 }
 
+// tuning "slab_ahead" / CWA_SLAB_AHEAD (default 1): count-ahead across the exchange
+static bool slab_count_ahead(cwa_ctx* c)
+{
+    if (c->tune.slab_ahead < 0) { const char* e = getenv("CWA_SLAB_AHEAD"); c->tune.slab_ahead = (e && atoi(e) == 0) ? 0 : 1; }
+    return c->tune.slab_ahead != 0;
+}
+
 // part 1 of a frame: everything up to and including this rank's pushes.  Nothing in it waits for a push that another rank enqueues
 // in the SAME part of the SAME frame, so ranks that share a host thread (cwa_slab_group_step) can be enqueued one after the other.
 static int slab_frame_begin(cwa_ctx* ctx, SlabObj* sl, bool last, int coupling)
@@ -683,8 +722,18 @@ static int slab_frame_begin(cwa_ctx* ctx, SlabObj* sl, bool last, int coupling)
         const float4* rcv_r = has_right ? reinterpret_cast<const float4*>(sl->mail + slab_part_off(sl, 1, par)) : nullptr;
         const long long max_in = 4ll * (2ll * (2ll * d.cap_mig + d.cap_ghost));
         KScope k(ctx, KID_EXCHANGE);
+        SlabAheadArgs ah;
+        memset(&ah, 0, sizeof(ah));
+        GridObj* g = get_grid(ctx, s->grid);
+        if (s->counts_ahead && g != nullptr && d.world > 1) {          // the last frame's integrate pass counted the particles that stayed
+            ah.g = g->view; ah.counter = g->counter; ah.cell_of = g->cell_of; ah.rank = g->rank;
+            ah.arrivals = sl->arrivals; ah.arrivals_max = sl->arrivals_max;
+            s->arrivals = sl->arrivals; s->arrivals_count = sl->arrivals + sl->arrivals_max; s->arrivals_max = sl->arrivals_max;
+        } else {
+            s->arrivals = nullptr; s->arrivals_count = nullptr; s->arrivals_max = 0;
+        }
         slab2_unpack_kernel<<<d.world > 1 ? ceil_div(max_in, 256) : 1, 256, 0, M>>>(aos, d.capacity, rcv_l, rcv_r, snd_l, snd_r, d.cap_mig, d.cap_ghost,
-                                                                                  sin, sout, sl->free_list, sl->err, sl->stats);
+                                                                                  sin, sout, sl->free_list, sl->err, sl->stats, ah);
         CWA_CUDA(cudaGetLastError());
     }
     sl->pseq++;
@@ -708,7 +757,8 @@ static int slab_frame_begin(cwa_ctx* ctx, SlabObj* sl, bool last, int coupling)
         pa.msg_l = snd_l; pa.msg_r = snd_r; pa.cap_mig = d.cap_mig; pa.cap_ghost = d.cap_ghost;
         pa.free_list = sl->free_list; pa.free_count = &sout->free_count;
     }
-    const int rc = sph_passes_internal(ctx, s, wave_tex_view(ctx, sl->wave, image), 7, false, pack_next ? &pa : nullptr);
+    const bool ahead = pack_next && slab_count_ahead(ctx);      // the integrate pass counts the particles that stay, the next unpack the arrivals
+    const int rc = sph_passes_internal(ctx, s, wave_tex_view(ctx, sl->wave, image), 7, ahead, pack_next ? &pa : nullptr);
     if (s->wait_before_sampling) {                         // not consumed (the call failed early)
         cudaStreamWaitEvent(M, s->wait_before_sampling, 0);
         s->wait_before_sampling = nullptr;
@@ -753,6 +803,7 @@ static int slab_call_end(cwa_ctx* ctx, SlabObj* sl)
 {
     if (sl->wave_in_flight) CWA_CUDA(cudaStreamWaitEvent(ctx->stream, sl->ev_wave, 0));   // the main stream is behind everything the side stream was given
     sl->wave_in_flight = false;
+    if (SphObj* s = get_sph(ctx, sl->sph)) { s->counts_ahead = false; s->arrivals = nullptr; s->arrivals_count = nullptr; s->arrivals_max = 0; }
     return 0;
 }
 

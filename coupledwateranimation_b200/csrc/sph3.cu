@@ -1237,7 +1237,7 @@ sph3_force_heavy_kernel(const float4* __restrict__ pack, const int* __restrict__
 // the position it just wrote -- the same cwa_cell3 on the same stored floats as grid_hash_count_kernel, warp-aggregated
 // (threads are in cell order, so most lanes of a warp share a few cells) -- and leaves cell id and arrival rank indexed
 // by its slot: the next grid build starts at the scan and never re-reads the particle records for the hash.
-// MODE 2 (slab decomposition, cwa_sph_step_slab): an OWNED particle (original slot < n_owned) that ends the frame within `band` of a
+// MODE 2 / 3 (slab decomposition, cwa_sph_step_slab; 3 = with count-ahead): an OWNED particle (original slot < n_owned) that ends the frame within `band` of a
 // slab face, or beyond it, is also copied into the message for that neighbour -- the selection, message layout and dead-slot marking
 // of slab_pack_kernel (multi.cu), applied to the record in registers instead of a second pass over the SSBO.
 #define CWA_DEAD_W_SPH (-1.0f)
@@ -1251,7 +1251,8 @@ sph3_finalize_integrate_sorted_kernel(const float4* __restrict__ pack,
                                       GridView g, int n, int* __restrict__ counter, int* __restrict__ cell_next, int* __restrict__ rank_next,
                                       SlabPackArgs sp)
 {
-    constexpr bool AHEAD = (MODE == 1);
+    constexpr bool AHEAD = (MODE == 1 || MODE == 3);  // 3: slab pack AND count-ahead (the particles that stay owned; arrivals are counted by the unpack kernel)
+    constexpr bool SLAB = (MODE == 2 || MODE == 3);
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = s < __ldg(count);
     if (!AHEAD && !live) return;
@@ -1269,7 +1270,9 @@ sph3_finalize_integrate_sorted_kernel(const float4* __restrict__ pack,
         float4* o = aos + (size_t)id * 4;                          // 64-byte record = two 256-bit stores (two full sectors)
         const float4 ex = make_float4(rho, prs, m.z, m.w);
         float4 pos_out = pos;
-        if (MODE == 2 && id < (sp.n_owned_dev != nullptr ? __ldg(sp.n_owned_dev) : sp.n_owned)) {
+        bool stays = true;                                      // still in this rank's owned range after the frame (always, outside slab frames)
+        if (SLAB) stays = id < (sp.n_owned_dev != nullptr ? __ldg(sp.n_owned_dev) : sp.n_owned);   // ghosts are dropped
+        if (SLAB && stays) {
             const float z = pos.z;                                 // NaN z: every test below is false -> stays
             float4* msg = nullptr;
             bool migrate = false;
@@ -1286,6 +1289,7 @@ sph3_finalize_integrate_sorted_kernel(const float4* __restrict__ pack,
                     cwa_stg256(d, pos, vel);
                     cwa_stg256(d + 2, f, ex);
                     if (migrate) {
+                        stays = false;
                         pos_out = make_float4(__int_as_float(0x7fffffff), __int_as_float(0x7fffffff), __int_as_float(0x7fffffff), CWA_DEAD_W_SPH);
                         if (sp.free_list != nullptr) sp.free_list[atomicAdd(sp.free_count, 1)] = id;   // the slot is reused by the next unpack
                     }
@@ -1296,7 +1300,7 @@ sph3_finalize_integrate_sorted_kernel(const float4* __restrict__ pack,
         cwa_stg256(o + 2, f, ex);
         if (AHEAD) {
             cell = -1;
-            if (pos.x == pos.x && pos.y == pos.y && pos.z == pos.z) {          // as grid_hash_count_kernel<3>
+            if (stays && pos.x == pos.x && pos.y == pos.y && pos.z == pos.z) { // as grid_hash_count_kernel<3>
                 int ci, cj, ck;
                 cwa_cell3(g, pos.x, pos.y, pos.z, ci, cj, ck);
                 cell = (ci * g.n[1] + cj) * g.kstride + ck;
@@ -1694,6 +1698,7 @@ extern "C" int cwa_set_tuning(cwa_ctx* ctx, const char* key, int value)
     else if (k == "fused_order") { ctx->tune.fused_order = value ? 1 : 0; }
     else if (k == "fused_integrate") { ctx->tune.fused_integrate = value ? 1 : 0; }
     else if (k == "nbr_k") { CWA_CHECK(value >= 8 && value <= NBR_K_MAX && value % 4 == 0, "nbr_k %d: multiple of 4 in [8, %d]", value, NBR_K_MAX); ctx->tune.nbr_k = value; }
+    else if (k == "slab_ahead") { ctx->tune.slab_ahead = value ? 1 : 0; }
     else if (k == "allpairs_balanced") { CWA_CHECK(value >= 0 && value <= 2, "allpairs_balanced %d: 0 off, 1 density pass, 2 both passes", value); ctx->tune.allpairs_bal = value; }
     else if (k == "inplace_max") { CWA_CHECK(value >= 0, "inplace_max %d negative", value); ctx->tune.inplace_max = value; }
     else if (k == "extreme_candidates") { CWA_CHECK(value >= 16, "extreme_candidates %d too small", value); ctx->tune.extreme = value; }
@@ -1809,15 +1814,19 @@ static int launch_force_list(cwa_ctx* ctx, SphObj* s, GridObj* g, bool fused, fl
     return 0;
 }
 
-static int sph_snapshot(cwa_ctx* ctx, SphObj* s, bool count_next_ahead = false)
+static int sph_snapshot(cwa_ctx* ctx, SphObj* s, bool count_next_ahead = false, bool clear_for_next_build = false)
 {
     GridObj* g = get_grid(ctx, s->grid);
     BufferObj* pb = get_buffer(ctx, s->particles);
     CWA_CHECK(g && pb, "sph: grid or particle buffer vanished");
     GridBuildOpts opts;
     opts.canonical_order = !fused_order(ctx);
-    if (s->counts_ahead) { opts.ahead_cell = s->cell_next; opts.ahead_rank = s->rank_next; }
-    opts.clear_after_scan = count_next_ahead;
+    if (s->counts_ahead) {
+        opts.ahead_cell = s->cell_next; opts.ahead_rank = s->rank_next;
+        opts.arrivals = s->arrivals; opts.arrivals_count = s->arrivals_count; opts.arrivals_max = s->arrivals_max;
+    }
+    opts.clear_after_scan = count_next_ahead || clear_for_next_build;
+    opts.clear_is_for_next_build = clear_for_next_build && !count_next_ahead;
     opts.n_dev = s->n_dev;
     s->counts_ahead = false;
     CWA_TRY(grid_build_internal(ctx, g, pb->ptr, 64, s->n, opts));
@@ -1917,11 +1926,12 @@ int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which, bool co
     const int cfg = nb_config(ctx);
     const bool lists = cfg >= 7;                                   // neighbour-list kernels (7: round-1 density pass, 8: flat density pass)
     const bool fused_tail = full && lists && fused_integrate(ctx);   // the force kernels finish the particle (epilogue + integrate + write-back)
-    count_ahead = count_ahead && full && !fused_tail && slab == nullptr;
+    count_ahead = count_ahead && full && !fused_tail;                 // (slab frames too: the unpack kernel of the next frame counts the arrivals)
     CWA_CHECK(slab == nullptr || (full && !fused_tail), "slab pack: needs a full step with the separate integrate kernel (fused_integrate = 0)");
     if (!(which & 1)) CWA_TRY(wave_sampling_copy(ctx, s->wave, s->wave_image, &tex));
     if (which & 1) {
-        CWA_TRY(sph_snapshot(ctx, s, count_ahead));                // positions changed since the last frame
+        // (slab frames that are followed by another frame of the call: the next build finds counter + scan state cleared, off its critical path)
+        CWA_TRY(sph_snapshot(ctx, s, count_ahead, slab != nullptr && !count_ahead));   // positions changed since the last frame
         if (s->wait_before_sampling) {                             // the wave level this frame samples may still be in flight on the side stream
             CWA_CUDA(cudaStreamWaitEvent(ctx->stream, s->wait_before_sampling, 0));
             s->wait_before_sampling = nullptr;
@@ -1973,12 +1983,12 @@ int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which, bool co
         if (full) {
             const bool local = tex_view_is_local(tex);
             const SlabPackArgs spa = slab ? *slab : SlabPackArgs();
-            const int mode = slab ? 2 : (count_ahead ? 1 : 0);
+            const int mode = slab ? (count_ahead ? 3 : 2) : (count_ahead ? 1 : 0);
 #define CWA_FIN_INT(L, M) sph3_finalize_integrate_sorted_kernel<L, M><<<ceil_div(n, 128), 128, 0, ctx->stream>>>( \
                     s->pack, s->forceS, s->miscS, s->pairP, s->pairV, g->index_list, g->offset + g->view.num_cells, aos, cc, tex, \
                     g->view, n, g->counter, s->cell_next, s->rank_next, spa)
-            if (local) { if (mode == 2) CWA_FIN_INT(true, 2); else if (mode == 1) CWA_FIN_INT(true, 1); else CWA_FIN_INT(true, 0); }
-            else       { if (mode == 2) CWA_FIN_INT(false, 2); else if (mode == 1) CWA_FIN_INT(false, 1); else CWA_FIN_INT(false, 0); }
+            if (local) { if (mode == 3) CWA_FIN_INT(true, 3); else if (mode == 2) CWA_FIN_INT(true, 2); else if (mode == 1) CWA_FIN_INT(true, 1); else CWA_FIN_INT(true, 0); }
+            else       { if (mode == 3) CWA_FIN_INT(false, 3); else if (mode == 2) CWA_FIN_INT(false, 2); else if (mode == 1) CWA_FIN_INT(false, 1); else CWA_FIN_INT(false, 0); }
 #undef CWA_FIN_INT
             s->counts_ahead = count_ahead;
         } else {

@@ -45,3 +45,16 @@ def test_free_slots_are_reused():
     assert res["migrated"] > 300
     # without reuse every adopted migrant would be appended: owned ranges would add up to particles + migrants
     assert sum(res["owned_range"]) < p.size + res["migrated"] // 2, res
+
+
+def test_count_ahead_across_the_exchange_changes_nothing(monkeypatch):
+    """Frames in the middle of a call skip the cell hash: the integrate pass counts the particles that stay, the next frame's unpack
+    kernel the arrivals (csrc/slab.cu).  Same cells, same canonical order inside a cell -> the same bits as the plain grid build."""
+    import dist_check
+    out = {}
+    for ahead in ("0", "1"):
+        monkeypatch.setenv("CWA_SLAB_AHEAD", ahead)
+        out[ahead] = dist_check.run_group(3, frames=12, coupling=0, calls=2)
+        _check(out[ahead], 3)
+    for key in ("pos_max_rel", "vel_max_rel", "migrated", "owned_range", "free_slots"):
+        assert out["0"][key] == out["1"][key], (key, out["0"][key], out["1"][key])
