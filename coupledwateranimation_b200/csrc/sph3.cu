@@ -1081,18 +1081,24 @@ sph3_force_rows_kernel(const float4* __restrict__ pack, const int2* __restrict__
     const int slot = blockIdx.x * TILE_P + tid;
     const int n = min(n_max, __ldg(offset + g.num_cells));   // inserted particles
     if (slot >= n) return;
+    // A target has a dozen neighbours: the loop below is short, and the chain of dependent loads in front of it (row count -> rows ->
+    // first neighbour record) was 40 % of the kernel's stall samples (ncu source view).  So everything the thread will need is requested
+    // at once: all nine row slots (entries behind the count are stale and never used), the count and the target's own record.
+    const int2* rows = rows_of(const_cast<int2*>(nbr_rows), slot);
+    int2 rw[RT_ROWS];
+#pragma unroll
+    for (int r = 0; r < RT_ROWS; r++) rw[r] = __ldg(rows + r * 32);
+    const f4x2 own = cwa_ldg256(pack + 2 * (size_t)slot);
     const int nr = __ldg(nbr_count + slot);
     if (nr > RT_ROWS) {                                // clump target (INPLACE_MARK or EXTREME_MARK): sph3_force_heavy_kernel
         const int qi = atomicAdd(heavy_count, 1);
         if (qi < n_max) heavy_queue[qi] = slot;        // (a pass dispatched twice without a grid build in between re-queues: same results)
         return;
     }
-    const int2* rows = rows_of(const_cast<int2*>(nbr_rows), slot);
 #pragma unroll
     for (int r = 0; r < RT_ROWS; r++)
-        if (r < nr) tab[r * TILE_P + tid] = __ldg(rows + r * 32);
+        if (r < nr) tab[r * TILE_P + tid] = rw[r];
     const Sph3Const c = *cc;
-    const f4x2 own = cwa_ldg256(pack + 2 * (size_t)slot);
     const float4 pa = own.a, pb = own.b;
     float fpx = 0.f, fpy = 0.f, fpz = 0.f, fvx = 0.f, fvy = 0.f, fvz = 0.f;
     {
@@ -1467,71 +1473,96 @@ sph3_force_allpairs_kernel(const float4* __restrict__ aos, int n, const Sph3Cons
     }
 }
 
-// SM-balanced all-pairs kernels (used when the targets of one SM fit one CTA: n <= 1024 x SMs; the shipped scene has 138 per SM).
+// SM-balanced, register-tiled all-pairs kernels (used when the targets of one SM fit one CTA: the shipped scene has 138 per SM).
 // The kernels above cut the targets into tiles of 64: 20 480 targets = 320 CTAs on 148 SMs = 2.16 per SM, i.e. the SMs that get three
-// CTAs set the time and the rest idle a third of it.  Here ONE CTA per SM owns ceil(n / SMs) consecutive targets and spends its up to
-// 1024 threads on them, L lanes each (L need not be a power of two: the partial sums meet in shared memory, fixed order); every
-// candidate tile is staged once per SM.  The density accumulation is branch-free (weight 0 when rejected).
+// CTAs set the time and the rest idle a third of it; and every pair test pays its own shared-memory load and loop step (16 instructions
+// per test: the kernels are issue-bound).  Here ONE CTA per SM owns ceil(n / SMs) consecutive targets; a thread tests every candidate
+// it reads against T targets held in registers, and L lanes share a group of T targets (L need not be a power of two: the partial sums
+// meet in shared memory, fixed order).  The density accumulation is branch-free (weight 0 when rejected).
 constexpr int APB_THREADS = 1024;
-constexpr int APB_TILE = 256;         // candidates per tile: at most 64 per lane (the force kernel's accept mask) for L >= 4
+constexpr int APB_TILE_D = 1024;      // candidates per tile, density pass (a barrier pair per tile: few, long tiles)
+constexpr int APB_TILE = 512;         // candidates per tile, force pass: at most 64 per lane (its accept mask) for L >= 8
+constexpr int APB_TD = 4;             // targets per thread, density pass
+constexpr int APB_TF = 2;             // targets per thread, force pass
 
+template <int T>
 __global__ void __launch_bounds__(APB_THREADS)
 sph3_density_allpairs_bal_kernel(const float4* __restrict__ aos, int n, int tpc, int L, const Sph3Const* __restrict__ cc, TexView tex,
                                  float2* __restrict__ out_rp)
 {
-    __shared__ float4 tile[APB_TILE];
-    __shared__ float part[APB_THREADS];
+    __shared__ float4 tile[APB_TILE_D];
+    __shared__ float part[T][APB_THREADS];
     const int tid = threadIdx.x;
-    const int tl = tid / L, sub = tid - tl * L;
-    const int i = blockIdx.x * tpc + tl;
-    const bool active = tl < tpc && i < n;
+    const int grp = tid / L, sub = tid - grp * L;
+    const int t0 = blockIdx.x * tpc + grp * T;                    // first target of the thread's group
+    const int t_end = min(n, (blockIdx.x + 1) * tpc);             // one past the CTA's last target
+    const bool active = grp * T < tpc && t0 < t_end;
     const float accept_r2 = cc->accept_r2, h2 = cc->h2, poly6 = cc->poly6;
-    const float4 p = active ? aos[(size_t)i * 4] : make_float4(0.f, 0.f, 0.f, 0.f);
-    float rho = 0.0f;
-    for (int j0 = 0; j0 < n; j0 += APB_TILE) {
-        if (tid < APB_TILE) {
+    float px[T], py[T], pz[T], rho[T];
+#pragma unroll
+    for (int k = 0; k < T; k++) {
+        const bool on = active && t0 + k < t_end;
+        const float4 p = on ? aos[(size_t)(t0 + k) * 4] : make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f);   // parked: every test fails
+        px[k] = p.x; py[k] = p.y; pz[k] = p.z; rho[k] = 0.0f;
+    }
+    for (int j0 = 0; j0 < n; j0 += APB_TILE_D) {
+        if (tid < APB_TILE_D) {
             const int j = j0 + tid;
-            tile[tid] = (j < n) ? aos[(size_t)j * 4] : make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f);
+            tile[tid] = (j < n) ? aos[(size_t)j * 4] : make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, 0.f);
         }
         __syncthreads();
         if (active) {
-#pragma unroll 4
-            for (int q = sub; q < APB_TILE; q += L) {
+#pragma unroll 2
+            for (int q = sub; q < APB_TILE_D; q += L) {
                 const float4 c = tile[q];
-                const float r2 = cwa_len3sq(p.x - c.x, p.y - c.y, p.z - c.z);
-                const float d = (r2 <= accept_r2) ? (h2 - r2) : 0.0f;
-                rho = fmaf(poly6, d * d * d, rho);
+#pragma unroll
+                for (int k = 0; k < T; k++) {
+                    const float r2 = cwa_len3sq(px[k] - c.x, py[k] - c.y, pz[k] - c.z);
+                    const float d = (r2 <= accept_r2) ? (h2 - r2) : 0.0f;
+                    rho[k] = fmaf(poly6, d * d * d, rho[k]);
+                }
             }
         }
         __syncthreads();
     }
-    part[tid] = rho;
+#pragma unroll
+    for (int k = 0; k < T; k++) part[k][tid] = rho[k];
     __syncthreads();
-    if (active && sub == 0) {
+    if (active && sub < T && t0 + sub < t_end) {                  // lane k of the group finishes target k
         float sum = 0.0f;
-        for (int l = 0; l < L; l++) sum += part[tid + l];
+        for (int l = 0; l < L; l++) sum += part[sub][tid - sub + l];
+        const float4 p = aos[(size_t)(t0 + sub) * 4];
         float rho_out, prs_out;
         density_epilogue(*cc, tex, p.x, p.z, sum, rho_out, prs_out);
-        out_rp[i] = make_float2(rho_out, prs_out);     // committed to the SSBO after the pass
+        out_rp[t0 + sub] = make_float2(rho_out, prs_out);         // committed to the SSBO after the pass
     }
 }
 
+template <int T>
 __global__ void __launch_bounds__(APB_THREADS)
 sph3_force_allpairs_bal_kernel(const float4* __restrict__ aos, int n, int tpc, int L, const Sph3Const* __restrict__ cc, TexView tex,
                                float4* __restrict__ out_force)
 {
     __shared__ float4 tileA[APB_TILE];
     __shared__ float4 tileB[APB_TILE];
-    __shared__ float part[6][APB_THREADS];
+    __shared__ float part[6][APB_THREADS];             // reused for each of the thread's T targets
     const int tid = threadIdx.x;
-    const int tl = tid / L, sub = tid - tl * L;
-    const int i = blockIdx.x * tpc + tl;
-    const bool active = tl < tpc && i < n;
+    const int grp = tid / L, sub = tid - grp * L;
+    const int t0 = blockIdx.x * tpc + grp * T;
+    const int t_end = min(n, (blockIdx.x + 1) * tpc);
+    const bool active = grp * T < tpc && t0 < t_end;
     const Sph3Const c = *cc;
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f), v = p, e = p;
-    if (active) { p = aos[(size_t)i * 4]; v = aos[(size_t)i * 4 + 1]; e = aos[(size_t)i * 4 + 3]; }
-    float fpx = 0.f, fpy = 0.f, fpz = 0.f, fvx = 0.f, fvy = 0.f, fvz = 0.f;
-    const int per_lane = (APB_TILE + L - 1) / L;       // <= 64: the launcher keeps L >= 4
+    float4 p[T], v[T];
+    float prs[T], acc[T][6];
+#pragma unroll
+    for (int k = 0; k < T; k++) {
+        const bool on = active && t0 + k < t_end;
+        p[k] = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f); v[k] = make_float4(0.f, 0.f, 0.f, 0.f); prs[k] = 0.f;
+        if (on) { p[k] = aos[(size_t)(t0 + k) * 4]; v[k] = aos[(size_t)(t0 + k) * 4 + 1]; prs[k] = aos[(size_t)(t0 + k) * 4 + 3].y; }
+#pragma unroll
+        for (int a = 0; a < 6; a++) acc[k][a] = 0.f;
+    }
+    const int per_lane = (APB_TILE + L - 1) / L;       // <= 64: the launcher keeps L >= 8
     for (int j0 = 0; j0 < n; j0 += APB_TILE) {
         if (tid < APB_TILE) {
             const int j = j0 + tid;
@@ -1540,41 +1571,58 @@ sph3_force_allpairs_bal_kernel(const float4* __restrict__ aos, int n, int tpc, i
                 tileA[tid] = make_float4(qp.x, qp.y, qp.z, qe.y);
                 tileB[tid] = make_float4(qv.x, qv.y, qv.z, qe.x);
             } else {
-                tileA[tid] = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f);
+                tileA[tid] = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, 0.f);
                 tileB[tid] = make_float4(0.f, 0.f, 0.f, 1.f);
             }
         }
         __syncthreads();
         if (active) {
-            // two phases: mark the accepted candidates of the lane (cheap, every candidate), then evaluate only those
-            unsigned long long mask = 0ull;
-#pragma unroll 4
+            // two phases: mark the accepted candidates of the lane for each of its targets (cheap, every candidate, one shared-memory read
+            // for all T of them), then evaluate only those
+            unsigned long long mask[T];
+#pragma unroll
+            for (int k = 0; k < T; k++) mask[k] = 0ull;
+#pragma unroll 2
             for (int t = 0; t < per_lane; t++) {
                 const int q = sub + t * L;
                 if (q < APB_TILE) {
                     const float4 qa = tileA[q];
-                    const float r2 = cwa_len3sq(p.x - qa.x, p.y - qa.y, p.z - qa.z);
-                    if (r2 <= c.accept_r2 && (j0 + q) != i) mask |= (1ull << t);
+#pragma unroll
+                    for (int k = 0; k < T; k++) {
+                        const float r2 = cwa_len3sq(p[k].x - qa.x, p[k].y - qa.y, p[k].z - qa.z);
+                        if (r2 <= c.accept_r2 && (j0 + q) != t0 + k) mask[k] |= (1ull << t);
+                    }
                 }
             }
-            while (mask) {
-                const int t = __ffsll((long long)mask) - 1;
-                mask &= mask - 1ull;
-                const int q = sub + t * L;
-                pair_force(c, p.x, p.y, p.z, e.y, v.x, v.y, v.z, tileA[q], tileB[q], fpx, fpy, fpz, fvx, fvy, fvz);
+#pragma unroll
+            for (int k = 0; k < T; k++) {
+                unsigned long long m = mask[k];
+                while (m) {
+                    const int t = __ffsll((long long)m) - 1;
+                    m &= m - 1ull;
+                    const int q = sub + t * L;
+                    pair_force(c, p[k].x, p[k].y, p[k].z, prs[k], v[k].x, v[k].y, v[k].z, tileA[q], tileB[q],
+                               acc[k][0], acc[k][1], acc[k][2], acc[k][3], acc[k][4], acc[k][5]);
+                }
             }
         }
         __syncthreads();
     }
-    part[0][tid] = fpx; part[1][tid] = fpy; part[2][tid] = fpz; part[3][tid] = fvx; part[4][tid] = fvy; part[5][tid] = fvz;
-    __syncthreads();
-    if (active && sub == 0) {
-        float sm[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int l = 0; l < L; l++)
 #pragma unroll
-            for (int k = 0; k < 6; k++) sm[k] += part[k][tid + l];
-        const float4 fprev = aos[(size_t)i * 4 + 2];
-        out_force[i] = force_epilogue(c, tex, p.x, p.y, p.z, v.x, v.y, v.z, e.x, fprev, sm[0], sm[1], sm[2], sm[3], sm[4], sm[5]);
+    for (int k = 0; k < T; k++) {                                 // lane k of the group finishes target k
+#pragma unroll
+        for (int a = 0; a < 6; a++) part[a][tid] = acc[k][a];
+        __syncthreads();
+        if (active && sub == k && t0 + k < t_end) {
+            const int i = t0 + k;
+            float sm[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int l = 0; l < L; l++)
+#pragma unroll
+                for (int a = 0; a < 6; a++) sm[a] += part[a][tid - sub + l];
+            const float4 pi = aos[(size_t)i * 4], vi = aos[(size_t)i * 4 + 1], ei = aos[(size_t)i * 4 + 3], fprev = aos[(size_t)i * 4 + 2];
+            out_force[i] = force_epilogue(c, tex, pi.x, pi.y, pi.z, vi.x, vi.y, vi.z, ei.x, fprev, sm[0], sm[1], sm[2], sm[3], sm[4], sm[5]);
+        }
+        __syncthreads();
     }
 }
 
@@ -1684,7 +1732,7 @@ static int pipeline_mode(cwa_ctx* c) { if (c->tune.pipeline < 0) c->tune.pipelin
 static int nbr_k(cwa_ctx* c) { if (c->tune.nbr_k < 0) c->tune.nbr_k = env_int("CWA_NBR_K", NBR_K_DEFAULT, 8, NBR_K_MAX) & ~3; return c->tune.nbr_k; }
 static int extreme_candidates(cwa_ctx* c) { if (c->tune.extreme < 0) c->tune.extreme = env_int("CWA_EXTREME", EXTREME_CANDIDATES, 16, 1 << 20); return c->tune.extreme; }
 static int inplace_max(cwa_ctx* c) { if (c->tune.inplace_max < 0) c->tune.inplace_max = env_int("CWA_INPLACE_MAX", INPLACE_MAX, 0, 1 << 20); return c->tune.inplace_max; }
-static bool allpairs_balanced(cwa_ctx* c) { if (c->tune.allpairs_bal < 0) c->tune.allpairs_bal = env_int("CWA_ALLPAIRS_BALANCED", 1, 0, 2); return c->tune.allpairs_bal != 0; }
+static int allpairs_balanced(cwa_ctx* c) { if (c->tune.allpairs_bal < 0) c->tune.allpairs_bal = env_int("CWA_ALLPAIRS_BALANCED", 2, 0, 2); return c->tune.allpairs_bal; }
 static bool fused_order(cwa_ctx* c) { if (c->tune.fused_order < 0) c->tune.fused_order = env_int("CWA_FUSED_ORDER", 1, 0, 1); return c->tune.fused_order != 0; }
 
 extern "C" int cwa_set_tuning(cwa_ctx* ctx, const char* key, int value)
@@ -1892,21 +1940,20 @@ int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which, bool co
         const int blocks = ceil_div(n, AP_TT);
         // one CTA per SM with an equal share of the targets when that share fits a CTA with at least 4 lanes per target
         const int tpc = ceil_div(n, ctx->sm_count);
-        const int lanes = tpc > 0 ? (APB_THREADS / tpc < 32 ? APB_THREADS / tpc : 32) : 0;
-        const bool balanced = lanes >= 4 && allpairs_balanced(ctx);
+        auto lanes_for = [&](int T) { const int groups = ceil_div(tpc > 0 ? tpc : 1, T); const int l = APB_THREADS / groups; return l < 64 ? l : 64; };
+        const int lanes_d = lanes_for(APB_TD), lanes_f = lanes_for(APB_TF);
+        const bool balanced = tpc > 0 && lanes_d >= 4 && lanes_f >= 8 && allpairs_balanced(ctx) != 0;
         const int bal_blocks = balanced ? ceil_div(n, tpc) : 0;
         if (which & 1) {
             { KScope k(ctx, KID_DENSITY);
-              if (balanced) sph3_density_allpairs_bal_kernel<<<bal_blocks, APB_THREADS, 0, ctx->stream>>>(aos, n, tpc, lanes, cc, tex, sph_scratch_rp(s));
+              if (balanced) sph3_density_allpairs_bal_kernel<APB_TD><<<bal_blocks, APB_THREADS, 0, ctx->stream>>>(aos, n, tpc, lanes_d, cc, tex, sph_scratch_rp(s));
               else sph3_density_allpairs_kernel<<<blocks, AP_TT * AP_L, 0, ctx->stream>>>(aos, n, cc, tex, sph_scratch_rp(s)); }
             { KScope k(ctx, KID_OTHER);
               sph3_commit_rho_pres_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(sph_scratch_rp(s), n, aos); }
         }
         if (which & 2) {
             { KScope k(ctx, KID_FORCE);
-              // (the SM-balanced force variant measured slower on the shipped scene: 461 vs 448 us -- 62 registers x 1024 threads leave one CTA
-              // per SM; it is kept behind the tuning value 2 for other shapes)
-              if (balanced && ctx->tune.allpairs_bal == 2) sph3_force_allpairs_bal_kernel<<<bal_blocks, APB_THREADS, 0, ctx->stream>>>(aos, n, tpc, lanes, cc, tex, sph_scratch_force(s));
+              if (balanced && ctx->tune.allpairs_bal == 2) sph3_force_allpairs_bal_kernel<APB_TF><<<bal_blocks, APB_THREADS, 0, ctx->stream>>>(aos, n, tpc, lanes_f, cc, tex, sph_scratch_force(s));
               else sph3_force_allpairs_kernel<<<blocks, AP_TT * AP_L, 0, ctx->stream>>>(aos, n, cc, tex, sph_scratch_force(s)); }
             { KScope k(ctx, KID_OTHER);
               sph3_commit_force_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(sph_scratch_force(s), n, aos); }
