@@ -158,13 +158,21 @@ __device__ __forceinline__ bool sph2_target(int t, int n, int m, bool tail, cons
     return true;
 }
 
+// L lanes per target (a power of two <= 32): C2 has 65 536 targets with ~144 candidates each -- one thread per target leaves a B200 with
+// 14 warps per SM, each on a serial chain of 144 dependent-latency steps.  The lanes of a target split every row of candidates and meet
+// in a shuffle reduction over their own group (every exit before it is taken by all lanes of the group: they hold the same target).
+template <int S2_LANES>
+__device__ __forceinline__ unsigned s2_group_mask() { return (S2_LANES == 32 ? 0xffffffffu : ((1u << (S2_LANES & 31)) - 1u)) << ((threadIdx.x & 31u) & ~(unsigned)(S2_LANES - 1)); }
+
+template <int S2_LANES>
 __global__ void __launch_bounds__(128)
 sph2_density_kernel(const float4* __restrict__ in, float4* __restrict__ out, int n, GridView g,
                     const int* __restrict__ offset, const int* __restrict__ index_list, const int* __restrict__ cell_of,
                     const float4* __restrict__ posS, Sph2Params prm, int tail)
 {
     using namespace k2d;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = gt / S2_LANES, sub = gt % S2_LANES;
     const int m = __ldg(offset + g.num_cells);
     int ix;
     if (!sph2_target(t, n, m, tail != 0, index_list, cell_of, ix)) return;
@@ -186,7 +194,7 @@ sph2_density_kernel(const float4* __restrict__ in, float4* __restrict__ out, int
         pi.vel.x -= 1.75f * vn * db.x; pi.vel.y -= 1.75f * vn * db.y;
     }
     float4* o = out + (size_t)ix * 3;
-    if (pi.pos.y > VIEW_HEIGHT) { o[0] = pi.pos; o[1] = pi.vel; o[2] = pi.acc; return; }   // :427-431
+    if (pi.pos.y > VIEW_HEIGHT) { if (sub == 0) { o[0] = pi.pos; o[1] = pi.vel; o[2] = pi.acc; } return; }   // :427-431
 
     float rho = 0.0f;
     int i0, j0, i1, j1;
@@ -195,12 +203,18 @@ sph2_density_kernel(const float4* __restrict__ in, float4* __restrict__ out, int
     for (int i = i0; i <= i1; i++) {
         const int base = i * g.n[1];
         const int g0 = __ldg(offset + base + j0), g1 = __ldg(offset + base + j1 + 1);
-        for (int q = g0; q < g1; q++) {
+        for (int q = g0 + sub; q < g1; q += S2_LANES) {
             const float4 pj = __ldg(posS + q);
             const float r2 = cwa_len2sq(pi.pos.x - pj.x, pi.pos.y - pj.y);
             if (r2 < HSQ) rho += k2_W_cubic(sqrtf(r2));                   // :456-459
         }
     }
+    {
+        const unsigned gm = s2_group_mask<S2_LANES>();
+#pragma unroll
+        for (int d = 1; d < S2_LANES; d <<= 1) rho += __shfl_xor_sync(gm, rho, d);
+    }
+    if (sub != 0) return;
     rho = MASS * rho;                                                     // :471
     if (db.z < H) rho += PSI * k2_W_cubic(fmaxf(0.0f, db.z + 0.0f * PARTICLE_RADIUS));
     rho = fmaxf(REST_DENS, rho);
@@ -210,6 +224,7 @@ sph2_density_kernel(const float4* __restrict__ in, float4* __restrict__ out, int
     o[0] = pi.pos; o[1] = pi.vel; o[2] = pi.acc;
 }
 
+template <int S2_LANES>
 __global__ void __launch_bounds__(128)
 sph2_forces_kernel(const float4* __restrict__ in, float4* __restrict__ out, int n, GridView g,
                    const int* __restrict__ offset, const int* __restrict__ index_list, const int* __restrict__ cell_of,
@@ -217,7 +232,8 @@ sph2_forces_kernel(const float4* __restrict__ in, float4* __restrict__ out, int 
                    Sph2Params prm, int tail)
 {
     using namespace k2d;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = gt / S2_LANES, sub = gt % S2_LANES;
     const int m = __ldg(offset + g.num_cells);
     int ix;
     if (!sph2_target(t, n, m, tail != 0, index_list, cell_of, ix)) return;
@@ -225,7 +241,7 @@ sph2_forces_kernel(const float4* __restrict__ in, float4* __restrict__ out, int 
     P2 pi;
     pi.pos = __ldg(in + (size_t)ix * 3); pi.vel = __ldg(in + (size_t)ix * 3 + 1); pi.acc = __ldg(in + (size_t)ix * 3 + 2);
     float4* o = out + (size_t)ix * 3;
-    if (prm.variant == CWA_SPH2_WAVE && pi.pos.w == 0.0f) { o[0] = pi.pos; o[1] = pi.vel; o[2] = pi.acc; return; }   // :494-498
+    if (prm.variant == CWA_SPH2_WAVE && pi.pos.w == 0.0f) { if (sub == 0) { o[0] = pi.pos; o[1] = pi.vel; o[2] = pi.acc; } return; }   // :494-498
     const float PSI = (prm.psi < 0.0f) ? REST_DENS / (1.5f * K2) : prm.psi;
     const float rho_i = pi.acc.w;
     const float c_visc = -VISC * 8.0f * MASS, c_press = MASS;
@@ -237,7 +253,7 @@ sph2_forces_kernel(const float4* __restrict__ in, float4* __restrict__ out, int 
     for (int i = i0; i <= i1; i++) {
         const int base = i * g.n[1];
         const int g0 = __ldg(offset + base + j0), g1 = __ldg(offset + base + j1 + 1);
-        for (int q = g0; q < g1; q++) {
+        for (int q = g0 + sub; q < g1; q += S2_LANES) {
             if (q == self_slot) continue;                                  // jx != ix
             const float4 pj = __ldg(posS + q);
             const float rx = pi.pos.x - pj.x, ry = pi.pos.y - pj.y;
@@ -255,6 +271,15 @@ sph2_forces_kernel(const float4* __restrict__ in, float4* __restrict__ out, int 
             }
         }
     }
+    {
+        const unsigned gm = s2_group_mask<S2_LANES>();
+#pragma unroll
+        for (int d = 1; d < S2_LANES; d <<= 1) {
+            apx += __shfl_xor_sync(gm, apx, d); apy += __shfl_xor_sync(gm, apy, d);
+            avx += __shfl_xor_sync(gm, avx, d); avy += __shfl_xor_sync(gm, avy, d);
+        }
+    }
+    if (sub != 0) return;
     avx *= c_visc; avy *= c_visc;
     apx *= c_press; apy *= c_press;
     const float4 db = k2_boundary_sdf(prm, pi.pos.x, pi.pos.y);
@@ -395,7 +420,10 @@ extern "C" int cwa_sph2_compute(cwa_ctx* ctx, cwa_sph2 h, int nframes)
     CWA_CHECK(g, "sph2: grid vanished");
     const int n = s->n;
     const Sph2Params prm = sph2_params(ctx, s);
-    const int blocks = ceil_div(n, 128);
+    // lanes per target of the neighbour kernels (tuning CWA_S2_LANES: 4, 8, 16 or 32)
+    static const int lanes_env = [] { const char* e = getenv("CWA_S2_LANES"); const int v = e ? atoi(e) : 8; return (v == 4 || v == 8 || v == 16 || v == 32) ? v : 8; }();
+    const int lanes = lanes_env;
+    const int blocks = ceil_div((long long)n * lanes, 128);
     for (int f = 0; f < nframes; f++) {
         for (int sub = 0; sub < s->substeps; sub++) {
             const float4* rd = (const float4*)get_buffer(ctx, s->buffer[s->read_index])->ptr;
@@ -405,7 +433,9 @@ extern "C" int cwa_sph2_compute(cwa_ctx* ctx, cwa_sph2 h, int nframes)
               sph2_reorder_kernel<<<ceil_div((long long)n * 3, 256), 256, 0, ctx->stream>>>(rd, g->index_list, g->offset, g->view.num_cells, s->posS, s->velS, s->accS); }
             for (int tail = 0; tail < 2; tail++) {                           // mode 1 :169-176
                 KScope k(ctx, KID_DENSITY);
-                sph2_density_kernel<<<blocks, 128, 0, ctx->stream>>>(rd, wr, n, g->view, g->offset, g->index_list, g->cell_of, s->posS, prm, tail);
+#define CWA_S2_DENS(L) sph2_density_kernel<L><<<blocks, 128, 0, ctx->stream>>>(rd, wr, n, g->view, g->offset, g->index_list, g->cell_of, s->posS, prm, tail)
+                if (lanes == 4) CWA_S2_DENS(4); else if (lanes == 16) CWA_S2_DENS(16); else if (lanes == 32) CWA_S2_DENS(32); else CWA_S2_DENS(8);
+#undef CWA_S2_DENS
             }
             sph2_pingpong(s);
             rd = (const float4*)get_buffer(ctx, s->buffer[s->read_index])->ptr;
@@ -415,7 +445,9 @@ extern "C" int cwa_sph2_compute(cwa_ctx* ctx, cwa_sph2 h, int nframes)
               sph2_reorder_kernel<<<ceil_div((long long)n * 3, 256), 256, 0, ctx->stream>>>(rd, g->index_list, g->offset, g->view.num_cells, s->posS, s->velS, s->accS); }
             for (int tail = 0; tail < 2; tail++) {
                 KScope k(ctx, KID_FORCE);
-                sph2_forces_kernel<<<blocks, 128, 0, ctx->stream>>>(rd, wr, n, g->view, g->offset, g->index_list, g->cell_of, s->posS, s->velS, s->accS, prm, tail);
+#define CWA_S2_FORCE(L) sph2_forces_kernel<L><<<blocks, 128, 0, ctx->stream>>>(rd, wr, n, g->view, g->offset, g->index_list, g->cell_of, s->posS, s->velS, s->accS, prm, tail)
+                if (lanes == 4) CWA_S2_FORCE(4); else if (lanes == 16) CWA_S2_FORCE(16); else if (lanes == 32) CWA_S2_FORCE(32); else CWA_S2_FORCE(8);
+#undef CWA_S2_FORCE
             }
             sph2_pingpong(s);
         }
