@@ -540,7 +540,7 @@ sph3_force_grid_kernel(const float4* __restrict__ pack,
 // finished by the "heavy" kernels, one WARP per target, spread over the whole GPU.
 constexpr int RT_ROWS = 9;
 constexpr int TILE_P = 128;               // targets per tile (= CTA size of the list kernels)
-constexpr int EXTREME_CANDIDATES = 192;   // a target with more candidates than this is finished by a whole warp (heavy kernels)
+constexpr int EXTREME_CANDIDATES = 192;   // a target with more candidates than this (or more 31-slot row segments than table entries) is a clump target; tuning "extreme_candidates", up to 9 x 31 = 279
 constexpr int EXTREME_MARK = 1 << 30;     // neighbour count written for such a target: routes it to the heavy force kernel
 
 struct RowBounds { int b[RT_ROWS], e[RT_ROWS]; int total; bool wide; };
@@ -789,16 +789,26 @@ sph3_density_flat_kernel(const float4* __restrict__ posS, const float* __restric
     // target goes to sph3_force_heavy_kernel (measured, profiles/r2/tuning.md: one thread alone with the divergent pair term of a few
     // hundred candidates is a 50-150 us tail, in its own warp or from a queue).  heavy: a generic wide query or more than `inplace_max`
     // candidates -- sph3_density_heavy_kernel, one warp per target.
-    const bool maskable = !fr.wide && !fr.longrow && fr.total <= extreme_candidates;
+    // (a row longer than a mask is cut into segments of ROW_MASK_BITS slots -- table entries of their own -- while the table has room)
+    int segs = 0;
+#pragma unroll
+    for (int r = 0; r < RT_ROWS; r++) segs += (fr.e[r] - fr.b[r] + ROW_MASK_BITS - 1) / ROW_MASK_BITS;
+    const bool maskable = !fr.wide && segs <= RT_ROWS && fr.total <= extreme_candidates;
     if (!maskable && (fr.wide || fr.cell_lin < 0 || fr.total > inplace_max)) {
         const int qi = atomicAdd(heavy_count, 1);
         if (qi < n_max) heavy_queue[qi] = slot;
         return;
     }
     int nr = 0;
+    if (maskable && fr.longrow) {
 #pragma unroll
-    for (int r = 0; r < RT_ROWS; r++)
-        if (fr.e[r] > fr.b[r]) { tab[nr * TILE_P + tid] = make_int2(fr.b[r], fr.e[r]); nr++; }
+        for (int r = 0; r < RT_ROWS; r++)
+            for (int b = fr.b[r]; b < fr.e[r]; b += ROW_MASK_BITS) { tab[nr * TILE_P + tid] = make_int2(b, min(b + ROW_MASK_BITS, fr.e[r])); nr++; }
+    } else {
+#pragma unroll
+        for (int r = 0; r < RT_ROWS; r++)
+            if (fr.e[r] > fr.b[r]) { tab[nr * TILE_P + tid] = make_int2(fr.b[r], fr.e[r]); nr++; }
+    }
 
     // The candidates come as three coordinate streams (x | y | z, written by the reorder pass next to posS): a pair of consecutive slots
     // is one aligned 64-bit word per coordinate -- 24 bytes per pair through the L1 data pipe (the limit of this kernel, profiles/r2)
