@@ -78,3 +78,27 @@ def test_c5_is_baseline_config_5():
         gain = sc["torque"] * math.hypot(sc["box_x"], sc["box_z"])
         assert abs(gain - 0.25 * math.hypot(base["box_x"], base["box_z"])) < 1e-9
         assert bench.c5_scene(world, "literal")["torque"] == 0.0                            # 0 = the shader's literal 0.25
+
+
+def test_reference_arm_of_the_other_configs():
+    """`bench.py --impl reference --config D|C2|C3`: the CPU restatement of configs 1-3 with the contract keys and the workload text of the
+    native arm (bench_configs.py); bounded to a few steps here."""
+    import bench_configs
+    from oracle import oracle as O
+    O.build()
+    for cfg, unit in (("D", "particle-updates/s"), ("C2", "particle-updates/s"), ("C3", "cell-updates/s")):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", cfg, "--steps", "2", "--warmup", "0"],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        line = json.loads(r.stdout.strip().splitlines()[-1])
+        assert line["impl"] == "reference" and line["unit"].startswith(unit) and line["value"] > 0
+        assert line["config"]["workload"].startswith(cfg + ":") and line["cpu_baseline"]["kind"] == "port"
+        assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert set(bench_configs.RUNNERS) == {"D", "C2", "C3"}
+
+
+def test_bench_cli_names_every_baseline_config():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0
+    for word in ("--config", "C4", "C2", "C3", "--state-frame", "--scene", "--impl"):
+        assert word in r.stdout
