@@ -4,16 +4,16 @@
 //                                 rule, torque, wave drag / normal force, gravity)
 //   integrate_comp.glsl:56-178 -> sph3_integrate_* (symplectic Euler, foam rule, surface clamp, box)
 //
-// Grid mode (the north-star path): particles are gathered into cell order (coalesced float4
-// reorder); a CTA owns P consecutive cell-ordered particles and L lanes cooperate on each of them.
-// The neighbour rows of the CTA's cells are contiguous runs of the cell-ordered arrays, so each run
-// is staged into shared memory with ONE 1-D bulk async copy (cp.async.bulk, TMA engine, completion
-// on an mbarrier).  The L lanes of a particle walk CONSECUTIVE candidates of each row (conflict-free
-// 16*L-byte shared-memory reads, equal trip counts) and combine their partial sums with warp
-// shuffles.  The force kernel first marks accepted candidates in a per-lane bit mask and then
-// evaluates only those, so the expensive pair term runs with most lanes active.  Ranges that do not
-// fit the staging budget are read through L1 from global memory by the same loops.
-// All-pairs mode reproduces the shipped O(N^2) loops with shared-memory tiles.
+// Grid mode (the north-star path): particles are gathered into cell order (coalesced float4 reorder + x | y | z coordinate streams);
+// the neighbour rows of a target -- same (i, j), consecutive k -- are contiguous runs of the cell-ordered arrays.  Three families of
+// neighbour kernels share that snapshot (cwa_set_tuning "nb_config", all parity-tested):
+//   8 (default)  row-mask kernels: one thread per target walks its narrowed 3 x 3 rows in ONE loop, two candidates per trip on packed
+//                FP32 (FFMA2), accepted candidates recorded as one 32-bit mask per row; the force pass walks the set bits.
+//   7            round 1's index-list kernels (row loop nest, one store per accepted pair).
+//   0..6         "lanes" kernels: a CTA owns P targets x L lanes, neighbour-row windows staged in shared memory with 1-D bulk async copies
+//                (cp.async.bulk, TMA engine, mbarrier completion), lanes interleave over consecutive candidates, warp-shuffle reduction.
+// Clump targets (hundreds of candidates) are finished in place by the density pass and one warp each by the force pass.
+// All-pairs mode reproduces the shipped O(N^2) loops with shared-memory tiles, one CTA per SM, several targets per thread.
 #include "internal.cuh"
 #include <math_constants.h>
 #include <climits>
@@ -526,7 +526,7 @@ sph3_force_grid_kernel(const float4* __restrict__ pack,
 }
 
 // ---------------------------------------------------------------------------------------------
-// neighbour-list kernels (the default): ONE thread per target
+// neighbour-list kernels (nb_config 7, round 1's default): ONE thread per target
 // ---------------------------------------------------------------------------------------------
 // With h <= cell the query pos -+ h touches at most 3 x 3 rows (i,j) of cells, each a contiguous run
 // [offset[k0], offset[k1+1]) of the cell-ordered arrays.  The density pass loads the (up to) 18 row bounds
