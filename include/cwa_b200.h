@@ -272,7 +272,7 @@ CWA_API int cwa_gl_unmap(cwa_ctx* ctx, int resource);
 CWA_API int cwa_gl_register_image(cwa_ctx* ctx, unsigned gl_texture, unsigned gl_target, int* resource);
 CWA_API int cwa_gl_copy_wave_to_image(cwa_ctx* ctx, int resource, cwa_wave w, int image);
 CWA_API int cwa_gl_unregister(cwa_ctx* ctx, int resource);
-/* ReinitFromTexture (StencilImage2DTripleBuffered.cpp:61-77) from the decoded bytes of an RGBA8 init texture (init-textures/*.png) */
+/* ReinitFromTexture (StencilImage2DTripleBuffered.cpp:61-77) from the decoded bytes of an RGBA8 init texture (a PNG of init-textures/) */
 CWA_API int cwa_wave_reinit_from_rgba8(cwa_ctx* ctx, cwa_wave w, const unsigned char* rgba8, int tw, int th);
 
 /* ---- 2-D Koschier SPH on the uniform grid: SphUgrid (SphWave2D/StencilBuffer.cpp:138-179) ------ */

@@ -28,6 +28,7 @@ def test_cpp_host_compiles_and_links_against_the_c_abi():
     exe = _build()
     assert os.path.exists(exe)
     assert os.path.exists(_build("sphwave2d_main"))       # SphUgrid + ImageStencil: the 2-D app's simulation half
+    assert os.path.exists(_build("slab_main"))            # N ranks of the slab-decomposed frame through cwa_slab_* (plain C ABI)
     # C (not C++) consumers must be able to include the ABI header too
     r = subprocess.run(["gcc", "-std=c11", "-fsyntax-only", "-x", "c", os.path.join(ROOT, "include", "cwa_b200.h")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
@@ -77,3 +78,18 @@ def test_cpp_host_runs_the_2d_app_like_sphwave2d_main_cpp(oracle):
         ref = float(ref.astype(np.float64).mean())
         assert abs(float(got) - ref) <= 1e-5 * abs(ref) + 1e-6, (got, ref)
     assert abs(float(m.group(5)) - float(wave.read_image(0)[:, 0].astype(np.float64).sum())) <= 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ranks", [2, 3])
+def test_cpp_host_drives_several_ranks_through_the_slab_abi(ranks):
+    """examples/slab_main.cpp: a C++ host (no Python, no torch) plans the slabs, creates one context per rank, wires the mailboxes and steps
+    the ranks with cwa_slab_group_step; then runs the same scene with cwa_coupled_step and compares.  On one GPU the ranks share it."""
+    exe = _build("slab_main")
+    r = subprocess.run([exe, str(ranks), "8"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    m = re.search(r"ranks=(\d+) frames=8 particles=(\d+) ids_ok=1 nan_diff=0 migrated=(\d+) wave_bit_exact=1 max_pos_diff=([\d.eE+-]+) max_vel_rel=([\d.eE+-]+)", r.stdout)
+    assert m, r.stdout
+    assert int(m.group(1)) == ranks and int(m.group(2)) == 64 * 5 * 160
+    assert int(m.group(3)) > 0, "the fixture must move particles across slab faces"
+    assert float(m.group(4)) <= 1e-5 and float(m.group(5)) <= 2e-3, r.stdout
