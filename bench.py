@@ -47,6 +47,8 @@ elif _GRID_VARIANT == "h":                                    # cells of ~h over
     GRID_MAX, GRID_N, GRID_DESC = (0.55 * S, 1.0, 0.55 * S), (384, 101, 384), "cells of ~h"
 elif _GRID_VARIANT == "h_tight":
     GRID_MAX, GRID_N, GRID_DESC = (0.55 * S, 0.18, 0.55 * S), (384, 20, 384), "cells of h, y extent [-0.02, 0.18] + clamp"
+elif _GRID_VARIANT == "columns":                              # ONE layer in y: cells are columns over the sheet (3 x 3 columns per query)
+    GRID_MAX, GRID_N, GRID_DESC = (0.55 * S, 1.0, 0.55 * S), (384, 1, 384), "columns of ~h x ~h over the whole height (one cell layer in y)"
 elif _GRID_VARIANT == "2h_tight":
     GRID_MAX, GRID_N, GRID_DESC = (0.55 * S, 0.18, 0.55 * S), (192, 10, 192), "cells of 2h, y extent [-0.02, 0.18] + clamp"
 UV_SCALE = 2.0 / S

@@ -552,7 +552,7 @@ struct RowBounds { int b[RT_ROWS], e[RT_ROWS]; int total; bool wide; };
 __device__ __forceinline__ Query3 list_query(const GridView& g, float x, float y, float z, float h)
 {
     const float hm = h * (1.0f + 2.5e-3f), hx = h * 1.25f;
-    if (hm <= g.cell[0] && hm <= g.cell[1] && hm <= g.cell[2] && g.cell[0] <= hx && g.cell[1] <= hx && g.cell[2] <= hx) {
+    if (hm <= g.cell[0] && hm <= g.cell[1] && hm <= g.cell[2] && (g.cell[0] <= hx || g.n[0] == 1) && (g.cell[1] <= hx || g.n[1] == 1) && (g.cell[2] <= hx || g.n[2] == 1)) {
         Query3 q;
         const int ci = approx_cell(x, g.min[0], g.inv_cell[0], 0.0f, g.n[0]);
         const int cj = approx_cell(y, g.min[1], g.inv_cell[1], 0.0f, g.n[1]);
@@ -711,7 +711,8 @@ __device__ __forceinline__ FlatRows flat_rows_load(const GridView& g, const int*
 {
     FlatRows fr;
     const float hm = h * (1.0f + 2.5e-3f), hx = h * 1.25f;
-    const bool fast = hm <= g.cell[0] && hm <= g.cell[1] && hm <= g.cell[2] && g.cell[0] <= hx && g.cell[1] <= hx && g.cell[2] <= hx;
+    // (an axis with ONE layer of cells may be as thick as it likes: its single cell is the whole range; e.g. columns over a shallow sheet)
+    const bool fast = hm <= g.cell[0] && hm <= g.cell[1] && hm <= g.cell[2] && (g.cell[0] <= hx || g.n[0] == 1) && (g.cell[1] <= hx || g.n[1] == 1) && (g.cell[2] <= hx || g.n[2] == 1);
     fr.total = 0;
     fr.cell_lin = -1;
 #pragma unroll

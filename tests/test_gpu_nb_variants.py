@@ -15,6 +15,7 @@ GRIDS = {
     "h+": ((0.0, -0.02, 0.0), (0.26, 0.18, 0.26), (25, 19, 25)),        # cells 0.0104 x 0.0105: 3 x 3 rows of 3 cells
     "h": ((0.0, -0.02, 0.0), (0.26, 0.18, 0.26), (26, 20, 26)),         # cells of exactly h: conservative ranges may reach 4 cells
     "h/1.5": ((0.0, -0.02, 0.0), (0.26, 0.18, 0.26), (39, 30, 39)),     # h > cell: generic (wide) query
+    "columns": ((0.0, -0.02, 0.0), (0.26, 0.18, 0.26), (25, 1, 25)),    # ONE layer in y: cells are columns over the sheet, 3 x 3 columns per query
 }
 
 
