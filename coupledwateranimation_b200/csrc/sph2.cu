@@ -320,7 +320,8 @@ static Sph2Params sph2_params(cwa_ctx* ctx, Sph2Obj* s)
     return p;
 }
 
-static void sph2_pingpong(Sph2Obj* s) { std::swap(s->read_index, s->write_index); }   // StencilBuffer::PingPong :32-36
+static void sph2_pingpong(Sph2Obj* s) { std::swap(s->read_index, s->write_index); }
+static void sph2_drop_graph(Sph2Obj* s);   // StencilBuffer::PingPong :32-36
 
 extern "C" int cwa_sph2_reinit(cwa_ctx* ctx, cwa_sph2 h)
 {
@@ -365,6 +366,7 @@ extern "C" int cwa_sph2_destroy(cwa_ctx* ctx, cwa_sph2 h)
     Sph2Obj* s = get_sph2(ctx, h);
     CWA_CHECK(s, "invalid sph2 handle %d", h);
     CWA_CUDA(cudaStreamSynchronize(ctx->stream));
+    sph2_drop_graph(s);
     cudaFree(s->posS); cudaFree(s->velS); cudaFree(s->accS);
     for (int i = 0; i < 2; i++) cwa_buffer_destroy(ctx, s->buffer[i]);
     s->live = false;
@@ -411,6 +413,48 @@ extern "C" int cwa_sph2_bind_wave1d(cwa_ctx* ctx, cwa_sph2 h, cwa_buf rgba, int 
     return 0;
 }
 
+// one frame of SphUgrid::Compute (StencilBuffer.cpp:150-179): substeps x (grid build, density pass, forces pass)
+static int sph2_frame(cwa_ctx* ctx, Sph2Obj* s, GridObj* g, const Sph2Params& prm, int lanes)
+{
+    const int n = s->n;
+    const int blocks = ceil_div((long long)n * lanes, 128);
+    for (int sub = 0; sub < s->substeps; sub++) {
+        const float4* rd = (const float4*)get_buffer(ctx, s->buffer[s->read_index])->ptr;
+        float4* wr = (float4*)get_buffer(ctx, s->buffer[s->write_index])->ptr;
+        CWA_TRY(grid_build_internal(ctx, g, rd, 48, n));                 // mGrid.CollisionQuery() :163-164
+        { KScope k(ctx, KID_REORDER);
+          sph2_reorder_kernel<<<ceil_div((long long)n * 3, 256), 256, 0, ctx->stream>>>(rd, g->index_list, g->offset, g->view.num_cells, s->posS, s->velS, s->accS); }
+        for (int tail = 0; tail < 2; tail++) {                           // mode 1 :169-176
+            KScope k(ctx, KID_DENSITY);
+#define CWA_S2_DENS(L) sph2_density_kernel<L><<<blocks, 128, 0, ctx->stream>>>(rd, wr, n, g->view, g->offset, g->index_list, g->cell_of, s->posS, prm, tail)
+            if (lanes == 4) CWA_S2_DENS(4); else if (lanes == 16) CWA_S2_DENS(16); else if (lanes == 32) CWA_S2_DENS(32); else CWA_S2_DENS(8);
+#undef CWA_S2_DENS
+        }
+        sph2_pingpong(s);
+        rd = (const float4*)get_buffer(ctx, s->buffer[s->read_index])->ptr;
+        wr = (float4*)get_buffer(ctx, s->buffer[s->write_index])->ptr;
+        // mode 2 reads the density output through the SAME (now stale) grid lists
+        { KScope k(ctx, KID_REORDER);
+          sph2_reorder_kernel<<<ceil_div((long long)n * 3, 256), 256, 0, ctx->stream>>>(rd, g->index_list, g->offset, g->view.num_cells, s->posS, s->velS, s->accS); }
+        for (int tail = 0; tail < 2; tail++) {
+            KScope k(ctx, KID_FORCE);
+#define CWA_S2_FORCE(L) sph2_forces_kernel<L><<<blocks, 128, 0, ctx->stream>>>(rd, wr, n, g->view, g->offset, g->index_list, g->cell_of, s->posS, s->velS, s->accS, prm, tail)
+            if (lanes == 4) CWA_S2_FORCE(4); else if (lanes == 16) CWA_S2_FORCE(16); else if (lanes == 32) CWA_S2_FORCE(32); else CWA_S2_FORCE(8);
+#undef CWA_S2_FORCE
+        }
+        sph2_pingpong(s);
+    }
+    CWA_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static void sph2_drop_graph(Sph2Obj* s)
+{
+    if (s->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)s->graph_exec);
+    s->graph_exec = nullptr; s->graph_nodes = 0;
+    memset(s->graph_key, 0, sizeof(s->graph_key));
+}
+
 extern "C" int cwa_sph2_compute(cwa_ctx* ctx, cwa_sph2 h, int nframes)
 {
     DeviceGuard _dg(ctx);
@@ -418,41 +462,53 @@ extern "C" int cwa_sph2_compute(cwa_ctx* ctx, cwa_sph2 h, int nframes)
     CWA_CHECK(s, "invalid sph2 handle %d", h);
     GridObj* g = get_grid(ctx, s->grid);
     CWA_CHECK(g, "sph2: grid vanished");
-    const int n = s->n;
     const Sph2Params prm = sph2_params(ctx, s);
     // lanes per target of the neighbour kernels (tuning CWA_S2_LANES: 4, 8, 16 or 32)
     static const int lanes_env = [] { const char* e = getenv("CWA_S2_LANES"); const int v = e ? atoi(e) : 8; return (v == 4 || v == 8 || v == 16 || v == 32) ? v : 8; }();
     const int lanes = lanes_env;
-    const int blocks = ceil_div((long long)n * lanes, 128);
+    if (ctx->tune.graph < 0) { const char* e = getenv("CWA_GRAPH"); ctx->tune.graph = (e && atoi(e) == 0) ? 0 : 1; }
     for (int f = 0; f < nframes; f++) {
-        for (int sub = 0; sub < s->substeps; sub++) {
-            const float4* rd = (const float4*)get_buffer(ctx, s->buffer[s->read_index])->ptr;
-            float4* wr = (float4*)get_buffer(ctx, s->buffer[s->write_index])->ptr;
-            CWA_TRY(grid_build_internal(ctx, g, rd, 48, n));                 // mGrid.CollisionQuery() :163-164
-            { KScope k(ctx, KID_REORDER);
-              sph2_reorder_kernel<<<ceil_div((long long)n * 3, 256), 256, 0, ctx->stream>>>(rd, g->index_list, g->offset, g->view.num_cells, s->posS, s->velS, s->accS); }
-            for (int tail = 0; tail < 2; tail++) {                           // mode 1 :169-176
-                KScope k(ctx, KID_DENSITY);
-#define CWA_S2_DENS(L) sph2_density_kernel<L><<<blocks, 128, 0, ctx->stream>>>(rd, wr, n, g->view, g->offset, g->index_list, g->cell_of, s->posS, prm, tail)
-                if (lanes == 4) CWA_S2_DENS(4); else if (lanes == 16) CWA_S2_DENS(16); else if (lanes == 32) CWA_S2_DENS(32); else CWA_S2_DENS(8);
-#undef CWA_S2_DENS
-            }
-            sph2_pingpong(s);
-            rd = (const float4*)get_buffer(ctx, s->buffer[s->read_index])->ptr;
-            wr = (float4*)get_buffer(ctx, s->buffer[s->write_index])->ptr;
-            // mode 2 reads the density output through the SAME (now stale) grid lists
-            { KScope k(ctx, KID_REORDER);
-              sph2_reorder_kernel<<<ceil_div((long long)n * 3, 256), 256, 0, ctx->stream>>>(rd, g->index_list, g->offset, g->view.num_cells, s->posS, s->velS, s->accS); }
-            for (int tail = 0; tail < 2; tail++) {
-                KScope k(ctx, KID_FORCE);
-#define CWA_S2_FORCE(L) sph2_forces_kernel<L><<<blocks, 128, 0, ctx->stream>>>(rd, wr, n, g->view, g->offset, g->index_list, g->cell_of, s->posS, s->velS, s->accS, prm, tail)
-                if (lanes == 4) CWA_S2_FORCE(4); else if (lanes == 16) CWA_S2_FORCE(16); else if (lanes == 32) CWA_S2_FORCE(32); else CWA_S2_FORCE(8);
-#undef CWA_S2_FORCE
-            }
-            sph2_pingpong(s);
+        // what a frame depends on besides the contents of the buffers: 2 x substeps ping-pongs leave the roles where they were, so while
+        // nothing below changes every frame is the same launch sequence
+        long long key[12] = {};
+        key[0] = (long long)(intptr_t)get_buffer(ctx, s->buffer[s->read_index])->ptr; key[1] = (long long)(intptr_t)get_buffer(ctx, s->buffer[s->write_index])->ptr;
+        key[2] = s->n; key[3] = s->substeps; key[4] = (long long)(intptr_t)g->counter; key[5] = lanes; key[6] = prm.variant;
+        memcpy(&key[7], &prm.time, 4); memcpy((char*)&key[7] + 4, &prm.bottom, 4); memcpy(&key[8], &prm.psi, 4); memcpy((char*)&key[8] + 4, &prm.view_width, 4);
+        key[9] = prm.init_width; key[10] = (long long)(intptr_t)prm.wave1d; key[11] = prm.wave1d_width;
+        const bool use_graph = ctx->tune.graph != 0 && !ctx->profiling && s->n > 0;
+        if (use_graph && s->graph_exec != nullptr && memcmp(key, s->graph_key, sizeof(key)) == 0) {
+            CWA_CUDA(cudaGraphLaunch((cudaGraphExec_t)s->graph_exec, ctx->stream));
+            ctx->launches += s->graph_nodes;
+            continue;
         }
+        if (use_graph && memcmp(key, s->last_key, sizeof(key)) == 0) {   // the second identical frame in a row: worth a capture
+            sph2_drop_graph(s);
+            if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                const unsigned long long l0 = ctx->launches;
+                const int rc = sph2_frame(ctx, s, g, prm, lanes);
+                cudaGraph_t graph = nullptr;
+                const cudaError_t ee = cudaStreamEndCapture(ctx->stream, &graph);
+                cudaGraphExec_t exec = nullptr;
+                if (rc == 0 && ee == cudaSuccess && graph != nullptr && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+                    s->graph_exec = exec; s->graph_nodes = (unsigned)(ctx->launches - l0);
+                    memcpy(s->graph_key, key, sizeof(key));
+                }
+                if (graph) cudaGraphDestroy(graph);
+                (void)cudaGetLastError();
+                ctx->launches = l0;
+                if (rc != 0) return rc;
+                if (s->graph_exec != nullptr) {                          // the captured frame has not run yet
+                    CWA_CUDA(cudaGraphLaunch((cudaGraphExec_t)s->graph_exec, ctx->stream));
+                    ctx->launches += s->graph_nodes;
+                    continue;
+                }
+            } else {
+                (void)cudaGetLastError();
+            }
+        }
+        memcpy(s->last_key, key, sizeof(key));
+        CWA_TRY(sph2_frame(ctx, s, g, prm, lanes));
     }
-    CWA_CUDA(cudaGetLastError());
     return 0;
 }
 

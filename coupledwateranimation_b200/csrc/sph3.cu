@@ -702,6 +702,8 @@ __device__ __forceinline__ void f2_unpack(unsigned long long v, float& lo, float
 __device__ __forceinline__ unsigned long long f2_sub(unsigned long long a, unsigned long long b) { unsigned long long r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) { unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) { unsigned long long r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+// 1 << n with PTX semantics (a shift by 32 or more gives 0): the rows of a clump target finished without masks are longer than a mask
+__device__ __forceinline__ unsigned shl_clamp(unsigned v, int n) { unsigned r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }
 __device__ __forceinline__ unsigned long long f2_ldg(const float* p) { unsigned long long r; asm("ld.global.nc.b64 %0, [%1];" : "=l"(r) : "l"(p)); return r; }
 
 constexpr int ROW_MASK_BITS = 31;         // longest row a mask records: with an odd first slot the pair loop shifts by (length + 1) - 1 at most
@@ -856,7 +858,7 @@ sph3_density_flat_kernel(const float4* __restrict__ posS, const float* __restric
             const int2 rown = adv ? cand : row;                                                    \
             const int jn = adv ? (cand.x & ~1) : j + 2;                                            \
             if (more) { NX = f2_ldg(xs + jn); NY = f2_ldg(ys + jn); NZ = f2_ldg(zs + jn); }        \
-            step2(CX, CY, CZ, j, row.x, row.y, 1u << (j + 1 - row.x));                             \
+            step2(CX, CY, CZ, j, row.x, row.y, shl_clamp(1u, j + 1 - row.x));                      \
             if (adv) { tp_cur->y = (int)mask; mask = 0u; }                                         \
             if (!more) break;                                                                      \
             j = jn; row = rown;                                                                    \

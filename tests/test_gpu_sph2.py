@@ -83,3 +83,30 @@ def test_c2_size_64k_particles_runs_and_conserves_count(cwa, ctx, oracle):
     ref = (b0, b1)[r]
     assert_close(got["acc"][:, 3], ref["acc"][:, 3], rtol=1e-3, what="rho after 3 frames")
     assert_close(got["pos"][:, :2], ref["pos"][:, :2], rtol=1e-3, scale=1e-2, what="pos after 3 frames")
+
+
+def test_frame_graph_replays_the_same_frames(cwa, ctx, oracle):
+    """cwa_sph2_compute captures a CUDA graph of the frame the second time the same frame is asked for and replays it while buffers, uniforms
+    and grid stay put; a changed uniform falls back to plain launches (and a new capture).  Bit-identical to the plain launch sequence."""
+    n = 4096
+    ext = ((0.0, 0.0), (9.6, 9.6), (32, 32))
+
+    def run(graph):
+        ctx.set_tuning(graph=graph)
+        grid = cwa.UniformGrid(ctx, 2, *ext, n)
+        s = cwa.SphUgrid(ctx, n, grid, cwa.SPH2_WAVE, substeps=2)
+        s.Reinit()
+        s.Compute(5)                       # frames 3..5 are replays when graphs are on
+        s.set_uniforms(bottom=0.35)        # a uniform changes: plain launch, then a new capture
+        s.Compute(4)
+        s.Compute(1)
+        out = s.download()
+        s.destroy(); grid.destroy()
+        return out
+
+    try:
+        a, b = run(0), run(1)
+    finally:
+        ctx.set_tuning(graph=1)
+    assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+    assert np.isfinite(a["pos"][:, :2]).all()
