@@ -775,11 +775,18 @@ def main():
     ap.add_argument("--config", default="C4", choices=["C4", "D", "C2", "C3"],
                     help="BASELINE.json config at --gpus 1: C4 (default, the metric's configuration), D (shipped scene), C2 (2-D Koschier 64k), C3 (4096^2 wave)")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the short D / C2 / C3 rows added to the default C4 line")
+    ap.add_argument("--box", default="contains", choices=["contains", "literal"],
+                    help="C4 tank: upper.xz = 0.55 s (contains the lattice; default) or SURVEY's literal 0.48 s (the lattice overhangs: the first integrate "
+                         "clamps 7 s columns onto the wall, coincident particles turn NaN -- the reference's own behaviour, SURVEY App. C)")
     ap.add_argument("--state-frame", type=int, default=0,
                     help="C4: advance the simulation to this frame before the timed region (the cost of a frame drifts as the fluid clumps); 0 = early state")
     ap.add_argument("--scene", default="", choices=["", "torque_scaled", "literal", "weak"],
                     help="--gpus N > 1: C5 with torque_coeff 0.25/4 (default), C5 with the shader's literal 0.25, or the weak-scaling scene C4 x sqrt(N)")
     args = ap.parse_args()
+    if args.box == "literal":
+        global BOX_UPPER, WORKLOAD
+        BOX_UPPER = (0.48 * S, 1.0, 0.48 * S, 500.0)
+        WORKLOAD += ", tank upper.xz = 0.48 s as SURVEY writes it (lattice overhangs the wall)"
     if args.impl == "reference":
         run_reference(args)
     else:
