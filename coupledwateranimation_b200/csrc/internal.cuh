@@ -248,7 +248,7 @@ struct ProfRec { int id; cudaEvent_t a, b; };
 // hold different settings.  -1 = not set yet: the default comes from the environment (CWA_NB_CONFIG, ...) on first use.
 struct CtxTuning {
     int config = -1, cap_d = -1, cap_f = -1, fused_order = -1, fused_integrate = -1, pipeline = -1, nbr_k = -1, extreme = -1;
-    int scan_config = -1, wave_transpose = -1, graph = -1, inplace_max = -1, allpairs_bal = -1, slab_ahead = -1;
+    int scan_config = -1, wave_transpose = -1, graph = -1, inplace_max = -1, allpairs_bal = -1, slab_ahead = -1, heavy8 = -1;
 };
 
 struct SlabObj;

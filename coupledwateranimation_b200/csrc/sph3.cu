@@ -538,6 +538,7 @@ sph3_force_grid_kernel(const float4* __restrict__ pack,
 // left alone with such a target would outlast the rest of the kernel.  Targets with more than EXTREME_CANDIDATES
 // candidates (density pass) or more than K neighbours (force pass) are therefore pushed to a device-side queue and
 // finished by the "heavy" kernels, one WARP per target, spread over the whole GPU.
+constexpr int SUB_WARP_MAX = 640;      // force of a queued target: up to here 8 lanes (4 targets per warp), beyond the whole warp
 constexpr int RT_ROWS = 9;
 constexpr int TILE_P = 128;               // targets per tile (= CTA size of the list kernels)
 constexpr int EXTREME_CANDIDATES = 192;   // a target with more candidates than this (or more 31-slot row segments than table entries) is a clump target; tuning "extreme_candidates", up to 9 x 31 = 279
@@ -1166,7 +1167,7 @@ template <bool FUSED, bool LOCAL>
 __global__ void __launch_bounds__(128)
 sph3_force_heavy_kernel(const float4* __restrict__ pack, const int* __restrict__ heavy_queue, const int* __restrict__ heavy_count, int cap,
                         float4* __restrict__ pairP, float2* __restrict__ pairV, GridView g,
-                        const int* __restrict__ offset, const Sph3Const* __restrict__ cc, FinishArgs fa)
+                        const int* __restrict__ offset, const Sph3Const* __restrict__ cc, FinishArgs fa, const bool sub_warp_heavy)
 {
     const int lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -1181,8 +1182,8 @@ sph3_force_heavy_kernel(const float4* __restrict__ pack, const int* __restrict__
     __shared__ int s_rows[HEAVY_WARPS][2][33];
     int* const sP = s_rows[(threadIdx.x >> 5) % HEAVY_WARPS][0];
     int* const sG = s_rows[(threadIdx.x >> 5) % HEAVY_WARPS][1];
-    for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < total; e += nwarps) {
-        const int slot = __ldg(heavy_queue + e);
+    // one target, the whole warp: lane l takes every 32nd candidate
+    auto whole_warp = [&](const int slot) {
         const f4x2 own = cwa_ldg256(pack + 2 * (size_t)slot);
         const float4 pa = own.a, pb = own.b;
         const Query3 q = list_query(g, pa.x, pa.y, pa.z, c.h);
@@ -1246,7 +1247,106 @@ sph3_force_heavy_kernel(const float4* __restrict__ pack, const int* __restrict__
                 kept = 0;
             }
         }
+    };
+    // Cells of ~h (every query is the 3 x 3 x 3 block: nine rows) and the separate integrate kernel: FOUR targets per warp, eight lanes each.
+    // A clump target has a few hundred candidates -- three trips of a whole warp -- so with one target per warp half the instructions were
+    // per-target overhead (set-up 17 %, candidate mapping 20 %, shuffle reduction 9 %: ncu at frame 3000, profiles/r2); four targets share
+    // those instructions.  The divergent pair term costs the same (a trip still tests 128 candidates).  Targets of more than SUB_WARP_MAX
+    // candidates (the few cells of hundreds of particles early in a run) keep the whole warp: eight lanes on thousands of candidates are a tail.
+    {
+        const float hm = c.h * (1.0f + 2.5e-3f), hx = c.h * 1.25f;
+        const bool fast = hm <= g.cell[0] && hm <= g.cell[1] && hm <= g.cell[2] && (g.cell[0] <= hx || g.n[0] == 1) && (g.cell[1] <= hx || g.n[1] == 1) &&
+                          (g.cell[2] <= hx || g.n[2] == 1);
+        if (!FUSED && fast && sub_warp_heavy && total > nwarps) {    // (fewer targets than warps: a warp each finishes sooner)
+            constexpr int G = 8;
+            const int gl = lane & (G - 1), grp = lane >> 3;
+            const unsigned gmask = 0xffu << (grp * G);
+            int* const gP = sP + grp * 8;                              // 4 groups x (<= 8 prefix entries) share the warp's 33 + 33 ints:
+            int* const gG = sG + grp * 8;                              // entry r < 8 of the group in gP / gG, row 8 and the total in registers
+            // (the warp's four targets are CONSECUTIVE queue entries -- neighbours in cell order, their candidates are the same cache lines;
+            //  measured with the four a stride apart: frame 3040 of C4 536 us instead of 489)
+            for (int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4; base < total; base += nwarps * 4) {
+                const int e = base + grp;
+                const bool valid = e < total;
+                const int slot = __ldg(heavy_queue + (valid ? e : base));
+                const f4x2 own = cwa_ldg256(pack + 2 * (size_t)slot);
+                const float4 pa = own.a, pb = own.b;
+                const int ci = approx_cell(pa.x, g.min[0], g.inv_cell[0], 0.0f, g.n[0]);
+                const int cj = approx_cell(pa.y, g.min[1], g.inv_cell[1], 0.0f, g.n[1]);
+                const int ck = approx_cell(pa.z, g.min[2], g.inv_cell[2], 0.0f, g.n[2]);
+                const int kl = max(ck - 1, 0), kh = min(ck + 1, g.n[2] - 1);
+                // rows 0..7: one per lane; row 8 (i + 1, j + 1): every lane loads it (same address: one transaction)
+                auto row_bounds = [&](int r, int& b, int& len) {
+                    const int i = ci + r / 3 - 1, j = cj + r % 3 - 1;
+                    b = 0; len = 0;
+                    if (i >= 0 && i < g.n[0] && j >= 0 && j < g.n[1]) {
+                        const int rowbase = (i * g.n[1] + j) * g.kstride;
+                        b = __ldg(offset + rowbase + kl);
+                        len = __ldg(offset + rowbase + kh + 1) - b;
+                    }
+                };
+                int b_own, len_own, b8, len8;
+                row_bounds(gl, b_own, len_own);
+                row_bounds(8, b8, len8);
+                int incl = len_own;
+#pragma unroll
+                for (int d = 1; d < G; d <<= 1) {
+                    const int t = __shfl_up_sync(gmask, incl, d, G);
+                    if (gl >= d) incl += t;
+                }
+                const int total8 = __shfl_sync(gmask, incl, G - 1, G);          // candidates of rows 0..7
+                const int ncand_all = total8 + len8;
+                const bool big = valid && ncand_all > SUB_WARP_MAX;             // a handful of these per frame: the whole warp, below
+                const int ncand = big ? 0 : ncand_all;
+                __syncwarp(gmask);                                              // the group's reads of the previous target's table are done
+                gP[gl] = incl - len_own; gG[gl] = b_own;
+                __syncwarp(gmask);
+                auto candidate = [&](int f, int& r) {                           // flat index -> cell-ordered slot; r only moves forward
+                    if (f >= total8) return b8 + (f - total8);
+                    while (r < G - 1 && f >= gP[r + 1]) r++;
+                    return gG[r] + (f - gP[r]);
+                };
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f, s5 = 0.f;
+                int r = 0;
+                for (int fb = gl; fb < ncand; fb += 4 * G) {
+                    int cand[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int f = fb + G * u;
+                        cand[u] = (f < ncand) ? candidate(f, r) : slot;              // past the end: the target itself, skipped below
+                    }
+                    f4x2 rec[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) rec[u] = cwa_ldg256(pack + 2 * (size_t)cand[u]);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const float r2 = cwa_len3sq(pa.x - rec[u].a.x, pa.y - rec[u].a.y, pa.z - rec[u].a.z);
+                        if (r2 <= c.accept_r2 && cand[u] != slot)
+                            pair_force(c, pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, rec[u].a, rec[u].b, s0, s1, s2, s3, s4, s5);
+                    }
+                }
+#pragma unroll
+                for (int d = G / 2; d >= 1; d >>= 1) {
+                    s0 += __shfl_xor_sync(gmask, s0, d, G); s1 += __shfl_xor_sync(gmask, s1, d, G);
+                    s2 += __shfl_xor_sync(gmask, s2, d, G); s3 += __shfl_xor_sync(gmask, s3, d, G);
+                    s4 += __shfl_xor_sync(gmask, s4, d, G); s5 += __shfl_xor_sync(gmask, s5, d, G);
+                }
+                if (gl == 0 && valid && !big) {
+                    pairP[slot] = make_float4(s0, s1, s2, s3);
+                    pairV[slot] = make_float2(s4, s5);
+                }
+                unsigned bigm = __ballot_sync(0xffffffffu, big && gl == 0);
+                for (; bigm; bigm &= bigm - 1) {                                // (warp-uniform; whole_warp syncs the warp around its table)
+                    const int slot_b = __shfl_sync(0xffffffffu, slot, __ffs(bigm) - 1);
+                    __syncwarp();
+                    whole_warp(slot_b);
+                    __syncwarp();
+                }
+            }
+            return;
+        }
     }
+    for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < total; e += nwarps) whole_warp(__ldg(heavy_queue + e));
     if (FUSED && lane < kept) finish_particle<LOCAL>(c, fa, k_slot, k_pa, k_pb, k0, k1, k2, k3, k4, k5);
 }
 
@@ -1746,6 +1846,7 @@ static int nbr_k(cwa_ctx* c) { if (c->tune.nbr_k < 0) c->tune.nbr_k = env_int("C
 static int extreme_candidates(cwa_ctx* c) { if (c->tune.extreme < 0) c->tune.extreme = env_int("CWA_EXTREME", EXTREME_CANDIDATES, 16, 1 << 20); return c->tune.extreme; }
 static int inplace_max(cwa_ctx* c) { if (c->tune.inplace_max < 0) c->tune.inplace_max = env_int("CWA_INPLACE_MAX", INPLACE_MAX, 0, 1 << 20); return c->tune.inplace_max; }
 static int allpairs_balanced(cwa_ctx* c) { if (c->tune.allpairs_bal < 0) c->tune.allpairs_bal = env_int("CWA_ALLPAIRS_BALANCED", 2, 0, 2); return c->tune.allpairs_bal; }
+static bool heavy_sub_warp(cwa_ctx* c) { if (c->tune.heavy8 < 0) c->tune.heavy8 = env_int("CWA_HEAVY8", 1, 0, 1); return c->tune.heavy8 != 0; }
 static bool fused_order(cwa_ctx* c) { if (c->tune.fused_order < 0) c->tune.fused_order = env_int("CWA_FUSED_ORDER", 1, 0, 1); return c->tune.fused_order != 0; }
 
 extern "C" int cwa_set_tuning(cwa_ctx* ctx, const char* key, int value)
@@ -1759,6 +1860,7 @@ extern "C" int cwa_set_tuning(cwa_ctx* ctx, const char* key, int value)
     else if (k == "fused_order") { ctx->tune.fused_order = value ? 1 : 0; }
     else if (k == "fused_integrate") { ctx->tune.fused_integrate = value ? 1 : 0; }
     else if (k == "nbr_k") { CWA_CHECK(value >= 8 && value <= NBR_K_MAX && value % 4 == 0, "nbr_k %d: multiple of 4 in [8, %d]", value, NBR_K_MAX); ctx->tune.nbr_k = value; }
+    else if (k == "heavy_sub_warp") { ctx->tune.heavy8 = value ? 1 : 0; }
     else if (k == "slab_ahead") { ctx->tune.slab_ahead = value ? 1 : 0; }
     else if (k == "allpairs_balanced") { CWA_CHECK(value >= 0 && value <= 2, "allpairs_balanced %d: 0 off, 1 density pass, 2 both passes", value); ctx->tune.allpairs_bal = value; }
     else if (k == "inplace_max") { CWA_CHECK(value >= 0, "inplace_max %d negative", value); ctx->tune.inplace_max = value; }
@@ -1858,7 +1960,7 @@ static int launch_force_list(cwa_ctx* ctx, SphObj* s, GridObj* g, bool fused, fl
 #define CWA_FORCE_LIST(F, L) sph3_force_list_kernel<F, L><<<blocks, TILE_P, 0, ctx->stream>>>( \
         s->pack, s->nbr_list, s->nbr_count, fq, s->heavy_cnt + 1, s->pairP, s->pairV, s->n, g->view, g->offset, cc, fa, s->nbr_k_used)
 #define CWA_FORCE_HEAVY(F, L) sph3_force_heavy_kernel<F, L><<<heavy_grid(ctx), 128, 0, ctx->stream>>>( \
-        s->pack, fq, s->heavy_cnt + 1, s->n, s->pairP, s->pairV, g->view, g->offset, cc, fa)
+        s->pack, fq, s->heavy_cnt + 1, s->n, s->pairP, s->pairV, g->view, g->offset, cc, fa, heavy_sub_warp(ctx))
 #define CWA_FORCE_ROWS(F, L) sph3_force_rows_kernel<F, L><<<blocks, TILE_P, 0, ctx->stream>>>( \
         s->pack, reinterpret_cast<const int2*>(s->nbr_list), s->nbr_count, fq, s->heavy_cnt + 1, s->pairP, s->pairV, s->n, g->view, g->offset, cc, fa)
     if (s->nbr_rows_fmt) {

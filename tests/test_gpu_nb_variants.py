@@ -147,8 +147,9 @@ def test_fused_integrate_tail_equals_separate_kernels(cwa, tuned, oracle, cluste
         sph.upload(p)
         sph.step(2)
         b = sph.download()
+        # (clump targets: the separate path sums a queued target's pairs over 8 lanes, the fused one over 32 -- another order of the same terms)
         for f in ("pos", "vel", "force", "extras"):
-            assert_close(b[f], a[f], rtol=5e-6, what=f)
+            assert_close(b[f], a[f], rtol=2e-5 if cluster else 5e-6, what=f)
         ref = p.copy()
         for _ in range(2):
             oracle.sph3_rho_pres(ref, prm, tex); oracle.sph3_force(ref, prm, tex); oracle.sph3_integrate(ref, prm, tex)
