@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(THREADS)
 scan_lookback_kernel(const int* __restrict__ in, int* __restrict__ out, int n, int write_total,
                      int* __restrict__ ticket, volatile unsigned long long* __restrict__ tile_state)
 {
+    cwa_pdl_enter();
     constexpr int TILE = THREADS * ITEMS;
     constexpr int WARPS = THREADS / 32;
     constexpr int Q = ITEMS / 4;
@@ -250,10 +251,10 @@ int scan_exclusive_launch(cwa_ctx* ctx, const int* in, int* out, int n, int* tic
     if (n < 0) n = -n;
     KScope k(ctx, KID_SCAN);
     switch (scan_config(ctx)) {
-    case 0: scan_lookback_kernel<256, 16, false><<<ceil_div(n, 256 * 16), 256, 0, ctx->stream>>>(in, out, n, write_total, ticket, tile_state); break;
-    case 1: scan_lookback_kernel<512, 32, false><<<ceil_div(n, 512 * 32), 512, 0, ctx->stream>>>(in, out, n, write_total, ticket, tile_state); break;
-    case 3: scan_lookback_kernel<1024, 16, true><<<ceil_div(n, 1024 * 16), 1024, 0, ctx->stream>>>(in, out, n, write_total, ticket, tile_state); break;
-    default: scan_lookback_kernel<512, 32, true><<<ceil_div(n, 512 * 32), 512, 0, ctx->stream>>>(in, out, n, write_total, ticket, tile_state); break;
+    case 0: cwa_launch(ctx, PDL_SCAN, scan_lookback_kernel<256, 16, false>, dim3(ceil_div(n, 256 * 16)), dim3(256), 0, in, out, n, write_total, ticket, tile_state); break;
+    case 1: cwa_launch(ctx, PDL_SCAN, scan_lookback_kernel<512, 32, false>, dim3(ceil_div(n, 512 * 32)), dim3(512), 0, in, out, n, write_total, ticket, tile_state); break;
+    case 3: cwa_launch(ctx, PDL_SCAN, scan_lookback_kernel<1024, 16, true>, dim3(ceil_div(n, 1024 * 16)), dim3(1024), 0, in, out, n, write_total, ticket, tile_state); break;
+    default: cwa_launch(ctx, PDL_SCAN, scan_lookback_kernel<512, 32, true>, dim3(ceil_div(n, 512 * 32)), dim3(512), 0, in, out, n, write_total, ticket, tile_state); break;
     }
     CWA_CUDA(cudaGetLastError());
     return 0;
@@ -334,6 +335,7 @@ __global__ void __launch_bounds__(256)
 grid_insert_ahead_kernel(const int* __restrict__ cell_s, const int* __restrict__ rank_s, const int* __restrict__ old_index_list,
                          const int* __restrict__ offset, int n, int* __restrict__ cell_of, int* __restrict__ arrival, bool keep_vanished)
 {
+    cwa_pdl_enter();
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const int c = __ldg(cell_s + s);
@@ -394,7 +396,7 @@ int grid_build_internal(cwa_ctx* ctx, GridObj* g, const void* particles, int str
         { KScope k(ctx, KID_INSERT);
           if (ahead)
           {
-              grid_insert_ahead_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(opts.ahead_cell, opts.ahead_rank, g->index_list, g->offset, n, g->cell_of, g->arrival,
+              cwa_launch(ctx, PDL_INSERT, grid_insert_ahead_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, opts.ahead_cell, opts.ahead_rank, g->index_list, g->offset, n, g->cell_of, g->arrival,
                                                                                   opts.arrivals != nullptr);
               if (opts.arrivals != nullptr && opts.arrivals_max > 0)
                   grid_insert_arrivals_kernel<<<ceil_div(opts.arrivals_max, 256), 256, 0, ctx->stream>>>(opts.arrivals, opts.arrivals_count, opts.arrivals_max,

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/cwa_b200.h"
@@ -248,7 +249,7 @@ struct ProfRec { int id; cudaEvent_t a, b; };
 // hold different settings.  -1 = not set yet: the default comes from the environment (CWA_NB_CONFIG, ...) on first use.
 struct CtxTuning {
     int config = -1, cap_d = -1, cap_f = -1, fused_order = -1, fused_integrate = -1, pipeline = -1, nbr_k = -1, extreme = -1;
-    int scan_config = -1, wave_transpose = -1, graph = -1, inplace_max = -1, allpairs_bal = -1, slab_ahead = -1, heavy8 = -1;
+    int scan_config = -1, wave_transpose = -1, graph = -1, inplace_max = -1, allpairs_bal = -1, slab_ahead = -1, heavy8 = -1, pdl = -1;
 };
 
 struct SlabObj;
@@ -421,6 +422,39 @@ struct KScope {
 // device helpers shared by the kernels
 // ---------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+// Programmatic dependent launch (sm_90+): the kernels of a frame run back to back on one stream, each a few tens of microseconds, and
+// every boundary costs the drain of the last wave plus the ramp-up of the next grid.  A kernel of the chain starts with cwa_pdl_enter():
+// `launch_dependents` lets the NEXT kernel's CTAs be scheduled as soon as every CTA of this one has started (they fill the SMs the last
+// wave leaves idle), `wait` holds them until the PREVIOUS grid has completed and its writes are visible -- so nothing before the wait may
+// touch global memory another kernel writes.  Without the launch attribute (cwa_launch with pdl off, or <<<>>>) both are no-ops.
+__device__ __forceinline__ void cwa_pdl_enter()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// the kernels of the chain, as bits of the tuning value `pdl` (which launches carry the attribute)
+enum { PDL_SCAN = 1, PDL_INSERT = 2, PDL_REORDER = 4, PDL_DENSITY = 8, PDL_DENSITY_HEAVY = 16, PDL_FORCE = 32, PDL_FORCE_HEAVY = 64, PDL_INTEGRATE = 128 };
+#define CWA_PDL_DEFAULT (255 & ~(PDL_INSERT | PDL_REORDER))   // measured (profiles/r2/tuning.md): those two cost more than they gain
+static inline bool cwa_pdl_enabled(cwa_ctx* c, int bit)
+{
+    if (c->tune.pdl < 0) { const char* e = getenv("CWA_PDL"); c->tune.pdl = (e && *e) ? (atoi(e) & 255) : CWA_PDL_DEFAULT; }
+    return (c->tune.pdl & bit) != 0 && !c->profiling;      // (a profile brackets every launch with events: nothing to overlap)
+}
+
+// <<<grid, block, smem, ctx->stream>>> with the programmatic-serialization attribute; the kernel must begin with cwa_pdl_enter()
+template <typename... KArgs, typename... Args>
+static inline cudaError_t cwa_launch(cwa_ctx* ctx, int pdl_bit, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = cwa_pdl_enabled(ctx, pdl_bit) ? 1u : 0u;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // 256-bit global accesses (sm_100: LDG.E.ENL2.256 / STG.E.ENL2.256).  The 32-byte records of the hot path --
 // the (pos, p | vel, rho) pack of a cell-ordered slot, half a particle record, a pair of candidate positions

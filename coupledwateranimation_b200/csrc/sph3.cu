@@ -274,6 +274,7 @@ sph3_order_reorder_kernel(const float4* __restrict__ aos, const int* __restrict_
                           float4* __restrict__ posS, float4* __restrict__ velS, float4* __restrict__ forceS,
                           float4* __restrict__ miscS, int* __restrict__ heavy_cnt, float* __restrict__ xyzS, size_t xyz_stride)
 {
+    cwa_pdl_enter();
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s == 0) { heavy_cnt[0] = 0; heavy_cnt[1] = 0; }   // clump queues of the density / force passes that follow this snapshot
     if (s >= __ldg(count)) return;                 // inserted particles (NaN positions are left out)
@@ -778,6 +779,7 @@ sph3_density_flat_kernel(const float4* __restrict__ posS, const float* __restric
                          int n_max, GridView g, const int* __restrict__ offset, const Sph3Const* __restrict__ cc, TexView tex,
                          const int extreme_candidates, const int inplace_max)
 {
+    cwa_pdl_enter();
     __shared__ int2 tab[(RT_ROWS + 1) * TILE_P];       // non-empty rows of every target, compacted: (first slot, end slot), later (first slot, mask)
     const int tid = threadIdx.x;
     const int slot = blockIdx.x * TILE_P + tid;
@@ -937,6 +939,7 @@ sph3_density_heavy_kernel(const float4* __restrict__ posS, const float4* __restr
                           int* __restrict__ nbr_count, const int* __restrict__ heavy_queue, const int* __restrict__ heavy_count, int cap,
                           GridView g, const int* __restrict__ offset, const Sph3Const* __restrict__ cc, TexView tex)
 {
+    cwa_pdl_enter();
     const int lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int total = min(__ldg(heavy_count), cap);
@@ -1090,6 +1093,7 @@ sph3_force_rows_kernel(const float4* __restrict__ pack, const int2* __restrict__
                        float4* __restrict__ pairP, float2* __restrict__ pairV, int n_max,
                        GridView g, const int* __restrict__ offset, const Sph3Const* __restrict__ cc, FinishArgs fa)
 {
+    cwa_pdl_enter();
     __shared__ int2 tab[(RT_ROWS + 1) * TILE_P];
     const int tid = threadIdx.x;
     const int slot = blockIdx.x * TILE_P + tid;
@@ -1169,6 +1173,7 @@ sph3_force_heavy_kernel(const float4* __restrict__ pack, const int* __restrict__
                         float4* __restrict__ pairP, float2* __restrict__ pairV, GridView g,
                         const int* __restrict__ offset, const Sph3Const* __restrict__ cc, FinishArgs fa, const bool sub_warp_heavy)
 {
+    cwa_pdl_enter();
     const int lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int total = min(__ldg(heavy_count), cap);
@@ -1370,6 +1375,7 @@ sph3_finalize_integrate_sorted_kernel(const float4* __restrict__ pack,
                                       GridView g, int n, int* __restrict__ counter, int* __restrict__ cell_next, int* __restrict__ rank_next,
                                       SlabPackArgs sp)
 {
+    cwa_pdl_enter();
     constexpr bool AHEAD = (MODE == 1 || MODE == 3);  // 3: slab pack AND count-ahead (the particles that stay owned; arrivals are counted by the unpack kernel)
     constexpr bool SLAB = (MODE == 2 || MODE == 3);
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1861,6 +1867,7 @@ extern "C" int cwa_set_tuning(cwa_ctx* ctx, const char* key, int value)
     else if (k == "fused_integrate") { ctx->tune.fused_integrate = value ? 1 : 0; }
     else if (k == "nbr_k") { CWA_CHECK(value >= 8 && value <= NBR_K_MAX && value % 4 == 0, "nbr_k %d: multiple of 4 in [8, %d]", value, NBR_K_MAX); ctx->tune.nbr_k = value; }
     else if (k == "heavy_sub_warp") { ctx->tune.heavy8 = value ? 1 : 0; }
+    else if (k == "pdl") { ctx->tune.pdl = value & 255; }
     else if (k == "slab_ahead") { ctx->tune.slab_ahead = value ? 1 : 0; }
     else if (k == "allpairs_balanced") { CWA_CHECK(value >= 0 && value <= 2, "allpairs_balanced %d: 0 off, 1 density pass, 2 both passes", value); ctx->tune.allpairs_bal = value; }
     else if (k == "inplace_max") { CWA_CHECK(value >= 0, "inplace_max %d negative", value); ctx->tune.inplace_max = value; }
@@ -1925,10 +1932,10 @@ static int launch_density_list(cwa_ctx* ctx, SphObj* s, GridObj* g, TexView tex,
         KScope k(ctx, KID_DENSITY);
         int2* rows = reinterpret_cast<int2*>(s->nbr_list);
         if (local)
-            sph3_density_flat_kernel<true><<<ntiles, TILE_P, 0, ctx->stream>>>(
+            cwa_launch(ctx, PDL_DENSITY, sph3_density_flat_kernel<true>, dim3(ntiles), dim3(TILE_P), 0,
                 s->posS, s->xyzS, s->xyz_stride, s->velS, s->pack, rows, s->nbr_count, s->heavy_queue, hc, s->n, g->view, g->offset, cc, tex, extreme_candidates(ctx), inplace_max(ctx));
         else
-            sph3_density_flat_kernel<false><<<ntiles, TILE_P, 0, ctx->stream>>>(
+            cwa_launch(ctx, PDL_DENSITY, sph3_density_flat_kernel<false>, dim3(ntiles), dim3(TILE_P), 0,
                 s->posS, s->xyzS, s->xyz_stride, s->velS, s->pack, rows, s->nbr_count, s->heavy_queue, hc, s->n, g->view, g->offset, cc, tex, extreme_candidates(ctx), inplace_max(ctx));
     } else {
       KScope k(ctx, KID_DENSITY);
@@ -1940,10 +1947,10 @@ static int launch_density_list(cwa_ctx* ctx, SphObj* s, GridObj* g, TexView tex,
               s->posS, s->velS, s->pack, s->nbr_list, s->nbr_count, s->heavy_queue, hc, s->n, g->view, g->offset, cc, tex, K, extreme_candidates(ctx)); }
     { KScope k(ctx, KID_HEAVY);
       if (local)
-          sph3_density_heavy_kernel<true><<<heavy_grid(ctx), 128, 0, ctx->stream>>>(
+          cwa_launch(ctx, PDL_DENSITY_HEAVY, sph3_density_heavy_kernel<true>, dim3(heavy_grid(ctx)), dim3(128), 0,
               s->posS, s->velS, s->pack, s->nbr_count, s->heavy_queue, hc, s->n, g->view, g->offset, cc, tex);
       else
-          sph3_density_heavy_kernel<false><<<heavy_grid(ctx), 128, 0, ctx->stream>>>(
+          cwa_launch(ctx, PDL_DENSITY_HEAVY, sph3_density_heavy_kernel<false>, dim3(heavy_grid(ctx)), dim3(128), 0,
               s->posS, s->velS, s->pack, s->nbr_count, s->heavy_queue, hc, s->n, g->view, g->offset, cc, tex); }
     s->nbr_lists_valid = true;
     return 0;
@@ -1959,9 +1966,9 @@ static int launch_force_list(cwa_ctx* ctx, SphObj* s, GridObj* g, bool fused, fl
     const bool local = tex_view_is_local(tex);
 #define CWA_FORCE_LIST(F, L) sph3_force_list_kernel<F, L><<<blocks, TILE_P, 0, ctx->stream>>>( \
         s->pack, s->nbr_list, s->nbr_count, fq, s->heavy_cnt + 1, s->pairP, s->pairV, s->n, g->view, g->offset, cc, fa, s->nbr_k_used)
-#define CWA_FORCE_HEAVY(F, L) sph3_force_heavy_kernel<F, L><<<heavy_grid(ctx), 128, 0, ctx->stream>>>( \
+#define CWA_FORCE_HEAVY(F, L) cwa_launch(ctx, PDL_FORCE_HEAVY, sph3_force_heavy_kernel<F, L>, dim3(heavy_grid(ctx)), dim3(128), 0, \
         s->pack, fq, s->heavy_cnt + 1, s->n, s->pairP, s->pairV, g->view, g->offset, cc, fa, heavy_sub_warp(ctx))
-#define CWA_FORCE_ROWS(F, L) sph3_force_rows_kernel<F, L><<<blocks, TILE_P, 0, ctx->stream>>>( \
+#define CWA_FORCE_ROWS(F, L) cwa_launch(ctx, PDL_FORCE, sph3_force_rows_kernel<F, L>, dim3(blocks), dim3(TILE_P), 0, \
         s->pack, reinterpret_cast<const int2*>(s->nbr_list), s->nbr_count, fq, s->heavy_cnt + 1, s->pairP, s->pairV, s->n, g->view, g->offset, cc, fa)
     if (s->nbr_rows_fmt) {
       KScope k(ctx, KID_FORCE);
@@ -1995,7 +2002,7 @@ static int sph_snapshot(cwa_ctx* ctx, SphObj* s, bool count_next_ahead = false, 
     CWA_TRY(grid_build_internal(ctx, g, pb->ptr, 64, s->n, opts));
     if (fused_order(ctx)) {
         KScope k(ctx, KID_REORDER);
-        sph3_order_reorder_kernel<<<ceil_div(s->n > 0 ? s->n : 1, 256), 256, 0, ctx->stream>>>(
+        cwa_launch(ctx, PDL_REORDER, sph3_order_reorder_kernel, dim3(ceil_div(s->n > 0 ? s->n : 1, 256)), dim3(256), 0,
             (const float4*)pb->ptr, g->arrival, g->cell_of, g->offset, g->offset + g->view.num_cells, g->index_list,
             s->posS, s->velS, s->forceS, s->miscS, s->heavy_cnt, s->xyzS, s->xyz_stride);
     } else {
@@ -2146,7 +2153,7 @@ int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which, bool co
             const bool local = tex_view_is_local(tex);
             const SlabPackArgs spa = slab ? *slab : SlabPackArgs();
             const int mode = slab ? (count_ahead ? 3 : 2) : (count_ahead ? 1 : 0);
-#define CWA_FIN_INT(L, M) sph3_finalize_integrate_sorted_kernel<L, M><<<ceil_div(n, 128), 128, 0, ctx->stream>>>( \
+#define CWA_FIN_INT(L, M) cwa_launch(ctx, PDL_INTEGRATE, sph3_finalize_integrate_sorted_kernel<L, M>, dim3(ceil_div(n, 128)), dim3(128), 0, \
                     s->pack, s->forceS, s->miscS, s->pairP, s->pairV, g->index_list, g->offset + g->view.num_cells, aos, cc, tex, \
                     g->view, n, g->counter, s->cell_next, s->rank_next, spa)
             if (local) { if (mode == 3) CWA_FIN_INT(true, 3); else if (mode == 2) CWA_FIN_INT(true, 2); else if (mode == 1) CWA_FIN_INT(true, 1); else CWA_FIN_INT(true, 0); }
