@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(256)
 grid_hash_count_kernel(const char* __restrict__ particles, int stride_bytes, int n, const int* __restrict__ n_dev, GridView g,
                        int* __restrict__ counter, int* __restrict__ cell_of, int* __restrict__ rank)
 {
+    cwa_pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (n_dev != nullptr) n = min(n, __ldg(n_dev));     // device-resident particle count (slab decomposition): `n` is only the launch bound
     int cell = -1;
@@ -298,6 +299,7 @@ __global__ void __launch_bounds__(256)
 grid_insert_kernel(const int* __restrict__ cell_of, const int* __restrict__ rank, const int* __restrict__ offset,
                    int n, const int* __restrict__ n_dev, int* __restrict__ arrival)
 {
+    cwa_pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (n_dev != nullptr) n = min(n, __ldg(n_dev));
     if (i >= n) return;
@@ -314,6 +316,7 @@ __global__ void __launch_bounds__(256)
 grid_cell_order_kernel(const int* __restrict__ cell_of, const int* __restrict__ offset, const int* __restrict__ arrival,
                        int n, const int* __restrict__ n_dev, int* __restrict__ index_list)
 {
+    cwa_pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (n_dev != nullptr) n = min(n, __ldg(n_dev));
     if (i >= n) return;
@@ -374,7 +377,7 @@ int grid_build_internal(cwa_ctx* ctx, GridObj* g, const void* particles, int str
         if (n > 0) {
             KScope k(ctx, KID_HASH_COUNT);
             if (g->dim == 2)
-                grid_hash_count_kernel<2><<<ceil_div(n, 256), 256, 0, ctx->stream>>>((const char*)particles, stride_bytes, n, opts.n_dev, g->view, g->counter, g->cell_of, g->rank);
+                cwa_launch(ctx, PDL_GRID2, grid_hash_count_kernel<2>, dim3(ceil_div(n, 256)), dim3(256), 0, (const char*)particles, stride_bytes, n, opts.n_dev, g->view, g->counter, g->cell_of, g->rank);
             else
                 grid_hash_count_kernel<3><<<ceil_div(n, 256), 256, 0, ctx->stream>>>((const char*)particles, stride_bytes, n, opts.n_dev, g->view, g->counter, g->cell_of, g->rank);
             CWA_CUDA(cudaGetLastError());
@@ -403,11 +406,11 @@ int grid_build_internal(cwa_ctx* ctx, GridObj* g, const void* particles, int str
                                                                                                           g->cell_of, g->rank, g->offset, g->arrival);
           }
           else
-              grid_insert_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(g->cell_of, g->rank, g->offset, n, opts.n_dev, g->arrival); }
+              cwa_launch(ctx, g->dim == 2 ? PDL_GRID2 : 0, grid_insert_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, g->cell_of, g->rank, g->offset, n, opts.n_dev, g->arrival); }
         CWA_CUDA(cudaGetLastError());
         if (opts.canonical_order) {
             KScope k(ctx, KID_CELL_ORDER);
-            grid_cell_order_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(g->cell_of, g->offset, g->arrival, n, opts.n_dev, g->index_list);
+            cwa_launch(ctx, g->dim == 2 ? PDL_GRID2 : 0, grid_cell_order_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, g->cell_of, g->offset, g->arrival, n, opts.n_dev, g->index_list);
         }
         CWA_CUDA(cudaGetLastError());
     }

@@ -435,12 +435,13 @@ __device__ __forceinline__ void cwa_pdl_enter()
 }
 
 // the kernels of the chain, as bits of the tuning value `pdl` (which launches carry the attribute)
-enum { PDL_SCAN = 1, PDL_INSERT = 2, PDL_REORDER = 4, PDL_DENSITY = 8, PDL_DENSITY_HEAVY = 16, PDL_FORCE = 32, PDL_FORCE_HEAVY = 64, PDL_INTEGRATE = 128 };
-#define CWA_PDL_DEFAULT (255 & ~(PDL_INSERT | PDL_REORDER))   // measured (profiles/r2/tuning.md): those two cost more than they gain
+enum { PDL_SCAN = 1, PDL_INSERT = 2, PDL_REORDER = 4, PDL_DENSITY = 8, PDL_DENSITY_HEAVY = 16, PDL_FORCE = 32, PDL_FORCE_HEAVY = 64, PDL_INTEGRATE = 128,
+       PDL_GRID2 = 256 /* the 2-D frame (SphUgrid): hash, insert, cell order, reorder, density, forces */ };
+#define CWA_PDL_DEFAULT (511 & ~(PDL_INSERT | PDL_REORDER))   // measured (profiles/r2/tuning.md): those two cost more than they gain
 static inline bool cwa_pdl_enabled(cwa_ctx* c, int bit)
 {
-    if (c->tune.pdl < 0) { const char* e = getenv("CWA_PDL"); c->tune.pdl = (e && *e) ? (atoi(e) & 255) : CWA_PDL_DEFAULT; }
-    return (c->tune.pdl & bit) != 0 && !c->profiling;      // (a profile brackets every launch with events: nothing to overlap)
+    if (c->tune.pdl < 0) { const char* e = getenv("CWA_PDL"); c->tune.pdl = (e && *e) ? (atoi(e) & 511) : CWA_PDL_DEFAULT; }
+    return bit != 0 && (c->tune.pdl & bit) != 0 && !c->profiling;      // (a profile brackets every launch with events: nothing to overlap)
 }
 
 // <<<grid, block, smem, ctx->stream>>> with the programmatic-serialization attribute; the kernel must begin with cwa_pdl_enter()

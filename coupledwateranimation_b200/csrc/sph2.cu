@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(256)
 sph2_reorder_kernel(const float4* __restrict__ aos, const int* __restrict__ index_list, const int* __restrict__ offset,
                     int num_cells, float4* __restrict__ posS, float4* __restrict__ velS, float4* __restrict__ accS)
 {
+    cwa_pdl_enter();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int m = __ldg(offset + num_cells);              // number of inserted particles
     const int s = t / 3, q = t - 3 * s;
@@ -170,6 +171,7 @@ sph2_density_kernel(const float4* __restrict__ in, float4* __restrict__ out, int
                     const int* __restrict__ offset, const int* __restrict__ index_list, const int* __restrict__ cell_of,
                     const float4* __restrict__ posS, Sph2Params prm, int tail)
 {
+    cwa_pdl_enter();
     using namespace k2d;
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
     const int t = gt / S2_LANES, sub = gt % S2_LANES;
@@ -231,6 +233,7 @@ sph2_forces_kernel(const float4* __restrict__ in, float4* __restrict__ out, int 
                    const float4* __restrict__ posS, const float4* __restrict__ velS, const float4* __restrict__ accS,
                    Sph2Params prm, int tail)
 {
+    cwa_pdl_enter();
     using namespace k2d;
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
     const int t = gt / S2_LANES, sub = gt % S2_LANES;
@@ -423,10 +426,10 @@ static int sph2_frame(cwa_ctx* ctx, Sph2Obj* s, GridObj* g, const Sph2Params& pr
         float4* wr = (float4*)get_buffer(ctx, s->buffer[s->write_index])->ptr;
         CWA_TRY(grid_build_internal(ctx, g, rd, 48, n));                 // mGrid.CollisionQuery() :163-164
         { KScope k(ctx, KID_REORDER);
-          sph2_reorder_kernel<<<ceil_div((long long)n * 3, 256), 256, 0, ctx->stream>>>(rd, g->index_list, g->offset, g->view.num_cells, s->posS, s->velS, s->accS); }
+          cwa_launch(ctx, PDL_GRID2, sph2_reorder_kernel, dim3(ceil_div((long long)n * 3, 256)), dim3(256), 0, rd, g->index_list, g->offset, g->view.num_cells, s->posS, s->velS, s->accS); }
         for (int tail = 0; tail < 2; tail++) {                           // mode 1 :169-176
             KScope k(ctx, KID_DENSITY);
-#define CWA_S2_DENS(L) sph2_density_kernel<L><<<blocks, 128, 0, ctx->stream>>>(rd, wr, n, g->view, g->offset, g->index_list, g->cell_of, s->posS, prm, tail)
+#define CWA_S2_DENS(L) cwa_launch(ctx, PDL_GRID2, sph2_density_kernel<L>, dim3(blocks), dim3(128), 0, rd, wr, n, g->view, g->offset, g->index_list, g->cell_of, s->posS, prm, tail)
             if (lanes == 4) CWA_S2_DENS(4); else if (lanes == 16) CWA_S2_DENS(16); else if (lanes == 32) CWA_S2_DENS(32); else CWA_S2_DENS(8);
 #undef CWA_S2_DENS
         }
@@ -435,10 +438,10 @@ static int sph2_frame(cwa_ctx* ctx, Sph2Obj* s, GridObj* g, const Sph2Params& pr
         wr = (float4*)get_buffer(ctx, s->buffer[s->write_index])->ptr;
         // mode 2 reads the density output through the SAME (now stale) grid lists
         { KScope k(ctx, KID_REORDER);
-          sph2_reorder_kernel<<<ceil_div((long long)n * 3, 256), 256, 0, ctx->stream>>>(rd, g->index_list, g->offset, g->view.num_cells, s->posS, s->velS, s->accS); }
+          cwa_launch(ctx, PDL_GRID2, sph2_reorder_kernel, dim3(ceil_div((long long)n * 3, 256)), dim3(256), 0, rd, g->index_list, g->offset, g->view.num_cells, s->posS, s->velS, s->accS); }
         for (int tail = 0; tail < 2; tail++) {
             KScope k(ctx, KID_FORCE);
-#define CWA_S2_FORCE(L) sph2_forces_kernel<L><<<blocks, 128, 0, ctx->stream>>>(rd, wr, n, g->view, g->offset, g->index_list, g->cell_of, s->posS, s->velS, s->accS, prm, tail)
+#define CWA_S2_FORCE(L) cwa_launch(ctx, PDL_GRID2, sph2_forces_kernel<L>, dim3(blocks), dim3(128), 0, rd, wr, n, g->view, g->offset, g->index_list, g->cell_of, s->posS, s->velS, s->accS, prm, tail)
             if (lanes == 4) CWA_S2_FORCE(4); else if (lanes == 16) CWA_S2_FORCE(16); else if (lanes == 32) CWA_S2_FORCE(32); else CWA_S2_FORCE(8);
 #undef CWA_S2_FORCE
         }

@@ -1867,7 +1867,7 @@ extern "C" int cwa_set_tuning(cwa_ctx* ctx, const char* key, int value)
     else if (k == "fused_integrate") { ctx->tune.fused_integrate = value ? 1 : 0; }
     else if (k == "nbr_k") { CWA_CHECK(value >= 8 && value <= NBR_K_MAX && value % 4 == 0, "nbr_k %d: multiple of 4 in [8, %d]", value, NBR_K_MAX); ctx->tune.nbr_k = value; }
     else if (k == "heavy_sub_warp") { ctx->tune.heavy8 = value ? 1 : 0; }
-    else if (k == "pdl") { ctx->tune.pdl = value & 255; }
+    else if (k == "pdl") { ctx->tune.pdl = value & 511; }
     else if (k == "slab_ahead") { ctx->tune.slab_ahead = value ? 1 : 0; }
     else if (k == "allpairs_balanced") { CWA_CHECK(value >= 0 && value <= 2, "allpairs_balanced %d: 0 off, 1 density pass, 2 both passes", value); ctx->tune.allpairs_bal = value; }
     else if (k == "inplace_max") { CWA_CHECK(value >= 0, "inplace_max %d negative", value); ctx->tune.inplace_max = value; }
