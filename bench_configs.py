@@ -66,7 +66,7 @@ def run_D(cwa, ctx, torch, K, W, peak, peak_src, brief=False, oracle=None):
     tf = flops.get(dom["kernel"], 0.0) / (dom["avg_us"] * 1e-6) / 1e12
     roofline = {"kernel": dom["kernel"], "bound": "fp32 (non-tensor; no pass is a dense contraction)", "achieved": tf, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
                 "frac": tf / FP32_PEAK_TFLOPS, "traffic": None, "peak_source": "148 SMs x 128 lanes x 2 x 1.965 GHz (nominal; MEASURED_PEAKS.json holds no FP32 figure)",
-                "note": f"{n}^2 pair tests per pass at ~{flops.get(dom['kernel'], 0) / n / n:.0f} flop each (SURVEY 8d); the frame is 6 launches, replayed as one CUDA graph"}
+                "note": f"{n}^2 pair tests per pass at ~{flops.get(dom['kernel'], 0) / n / n:.0f} flop each (SURVEY 8d) -- EFFECTIVE rate: candidate tiles whose bounding box is farther than h from a CTA's targets are skipped, exactly (tuning allpairs_cull); the frame is 7 launches, replayed as one CUDA graph"}
     # end to end: particles + the two wave levels the stencil reads go up, one frame, particles + the new level come back
     lib, h = ctx.lib, ctx.h
     pp = _pin(torch, n * 64); hp = pp.numpy().view(cwa.PARTICLE)

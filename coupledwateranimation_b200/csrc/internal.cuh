@@ -157,6 +157,7 @@ struct SphObj {
     size_t  xyz_stride = 0;
     float4 *pack = nullptr;                      // per slot two float4: (pos.xyz, p) at 2s and (vel.xyz, rho) at 2s+1 -- one 32-byte sector
     float4 *scratch = nullptr;                   // all-pairs mode: pass results before they are committed to the SSBO
+    float4 *boxes = nullptr;                     // all-pairs mode: bounding boxes of every 512 consecutive particles (inside the scratch allocation)
     float4 *pairP = nullptr;                     // neighbour sums of the force pass: (pres.xyz, visc.x)
     float2 *pairV = nullptr;                     //                                   (visc.y, visc.z)
     int   *nbr_list = nullptr, *nbr_count = nullptr;   // neighbour lists of the density pass ([slot][K]) and true counts
@@ -249,7 +250,7 @@ struct ProfRec { int id; cudaEvent_t a, b; };
 // hold different settings.  -1 = not set yet: the default comes from the environment (CWA_NB_CONFIG, ...) on first use.
 struct CtxTuning {
     int config = -1, cap_d = -1, cap_f = -1, fused_order = -1, fused_integrate = -1, pipeline = -1, nbr_k = -1, extreme = -1;
-    int scan_config = -1, wave_transpose = -1, graph = -1, inplace_max = -1, allpairs_bal = -1, slab_ahead = -1, heavy8 = -1, pdl = -1;
+    int scan_config = -1, wave_transpose = -1, graph = -1, inplace_max = -1, allpairs_bal = -1, slab_ahead = -1, heavy8 = -1, pdl = -1, ap_cull = -1;
 };
 
 struct SlabObj;

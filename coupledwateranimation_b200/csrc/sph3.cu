@@ -1604,13 +1604,121 @@ constexpr int APB_TILE = 512;         // candidates per tile, force pass: at mos
 constexpr int APB_TD = 4;             // targets per thread, density pass
 constexpr int APB_TF = 2;             // targets per thread, force pass
 
+// Tile boxes.  Both passes cut the candidates into tiles of consecutive particles, and consecutive particles of the shipped scene are
+// neighbours in space (a lattice in id order that deforms slowly), as are a CTA's ~138 consecutive targets: most (CTA, tile) combinations cannot
+// hold a pair within h.  A small kernel computes the bounding box of every APB_BOX particles (NaN coordinates left out: they are never accepted);
+// a CTA skips -- without loading it -- every tile whose box is farther than h from the box of its own targets, and a thread skips the tiles
+// farther than h from each of its T targets.  Exact: a skipped tile holds no accepted pair (margin 1 % on h^2, a thousand times the rounding
+// of the distance), so sums and summation order are those of the unculled kernels; in the worst case (fully mixed particles) nothing is
+// skipped and the cost is the box tests.
+constexpr int APB_BOX = 512;          // particles per box; both tile sizes are multiples
+__global__ void __launch_bounds__(128)
+sph3_allpairs_boxes_kernel(const float4* __restrict__ aos, int n, float4* __restrict__ boxes)
+{
+    __shared__ float red[6][4];
+    const int tid = threadIdx.x;
+    float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+    for (int q = tid; q < APB_BOX; q += 128) {
+        const int j = blockIdx.x * APB_BOX + q;
+        if (j < n) {
+            const float4 p = aos[(size_t)j * 4];
+            lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);      // fminf / fmaxf drop a NaN operand
+            hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], d));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], d));
+        }
+    if ((tid & 31) == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) { red[a][tid >> 5] = lo[a]; red[3 + a][tid >> 5] = hi[a]; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+            for (int w = 1; w < 4; w++) { lo[a] = fminf(lo[a], red[a][w]); hi[a] = fmaxf(hi[a], red[3 + a][w]); }
+        boxes[2 * blockIdx.x] = make_float4(lo[0], lo[1], lo[2], 0.f);
+        boxes[2 * blockIdx.x + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
+    }
+}
+
+struct Box3 { float lo[3], hi[3]; };
+// box of the particles [j0, j0 + count) from the APB_BOX-granular boxes (count a multiple of APB_BOX)
+__device__ __forceinline__ Box3 apb_tile_box(const float4* __restrict__ boxes, int j0, int count, int n)
+{
+    Box3 b;
+#pragma unroll
+    for (int a = 0; a < 3; a++) { b.lo[a] = CUDART_INF_F; b.hi[a] = -CUDART_INF_F; }
+    for (int t = j0 / APB_BOX; t < (j0 + count) / APB_BOX && t * APB_BOX < n; t++) {
+        const float4 l = __ldg(boxes + 2 * t), h = __ldg(boxes + 2 * t + 1);
+        b.lo[0] = fminf(b.lo[0], l.x); b.lo[1] = fminf(b.lo[1], l.y); b.lo[2] = fminf(b.lo[2], l.z);
+        b.hi[0] = fmaxf(b.hi[0], h.x); b.hi[1] = fmaxf(b.hi[1], h.y); b.hi[2] = fmaxf(b.hi[2], h.z);
+    }
+    return b;
+}
+// squared distance between two boxes / a point and a box; anything NaN compares false below: not skipped
+__device__ __forceinline__ float apb_box_box_d2(const Box3& a, const Box3& b)
+{
+    float d2 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { const float d = fmaxf(fmaxf(a.lo[k] - b.hi[k], b.lo[k] - a.hi[k]), 0.0f); d2 = fmaf(d, d, d2); }
+    return d2;
+}
+__device__ __forceinline__ float apb_point_box_d2(float x, float y, float z, const Box3& b)
+{
+    const float p[3] = {x, y, z};
+    float d2 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { const float d = fmaxf(fmaxf(b.lo[k] - p[k], p[k] - b.hi[k]), 0.0f); d2 = fmaf(d, d, d2); }
+    return d2;
+}
+// box of the CTA's own targets [t_first, t_end): every thread gets the same six numbers (one block reduction at kernel start)
+__device__ __forceinline__ Box3 apb_cta_box(const float4* __restrict__ aos, int t_first, int t_end, float (*red)[32])
+{
+    const int tid = threadIdx.x;
+    float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+    for (int t = t_first + tid; t < t_end; t += blockDim.x) {
+        const float4 p = aos[(size_t)t * 4];
+        lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
+        hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], d));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], d));
+        }
+    if ((tid & 31) == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) { red[a][tid >> 5] = lo[a]; red[3 + a][tid >> 5] = hi[a]; }
+    }
+    __syncthreads();
+    Box3 b;
+    const int nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        float l = CUDART_INF_F, h = -CUDART_INF_F;
+        for (int w = 0; w < nw; w++) { l = fminf(l, red[a][w]); h = fmaxf(h, red[3 + a][w]); }
+        b.lo[a] = l; b.hi[a] = h;
+    }
+    __syncthreads();
+    return b;
+}
+
 template <int T>
 __global__ void __launch_bounds__(APB_THREADS)
 sph3_density_allpairs_bal_kernel(const float4* __restrict__ aos, int n, int tpc, int L, const Sph3Const* __restrict__ cc, TexView tex,
-                                 float2* __restrict__ out_rp)
+                                 float2* __restrict__ out_rp, const float4* __restrict__ boxes)
 {
     __shared__ float4 tile[APB_TILE_D];
     __shared__ float part[T][APB_THREADS];
+    __shared__ float red[6][32];
     const int tid = threadIdx.x;
     const int grp = tid / L, sub = tid - grp * L;
     const int t0 = blockIdx.x * tpc + grp * T;                    // first target of the thread's group
@@ -1624,13 +1732,26 @@ sph3_density_allpairs_bal_kernel(const float4* __restrict__ aos, int n, int tpc,
         const float4 p = on ? aos[(size_t)(t0 + k) * 4] : make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f);   // parked: every test fails
         px[k] = p.x; py[k] = p.y; pz[k] = p.z; rho[k] = 0.0f;
     }
+    const float cull_r2 = h2 * 1.01f;
+    const bool cull = boxes != nullptr;
+    Box3 mine;
+    if (cull) mine = apb_cta_box(aos, blockIdx.x * tpc, t_end, red);
     for (int j0 = 0; j0 < n; j0 += APB_TILE_D) {
+        bool near = active;
+        if (cull) {
+            const Box3 tb = apb_tile_box(boxes, j0, APB_TILE_D, n);
+            if (apb_box_box_d2(mine, tb) > cull_r2) continue;                 // uniform over the CTA: no load, no barrier
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < T; k++) any = any || !(apb_point_box_d2(px[k], py[k], pz[k], tb) > cull_r2);
+            near = active && any;
+        }
         if (tid < APB_TILE_D) {
             const int j = j0 + tid;
             tile[tid] = (j < n) ? aos[(size_t)j * 4] : make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, 0.f);
         }
         __syncthreads();
-        if (active) {
+        if (near) {
 #pragma unroll 2
             for (int q = sub; q < APB_TILE_D; q += L) {
                 const float4 c = tile[q];
@@ -1660,11 +1781,11 @@ sph3_density_allpairs_bal_kernel(const float4* __restrict__ aos, int n, int tpc,
 template <int T>
 __global__ void __launch_bounds__(APB_THREADS)
 sph3_force_allpairs_bal_kernel(const float4* __restrict__ aos, int n, int tpc, int L, const Sph3Const* __restrict__ cc, TexView tex,
-                               float4* __restrict__ out_force)
+                               float4* __restrict__ out_force, const float4* __restrict__ boxes)
 {
     __shared__ float4 tileA[APB_TILE];
     __shared__ float4 tileB[APB_TILE];
-    __shared__ float part[6][APB_THREADS];             // reused for each of the thread's T targets
+    __shared__ float part[6][APB_THREADS];             // reused for each of the thread's T targets; first the CTA's box reduction
     const int tid = threadIdx.x;
     const int grp = tid / L, sub = tid - grp * L;
     const int t0 = blockIdx.x * tpc + grp * T;
@@ -1682,7 +1803,20 @@ sph3_force_allpairs_bal_kernel(const float4* __restrict__ aos, int n, int tpc, i
         for (int a = 0; a < 6; a++) acc[k][a] = 0.f;
     }
     const int per_lane = (APB_TILE + L - 1) / L;       // <= 64: the launcher keeps L >= 8
+    const float cull_r2 = c.h2 * 1.01f;
+    const bool cull = boxes != nullptr;
+    Box3 mine;
+    if (cull) mine = apb_cta_box(aos, blockIdx.x * tpc, t_end, reinterpret_cast<float (*)[32]>(&part[0][0]));
     for (int j0 = 0; j0 < n; j0 += APB_TILE) {
+        bool near = active;
+        if (cull) {
+            const Box3 tb = apb_tile_box(boxes, j0, APB_TILE, n);
+            if (apb_box_box_d2(mine, tb) > cull_r2) continue;                 // uniform over the CTA: no load, no barrier
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < T; k++) any = any || !(apb_point_box_d2(p[k].x, p[k].y, p[k].z, tb) > cull_r2);
+            near = active && any;
+        }
         if (tid < APB_TILE) {
             const int j = j0 + tid;
             if (j < n) {
@@ -1695,7 +1829,7 @@ sph3_force_allpairs_bal_kernel(const float4* __restrict__ aos, int n, int tpc, i
             }
         }
         __syncthreads();
-        if (active) {
+        if (near) {
             // two phases: mark the accepted candidates of the lane for each of its targets (cheap, every candidate, one shared-memory read
             // for all T of them), then evaluate only those
             unsigned long long mask[T];
@@ -1852,6 +1986,7 @@ static int nbr_k(cwa_ctx* c) { if (c->tune.nbr_k < 0) c->tune.nbr_k = env_int("C
 static int extreme_candidates(cwa_ctx* c) { if (c->tune.extreme < 0) c->tune.extreme = env_int("CWA_EXTREME", EXTREME_CANDIDATES, 16, 1 << 20); return c->tune.extreme; }
 static int inplace_max(cwa_ctx* c) { if (c->tune.inplace_max < 0) c->tune.inplace_max = env_int("CWA_INPLACE_MAX", INPLACE_MAX, 0, 1 << 20); return c->tune.inplace_max; }
 static int allpairs_balanced(cwa_ctx* c) { if (c->tune.allpairs_bal < 0) c->tune.allpairs_bal = env_int("CWA_ALLPAIRS_BALANCED", 2, 0, 2); return c->tune.allpairs_bal; }
+static bool allpairs_cull(cwa_ctx* c) { if (c->tune.ap_cull < 0) c->tune.ap_cull = env_int("CWA_ALLPAIRS_CULL", 1, 0, 1); return c->tune.ap_cull != 0; }
 static bool heavy_sub_warp(cwa_ctx* c) { if (c->tune.heavy8 < 0) c->tune.heavy8 = env_int("CWA_HEAVY8", 1, 0, 1); return c->tune.heavy8 != 0; }
 static bool fused_order(cwa_ctx* c) { if (c->tune.fused_order < 0) c->tune.fused_order = env_int("CWA_FUSED_ORDER", 1, 0, 1); return c->tune.fused_order != 0; }
 
@@ -1867,6 +2002,7 @@ extern "C" int cwa_set_tuning(cwa_ctx* ctx, const char* key, int value)
     else if (k == "fused_integrate") { ctx->tune.fused_integrate = value ? 1 : 0; }
     else if (k == "nbr_k") { CWA_CHECK(value >= 8 && value <= NBR_K_MAX && value % 4 == 0, "nbr_k %d: multiple of 4 in [8, %d]", value, NBR_K_MAX); ctx->tune.nbr_k = value; }
     else if (k == "heavy_sub_warp") { ctx->tune.heavy8 = value ? 1 : 0; }
+    else if (k == "allpairs_cull") { ctx->tune.ap_cull = value ? 1 : 0; }
     else if (k == "pdl") { ctx->tune.pdl = value & 511; }
     else if (k == "slab_ahead") { ctx->tune.slab_ahead = value ? 1 : 0; }
     else if (k == "allpairs_balanced") { CWA_CHECK(value >= 0 && value <= 2, "allpairs_balanced %d: 0 off, 1 density pass, 2 both passes", value); ctx->tune.allpairs_bal = value; }
@@ -2066,16 +2202,21 @@ int sph_passes_internal(cwa_ctx* ctx, SphObj* s, TexView tex, int which, bool co
         const int lanes_d = lanes_for(APB_TD), lanes_f = lanes_for(APB_TF);
         const bool balanced = tpc > 0 && lanes_d >= 4 && lanes_f >= 8 && allpairs_balanced(ctx) != 0;
         const int bal_blocks = balanced ? ceil_div(n, tpc) : 0;
+        const bool cull = balanced && allpairs_cull(ctx);             // tile boxes (exact culling of far tiles)
         if (which & 1) {
+            if (cull) { KScope k(ctx, KID_OTHER); sph3_allpairs_boxes_kernel<<<ceil_div(n, APB_BOX), 128, 0, ctx->stream>>>(aos, n, s->boxes); }
             { KScope k(ctx, KID_DENSITY);
-              if (balanced) sph3_density_allpairs_bal_kernel<APB_TD><<<bal_blocks, APB_THREADS, 0, ctx->stream>>>(aos, n, tpc, lanes_d, cc, tex, sph_scratch_rp(s));
+              if (balanced) sph3_density_allpairs_bal_kernel<APB_TD><<<bal_blocks, APB_THREADS, 0, ctx->stream>>>(aos, n, tpc, lanes_d, cc, tex, sph_scratch_rp(s), cull ? s->boxes : nullptr);
               else sph3_density_allpairs_kernel<<<blocks, AP_TT * AP_L, 0, ctx->stream>>>(aos, n, cc, tex, sph_scratch_rp(s)); }
             { KScope k(ctx, KID_OTHER);
               sph3_commit_rho_pres_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(sph_scratch_rp(s), n, aos); }
         }
         if (which & 2) {
+            const bool bal_force = balanced && ctx->tune.allpairs_bal == 2;
+            if (cull && bal_force && !(which & 1)) {                 // (the pass dispatched alone: the boxes of the density pass are not there)
+                KScope k(ctx, KID_OTHER); sph3_allpairs_boxes_kernel<<<ceil_div(n, APB_BOX), 128, 0, ctx->stream>>>(aos, n, s->boxes); }
             { KScope k(ctx, KID_FORCE);
-              if (balanced && ctx->tune.allpairs_bal == 2) sph3_force_allpairs_bal_kernel<APB_TF><<<bal_blocks, APB_THREADS, 0, ctx->stream>>>(aos, n, tpc, lanes_f, cc, tex, sph_scratch_force(s));
+              if (bal_force) sph3_force_allpairs_bal_kernel<APB_TF><<<bal_blocks, APB_THREADS, 0, ctx->stream>>>(aos, n, tpc, lanes_f, cc, tex, sph_scratch_force(s), cull ? s->boxes : nullptr);
               else sph3_force_allpairs_kernel<<<blocks, AP_TT * AP_L, 0, ctx->stream>>>(aos, n, cc, tex, sph_scratch_force(s)); }
             { KScope k(ctx, KID_OTHER);
               sph3_commit_force_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(sph_scratch_force(s), n, aos); }
@@ -2188,7 +2329,11 @@ extern "C" int cwa_sph_create(cwa_ctx* ctx, cwa_buf particles, int n, cwa_grid g
     const size_t bytes = (size_t)(n > 0 ? n : 1) * 16 + 64;          // + 4 slots: the neighbour loops read up to 3 slots past a row
     CWA_CUDA(cudaMalloc(&s.consts, sizeof(Sph3Const)));
     if (grid >= 0) CWA_CUDA(cudaMalloc(&s.pack, 2 * bytes));
-    else CWA_CUDA(cudaMalloc(&s.scratch, bytes));
+    else {                                                        // pass results + the tile boxes of the all-pairs kernels
+        const size_t box_off = (bytes + 31) / 32 * 32;
+        CWA_CUDA(cudaMalloc(&s.scratch, box_off + ((size_t)(n > 0 ? n : 1) + APB_BOX - 1) / APB_BOX * 32));
+        s.boxes = reinterpret_cast<float4*>(reinterpret_cast<char*>(s.scratch) + box_off);
+    }
     if (grid >= 0) {
         CWA_CUDA(cudaMalloc(&s.posS, bytes));
         CWA_CUDA(cudaMemsetAsync(s.posS, 0, bytes, ctx->stream));     // the 4 pad slots are read (and masked out) by the neighbour loops

@@ -107,6 +107,34 @@ def test_allpairs_kernel_variants(cwa, ctx, oracle, mode):
         ctx.set_tuning(allpairs_balanced=1)
 
 
+@pytest.mark.parametrize("order", ["lattice", "shuffled"])
+def test_allpairs_tile_culling_changes_nothing(cwa, ctx, oracle, order):
+    """The balanced all-pairs kernels skip candidate tiles whose bounding box is farther than h from the CTA's targets (sph3_allpairs_boxes_kernel).
+    A skipped tile holds no accepted pair, so every sum has the same terms in the same order: bit-identical records after several frames, with
+    the particles in lattice order (most tiles skipped) and shuffled (nearly none), NaN and far-away particles included."""
+    def run(cull):
+        ctx.set_tuning(allpairs_balanced=2, allpairs_cull=cull)
+        prm, p, tex, sph, wave = _scene(cwa, ctx, oracle, False, vel=5.0)
+        if order == "shuffled":
+            p = p[np.random.default_rng(5).permutation(p.size)]
+        p["pos"][3, 0] = np.nan; p["pos"][700, :3] = np.nan
+        p["pos"][1500, :3] = (40.0, 3.0, -25.0)                   # far outside everything: stretches its tile's box
+        sph.upload(p)
+        sph.step(3)
+        a = sph.download()
+        sph.rho_pres(); sph.force()                               # the passes dispatched alone take the boxes too
+        return a, sph.download()
+    try:
+        a0, b0 = run(0)
+        a1, b1 = run(1)
+        for f in ("pos", "vel", "force", "extras"):
+            assert a0[f].tobytes() == a1[f].tobytes(), f
+            assert b0[f].tobytes() == b1[f].tobytes(), f
+        assert np.isfinite(a1["pos"][:, :3]).sum() > 0.9 * a1["pos"][:, :3].size
+    finally:
+        ctx.set_tuning(allpairs_balanced=1, allpairs_cull=1)
+
+
 @pytest.mark.parametrize("use_grid", [False, True])
 def test_integrate_pass_and_branch_decisions(cwa, ctx, oracle, use_grid):
     prm, p, tex, sph, wave = _scene(cwa, ctx, oracle, use_grid, vel=40.0)      # some |v| > 25: foam rule fires
