@@ -1599,8 +1599,17 @@ sph3_force_allpairs_kernel(const float4* __restrict__ aos, int n, const Sph3Cons
 // it reads against T targets held in registers, and L lanes share a group of T targets (L need not be a power of two: the partial sums
 // meet in shared memory, fixed order).  The density accumulation is branch-free (weight 0 when rejected).
 constexpr int APB_THREADS = 1024;
-constexpr int APB_TILE_D = 1024;      // candidates per tile, density pass (a barrier pair per tile: few, long tiles)
-constexpr int APB_TILE = 512;         // candidates per tile, force pass: at most 64 per lane (its accept mask) for L >= 8
+#ifndef CWA_APB_TILE_D
+#define CWA_APB_TILE_D 1024
+#endif
+#ifndef CWA_APB_TILE
+#define CWA_APB_TILE 512
+#endif
+#ifndef CWA_APB_BOX
+#define CWA_APB_BOX 512
+#endif
+constexpr int APB_TILE_D = CWA_APB_TILE_D;      // candidates per tile, density pass (a barrier pair per tile: few, long tiles)
+constexpr int APB_TILE = CWA_APB_TILE;         // candidates per tile, force pass: at most 64 per lane (its accept mask) for L >= 8
 constexpr int APB_TD = 4;             // targets per thread, density pass
 constexpr int APB_TF = 2;             // targets per thread, force pass
 
@@ -1611,7 +1620,7 @@ constexpr int APB_TF = 2;             // targets per thread, force pass
 // farther than h from each of its T targets.  Exact: a skipped tile holds no accepted pair (margin 1 % on h^2, a thousand times the rounding
 // of the distance), so sums and summation order are those of the unculled kernels; in the worst case (fully mixed particles) nothing is
 // skipped and the cost is the box tests.
-constexpr int APB_BOX = 512;          // particles per box; both tile sizes are multiples
+constexpr int APB_BOX = CWA_APB_BOX;          // particles per box; both tile sizes are multiples
 __global__ void __launch_bounds__(128)
 sph3_allpairs_boxes_kernel(const float4* __restrict__ aos, int n, float4* __restrict__ boxes)
 {
