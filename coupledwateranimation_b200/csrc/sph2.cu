@@ -147,6 +147,29 @@ sph2_reorder_kernel(const float4* __restrict__ aos, const int* __restrict__ inde
     if (q == 0) posS[s] = v; else if (q == 1) velS[s] = v; else accS[s] = v;
 }
 
+// Canonical order + gather in one pass, as sph3_order_reorder_kernel does for the 3-D frame (thread per arrival slot): the particle that
+// arrived at slot s is ranked among its cell peers by counting the smaller ids (ascending id inside a cell == the CPU twin), its id goes
+// to index_list[rank slot] and its 48-byte record into the cell-ordered arrays; the record loads are issued before the rank chain.
+__global__ void __launch_bounds__(256)
+sph2_order_reorder_kernel(const float4* __restrict__ aos, const int* __restrict__ arrival, const int* __restrict__ cell_of,
+                          const int* __restrict__ offset, int num_cells, int* __restrict__ index_list,
+                          float4* __restrict__ posS, float4* __restrict__ velS, float4* __restrict__ accS)
+{
+    cwa_pdl_enter();
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= __ldg(offset + num_cells)) return;           // inserted particles
+    const int id = __ldg(arrival + s);
+    const float4 r0 = __ldg(aos + (size_t)id * 3), r1 = __ldg(aos + (size_t)id * 3 + 1), r2 = __ldg(aos + (size_t)id * 3 + 2);
+    const int c = __ldg(cell_of + id);
+    const int b = __ldg(offset + c), e = __ldg(offset + c + 1);
+    int smaller = 0;
+#pragma unroll 4
+    for (int q = b; q < e; q++) smaller += (__ldg(arrival + q) < id) ? 1 : 0;
+    const int t = b + smaller;
+    index_list[t] = id;
+    posS[t] = r0; velS[t] = r1; accS[t] = r2;
+}
+
 // target enumeration shared by both passes: first the inserted particles in cell order, then the
 // particles the grid rejected (cell_of == -1) in a second launch over the original order.
 __device__ __forceinline__ bool sph2_target(int t, int n, int m, bool tail, const int* __restrict__ index_list,
@@ -169,11 +192,13 @@ template <int S2_LANES>
 __global__ void __launch_bounds__(128)
 sph2_density_kernel(const float4* __restrict__ in, float4* __restrict__ out, int n, GridView g,
                     const int* __restrict__ offset, const int* __restrict__ index_list, const int* __restrict__ cell_of,
-                    const float4* __restrict__ posS, Sph2Params prm, int tail)
+                    const float4* __restrict__ posS, Sph2Params prm, int main_blocks)
 {
     cwa_pdl_enter();
     using namespace k2d;
-    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    // one launch for both target lists: blocks [0, main_blocks) take the inserted particles in cell order, the rest the rejected ones
+    const int tail = (int)blockIdx.x >= main_blocks;
+    const int gt = (blockIdx.x - (tail ? main_blocks : 0)) * blockDim.x + threadIdx.x;
     const int t = gt / S2_LANES, sub = gt % S2_LANES;
     const int m = __ldg(offset + g.num_cells);
     int ix;
@@ -231,11 +256,12 @@ __global__ void __launch_bounds__(128)
 sph2_forces_kernel(const float4* __restrict__ in, float4* __restrict__ out, int n, GridView g,
                    const int* __restrict__ offset, const int* __restrict__ index_list, const int* __restrict__ cell_of,
                    const float4* __restrict__ posS, const float4* __restrict__ velS, const float4* __restrict__ accS,
-                   Sph2Params prm, int tail)
+                   Sph2Params prm, int main_blocks)
 {
     cwa_pdl_enter();
     using namespace k2d;
-    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int tail = (int)blockIdx.x >= main_blocks;
+    const int gt = (blockIdx.x - (tail ? main_blocks : 0)) * blockDim.x + threadIdx.x;
     const int t = gt / S2_LANES, sub = gt % S2_LANES;
     const int m = __ldg(offset + g.num_cells);
     int ix;
@@ -424,12 +450,14 @@ static int sph2_frame(cwa_ctx* ctx, Sph2Obj* s, GridObj* g, const Sph2Params& pr
     for (int sub = 0; sub < s->substeps; sub++) {
         const float4* rd = (const float4*)get_buffer(ctx, s->buffer[s->read_index])->ptr;
         float4* wr = (float4*)get_buffer(ctx, s->buffer[s->write_index])->ptr;
-        CWA_TRY(grid_build_internal(ctx, g, rd, 48, n));                 // mGrid.CollisionQuery() :163-164
-        { KScope k(ctx, KID_REORDER);
-          cwa_launch(ctx, PDL_GRID2, sph2_reorder_kernel, dim3(ceil_div((long long)n * 3, 256)), dim3(256), 0, rd, g->index_list, g->offset, g->view.num_cells, s->posS, s->velS, s->accS); }
-        for (int tail = 0; tail < 2; tail++) {                           // mode 1 :169-176
+        GridBuildOpts opts;
+        opts.canonical_order = false;                                    // ranked and gathered in one pass below
+        CWA_TRY(grid_build_internal(ctx, g, rd, 48, n, opts));           // mGrid.CollisionQuery() :163-164
+        if (n > 0) { KScope k(ctx, KID_REORDER);
+          cwa_launch(ctx, PDL_GRID2, sph2_order_reorder_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, rd, g->arrival, g->cell_of, g->offset, g->view.num_cells, g->index_list, s->posS, s->velS, s->accS); }
+        {                                                                // mode 1 :169-176 (inserted particles + the rejected ones: one launch)
             KScope k(ctx, KID_DENSITY);
-#define CWA_S2_DENS(L) cwa_launch(ctx, PDL_GRID2, sph2_density_kernel<L>, dim3(blocks), dim3(128), 0, rd, wr, n, g->view, g->offset, g->index_list, g->cell_of, s->posS, prm, tail)
+#define CWA_S2_DENS(L) cwa_launch(ctx, PDL_GRID2, sph2_density_kernel<L>, dim3(2 * blocks), dim3(128), 0, rd, wr, n, g->view, g->offset, g->index_list, g->cell_of, s->posS, prm, blocks)
             if (lanes == 4) CWA_S2_DENS(4); else if (lanes == 16) CWA_S2_DENS(16); else if (lanes == 32) CWA_S2_DENS(32); else CWA_S2_DENS(8);
 #undef CWA_S2_DENS
         }
@@ -439,9 +467,9 @@ static int sph2_frame(cwa_ctx* ctx, Sph2Obj* s, GridObj* g, const Sph2Params& pr
         // mode 2 reads the density output through the SAME (now stale) grid lists
         { KScope k(ctx, KID_REORDER);
           cwa_launch(ctx, PDL_GRID2, sph2_reorder_kernel, dim3(ceil_div((long long)n * 3, 256)), dim3(256), 0, rd, g->index_list, g->offset, g->view.num_cells, s->posS, s->velS, s->accS); }
-        for (int tail = 0; tail < 2; tail++) {
+        {
             KScope k(ctx, KID_FORCE);
-#define CWA_S2_FORCE(L) cwa_launch(ctx, PDL_GRID2, sph2_forces_kernel<L>, dim3(blocks), dim3(128), 0, rd, wr, n, g->view, g->offset, g->index_list, g->cell_of, s->posS, s->velS, s->accS, prm, tail)
+#define CWA_S2_FORCE(L) cwa_launch(ctx, PDL_GRID2, sph2_forces_kernel<L>, dim3(2 * blocks), dim3(128), 0, rd, wr, n, g->view, g->offset, g->index_list, g->cell_of, s->posS, s->velS, s->accS, prm, blocks)
             if (lanes == 4) CWA_S2_FORCE(4); else if (lanes == 16) CWA_S2_FORCE(16); else if (lanes == 32) CWA_S2_FORCE(32); else CWA_S2_FORCE(8);
 #undef CWA_S2_FORCE
         }
