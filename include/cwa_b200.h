@@ -96,7 +96,7 @@ CWA_API const char* cwa_profile_kernel_name(int id);
 CWA_API int  cwa_profile_begin(cwa_ctx* ctx);
 CWA_API int  cwa_profile_end(cwa_ctx* ctx, float* ms, int* launches, int cap);   /* synchronises */
 /* kernel-variant / staging knobs of the neighbour loops (no reference counterpart: the GLSL has one variant).
- * keys: "nb_config" (7: neighbour-list kernels, the default; 0..6: shared-memory-staged "lanes" kernels),
+ * keys: "nb_config" (8: row-mask kernels, the default; 7: neighbour-list kernels; 0..6: shared-memory-staged "lanes" kernels),
  *       "nb_cap_d", "nb_cap_f" (staged slots of the lanes kernels),
  *       "fused_order" (1: canonical ordering fused into the reorder pass),
  *       "fused_integrate" (1: in a full step the force kernels also run the epilogue + integrate; default 0:
@@ -109,7 +109,15 @@ CWA_API int  cwa_profile_end(cwa_ctx* ctx, float* ms, int* launches, int cap);  
  *       "nbr_k" (neighbour-list entries per target, multiple of 4 in [8, 256], default 64; set before the SPH object is used) and
  *       "extreme_candidates" (a target with more candidates is finished by a whole warp, default 192),
  *       "wave_transpose" (1, default: the SPH passes sample a transposed copy of the bound wave level -- the grid runs fastest along
- *       z = the texture's t axis -- rebuilt only when that level changed; same texels, bit-identical results). */
+ *       z = the texture's t axis -- rebuilt only when that level changed; same texels, bit-identical results),
+ *       "inplace_max" (a clump target with at most this many candidates is finished by its own thread in the density pass, default 640),
+ *       "heavy_sub_warp" (1, default: queued clump targets of the force pass get eight lanes each, four per warp, when the queue is longer
+ *       than the launch), "allpairs_balanced" (0: tiles of 64 targets; 1 / 2: one CTA per SM for the density pass / both passes, default 2),
+ *       "allpairs_cull" (1, default: the balanced all-pairs kernels skip candidate tiles whose bounding box is farther than h from the
+ *       CTA's targets; bit-identical results), "graph" (1, default: the all-pairs frame and the 2-D frame replay as one CUDA graph),
+ *       "slab_ahead" (1, default: count-ahead across the slab exchange) and
+ *       "pdl" (bit mask of the launches that carry the programmatic-dependent-launch attribute: 1 scan, 2 insert, 4 reorder, 8 density,
+ *       16 density of queued targets, 32 force, 64 force of queued targets, 128 integrate, 256 the 2-D frame; default all but 2 and 4). */
 CWA_API int  cwa_set_tuning(cwa_ctx* ctx, const char* key, int value);
 
 /* ---- Buffer: Init / BufferSubData / BindBufferBase / DebugRead*  (SphWave2D/Buffer.cpp:5-83) -- */
