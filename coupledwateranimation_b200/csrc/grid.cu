@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(256)
 grid_hash_count_kernel(const char* __restrict__ particles, int stride_bytes, int n, const int* __restrict__ n_dev, GridView g,
                        int* __restrict__ counter, int* __restrict__ cell_of, int* __restrict__ rank)
 {
-    cwa_pdl_enter();
+    CWA_PDL_ENTER();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (n_dev != nullptr) n = min(n, __ldg(n_dev));     // device-resident particle count (slab decomposition): `n` is only the launch bound
     int cell = -1;
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(THREADS)
 scan_lookback_kernel(const int* __restrict__ in, int* __restrict__ out, int n, int write_total,
                      int* __restrict__ ticket, volatile unsigned long long* __restrict__ tile_state)
 {
-    cwa_pdl_enter();
+    CWA_PDL_ENTER();
     constexpr int TILE = THREADS * ITEMS;
     constexpr int WARPS = THREADS / 32;
     constexpr int Q = ITEMS / 4;
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(256)
 grid_insert_kernel(const int* __restrict__ cell_of, const int* __restrict__ rank, const int* __restrict__ offset,
                    int n, const int* __restrict__ n_dev, int* __restrict__ arrival)
 {
-    cwa_pdl_enter();
+    CWA_PDL_ENTER();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (n_dev != nullptr) n = min(n, __ldg(n_dev));
     if (i >= n) return;
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(256)
 grid_cell_order_kernel(const int* __restrict__ cell_of, const int* __restrict__ offset, const int* __restrict__ arrival,
                        int n, const int* __restrict__ n_dev, int* __restrict__ index_list)
 {
-    cwa_pdl_enter();
+    CWA_PDL_ENTER();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (n_dev != nullptr) n = min(n, __ldg(n_dev));
     if (i >= n) return;
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(256)
 grid_insert_ahead_kernel(const int* __restrict__ cell_s, const int* __restrict__ rank_s, const int* __restrict__ old_index_list,
                          const int* __restrict__ offset, int n, int* __restrict__ cell_of, int* __restrict__ arrival, bool keep_vanished)
 {
-    cwa_pdl_enter();
+    CWA_PDL_ENTER();
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const int c = __ldg(cell_s + s);

@@ -425,15 +425,23 @@ struct KScope {
 #ifdef __CUDACC__
 
 // Programmatic dependent launch (sm_90+): the kernels of a frame run back to back on one stream, each a few tens of microseconds, and
-// every boundary costs the drain of the last wave plus the ramp-up of the next grid.  A kernel of the chain starts with cwa_pdl_enter():
+// every boundary costs the drain of the last wave plus the ramp-up of the next grid.  A kernel of the chain starts with CWA_PDL_ENTER():
 // `launch_dependents` lets the NEXT kernel's CTAs be scheduled as soon as every CTA of this one has started (they fill the SMs the last
 // wave leaves idle), `wait` holds them until the PREVIOUS grid has completed and its writes are visible -- so nothing before the wait may
 // touch global memory another kernel writes.  Without the launch attribute (cwa_launch with pdl off, or <<<>>>) both are no-ops.
-__device__ __forceinline__ void cwa_pdl_enter()
+// The compiler may hoist read-only loads (__ldg, const __restrict__: "invariant for the kernel's lifetime") above an inline-asm barrier; a load
+// that runs before the wait reads what the previous frame left there (seen: the queue length of sph3_force_heavy_kernel fetched before the force
+// pass had filled the queue).  ptxas does the same with ld.global.nc, whatever the PTX order.  So the wait is followed by a branch on a run-time value
+// (CWA_PDL_ENTER: `if (%smid == ~0) return;`, never taken) and the whole kernel body is control-dependent on it -- global loads are not speculated above a branch.  tools/check_pdl_sass.py (run by tests/test_pdl_sass.py)
+// verifies in the SASS that no kernel touches memory before its ACQBULK.
+__device__ __forceinline__ bool cwa_pdl_enter()
 {
+    unsigned smid;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.wait;\n\tmov.u32 %0, %%smid;" : "=r"(smid) :: "memory");
+    return smid == 0xffffffffu;                       // never (%smid < %nsmid), but neither the optimizer nor ptxas can fold it
 }
+#define CWA_PDL_ENTER() do { if (cwa_pdl_enter()) return; } while (0)
 
 // the kernels of the chain, as bits of the tuning value `pdl` (which launches carry the attribute)
 enum { PDL_SCAN = 1, PDL_INSERT = 2, PDL_REORDER = 4, PDL_DENSITY = 8, PDL_DENSITY_HEAVY = 16, PDL_FORCE = 32, PDL_FORCE_HEAVY = 64, PDL_INTEGRATE = 128,
@@ -445,7 +453,7 @@ static inline bool cwa_pdl_enabled(cwa_ctx* c, int bit)
     return bit != 0 && (c->tune.pdl & bit) != 0 && !c->profiling;      // (a profile brackets every launch with events: nothing to overlap)
 }
 
-// <<<grid, block, smem, ctx->stream>>> with the programmatic-serialization attribute; the kernel must begin with cwa_pdl_enter()
+// <<<grid, block, smem, ctx->stream>>> with the programmatic-serialization attribute; the kernel must begin with CWA_PDL_ENTER()
 template <typename... KArgs, typename... Args>
 static inline cudaError_t cwa_launch(cwa_ctx* ctx, int pdl_bit, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args)
 {

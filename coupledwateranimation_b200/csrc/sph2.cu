@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256)
 sph2_reorder_kernel(const float4* __restrict__ aos, const int* __restrict__ index_list, const int* __restrict__ offset,
                     int num_cells, float4* __restrict__ posS, float4* __restrict__ velS, float4* __restrict__ accS)
 {
-    cwa_pdl_enter();
+    CWA_PDL_ENTER();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int m = __ldg(offset + num_cells);              // number of inserted particles
     const int s = t / 3, q = t - 3 * s;
@@ -155,7 +155,7 @@ sph2_order_reorder_kernel(const float4* __restrict__ aos, const int* __restrict_
                           const int* __restrict__ offset, int num_cells, int* __restrict__ index_list,
                           float4* __restrict__ posS, float4* __restrict__ velS, float4* __restrict__ accS)
 {
-    cwa_pdl_enter();
+    CWA_PDL_ENTER();
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= __ldg(offset + num_cells)) return;           // inserted particles
     const int id = __ldg(arrival + s);
@@ -194,7 +194,7 @@ sph2_density_kernel(const float4* __restrict__ in, float4* __restrict__ out, int
                     const int* __restrict__ offset, const int* __restrict__ index_list, const int* __restrict__ cell_of,
                     const float4* __restrict__ posS, Sph2Params prm, int main_blocks)
 {
-    cwa_pdl_enter();
+    CWA_PDL_ENTER();
     using namespace k2d;
     // one launch for both target lists: blocks [0, main_blocks) take the inserted particles in cell order, the rest the rejected ones
     const int tail = (int)blockIdx.x >= main_blocks;
@@ -258,7 +258,7 @@ sph2_forces_kernel(const float4* __restrict__ in, float4* __restrict__ out, int 
                    const float4* __restrict__ posS, const float4* __restrict__ velS, const float4* __restrict__ accS,
                    Sph2Params prm, int main_blocks)
 {
-    cwa_pdl_enter();
+    CWA_PDL_ENTER();
     using namespace k2d;
     const int tail = (int)blockIdx.x >= main_blocks;
     const int gt = (blockIdx.x - (tail ? main_blocks : 0)) * blockDim.x + threadIdx.x;

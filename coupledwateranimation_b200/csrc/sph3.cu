@@ -274,7 +274,7 @@ sph3_order_reorder_kernel(const float4* __restrict__ aos, const int* __restrict_
                           float4* __restrict__ posS, float4* __restrict__ velS, float4* __restrict__ forceS,
                           float4* __restrict__ miscS, int* __restrict__ heavy_cnt, float* __restrict__ xyzS, size_t xyz_stride)
 {
-    cwa_pdl_enter();
+    CWA_PDL_ENTER();
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s == 0) { heavy_cnt[0] = 0; heavy_cnt[1] = 0; }   // clump queues of the density / force passes that follow this snapshot
     if (s >= __ldg(count)) return;                 // inserted particles (NaN positions are left out)
@@ -539,7 +539,6 @@ sph3_force_grid_kernel(const float4* __restrict__ pack,
 // left alone with such a target would outlast the rest of the kernel.  Targets with more than EXTREME_CANDIDATES
 // candidates (density pass) or more than K neighbours (force pass) are therefore pushed to a device-side queue and
 // finished by the "heavy" kernels, one WARP per target, spread over the whole GPU.
-constexpr int SUB_WARP_MAX = 640;      // force of a queued target: up to here 8 lanes (4 targets per warp), beyond the whole warp
 constexpr int RT_ROWS = 9;
 constexpr int TILE_P = 128;               // targets per tile (= CTA size of the list kernels)
 constexpr int EXTREME_CANDIDATES = 192;   // a target with more candidates than this (or more 31-slot row segments than table entries) is a clump target; tuning "extreme_candidates", up to 9 x 31 = 279
@@ -779,7 +778,7 @@ sph3_density_flat_kernel(const float4* __restrict__ posS, const float* __restric
                          int n_max, GridView g, const int* __restrict__ offset, const Sph3Const* __restrict__ cc, TexView tex,
                          const int extreme_candidates, const int inplace_max)
 {
-    cwa_pdl_enter();
+    CWA_PDL_ENTER();
     __shared__ int2 tab[(RT_ROWS + 1) * TILE_P];       // non-empty rows of every target, compacted: (first slot, end slot), later (first slot, mask)
     const int tid = threadIdx.x;
     const int slot = blockIdx.x * TILE_P + tid;
@@ -939,7 +938,7 @@ sph3_density_heavy_kernel(const float4* __restrict__ posS, const float4* __restr
                           int* __restrict__ nbr_count, const int* __restrict__ heavy_queue, const int* __restrict__ heavy_count, int cap,
                           GridView g, const int* __restrict__ offset, const Sph3Const* __restrict__ cc, TexView tex)
 {
-    cwa_pdl_enter();
+    CWA_PDL_ENTER();
     const int lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int total = min(__ldg(heavy_count), cap);
@@ -1093,7 +1092,7 @@ sph3_force_rows_kernel(const float4* __restrict__ pack, const int2* __restrict__
                        float4* __restrict__ pairP, float2* __restrict__ pairV, int n_max,
                        GridView g, const int* __restrict__ offset, const Sph3Const* __restrict__ cc, FinishArgs fa)
 {
-    cwa_pdl_enter();
+    CWA_PDL_ENTER();
     __shared__ int2 tab[(RT_ROWS + 1) * TILE_P];
     const int tid = threadIdx.x;
     const int slot = blockIdx.x * TILE_P + tid;
@@ -1171,9 +1170,9 @@ template <bool FUSED, bool LOCAL>
 __global__ void __launch_bounds__(128)
 sph3_force_heavy_kernel(const float4* __restrict__ pack, const int* __restrict__ heavy_queue, const int* __restrict__ heavy_count, int cap,
                         float4* __restrict__ pairP, float2* __restrict__ pairV, GridView g,
-                        const int* __restrict__ offset, const Sph3Const* __restrict__ cc, FinishArgs fa, const bool sub_warp_heavy)
+                        const int* __restrict__ offset, const Sph3Const* __restrict__ cc, FinishArgs fa, const int sub_warp_heavy, const int sub_warp_max)
 {
-    cwa_pdl_enter();
+    CWA_PDL_ENTER();
     const int lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int total = min(__ldg(heavy_count), cap);
@@ -1256,13 +1255,14 @@ sph3_force_heavy_kernel(const float4* __restrict__ pack, const int* __restrict__
     // Cells of ~h (every query is the 3 x 3 x 3 block: nine rows) and the separate integrate kernel: FOUR targets per warp, eight lanes each.
     // A clump target has a few hundred candidates -- three trips of a whole warp -- so with one target per warp half the instructions were
     // per-target overhead (set-up 17 %, candidate mapping 20 %, shuffle reduction 9 %: ncu at frame 3000, profiles/r2); four targets share
-    // those instructions.  The divergent pair term costs the same (a trip still tests 128 candidates).  Targets of more than SUB_WARP_MAX
+    // those instructions.  The divergent pair term costs the same (a trip still tests 128 candidates).  Targets of more than `sub_warp_max` (= `inplace_max`: the ones the density pass queued as well)
     // candidates (the few cells of hundreds of particles early in a run) keep the whole warp: eight lanes on thousands of candidates are a tail.
     {
         const float hm = c.h * (1.0f + 2.5e-3f), hx = c.h * 1.25f;
         const bool fast = hm <= g.cell[0] && hm <= g.cell[1] && hm <= g.cell[2] && (g.cell[0] <= hx || g.n[0] == 1) && (g.cell[1] <= hx || g.n[1] == 1) &&
                           (g.cell[2] <= hx || g.n[2] == 1);
-        if (!FUSED && fast && sub_warp_heavy && total > nwarps) {    // (fewer targets than warps: a warp each finishes sooner)
+        // (fewer targets than warps: a warp each finishes sooner; sub_warp_heavy == 2, the tests: whatever the queue length)
+        if (!FUSED && fast && (sub_warp_heavy == 2 || (sub_warp_heavy == 1 && total > nwarps))) {
             constexpr int G = 8;
             const int gl = lane & (G - 1), grp = lane >> 3;
             const unsigned gmask = 0xffu << (grp * G);
@@ -1301,7 +1301,7 @@ sph3_force_heavy_kernel(const float4* __restrict__ pack, const int* __restrict__
                 }
                 const int total8 = __shfl_sync(gmask, incl, G - 1, G);          // candidates of rows 0..7
                 const int ncand_all = total8 + len8;
-                const bool big = valid && ncand_all > SUB_WARP_MAX;             // a handful of these per frame: the whole warp, below
+                const bool big = valid && ncand_all > sub_warp_max;             // a handful of these per frame: the whole warp, below
                 const int ncand = big ? 0 : ncand_all;
                 __syncwarp(gmask);                                              // the group's reads of the previous target's table are done
                 gP[gl] = incl - len_own; gG[gl] = b_own;
@@ -1375,7 +1375,7 @@ sph3_finalize_integrate_sorted_kernel(const float4* __restrict__ pack,
                                       GridView g, int n, int* __restrict__ counter, int* __restrict__ cell_next, int* __restrict__ rank_next,
                                       SlabPackArgs sp)
 {
-    cwa_pdl_enter();
+    CWA_PDL_ENTER();
     constexpr bool AHEAD = (MODE == 1 || MODE == 3);  // 3: slab pack AND count-ahead (the particles that stay owned; arrivals are counted by the unpack kernel)
     constexpr bool SLAB = (MODE == 2 || MODE == 3);
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1996,7 +1996,7 @@ static int extreme_candidates(cwa_ctx* c) { if (c->tune.extreme < 0) c->tune.ext
 static int inplace_max(cwa_ctx* c) { if (c->tune.inplace_max < 0) c->tune.inplace_max = env_int("CWA_INPLACE_MAX", INPLACE_MAX, 0, 1 << 20); return c->tune.inplace_max; }
 static int allpairs_balanced(cwa_ctx* c) { if (c->tune.allpairs_bal < 0) c->tune.allpairs_bal = env_int("CWA_ALLPAIRS_BALANCED", 2, 0, 2); return c->tune.allpairs_bal; }
 static bool allpairs_cull(cwa_ctx* c) { if (c->tune.ap_cull < 0) c->tune.ap_cull = env_int("CWA_ALLPAIRS_CULL", 1, 0, 1); return c->tune.ap_cull != 0; }
-static bool heavy_sub_warp(cwa_ctx* c) { if (c->tune.heavy8 < 0) c->tune.heavy8 = env_int("CWA_HEAVY8", 1, 0, 1); return c->tune.heavy8 != 0; }
+static int heavy_sub_warp(cwa_ctx* c) { if (c->tune.heavy8 < 0) c->tune.heavy8 = env_int("CWA_HEAVY8", 1, 0, 2); return c->tune.heavy8; }
 static bool fused_order(cwa_ctx* c) { if (c->tune.fused_order < 0) c->tune.fused_order = env_int("CWA_FUSED_ORDER", 1, 0, 1); return c->tune.fused_order != 0; }
 
 extern "C" int cwa_set_tuning(cwa_ctx* ctx, const char* key, int value)
@@ -2010,7 +2010,7 @@ extern "C" int cwa_set_tuning(cwa_ctx* ctx, const char* key, int value)
     else if (k == "fused_order") { ctx->tune.fused_order = value ? 1 : 0; }
     else if (k == "fused_integrate") { ctx->tune.fused_integrate = value ? 1 : 0; }
     else if (k == "nbr_k") { CWA_CHECK(value >= 8 && value <= NBR_K_MAX && value % 4 == 0, "nbr_k %d: multiple of 4 in [8, %d]", value, NBR_K_MAX); ctx->tune.nbr_k = value; }
-    else if (k == "heavy_sub_warp") { ctx->tune.heavy8 = value ? 1 : 0; }
+    else if (k == "heavy_sub_warp") { ctx->tune.heavy8 = value < 0 ? 0 : (value > 2 ? 2 : value); }
     else if (k == "allpairs_cull") { ctx->tune.ap_cull = value ? 1 : 0; }
     else if (k == "pdl") { ctx->tune.pdl = value & 511; }
     else if (k == "slab_ahead") { ctx->tune.slab_ahead = value ? 1 : 0; }
@@ -2112,7 +2112,7 @@ static int launch_force_list(cwa_ctx* ctx, SphObj* s, GridObj* g, bool fused, fl
 #define CWA_FORCE_LIST(F, L) sph3_force_list_kernel<F, L><<<blocks, TILE_P, 0, ctx->stream>>>( \
         s->pack, s->nbr_list, s->nbr_count, fq, s->heavy_cnt + 1, s->pairP, s->pairV, s->n, g->view, g->offset, cc, fa, s->nbr_k_used)
 #define CWA_FORCE_HEAVY(F, L) cwa_launch(ctx, PDL_FORCE_HEAVY, sph3_force_heavy_kernel<F, L>, dim3(heavy_grid(ctx)), dim3(128), 0, \
-        s->pack, fq, s->heavy_cnt + 1, s->n, s->pairP, s->pairV, g->view, g->offset, cc, fa, heavy_sub_warp(ctx))
+        s->pack, fq, s->heavy_cnt + 1, s->n, s->pairP, s->pairV, g->view, g->offset, cc, fa, heavy_sub_warp(ctx), inplace_max(ctx))
 #define CWA_FORCE_ROWS(F, L) cwa_launch(ctx, PDL_FORCE, sph3_force_rows_kernel<F, L>, dim3(blocks), dim3(TILE_P), 0, \
         s->pack, reinterpret_cast<const int2*>(s->nbr_list), s->nbr_count, fq, s->heavy_cnt + 1, s->pairP, s->pairV, s->n, g->view, g->offset, cc, fa)
     if (s->nbr_rows_fmt) {

@@ -89,6 +89,30 @@ def test_variant_dense_cluster(cwa, tuned, oracle, cfg, grid_key):
     _check(oracle, prm, p, tex, sph)
 
 
+@pytest.mark.parametrize("grid_key", ["h+", "columns"])
+def test_queued_clump_targets_eight_lanes_each(cwa, tuned, oracle, grid_key):
+    """The force pass of queued clump targets has a second shape -- four targets per warp, eight lanes each -- that the library takes when
+    the queue is longer than the launch (never in a scene the oracle finishes in seconds); heavy_sub_warp = 2 forces it.  Same clump as
+    above against the oracle, with targets beyond `inplace_max` candidates (whole-warp fallback inside that path) and a thin queue."""
+    try:
+        tuned.set_tuning(nb_config=8, heavy_sub_warp=2, extreme_candidates=40, inplace_max=250)
+        prm, p, tex, sph = _scene(cwa, tuned, oracle, grid_key, cluster=True)
+        nb = oracle.sph3_neighbour_count(p, 0.01)
+        assert nb.max() >= 300
+        _check(oracle, prm, p, tex, sph)
+        sph.upload(p)
+        sph.step(3)                                            # and through full frames: the one-warp-per-target shape is the reference
+        a = sph.download()
+        tuned.set_tuning(heavy_sub_warp=0)
+        sph.upload(p)
+        sph.step(3)
+        b = sph.download()
+        assert_close(a["pos"][:, :3], b["pos"][:, :3], scale=1e-3, rtol=1e-3, what="pos")
+        assert_close(a["vel"][:, :3], b["vel"][:, :3], rtol=1e-3, what="vel")
+    finally:
+        tuned.set_tuning(heavy_sub_warp=1, extreme_candidates=192, inplace_max=640)
+
+
 @pytest.mark.parametrize("cfg", [7, 8])
 def test_rows_variant_full_frames_equal_lanes_variant(cwa, tuned, oracle, cfg):
     """3 fused frames: rows kernels vs the lanes kernels (same physics, summation order differs)."""
