@@ -61,7 +61,7 @@ __device__ __forceinline__ float k2_W_cubic_grad(float r)             // :248-26
 __device__ __forceinline__ float4 k2_boundary_sdf(const Sph2Params& prm, float px, float py)
 {
     using namespace k2d;
-    float4 res;
+    float4 res = make_float4(0.f, 0.f, 0.f, 0.f);                     // (set by both branches below before the first opU)
     auto opU = [&](float nx, float ny, float d, float id) {
         if (!(res.z < d)) res = make_float4(nx, ny, d, id);           // (d1.z<d2.z) ? d1 : d2
     };

@@ -232,8 +232,6 @@ static int s1d_run(cwa_ctx* ctx, Stencil1dObj* s, int mode0, int nmodes, int ndi
     const Stencil1dParams p = s1d_params(s);
     const size_t smem = (size_t)N * w * sizeof(float4);
     if (smem <= 200 * 1024) {
-        float4* r[3] = {nullptr, nullptr, nullptr};
-        for (int k = 0; k < N; k++) r[k] = s->image[k];
         // the kernel wants the images by role; hand it the storage images permuted so that slot k holds unit k's image
         float4* by_unit[3] = {nullptr, nullptr, nullptr};
         for (int u = 0; u < N; u++) by_unit[u] = s->image[s1d_image_with_unit(s, u)];
